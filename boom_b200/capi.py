@@ -1,0 +1,237 @@
+"""ctypes binding of include/boomgpu.h.  Thin by design: every method is one C call."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_double_p = C.POINTER(C.c_double)
+c_i64_p = C.POINTER(C.c_int64)
+c_i32_p = C.POINTER(C.c_int32)
+
+NUM_KERNEL_CLASSES = 5
+KERNEL_CLASSES = ("fused_small", "impute_rows", "syrk_dmma", "reduce", "other")
+
+# every symbol include/boomgpu.h declares (tests/test_capi_symbols.py checks the library exports them all)
+SYMBOLS = (
+    "boomgpu_create", "boomgpu_destroy", "boomgpu_last_error", "boomgpu_version", "boomgpu_set_stream",
+    "boomgpu_set_row_offset", "boomgpu_set_option", "boomgpu_upload_binomial", "boomgpu_upload_poisson",
+    "boomgpu_adopt_binomial", "boomgpu_adopt_poisson", "boomgpu_set_logit_mixture", "boomgpu_set_poisson_table",
+    "boomgpu_logit_step", "boomgpu_poisson_step", "boomgpu_suf_len", "boomgpu_logit_step_device",
+    "boomgpu_poisson_step_device", "boomgpu_synchronize", "boomgpu_accumulate", "boomgpu_logit_draw",
+    "boomgpu_poisson_draw", "boomgpu_binomial_loglike", "boomgpu_poisson_loglike", "boomgpu_kernel_launches",
+    "boomgpu_get_timings",
+)
+
+
+class BoomGpuError(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(_HERE, "libboomgpu.so")
+
+
+def load_library():
+    """Loads libboomgpu.so; fails loudly when it has not been built (no fallback exists)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise BoomGpuError(
+            "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or make -C boom_b200/csrc). boom_b200 has no CPU fallback." % path)
+    lib = C.CDLL(path)
+    lib.boomgpu_last_error.restype = C.c_char_p
+    lib.boomgpu_last_error.argtypes = [C.c_void_p]
+    lib.boomgpu_version.restype = C.c_char_p
+    lib.boomgpu_suf_len.restype = C.c_int64
+    lib.boomgpu_suf_len.argtypes = [C.c_int]
+    lib.boomgpu_kernel_launches.restype = C.c_int64
+    lib.boomgpu_kernel_launches.argtypes = [C.c_void_p]
+    lib.boomgpu_destroy.restype = None
+    lib.boomgpu_destroy.argtypes = [C.c_void_p]
+    _LIB = lib
+    return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+class Context:
+    """One boomgpu context = one CUDA device."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.boomgpu_create(C.byref(self._h), C.c_int(device))
+        if rc:
+            raise BoomGpuError(self._lib.boomgpu_last_error(None).decode())
+        self.n = 0
+        self.p = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.boomgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc:
+            raise BoomGpuError("boomgpu error %d: %s" % (rc, self._lib.boomgpu_last_error(self._h).decode()))
+
+    # ---- configuration
+    def set_option(self, name, value):
+        self._check(self._lib.boomgpu_set_option(self._h, name.encode(), C.c_int64(int(value))))
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.boomgpu_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def set_row_offset(self, first_global_row):
+        self._check(self._lib.boomgpu_set_row_offset(self._h, C.c_uint64(int(first_global_row))))
+
+    def set_logit_mixture(self, mu, sigma, weights):
+        mu, sigma, weights = _f64(mu), _f64(sigma), _f64(weights)
+        self._check(self._lib.boomgpu_set_logit_mixture(self._h, C.c_int(len(sigma)), _dp(mu), _dp(sigma), _dp(weights)))
+
+    def set_poisson_table(self, nu, offset, weights, mu, sigma, gaussian_cutoff):
+        nu = np.ascontiguousarray(nu, dtype=np.int64)
+        offset = np.ascontiguousarray(offset, dtype=np.int32)
+        weights, mu, sigma = _f64(weights), _f64(mu), _f64(sigma)
+        self._check(self._lib.boomgpu_set_poisson_table(
+            self._h, C.c_int(len(nu)), nu.ctypes.data_as(c_i64_p), offset.ctypes.data_as(c_i32_p), _dp(weights), _dp(mu),
+            _dp(sigma), C.c_int64(int(gaussian_cutoff))))
+
+    # ---- data
+    def upload_binomial(self, X, y, ntrials):
+        X, y, ntrials = _f64(X), _f64(y), _f64(ntrials)
+        n, p = X.shape
+        self._check(self._lib.boomgpu_upload_binomial(self._h, C.c_int64(n), C.c_int(p), _dp(X), C.c_int64(p), _dp(y),
+                                                      _dp(ntrials)))
+        self.n, self.p = n, p
+
+    def upload_poisson(self, X, y, exposure):
+        X, exposure = _f64(X), _f64(exposure)
+        y = np.ascontiguousarray(y, dtype=np.int64)
+        n, p = X.shape
+        self._check(self._lib.boomgpu_upload_poisson(self._h, C.c_int64(n), C.c_int(p), _dp(X), C.c_int64(p),
+                                                     y.ctypes.data_as(c_i64_p), _dp(exposure)))
+        self.n, self.p = n, p
+
+    def adopt_binomial(self, n, p, dX, ldx, dy, dntrials, keepalive=()):
+        """dX/dy/dntrials: device pointers (ints), e.g. torch tensor .data_ptr()."""
+        self._check(self._lib.boomgpu_adopt_binomial(self._h, C.c_int64(n), C.c_int(p), C.c_void_p(dX), C.c_int64(ldx),
+                                                     C.c_void_p(dy), C.c_void_p(dntrials)))
+        self.n, self.p = n, p
+        self._keep = list(keepalive)
+
+    def adopt_poisson(self, n, p, dX, ldx, dy, dexposure, keepalive=()):
+        self._check(self._lib.boomgpu_adopt_poisson(self._h, C.c_int64(n), C.c_int(p), C.c_void_p(dX), C.c_int64(ldx),
+                                                    C.c_void_p(dy), C.c_void_p(dexposure)))
+        self.n, self.p = n, p
+        self._keep = list(keepalive)
+
+    # ---- hot path
+    def logit_step(self, beta, clt_threshold, seed, iteration):
+        p = self.p
+        beta = _f64(beta)
+        xtx = np.empty((p, p))
+        xty = np.empty(p)
+        ss = C.c_int64()
+        self._check(self._lib.boomgpu_logit_step(self._h, _dp(beta), C.c_int(clt_threshold), C.c_uint64(seed),
+                                                 C.c_uint64(iteration), _dp(xtx), _dp(xty), C.byref(ss)))
+        return xtx, xty, ss.value
+
+    def poisson_step(self, beta, seed, iteration):
+        p = self.p
+        beta = _f64(beta)
+        xtx = np.empty((p, p))
+        xty = np.empty(p)
+        sc = np.empty(4)
+        self._check(self._lib.boomgpu_poisson_step(self._h, _dp(beta), C.c_uint64(seed), C.c_uint64(iteration), _dp(xtx),
+                                                   _dp(xty), _dp(sc)))
+        return xtx, xty, sc
+
+    def suf_len(self):
+        return int(self._lib.boomgpu_suf_len(C.c_int(self.p)))
+
+    def logit_step_device(self, beta, clt_threshold, seed, iteration, suf_dev_ptr):
+        beta = _f64(beta)
+        self._check(self._lib.boomgpu_logit_step_device(self._h, _dp(beta), C.c_int(clt_threshold), C.c_uint64(seed),
+                                                        C.c_uint64(iteration), C.c_void_p(suf_dev_ptr)))
+
+    def poisson_step_device(self, beta, seed, iteration, suf_dev_ptr):
+        beta = _f64(beta)
+        self._check(self._lib.boomgpu_poisson_step_device(self._h, _dp(beta), C.c_uint64(seed), C.c_uint64(iteration),
+                                                          C.c_void_p(suf_dev_ptr)))
+
+    def synchronize(self):
+        self._check(self._lib.boomgpu_synchronize(self._h))
+
+    # ---- parity hooks
+    def accumulate(self, weight, weighted_value):
+        p = self.p
+        w, s = _f64(weight), _f64(weighted_value)
+        assert len(w) == self.n and len(s) == self.n
+        xtx = np.empty((p, p))
+        xty = np.empty(p)
+        self._check(self._lib.boomgpu_accumulate(self._h, _dp(w), _dp(s), _dp(xtx), _dp(xty)))
+        return xtx, xty
+
+    def logit_draw(self, beta, clt_threshold, seed, iteration):
+        beta = _f64(beta)
+        s = np.empty(self.n)
+        w = np.empty(self.n)
+        self._check(self._lib.boomgpu_logit_draw(self._h, _dp(beta), C.c_int(clt_threshold), C.c_uint64(seed),
+                                                 C.c_uint64(iteration), _dp(s), _dp(w)))
+        return s, w
+
+    def poisson_draw(self, beta, seed, iteration):
+        beta = _f64(beta)
+        out = np.empty((self.n, 6))
+        k2 = np.empty((self.n, 2), dtype=np.int32)
+        self._check(self._lib.boomgpu_poisson_draw(self._h, _dp(beta), C.c_uint64(seed), C.c_uint64(iteration), _dp(out),
+                                                   k2.ctypes.data_as(c_i32_p)))
+        return out, k2
+
+    def binomial_loglike(self, beta):
+        beta = _f64(beta)
+        out = C.c_double()
+        self._check(self._lib.boomgpu_binomial_loglike(self._h, _dp(beta), C.byref(out)))
+        return out.value
+
+    def poisson_loglike(self, beta):
+        beta = _f64(beta)
+        out = C.c_double()
+        self._check(self._lib.boomgpu_poisson_loglike(self._h, _dp(beta), C.byref(out)))
+        return out.value
+
+    # ---- instrumentation
+    def kernel_launches(self):
+        return int(self._lib.boomgpu_kernel_launches(self._h))
+
+    def timings(self, reset=False):
+        ms = (C.c_double * NUM_KERNEL_CLASSES)()
+        cnt = (C.c_int64 * NUM_KERNEL_CLASSES)()
+        self._check(self._lib.boomgpu_get_timings(self._h, ms, cnt, C.c_int(int(reset))))
+        return {KERNEL_CLASSES[i]: (ms[i], int(cnt[i])) for i in range(NUM_KERNEL_CLASSES)}

@@ -1,0 +1,827 @@
+// boomgpu_api.cu -- the C ABI of include/boomgpu.h over the kernels in kernels.cuh.
+// One context = one CUDA device, one stream; no CPU fallback anywhere.
+#include "../../include/boomgpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace boomgpu;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct TimedLaunch { cudaEvent_t a, b; int cls; };
+
+}  // namespace
+
+struct boomgpu_ctx {
+  int device = 0;
+  int sms = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string error;
+
+  // data
+  int model = -1;  // kLogit / kPoisson
+  int64_t n = 0;
+  int p = 0;
+  int64_t ldx = 0;
+  const double *X = nullptr;
+  const double *y = nullptr, *ntrials = nullptr, *exposure = nullptr;
+  const int64_t *yi = nullptr;
+  std::vector<void *> owned;  // device allocations made for uploaded data
+  uint64_t row_offset = 0;
+
+  // mixtures
+  LogitMixture mix{};
+  bool have_mix = false;
+  PoissonTable tab{};
+  bool have_tab = false;
+  std::vector<void *> tab_owned;
+
+  // workspaces
+  double *beta_dev = nullptr; int beta_cap = 0;
+  double *beta_pin = nullptr;
+  double *suf_dev = nullptr; int64_t suf_cap = 0;
+  double *suf_pin = nullptr; int64_t suf_pin_cap = 0;
+  double *partials = nullptr; int64_t partials_cap = 0;
+  double *scal_partials = nullptr; int64_t scal_cap = 0;
+  double *w_buf = nullptr, *s_buf = nullptr; int64_t ws_cap = 0;
+  int *err_dev = nullptr;
+  int *err_pin = nullptr;
+
+  // options / instrumentation
+  int path = 0;
+  bool timing = false;
+  int64_t launches = 0;
+  std::vector<TimedLaunch> timed;
+  std::vector<cudaEvent_t> event_pool;
+  double ms_acc[BOOMGPU_NUM_KERNEL_CLASSES] = {0, 0, 0, 0, 0};
+  int64_t n_acc[BOOMGPU_NUM_KERNEL_CLASSES] = {0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(boomgpu_ctx *c, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->error = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess)                                                                                \
+      return fail(ctx, BOOMGPU_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <class T>
+int ensure(boomgpu_ctx *ctx, T **ptr, int64_t *cap, int64_t need) {
+  if (*cap >= need && *ptr) return 0;
+  if (*ptr) { CU(cudaFree(*ptr)); *ptr = nullptr; *cap = 0; }
+  CU(cudaMalloc((void **)ptr, sizeof(T) * (size_t)need));
+  *cap = need;
+  return 0;
+}
+
+void free_data(boomgpu_ctx *ctx) {
+  for (void *q : ctx->owned) cudaFree(q);
+  ctx->owned.clear();
+  ctx->X = ctx->y = ctx->ntrials = ctx->exposure = nullptr;
+  ctx->yi = nullptr;
+  ctx->n = 0; ctx->p = 0; ctx->model = -1;
+}
+
+// ---- launch bookkeeping -------------------------------------------------------------------
+struct LaunchScope {
+  boomgpu_ctx *ctx; int cls; cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(boomgpu_ctx *c, int cls_) : ctx(c), cls(cls_) {
+    ++ctx->launches;
+    if (ctx->timing) {
+      auto get = [&]() {
+        cudaEvent_t e;
+        if (!ctx->event_pool.empty()) { e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+      };
+      a = get(); b = get();
+      cudaEventRecord(a, ctx->stream);
+    }
+  }
+  ~LaunchScope() {
+    if (ctx->timing) { cudaEventRecord(b, ctx->stream); ctx->timed.push_back({a, b, cls}); }
+  }
+};
+
+void drain_timings(boomgpu_ctx *ctx) {
+  for (auto &t : ctx->timed) {
+    float ms = 0;
+    cudaEventSynchronize(t.b);
+    if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { ctx->ms_acc[t.cls] += ms; ctx->n_acc[t.cls] += 1; }
+    ctx->event_pool.push_back(t.a);
+    ctx->event_pool.push_back(t.b);
+  }
+  ctx->timed.clear();
+}
+
+SyrkUnitTable make_unit_table() {
+  SyrkUnitTable t;
+  memset(&t, 0, sizeof(t));
+  // off-diagonal region: warp w owns units (w/2, 2(w%2)) and (w/2, 2(w%2)+1) (shared A fragments)
+  for (int w = 0; w < kSyrkConsumerWarps; ++w) {
+    t.u[0][w][0] = {(int8_t)(w / 2), (int8_t)(2 * (w % 2)), 1};
+    t.u[0][w][1] = {(int8_t)(w / 2), (int8_t)(2 * (w % 2) + 1), 1};
+  }
+  // diagonal region: 6 full units (16 DMMA / k-step), 4 diagonal units (10), 4 xty duties (+4),
+  // balanced over the four SM sub-partitions (warp w issues on sub-partition w % 4): 40/36/36/40.
+  const int8_t V = 1, D = 2, Y = 4, F = 8;  // F: fallback xty duty
+  t.u[1][0][0] = {0, 1, (int8_t)(V | Y)};
+  t.u[1][4][0] = {0, 0, (int8_t)(V | D | F)}; t.u[1][4][1] = {1, 1, (int8_t)(V | D | F)};
+  t.u[1][1][0] = {1, 2, (int8_t)(V | Y)};
+  t.u[1][5][0] = {0, 2, V};
+  t.u[1][2][0] = {2, 3, (int8_t)(V | Y)};
+  t.u[1][6][0] = {0, 3, V};
+  t.u[1][3][0] = {1, 3, V};
+  t.u[1][7][0] = {3, 3, (int8_t)(V | D | Y)}; t.u[1][7][1] = {2, 2, (int8_t)(V | D | F)};
+  return t;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int choose_path(boomgpu_ctx *ctx, int *path) {
+  if (ctx->path == 1) {
+    if (ctx->p > 64) return fail(ctx, BOOMGPU_ERR_ARG, "option path=1 (fused single pass) needs p <= 64, p = %d", ctx->p);
+    *path = 1;
+  } else if (ctx->path == 2) {
+    *path = 2;
+  } else {
+    *path = ctx->p <= 64 ? 1 : 2;
+  }
+  if (*path == 2 && ((ctx->ldx & 1) || !aligned16(ctx->X)))
+    return fail(ctx, BOOMGPU_ERR_ARG, "the two-pass path needs an even leading dimension and a 16-byte aligned X "
+                "(ldx = %lld); boomgpu_upload_* pads for you", (long long)ctx->ldx);
+  return 0;
+}
+
+template <int MODEL>
+struct SmallLauncher {
+  template <int NB>
+  static cudaError_t go(boomgpu_ctx *ctx, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts) {
+    auto kern = fused_small_kernel<NB, MODEL>;
+    const size_t smem = small_smem_bytes(NB);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSmallThreads, smem);
+    if (e != cudaSuccess) return e;
+    occ = std::max(occ, 1);
+    const int R = small_rows(NB);
+    const int64_t nchunks = (d.n + R - 1) / R;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, (int64_t)ctx->sms * occ));
+    const int64_t need = (int64_t)grid * small_partial_len(NB);
+    if (ctx->partials_cap < need) {
+      if (ctx->partials) cudaFree(ctx->partials);
+      ctx->partials = nullptr; ctx->partials_cap = 0;
+      e = cudaMalloc((void **)&ctx->partials, sizeof(double) * (size_t)need);
+      if (e != cudaSuccess) return e;
+      ctx->partials_cap = need;
+    }
+    const uint32_t magic = (uint32_t)(0x100000000ull / (uint64_t)d.p) + 1u;
+    const int vec2 = (d.p % 2 == 0) && (d.ldx % 2 == 0) && aligned16(d.X);
+    {
+      LaunchScope ls(ctx, 0);
+      kern<<<grid, kSmallThreads, smem, ctx->stream>>>(d, prm, out, ctx->beta_dev, ctx->partials, ctx->err_dev, magic, vec2);
+    }
+    *nparts = grid;
+    return cudaGetLastError();
+  }
+  static cudaError_t dispatch(boomgpu_ctx *ctx, int nb, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts) {
+    switch (nb) {
+      case 1: return go<1>(ctx, d, prm, out, nparts);
+      case 2: return go<2>(ctx, d, prm, out, nparts);
+      case 3: return go<3>(ctx, d, prm, out, nparts);
+      case 4: return go<4>(ctx, d, prm, out, nparts);
+      case 5: return go<5>(ctx, d, prm, out, nparts);
+      case 6: return go<6>(ctx, d, prm, out, nparts);
+      case 7: return go<7>(ctx, d, prm, out, nparts);
+      case 8: return go<8>(ctx, d, prm, out, nparts);
+    }
+    return cudaErrorInvalidValue;
+  }
+};
+
+template <int MODEL>
+cudaError_t launch_impute_rows(boomgpu_ctx *ctx, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts) {
+  const bool vec2 = (d.ldx % 2 == 0) && aligned16(d.X);
+  const size_t smem = sizeof(double) * (size_t)(d.p + 2);
+  const int64_t ngroups = (d.n + 31) / 32;
+  int occ = 1;
+  cudaError_t e;
+  if (vec2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, impute_rows_kernel<MODEL, true>, kImputeThreads, smem);
+  else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, impute_rows_kernel<MODEL, false>, kImputeThreads, smem);
+  if (e != cudaSuccess) return e;
+  occ = std::max(occ, 1);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ngroups + 7) / 8, (int64_t)ctx->sms * occ));
+  if (ctx->scal_cap < (int64_t)grid * 4) {
+    if (ctx->scal_partials) cudaFree(ctx->scal_partials);
+    ctx->scal_partials = nullptr; ctx->scal_cap = 0;
+    e = cudaMalloc((void **)&ctx->scal_partials, sizeof(double) * (size_t)grid * 4);
+    if (e != cudaSuccess) return e;
+    ctx->scal_cap = (int64_t)grid * 4;
+  }
+  {
+    LaunchScope ls(ctx, 1);
+    if (vec2)
+      impute_rows_kernel<MODEL, true><<<grid, kImputeThreads, smem, ctx->stream>>>(d, prm, out, ctx->beta_dev, ctx->w_buf,
+                                                                                  ctx->s_buf, ctx->scal_partials, ctx->err_dev);
+    else
+      impute_rows_kernel<MODEL, false><<<grid, kImputeThreads, smem, ctx->stream>>>(d, prm, out, ctx->beta_dev, ctx->w_buf,
+                                                                                   ctx->s_buf, ctx->scal_partials, ctx->err_dev);
+  }
+  *nparts = grid;
+  return cudaGetLastError();
+}
+
+int ensure_ws(boomgpu_ctx *ctx) {
+  const int64_t npad = ((ctx->n + kSyrkKB - 1) / kSyrkKB) * kSyrkKB + kSyrkKB;
+  if (ctx->ws_cap < npad) {
+    if (ctx->w_buf) { CU(cudaFree(ctx->w_buf)); ctx->w_buf = nullptr; }
+    if (ctx->s_buf) { CU(cudaFree(ctx->s_buf)); ctx->s_buf = nullptr; }
+    CU(cudaMalloc((void **)&ctx->w_buf, sizeof(double) * (size_t)npad));
+    CU(cudaMalloc((void **)&ctx->s_buf, sizeof(double) * (size_t)npad));
+    ctx->ws_cap = npad;
+  }
+  // rows beyond n must weigh nothing
+  CU(cudaMemsetAsync(ctx->w_buf + ctx->n, 0, sizeof(double) * (size_t)(npad - ctx->n), ctx->stream));
+  CU(cudaMemsetAsync(ctx->s_buf + ctx->n, 0, sizeof(double) * (size_t)(npad - ctx->n), ctx->stream));
+  return 0;
+}
+
+// pass 2 + reduction into suf (device)
+int launch_syrk(boomgpu_ctx *ctx, double *suf) {
+  SyrkParams sp;
+  sp.X = ctx->X; sp.ldx = ctx->ldx; sp.n = ctx->n; sp.p = ctx->p;
+  sp.w = ctx->w_buf; sp.s = ctx->s_buf;
+  sp.nblk = (ctx->p + 127) / 128;
+  sp.nregions = sp.nblk * (sp.nblk + 1) / 2;
+  // ~20 waves of CTAs for dynamic balance (diagonal regions are cheaper), at least 2048 rows per CTA
+  int64_t ksplit = (20 * (int64_t)ctx->sms + sp.nregions - 1) / sp.nregions;
+  ksplit = std::min<int64_t>(ksplit, std::max<int64_t>(1, ctx->n / 2048));
+  ksplit = std::max<int64_t>(ksplit, 1);
+  int64_t rows = (ctx->n + ksplit - 1) / ksplit;
+  rows = ((rows + kSyrkKB - 1) / kSyrkKB) * kSyrkKB;
+  ksplit = std::max<int64_t>(1, (ctx->n + rows - 1) / rows);
+  sp.ksplit = (int)ksplit;
+  sp.rows_per_slice = rows;
+  const int64_t need = ksplit * sp.nregions * kSyrkTileLen;
+  if (ensure(ctx, &ctx->partials, &ctx->partials_cap, need)) return BOOMGPU_ERR_CUDA;
+  sp.partials = ctx->partials;
+  static const SyrkUnitTable table = make_unit_table();
+  CU(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmemBytes));
+  {
+    LaunchScope ls(ctx, 2);
+    syrk_dmma_kernel<<<(unsigned)(ksplit * sp.nregions), kSyrkThreads, kSyrkSmemBytes, ctx->stream>>>(sp, table);
+  }
+  CU(cudaGetLastError());
+  {
+    LaunchScope ls(ctx, 3);
+    const int64_t total = (int64_t)sp.nregions * kSyrkTileLen;
+    reduce_syrk_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(sp, suf);
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// The whole device step for MODEL; leaves the packed statistics at suf (device).
+template <int MODEL>
+int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, const RowOut &out,
+             const double *w_in, const double *s_in, double *suf) {
+  int path = 0;
+  if (int rc = choose_path(ctx, &path)) return rc;
+  const int p = ctx->p;
+  if (ctx->beta_cap < p + 2) {
+    if (ctx->beta_dev) { CU(cudaFree(ctx->beta_dev)); ctx->beta_dev = nullptr; }
+    if (ctx->beta_pin) { CU(cudaFreeHost(ctx->beta_pin)); ctx->beta_pin = nullptr; }
+    CU(cudaMalloc((void **)&ctx->beta_dev, sizeof(double) * (size_t)(p + 2)));
+    CU(cudaMallocHost((void **)&ctx->beta_pin, sizeof(double) * (size_t)(p + 2)));
+    ctx->beta_cap = p + 2;
+  }
+  if (MODEL != kSupplied) {
+    memcpy(ctx->beta_pin, beta_host, sizeof(double) * p);
+  } else {
+    memset(ctx->beta_pin, 0, sizeof(double) * p);
+  }
+  CU(cudaMemcpyAsync(ctx->beta_dev, ctx->beta_pin, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+
+  RowData d;
+  d.X = ctx->X; d.ldx = ctx->ldx; d.n = ctx->n; d.p = p;
+  d.y = ctx->y; d.ntrials = ctx->ntrials; d.yi = ctx->yi; d.exposure = ctx->exposure;
+  d.w_in = w_in; d.s_in = s_in; d.row_offset = ctx->row_offset;
+
+  if (ctx->n == 0) {
+    CU(cudaMemsetAsync(suf, 0, sizeof(double) * (size_t)boomgpu_suf_len(p), ctx->stream));
+    return 0;
+  }
+  if (path == 1) {
+    int nparts = 0;
+    const int nb = (p + 7) / 8;
+    cudaError_t e = SmallLauncher<MODEL>::dispatch(ctx, nb, d, prm, out, &nparts);
+    if (e != cudaSuccess) return fail(ctx, BOOMGPU_ERR_CUDA, "fused_small_kernel launch failed: %s", cudaGetErrorString(e));
+    {
+      LaunchScope ls(ctx, 3);
+      const int total = p * p + p + 4;
+      reduce_small_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->partials, nparts, nb, p, suf);
+    }
+    CU(cudaGetLastError());
+  } else {
+    if (int rc = ensure_ws(ctx)) return rc;
+    int nparts = 0;
+    if (MODEL == kSupplied) {
+      CU(cudaMemcpyAsync(ctx->w_buf, w_in, sizeof(double) * (size_t)ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(ctx->s_buf, s_in, sizeof(double) * (size_t)ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+      CU(cudaMemsetAsync(suf + (int64_t)p * p + p, 0, sizeof(double) * 4, ctx->stream));
+    } else {
+      cudaError_t e = launch_impute_rows<MODEL>(ctx, d, prm, out, &nparts);
+      if (e != cudaSuccess) return fail(ctx, BOOMGPU_ERR_CUDA, "impute_rows_kernel launch failed: %s", cudaGetErrorString(e));
+      LaunchScope ls(ctx, 3);
+      reduce_scalars_kernel<<<1, 32, 0, ctx->stream>>>(ctx->scal_partials, nparts, suf + (int64_t)p * p + p);
+    }
+    CU(cudaGetLastError());
+    if (int rc = launch_syrk(ctx, suf)) return rc;
+  }
+  return 0;
+}
+
+int check_ready(boomgpu_ctx *ctx, int model) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (ctx->model != model || !ctx->X)
+    return fail(ctx, BOOMGPU_ERR_STATE, "no %s data uploaded to this context", model == kLogit ? "binomial" : "Poisson");
+  if (model == kLogit && !ctx->have_mix) return fail(ctx, BOOMGPU_ERR_STATE, "boomgpu_set_logit_mixture has not been called");
+  if (model == kPoisson && !ctx->have_tab) return fail(ctx, BOOMGPU_ERR_STATE, "boomgpu_set_poisson_table has not been called");
+  return 0;
+}
+
+int ensure_suf(boomgpu_ctx *ctx) {
+  const int64_t len = boomgpu_suf_len(ctx->p);
+  if (ensure(ctx, &ctx->suf_dev, &ctx->suf_cap, len)) return BOOMGPU_ERR_CUDA;
+  if (ctx->suf_pin_cap < len) {
+    if (ctx->suf_pin) { CU(cudaFreeHost(ctx->suf_pin)); ctx->suf_pin = nullptr; }
+    CU(cudaMallocHost((void **)&ctx->suf_pin, sizeof(double) * (size_t)len));
+    ctx->suf_pin_cap = len;
+  }
+  return 0;
+}
+
+int finish_and_check(boomgpu_ctx *ctx) {
+  CU(cudaMemcpyAsync(ctx->err_pin, ctx->err_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const int flag = *ctx->err_pin;
+  if (flag) {
+    CU(cudaMemsetAsync(ctx->err_dev, 0, sizeof(int), ctx->stream));
+    if (flag & 1) return fail(ctx, BOOMGPU_ERR_DATA, "a count y is missing from the Poisson mixture table "
+                              "(call NormalMixtureApproximationTable::approximate(y) for every distinct y before upload)");
+    return fail(ctx, BOOMGPU_ERR_DATA, "invalid observation on the device: successes > trials, a negative count/exposure, "
+                "or a non-finite linear predictor");
+  }
+  return 0;
+}
+
+DrawParams make_prm(boomgpu_ctx *ctx, int clt, uint64_t seed, uint64_t iteration) {
+  DrawParams prm;
+  prm.mix = ctx->mix;
+  prm.tab = ctx->tab;
+  prm.key.seed = seed;
+  prm.key.iteration = iteration;
+  prm.clt_threshold = clt;
+  return prm;
+}
+
+template <class T>
+int upload_array(boomgpu_ctx *ctx, const T *host, int64_t count, const T **dev_out) {
+  T *dptr = nullptr;
+  CU(cudaMalloc((void **)&dptr, sizeof(T) * (size_t)std::max<int64_t>(count, 1)));
+  ctx->owned.push_back(dptr);
+  if (count) CU(cudaMemcpyAsync(dptr, host, sizeof(T) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+  *dev_out = dptr;
+  return 0;
+}
+
+int upload_x(boomgpu_ctx *ctx, int64_t n, int p, const double *X, int64_t ldx) {
+  // device layout: row major, leading dimension rounded up to 8 doubles (64 B), pad columns zero
+  const int64_t ldd = ((int64_t)p + 7) / 8 * 8;
+  double *dX = nullptr;
+  CU(cudaMalloc((void **)&dX, sizeof(double) * (size_t)std::max<int64_t>(n * ldd, 1)));
+  ctx->owned.push_back(dX);
+  if (n) {
+    if (ldd != p) CU(cudaMemsetAsync(dX, 0, sizeof(double) * (size_t)(n * ldd), ctx->stream));
+    CU(cudaMemcpy2DAsync(dX, sizeof(double) * ldd, X, sizeof(double) * ldx, sizeof(double) * p, (size_t)n,
+                         cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->X = dX; ctx->ldx = ldd; ctx->n = n; ctx->p = p;
+  return 0;
+}
+
+int check_dims(boomgpu_ctx *ctx, int64_t n, int p, int64_t ldx, const void *X) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (n < 0 || p <= 0 || ldx < p || (!X && n > 0)) return fail(ctx, BOOMGPU_ERR_ARG, "bad dimensions n=%lld p=%d ldx=%lld", (long long)n, p, (long long)ldx);
+  if (p > 16384) return fail(ctx, BOOMGPU_ERR_ARG, "p = %d exceeds the supported maximum 16384", p);
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char *boomgpu_version(void) { return "boomgpu 0.1 (sm_100a)"; }
+
+int boomgpu_create(boomgpu_ctx **out, int device) {
+  boomgpu_ctx *ctx = nullptr;
+  if (!out) return fail(nullptr, BOOMGPU_ERR_ARG, "null ctx pointer");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, BOOMGPU_ERR_CUDA, "no CUDA device available (%s); boomgpu has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(nullptr, BOOMGPU_ERR_ARG, "device %d out of range (%d devices)", device, count);
+  ctx = new boomgpu_ctx;
+  ctx->device = device;
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, BOOMGPU_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  }
+  if (prop.major < 9) {
+    delete ctx;
+    return fail(nullptr, BOOMGPU_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  }
+  ctx->sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc((void **)&ctx->err_dev, sizeof(int)) != cudaSuccess ||
+      cudaMallocHost((void **)&ctx->err_pin, sizeof(int)) != cudaSuccess ||
+      cudaMemset(ctx->err_dev, 0, sizeof(int)) != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, BOOMGPU_ERR_CUDA, "context set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  ctx->own_stream = true;
+  *out = ctx;
+  return 0;
+}
+
+void boomgpu_destroy(boomgpu_ctx *ctx) {
+  if (!ctx) return;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  drain_timings(ctx);
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  free_data(ctx);
+  for (void *q : ctx->tab_owned) cudaFree(q);
+  cudaFree(ctx->beta_dev); cudaFreeHost(ctx->beta_pin);
+  cudaFree(ctx->suf_dev); cudaFreeHost(ctx->suf_pin);
+  cudaFree(ctx->partials); cudaFree(ctx->scal_partials);
+  cudaFree(ctx->w_buf); cudaFree(ctx->s_buf);
+  cudaFree(ctx->err_dev); cudaFreeHost(ctx->err_pin);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *boomgpu_last_error(const boomgpu_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int boomgpu_set_stream(boomgpu_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) { CU(cudaStreamDestroy(ctx->stream)); ctx->own_stream = false; }
+  ctx->stream = (cudaStream_t)cuda_stream;
+  return 0;
+}
+
+int boomgpu_set_row_offset(boomgpu_ctx *ctx, uint64_t first_global_row) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  ctx->row_offset = first_global_row;
+  return 0;
+}
+
+int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value) {
+  if (!ctx || !name) return BOOMGPU_ERR_ARG;
+  if (!strcmp(name, "path")) {
+    if (value < 0 || value > 2) return fail(ctx, BOOMGPU_ERR_ARG, "path must be 0, 1 or 2");
+    ctx->path = (int)value;
+    return 0;
+  }
+  if (!strcmp(name, "timing")) { ctx->timing = value != 0; return 0; }
+  return fail(ctx, BOOMGPU_ERR_ARG, "unknown option '%s'", name);
+}
+
+int boomgpu_upload_binomial(boomgpu_ctx *ctx, int64_t n, int p, const double *X, int64_t ldx, const double *y,
+                            const double *ntrials) {
+  if (int rc = check_dims(ctx, n, p, ldx, X)) return rc;
+  if (n > 0 && (!y || !ntrials)) return fail(ctx, BOOMGPU_ERR_ARG, "null y / ntrials");
+  DeviceGuard g(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  free_data(ctx);
+  if (int rc = upload_x(ctx, n, p, X, ldx)) return rc;
+  if (int rc = upload_array(ctx, y, n, &ctx->y)) return rc;
+  if (int rc = upload_array(ctx, ntrials, n, &ctx->ntrials)) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->model = kLogit;
+  return 0;
+}
+
+int boomgpu_upload_poisson(boomgpu_ctx *ctx, int64_t n, int p, const double *X, int64_t ldx, const int64_t *y,
+                           const double *exposure) {
+  if (int rc = check_dims(ctx, n, p, ldx, X)) return rc;
+  if (n > 0 && (!y || !exposure)) return fail(ctx, BOOMGPU_ERR_ARG, "null y / exposure");
+  DeviceGuard g(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  free_data(ctx);
+  if (int rc = upload_x(ctx, n, p, X, ldx)) return rc;
+  if (int rc = upload_array(ctx, y, n, &ctx->yi)) return rc;
+  if (int rc = upload_array(ctx, exposure, n, &ctx->exposure)) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->model = kPoisson;
+  return 0;
+}
+
+int boomgpu_adopt_binomial(boomgpu_ctx *ctx, int64_t n, int p, const double *dX, int64_t ldx, const double *dy,
+                           const double *dntrials) {
+  if (int rc = check_dims(ctx, n, p, ldx, dX)) return rc;
+  DeviceGuard g(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  free_data(ctx);
+  ctx->X = dX; ctx->ldx = ldx; ctx->n = n; ctx->p = p; ctx->y = dy; ctx->ntrials = dntrials;
+  ctx->model = kLogit;
+  return 0;
+}
+
+int boomgpu_adopt_poisson(boomgpu_ctx *ctx, int64_t n, int p, const double *dX, int64_t ldx, const int64_t *dy,
+                          const double *dexposure) {
+  if (int rc = check_dims(ctx, n, p, ldx, dX)) return rc;
+  DeviceGuard g(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  free_data(ctx);
+  ctx->X = dX; ctx->ldx = ldx; ctx->n = n; ctx->p = p; ctx->yi = dy; ctx->exposure = dexposure;
+  ctx->model = kPoisson;
+  return 0;
+}
+
+int boomgpu_set_logit_mixture(boomgpu_ctx *ctx, int K, const double *mu, const double *sigma, const double *weights) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (K < 1 || K > kMaxLogitK || !sigma || !weights) return fail(ctx, BOOMGPU_ERR_ARG, "mixture needs 1 <= K <= %d", kMaxLogitK);
+  LogitMixture &m = ctx->mix;
+  memset(&m, 0, sizeof(m));
+  m.K = K;
+  for (int k = 0; k < K; ++k) {
+    if (!(sigma[k] > 0) || !(weights[k] > 0)) return fail(ctx, BOOMGPU_ERR_ARG, "mixture sigma and weights must be positive");
+    m.mu[k] = mu ? mu[k] : 0.0;
+    m.sigma[k] = sigma[k];
+    m.inv_sigma[k] = 1.0 / sigma[k];
+    m.weights[k] = weights[k];
+    m.lconst[k] = std::log(weights[k]) - kLnSqrt2Pi - std::log(sigma[k]);
+    m.inv_sigsq[k] = 1.0 / (sigma[k] * sigma[k]);
+  }
+  ctx->have_mix = true;
+  return 0;
+}
+
+int boomgpu_set_poisson_table(boomgpu_ctx *ctx, int ntab, const int64_t *nu, const int32_t *offset, const double *weights,
+                              const double *mu, const double *sigma, int64_t gaussian_cutoff) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (ntab < 1 || !nu || !offset || !weights || !mu || !sigma) return fail(ctx, BOOMGPU_ERR_ARG, "bad Poisson table");
+  int e1 = -1;
+  for (int e = 0; e < ntab; ++e) {
+    if (e > 0 && nu[e] < nu[e - 1]) return fail(ctx, BOOMGPU_ERR_ARG, "Poisson table must be sorted by nu");
+    const int K = offset[e + 1] - offset[e];
+    if (K < 1 || K > kMaxLogitK) return fail(ctx, BOOMGPU_ERR_ARG, "table entry nu=%lld has %d components (max %d)", (long long)nu[e], K, kMaxLogitK);
+    if (nu[e] == 1 && e1 < 0) e1 = e;
+  }
+  if (e1 < 0) return fail(ctx, BOOMGPU_ERR_ARG, "Poisson table has no entry for nu = 1");
+  const int total = offset[ntab];
+  std::vector<double> inv_sigma(total), lconst(total);
+  for (int i = 0; i < total; ++i) {
+    if (!(sigma[i] > 0) || !(weights[i] > 0)) return fail(ctx, BOOMGPU_ERR_ARG, "table sigma and weights must be positive");
+    inv_sigma[i] = 1.0 / sigma[i];
+    lconst[i] = std::log(weights[i]) - kLnSqrt2Pi - std::log(sigma[i]);
+  }
+  DeviceGuard g(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (void *q : ctx->tab_owned) cudaFree(q);
+  ctx->tab_owned.clear();
+  auto up = [&](const void *src, size_t bytes, void **dst) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, bytes);
+    if (e != cudaSuccess) return e;
+    ctx->tab_owned.push_back(*dst);
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  };
+  PoissonTable &t = ctx->tab;
+  t.ntab = ntab; t.gaussian_cutoff = gaussian_cutoff; t.e1 = e1;
+  CU(up(nu, sizeof(int64_t) * ntab, (void **)&t.nu));
+  CU(up(offset, sizeof(int32_t) * (ntab + 1), (void **)&t.offset));
+  CU(up(mu, sizeof(double) * total, (void **)&t.mu));
+  CU(up(sigma, sizeof(double) * total, (void **)&t.sigma));
+  CU(up(inv_sigma.data(), sizeof(double) * total, (void **)&t.inv_sigma));
+  CU(up(lconst.data(), sizeof(double) * total, (void **)&t.lconst));
+  ctx->have_tab = true;
+  return 0;
+}
+
+int64_t boomgpu_suf_len(int p) { return (int64_t)p * p + p + 4; }
+
+int boomgpu_logit_step_device(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
+                              double *suf_dev) {
+  if (int rc = check_ready(ctx, kLogit)) return rc;
+  if (!beta || !suf_dev) return fail(ctx, BOOMGPU_ERR_ARG, "null beta / suf_dev");
+  DeviceGuard g(ctx->device);
+  RowOut out{nullptr, nullptr, nullptr, nullptr};
+  return run_step<kLogit>(ctx, beta, make_prm(ctx, clt_threshold, seed, iteration), out, nullptr, nullptr, suf_dev);
+}
+
+int boomgpu_poisson_step_device(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *suf_dev) {
+  if (int rc = check_ready(ctx, kPoisson)) return rc;
+  if (!beta || !suf_dev) return fail(ctx, BOOMGPU_ERR_ARG, "null beta / suf_dev");
+  DeviceGuard g(ctx->device);
+  RowOut out{nullptr, nullptr, nullptr, nullptr};
+  return run_step<kPoisson>(ctx, beta, make_prm(ctx, 0, seed, iteration), out, nullptr, nullptr, suf_dev);
+}
+
+int boomgpu_synchronize(boomgpu_ctx *ctx) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  return finish_and_check(ctx);
+}
+
+int boomgpu_logit_step(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
+                       double *xtx, double *xty, int64_t *sample_size) {
+  if (int rc = check_ready(ctx, kLogit)) return rc;
+  if (!beta || !xtx || !xty) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
+  DeviceGuard g(ctx->device);
+  if (int rc = ensure_suf(ctx)) return rc;
+  if (int rc = boomgpu_logit_step_device(ctx, beta, clt_threshold, seed, iteration, ctx->suf_dev)) return rc;
+  const int p = ctx->p;
+  CU(cudaMemcpyAsync(ctx->suf_pin, ctx->suf_dev, sizeof(double) * (size_t)boomgpu_suf_len(p), cudaMemcpyDeviceToHost, ctx->stream));
+  if (int rc = finish_and_check(ctx)) return rc;
+  memcpy(xtx, ctx->suf_pin, sizeof(double) * (size_t)p * p);
+  memcpy(xty, ctx->suf_pin + (size_t)p * p, sizeof(double) * p);
+  if (sample_size) *sample_size = (int64_t)llround(ctx->suf_pin[(size_t)p * p + p]);
+  return 0;
+}
+
+int boomgpu_poisson_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *xtwx, double *xtwy,
+                         double scalars[4]) {
+  if (int rc = check_ready(ctx, kPoisson)) return rc;
+  if (!beta || !xtwx || !xtwy) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
+  DeviceGuard g(ctx->device);
+  if (int rc = ensure_suf(ctx)) return rc;
+  if (int rc = boomgpu_poisson_step_device(ctx, beta, seed, iteration, ctx->suf_dev)) return rc;
+  const int p = ctx->p;
+  CU(cudaMemcpyAsync(ctx->suf_pin, ctx->suf_dev, sizeof(double) * (size_t)boomgpu_suf_len(p), cudaMemcpyDeviceToHost, ctx->stream));
+  if (int rc = finish_and_check(ctx)) return rc;
+  memcpy(xtwx, ctx->suf_pin, sizeof(double) * (size_t)p * p);
+  memcpy(xtwy, ctx->suf_pin + (size_t)p * p, sizeof(double) * p);
+  if (scalars) memcpy(scalars, ctx->suf_pin + (size_t)p * p + p, sizeof(double) * 4);
+  return 0;
+}
+
+int boomgpu_accumulate(boomgpu_ctx *ctx, const double *weight, const double *weighted_value, double *xtx, double *xty) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (!ctx->X) return fail(ctx, BOOMGPU_ERR_STATE, "no data uploaded to this context");
+  if (!weight || !weighted_value || !xtx || !xty) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
+  DeviceGuard g(ctx->device);
+  if (int rc = ensure_suf(ctx)) return rc;
+  double *dw = nullptr, *ds = nullptr;
+  const size_t bytes = sizeof(double) * (size_t)std::max<int64_t>(ctx->n, 1);
+  CU(cudaMalloc((void **)&dw, bytes));
+  CU(cudaMalloc((void **)&ds, bytes));
+  int rc = 0;
+  cudaError_t e1 = cudaMemcpyAsync(dw, weight, sizeof(double) * (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream);
+  cudaError_t e2 = cudaMemcpyAsync(ds, weighted_value, sizeof(double) * (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(ctx, BOOMGPU_ERR_CUDA, "copy of latents failed");
+  RowOut out{nullptr, nullptr, nullptr, nullptr};
+  DrawParams prm = make_prm(ctx, 0, 0, 0);
+  if (!rc) rc = run_step<kSupplied>(ctx, nullptr, prm, out, dw, ds, ctx->suf_dev);
+  const int p = ctx->p;
+  if (!rc && cudaMemcpyAsync(ctx->suf_pin, ctx->suf_dev, sizeof(double) * (size_t)boomgpu_suf_len(p), cudaMemcpyDeviceToHost,
+                             ctx->stream) != cudaSuccess)
+    rc = fail(ctx, BOOMGPU_ERR_CUDA, "copy of statistics failed");
+  if (!rc) rc = finish_and_check(ctx); else cudaStreamSynchronize(ctx->stream);
+  cudaFree(dw); cudaFree(ds);
+  if (rc) return rc;
+  memcpy(xtx, ctx->suf_pin, sizeof(double) * (size_t)p * p);
+  memcpy(xty, ctx->suf_pin + (size_t)p * p, sizeof(double) * p);
+  return 0;
+}
+
+int boomgpu_logit_draw(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
+                       double *sum_out, double *info_out) {
+  if (int rc = check_ready(ctx, kLogit)) return rc;
+  if (!beta || !sum_out || !info_out) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
+  DeviceGuard g(ctx->device);
+  if (int rc = ensure_suf(ctx)) return rc;
+  double *dw = nullptr, *ds = nullptr;
+  const size_t bytes = sizeof(double) * (size_t)std::max<int64_t>(ctx->n, 1);
+  CU(cudaMalloc((void **)&dw, bytes));
+  CU(cudaMalloc((void **)&ds, bytes));
+  RowOut out{dw, ds, nullptr, nullptr};
+  int rc = run_step<kLogit>(ctx, beta, make_prm(ctx, clt_threshold, seed, iteration), out, nullptr, nullptr, ctx->suf_dev);
+  if (!rc && (cudaMemcpyAsync(info_out, dw, sizeof(double) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+              cudaMemcpyAsync(sum_out, ds, sizeof(double) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess))
+    rc = fail(ctx, BOOMGPU_ERR_CUDA, "copy of draws failed");
+  if (!rc) rc = finish_and_check(ctx); else cudaStreamSynchronize(ctx->stream);
+  cudaFree(dw); cudaFree(ds);
+  return rc;
+}
+
+int boomgpu_poisson_draw(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *out6, int32_t *kout2) {
+  if (int rc = check_ready(ctx, kPoisson)) return rc;
+  if (!beta || !out6) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
+  DeviceGuard g(ctx->device);
+  if (int rc = ensure_suf(ctx)) return rc;
+  double *d6 = nullptr; int32_t *dk = nullptr;
+  const size_t n1 = (size_t)std::max<int64_t>(ctx->n, 1);
+  CU(cudaMalloc((void **)&d6, sizeof(double) * 6 * n1));
+  CU(cudaMalloc((void **)&dk, sizeof(int32_t) * 2 * n1));
+  CU(cudaMemsetAsync(d6, 0, sizeof(double) * 6 * n1, ctx->stream));
+  RowOut out{nullptr, nullptr, d6, dk};
+  int rc = run_step<kPoisson>(ctx, beta, make_prm(ctx, 0, seed, iteration), out, nullptr, nullptr, ctx->suf_dev);
+  if (!rc && cudaMemcpyAsync(out6, d6, sizeof(double) * 6 * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+    rc = fail(ctx, BOOMGPU_ERR_CUDA, "copy of draws failed");
+  if (!rc && kout2 && cudaMemcpyAsync(kout2, dk, sizeof(int32_t) * 2 * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+    rc = fail(ctx, BOOMGPU_ERR_CUDA, "copy of indicators failed");
+  if (!rc) rc = finish_and_check(ctx); else cudaStreamSynchronize(ctx->stream);
+  cudaFree(d6); cudaFree(dk);
+  return rc;
+}
+
+static int loglike_impl(boomgpu_ctx *ctx, int model, const double *beta, double *loglike) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (ctx->model != model || !ctx->X) return fail(ctx, BOOMGPU_ERR_STATE, "no matching data uploaded to this context");
+  if (!beta || !loglike) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
+  DeviceGuard g(ctx->device);
+  const int p = ctx->p;
+  double *dbeta = nullptr, *parts = nullptr;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->n + 7) / 8, (int64_t)ctx->sms * 8));
+  CU(cudaMalloc((void **)&dbeta, sizeof(double) * p));
+  CU(cudaMalloc((void **)&parts, sizeof(double) * (grid + 1)));
+  CU(cudaMemcpyAsync(dbeta, beta, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+  RowData d;
+  memset(&d, 0, sizeof(d));
+  d.X = ctx->X; d.ldx = ctx->ldx; d.n = ctx->n; d.p = p;
+  d.y = ctx->y; d.ntrials = ctx->ntrials; d.yi = ctx->yi; d.exposure = ctx->exposure;
+  {
+    LaunchScope ls(ctx, 4);
+    if (model == kLogit) loglike_kernel<kLogit><<<grid, 256, sizeof(double) * p, ctx->stream>>>(d, dbeta, parts);
+    else loglike_kernel<kPoisson><<<grid, 256, sizeof(double) * p, ctx->stream>>>(d, dbeta, parts);
+  }
+  {
+    LaunchScope ls(ctx, 3);
+    reduce_sum_kernel<<<1, 32, 0, ctx->stream>>>(parts, grid, parts + grid);
+  }
+  cudaError_t e = cudaGetLastError();
+  double result = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&result, parts + grid, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dbeta); cudaFree(parts);
+  if (e != cudaSuccess) return fail(ctx, BOOMGPU_ERR_CUDA, "log likelihood failed: %s", cudaGetErrorString(e));
+  *loglike = ctx->n == 0 ? 0.0 : result;
+  return 0;
+}
+
+int boomgpu_binomial_loglike(boomgpu_ctx *ctx, const double *beta, double *loglike) { return loglike_impl(ctx, kLogit, beta, loglike); }
+int boomgpu_poisson_loglike(boomgpu_ctx *ctx, const double *beta, double *loglike) { return loglike_impl(ctx, kPoisson, beta, loglike); }
+
+int64_t boomgpu_kernel_launches(const boomgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int boomgpu_get_timings(boomgpu_ctx *ctx, double ms[BOOMGPU_NUM_KERNEL_CLASSES], int64_t launches[BOOMGPU_NUM_KERNEL_CLASSES],
+                        int reset) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  drain_timings(ctx);
+  for (int c = 0; c < BOOMGPU_NUM_KERNEL_CLASSES; ++c) {
+    if (ms) ms[c] = ctx->ms_acc[c];
+    if (launches) launches[c] = ctx->n_acc[c];
+    if (reset) { ctx->ms_acc[c] = 0; ctx->n_acc[c] = 0; }
+  }
+  return 0;
+}
+
+}  // extern "C"

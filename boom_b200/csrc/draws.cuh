@@ -1,0 +1,349 @@
+// draws.cuh -- per-observation latent draws of the auxiliary-mixture samplers (device side).
+//
+// What the reference does per observation, and where:
+//   logit, small sample  BinomialLogitCltDataImputer::impute_small_sample
+//                        (Models/Glm/PosteriorSamplers/BinomialLogitDataImputer.cpp:134-152):
+//                        rtrun_logit_mt (distributions/trun_logit.cpp:163-174) then
+//                        NormalMixtureApproximation::unmix (NormalMixtureApproximation.cpp:280-290)
+//   logit, CLT           impute_large_sample (BinomialLogitDataImputer.cpp:155-210)
+//   Poisson              PoissonDataImputer::impute (PoissonDataImputer.cpp:36-98) and
+//                        unmix_poisson_augmented_data (poisson_mixture_approximation_table.cpp:44-61)
+// The random stream is Philox4x32-10 keyed by (seed, iteration, GLOBAL row, slot), so the
+// draws are identical for any sharding of the rows over GPUs.
+#pragma once
+#include <cstdint>
+
+namespace boomgpu {
+
+constexpr int kMaxLogitK = 16;
+constexpr double kLnSqrt2Pi = 0.918938533204672741780329736406;
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+
+// ---- Philox4x32-10 ------------------------------------------------------------------
+struct U4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    U4 n;
+    n.x = hi1 ^ c.y ^ k0; n.y = lo1; n.z = hi0 ^ c.w ^ k1; n.w = lo0;
+    c = n;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__device__ __forceinline__ double bits_to_open01(uint32_t hi, uint32_t lo) {
+  uint64_t k = ((uint64_t)hi << 20) | (uint64_t)(lo >> 12);
+  return ((double)k + 0.5) * 0x1p-52;  // (k + 1/2) 2^-52, exact, strictly inside (0,1)
+}
+
+struct RngKey { uint64_t seed, iteration; };
+
+__device__ __forceinline__ void uniform_pair(const RngKey &key, uint64_t row, uint32_t slot, double &u0, double &u1) {
+  U4 c;
+  c.x = (uint32_t)row; c.y = (uint32_t)(row >> 32);
+  c.z = (uint32_t)key.iteration;
+  c.w = (((uint32_t)(key.iteration >> 32) & 0xFFFFu) << 16) | (slot & 0xFFFFu);
+  U4 o = philox4x32_10(c, (uint32_t)key.seed, (uint32_t)(key.seed >> 32));
+  u0 = bits_to_open01(o.x, o.y);
+  u1 = bits_to_open01(o.z, o.w);
+}
+
+// ---- mixtures -------------------------------------------------------------------------
+// Passed by value as a kernel parameter (constant bank: every lane reads the same entry).
+struct LogitMixture {
+  int K;
+  double mu[kMaxLogitK];
+  double sigma[kMaxLogitK];
+  double inv_sigma[kMaxLogitK];
+  double weights[kMaxLogitK];
+  double lconst[kMaxLogitK];     // log w - ln sqrt(2 pi) - log sigma
+  double inv_sigsq[kMaxLogitK];  // 1 / (sigma * sigma)
+};
+
+// Poisson table in global memory (per-row nu makes the lookups divergent).
+struct PoissonTable {
+  int ntab;
+  const int64_t *nu;
+  const int32_t *offset;
+  const double *mu;
+  const double *inv_sigma;
+  const double *lconst;
+  const double *sigma;
+  int64_t gaussian_cutoff;
+  int e1;  // entry index of nu == 1 (every row uses it)
+};
+
+// NormalMixtureApproximation::unmix given its uniform.  The reference normalises the
+// probabilities before rmulti_mt draws v ~ U(0, sum); selecting on the unnormalised
+// cumulative sums with v = U * sum is the same event.
+template <class F>
+__device__ __forceinline__ int unmix_generic(int K, double unif, F lp_of) {
+  double lp[kMaxLogitK];
+  double mx = -1e300;
+#pragma unroll
+  for (int s = 0; s < kMaxLogitK; ++s) {
+    if (s < K) { lp[s] = lp_of(s); mx = fmax(mx, lp[s]); }
+  }
+  double tot = 0;
+#pragma unroll
+  for (int s = 0; s < kMaxLogitK; ++s) {
+    if (s < K) { lp[s] = exp(lp[s] - mx); tot += lp[s]; }
+  }
+  double v = unif * tot, cs = 0;
+  int k = K - 1;
+  bool found = false;
+#pragma unroll
+  for (int s = 0; s < kMaxLogitK; ++s) {
+    if (s < K) {
+      cs += lp[s];
+      if (!found && v <= cs) { k = s; found = true; }
+    }
+  }
+  return k;
+}
+
+__device__ __forceinline__ int unmix_logit(const LogitMixture &m, double resid, double unif) {
+  return unmix_generic(m.K, unif, [&](int s) {
+    double x = (resid - m.mu[s]) * m.inv_sigma[s];
+    return m.lconst[s] - 0.5 * x * x;
+  });
+}
+
+__device__ __forceinline__ double rtrun_logit(double eta, bool success, double unif) {
+  double c = 1.0 / (1.0 + exp(eta));  // plogis(0 - eta)
+  double u = success ? c + (1.0 - c) * unif : c * unif;
+  u = fmin(u, 1.0 - 0x1p-53);
+  u = fmax(u, 2.2250738585072014e-308);
+  return log(u / (1.0 - u)) + eta;
+}
+
+// log(1 - Phi(a)) and the hazard phi(a) / (1 - Phi(a)) through erfcx (stable in both tails)
+__device__ __forceinline__ double normal_hazard(double a) {
+  return 0.7978845608028654 / erfcx(a * 0.7071067811865476);  // sqrt(2/pi) / erfcx(a / sqrt 2)
+}
+
+__device__ __forceinline__ void trun_norm_moments(double mu, double sigma, bool positive, double &mean, double &var) {
+  double sigsq = sigma * sigma;
+  if (positive) {
+    double alpha = (0.0 - mu) / sigma;
+    double r = normal_hazard(alpha);
+    mean = mu + sigma * r;
+    var = sigsq * (1 - r * (r - alpha));
+  } else {
+    double beta = (0.0 - mu) / sigma;
+    double r = normal_hazard(-beta);
+    mean = mu - sigma * r;
+    var = sigsq * (1 - beta * r - r * r);
+  }
+  var = fmax(var, 0.0);
+}
+
+// Binomial(n, p) from one uniform: chop-down search outward from the mode (see oracle).
+__device__ inline int64_t binomial_from_uniform(int64_t n, double p, double unif) {
+  if (n <= 0 || p <= 0.0) return 0;
+  if (p >= 1.0) return n;
+  double q = 1.0 - p, dn = (double)n;
+  int64_t m = (int64_t)floor((dn + 1.0) * p);
+  if (m > n) m = n;
+  double dm = (double)m;
+  double fm = exp(lgamma(dn + 1.0) - lgamma(dm + 1.0) - lgamma(dn - dm + 1.0) + dm * log(p) + (dn - dm) * log(q));
+  double u = unif - fm;
+  if (u <= 0) return m;
+  double r = p / q, fu = fm, fd = fm;
+  int64_t ku = m, kd = m;
+  for (;;) {
+    bool moved = false;
+    if (ku < n) {
+      fu *= r * (double)(n - ku) / (double)(ku + 1);
+      ++ku; moved = true;
+      u -= fu;
+      if (u <= 0) return ku;
+    }
+    if (kd > 0) {
+      fd *= (double)kd / (r * (double)(n - kd + 1));
+      --kd; moved = true;
+      u -= fd;
+      if (u <= 0) return kd;
+    }
+    if (!moved) return m;
+  }
+}
+
+__device__ inline void multinomial_from_uniforms(int64_t n, int K, const double *prob, const double *unif, int64_t *out) {
+  double p_tot = 0;
+  for (int k = 0; k < K; ++k) { p_tot += prob[k]; out[k] = 0; }
+  if (n == 0) return;
+  for (int k = 0; k < K - 1; ++k) {
+    double pp = prob[k] / p_tot;
+    pp = fmin(pp, 1.0);
+    if (!(pp > 0.0)) pp = 0.0;
+    out[k] = binomial_from_uniform(n, pp, unif[k]);
+    n -= out[k];
+    if (n <= 0) return;
+    p_tot -= prob[k];
+  }
+  out[K - 1] = n;
+}
+
+// CLT branch, kept out of line: Bernoulli data never take it.
+__device__ __noinline__ void logit_impute_large(const LogitMixture &m, double ntrials, double y, double eta,
+                                                const RngKey &key, uint64_t row, double &sum, double &info) {
+  const int K = m.K;
+  double p0[kMaxLogitK], p1[kMaxLogitK], un0[8], un1[8];
+  int64_t N0[kMaxLogitK], N1[kMaxLogitK];
+  double neg = 1.0 / (1.0 + exp(eta)), pos = 1.0 / (1.0 + exp(-eta));
+  double s0 = 0, s1 = 0;
+  for (int k = 0; k < K; ++k) {
+    double a = (0.0 - eta) / m.sigma[k];
+    p0[k] = m.weights[k] / neg * normcdf(a);
+    p1[k] = m.weights[k] / pos * normcdf(-a);
+  }
+  for (int k = 0; k < K; ++k) { s0 += p0[k]; s1 += p1[k]; }
+  for (int k = 0; k < K; ++k) { p0[k] /= s0; p1[k] /= s1; }
+  for (int b = 0; b < 4; ++b) {
+    uniform_pair(key, row, b, un0[2 * b], un0[2 * b + 1]);
+    uniform_pair(key, row, 4 + b, un1[2 * b], un1[2 * b + 1]);
+  }
+  multinomial_from_uniforms((int64_t)(ntrials - y), K, p0, un0, N0);
+  multinomial_from_uniforms((int64_t)y, K, p1, un1, N1);
+  double mean = 0, var = 0, w = 0;
+  for (int k = 0; k < K; ++k) {
+    int64_t tot = N0[k] + N1[k];
+    if (tot == 0) continue;
+    double sigsq = m.sigma[k] * m.sigma[k], sig4 = sigsq * sigsq;
+    w += (double)tot / sigsq;
+    double tm, tv;
+    if (N0[k] > 0) {
+      trun_norm_moments(eta, m.sigma[k], false, tm, tv);
+      mean += (double)N0[k] * tm / sigsq;
+      var += (double)N0[k] * tv / sig4;
+    }
+    if (N1[k] > 0) {
+      trun_norm_moments(eta, m.sigma[k], true, tm, tv);
+      mean += (double)N1[k] * tm / sigsq;
+      var += (double)N1[k] * tv / sig4;
+    }
+  }
+  double u0, u1;
+  uniform_pair(key, row, 8, u0, u1);
+  double zn = sqrt(-2.0 * log(u0)) * cos(kTwoPi * u1);
+  sum = mean + sqrt(var) * zn;
+  info = w;
+}
+
+// BinomialLogitCltDataImputer::impute.  Returns false on invalid input (y > n, negative, NaN eta).
+__device__ __forceinline__ bool logit_impute(const LogitMixture &m, int clt_threshold, double ntrials, double y,
+                                             double eta, const RngKey &key, uint64_t row, double &sum, double &info) {
+  sum = 0; info = 0;
+  if (!(y <= ntrials) || y < 0 || ntrials < 0 || !isfinite(eta)) return false;
+  if (ntrials > (double)clt_threshold) {
+    if (m.K > 9) return false;  // slot layout of the CLT branch: K - 1 <= 8 conditional binomials per side
+    logit_impute_large(m, ntrials, y, eta, key, row, sum, info);
+    return true;
+  }
+  for (int i = 0; i < ntrials; ++i) {
+    double u0, u1;
+    uniform_pair(key, row, (uint32_t)i, u0, u1);
+    double z = rtrun_logit(eta, i < y, u0);
+    int k = unmix_logit(m, z - eta, u1);
+    double cw = m.inv_sigsq[k];
+    info += cw;
+    sum += z * cw;
+  }
+  return true;
+}
+
+// ---- Poisson --------------------------------------------------------------------------
+__device__ __forceinline__ int poisson_table_find(const PoissonTable &t, int64_t nu) {
+  int lo = 0, hi = t.ntab - 1;
+  while (lo <= hi) {
+    int mid = (lo + hi) >> 1;
+    int64_t v = __ldg(t.nu + mid);
+    if (v == nu) {
+      while (mid > 0 && __ldg(t.nu + mid - 1) == nu) --mid;
+      return mid;
+    }
+    if (v < nu) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ bool unmix_poisson(const PoissonTable &t, int entry, double resid, double unif,
+                                              double &mu, double &weight, int &kout) {
+  if (entry < 0) return false;
+  int a = __ldg(t.offset + entry), K = __ldg(t.offset + entry + 1) - a;
+  if (K > kMaxLogitK) return false;
+  int k = unmix_generic(K, unif, [&](int s) {
+    double x = (resid - __ldg(t.mu + a + s)) * __ldg(t.inv_sigma + a + s);
+    return __ldg(t.lconst + a + s) - 0.5 * x * x;
+  });
+  mu = __ldg(t.mu + a + k);
+  double sg = __ldg(t.sigma + a + k);
+  weight = 1.0 / (sg * sg);
+  kout = k;
+  return true;
+}
+
+struct PoissonLatent { double z_int, mu_int, w_int, z_ext, mu_ext, w_ext; int k_int, k_ext; };
+
+// PoissonDataImputer::impute.  rc: 0 ok, 1 nu missing from the table, 2 invalid input.
+__device__ __forceinline__ int poisson_impute(const PoissonTable &t, int64_t y, double exposure, double eta,
+                                              const RngKey &key, uint64_t row, PoissonLatent &o) {
+  o.z_int = o.mu_int = o.w_int = 0; o.k_int = o.k_ext = -1;
+  if (y < 0 || !(exposure >= 0) || !isfinite(eta)) return 2;
+  double ua0, ua1, ub0, ub1;
+  uniform_pair(key, row, 0, ua0, ua1);
+  uniform_pair(key, row, 1, ub0, ub1);
+  double tau = y > 0 ? exposure * pow(ua0, 1.0 / (double)y) : 0.0;  // Beta(y, 1) by inversion
+  double delta = exposure - tau;
+  double e1 = -log(ua1);
+  double z_ext;
+  if (fabs(eta) < 600) {
+    z_ext = -log(delta + (1.0 / exp(eta)) * e1);
+  } else if (delta > 0) {
+    double err = -log(e1);
+    double a = log(delta), b = -err - eta;
+    if (a < b) { double tmp = a; a = b; b = tmp; }
+    z_ext = -(a + log1p(exp(b - a)));
+  } else {
+    z_ext = eta + (-log(e1));
+  }
+  if (!unmix_poisson(t, t.e1, z_ext - eta, ub0, o.mu_ext, o.w_ext, o.k_ext)) return 1;
+  o.z_ext = z_ext;
+  if (y > 0) {
+    double z_int = -log(tau);
+    o.z_int = z_int;
+    if (y >= t.gaussian_cutoff) {
+      o.mu_int = -log((double)y);
+      o.w_int = 1.0 / (1.0 / (double)y);
+    } else {
+      if (!unmix_poisson(t, poisson_table_find(t, y), z_int - eta, ub1, o.mu_int, o.w_int, o.k_int)) return 1;
+    }
+  }
+  return 0;
+}
+
+// ---- log densities (value only) ---------------------------------------------------------
+// dbinom(y; n, p) on the log scale.  The reference uses R's saddle-point form
+// (Bmath/dbinom.cpp:61-99); lgamma + x log p + (n-x) log q agrees to ~1e-15 absolute per term.
+__device__ __forceinline__ double dbinom_log(double x, double n, double eta) {
+  // log p = -log1p(exp(-eta)), log q = -log1p(exp(eta)), stable for any eta
+  double lp = eta > 0 ? -log1p(exp(-eta)) : eta - log1p(exp(eta));
+  double lq = eta > 0 ? -eta - log1p(exp(-eta)) : -log1p(exp(eta));
+  double lc = (x == 0 || x == n) ? 0.0 : lgamma(n + 1.0) - lgamma(x + 1.0) - lgamma(n - x + 1.0);
+  double t1 = x == 0 ? 0.0 : x * lp;
+  double t2 = (n - x) == 0 ? 0.0 : (n - x) * lq;
+  return lc + t1 + t2;
+}
+
+__device__ __forceinline__ double dpois_log(double x, double lambda) {
+  if (lambda == 0) return x == 0 ? 0.0 : -INFINITY;
+  if (x == 0) return -lambda;
+  return x * log(lambda) - lambda - lgamma(x + 1.0);
+}
+
+}  // namespace boomgpu

@@ -1,0 +1,709 @@
+// kernels.cuh -- CUDA kernels of the auxiliary-mixture Gibbs hot path, written for sm_100a.
+//
+//   fused_small_kernel   p <= 64 : ONE pass over X. cp.async-staged row chunks in shared memory,
+//                        eta = x'beta, latent draw, weighted SYRK on FP64 DMMA with the whole upper
+//                        triangle of X'WX resident in registers.  HBM-bound (8 n (p+2) bytes).
+//   impute_rows_kernel   p  > 64 : pass 1, warp-per-row GEMV + latent draw -> (w_i, s_i).  HBM-bound.
+//   syrk_dmma_kernel     p  > 64 : pass 2, split-K weighted SYRK  X' diag(w) X  (upper triangle) and
+//                        X's on FP64 DMMA (mma.sync m8n8k4), X tiles staged by TMA bulk copies
+//                        (cp.async.bulk + mbarrier) through a 4-stage ring.  FP64-pipe-bound.
+//   reduce_* kernels     deterministic (fixed order) reduction of the per-CTA partials.
+//
+// The reference equivalent of all of this is the per-observation loop
+// Models/PosteriorSamplers/Imputer.hpp:175-180 with SufficientStatistics::update
+// (Models/Glm/PosteriorSamplers/BinomialLogitAuxmixSampler.cpp:61-67) /
+// WeightedRegSuf::add_data (Models/Glm/WeightedRegressionModel.cpp:161-169) inside.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "draws.cuh"
+
+namespace boomgpu {
+
+enum Model : int { kLogit = 0, kPoisson = 1, kSupplied = 2 };
+
+struct RowData {
+  const double *X;
+  int64_t ldx;
+  int64_t n;
+  int p;
+  const double *y;         // logit: successes
+  const double *ntrials;   // logit
+  const int64_t *yi;       // poisson counts
+  const double *exposure;  // poisson
+  const double *w_in;      // supplied latents (kSupplied)
+  const double *s_in;
+  uint64_t row_offset;
+};
+
+struct RowOut {           // optional per-row outputs (test hooks); any may be null
+  double *w;              // weight  (logit: information;      poisson: w_int + w_ext)
+  double *s;              // weighted value (logit: sum;       poisson: w_int r_int + w_ext r_ext)
+  double *out6;
+  int32_t *k2;
+};
+
+struct DrawParams {
+  LogitMixture mix;
+  PoissonTable tab;
+  RngKey key;
+  int clt_threshold;
+};
+
+// ---- small helpers ------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One observation: draw (or read) the latent summary.  Returns weight / weighted value of the
+// single rank-1 update the row contributes, plus the scalar statistics WeightedRegSuf keeps.
+struct RowLatent { double w, s, yWy, sumlogw, count; };
+
+template <int MODEL>
+__device__ __forceinline__ RowLatent impute_row(const RowData &d, const DrawParams &prm, const RowOut &out,
+                                                int64_t i, double eta, int *err) {
+  RowLatent r;
+  r.w = r.s = r.yWy = r.sumlogw = 0; r.count = 1;
+  if (MODEL == kLogit) {
+    double sum, info;
+    bool ok = logit_impute(prm.mix, prm.clt_threshold, d.ntrials[i], d.y[i], eta, prm.key, d.row_offset + (uint64_t)i,
+                           sum, info);
+    if (!ok) { atomicOr(err, 2); sum = 0; info = 0; }
+    r.w = info; r.s = sum;
+  } else if (MODEL == kPoisson) {
+    PoissonLatent o;
+    int rc = poisson_impute(prm.tab, d.yi[i], d.exposure[i], eta, prm.key, d.row_offset + (uint64_t)i, o);
+    if (rc) {
+      atomicOr(err, rc == 1 ? 1 : 2);
+    } else {
+      double re = o.z_ext - o.mu_ext;
+      r.w = o.w_ext; r.s = o.w_ext * re; r.yWy = o.w_ext * re * re; r.sumlogw = log(o.w_ext);
+      if (d.yi[i] > 0) {
+        double ri = o.z_int - o.mu_int;
+        r.w += o.w_int; r.s += o.w_int * ri; r.yWy += o.w_int * ri * ri; r.sumlogw += log(o.w_int);
+        r.count = 2;
+      }
+      if (out.out6) {
+        double *q = out.out6 + 6 * i;
+        q[0] = o.z_int; q[1] = o.mu_int; q[2] = o.w_int; q[3] = o.z_ext; q[4] = o.mu_ext; q[5] = o.w_ext;
+      }
+      if (out.k2) { out.k2[2 * i] = o.k_int; out.k2[2 * i + 1] = o.k_ext; }
+    }
+  } else {
+    r.w = d.w_in[i]; r.s = d.s_in[i];
+  }
+  if (out.w) out.w[i] = r.w;
+  if (out.s) out.s[i] = r.s;
+  return r;
+}
+
+// =============================================================================================
+// Fused single-pass kernel, p <= 64.
+//   NB  = ceil(p / 8) column blocks (8 x 8 DMMA atoms), NA = NB (NB+1) / 2 upper atoms per warp.
+//   R   = rows per chunk (256 when NB <= 4, else 128); thread r < R draws row r of the chunk.
+// Shared memory row stride LDS = 8 NB + 4 doubles: LDS = 4 (mod 8) makes the DMMA fragment loads
+// (4 rows x 8 columns per instruction) conflict free; the eta loop rotates its start column by
+// (r >> 2) & 3 to be conflict free with the same stride.
+// Per-CTA partial: [P8*P8 tile | P8 xty | 8 scalars], reduced by reduce_small_kernel.
+// =============================================================================================
+constexpr int kSmallThreads = 256;
+__host__ __device__ constexpr int small_rows(int nb) { return nb <= 4 ? 256 : 128; }
+__host__ __device__ constexpr int small_lds(int nb) { return 8 * nb + 4; }
+__host__ __device__ constexpr size_t small_smem_bytes(int nb) {
+  return sizeof(double) * (2 * (size_t)small_rows(nb) * small_lds(nb) + 2 * small_rows(nb) + 8 * nb + 64);
+}
+__host__ __device__ constexpr int64_t small_partial_len(int nb) { return 64 * nb * nb + 8 * nb + 8; }
+
+template <int NB, int MODEL>
+__global__ void __launch_bounds__(kSmallThreads, (NB <= 3) ? 2 : 1)
+fused_small_kernel(RowData d, DrawParams prm, RowOut out, const double *__restrict__ beta, double *__restrict__ partials,
+                   int *err, uint32_t div_magic, int vec2) {
+  constexpr int R = small_rows(NB);
+  constexpr int LDS = small_lds(NB);
+  constexpr int P8 = 8 * NB;
+  constexpr int NA = NB * (NB + 1) / 2;
+  constexpr int RW = R / 8;  // rows per warp in the SYRK phase
+  extern __shared__ __align__(128) double smem[];
+  double *xs0 = smem;
+  double *xs1 = smem + R * LDS;
+  double *w_s = smem + 2 * R * LDS;
+  double *s_s = w_s + R;
+  double *beta_s = s_s + R;
+  double *red_s = beta_s + P8;  // 64 doubles of scratch
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int p = d.p;
+  const int64_t nchunks = (d.n + R - 1) / R;
+
+  // zero both stages once (pad columns are never written by the copies) and stage beta
+  for (int e = tid; e < 2 * R * LDS; e += kSmallThreads) smem[e] = 0.0;
+  if (tid < P8) beta_s[tid] = tid < p ? beta[tid] : 0.0;
+  __syncthreads();
+
+  auto load_chunk = [&](int64_t chunk, double *xs) {
+    const int64_t row0 = chunk * R;
+    const int64_t valid_rows = min((int64_t)R, d.n - row0);
+    const double *src0 = d.X + row0 * d.ldx;
+    if (vec2) {
+      const int total = R * p / 2;
+      for (int q = tid; q < total; q += kSmallThreads) {
+        int e = 2 * q;
+        int i = __umulhi((uint32_t)e, div_magic);
+        int j = e - i * p;
+        double *dst = xs + i * LDS + j;
+        if (i < valid_rows) cp_async16(dst, src0 + (int64_t)i * d.ldx + j);
+        else { dst[0] = 0.0; dst[1] = 0.0; }
+      }
+    } else {
+      const int total = R * p;
+      for (int e = tid; e < total; e += kSmallThreads) {
+        int i = __umulhi((uint32_t)e, div_magic);
+        int j = e - i * p;
+        double *dst = xs + i * LDS + j;
+        if (i < valid_rows) cp_async8(dst, src0 + (int64_t)i * d.ldx + j);
+        else dst[0] = 0.0;
+      }
+    }
+    cp_async_commit();
+  };
+
+  double c[NA][2];
+#pragma unroll
+  for (int a = 0; a < NA; ++a) { c[a][0] = 0.0; c[a][1] = 0.0; }
+  double xty_acc = 0.0;
+  double sc_count = 0, sc_ywy = 0, sc_sumw = 0, sc_sumlogw = 0;
+
+  // xty mapping: thread -> (column j, row group g)
+  constexpr int G = kSmallThreads / P8;
+  const int xj = tid % P8, xg = tid / P8;
+
+  int64_t chunk = blockIdx.x;
+  int stage = 0;
+  if (chunk < nchunks) load_chunk(chunk, xs0);
+  for (; chunk < nchunks; chunk += gridDim.x) {
+    double *xs = stage ? xs1 : xs0;
+    cp_async_wait_all();
+    __syncthreads();
+    if (chunk + gridDim.x < nchunks) load_chunk(chunk + gridDim.x, stage ? xs0 : xs1);
+
+    // ---- draw phase: thread r owns row r of the chunk
+    if (tid < R) {
+      const int64_t i = chunk * R + tid;
+      double wv = 0, sv = 0;
+      if (i < d.n) {
+        const double *xr = xs + tid * LDS;
+        const int rot = (tid >> 2) & 3;
+        double eta = 0;
+#pragma unroll 8
+        for (int j = 0; j < P8; ++j) {
+          int jj = j + rot;
+          jj = jj >= P8 ? jj - P8 : jj;
+          eta = fma(xr[jj], beta_s[jj], eta);
+        }
+        RowLatent r = impute_row<MODEL>(d, prm, out, i, eta, err);
+        wv = r.w; sv = r.s;
+        sc_count += r.count; sc_ywy += r.yWy; sc_sumw += r.w; sc_sumlogw += r.sumlogw;
+      }
+      w_s[tid] = wv;
+      s_s[tid] = sv;
+    }
+    __syncthreads();
+
+    // ---- weighted SYRK on DMMA: warp wid owns rows [wid*RW, wid*RW + RW) of the chunk
+#pragma unroll 2
+    for (int kk = 0; kk < RW / 4; ++kk) {
+      const int row = wid * RW + kk * 4 + (lane & 3);
+      const double wv = w_s[row];
+      const double *xr = xs + row * LDS + (lane >> 2);
+      double xa[NB], xw[NB];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) { xa[b] = xr[8 * b]; xw[b] = xa[b] * wv; }
+      int a = 0;
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < NB; ++bj) { dmma884(c[a][0], c[a][1], xw[bi], xa[bj]); ++a; }
+    }
+    // ---- X's: thread (xj, xg) sums rows xg, xg+G, ...
+    if (xg < G) {
+#pragma unroll 4
+      for (int r = xg; r < R; r += G) xty_acc = fma(s_s[r], xs[r * LDS + xj], xty_acc);
+    }
+    stage ^= 1;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- CTA reduction in a fixed order (deterministic), then one partial per CTA
+  double *tile = smem;  // P8*P8 doubles, reuse stage memory
+  for (int e = tid; e < P8 * P8; e += kSmallThreads) tile[e] = 0.0;
+  double *xty_s = smem + P8 * P8;  // G * P8 doubles
+  if (xg < G) xty_s[xg * P8 + xj] = xty_acc;
+  __syncthreads();
+  for (int w = 0; w < 8; ++w) {
+    if (wid == w) {
+      int a = 0;
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < NB; ++bj) {
+          double *t = tile + (8 * bi + (lane >> 2)) * P8 + 8 * bj + 2 * (lane & 3);
+          t[0] += c[a][0];
+          t[1] += c[a][1];
+          ++a;
+        }
+    }
+    __syncthreads();
+  }
+  double *my = partials + (int64_t)blockIdx.x * small_partial_len(NB);
+  for (int e = tid; e < P8 * P8; e += kSmallThreads) my[e] = tile[e];
+  if (tid < P8) {
+    double s = 0;
+    for (int g = 0; g < G; ++g) s += xty_s[g * P8 + tid];
+    my[P8 * P8 + tid] = s;
+  }
+  // scalars: warp shuffle then the 8 warp values in order
+  double v0 = warp_sum(sc_count), v1 = warp_sum(sc_ywy), v2 = warp_sum(sc_sumw), v3 = warp_sum(sc_sumlogw);
+  if (lane == 0) { red_s[wid * 4 + 0] = v0; red_s[wid * 4 + 1] = v1; red_s[wid * 4 + 2] = v2; red_s[wid * 4 + 3] = v3; }
+  __syncthreads();
+  if (tid < 4) {
+    double s = 0;
+    for (int w = 0; w < 8; ++w) s += red_s[w * 4 + tid];
+    my[P8 * P8 + P8 + tid] = s;
+  }
+}
+
+// suf layout: [p*p | p | 4]; sums the per-CTA partials in CTA order and writes BOTH triangles.
+__global__ void reduce_small_kernel(const double *__restrict__ partials, int nparts, int nb, int p, double *__restrict__ suf) {
+  const int P8 = 8 * nb;
+  const int64_t plen = small_partial_len(nb);
+  const int total = p * p + p + 4;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    int64_t src;
+    bool skip = false;
+    int a = 0, b = 0;
+    if (e < p * p) {
+      a = e / p; b = e - a * p;
+      if (a > b) skip = true;
+      src = (int64_t)a * P8 + b;
+    } else {
+      src = (int64_t)P8 * P8 + (e - p * p < p ? (e - p * p) : P8 + (e - p * p - p));
+    }
+    if (skip) continue;
+    double s = 0;
+    for (int c = 0; c < nparts; ++c) s += partials[c * plen + src];
+    if (e < p * p) {
+      suf[a + (int64_t)b * p] = s;
+      suf[b + (int64_t)a * p] = s;
+    } else {
+      suf[e] = s;
+    }
+  }
+}
+
+// =============================================================================================
+// Pass 1 for p > 64: a warp owns 32 consecutive rows; eta by a warp-cooperative dot product
+// with coalesced 16-byte loads, then lane r draws row r.  Writes w_i and s_i (n doubles each)
+// and per-CTA scalar partials.
+// =============================================================================================
+constexpr int kImputeThreads = 256;
+
+template <int MODEL, bool VEC2>
+__global__ void __launch_bounds__(kImputeThreads)
+impute_rows_kernel(RowData d, DrawParams prm, RowOut out, const double *__restrict__ beta, double *__restrict__ w_buf,
+                   double *__restrict__ s_buf, double *__restrict__ scalar_partials, int *err) {
+  extern __shared__ __align__(128) double smem[];
+  double *beta_s = smem;  // p (+1) doubles
+  __shared__ double red_s[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int p = d.p;
+  for (int j = tid; j < p + 1; j += kImputeThreads) beta_s[j] = j < p ? beta[j] : 0.0;
+  __syncthreads();
+
+  double sc_count = 0, sc_ywy = 0, sc_sumw = 0, sc_sumlogw = 0;
+  const int64_t ngroups = (d.n + 31) / 32;
+  const int warps_per_grid = gridDim.x * (kImputeThreads / 32);
+  for (int64_t g = (int64_t)blockIdx.x * (kImputeThreads / 32) + wid; g < ngroups; g += warps_per_grid) {
+    const int64_t row0 = g * 32;
+    double my_eta = 0;
+    const int nrows = (int)min((int64_t)32, d.n - row0);
+    for (int r0 = 0; r0 < nrows; r0 += 4) {
+      double acc[4] = {0, 0, 0, 0};
+      const double *xr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xr[u] = d.X + (row0 + min(r0 + u, nrows - 1)) * d.ldx;  // clamped rows are discarded
+      if (VEC2) {
+        const double2 *b2 = reinterpret_cast<const double2 *>(beta_s);
+        const int p2 = p >> 1;
+#pragma unroll 2
+        for (int j = lane; j < p2; j += 32) {
+          double2 xv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) xv[u] = __ldg(reinterpret_cast<const double2 *>(xr[u]) + j);
+          const double2 bv = b2[j];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { acc[u] = fma(xv[u].x, bv.x, acc[u]); acc[u] = fma(xv[u].y, bv.y, acc[u]); }
+        }
+        if ((p & 1) && lane == 0) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = fma(__ldg(xr[u] + p - 1), beta_s[p - 1], acc[u]);
+        }
+      } else {
+#pragma unroll 2
+        for (int j = lane; j < p; j += 32) {
+          const double bv = beta_s[j];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = fma(__ldg(xr[u] + j), bv, acc[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        double e = warp_sum(acc[u]);
+        if (lane == r0 + u) my_eta = e;
+      }
+    }
+    const int64_t i = row0 + lane;
+    double wv = 0, sv = 0;
+    if (i < d.n) {
+      RowLatent r = impute_row<MODEL>(d, prm, out, i, my_eta, err);
+      wv = r.w; sv = r.s;
+      sc_count += r.count; sc_ywy += r.yWy; sc_sumw += r.w; sc_sumlogw += r.sumlogw;
+      w_buf[i] = wv;
+      s_buf[i] = sv;
+    }
+  }
+  double v0 = warp_sum(sc_count), v1 = warp_sum(sc_ywy), v2 = warp_sum(sc_sumw), v3 = warp_sum(sc_sumlogw);
+  if (lane == 0) { red_s[wid * 4 + 0] = v0; red_s[wid * 4 + 1] = v1; red_s[wid * 4 + 2] = v2; red_s[wid * 4 + 3] = v3; }
+  __syncthreads();
+  if (tid < 4) {
+    double s = 0;
+    for (int w = 0; w < kImputeThreads / 32; ++w) s += red_s[w * 4 + tid];
+    scalar_partials[(int64_t)blockIdx.x * 4 + tid] = s;
+  }
+}
+
+// =============================================================================================
+// Pass 2 for p > 64: split-K weighted SYRK on FP64 DMMA.
+//
+//   Output regions are 128 x 128 blocks (I <= J) of the upper triangle; a region is cut into
+//   32 x 32 "units" of 4 x 4 DMMA atoms.  A CTA = 8 warps (two units each; warp 0 also issues the
+//   TMA copies) and handles one (k-slice, region) pair: its rows are streamed through a 4-stage ring of
+//   KB = 16 row tiles written by TMA bulk copies (one 1-D cp.async.bulk per row and panel, row
+//   stride 132 doubles = 4 (mod 8), so fragment loads are conflict free), full/empty mbarriers.
+//   Diagonal regions only compute the 10 units on or above the diagonal (and the diagonal units
+//   skip their 6 lower atoms) and also produce X's for their 128 columns: one extra DMMA per
+//   A fragment with B = [s, 0, ..., 0].
+//   Per-CTA partial: 128 x 128 tile (+ 128 xty for diagonal regions), reduced by
+//   reduce_syrk_kernel in k-slice order (deterministic).
+// =============================================================================================
+constexpr int kSyrkConsumerWarps = 8;
+constexpr int kSyrkThreads = 32 * kSyrkConsumerWarps;
+constexpr int kSyrkKB = 16;        // rows per stage
+constexpr int kSyrkStages = 4;
+constexpr int kSyrkPanelLd = 132;  // doubles
+constexpr int kSyrkStageDoubles = 2 * kSyrkKB * kSyrkPanelLd + 2 * kSyrkKB;  // panels A, B, then w[KB], s[KB]
+constexpr size_t kSyrkSmemBytes = sizeof(double) * kSyrkStages * kSyrkStageDoubles + 8 * 2 * kSyrkStages + 64;
+constexpr int64_t kSyrkTileLen = 128 * 128 + 128;
+
+struct SyrkUnit { int8_t ui, uj, flags; };  // flags: 1 valid, 2 diagonal unit, 4 xty duty, 8 xty duty when unit (ui, ui+1) is cut off by p
+struct SyrkUnitTable { SyrkUnit u[2][kSyrkConsumerWarps][2]; };  // [region type: 0 off-diagonal, 1 diagonal]
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct SyrkParams {
+  const double *X;
+  int64_t ldx;
+  int64_t n;
+  int p;
+  const double *w;   // n rounded up to kSyrkKB, zero padded
+  const double *s;
+  int nblk;          // ceil(p / 128)
+  int nregions;      // nblk (nblk + 1) / 2
+  int ksplit;
+  int64_t rows_per_slice;  // multiple of kSyrkKB
+  double *partials;  // [ksplit][nregions][kSyrkTileLen]
+};
+
+__device__ __forceinline__ void region_to_blocks(int region, int nblk, int &I, int &J) {
+  // regions enumerated row by row over the upper triangle: (0,0),(0,1)...(0,nblk-1),(1,1),...
+  int i = 0, rem = region;
+  while (rem >= nblk - i) { rem -= nblk - i; ++i; }
+  I = i; J = i + rem;
+}
+
+__global__ void __launch_bounds__(kSyrkThreads, 1) syrk_dmma_kernel(SyrkParams prm, SyrkUnitTable table) {
+  extern __shared__ __align__(128) double smem[];
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kSyrkStages * kSyrkStageDoubles);
+  uint64_t *empty_bar = full_bar + kSyrkStages;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int kslice = blockIdx.x / prm.nregions;
+  const int region = blockIdx.x - kslice * prm.nregions;
+  int I, J;
+  region_to_blocks(region, prm.nblk, I, J);
+  const bool diag = (I == J);
+  const int64_t row_begin = (int64_t)kslice * prm.rows_per_slice;
+  const int64_t row_end = min(prm.n, row_begin + prm.rows_per_slice);
+  const int nstages_total = row_end > row_begin ? (int)((row_end - row_begin + kSyrkKB - 1) / kSyrkKB) : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < kSyrkStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, kSyrkConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  // valid columns of each panel (bytes to copy); X rows are ldx doubles apart and ldx is even
+  const int colsA = min(128, (int)min((int64_t)prm.ldx, (int64_t)((prm.p + 7) & ~7)) - 128 * I);
+  const int colsB = min(128, (int)min((int64_t)prm.ldx, (int64_t)((prm.p + 7) & ~7)) - 128 * J);
+
+  // ===== producer role (warp 0): lanes 0..15 copy the rows of panel A, lanes 16..31 those of panel B
+  const uint32_t bytesA = (uint32_t)colsA * 8, bytesB = diag ? 0u : (uint32_t)colsB * 8;
+  const uint32_t stage_bytes = kSyrkKB * (bytesA + bytesB) + 2 * kSyrkKB * 8;
+  auto produce = [&](int it) {
+    const int s = it % kSyrkStages;
+    const uint32_t phase = (it / kSyrkStages) & 1;
+    mbar_wait(empty_bar + s, phase ^ 1);
+    double *stage = smem + s * kSyrkStageDoubles;
+    const int64_t r0 = row_begin + (int64_t)it * kSyrkKB;
+    if (lane == 0) mbar_expect_tx(full_bar + s, stage_bytes);
+    __syncwarp();
+    const int rr = lane & 15;
+    const int64_t row = min(r0 + rr, prm.n - 1);  // clamp: padded rows carry w = 0
+    if (lane < 16) {
+      tma_bulk_g2s(stage + rr * kSyrkPanelLd, prm.X + row * prm.ldx + 128 * I, bytesA, full_bar + s);
+    } else if (!diag) {
+      tma_bulk_g2s(stage + (kSyrkKB + rr) * kSyrkPanelLd, prm.X + row * prm.ldx + 128 * J, bytesB, full_bar + s);
+    }
+    if (lane == 0) {
+      tma_bulk_g2s(stage + 2 * kSyrkKB * kSyrkPanelLd, prm.w + r0, kSyrkKB * 8, full_bar + s);
+      tma_bulk_g2s(stage + 2 * kSyrkKB * kSyrkPanelLd + kSyrkKB, prm.s + r0, kSyrkKB * 8, full_bar + s);
+    }
+  };
+  if (wid == 0) {
+    for (int it = 0; it < kSyrkStages - 1 && it < nstages_total; ++it) produce(it);
+  }
+
+  // ===== consumer warps
+  const SyrkUnit u0 = table.u[diag ? 1 : 0][wid][0];
+  const SyrkUnit u1 = table.u[diag ? 1 : 0][wid][1];
+  double c0[4][4][2], c1[4][4][2], cx[4][2];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { c0[m][n][0] = c0[m][n][1] = 0.0; c1[m][n][0] = c1[m][n][1] = 0.0; }
+    cx[m][0] = cx[m][1] = 0.0;
+  }
+  // units (and atoms) entirely beyond the last 8-column block of X are skipped
+  const int P8 = (prm.p + 7) & ~7;
+  const int mmax0 = min(4, (P8 - 128 * I - 32 * u0.ui + 7) / 8), nmax0 = min(4, (P8 - 128 * J - 32 * u0.uj + 7) / 8);
+  const int mmax1 = min(4, (P8 - 128 * I - 32 * u1.ui + 7) / 8), nmax1 = min(4, (P8 - 128 * J - 32 * u1.uj + 7) / 8);
+  const bool v0 = (u0.flags & 1) && mmax0 > 0 && nmax0 > 0, v1 = (u1.flags & 1) && mmax1 > 0 && nmax1 > 0;
+  const bool d0 = u0.flags & 2, d1 = u1.flags & 2;
+  // X's for row block ui: normally the full unit (ui, ui+1) carries it; when p cuts that unit off, the diagonal unit does
+  const bool duty0 = v0 && ((u0.flags & 4) || ((u0.flags & 8) && P8 - 128 * I - 32 * (u0.ui + 1) <= 0));
+  const bool duty1 = v1 && ((u1.flags & 4) || ((u1.flags & 8) && P8 - 128 * I - 32 * (u1.ui + 1) <= 0));
+  const int panelB_off = diag ? 0 : kSyrkKB * kSyrkPanelLd;
+  const int a0_off = 32 * u0.ui + (lane >> 2), b0_off = panelB_off + 32 * u0.uj + (lane >> 2);
+  const int a1_off = 32 * u1.ui + (lane >> 2), b1_off = panelB_off + 32 * u1.uj + (lane >> 2);
+  const bool same_a = v0 && v1 && (u0.ui == u1.ui);
+
+  for (int it = 0; it < nstages_total; ++it) {
+    const int s = it % kSyrkStages;
+    const uint32_t phase = (it / kSyrkStages) & 1;
+    // refill the stage consumed in the previous iteration (its empty barrier needs all 8 warps)
+    if (wid == 0 && it + kSyrkStages - 1 < nstages_total) produce(it + kSyrkStages - 1);
+    mbar_wait(full_bar + s, phase);
+    const double *stage = smem + s * kSyrkStageDoubles;
+    const double *w_s = stage + 2 * kSyrkKB * kSyrkPanelLd;
+    const double *s_s = w_s + kSyrkKB;
+#pragma unroll
+    for (int kk = 0; kk < kSyrkKB / 4; ++kk) {
+      const int row = kk * 4 + (lane & 3);
+      const double wv = w_s[row];
+      const double *xr = stage + row * kSyrkPanelLd;
+      double a[4], aw[4], b[4];
+      if (v0) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { a[m] = xr[a0_off + 8 * m]; aw[m] = a[m] * wv; b[m] = xr[b0_off + 8 * m]; }
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+            if ((!d0 || n >= m) && m < mmax0 && n < nmax0) dmma884(c0[m][n][0], c0[m][n][1], aw[m], b[n]);
+        if (duty0) {
+          const double sv = (lane >> 2) == 0 ? s_s[row] : 0.0;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) if (m < mmax0) dmma884(cx[m][0], cx[m][1], a[m], sv);
+        }
+      }
+      if (v1) {
+        if (!same_a) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) { a[m] = xr[a1_off + 8 * m]; aw[m] = a[m] * wv; }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) b[m] = xr[b1_off + 8 * m];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+            if ((!d1 || n >= m) && m < mmax1 && n < nmax1) dmma884(c1[m][n][0], c1[m][n][1], aw[m], b[n]);
+        if (duty1) {
+          const double sv = (lane >> 2) == 0 ? s_s[row] : 0.0;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) if (m < mmax1) dmma884(cx[m][0], cx[m][1], a[m], sv);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar + s);
+  }
+
+  // ===== epilogue: fragments -> this CTA's partial tile (row major 128 x 128, then 128 xty)
+  double *tile = prm.partials + ((int64_t)kslice * prm.nregions + region) * kSyrkTileLen;
+  auto store_unit = [&](const SyrkUnit &u, double (&cc)[4][4][2], bool dg, int mmax, int nmax) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        if ((dg && n < m) || m >= mmax || n >= nmax) continue;
+        const int r = 32 * u.ui + 8 * m + (lane >> 2);
+        const int cidx = 32 * u.uj + 8 * n + 2 * (lane & 3);
+        *reinterpret_cast<double2 *>(tile + r * 128 + cidx) = make_double2(cc[m][n][0], cc[m][n][1]);
+      }
+  };
+  if (v0) store_unit(u0, c0, d0, mmax0, nmax0);
+  if (v1) store_unit(u1, c1, d1, mmax1, nmax1);
+  if ((duty0 && v0) || (duty1 && v1)) {
+    const int ui = (duty0 && v0) ? u0.ui : u1.ui;
+    const int mmax = (duty0 && v0) ? mmax0 : mmax1;
+    if ((lane & 3) == 0) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+        if (m < mmax) tile[128 * 128 + 32 * ui + 8 * m + (lane >> 2)] = cx[m][0];
+    }
+  }
+}
+
+// Sums partial tiles over k-slices (fixed order) into the p x p matrix (both triangles) and xty.
+__global__ void reduce_syrk_kernel(SyrkParams prm, double *__restrict__ suf) {
+  const int p = prm.p;
+  const int64_t total = (int64_t)prm.nregions * kSyrkTileLen;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int region = (int)(e / kSyrkTileLen);
+    const int t = (int)(e - (int64_t)region * kSyrkTileLen);
+    int I, J;
+    region_to_blocks(region, prm.nblk, I, J);
+    int a, b = 0;
+    bool is_xty = t >= 128 * 128;
+    if (is_xty) {
+      if (I != J) continue;
+      a = 128 * I + (t - 128 * 128);
+      if (a >= p) continue;
+    } else {
+      a = 128 * I + t / 128;
+      b = 128 * J + t % 128;
+      if (a >= p || b >= p || a > b) continue;
+    }
+    double sum = 0;
+    for (int k = 0; k < prm.ksplit; ++k) sum += prm.partials[((int64_t)k * prm.nregions + region) * kSyrkTileLen + t];
+    if (is_xty) {
+      suf[(int64_t)p * p + a] = sum;
+    } else {
+      suf[a + (int64_t)b * p] = sum;
+      suf[b + (int64_t)a * p] = sum;
+    }
+  }
+}
+
+// sums per-CTA scalar partials (4 per CTA) into suf[p*p+p .. +4)
+__global__ void reduce_scalars_kernel(const double *__restrict__ partials, int nparts, double *__restrict__ dst) {
+  if (threadIdx.x < 4) {
+    double s = 0;
+    for (int c = 0; c < nparts; ++c) s += partials[(int64_t)c * 4 + threadIdx.x];
+    dst[threadIdx.x] = s;
+  }
+}
+
+// =============================================================================================
+// Log likelihood (value only): warp per row, block partials, fixed-order final sum.
+// =============================================================================================
+template <int MODEL>
+__global__ void __launch_bounds__(256) loglike_kernel(RowData d, const double *__restrict__ beta, double *__restrict__ partials) {
+  extern __shared__ __align__(128) double smem[];
+  double *beta_s = smem;
+  __shared__ double red_s[8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int j = tid; j < d.p; j += 256) beta_s[j] = beta[j];
+  __syncthreads();
+  double acc = 0;
+  const int warps_per_grid = gridDim.x * 8;
+  for (int64_t i = (int64_t)blockIdx.x * 8 + wid; i < d.n; i += warps_per_grid) {
+    const double *xr = d.X + i * d.ldx;
+    double e = 0;
+    for (int j = lane; j < d.p; j += 32) e = fma(__ldg(xr + j), beta_s[j], e);
+    e = warp_sum(e);
+    if (lane == 0) {
+      if (MODEL == kLogit) acc += dbinom_log(d.y[i], d.ntrials[i], e);
+      else acc += dpois_log((double)d.yi[i], d.exposure[i] * exp(e));
+    }
+  }
+  if (lane == 0) red_s[wid] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0;
+    for (int w = 0; w < 8; ++w) s += red_s[w];
+    partials[blockIdx.x] = s;
+  }
+}
+
+__global__ void reduce_sum_kernel(const double *__restrict__ partials, int nparts, double *__restrict__ dst) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0;
+    for (int c = 0; c < nparts; ++c) s += partials[c];
+    dst[0] = s;
+  }
+}
+
+}  // namespace boomgpu

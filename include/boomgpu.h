@@ -1,0 +1,142 @@
+/*
+ * boomgpu.h -- C ABI of the B200-native auxiliary-mixture Gibbs hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int
+ * status (0 = ok) plus boomgpu_last_error().  The C++ sampler classes that keep
+ * BOOM's PosteriorSampler::draw() surface (boom_b200/host, boom_b200/boom_adapter)
+ * are the only intended callers; INTEGRATION.md shows the binding.
+ *
+ * What each entry point replaces in the reference (steve-the-bayesian/BOOM,
+ * paths relative to its root):
+ *
+ *   boomgpu_upload_binomial / _poisson
+ *       the AoS of heap objects behind IID_DataPolicy::dat()
+ *       (Models/Policies/IID_DataPolicy.hpp:43-58, Models/Glm/BinomialRegressionData.hpp:25-55,
+ *        Models/Glm/PoissonRegressionData.hpp:25-62) becomes one row-major matrix in HBM.
+ *   boomgpu_set_logit_mixture
+ *       BinomialLogitDataImputer::mixture_approximation
+ *       (Models/Glm/PosteriorSamplers/BinomialLogitDataImputer.hpp:51, NormalMixtureApproximation.cpp:416-424)
+ *   boomgpu_set_poisson_table
+ *       PoissonDataImputer::mixture_table_ (PoissonDataImputer.hpp:99, serialize format
+ *       NormalMixtureApproximation.cpp:393-399,534-542)
+ *   boomgpu_logit_step
+ *       LatentDataSampler::impute_latent_data for the logit samplers, i.e. the worker-pool loop
+ *       Models/PosteriorSamplers/Imputer.hpp:175-180 + Imputer.cpp:27-66 over
+ *       ImputeWorker::impute_latent_data_point (BinomialLogitAuxmixSampler.cpp:77-97):
+ *       GlmCoefs::predict (GlmCoefs.cpp:134-156), BinomialLogitCltDataImputer::impute
+ *       (BinomialLogitDataImputer.cpp:122-210) and SufficientStatistics::update/combine
+ *       (BinomialLogitAuxmixSampler.cpp:44-67).
+ *   boomgpu_poisson_step
+ *       the same framework over PoissonRegressionDataImputer::impute_latent_data_point
+ *       (PoissonRegressionAuxMixSampler.cpp:58-81): PoissonDataImputer::impute
+ *       (PoissonDataImputer.cpp:36-98) and WeightedRegSuf::add_data/combine
+ *       (Models/Glm/WeightedRegressionModel.cpp:69-87,161-169).
+ *   boomgpu_binomial_loglike / boomgpu_poisson_loglike
+ *       BinomialLogitModel::log_likelihood (Models/Glm/BinomialLogitModel.cpp:140-180),
+ *       PoissonRegressionModel::log_likelihood (Models/Glm/PoissonRegressionModel.cpp:56-95), value only.
+ *
+ * Threading: one host thread per context; a context is bound to one CUDA device.
+ * Multi-GPU = one context (one process) per GPU, rows sharded, the packed
+ * statistics of the *_step_device variants all-reduced by the caller (NCCL).
+ * Ownership: the caller owns every host buffer; the context owns device memory
+ * it allocated (uploaded data, workspaces) but NOT adopted device pointers.
+ * There is no CPU fallback: every compute entry point fails if CUDA fails.
+ */
+#ifndef BOOMGPU_H
+#define BOOMGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#pragma GCC visibility push(default)
+
+typedef struct boomgpu_ctx boomgpu_ctx;
+
+#define BOOMGPU_OK 0
+#define BOOMGPU_ERR_CUDA 1
+#define BOOMGPU_ERR_ARG 2
+#define BOOMGPU_ERR_STATE 3
+#define BOOMGPU_ERR_DATA 4 /* device-side input validation failed (y > n, NaN eta, nu missing from table ...) */
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int boomgpu_create(boomgpu_ctx **ctx, int device);
+void boomgpu_destroy(boomgpu_ctx *ctx);
+/* message of the last failing call on ctx (ctx == NULL: last failing boomgpu_create) */
+const char *boomgpu_last_error(const boomgpu_ctx *ctx);
+const char *boomgpu_version(void);
+
+/* cudaStream_t to launch on (default: a stream owned by the context). */
+int boomgpu_set_stream(boomgpu_ctx *ctx, void *cuda_stream);
+/* global index of this shard's first row: keys the Philox counters so draws do not depend on the sharding */
+int boomgpu_set_row_offset(boomgpu_ctx *ctx, uint64_t first_global_row);
+/* options: "path" = 0 auto | 1 fused single pass (p <= 64) | 2 two-pass imputer + DMMA SYRK;
+ *          "timing" = 1 records CUDA events around every kernel (boomgpu_get_timings) */
+int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value);
+
+/* ---- data ---------------------------------------------------------------------------- */
+/* host -> device; X row major, n x p, leading dimension ldx >= p */
+int boomgpu_upload_binomial(boomgpu_ctx *ctx, int64_t n, int p, const double *X, int64_t ldx,
+                            const double *y, const double *ntrials);
+int boomgpu_upload_poisson(boomgpu_ctx *ctx, int64_t n, int p, const double *X, int64_t ldx,
+                           const int64_t *y, const double *exposure);
+/* data already resident in HBM (device pointers; caller keeps them alive) */
+int boomgpu_adopt_binomial(boomgpu_ctx *ctx, int64_t n, int p, const double *dX, int64_t ldx,
+                           const double *dy, const double *dntrials);
+int boomgpu_adopt_poisson(boomgpu_ctx *ctx, int64_t n, int p, const double *dX, int64_t ldx,
+                          const int64_t *dy, const double *dexposure);
+
+int boomgpu_set_logit_mixture(boomgpu_ctx *ctx, int K, const double *mu, const double *sigma,
+                              const double *weights);
+/* ntab entries sorted by nu; entry e owns components offset[e] .. offset[e+1]-1 of the flat arrays */
+int boomgpu_set_poisson_table(boomgpu_ctx *ctx, int ntab, const int64_t *nu, const int32_t *offset,
+                              const double *weights, const double *mu, const double *sigma,
+                              int64_t gaussian_cutoff);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+/* One imputation pass.  xtx: p x p (symmetric, both triangles filled), xty: p.  Synchronous. */
+int boomgpu_logit_step(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed,
+                       uint64_t iteration, double *xtx, double *xty, int64_t *sample_size);
+/* scalars = {n, y'Wy, sum w, sum log w} as WeightedRegSuf keeps them */
+int boomgpu_poisson_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration,
+                         double *xtwx, double *xtwy, double scalars[4]);
+
+/* Asynchronous variants: the packed statistics stay in HBM at suf_dev (device pointer,
+ * boomgpu_suf_len(p) doubles: [p*p matrix | p vector | 4 scalars]; logit scalars = {sample_size,0,0,0}),
+ * ready for an in-place all-reduce on the same stream.  beta is a HOST pointer. */
+int64_t boomgpu_suf_len(int p);
+int boomgpu_logit_step_device(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed,
+                              uint64_t iteration, double *suf_dev);
+int boomgpu_poisson_step_device(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration,
+                                double *suf_dev);
+/* waits for the context's stream and reports device-side validation errors of the steps since the last call */
+int boomgpu_synchronize(boomgpu_ctx *ctx);
+
+/* ---- parity / test hooks --------------------------------------------------------------- */
+/* deterministic accumulation from caller supplied latents (host arrays of length n) */
+int boomgpu_accumulate(boomgpu_ctx *ctx, const double *weight, const double *weighted_value,
+                       double *xtx, double *xty);
+/* per-row latent draws without accumulation: sum_out/info_out host arrays of length n */
+int boomgpu_logit_draw(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed,
+                       uint64_t iteration, double *sum_out, double *info_out);
+/* out6 (n x 6) = {z_int, mu_int, w_int, z_ext, mu_ext, w_ext}; kout2 (n x 2, may be NULL) component indices */
+int boomgpu_poisson_draw(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration,
+                         double *out6, int32_t *kout2);
+int boomgpu_binomial_loglike(boomgpu_ctx *ctx, const double *beta, double *loglike);
+int boomgpu_poisson_loglike(boomgpu_ctx *ctx, const double *beta, double *loglike);
+
+/* ---- instrumentation ------------------------------------------------------------------- */
+/* number of kernels this context has launched so far */
+int64_t boomgpu_kernel_launches(const boomgpu_ctx *ctx);
+/* with option "timing" = 1: accumulated CUDA-event milliseconds and launch counts per kernel class
+ * since the last reset; classes: 0 fused small-p, 1 imputer pass, 2 DMMA SYRK, 3 reductions, 4 other */
+#define BOOMGPU_NUM_KERNEL_CLASSES 5
+int boomgpu_get_timings(boomgpu_ctx *ctx, double ms[BOOMGPU_NUM_KERNEL_CLASSES],
+                        int64_t launches[BOOMGPU_NUM_KERNEL_CLASSES], int reset);
+
+#pragma GCC visibility pop
+#ifdef __cplusplus
+}
+#endif
+#endif

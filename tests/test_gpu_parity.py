@@ -1,0 +1,189 @@
+"""GPU parity tests proper: the CUDA path, driven through the C ABI (include/boomgpu.h),
+against the C oracle on the same seeded inputs.  Tolerances (BASELINE.json north_star):
+deterministic statistics 1e-12 (normwise for X'WX), mixture-indicator counting exact.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.helpers import logit_ctx, normwise_err, poisson_ctx, vec_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def _latents(n, seed):
+    rng = np.random.default_rng(seed)
+    return 0.05 + 1.5 * rng.random(n), 6.0 * (rng.random(n) - 0.5)
+
+
+# ---------------------------------------------------------------- deterministic accumulation
+@pytest.mark.parametrize("n,p,path", [
+    (1, 3, 0), (37, 5, 0), (1000, 16, 0), (5003, 20, 0), (777, 33, 0), (2049, 50, 0), (1500, 64, 0), (300, 7, 0),
+    (1000, 16, 2), (37, 5, 2), (4097, 50, 2), (3000, 100, 0), (2500, 128, 0), (2100, 130, 0), (5000, 260, 0),
+    (6000, 500, 0), (1, 200, 0), (15, 129, 0),
+])
+def test_accumulate_matches_oracle(n, p, path):
+    X = O.synth_x(n, p, seed=100 + p)
+    w, s = _latents(n, p)
+    ctx, _ = logit_ctx(X, np.zeros(n), np.ones(n), path=path)
+    xtx, xty = ctx.accumulate(w, s)
+    ref_xtx, ref_xty = O.accumulate(X, w, s)
+    assert normwise_err(xtx, ref_xtx) < TOL
+    assert vec_err(xty, ref_xty) < TOL
+    np.testing.assert_array_equal(xtx, xtx.T)   # both triangles filled, exactly symmetric
+    ctx.close()
+
+
+def test_accumulate_golden_fixture(golden):
+    g = golden("suf.json")
+    n, p = int(g["n"]), int(g["p"])
+    X = np.array(g["X"]).reshape(n, p)
+    ctx, _ = logit_ctx(X, np.zeros(n), np.ones(n))
+    xtx, xty = ctx.accumulate(g["weight"], g["weighted_value"])
+    ref = np.array(g["xtx_colmajor"]).reshape(p, p).T
+    assert normwise_err(xtx, ref) < TOL and vec_err(xty, np.array(g["xty"])) < TOL
+    ctx.close()
+
+
+# ---------------------------------------------------------------- latent draws, value by value
+@pytest.mark.parametrize("n,p,max_trials,path", [(4000, 6, 1, 0), (3000, 20, 4, 0), (2000, 8, 40, 0), (1500, 70, 1, 0),
+                                                 (1200, 90, 30, 0)])
+def test_logit_draws_match_oracle(n, p, max_trials, path):
+    X, y, nt, beta_true = O.synth_binomial(n, p, 3, seed=11 + p, max_trials=max_trials)
+    beta = beta_true * 0.9 + 0.01
+    ctx, mix = logit_ctx(X, y, nt, path=path)
+    s, w = ctx.logit_draw(beta, 10, seed=99, iteration=3)
+    rs, rw = O.logit_draw(X, y, nt, beta, 10, mix, 99, 3)
+    # information = sum of 1/sigma_k^2 over the drawn indicators: any indicator mismatch shows here
+    np.testing.assert_allclose(w, rw, rtol=1e-13)
+    np.testing.assert_allclose(s, rs, rtol=1e-9, atol=1e-9)
+    ctx.close()
+
+
+def test_logit_indicator_counts_exact():
+    """Histogram of the mixture indicators (decoded from info = 1/sigma_k^2) is bit exact vs the oracle."""
+    n, p = 20000, 4
+    X, y, nt, beta = O.synth_binomial(n, p, 2, seed=5)
+    ctx, mix = logit_ctx(X, y, nt)
+    _, w = ctx.logit_draw(beta, 10, seed=1, iteration=0)
+    _, _, _, kc = O.logit_step(X, y, nt, beta, 10, mix, 1, 0)
+    inv = 1.0 / (mix.sigma * mix.sigma)
+    k_dev = np.argmin(np.abs(w[:, None] - inv[None, :]), axis=1)
+    assert np.array_equal(np.bincount(k_dev, minlength=9), kc)
+    ctx.close()
+
+
+def test_poisson_draws_match_oracle():
+    n, p = 5000, 6
+    X, y, ex, beta_true = O.synth_poisson(n, p, 3, seed=21)
+    y[:7] = [0, 1, 2, 40, 120, 299, 35000]      # table edges and the gaussian cutoff
+    ex[:4] = [0.5, 2.0, 1.5, 3.0]
+    ctx, tab = poisson_ctx(X, y, ex)
+    out, k2 = ctx.poisson_draw(beta_true, seed=8, iteration=2)
+    ref, rk2 = O.poisson_draw(X, y, ex, beta_true, tab, 8, 2)
+    assert np.array_equal(k2, rk2)
+    np.testing.assert_allclose(out, ref, rtol=1e-10, atol=1e-12)
+    ctx.close()
+
+
+# ---------------------------------------------------------------- whole steps
+@pytest.mark.parametrize("n,p,max_trials", [(3001, 20, 1), (2000, 16, 25), (2500, 50, 1), (2200, 100, 1), (2000, 200, 12)])
+def test_logit_step_matches_oracle(n, p, max_trials):
+    X, y, nt, beta = O.synth_binomial(n, p, 5, seed=31 + p, max_trials=max_trials)
+    ctx, mix = logit_ctx(X, y, nt)
+    xtx, xty, ss = ctx.logit_step(beta, 10, seed=77, iteration=5)
+    rxtx, rxty, rss, _ = O.logit_step(X, y, nt, beta, 10, mix, 77, 5)
+    assert ss == rss == n
+    assert normwise_err(xtx, rxtx) < 1e-11     # draws differ by libm-vs-CUDA ulps before the sum
+    assert vec_err(xty, rxty) < 1e-10
+    ctx.close()
+
+
+@pytest.mark.parametrize("n,p", [(3000, 5), (2500, 50), (2000, 80)])
+def test_poisson_step_matches_oracle(n, p):
+    X, y, ex, beta = O.synth_poisson(n, p, 3, seed=41 + p)
+    ctx, tab = poisson_ctx(X, y, ex)
+    xtx, xty, sc = ctx.poisson_step(beta, seed=13, iteration=1)
+    rxtx, rxty, rsc = O.poisson_step(X, y, ex, beta, tab, 13, 1)
+    assert sc[0] == rsc[0] == n + np.count_nonzero(y)
+    assert normwise_err(xtx, rxtx) < 1e-11
+    assert vec_err(xty, rxty) < 1e-10
+    np.testing.assert_allclose(sc, rsc, rtol=1e-10)
+    ctx.close()
+
+
+def test_steps_are_reproducible_and_iteration_keyed():
+    X, y, nt, beta = O.synth_binomial(5000, 12, 3, seed=3)
+    ctx, _ = logit_ctx(X, y, nt)
+    a = ctx.logit_step(beta, 10, 5, 9)
+    b = ctx.logit_step(beta, 10, 5, 9)
+    c = ctx.logit_step(beta, 10, 5, 10)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+    assert np.max(np.abs(a[1] - c[1])) > 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("p", [10, 150])
+def test_sharding_invariance(p):
+    """Rows split over two contexts with their global row offsets give the same statistics as one context."""
+    n = 4000
+    X, y, nt, beta = O.synth_binomial(n, p, 3, seed=17)
+    full, _ = logit_ctx(X, y, nt)
+    fx, fy, _ = full.logit_step(beta, 10, 123, 4)
+    cut = 1777
+    a, _ = logit_ctx(X[:cut], y[:cut], nt[:cut])
+    b, _ = logit_ctx(X[cut:], y[cut:], nt[cut:])
+    b.set_row_offset(cut)
+    ax, ay, an = a.logit_step(beta, 10, 123, 4)
+    bx, by, bn = b.logit_step(beta, 10, 123, 4)
+    assert an + bn == n
+    assert normwise_err(ax + bx, fx) < 1e-13 and vec_err(ay + by, fy) < 1e-12
+    for c in (full, a, b):
+        c.close()
+
+
+# ---------------------------------------------------------------- log likelihood
+def test_loglike_matches_oracle_and_golden(golden):
+    g = golden("loglike.json")
+    n, p = int(g["n"]), int(g["p"])
+    X = np.array(g["X"]).reshape(n, p)
+    ctx, _ = logit_ctx(X, g["y"], g["ntrials"])
+    assert ctx.binomial_loglike(g["beta"]) == pytest.approx(g["binomial_loglike"], rel=1e-12)
+    ctx.close()
+    Xp = np.array(g["poisson_X"]).reshape(n, p)
+    ctx, _ = poisson_ctx(Xp, g["poisson_y"], g["poisson_exposure"])
+    assert ctx.poisson_loglike(g["poisson_beta"]) == pytest.approx(g["poisson_loglike"], rel=1e-12)
+    ctx.close()
+    X, y, nt, beta = O.synth_binomial(20000, 30, 4, seed=2, max_trials=15)
+    ctx, _ = logit_ctx(X, y, nt)
+    assert ctx.binomial_loglike(beta) == pytest.approx(O.binomial_logit_loglike(X, y, nt, beta), rel=1e-12)
+    ctx.close()
+
+
+# ---------------------------------------------------------------- errors
+def test_invalid_data_is_reported():
+    import boom_b200
+    X, y, nt, beta = O.synth_binomial(500, 4, 2, seed=1)
+    y[100] = 3.0  # successes > trials
+    ctx, _ = logit_ctx(X, y, nt)
+    with pytest.raises(boom_b200.BoomGpuError, match="invalid observation"):
+        ctx.logit_step(beta, 10, 1, 0)
+    ctx.close()
+    Xp, yp, ex, bp = O.synth_poisson(500, 4, 2, seed=1)
+    yp[3] = 12345  # off-grid count that the fixture table does not hold
+    ctx, _ = poisson_ctx(Xp, yp, ex)
+    with pytest.raises(boom_b200.BoomGpuError, match="missing from the Poisson mixture table"):
+        ctx.poisson_step(bp, 1, 0)
+    ctx.close()
+
+
+def test_state_errors():
+    import boom_b200
+    ctx = boom_b200.Context(0)
+    with pytest.raises(boom_b200.BoomGpuError, match="no binomial data"):
+        ctx.p = 3
+        ctx.logit_step(np.zeros(3), 10, 1, 0)
+    ctx.close()
