@@ -160,7 +160,7 @@ SyrkUnitTable make_unit_table() {
   t.u[1][2][0] = {2, 3, (int8_t)(V | Y)};
   t.u[1][6][0] = {0, 3, V};
   t.u[1][3][0] = {1, 3, V};
-  t.u[1][7][0] = {3, 3, (int8_t)(V | D | Y)}; t.u[1][7][1] = {2, 2, (int8_t)(V | D | F)};
+  t.u[1][7][0] = {2, 2, (int8_t)(V | D | F)}; t.u[1][7][1] = {3, 3, (int8_t)(V | D | Y)};
   return t;
 }
 

@@ -403,8 +403,8 @@ impute_rows_kernel(RowData d, DrawParams prm, RowOut out, const double *__restri
 // Pass 2 for p > 64: split-K weighted SYRK on FP64 DMMA.
 //
 //   Output regions are 128 x 128 blocks (I <= J) of the upper triangle; a region is cut into
-//   32 x 32 "units" of 4 x 4 DMMA atoms.  A CTA = 8 warps (two units each; warp 0 also issues the
-//   TMA copies) and handles one (k-slice, region) pair: its rows are streamed through a 4-stage ring of
+//   32 x 32 "units" of 4 x 4 DMMA atoms.  A CTA = 8 consumer warps (two units each) + 1 producer
+//   warp, and handles one (k-slice, region) pair: its rows are streamed through a 6-stage ring of
 //   KB = 16 row tiles written by TMA bulk copies (one 1-D cp.async.bulk per row and panel, row
 //   stride 132 doubles = 4 (mod 8), so fragment loads are conflict free), full/empty mbarriers.
 //   Diagonal regions only compute the 10 units on or above the diagonal (and the diagonal units
@@ -414,9 +414,9 @@ impute_rows_kernel(RowData d, DrawParams prm, RowOut out, const double *__restri
 //   reduce_syrk_kernel in k-slice order (deterministic).
 // =============================================================================================
 constexpr int kSyrkConsumerWarps = 8;
-constexpr int kSyrkThreads = 32 * kSyrkConsumerWarps;
+constexpr int kSyrkThreads = 32 * (kSyrkConsumerWarps + 4);  // + a producer warpgroup (1 TMA warp, 3 idle)
 constexpr int kSyrkKB = 16;        // rows per stage
-constexpr int kSyrkStages = 4;
+constexpr int kSyrkStages = 6;
 constexpr int kSyrkPanelLd = 132;  // doubles
 constexpr int kSyrkStageDoubles = 2 * kSyrkKB * kSyrkPanelLd + 2 * kSyrkKB;  // panels A, B, then w[KB], s[KB]
 constexpr size_t kSyrkSmemBytes = sizeof(double) * kSyrkStages * kSyrkStageDoubles + 8 * 2 * kSyrkStages + 64;
@@ -472,6 +472,108 @@ __device__ __forceinline__ void region_to_blocks(int region, int nblk, int &I, i
   I = i; J = i + rem;
 }
 
+struct SyrkWarpCtx {
+  double *smem;
+  uint64_t *full_bar, *empty_bar;
+  int nstages_total, lane, panelB_off;
+  SyrkUnit u0, u1;
+  int mmax0, nmax0, mmax1, nmax1;
+  double *tile;
+};
+
+// The k loop of one consumer warp.  T0/T1: unit type (0 none, 1 full 4x4 atoms, 2 diagonal unit: the 10
+// atoms with n >= m); DUTY: which unit (1 or 2; 0 none) also accumulates X's for its row block.
+// Two full units of one warp always share their A fragments (same row block).
+template <int T0, int T1, int DUTY>
+__device__ __forceinline__ void syrk_consume(const SyrkWarpCtx &wc) {
+  const int lane = wc.lane;
+  double c0[4][4][2], c1[4][4][2], cx[4][2];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { c0[m][n][0] = c0[m][n][1] = 0.0; c1[m][n][0] = c1[m][n][1] = 0.0; }
+    cx[m][0] = cx[m][1] = 0.0;
+  }
+  const int a0_off = 32 * wc.u0.ui + (lane >> 2), b0_off = wc.panelB_off + 32 * wc.u0.uj + (lane >> 2);
+  const int a1_off = 32 * wc.u1.ui + (lane >> 2), b1_off = wc.panelB_off + 32 * wc.u1.uj + (lane >> 2);
+  constexpr bool kSameA = (T0 == 1 && T1 == 1);
+
+  for (int it = 0; it < wc.nstages_total; ++it) {
+    const int s = it % kSyrkStages;
+    const uint32_t phase = (it / kSyrkStages) & 1;
+    mbar_wait(wc.full_bar + s, phase);
+    const double *stage = wc.smem + s * kSyrkStageDoubles;
+    const double *w_s = stage + 2 * kSyrkKB * kSyrkPanelLd;
+    const double *s_s = w_s + kSyrkKB;
+    if (T0 != 0) {
+#pragma unroll
+      for (int kk = 0; kk < kSyrkKB / 4; ++kk) {
+        const int row = kk * 4 + (lane & 3);
+        const double wv = w_s[row];
+        const double *xr = stage + row * kSyrkPanelLd;
+        double a[4], aw[4], b[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { a[m] = xr[a0_off + 8 * m]; aw[m] = a[m] * wv; b[m] = xr[b0_off + 8 * m]; }
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+            if (T0 == 1 || n >= m) dmma884(c0[m][n][0], c0[m][n][1], aw[m], b[n]);
+        if (DUTY == 1) {
+          const double sv = (lane >> 2) == 0 ? s_s[row] : 0.0;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) dmma884(cx[m][0], cx[m][1], a[m], sv);
+        }
+        if (T1 != 0) {
+          if (!kSameA) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { a[m] = xr[a1_off + 8 * m]; aw[m] = a[m] * wv; }
+          }
+#pragma unroll
+          for (int m = 0; m < 4; ++m) b[m] = xr[b1_off + 8 * m];
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+              if (T1 == 1 || n >= m) dmma884(c1[m][n][0], c1[m][n][1], aw[m], b[n]);
+          if (DUTY == 2) {
+            const double sv = (lane >> 2) == 0 ? s_s[row] : 0.0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) dmma884(cx[m][0], cx[m][1], a[m], sv);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(wc.empty_bar + s);
+  }
+
+  // ===== epilogue: fragments -> this CTA's partial tile (row major 128 x 128, then 128 xty)
+  double *tile = wc.tile;
+  auto store_unit = [&](const SyrkUnit &u, double (&cc)[4][4][2], bool dg, int mmax, int nmax) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        if ((dg && n < m) || m >= mmax || n >= nmax) continue;
+        const int r = 32 * u.ui + 8 * m + (lane >> 2);
+        const int cidx = 32 * u.uj + 8 * n + 2 * (lane & 3);
+        *reinterpret_cast<double2 *>(tile + r * 128 + cidx) = make_double2(cc[m][n][0], cc[m][n][1]);
+      }
+  };
+  if (T0 != 0) store_unit(wc.u0, c0, T0 == 2, wc.mmax0, wc.nmax0);
+  if (T1 != 0) store_unit(wc.u1, c1, T1 == 2, wc.mmax1, wc.nmax1);
+  if (DUTY != 0) {
+    const int ui = DUTY == 1 ? wc.u0.ui : wc.u1.ui;
+    const int mmax = DUTY == 1 ? wc.mmax0 : wc.mmax1;
+    if ((lane & 3) == 0) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+        if (m < mmax) tile[128 * 128 + 32 * ui + 8 * m + (lane >> 2)] = cx[m][0];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kSyrkThreads, 1) syrk_dmma_kernel(SyrkParams prm, SyrkUnitTable table) {
   extern __shared__ __align__(128) double smem[];
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kSyrkStages * kSyrkStageDoubles);
@@ -520,109 +622,52 @@ __global__ void __launch_bounds__(kSyrkThreads, 1) syrk_dmma_kernel(SyrkParams p
       tma_bulk_g2s(stage + 2 * kSyrkKB * kSyrkPanelLd + kSyrkKB, prm.s + r0, kSyrkKB * 8, full_bar + s);
     }
   };
-  if (wid == 0) {
-    for (int it = 0; it < kSyrkStages - 1 && it < nstages_total; ++it) produce(it);
+  if (wid >= kSyrkConsumerWarps) {
+    // producer warpgroup: hands its registers to the consumers and never competes for the DMMA pipe
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    if (wid == kSyrkConsumerWarps) {
+      for (int it = 0; it < nstages_total; ++it) produce(it);
+    }
+    return;
   }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
 
-  // ===== consumer warps
-  const SyrkUnit u0 = table.u[diag ? 1 : 0][wid][0];
-  const SyrkUnit u1 = table.u[diag ? 1 : 0][wid][1];
-  double c0[4][4][2], c1[4][4][2], cx[4][2];
-#pragma unroll
-  for (int m = 0; m < 4; ++m) {
-#pragma unroll
-    for (int n = 0; n < 4; ++n) { c0[m][n][0] = c0[m][n][1] = 0.0; c1[m][n][0] = c1[m][n][1] = 0.0; }
-    cx[m][0] = cx[m][1] = 0.0;
-  }
-  // units (and atoms) entirely beyond the last 8-column block of X are skipped
+  // ===== consumer role: resolved ONCE per warp into compile-time unit types so that the k loop
+  // carries no predicates (a predicated mma.sync costs a WARPSYNC + branch per instruction).
+  SyrkUnit u0 = table.u[diag ? 1 : 0][wid][0];
+  SyrkUnit u1 = table.u[diag ? 1 : 0][wid][1];
   const int P8 = (prm.p + 7) & ~7;
-  const int mmax0 = min(4, (P8 - 128 * I - 32 * u0.ui + 7) / 8), nmax0 = min(4, (P8 - 128 * J - 32 * u0.uj + 7) / 8);
-  const int mmax1 = min(4, (P8 - 128 * I - 32 * u1.ui + 7) / 8), nmax1 = min(4, (P8 - 128 * J - 32 * u1.uj + 7) / 8);
+  // 8-column atoms of each unit that lie inside X (<= 0: the whole unit is cut off by p)
+  const int mmax0 = min(4, (P8 - 128 * I - 32 * u0.ui) / 8), nmax0 = min(4, (P8 - 128 * J - 32 * u0.uj) / 8);
+  const int mmax1 = min(4, (P8 - 128 * I - 32 * u1.ui) / 8), nmax1 = min(4, (P8 - 128 * J - 32 * u1.uj) / 8);
   const bool v0 = (u0.flags & 1) && mmax0 > 0 && nmax0 > 0, v1 = (u1.flags & 1) && mmax1 > 0 && nmax1 > 0;
-  const bool d0 = u0.flags & 2, d1 = u1.flags & 2;
-  // X's for row block ui: normally the full unit (ui, ui+1) carries it; when p cuts that unit off, the diagonal unit does
+  // X's for row block ui: the full unit (ui, ui+1) carries it; when p cuts that unit off, the diagonal unit does
   const bool duty0 = v0 && ((u0.flags & 4) || ((u0.flags & 8) && P8 - 128 * I - 32 * (u0.ui + 1) <= 0));
   const bool duty1 = v1 && ((u1.flags & 4) || ((u1.flags & 8) && P8 - 128 * I - 32 * (u1.ui + 1) <= 0));
-  const int panelB_off = diag ? 0 : kSyrkKB * kSyrkPanelLd;
-  const int a0_off = 32 * u0.ui + (lane >> 2), b0_off = panelB_off + 32 * u0.uj + (lane >> 2);
-  const int a1_off = 32 * u1.ui + (lane >> 2), b1_off = panelB_off + 32 * u1.uj + (lane >> 2);
-  const bool same_a = v0 && v1 && (u0.ui == u1.ui);
+  const int t0 = v0 ? ((u0.flags & 2) ? 2 : 1) : 0;
+  const int t1 = v1 ? ((u1.flags & 2) ? 2 : 1) : 0;   // the unit table lists units so that v1 implies v0
+  const int duty = duty0 ? 1 : (duty1 ? 2 : 0);
 
-  for (int it = 0; it < nstages_total; ++it) {
-    const int s = it % kSyrkStages;
-    const uint32_t phase = (it / kSyrkStages) & 1;
-    // refill the stage consumed in the previous iteration (its empty barrier needs all 8 warps)
-    if (wid == 0 && it + kSyrkStages - 1 < nstages_total) produce(it + kSyrkStages - 1);
-    mbar_wait(full_bar + s, phase);
-    const double *stage = smem + s * kSyrkStageDoubles;
-    const double *w_s = stage + 2 * kSyrkKB * kSyrkPanelLd;
-    const double *s_s = w_s + kSyrkKB;
-#pragma unroll
-    for (int kk = 0; kk < kSyrkKB / 4; ++kk) {
-      const int row = kk * 4 + (lane & 3);
-      const double wv = w_s[row];
-      const double *xr = stage + row * kSyrkPanelLd;
-      double a[4], aw[4], b[4];
-      if (v0) {
-#pragma unroll
-        for (int m = 0; m < 4; ++m) { a[m] = xr[a0_off + 8 * m]; aw[m] = a[m] * wv; b[m] = xr[b0_off + 8 * m]; }
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-#pragma unroll
-          for (int n = 0; n < 4; ++n)
-            if ((!d0 || n >= m) && m < mmax0 && n < nmax0) dmma884(c0[m][n][0], c0[m][n][1], aw[m], b[n]);
-        if (duty0) {
-          const double sv = (lane >> 2) == 0 ? s_s[row] : 0.0;
-#pragma unroll
-          for (int m = 0; m < 4; ++m) if (m < mmax0) dmma884(cx[m][0], cx[m][1], a[m], sv);
-        }
-      }
-      if (v1) {
-        if (!same_a) {
-#pragma unroll
-          for (int m = 0; m < 4; ++m) { a[m] = xr[a1_off + 8 * m]; aw[m] = a[m] * wv; }
-        }
-#pragma unroll
-        for (int m = 0; m < 4; ++m) b[m] = xr[b1_off + 8 * m];
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-#pragma unroll
-          for (int n = 0; n < 4; ++n)
-            if ((!d1 || n >= m) && m < mmax1 && n < nmax1) dmma884(c1[m][n][0], c1[m][n][1], aw[m], b[n]);
-        if (duty1) {
-          const double sv = (lane >> 2) == 0 ? s_s[row] : 0.0;
-#pragma unroll
-          for (int m = 0; m < 4; ++m) if (m < mmax1) dmma884(cx[m][0], cx[m][1], a[m], sv);
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty_bar + s);
-  }
+  SyrkWarpCtx wc;
+  wc.smem = smem; wc.full_bar = full_bar; wc.empty_bar = empty_bar; wc.nstages_total = nstages_total;
+  wc.lane = lane;
+  wc.panelB_off = diag ? 0 : kSyrkKB * kSyrkPanelLd;
+  wc.u0 = u0; wc.u1 = u1;
+  wc.mmax0 = mmax0; wc.nmax0 = nmax0; wc.mmax1 = mmax1; wc.nmax1 = nmax1;
+  wc.tile = prm.partials + ((int64_t)kslice * prm.nregions + region) * kSyrkTileLen;
 
-  // ===== epilogue: fragments -> this CTA's partial tile (row major 128 x 128, then 128 xty)
-  double *tile = prm.partials + ((int64_t)kslice * prm.nregions + region) * kSyrkTileLen;
-  auto store_unit = [&](const SyrkUnit &u, double (&cc)[4][4][2], bool dg, int mmax, int nmax) {
-#pragma unroll
-    for (int m = 0; m < 4; ++m)
-#pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        if ((dg && n < m) || m >= mmax || n >= nmax) continue;
-        const int r = 32 * u.ui + 8 * m + (lane >> 2);
-        const int cidx = 32 * u.uj + 8 * n + 2 * (lane & 3);
-        *reinterpret_cast<double2 *>(tile + r * 128 + cidx) = make_double2(cc[m][n][0], cc[m][n][1]);
-      }
-  };
-  if (v0) store_unit(u0, c0, d0, mmax0, nmax0);
-  if (v1) store_unit(u1, c1, d1, mmax1, nmax1);
-  if ((duty0 && v0) || (duty1 && v1)) {
-    const int ui = (duty0 && v0) ? u0.ui : u1.ui;
-    const int mmax = (duty0 && v0) ? mmax0 : mmax1;
-    if ((lane & 3) == 0) {
-#pragma unroll
-      for (int m = 0; m < 4; ++m)
-        if (m < mmax) tile[128 * 128 + 32 * ui + 8 * m + (lane >> 2)] = cx[m][0];
-    }
+  const int role = t0 * 100 + t1 * 10 + duty;
+  switch (role) {
+    case 0:   syrk_consume<0, 0, 0>(wc); break;
+    case 100: syrk_consume<1, 0, 0>(wc); break;
+    case 101: syrk_consume<1, 0, 1>(wc); break;
+    case 110: syrk_consume<1, 1, 0>(wc); break;
+    case 200: syrk_consume<2, 0, 0>(wc); break;
+    case 201: syrk_consume<2, 0, 1>(wc); break;
+    case 220: syrk_consume<2, 2, 0>(wc); break;
+    case 221: syrk_consume<2, 2, 1>(wc); break;
+    case 222: syrk_consume<2, 2, 2>(wc); break;
+    default: __trap();
   }
 }
 
