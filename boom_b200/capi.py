@@ -20,7 +20,7 @@ SYMBOLS = (
     "boomgpu_set_row_offset", "boomgpu_set_option", "boomgpu_upload_binomial", "boomgpu_upload_poisson",
     "boomgpu_adopt_binomial", "boomgpu_adopt_poisson", "boomgpu_set_logit_mixture", "boomgpu_set_poisson_table",
     "boomgpu_logit_step", "boomgpu_poisson_step", "boomgpu_suf_len", "boomgpu_logit_step_device",
-    "boomgpu_poisson_step_device", "boomgpu_synchronize", "boomgpu_accumulate", "boomgpu_logit_draw",
+    "boomgpu_poisson_step_device", "boomgpu_synchronize", "boomgpu_suf_buffer", "boomgpu_download", "boomgpu_accumulate", "boomgpu_logit_draw",
     "boomgpu_poisson_draw", "boomgpu_binomial_loglike", "boomgpu_poisson_loglike", "boomgpu_kernel_launches",
     "boomgpu_get_timings",
 )
@@ -187,6 +187,16 @@ class Context:
 
     def synchronize(self):
         self._check(self._lib.boomgpu_synchronize(self._h))
+
+    def suf_buffer(self):
+        ptr = C.c_void_p()
+        self._check(self._lib.boomgpu_suf_buffer(self._h, C.byref(ptr)))
+        return ptr.value
+
+    def download(self, src_dev_ptr, count):
+        out = np.empty(int(count))
+        self._check(self._lib.boomgpu_download(self._h, C.c_void_p(src_dev_ptr), _dp(out), C.c_int64(int(count))))
+        return out
 
     # ---- parity hooks
     def accumulate(self, weight, weighted_value):

@@ -669,6 +669,29 @@ int boomgpu_synchronize(boomgpu_ctx *ctx) {
   return finish_and_check(ctx);
 }
 
+int boomgpu_suf_buffer(boomgpu_ctx *ctx, double **suf_dev) {
+  if (!ctx || !suf_dev) return BOOMGPU_ERR_ARG;
+  if (!ctx->X) return fail(ctx, BOOMGPU_ERR_STATE, "no data uploaded to this context");
+  DeviceGuard g(ctx->device);
+  if (int rc = ensure_suf(ctx)) return rc;
+  *suf_dev = ctx->suf_dev;
+  return 0;
+}
+
+int boomgpu_download(boomgpu_ctx *ctx, const double *src_dev, double *dst_host, int64_t count) {
+  if (!ctx || !src_dev || !dst_host || count < 0) return BOOMGPU_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  if (ctx->suf_pin_cap < count) {
+    if (ctx->suf_pin) { CU(cudaFreeHost(ctx->suf_pin)); ctx->suf_pin = nullptr; }
+    CU(cudaMallocHost((void **)&ctx->suf_pin, sizeof(double) * (size_t)count));
+    ctx->suf_pin_cap = count;
+  }
+  CU(cudaMemcpyAsync(ctx->suf_pin, src_dev, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  if (int rc = finish_and_check(ctx)) return rc;
+  memcpy(dst_host, ctx->suf_pin, sizeof(double) * (size_t)count);
+  return 0;
+}
+
 int boomgpu_logit_step(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
                        double *xtx, double *xty, int64_t *sample_size) {
   if (int rc = check_ready(ctx, kLogit)) return rc;

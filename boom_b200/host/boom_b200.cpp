@@ -1,0 +1,661 @@
+// boom_b200.cpp -- host side of the B200-native auxiliary-mixture samplers (see boom_b200.hpp).
+#include "boom_b200.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <mutex>
+#include <sstream>
+
+#include "../../include/boomgpu.h"
+
+namespace BOOM_B200 {
+
+void report_error(const std::string &msg) { throw std::runtime_error(msg); }
+
+RNG GlobalRng::rng(8675309);
+
+RNG::RngIntType seed_rng(RNG &rng) {
+  RNG::RngIntType ans = 0;
+  while (ans <= 2) {
+    double u = rng() * static_cast<double>(std::numeric_limits<RNG::RngIntType>::max());
+    ans = (RNG::RngIntType)std::llround(std::min(u, 9.2e18));
+  }
+  return ans;
+}
+
+double runif_mt(RNG &rng, double lo, double hi) { return lo + (hi - lo) * rng(); }
+
+double rnorm_mt(RNG &rng, double mu, double sd) {
+  // Box-Muller on the sampler's own stream (the reference uses Kinderman-Ramage, Bmath/snorm.cpp:77;
+  // only the distribution has to agree).
+  double u1 = rng(), u2 = rng();
+  while (u1 <= 0) u1 = rng();
+  return mu + sd * std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586476925286766559 * u2);
+}
+
+int random_int_mt(RNG &rng, int lo, int hi) { return (int)std::floor(runif_mt(rng, lo, hi + 1)); }
+
+// ---------------------------------------------------------------------------------------------
+bool cholesky_lower(double *a, int n) {
+  for (int j = 0; j < n; ++j) {
+    double *rj = a + (size_t)j * n;
+    double d = rj[j];
+    for (int k = 0; k < j; ++k) d -= rj[k] * rj[k];
+    if (!(d > 0) || !std::isfinite(d)) return false;
+    d = std::sqrt(d);
+    rj[j] = d;
+    const double inv = 1.0 / d;
+    for (int i = j + 1; i < n; ++i) {
+      double *ri = a + (size_t)i * n;
+      double s = ri[j];
+      for (int k = 0; k < j; ++k) s -= ri[k] * rj[k];
+      ri[j] = s * inv;
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j) a[(size_t)i * n + j] = 0.0;
+  return true;
+}
+
+void lsolve_inplace(const double *L, int n, double *b) {
+  for (int i = 0; i < n; ++i) {
+    const double *ri = L + (size_t)i * n;
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= ri[k] * b[k];
+    b[i] = s / ri[i];
+  }
+}
+
+void ltsolve_inplace(const double *L, int n, double *b) {
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[i] / L[(size_t)i * n + i];
+    b[i] = s;
+    const double *ri = L + (size_t)i * n;
+    for (int k = 0; k < i; ++k) b[k] -= ri[k] * s;
+  }
+}
+
+// rmvn_suf_mt (distributions/mvn.cpp:128-136): beta = L^-T z + (L L^T)^-1 ivar_mu
+Vector rmvn_suf_mt(RNG &rng, const SpdMatrix &ivar, const Vector &ivar_mu) {
+  const int n = ivar.dim;
+  Vector L(ivar.a);
+  if (!cholesky_lower(L.data(), n)) report_error("Cholesky decomposition failed in rmvn_suf_mt.");
+  Vector z(n);
+  for (int i = 0; i < n; ++i) z[i] = rnorm_mt(rng);
+  ltsolve_inplace(L.data(), n, z.data());
+  Vector m(ivar_mu);
+  lsolve_inplace(L.data(), n, m.data());
+  ltsolve_inplace(L.data(), n, m.data());
+  for (int i = 0; i < n; ++i) z[i] += m[i];
+  return z;
+}
+
+static double logdet_spd(const SpdMatrix &m, bool *ok) {
+  Vector L(m.a);
+  if (!cholesky_lower(L.data(), m.dim)) { *ok = false; return -std::numeric_limits<double>::infinity(); }
+  *ok = true;
+  double s = 0;
+  for (int i = 0; i < m.dim; ++i) s += std::log(L[(size_t)i * m.dim + i]);
+  return 2 * s;
+}
+
+// ---------------------------------------------------------------------------------------------
+int Selector::nvars() const { return (int)std::count(inc_.begin(), inc_.end(), true); }
+
+std::vector<int> Selector::included_positions() const {
+  std::vector<int> pos;
+  for (int i = 0; i < (int)inc_.size(); ++i) if (inc_[i]) pos.push_back(i);
+  return pos;
+}
+
+Vector Selector::select(const Vector &v) const {
+  if ((int)v.size() != nvars_possible()) report_error("Selector::select: wrong size vector");
+  Vector out;
+  for (int i = 0; i < (int)inc_.size(); ++i) if (inc_[i]) out.push_back(v[i]);
+  return out;
+}
+
+SpdMatrix Selector::select(const SpdMatrix &m) const {
+  const std::vector<int> pos = included_positions();
+  const int k = (int)pos.size();
+  SpdMatrix out(k);
+  for (int i = 0; i < k; ++i) {
+    const double *row = m.a.data() + (size_t)pos[i] * m.dim;
+    for (int j = 0; j < k; ++j) out.a[(size_t)i * k + j] = row[pos[j]];
+  }
+  return out;
+}
+
+Vector Selector::expand(const Vector &sub) const {
+  Vector out(inc_.size(), 0.0);
+  int k = 0;
+  for (int i = 0; i < (int)inc_.size(); ++i) if (inc_[i]) out[i] = sub[k++];
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+double MvnBase::logp(const Vector &x) const {
+  const int p = dim();
+  const SpdMatrix &P(siginv());
+  bool ok = true;
+  const double ld = logdet_spd(P, &ok);
+  if (!ok) return -std::numeric_limits<double>::infinity();
+  double q = 0;
+  for (int i = 0; i < p; ++i) {
+    double s = 0;
+    for (int j = 0; j < p; ++j) s += P(i, j) * (x[j] - mu()[j]);
+    q += s * (x[i] - mu()[i]);
+  }
+  return -0.5 * p * std::log(6.283185307179586476925286766559) + 0.5 * ld - 0.5 * q;
+}
+
+MvnModel::MvnModel(const Vector &mean, const SpdMatrix &V, bool ivar) : mu_(mean), siginv_(V) {
+  if ((int)mean.size() != V.dim) report_error("MvnModel: mean and variance dimensions differ");
+  if (!ivar) {
+    const int p = V.dim;
+    Vector L(V.a);
+    if (!cholesky_lower(L.data(), p)) report_error("MvnModel: variance matrix is not positive definite");
+    for (int c = 0; c < p; ++c) {
+      Vector e(p, 0.0);
+      e[c] = 1.0;
+      lsolve_inplace(L.data(), p, e.data());
+      ltsolve_inplace(L.data(), p, e.data());
+      for (int r = 0; r < p; ++r) siginv_(r, c) = e[r];
+    }
+  }
+}
+
+VariableSelectionPrior::VariableSelectionPrior(int n, double pr) : VariableSelectionPrior(Vector(n, pr)) {}
+
+VariableSelectionPrior::VariableSelectionPrior(const Vector &probs) : probs_(probs), log_p_(probs.size()), log_q_(probs.size()) {
+  for (size_t i = 0; i < probs.size(); ++i) {
+    if (!(probs[i] >= 0 && probs[i] <= 1)) report_error("prior inclusion probabilities must lie in [0, 1]");
+    log_p_[i] = probs[i] > 0 ? std::log(probs[i]) : -std::numeric_limits<double>::infinity();
+    log_q_[i] = probs[i] < 1 ? std::log(1 - probs[i]) : -std::numeric_limits<double>::infinity();
+  }
+}
+
+double VariableSelectionPrior::logp(const Selector &inc) const {
+  if (max_model_size_ >= 0 && inc.nvars() > max_model_size_) return -std::numeric_limits<double>::infinity();
+  double ans = 0;
+  for (int i = 0; i < inc.nvars_possible(); ++i) {
+    ans += inc[i] ? log_p_[i] : log_q_[i];
+    if (!std::isfinite(ans)) return -std::numeric_limits<double>::infinity();
+  }
+  return ans;
+}
+
+void VariableSelectionPrior::make_valid(Selector &inc) const {
+  if (inc.nvars_possible() != (int)probs_.size()) report_error("Wrong size Selector passed to make_valid.");
+  for (size_t i = 0; i < probs_.size(); ++i) {
+    if (probs_[i] <= 0.0 && inc[i]) inc.flip(i);
+    if (probs_[i] >= 1.0 && !inc[i]) inc.flip(i);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+void GlmCoefs::set_Beta(const Vector &b) {
+  if (b.size() != beta_.size()) report_error("GlmCoefs::set_Beta: wrong size");
+  beta_ = b;
+}
+
+void GlmCoefs::set_inc(const Selector &g) {
+  if (g.nvars_possible() != inc_.nvars_possible()) report_error("GlmCoefs::set_inc: wrong size");
+  inc_ = g;
+  for (size_t i = 0; i < beta_.size(); ++i) if (!inc_[i]) beta_[i] = 0.0;
+}
+
+void GlmCoefs::set_included_coefficients(const Vector &b) {
+  if ((int)b.size() != inc_.nvars()) report_error("GlmCoefs::set_included_coefficients: wrong size");
+  beta_ = inc_.expand(b);
+}
+
+// ---------------------------------------------------------------------------------------------
+DeviceData::DeviceData(int device) : device_(device) {
+  if (boomgpu_create(&ctx_, device)) report_error(std::string("boomgpu_create: ") + boomgpu_last_error(nullptr));
+}
+DeviceData::~DeviceData() { boomgpu_destroy(ctx_); }
+void DeviceData::check(int rc) const {
+  if (rc) report_error(std::string("boomgpu: ") + boomgpu_last_error(ctx_));
+}
+
+void GlmModelBase::set_method(const std::shared_ptr<PosteriorSampler> &sampler) { samplers_.push_back(sampler); }
+void GlmModelBase::sample_posterior() {
+  if (samplers_.empty()) report_error("sample_posterior() called with no sampler: call set_method first");
+  for (auto &s : samplers_) s->draw();
+}
+double GlmModelBase::logpri() const {
+  double ans = 0;
+  for (auto &s : samplers_) ans += s->logpri();
+  return ans;
+}
+void GlmModelBase::set_device(int device) {
+  if (device != device_) { dev_.reset(); uploaded_version_ = 0; }
+  device_ = device;
+}
+void GlmModelBase::set_stream(void *cuda_stream) {
+  stream_ = cuda_stream; have_stream_ = true;
+  if (dev_) dev_->check(boomgpu_set_stream(dev_->ctx(), cuda_stream));
+}
+void GlmModelBase::set_row_offset(uint64_t r) {
+  row_offset_ = r;
+  if (dev_) dev_->check(boomgpu_set_row_offset(dev_->ctx(), r));
+}
+DeviceData &GlmModelBase::device_data() {
+  if (!dev_) {
+    dev_.reset(new DeviceData(device_));
+    uploaded_version_ = 0;
+    if (have_stream_) dev_->check(boomgpu_set_stream(dev_->ctx(), stream_));
+  }
+  if (uploaded_version_ != data_version_) {
+    upload(*dev_);
+    dev_->check(boomgpu_set_row_offset(dev_->ctx(), row_offset_));
+    uploaded_version_ = data_version_;
+  }
+  return *dev_;
+}
+
+BinomialLogitModel::BinomialLogitModel(int64_t n, int p, const double *X, const double *y, const double *nt)
+    : GlmModelBase(p) {
+  x_.assign(X, X + (size_t)n * p);
+  y_.assign(y, y + n);
+  n_.assign(nt, nt + n);
+  for (int64_t i = 0; i < n; ++i)
+    if (y_[i] > n_[i] || y_[i] < 0) report_error("BinomialRegressionData: y must lie in [0, n]");
+}
+void BinomialLogitModel::add_data(double y, double n, const Vector &x) {
+  if ((int)x.size() != xdim()) report_error("BinomialLogitModel::add_data: wrong size x");
+  if (y > n || y < 0 || n < 0) report_error("BinomialRegressionData: y must lie in [0, n]");
+  if (adopted_) report_error("add_data on a model whose data live in adopted device memory");
+  x_.insert(x_.end(), x.begin(), x.end());
+  y_.push_back(y);
+  n_.push_back(n);
+  touch();
+}
+void BinomialLogitModel::adopt_device_data(int64_t n, const double *dX, int64_t ldx, const double *dy, const double *dn) {
+  adopted_ = true; adopted_n_ = n; dX_ = dX; dldx_ = ldx; dy_ = dy; dn_ = dn;
+  touch();
+}
+void BinomialLogitModel::upload(DeviceData &dev) {
+  if (adopted_) dev.check(boomgpu_adopt_binomial(dev.ctx(), adopted_n_, xdim(), dX_, dldx_, dy_, dn_));
+  else dev.check(boomgpu_upload_binomial(dev.ctx(), (int64_t)y_.size(), xdim(), x_.data(), xdim(), y_.data(), n_.data()));
+}
+double BinomialLogitModel::log_likelihood(const Vector &beta) {
+  if ((int)beta.size() != xdim()) report_error("log_likelihood: wrong size beta");
+  DeviceData &dev(device_data());
+  double ans = 0;
+  dev.check(boomgpu_binomial_loglike(dev.ctx(), beta.data(), &ans));
+  return ans;
+}
+
+PoissonRegressionModel::PoissonRegressionModel(int64_t n, int p, const double *X, const int64_t *y, const double *ex)
+    : GlmModelBase(p) {
+  x_.assign(X, X + (size_t)n * p);
+  y_.assign(y, y + n);
+  exposure_.assign(ex, ex + n);
+}
+void PoissonRegressionModel::add_data(int64_t y, const Vector &x, double exposure) {
+  if ((int)x.size() != xdim()) report_error("PoissonRegressionModel::add_data: wrong size x");
+  if (y < 0 || exposure < 0) report_error("PoissonRegressionData: y and exposure must be non-negative");
+  if (adopted_) report_error("add_data on a model whose data live in adopted device memory");
+  x_.insert(x_.end(), x.begin(), x.end());
+  y_.push_back(y);
+  exposure_.push_back(exposure);
+  touch();
+}
+void PoissonRegressionModel::adopt_device_data(int64_t n, const double *dX, int64_t ldx, const int64_t *dy, const double *dex) {
+  adopted_ = true; adopted_n_ = n; dX_ = dX; dldx_ = ldx; dy_ = dy; dexp_ = dex;
+  touch();
+}
+void PoissonRegressionModel::upload(DeviceData &dev) {
+  if (adopted_) dev.check(boomgpu_adopt_poisson(dev.ctx(), adopted_n_, xdim(), dX_, dldx_, dy_, dexp_));
+  else dev.check(boomgpu_upload_poisson(dev.ctx(), (int64_t)y_.size(), xdim(), x_.data(), xdim(), y_.data(), exposure_.data()));
+}
+double PoissonRegressionModel::log_likelihood(const Vector &beta) {
+  if ((int)beta.size() != xdim()) report_error("log_likelihood: wrong size beta");
+  DeviceData &dev(device_data());
+  double ans = 0;
+  dev.check(boomgpu_poisson_loglike(dev.ctx(), beta.data(), &ans));
+  return ans;
+}
+
+// ---------------------------------------------------------------------------------------------
+void WeightedRegSuf::clear() {
+  std::fill(xtx_.a.begin(), xtx_.a.end(), 0.0);
+  std::fill(xty_.begin(), xty_.end(), 0.0);
+  n_ = yty_ = sumw_ = sumlogw_ = 0;
+}
+void WeightedRegSuf::update(const Vector &x, double weighted_value, double weight) {
+  const int p = xtx_.dim;
+  if ((int)x.size() != p) report_error("sufficient statistics: wrong size x");
+  for (int i = 0; i < p; ++i) {
+    const double a = weight * x[i];
+    for (int j = 0; j < p; ++j) xtx_.a[(size_t)i * p + j] += a * x[j];
+    xty_[i] += x[i] * weighted_value;
+  }
+  n_ += 1;
+}
+void WeightedRegSuf::add_data(const Vector &x, double y, double w) {
+  update(x, w * y, w);
+  yty_ += w * y * y;
+  sumw_ += w;
+  sumlogw_ += std::log(w);
+}
+void WeightedRegSuf::reset(const double *packed, int p) {
+  if (xtx_.dim != p) { xtx_ = SpdMatrix(p); xty_.assign(p, 0.0); }
+  std::copy(packed, packed + (size_t)p * p, xtx_.a.begin());
+  std::copy(packed + (size_t)p * p, packed + (size_t)p * p + p, xty_.begin());
+  const double *sc = packed + (size_t)p * p + p;
+  n_ = sc[0]; yty_ = sc[1]; sumw_ = sc[2]; sumlogw_ = sc[3];
+}
+
+// ---------------------------------------------------------------------------------------------
+SpikeSlabCore::SpikeSlabCore(const std::shared_ptr<MvnBase> &slab, const std::shared_ptr<VariableSelectionPrior> &spike,
+                             bool fisher_yates)
+    : slab_(slab), spike_(spike), fisher_yates_(fisher_yates) {
+  if (!slab || !spike) report_error("spike and slab priors must not be null");
+  if (slab->dim() != spike->potential_nvars()) report_error("Slab and spike dimensions differ.");
+}
+
+// BinomialLogitSpikeSlabSampler::log_model_prob (.cpp:88-117) == SpikeSlabSampler::log_model_prob with sigsq = 1
+double SpikeSlabCore::log_model_prob(const Selector &g, const WeightedRegSuf &suf) const {
+  const double neg_inf = -std::numeric_limits<double>::infinity();
+  double num = spike_->logp(g);
+  if (num == neg_inf || g.nvars() == 0) return num;
+  SpdMatrix ivar = g.select(slab_->siginv());
+  bool ok = true;
+  num += .5 * logdet_spd(ivar, &ok);
+  if (!ok || num == neg_inf) return neg_inf;
+  const int k = ivar.dim;
+  Vector mu = g.select(slab_->mu());
+  Vector ivar_mu(k, 0.0);
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) ivar_mu[i] += ivar(i, j) * mu[j];
+  double q = 0;
+  for (int i = 0; i < k; ++i) q += mu[i] * ivar_mu[i];
+  num -= .5 * q;
+  const std::vector<int> pos = g.included_positions();
+  const SpdMatrix &xtx(suf.xtx());
+  for (int i = 0; i < k; ++i) {
+    const double *row = xtx.a.data() + (size_t)pos[i] * xtx.dim;
+    for (int j = 0; j < k; ++j) ivar.a[(size_t)i * k + j] += row[pos[j]];
+  }
+  if (!cholesky_lower(ivar.a.data(), k)) return neg_inf;
+  double denom = 0;
+  for (int i = 0; i < k; ++i) denom += std::log(ivar(i, i));  // = .5 log |ivar|
+  Vector S(k);
+  for (int i = 0; i < k; ++i) S[i] = suf.xty()[pos[i]] + ivar_mu[i];
+  lsolve_inplace(ivar.a.data(), k, S.data());
+  double nsq = 0;
+  for (int i = 0; i < k; ++i) nsq += S[i] * S[i];
+  denom -= .5 * nsq;
+  return num - denom;
+}
+
+void SpikeSlabCore::draw_model_indicators(RNG &rng, GlmCoefs &coef, const WeightedRegSuf &suf) const {
+  if (!allow_model_selection_) return;
+  Selector g = coef.inc();
+  const int nv = g.nvars_possible();
+  std::vector<int> indx(nv);
+  for (int i = 0; i < nv; ++i) indx[i] = i;
+  if (fisher_yates_) {  // SpikeSlabSampler.cpp:52-57
+    for (int i = nv - 1; i > 0; --i) {
+      int j = random_int_mt(rng, 0, i);
+      if (j != i) std::swap(indx[i], indx[j]);
+    }
+  } else {  // BinomialLogitSpikeSlabSampler.cpp:185-188
+    for (int i = 0; i < nv; ++i) {
+      int j = random_int_mt(rng, 0, nv - 1);
+      std::swap(indx[i], indx[j]);
+    }
+  }
+  double logp = log_model_prob(g, suf);
+  if (!std::isfinite(logp)) {
+    spike_->make_valid(g);
+    logp = log_model_prob(g, suf);
+  }
+  if (!std::isfinite(logp)) report_error("The spike and slab sampler did not start with a legal configuration.");
+  int n = nv;
+  if (max_flips_ > 0) n = std::min(n, max_flips_);
+  for (int i = 0; i < n; ++i) {  // mcmc_one_flip (.cpp:213-222)
+    g.flip(indx[i]);
+    const double logp_new = log_model_prob(g, suf);
+    const double u = runif_mt(rng, 0, 1);
+    if (std::log(u) > logp_new - logp) g.flip(indx[i]);
+    else logp = logp_new;
+  }
+  coef.set_inc(g);
+}
+
+// BinomialLogitSpikeSlabSampler::draw_beta (.cpp:56-75)
+void SpikeSlabCore::draw_beta(RNG &rng, GlmCoefs &coef, const WeightedRegSuf &suf) const {
+  const Selector &g(coef.inc());
+  if (g.nvars() == 0) { coef.drop_all(); return; }
+  SpdMatrix precision = g.select(slab_->siginv());
+  const int k = precision.dim;
+  Vector mu = g.select(slab_->mu());
+  Vector scaled_mean(k, 0.0);
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) scaled_mean[i] += precision(i, j) * mu[j];
+  const std::vector<int> pos = g.included_positions();
+  const SpdMatrix &xtx(suf.xtx());
+  for (int i = 0; i < k; ++i) {
+    const double *row = xtx.a.data() + (size_t)pos[i] * xtx.dim;
+    for (int j = 0; j < k; ++j) precision.a[(size_t)i * k + j] += row[pos[j]];
+    scaled_mean[i] += suf.xty()[pos[i]];
+  }
+  if (!cholesky_lower(precision.a.data(), k)) report_error("Cholesky decomposition failed in draw_beta.");
+  lsolve_inplace(precision.a.data(), k, scaled_mean.data());
+  ltsolve_inplace(precision.a.data(), k, scaled_mean.data());  // posterior mean
+  Vector z(k);
+  for (int i = 0; i < k; ++i) z[i] = rnorm_mt(rng, 0, 1);
+  ltsolve_inplace(precision.a.data(), k, z.data());  // rmvn_precision_upper_cholesky_mt (mvn.cpp:114-122)
+  for (int i = 0; i < k; ++i) z[i] += scaled_mean[i];
+  coef.set_included_coefficients(z);
+}
+
+double SpikeSlabCore::logpri(const GlmCoefs &coef) const {
+  const Selector &g(coef.inc());
+  double ans = spike_->logp(g);
+  if (!std::isfinite(ans)) return ans;
+  if (g.nvars() > 0) {
+    MvnModel sub(g.select(slab_->mu()), g.select(slab_->siginv()), true);
+    ans += sub.logp(coef.included_coefficients());
+  }
+  return ans;
+}
+
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct LogitMixtureStore {
+  Vector mu = Vector(9, 0.0);
+  // Fruhwirth-Schnatter & Fruhwirth scale mixture for the logistic (values as in
+  // Models/Glm/PosteriorSamplers/NormalMixtureApproximation.cpp:416-424)
+  Vector sigma = {0.88437229872213, 1.16097607474416, 1.28021991084306, 1.3592552924727, 1.67589879794907,
+                  2.20287232043947, 2.20507148325819, 2.91944313615144, 3.90807611741308};
+  Vector weights = {0.038483985581272, 0.13389889791451, 0.0657842076622429, 0.105680086433879, 0.345939491553619,
+                    0.0442261124345564, 0.193289780660134, 0.068173066865908, 0.00452437089387876};
+};
+LogitMixtureStore &logit_mixture_store() { static LogitMixtureStore s; return s; }
+
+struct PoissonTableStore {
+  std::vector<int64_t> nu;
+  std::vector<int32_t> offset;
+  Vector weights, mu, sigma;
+  int64_t largest = 0;
+  uint64_t version = 0;
+};
+PoissonTableStore &poisson_table_store() { static PoissonTableStore s; return s; }
+
+// device step -> allreduce hook -> packed statistics on the host
+template <class StepFn>
+void run_device_step(GlmModelBase &model, Vector &packed, StepFn step) {
+  DeviceData &dev(model.device_data());
+  const int p = model.xdim();
+  const int64_t len = boomgpu_suf_len(p);
+  packed.resize((size_t)len);
+  double *suf_dev = nullptr;
+  dev.check(boomgpu_suf_buffer(dev.ctx(), &suf_dev));
+  dev.check(step(dev.ctx(), suf_dev));
+  if (model.allreduce()) model.allreduce()(suf_dev, len);
+  dev.check(boomgpu_download(dev.ctx(), suf_dev, packed.data(), len));
+}
+}  // namespace
+
+void set_logit_mixture(const Vector &mu, const Vector &sigma, const Vector &weights) {
+  if (sigma.empty() || sigma.size() != weights.size() || mu.size() != sigma.size())
+    report_error("set_logit_mixture: mu, sigma and weights must have the same positive length");
+  LogitMixtureStore &s(logit_mixture_store());
+  s.mu = mu; s.sigma = sigma; s.weights = weights;
+}
+
+// ---------------------------------------------------------------------------------------------
+BinomialLogitAuxmixSampler::BinomialLogitAuxmixSampler(BinomialLogitModel *model, const std::shared_ptr<MvnBase> &prior,
+                                                       int clt_threshold, RNG &seeding_rng)
+    : PosteriorSampler(seeding_rng), model_(model), prior_(prior), suf_(model ? model->xdim() : 0),
+      clt_threshold_(clt_threshold) {
+  if (!model) report_error("BinomialLogitAuxmixSampler: null model");
+  if (!prior || prior->dim() != model->xdim()) report_error("Prior does not match model dimension.");
+  device_seed_ = seed_rng(rng());
+}
+
+void BinomialLogitAuxmixSampler::on_seed() { device_seed_ = seed_rng(rng()); iteration_ = 0; }
+
+double BinomialLogitAuxmixSampler::logpri() const { return prior_->logp(model_->Beta()); }
+
+void BinomialLogitAuxmixSampler::draw() {
+  impute_latent_data();
+  draw_params();
+}
+
+void BinomialLogitAuxmixSampler::impute_latent_data() {
+  if (latent_data_fixed_) return;  // statistics are under external control (Imputer.hpp:282-299)
+  const LogitMixtureStore &mix(logit_mixture_store());
+  const int clt = clt_threshold_;
+  const uint64_t seed = device_seed_, it = iteration_++;
+  const Vector &beta(model_->Beta());
+  run_device_step(*model_, packed_, [&](boomgpu_ctx *ctx, double *suf_dev) {
+    int rc = boomgpu_set_logit_mixture(ctx, (int)mix.sigma.size(), mix.mu.data(), mix.sigma.data(), mix.weights.data());
+    if (rc) return rc;
+    return boomgpu_logit_step_device(ctx, beta.data(), clt, seed, it, suf_dev);
+  });
+  suf_.reset(packed_.data(), model_->xdim());
+}
+
+void BinomialLogitAuxmixSampler::draw_params() {
+  const int p = model_->xdim();
+  SpdMatrix ivar(prior_->siginv());
+  Vector ivar_mu(suf_.xty());
+  for (int i = 0; i < p; ++i) {
+    double s = 0;
+    for (int j = 0; j < p; ++j) {
+      ivar.a[(size_t)i * p + j] += suf_.xtx()(i, j);
+      s += prior_->siginv()(i, j) * prior_->mu()[j];
+    }
+    ivar_mu[i] += s;
+  }
+  model_->set_Beta(rmvn_suf_mt(rng(), ivar, ivar_mu));
+}
+
+BinomialLogitSpikeSlabSampler::BinomialLogitSpikeSlabSampler(BinomialLogitModel *model, const std::shared_ptr<MvnBase> &slab,
+                                                             const std::shared_ptr<VariableSelectionPrior> &spike,
+                                                             int clt_threshold, RNG &seeding_rng)
+    : BinomialLogitAuxmixSampler(model, slab, clt_threshold, seeding_rng), core_(slab, spike, false) {
+  if (spike->potential_nvars() != model->xdim()) report_error("Spike does not match model dimension.");
+}
+
+void BinomialLogitSpikeSlabSampler::draw() {
+  impute_latent_data();
+  if (core_.model_selection_allowed()) draw_model_indicators();
+  draw_beta();
+}
+double BinomialLogitSpikeSlabSampler::logpri() const { return core_.logpri(model_->coef()); }
+void BinomialLogitSpikeSlabSampler::draw_model_indicators() { core_.draw_model_indicators(rng(), model_->coef(), suf()); }
+void BinomialLogitSpikeSlabSampler::draw_beta() { core_.draw_beta(rng(), model_->coef(), suf()); }
+double BinomialLogitSpikeSlabSampler::log_model_prob(const Selector &g) const { return core_.log_model_prob(g, suf()); }
+
+// ---------------------------------------------------------------------------------------------
+void PoissonRegressionAuxMixSampler::set_mixture_table(const Vector &ser, int64_t largest_index) {
+  PoissonTableStore t;
+  t.offset.push_back(0);
+  size_t i = 0;
+  while (i < ser.size()) {
+    if (i + 1 >= ser.size()) report_error("set_mixture_table: truncated table");
+    const int64_t nu = std::llround(ser[i]);
+    const int K = (int)std::llround(ser[i + 1]);
+    if (K < 1 || i + 2 + 3 * (size_t)K > ser.size()) report_error("set_mixture_table: malformed table");
+    t.nu.push_back(nu);
+    for (int k = 0; k < K; ++k) t.weights.push_back(ser[i + 2 + k]);
+    for (int k = 0; k < K; ++k) t.sigma.push_back(ser[i + 2 + K + k]);
+    for (int k = 0; k < K; ++k) t.mu.push_back(ser[i + 2 + 2 * K + k]);
+    t.offset.push_back(t.offset.back() + K);
+    i += 2 + 3 * (size_t)K;
+  }
+  t.largest = largest_index;
+  t.version = poisson_table_store().version + 1;
+  poisson_table_store() = t;
+}
+bool PoissonRegressionAuxMixSampler::mixture_table_is_set() { return !poisson_table_store().nu.empty(); }
+
+PoissonRegressionAuxMixSampler::PoissonRegressionAuxMixSampler(PoissonRegressionModel *model, const std::shared_ptr<MvnBase> &prior,
+                                                               int, RNG &seeding_rng)
+    : PosteriorSampler(seeding_rng), model_(model), prior_(prior), suf_(model ? model->xdim() : 0) {
+  if (!model) report_error("PoissonRegressionAuxMixSampler: null model");
+  if (!prior || prior->dim() != model->xdim()) report_error("Prior does not match model dimension.");
+  device_seed_ = seed_rng(rng());
+}
+void PoissonRegressionAuxMixSampler::on_seed() { device_seed_ = seed_rng(rng()); iteration_ = 0; }
+double PoissonRegressionAuxMixSampler::logpri() const { return prior_->logp(model_->Beta()); }
+void PoissonRegressionAuxMixSampler::draw() {
+  impute_latent_data();
+  draw_beta_given_complete_data();
+}
+void PoissonRegressionAuxMixSampler::impute_latent_data() {
+  if (latent_data_fixed_) return;
+  const PoissonTableStore &t(poisson_table_store());
+  if (t.nu.empty())
+    report_error("PoissonRegressionAuxMixSampler: no mixture table; call set_mixture_table with the serialized "
+                 "NormalMixtureApproximationTable (see boom_b200/data/poisson_mixture_table.json)");
+  const uint64_t seed = device_seed_, it = iteration_++;
+  const Vector &beta(model_->Beta());
+  run_device_step(*model_, packed_, [&](boomgpu_ctx *ctx, double *suf_dev) {
+    if (table_version_seen_ != t.version) {
+      int rc = boomgpu_set_poisson_table(ctx, (int)t.nu.size(), t.nu.data(), t.offset.data(), t.weights.data(), t.mu.data(),
+                                         t.sigma.data(), t.largest);
+      if (rc) return rc;
+      table_version_seen_ = t.version;
+    }
+    return boomgpu_poisson_step_device(ctx, beta.data(), seed, it, suf_dev);
+  });
+  suf_.reset(packed_.data(), model_->xdim());
+}
+void PoissonRegressionAuxMixSampler::draw_beta_given_complete_data() {
+  const int p = model_->xdim();
+  SpdMatrix ivar(prior_->siginv());
+  Vector ivar_mu(suf_.xty());
+  for (int i = 0; i < p; ++i) {
+    double s = 0;
+    for (int j = 0; j < p; ++j) {
+      ivar.a[(size_t)i * p + j] += suf_.xtx()(i, j);
+      s += prior_->siginv()(i, j) * prior_->mu()[j];
+    }
+    ivar_mu[i] += s;
+  }
+  model_->set_Beta(rmvn_suf_mt(rng(), ivar, ivar_mu));
+}
+
+PoissonRegressionSpikeSlabSampler::PoissonRegressionSpikeSlabSampler(PoissonRegressionModel *model, const std::shared_ptr<MvnBase> &slab,
+                                                                     const std::shared_ptr<VariableSelectionPrior> &spike,
+                                                                     int number_of_threads, RNG &seeding_rng)
+    : PoissonRegressionAuxMixSampler(model, slab, number_of_threads, seeding_rng), core_(slab, spike, true) {
+  if (spike->potential_nvars() != model->xdim()) report_error("Spike does not match model dimension.");
+}
+void PoissonRegressionSpikeSlabSampler::draw() {
+  impute_latent_data();
+  core_.draw_model_indicators(rng(), model_->coef(), suf_);
+  core_.draw_beta(rng(), model_->coef(), suf_);
+}
+double PoissonRegressionSpikeSlabSampler::logpri() const { return core_.logpri(model_->coef()); }
+
+}  // namespace BOOM_B200

@@ -1,0 +1,454 @@
+// boom_b200.hpp -- C++ host side of the B200-native auxiliary-mixture Gibbs samplers.
+//
+// The classes keep the surface of the reference (steve-the-bayesian/BOOM; file:line relative to
+// its root) for this path so that a BOOM user finds the calls they know:
+//
+//   Model::set_method / sample_posterior        Models/ModelTypes.hpp:81-100, Models/Policies/PriorPolicy.cpp:25-39
+//   PosteriorSampler::{draw,logpri,rng,set_seed} Models/PosteriorSamplers/PosteriorSampler.hpp:44-107
+//   BinomialLogitModel                          Models/Glm/BinomialLogitModel.hpp:33-87
+//   PoissonRegressionModel                      Models/Glm/PoissonRegressionModel.hpp:35-94
+//   MvnModel (as the MvnBase prior)             Models/MvnBase.hpp:92-139
+//   VariableSelectionPrior                      Models/Glm/VariableSelectionPrior.hpp:99-101, .cpp:271-300
+//   BinomialLogitAuxmixSampler                  Models/Glm/PosteriorSamplers/BinomialLogitAuxmixSampler.hpp:109-152
+//   BinomialLogitSpikeSlabSampler               Models/Glm/PosteriorSamplers/BinomialLogitSpikeSlabSampler.hpp:27-96
+//   PoissonRegressionAuxMixSampler              Models/Glm/PosteriorSamplers/PoissonRegressionAuxMixSampler.hpp:37-125
+//   PoissonRegressionSpikeSlabSampler           Models/Glm/PosteriorSamplers/PoissonRegressionSpikeSlabSampler.cpp:55-59
+//
+// What changes underneath: the worker pool of Models/PosteriorSamplers/Imputer.hpp:241-343 (one
+// virtual call and one rank-1 update per observation) is ONE device step through the C ABI of
+// include/boomgpu.h.  The small-state steps (Cholesky draw of beta, the sweep over the inclusion
+// indicators) stay on the host as in the reference.  There is no CPU fallback for the device step.
+//
+// This layer is standalone (no BOOM headers) so it builds and runs on the GPU box; the adapter in
+// boom_b200/boom_adapter derives the same samplers from BOOM::PosteriorSampler for a true drop-in.
+#pragma once
+
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+struct boomgpu_ctx;
+
+namespace BOOM_B200 {
+
+typedef std::vector<double> Vector;
+
+// report_error (cpputil/report_error.cpp:29-31): everything surfaces as std::runtime_error.
+[[noreturn]] void report_error(const std::string &msg);
+
+// distributions/rng.hpp:28-54
+class RNG {
+ public:
+  typedef std::uint_fast64_t RngIntType;
+  RNG() : generator_(8675309) {}
+  explicit RNG(RngIntType seed) : generator_(seed) {}
+  void seed(RngIntType s) { generator_.seed(s); }
+  double operator()() { return dist_(generator_); }
+  std::mt19937_64 &generator() { return generator_; }
+
+ private:
+  std::mt19937_64 generator_;
+  std::uniform_real_distribution<double> dist_;
+};
+struct GlobalRng { static RNG rng; };
+RNG::RngIntType seed_rng(RNG &rng = GlobalRng::rng);  // distributions/rng.cpp:39-47
+double runif_mt(RNG &rng, double lo = 0, double hi = 1);
+double rnorm_mt(RNG &rng, double mu = 0, double sd = 1);
+int random_int_mt(RNG &rng, int lo, int hi);            // distributions/random_int.cpp:26-29
+
+// Dense symmetric matrix, row major (== column major), p x p.
+struct SpdMatrix {
+  int dim = 0;
+  Vector a;
+  SpdMatrix() {}
+  explicit SpdMatrix(int p, double diag = 0.0) : dim(p), a((size_t)p * p, 0.0) {
+    for (int i = 0; i < p; ++i) a[(size_t)i * p + i] = diag;
+  }
+  double &operator()(int i, int j) { return a[(size_t)i * dim + j]; }
+  double operator()(int i, int j) const { return a[(size_t)i * dim + j]; }
+  int nrow() const { return dim; }
+};
+
+// LinAlg/Selector.hpp: which coefficients are in the model.
+class Selector {
+ public:
+  Selector() {}
+  explicit Selector(int n, bool all = true) : inc_(n, all) {}
+  int nvars_possible() const { return (int)inc_.size(); }
+  int nvars() const;
+  bool operator[](int i) const { return inc_[i]; }
+  void flip(int i) { inc_[i] = !inc_[i]; }
+  void add(int i) { inc_[i] = true; }
+  void drop(int i) { inc_[i] = false; }
+  void drop_all() { inc_.assign(inc_.size(), false); }
+  void add_all() { inc_.assign(inc_.size(), true); }
+  std::vector<int> included_positions() const;
+  Vector select(const Vector &v) const;
+  SpdMatrix select(const SpdMatrix &m) const;  // LinAlg/Selector.cpp:411-426
+  Vector expand(const Vector &sub) const;
+  const std::vector<bool> &bits() const { return inc_; }
+
+ private:
+  std::vector<bool> inc_;
+};
+
+// Models/MvnBase.hpp:92-139 -- the prior is read through mu() and siginv().
+class MvnBase {
+ public:
+  virtual ~MvnBase() {}
+  virtual int dim() const = 0;
+  virtual const Vector &mu() const = 0;
+  virtual const SpdMatrix &siginv() const = 0;
+  double logp(const Vector &x) const;
+};
+
+class MvnModel : public MvnBase {
+ public:
+  // ivar = false: V is the variance matrix (inverted here); true: V is the precision.
+  MvnModel(const Vector &mean, const SpdMatrix &V, bool ivar = false);
+  int dim() const override { return (int)mu_.size(); }
+  const Vector &mu() const override { return mu_; }
+  const SpdMatrix &siginv() const override { return siginv_; }
+
+ private:
+  Vector mu_;
+  SpdMatrix siginv_;
+};
+
+// Models/Glm/VariableSelectionPrior.cpp:271-300
+class VariableSelectionPrior {
+ public:
+  VariableSelectionPrior(int n, double inclusion_probability = 1.0);
+  explicit VariableSelectionPrior(const Vector &prior_inclusion_probabilities);
+  double logp(const Selector &inc) const;
+  void make_valid(Selector &inc) const;
+  const Vector &prior_inclusion_probabilities() const { return probs_; }
+  void set_max_model_size(int m) { max_model_size_ = m; }
+  int potential_nvars() const { return (int)probs_.size(); }
+
+ private:
+  Vector probs_, log_p_, log_q_;
+  int max_model_size_ = -1;
+};
+
+// Models/Glm/GlmCoefs.hpp:26-140 -- beta with exact zeros at excluded positions.
+class GlmCoefs {
+ public:
+  explicit GlmCoefs(int p, bool all = true) : beta_(p, 0.0), inc_(p, all) {}
+  const Vector &Beta() const { return beta_; }
+  void set_Beta(const Vector &b);
+  const Selector &inc() const { return inc_; }
+  void set_inc(const Selector &g);
+  Vector included_coefficients() const { return inc_.select(beta_); }
+  void set_included_coefficients(const Vector &b);
+  void drop_all() { inc_.drop_all(); beta_.assign(beta_.size(), 0.0); }
+  void add_all() { inc_.add_all(); }
+  void add(int i) { inc_.add(i); }
+  void drop(int i) { inc_.drop(i); beta_[i] = 0.0; }
+  int nvars() const { return inc_.nvars(); }
+  int nvars_possible() const { return inc_.nvars_possible(); }
+
+ private:
+  Vector beta_;
+  Selector inc_;
+};
+
+class PosteriorSampler;
+
+// The hook a multi-GPU launcher installs: sum the packed statistics (count doubles at a DEVICE
+// pointer, on the CUDA stream returned by DeviceData::stream()) over all ranks, in place.
+typedef std::function<void(double *suf_dev, int64_t count)> AllReduceFn;
+
+// Device residency of one model's data: the replacement of the AoS behind IID_DataPolicy::dat()
+// (Models/Policies/IID_DataPolicy.hpp:43-58).  Rows are packed once and re-packed when data change.
+class DeviceData {
+ public:
+  explicit DeviceData(int device = 0);
+  ~DeviceData();
+  DeviceData(const DeviceData &) = delete;
+  boomgpu_ctx *ctx() { return ctx_; }
+  void check(int rc) const;  // boomgpu status -> report_error
+  int device() const { return device_; }
+
+ private:
+  boomgpu_ctx *ctx_ = nullptr;
+  int device_ = 0;
+};
+
+// Common base of the two regression models: SoA data + coefficients + sampler list.
+class GlmModelBase {
+ public:
+  explicit GlmModelBase(int xdim, bool all = true) : coef_(xdim, all) {}
+  virtual ~GlmModelBase() {}
+  int xdim() const { return coef_.nvars_possible(); }
+  int64_t sample_size() const { return (int64_t)(x_.size() / (size_t)std::max(1, xdim())); }
+  GlmCoefs &coef() { return coef_; }
+  const GlmCoefs &coef() const { return coef_; }
+  const Vector &Beta() const { return coef_.Beta(); }
+  void set_Beta(const Vector &b) { coef_.set_Beta(b); }
+  Vector included_coefficients() const { return coef_.included_coefficients(); }
+  void set_included_coefficients(const Vector &b) { coef_.set_included_coefficients(b); }
+  void drop_all() { coef_.drop_all(); }
+
+  // Model::set_method / sample_posterior (Models/Policies/PriorPolicy.cpp:25-39)
+  void set_method(const std::shared_ptr<PosteriorSampler> &sampler);
+  void clear_methods() { samplers_.clear(); }
+  void sample_posterior();
+  double logpri() const;
+
+  // ---- device residency
+  void set_device(int device);            // which GPU holds this model's rows (default 0)
+  void set_row_offset(uint64_t first_global_row);  // this shard's first global row (multi-GPU)
+  void set_stream(void *cuda_stream);     // cudaStream_t the device step (and the all-reduce hook) runs on
+  void set_allreduce(const AllReduceFn &fn) { allreduce_ = fn; }
+  const AllReduceFn &allreduce() const { return allreduce_; }
+  // rows already resident in HBM (device pointers): nothing is copied; the caller keeps them alive
+  DeviceData &device_data();              // packs / uploads when stale
+  const Vector &x_rows() const { return x_; }
+  uint64_t data_version() const { return data_version_; }
+
+ protected:
+  virtual void upload(DeviceData &dev) = 0;
+  void touch() { ++data_version_; }
+  Vector x_;  // row major n x p
+  bool adopted_ = false;
+  int64_t adopted_n_ = 0;
+
+ private:
+  GlmCoefs coef_;
+  std::vector<std::shared_ptr<PosteriorSampler>> samplers_;
+  std::unique_ptr<DeviceData> dev_;
+  int device_ = 0;
+  uint64_t row_offset_ = 0;
+  uint64_t data_version_ = 1, uploaded_version_ = 0;
+  AllReduceFn allreduce_;
+  void *stream_ = nullptr;
+  bool have_stream_ = false;
+};
+
+class BinomialLogitModel : public GlmModelBase {
+ public:
+  explicit BinomialLogitModel(int xdim, bool all = true) : GlmModelBase(xdim, all) {}
+  // bulk constructor (Models/Glm/BinomialLogitModel.cpp:40-49): X row major n x p
+  BinomialLogitModel(int64_t n, int p, const double *X, const double *y, const double *ntrials);
+  // model->add_data(new BinomialRegressionData(y, n, x))  (BinomialRegressionData.hpp:25-55)
+  void add_data(double y, double n, const Vector &x);
+  void adopt_device_data(int64_t n, const double *dX, int64_t ldx, const double *dy, const double *dntrials);
+  int64_t nobs() const { return adopted_ ? adopted_n_ : (int64_t)y_.size(); }
+  // Models/Glm/BinomialLogitModel.cpp:140-180, value only, evaluated on the device
+  double log_likelihood(const Vector &beta);
+  double log_likelihood() { return log_likelihood(Beta()); }
+
+ protected:
+  void upload(DeviceData &dev) override;
+
+ private:
+  Vector y_, n_;
+  const double *dX_ = nullptr, *dy_ = nullptr, *dn_ = nullptr;
+  int64_t dldx_ = 0;
+};
+
+class PoissonRegressionModel : public GlmModelBase {
+ public:
+  explicit PoissonRegressionModel(int xdim, bool all = true) : GlmModelBase(xdim, all) {}
+  PoissonRegressionModel(int64_t n, int p, const double *X, const int64_t *y, const double *exposure);
+  // model->add_data(new PoissonRegressionData(y, x, exposure))  (PoissonRegressionData.hpp:25-62)
+  void add_data(int64_t y, const Vector &x, double exposure = 1.0);
+  void adopt_device_data(int64_t n, const double *dX, int64_t ldx, const int64_t *dy, const double *dexposure);
+  int64_t nobs() const { return adopted_ ? adopted_n_ : (int64_t)y_.size(); }
+  double log_likelihood(const Vector &beta);
+  double log_likelihood() { return log_likelihood(Beta()); }
+  const std::vector<int64_t> &y() const { return y_; }
+
+ protected:
+  void upload(DeviceData &dev) override;
+
+ private:
+  std::vector<int64_t> y_;
+  Vector exposure_;
+  const double *dX_ = nullptr, *dexp_ = nullptr;
+  const int64_t *dy_ = nullptr;
+  int64_t dldx_ = 0;
+};
+
+// Models/PosteriorSamplers/PosteriorSampler.hpp:44-107
+class PosteriorSampler {
+ public:
+  explicit PosteriorSampler(RNG &seeding_rng) : rng_(seed_rng(seeding_rng)) {}
+  virtual ~PosteriorSampler() {}
+  virtual void draw() = 0;
+  virtual double logpri() const = 0;
+  RNG &rng() const { return rng_; }
+  void set_seed(unsigned long s) { rng_.seed(s); on_seed(); }
+
+ protected:
+  virtual void on_seed() {}
+
+ private:
+  mutable RNG rng_;
+};
+
+// BinomialLogit::SufficientStatistics (BinomialLogitAuxmixSampler.hpp:39-67) and, with the four
+// scalars, WeightedRegSuf (Models/Glm/WeightedRegressionModel.hpp:40-110).
+class WeightedRegSuf {
+ public:
+  explicit WeightedRegSuf(int p = 0) : xtx_(p), xty_(p, 0.0) {}
+  void clear();
+  // rank-1 update on the host: the path state-space callers drive (fix_latent_data(true))
+  void add_data(const Vector &x, double y, double w);            // WeightedRegressionModel.cpp:161-169
+  void update(const Vector &x, double weighted_value, double weight);  // BinomialLogitAuxmixSampler.cpp:61-67
+  // bulk load of a device result (WeightedRegSuf::reset, WeightedRegressionModel.cpp:148-157)
+  void reset(const double *packed, int p);
+  const SpdMatrix &xtx() const { return xtx_; }
+  const Vector &xty() const { return xty_; }
+  double n() const { return n_; }
+  double yty() const { return yty_; }
+  double sumw() const { return sumw_; }
+  double sumlogw() const { return sumlogw_; }
+  int64_t sample_size() const { return (int64_t)(n_ + 0.5); }
+
+ private:
+  SpdMatrix xtx_;
+  Vector xty_;
+  double n_ = 0, yty_ = 0, sumw_ = 0, sumlogw_ = 0;
+};
+typedef WeightedRegSuf SufficientStatistics;
+
+// The host-side spike-and-slab steps shared by the logit and Poisson samplers
+// (BinomialLogitSpikeSlabSampler.cpp:56-117,180-222; SpikeSlabSampler.cpp:40-216 with sigsq = 1).
+class SpikeSlabCore {
+ public:
+  SpikeSlabCore(const std::shared_ptr<MvnBase> &slab, const std::shared_ptr<VariableSelectionPrior> &spike,
+                bool fisher_yates);
+  double log_model_prob(const Selector &g, const WeightedRegSuf &suf) const;
+  void draw_model_indicators(RNG &rng, GlmCoefs &coef, const WeightedRegSuf &suf) const;
+  void draw_beta(RNG &rng, GlmCoefs &coef, const WeightedRegSuf &suf) const;
+  double logpri(const GlmCoefs &coef) const;
+  void allow_model_selection(bool tf) { allow_model_selection_ = tf; }
+  void limit_model_selection(int max_flips) { max_flips_ = max_flips; }
+  bool model_selection_allowed() const { return allow_model_selection_; }
+
+ private:
+  std::shared_ptr<MvnBase> slab_;
+  std::shared_ptr<VariableSelectionPrior> spike_;
+  bool fisher_yates_;
+  bool allow_model_selection_ = true;
+  int max_flips_ = -1;
+};
+
+// ---------------------------------------------------------------------------------------------
+class BinomialLogitAuxmixSampler : public PosteriorSampler {
+ public:
+  BinomialLogitAuxmixSampler(BinomialLogitModel *model, const std::shared_ptr<MvnBase> &prior,
+                             int clt_threshold = 10, RNG &seeding_rng = GlobalRng::rng);
+  void draw() override;                // impute_latent_data(); draw_params();   (.cpp:115-118)
+  double logpri() const override;
+  void impute_latent_data();           // ONE device step instead of the worker pool
+  void draw_params();                  // .cpp:125-130
+  const SufficientStatistics &suf() const { return suf_; }
+  int clt_threshold() const { return clt_threshold_; }
+  void clear_complete_data_sufficient_statistics() { suf_.clear(); }
+  void update_complete_data_sufficient_statistics(double precision_weighted_sum, double total_precision,
+                                                  const Vector &x) { suf_.update(x, precision_weighted_sum, total_precision); }
+  // LatentDataSampler surface (Models/PosteriorSamplers/Imputer.hpp:260-314)
+  void fix_latent_data(bool fixed = true) { latent_data_fixed_ = fixed; }
+  void set_number_of_workers(int) {}       // the device replaces the worker pool
+  void reassign_data_each_time(bool) {}    // rows are re-packed whenever the model's data change
+  uint64_t iteration() const { return iteration_; }
+
+ protected:
+  void on_seed() override;
+  BinomialLogitModel *model_;
+  std::shared_ptr<MvnBase> prior_;
+
+ private:
+  SufficientStatistics suf_;
+  int clt_threshold_;
+  bool latent_data_fixed_ = false;
+  uint64_t device_seed_, iteration_ = 0;
+  Vector packed_;
+};
+
+class BinomialLogitSpikeSlabSampler : public BinomialLogitAuxmixSampler {
+ public:
+  BinomialLogitSpikeSlabSampler(BinomialLogitModel *model, const std::shared_ptr<MvnBase> &slab,
+                                const std::shared_ptr<VariableSelectionPrior> &spike, int clt_threshold = 5,
+                                RNG &seeding_rng = GlobalRng::rng);
+  void draw() override;                // .cpp:50-54
+  double logpri() const override;
+  void draw_model_indicators();        // .cpp:180-211
+  void draw_beta();                    // .cpp:56-75
+  double log_model_prob(const Selector &g) const;  // .cpp:88-117
+  void allow_model_selection(bool tf) { core_.allow_model_selection(tf); }
+  void limit_model_selection(int max_flips) { core_.limit_model_selection(max_flips); }
+  int xdim() const { return model_->xdim(); }
+
+ private:
+  SpikeSlabCore core_;
+};
+
+class PoissonRegressionAuxMixSampler : public PosteriorSampler {
+ public:
+  PoissonRegressionAuxMixSampler(PoissonRegressionModel *model, const std::shared_ptr<MvnBase> &prior,
+                                 int number_of_threads = 1, RNG &seeding_rng = GlobalRng::rng);
+  void draw() override;                // .cpp:108-111
+  double logpri() const override;
+  void impute_latent_data();
+  void draw_beta_given_complete_data();  // .cpp:123-128
+  const WeightedRegSuf &complete_data_sufficient_statistics() const { return suf_; }
+  void clear_complete_data_sufficient_statistics() { suf_.clear(); }
+  void update_complete_data_sufficient_statistics(double precision_weighted_sum, double total_precision,
+                                                  const Vector &x) {  // .cpp:153-158
+    suf_.add_data(x, precision_weighted_sum / total_precision, total_precision);
+  }
+  void fix_latent_data(bool fixed = true) { latent_data_fixed_ = fixed; }
+  void set_number_of_workers(int) {}
+  // The mixture table (PoissonDataImputer::mixture_table_): serialized as
+  // NormalMixtureApproximationTable::serialize() writes it (NormalMixtureApproximation.cpp:534-542).
+  // Must hold every distinct count of the data below largest_index.
+  static void set_mixture_table(const Vector &serialized, int64_t largest_index);
+  static bool mixture_table_is_set();
+
+ protected:
+  void on_seed() override;
+  PoissonRegressionModel *model_;
+  std::shared_ptr<MvnBase> prior_;
+  WeightedRegSuf suf_;
+
+ private:
+  bool latent_data_fixed_ = false;
+  uint64_t device_seed_, iteration_ = 0, table_version_seen_ = 0;
+  Vector packed_;
+};
+
+class PoissonRegressionSpikeSlabSampler : public PoissonRegressionAuxMixSampler {
+ public:
+  PoissonRegressionSpikeSlabSampler(PoissonRegressionModel *model, const std::shared_ptr<MvnBase> &slab,
+                                    const std::shared_ptr<VariableSelectionPrior> &spike, int number_of_threads = 1,
+                                    RNG &seeding_rng = GlobalRng::rng);
+  void draw() override;                // PoissonRegressionSpikeSlabSampler.cpp:55-59
+  double logpri() const override;
+  void allow_model_selection(bool tf) { core_.allow_model_selection(tf); }
+  void limit_model_selection(int max_flips) { core_.limit_model_selection(max_flips); }
+
+ private:
+  SpikeSlabCore core_;
+};
+
+// The logit mixture every BinomialLogit sampler uploads; defaults to the 9-component table of
+// Fruhwirth-Schnatter & Fruhwirth that the reference hard-codes (NormalMixtureApproximation.cpp:416-424);
+// the BOOM adapter overwrites it from the live BinomialLogitDataImputer::mixture_approximation.
+void set_logit_mixture(const Vector &mu, const Vector &sigma, const Vector &weights);
+
+// ---- host linear algebra used by the small-state steps (exposed for tests) -----------------
+// in-place lower Cholesky of a row-major n x n matrix; returns false when not positive definite
+bool cholesky_lower(double *a, int n);
+void lsolve_inplace(const double *L, int n, double *b);   // L x = b
+void ltsolve_inplace(const double *L, int n, double *b);  // L' x = b
+Vector rmvn_suf_mt(RNG &rng, const SpdMatrix &ivar, const Vector &ivar_mu);  // distributions/mvn.cpp:128-136
+
+}  // namespace BOOM_B200

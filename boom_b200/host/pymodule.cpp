@@ -1,0 +1,245 @@
+// pymodule.cpp -- pybind11 view of boom_b200.hpp, shaped like the reference's own bindings
+// (Interfaces/python/BayesBoom/Models/Glm/GlmModel_def.cpp:935-1055): models, priors, samplers,
+// model.set_method(sampler), model.sample_posterior().
+#include <pybind11/functional.h>
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "boom_b200.hpp"
+
+namespace py = pybind11;
+using namespace BOOM_B200;
+
+namespace {
+typedef py::array_t<double, py::array::c_style | py::array::forcecast> NpD;
+typedef py::array_t<int64_t, py::array::c_style | py::array::forcecast> NpI;
+
+SpdMatrix to_spd(const NpD &a) {
+  if (a.ndim() != 2 || a.shape(0) != a.shape(1)) report_error("expected a square matrix");
+  SpdMatrix m((int)a.shape(0));
+  std::copy(a.data(), a.data() + a.size(), m.a.begin());
+  return m;
+}
+NpD from_spd(const SpdMatrix &m) {
+  NpD out({m.dim, m.dim});
+  std::copy(m.a.begin(), m.a.end(), out.mutable_data());
+  return out;
+}
+Vector to_vec(const NpD &a) { return Vector(a.data(), a.data() + a.size()); }
+NpD from_vec(const Vector &v) {
+  NpD out((py::ssize_t)v.size());
+  std::copy(v.begin(), v.end(), out.mutable_data());
+  return out;
+}
+
+template <class M>
+void bind_model_common(py::class_<M, std::shared_ptr<M>> &c) {
+  c.def_property_readonly("xdim", &M::xdim)
+      .def_property_readonly("sample_size", [](const M &m) { return m.nobs(); })
+      .def_property("Beta", [](const M &m) { return from_vec(m.Beta()); }, [](M &m, const NpD &b) { m.set_Beta(to_vec(b)); })
+      .def("set_Beta", [](M &m, const NpD &b) { m.set_Beta(to_vec(b)); })
+      .def_property_readonly("inc", [](const M &m) {
+        py::array_t<bool> out((py::ssize_t)m.xdim());
+        for (int i = 0; i < m.xdim(); ++i) out.mutable_data()[i] = m.coef().inc()[i];
+        return out;
+      })
+      .def("set_inc", [](M &m, const std::vector<bool> &bits) {
+        Selector g((int)bits.size(), false);
+        for (size_t i = 0; i < bits.size(); ++i) if (bits[i]) g.add((int)i);
+        m.coef().set_inc(g);
+      })
+      .def("drop_all", &M::drop_all)
+      .def("add", [](M &m, int i) { m.coef().add(i); })
+      .def("set_method", [](M &m, const std::shared_ptr<PosteriorSampler> &s) { m.set_method(s); })
+      .def("clear_methods", &M::clear_methods)
+      .def("sample_posterior", [](M &m) { py::gil_scoped_release rel; m.sample_posterior(); })
+      .def("logpri", &M::logpri)
+      .def("set_device", &M::set_device)
+      .def("set_row_offset", &M::set_row_offset)
+      .def("set_stream", [](M &m, uintptr_t s) { m.set_stream(reinterpret_cast<void *>(s)); })
+      .def("set_allreduce", [](M &m, py::object fn) {
+        if (fn.is_none()) { m.set_allreduce(AllReduceFn()); return; }
+        m.set_allreduce([fn](double *dev, int64_t count) {
+          py::gil_scoped_acquire acq;
+          fn(reinterpret_cast<uintptr_t>(dev), count);
+        });
+      })
+      .def("log_likelihood", [](M &m) { return m.log_likelihood(); })
+      .def("log_likelihood", [](M &m, const NpD &b) { return m.log_likelihood(to_vec(b)); });
+}
+}  // namespace
+
+PYBIND11_MODULE(_host, m) {
+  m.doc() = "B200-native auxiliary-mixture Gibbs samplers behind BOOM's sampler surface";
+
+  py::class_<RNG>(m, "RNG").def(py::init<>()).def(py::init<RNG::RngIntType>()).def("seed", [](RNG &r, RNG::RngIntType s) { r.seed(s); })
+      .def("__call__", [](RNG &r) { return r(); });
+  m.def("global_rng", []() -> RNG & { return GlobalRng::rng; }, py::return_value_policy::reference);
+  m.def("set_logit_mixture", [](const NpD &mu, const NpD &sigma, const NpD &w) { set_logit_mixture(to_vec(mu), to_vec(sigma), to_vec(w)); });
+  m.def("set_poisson_mixture_table", [](const NpD &ser, int64_t largest) {
+    PoissonRegressionAuxMixSampler::set_mixture_table(to_vec(ser), largest);
+  });
+
+  py::class_<MvnBase, std::shared_ptr<MvnBase>>(m, "MvnBase");
+  py::class_<MvnModel, MvnBase, std::shared_ptr<MvnModel>>(m, "MvnModel")
+      .def(py::init([](const NpD &mu, const NpD &V, bool ivar) { return std::make_shared<MvnModel>(to_vec(mu), to_spd(V), ivar); }),
+           py::arg("mu"), py::arg("Sigma"), py::arg("ivar") = false)
+      .def_property_readonly("mu", [](const MvnModel &p) { return from_vec(p.mu()); })
+      .def_property_readonly("siginv", [](const MvnModel &p) { return from_spd(p.siginv()); })
+      .def("logp", [](const MvnModel &p, const NpD &x) { return p.logp(to_vec(x)); });
+  py::class_<VariableSelectionPrior, std::shared_ptr<VariableSelectionPrior>>(m, "VariableSelectionPrior")
+      .def(py::init<int, double>(), py::arg("n"), py::arg("inclusion_probability") = 1.0)
+      .def(py::init([](const NpD &probs) { return std::make_shared<VariableSelectionPrior>(to_vec(probs)); }))
+      .def("set_max_model_size", &VariableSelectionPrior::set_max_model_size);
+
+  py::class_<BinomialLogitModel, std::shared_ptr<BinomialLogitModel>> blm(m, "BinomialLogitModel");
+  blm.def(py::init<int, bool>(), py::arg("xdim"), py::arg("all") = true)
+      .def(py::init([](const NpD &X, const NpD &y, const NpD &n) {
+        if (X.ndim() != 2 || y.size() != X.shape(0) || n.size() != X.shape(0)) report_error("BinomialLogitModel(X, y, n): shape mismatch");
+        return std::make_shared<BinomialLogitModel>((int64_t)X.shape(0), (int)X.shape(1), X.data(), y.data(), n.data());
+      }))
+      .def("add_data", [](BinomialLogitModel &mo, double y, double n, const NpD &x) { mo.add_data(y, n, to_vec(x)); })
+      .def("adopt_device_data", [](BinomialLogitModel &mo, int64_t n, uintptr_t dX, int64_t ldx, uintptr_t dy, uintptr_t dn) {
+        mo.adopt_device_data(n, reinterpret_cast<const double *>(dX), ldx, reinterpret_cast<const double *>(dy),
+                             reinterpret_cast<const double *>(dn));
+      });
+  bind_model_common(blm);
+
+  py::class_<PoissonRegressionModel, std::shared_ptr<PoissonRegressionModel>> prm(m, "PoissonRegressionModel");
+  prm.def(py::init<int, bool>(), py::arg("xdim"), py::arg("all") = true)
+      .def(py::init([](const NpD &X, const NpI &y, const NpD &e) {
+        if (X.ndim() != 2 || y.size() != X.shape(0) || e.size() != X.shape(0)) report_error("PoissonRegressionModel(X, y, exposure): shape mismatch");
+        return std::make_shared<PoissonRegressionModel>((int64_t)X.shape(0), (int)X.shape(1), X.data(), y.data(), e.data());
+      }))
+      .def("add_data", [](PoissonRegressionModel &mo, int64_t y, const NpD &x, double e) { mo.add_data(y, to_vec(x), e); },
+           py::arg("y"), py::arg("x"), py::arg("exposure") = 1.0)
+      .def("adopt_device_data", [](PoissonRegressionModel &mo, int64_t n, uintptr_t dX, int64_t ldx, uintptr_t dy, uintptr_t de) {
+        mo.adopt_device_data(n, reinterpret_cast<const double *>(dX), ldx, reinterpret_cast<const int64_t *>(dy),
+                             reinterpret_cast<const double *>(de));
+      });
+  bind_model_common(prm);
+
+  py::class_<WeightedRegSuf>(m, "WeightedRegSuf")
+      .def_property_readonly("xtx", [](const WeightedRegSuf &s) { return from_spd(s.xtx()); })
+      .def_property_readonly("xty", [](const WeightedRegSuf &s) { return from_vec(s.xty()); })
+      .def_property_readonly("n", &WeightedRegSuf::n)
+      .def_property_readonly("yty", &WeightedRegSuf::yty)
+      .def_property_readonly("sumw", &WeightedRegSuf::sumw)
+      .def_property_readonly("sumlogw", &WeightedRegSuf::sumlogw)
+      .def_property_readonly("sample_size", &WeightedRegSuf::sample_size);
+
+  py::class_<PosteriorSampler, std::shared_ptr<PosteriorSampler>>(m, "PosteriorSampler")
+      .def("draw", [](PosteriorSampler &s) { py::gil_scoped_release rel; s.draw(); })
+      .def("logpri", &PosteriorSampler::logpri)
+      .def("set_seed", &PosteriorSampler::set_seed);
+
+  py::class_<BinomialLogitAuxmixSampler, PosteriorSampler, std::shared_ptr<BinomialLogitAuxmixSampler>>(m, "BinomialLogitAuxmixSampler")
+      .def(py::init([](BinomialLogitModel *model, const std::shared_ptr<MvnBase> &prior, int clt, RNG &rng) {
+             return std::make_shared<BinomialLogitAuxmixSampler>(model, prior, clt, rng);
+           }),
+           py::arg("model"), py::arg("prior"), py::arg("clt_threshold") = 10, py::arg("seeding_rng") = std::ref(GlobalRng::rng),
+           py::keep_alive<1, 2>())
+      .def("impute_latent_data", [](BinomialLogitAuxmixSampler &s) { py::gil_scoped_release rel; s.impute_latent_data(); })
+      .def("draw_params", &BinomialLogitAuxmixSampler::draw_params)
+      .def_property_readonly("suf", &BinomialLogitAuxmixSampler::suf, py::return_value_policy::reference_internal)
+      .def_property_readonly("clt_threshold", &BinomialLogitAuxmixSampler::clt_threshold)
+      .def("clear_complete_data_sufficient_statistics", &BinomialLogitAuxmixSampler::clear_complete_data_sufficient_statistics)
+      .def("update_complete_data_sufficient_statistics",
+           [](BinomialLogitAuxmixSampler &s, double sum, double prec, const NpD &x) {
+             s.update_complete_data_sufficient_statistics(sum, prec, to_vec(x));
+           })
+      .def("fix_latent_data", &BinomialLogitAuxmixSampler::fix_latent_data, py::arg("fixed") = true)
+      .def("set_number_of_workers", &BinomialLogitAuxmixSampler::set_number_of_workers);
+
+  py::class_<BinomialLogitSpikeSlabSampler, BinomialLogitAuxmixSampler, std::shared_ptr<BinomialLogitSpikeSlabSampler>>(
+      m, "BinomialLogitSpikeSlabSampler")
+      .def(py::init([](BinomialLogitModel *model, const std::shared_ptr<MvnBase> &slab,
+                       const std::shared_ptr<VariableSelectionPrior> &spike, int clt, RNG &rng) {
+             return std::make_shared<BinomialLogitSpikeSlabSampler>(model, slab, spike, clt, rng);
+           }),
+           py::arg("model"), py::arg("slab"), py::arg("spike"), py::arg("clt_threshold") = 5,
+           py::arg("seeding_rng") = std::ref(GlobalRng::rng), py::keep_alive<1, 2>())
+      .def("draw_model_indicators", &BinomialLogitSpikeSlabSampler::draw_model_indicators)
+      .def("draw_beta", &BinomialLogitSpikeSlabSampler::draw_beta)
+      .def("log_model_prob", [](const BinomialLogitSpikeSlabSampler &s, const std::vector<bool> &bits) {
+        Selector g((int)bits.size(), false);
+        for (size_t i = 0; i < bits.size(); ++i) if (bits[i]) g.add((int)i);
+        return s.log_model_prob(g);
+      })
+      .def("allow_model_selection", &BinomialLogitSpikeSlabSampler::allow_model_selection)
+      .def("limit_model_selection", &BinomialLogitSpikeSlabSampler::limit_model_selection);
+
+  py::class_<PoissonRegressionAuxMixSampler, PosteriorSampler, std::shared_ptr<PoissonRegressionAuxMixSampler>>(
+      m, "PoissonRegressionAuxMixSampler")
+      .def(py::init([](PoissonRegressionModel *model, const std::shared_ptr<MvnBase> &prior, int nthreads, RNG &rng) {
+             return std::make_shared<PoissonRegressionAuxMixSampler>(model, prior, nthreads, rng);
+           }),
+           py::arg("model"), py::arg("prior"), py::arg("number_of_threads") = 1, py::arg("seeding_rng") = std::ref(GlobalRng::rng),
+           py::keep_alive<1, 2>())
+      .def("impute_latent_data", [](PoissonRegressionAuxMixSampler &s) { py::gil_scoped_release rel; s.impute_latent_data(); })
+      .def("draw_beta_given_complete_data", &PoissonRegressionAuxMixSampler::draw_beta_given_complete_data)
+      .def_property_readonly("complete_data_sufficient_statistics", &PoissonRegressionAuxMixSampler::complete_data_sufficient_statistics,
+                             py::return_value_policy::reference_internal)
+      .def("clear_complete_data_sufficient_statistics", &PoissonRegressionAuxMixSampler::clear_complete_data_sufficient_statistics)
+      .def("update_complete_data_sufficient_statistics",
+           [](PoissonRegressionAuxMixSampler &s, double sum, double prec, const NpD &x) {
+             s.update_complete_data_sufficient_statistics(sum, prec, to_vec(x));
+           })
+      .def("fix_latent_data", &PoissonRegressionAuxMixSampler::fix_latent_data, py::arg("fixed") = true)
+      .def("set_number_of_workers", &PoissonRegressionAuxMixSampler::set_number_of_workers);
+
+  py::class_<PoissonRegressionSpikeSlabSampler, PoissonRegressionAuxMixSampler, std::shared_ptr<PoissonRegressionSpikeSlabSampler>>(
+      m, "PoissonRegressionSpikeSlabSampler")
+      .def(py::init([](PoissonRegressionModel *model, const std::shared_ptr<MvnBase> &slab,
+                       const std::shared_ptr<VariableSelectionPrior> &spike, int nthreads, RNG &rng) {
+             return std::make_shared<PoissonRegressionSpikeSlabSampler>(model, slab, spike, nthreads, rng);
+           }),
+           py::arg("model"), py::arg("slab"), py::arg("spike"), py::arg("number_of_threads") = 1,
+           py::arg("seeding_rng") = std::ref(GlobalRng::rng), py::keep_alive<1, 2>())
+      .def("allow_model_selection", &PoissonRegressionSpikeSlabSampler::allow_model_selection)
+      .def("limit_model_selection", &PoissonRegressionSpikeSlabSampler::limit_model_selection);
+
+  // host linear algebra, exposed for the CPU-side tests
+  m.def("cholesky_lower", [](const NpD &a) {
+    SpdMatrix s = to_spd(a);
+    bool ok = cholesky_lower(s.a.data(), s.dim);
+    return py::make_tuple(ok, from_spd(s));
+  });
+  m.def("rmvn_suf", [](RNG &rng, const NpD &ivar, const NpD &ivar_mu) { return from_vec(rmvn_suf_mt(rng, to_spd(ivar), to_vec(ivar_mu))); });
+  m.def("spike_slab_sweep", [](RNG &rng, const NpD &xtx, const NpD &xty, const std::shared_ptr<MvnBase> &slab,
+                               const std::shared_ptr<VariableSelectionPrior> &spike, std::vector<bool> bits, int sweeps, bool fisher_yates) {
+    // host-only driver of the inclusion sweep + beta draw on fixed statistics (CPU tests of the small-state steps)
+    const int p = (int)xty.size();
+    Vector packed((size_t)p * p + p + 4, 0.0);
+    std::copy(xtx.data(), xtx.data() + (size_t)p * p, packed.begin());
+    std::copy(xty.data(), xty.data() + p, packed.begin() + (size_t)p * p);
+    WeightedRegSuf suf(p);
+    suf.reset(packed.data(), p);
+    GlmCoefs coef(p, false);
+    Selector g(p, false);
+    for (int i = 0; i < p; ++i) if (bits[i]) g.add(i);
+    coef.set_inc(g);
+    SpikeSlabCore core(slab, spike, fisher_yates);
+    Vector inc_sum(p, 0.0), beta_sum(p, 0.0);
+    for (int s = 0; s < sweeps; ++s) {
+      core.draw_model_indicators(rng, coef, suf);
+      core.draw_beta(rng, coef, suf);
+      for (int i = 0; i < p; ++i) { inc_sum[i] += coef.inc()[i]; beta_sum[i] += coef.Beta()[i]; }
+    }
+    for (int i = 0; i < p; ++i) { inc_sum[i] /= sweeps; beta_sum[i] /= sweeps; }
+    return py::make_tuple(from_vec(inc_sum), from_vec(beta_sum));
+  });
+  m.def("log_model_prob", [](const NpD &xtx, const NpD &xty, const std::shared_ptr<MvnBase> &slab,
+                             const std::shared_ptr<VariableSelectionPrior> &spike, std::vector<bool> bits) {
+    const int p = (int)xty.size();
+    Vector packed((size_t)p * p + p + 4, 0.0);
+    std::copy(xtx.data(), xtx.data() + (size_t)p * p, packed.begin());
+    std::copy(xty.data(), xty.data() + p, packed.begin() + (size_t)p * p);
+    WeightedRegSuf suf(p);
+    suf.reset(packed.data(), p);
+    Selector g(p, false);
+    for (int i = 0; i < p; ++i) if (bits[i]) g.add(i);
+    return SpikeSlabCore(slab, spike, false).log_model_prob(g, suf);
+  });
+}

@@ -112,6 +112,11 @@ int boomgpu_poisson_step_device(boomgpu_ctx *ctx, const double *beta, uint64_t s
                                 double *suf_dev);
 /* waits for the context's stream and reports device-side validation errors of the steps since the last call */
 int boomgpu_synchronize(boomgpu_ctx *ctx);
+/* a context-owned device buffer of boomgpu_suf_len(p) doubles for the *_step_device variants */
+int boomgpu_suf_buffer(boomgpu_ctx *ctx, double **suf_dev);
+/* device -> host copy of count doubles on the context's stream (through pinned staging), then
+ * boomgpu_synchronize: the read side of a step_device + all-reduce sequence */
+int boomgpu_download(boomgpu_ctx *ctx, const double *src_dev, double *dst_host, int64_t count);
 
 /* ---- parity / test hooks --------------------------------------------------------------- */
 /* deterministic accumulation from caller supplied latents (host arrays of length n) */

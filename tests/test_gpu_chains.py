@@ -1,0 +1,161 @@
+"""Posterior agreement with the reference's own CPU chains (tests/golden/ref_chains.json, written by
+oracle/ref_driver.cpp from the unmodified reference) on the same synthetic data, through the
+drop-in sampler surface: model.set_method(sampler); model.sample_posterior().
+
+Tolerance (BASELINE.json north_star: 'within Monte Carlo standard error'): chains are autocorrelated,
+so the standard error of a posterior mean is taken as sd * sqrt(tau / N) with tau = 10."""
+import numpy as np
+import pytest
+
+import boom_b200
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TAU = 10.0
+
+
+def _check_moments(draws, ref_mean, ref_sd, n_ref):
+    mean, sd = draws.mean(0), draws.std(0)
+    se = np.sqrt(ref_sd ** 2 * TAU / n_ref + sd ** 2 * TAU / len(draws))
+    assert np.all(np.abs(mean - ref_mean) < 4 * se + 1e-4), (mean, ref_mean, se)
+    big = ref_sd > 0.01
+    np.testing.assert_allclose(sd[big], ref_sd[big], rtol=0.15)
+
+
+def _run(model, iters, burn):
+    out = []
+    for it in range(iters):
+        model.sample_posterior()
+        if it >= burn:
+            out.append(model.Beta.copy())
+    return np.array(out)
+
+
+def test_logit_auxmix_posterior(golden):
+    g = golden("ref_chains.json"); c = g["logit_auxmix"]
+    X, y, nt, _ = O.synth_binomial(c["n"], c["p"], c["nonzero"], c["seed"], c["max_trials"])
+    model = boom_b200.BinomialLogitModel(X, y, nt)
+    prior = boom_b200.MvnModel(np.zeros(c["p"]), np.eye(c["p"]))
+    sampler = boom_b200.BinomialLogitAuxmixSampler(model, prior, 10, boom_b200.RNG(42))
+    model.set_method(sampler)
+    draws = _run(model, 4000, 500)
+    _check_moments(draws, np.array(g["logit_auxmix_mean"]), np.array(g["logit_auxmix_sd"]), c["iters"] - c["burn"])
+    assert sampler.suf.sample_size == c["n"]
+
+
+def test_logit_binomial_clt_posterior(golden):
+    g = golden("ref_chains.json"); c = g["logit_binomial"]
+    X, y, nt, _ = O.synth_binomial(c["n"], c["p"], c["nonzero"], c["seed"], c["max_trials"])
+    model = boom_b200.BinomialLogitModel(X, y, nt)
+    sampler = boom_b200.BinomialLogitAuxmixSampler(model, boom_b200.MvnModel(np.zeros(c["p"]), np.eye(c["p"])), 10,
+                                                   boom_b200.RNG(43))
+    model.set_method(sampler)
+    draws = _run(model, 4000, 500)
+    _check_moments(draws, np.array(g["logit_binomial_mean"]), np.array(g["logit_binomial_sd"]), c["iters"] - c["burn"])
+
+
+def test_logit_spike_slab_posterior(golden):
+    g = golden("ref_chains.json"); c = g["logit_spike_slab"]
+    p = c["p"]
+    X, y, nt, _ = O.synth_binomial(c["n"], p, c["nonzero"], c["seed"], c["max_trials"])
+    model = boom_b200.BinomialLogitModel(X, y, nt)
+    slab = boom_b200.MvnModel(np.zeros(p), np.eye(p))
+    spike = boom_b200.VariableSelectionPrior(p, c["prior_inclusion"])
+    sampler = boom_b200.BinomialLogitSpikeSlabSampler(model, slab, spike, 10, boom_b200.RNG(44))
+    model.set_method(sampler)
+    betas, incs = [], []
+    for it in range(4000):
+        model.sample_posterior()
+        if it >= 500:
+            betas.append(model.Beta.copy()); incs.append(model.inc.copy())
+    betas, incs = np.array(betas), np.array(incs, dtype=float)
+    ref_inc = np.array(g["logit_spike_slab_inclusion"])
+    assert np.max(np.abs(incs.mean(0) - ref_inc)) < 0.05
+    strong = ref_inc > 0.95
+    _check_moments(betas[:, strong], np.array(g["logit_spike_slab_mean"])[strong], np.array(g["logit_spike_slab_sd"])[strong],
+                   c["iters"] - c["burn"])
+    # excluded coefficients are exact zeros (GlmCoefs.cpp:304-309)
+    assert np.all(betas[incs == 0] == 0)
+
+
+def test_poisson_auxmix_posterior(golden):
+    g = golden("ref_chains.json"); c = g["poisson_auxmix"]
+    X, y, ex, _ = O.synth_poisson(c["n"], c["p"], c["nonzero"], c["seed"])
+    boom_b200.load_poisson_mixture_table()
+    model = boom_b200.PoissonRegressionModel(X, y, ex)
+    sampler = boom_b200.PoissonRegressionAuxMixSampler(model, boom_b200.MvnModel(np.zeros(c["p"]), np.eye(c["p"])), 1,
+                                                       boom_b200.RNG(45))
+    model.set_method(sampler)
+    draws = _run(model, 4000, 500)
+    _check_moments(draws, np.array(g["poisson_auxmix_mean"]), np.array(g["poisson_auxmix_sd"]), c["iters"] - c["burn"])
+    suf = sampler.complete_data_sufficient_statistics
+    assert suf.n == c["n"] + np.count_nonzero(y)
+
+
+def test_poisson_spike_slab_recovers_signal():
+    """The R test of the reference (Interfaces/R/BoomSpikeSlab/tests/testthat/test-poisson.R:70-124):
+    the true variables are found, the noise variables are not."""
+    n, p = 4000, 10
+    X, y, ex, beta = O.synth_poisson(n, p, 3, seed=99)
+    boom_b200.load_poisson_mixture_table()
+    model = boom_b200.PoissonRegressionModel(X, y, ex)
+    sampler = boom_b200.PoissonRegressionSpikeSlabSampler(model, boom_b200.MvnModel(np.zeros(p), np.eye(p)),
+                                                          boom_b200.VariableSelectionPrior(p, 0.3), 1, boom_b200.RNG(46))
+    model.set_method(sampler)
+    incs = []
+    for it in range(1500):
+        model.sample_posterior()
+        if it >= 300:
+            incs.append(model.inc.copy())
+    inc = np.array(incs, dtype=float).mean(0)
+    assert np.all(inc[:4] > 0.9) and np.all(inc[4:] < 0.2)
+
+
+def test_same_seed_repeatability():
+    """test-logit.R:23-45 of the reference: the same seed gives the same chain."""
+    X, y, nt, _ = O.synth_binomial(2000, 6, 3, seed=8)
+    out = []
+    for _ in range(2):
+        model = boom_b200.BinomialLogitModel(X, y, nt)
+        sampler = boom_b200.BinomialLogitSpikeSlabSampler(model, boom_b200.MvnModel(np.zeros(6), np.eye(6)),
+                                                          boom_b200.VariableSelectionPrior(6, 0.5), 10, boom_b200.RNG(5))
+        model.set_method(sampler)
+        out.append(_run(model, 30, 0))
+    np.testing.assert_array_equal(out[0], out[1])
+
+
+def test_externally_driven_statistics():
+    """The state-space callers' path (StateSpaceLogitPosteriorSampler.cpp:58,111-123): latent data fixed,
+    statistics pushed row by row, then draw_params()."""
+    X, y, nt, _ = O.synth_binomial(300, 3, 2, seed=4)
+    model = boom_b200.BinomialLogitModel(X, y, nt)
+    sampler = boom_b200.BinomialLogitAuxmixSampler(model, boom_b200.MvnModel(np.zeros(3), np.eye(3)), 10, boom_b200.RNG(3))
+    sampler.fix_latent_data(True)
+    sampler.clear_complete_data_sufficient_statistics()
+    rng = np.random.default_rng(0)
+    w = 0.2 + rng.random(300); s = rng.normal(size=300)
+    for i in range(300):
+        sampler.update_complete_data_sufficient_statistics(s[i], w[i], X[i])
+    sampler.impute_latent_data()   # must be a no-op now
+    xtx, xty = O.accumulate(X, w, s)
+    np.testing.assert_allclose(sampler.suf.xtx, xtx, rtol=1e-12)
+    np.testing.assert_allclose(sampler.suf.xty, xty, rtol=1e-12)
+    sampler.draw_params()
+    assert np.all(np.isfinite(model.Beta))
+
+
+def test_data_added_after_construction_is_picked_up():
+    X, y, nt, _ = O.synth_binomial(500, 4, 2, seed=6)
+    model = boom_b200.BinomialLogitModel(4)
+    for i in range(250):
+        model.add_data(y[i], nt[i], X[i])
+    sampler = boom_b200.BinomialLogitAuxmixSampler(model, boom_b200.MvnModel(np.zeros(4), np.eye(4)), 10, boom_b200.RNG(2))
+    model.set_method(sampler)
+    model.sample_posterior()
+    assert sampler.suf.sample_size == 250
+    for i in range(250, 500):
+        model.add_data(y[i], nt[i], X[i])
+    model.sample_posterior()
+    assert sampler.suf.sample_size == 500
+    assert model.log_likelihood() == pytest.approx(O.binomial_logit_loglike(X, y, nt, model.Beta), rel=1e-12)

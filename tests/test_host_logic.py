@@ -1,0 +1,118 @@
+"""CPU tests of the host-side small-state steps (the parts that stay on the host as in the
+reference): Cholesky, the beta draw, log_model_prob and the inclusion sweep, on FIXED
+sufficient statistics.  No GPU, no oracle needed: the checks are against numpy / exact enumeration.
+Reference: BinomialLogitSpikeSlabSampler.cpp:56-117,180-222; distributions/mvn.cpp:128-136."""
+import itertools
+
+import numpy as np
+import pytest
+
+import boom_b200
+
+
+def _suf(p, n=400, seed=0):
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(n, p)); X[:, 0] = 1
+    w = 0.1 + rng.random(n)
+    beta = np.zeros(p); beta[:3] = [0.8, -0.7, 0.6]
+    z = X @ beta + rng.normal(size=n) / np.sqrt(w)
+    return (X.T * w) @ X, X.T @ (w * z)
+
+
+def test_cholesky_matches_numpy():
+    h = boom_b200.host()
+    xtx, _ = _suf(40)
+    ok, L = h.cholesky_lower(xtx)
+    assert ok
+    np.testing.assert_allclose(L, np.linalg.cholesky(xtx), rtol=1e-12, atol=1e-12)
+    ok, _ = h.cholesky_lower(-np.eye(3))
+    assert not ok
+
+
+def test_rmvn_suf_moments():
+    h = boom_b200.host()
+    p = 4
+    xtx, xty = _suf(p)
+    rng = boom_b200.RNG(11)
+    draws = np.array([h.rmvn_suf(rng, xtx, xty) for _ in range(20000)])
+    cov = np.linalg.inv(xtx)
+    mean = cov @ xty
+    se = np.sqrt(np.diag(cov) / len(draws))
+    assert np.all(np.abs(draws.mean(0) - mean) < 5 * se)
+    mc = 5 * np.sqrt(np.outer(np.diag(cov), np.diag(cov)) * 2 / len(draws))   # 5 sigma of a covariance estimate
+    assert np.all(np.abs(np.cov(draws.T) - cov) < mc)
+
+
+def _log_model_prob_numpy(xtx, xty, mu, siginv, probs, g):
+    idx = np.flatnonzero(g)
+    num = np.sum(np.where(g, np.log(probs), np.log1p(-probs)))
+    if len(idx) == 0:
+        return num
+    iv = siginv[np.ix_(idx, idx)]
+    num += 0.5 * np.linalg.slogdet(iv)[1]
+    m = mu[idx]
+    num -= 0.5 * m @ iv @ m
+    post = iv + xtx[np.ix_(idx, idx)]
+    L = np.linalg.cholesky(post)
+    S = np.linalg.solve(L, xty[idx] + iv @ m)
+    denom = np.sum(np.log(np.diag(L))) - 0.5 * S @ S
+    return num - denom
+
+
+def test_log_model_prob_matches_formula():
+    h = boom_b200.host()
+    p = 7
+    xtx, xty = _suf(p, seed=3)
+    mu = np.linspace(-0.2, 0.2, p)
+    A = np.random.default_rng(1).normal(size=(p, p)); siginv = A @ A.T + p * np.eye(p)
+    probs = np.full(p, 0.3)
+    slab = boom_b200.MvnModel(mu, siginv, True)
+    spike = boom_b200.VariableSelectionPrior(probs)
+    for g in ([1, 0, 0, 0, 0, 0, 0], [1, 1, 1, 0, 0, 1, 0], [0] * 7, [1] * 7):
+        g = np.array(g, dtype=bool)
+        assert h.log_model_prob(xtx, xty, slab, spike, list(g)) == pytest.approx(
+            _log_model_prob_numpy(xtx, xty, mu, siginv, probs, g), rel=1e-11, abs=1e-9)
+
+
+@pytest.mark.parametrize("fisher_yates", [False, True])
+def test_inclusion_sweep_matches_exact_enumeration(fisher_yates):
+    """Marginal inclusion probabilities of the Gibbs sweep on fixed statistics vs the exact
+    posterior over all 2^p models (p = 6)."""
+    h = boom_b200.host()
+    p = 6
+    xtx, xty = _suf(p, n=60, seed=5)
+    mu = np.zeros(p); siginv = np.eye(p)
+    probs = np.full(p, 0.4)
+    slab = boom_b200.MvnModel(mu, siginv, True)
+    spike = boom_b200.VariableSelectionPrior(probs)
+    lp, gs = [], []
+    for bits in itertools.product([0, 1], repeat=p):
+        g = np.array(bits, dtype=bool)
+        gs.append(g); lp.append(_log_model_prob_numpy(xtx, xty, mu, siginv, probs, g))
+    lp = np.array(lp); w = np.exp(lp - lp.max()); w /= w.sum()
+    exact = (np.array(gs) * w[:, None]).sum(0)
+    inc, _ = h.spike_slab_sweep(boom_b200.RNG(7), xtx, xty, slab, spike, [True] + [False] * (p - 1), 30000, fisher_yates)
+    assert np.max(np.abs(inc - exact)) < 0.02
+
+
+def test_spike_prior_limits():
+    spike = boom_b200.VariableSelectionPrior(np.array([1.0, 0.5, 0.0]))
+    slab = boom_b200.MvnModel(np.zeros(3), np.eye(3))
+    xtx, xty = _suf(3)
+    h = boom_b200.host()
+    # variable 2 has prior probability 0: including it is a zero-support point
+    assert h.log_model_prob(xtx, xty, slab, spike, [True, False, True]) == -np.inf
+    inc, _ = h.spike_slab_sweep(boom_b200.RNG(1), xtx, xty, slab, spike, [True, False, False], 200, False)
+    assert inc[0] == 1.0 and inc[2] == 0.0
+
+
+def test_errors_surface_as_exceptions():
+    with pytest.raises(RuntimeError, match="wrong size"):
+        boom_b200.BinomialLogitModel(3).add_data(1, 1, np.zeros(2))
+    with pytest.raises(RuntimeError, match=r"\[0, n\]"):
+        boom_b200.BinomialLogitModel(2).add_data(3, 1, np.zeros(2))
+    with pytest.raises(RuntimeError, match="dimension"):
+        boom_b200.BinomialLogitAuxmixSampler(boom_b200.BinomialLogitModel(3), boom_b200.MvnModel(np.zeros(2), np.eye(2)))
+    m = boom_b200.PoissonRegressionModel(2)
+    with pytest.raises(RuntimeError, match="no sampler"):
+        m.sample_posterior()
