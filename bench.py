@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- Gibbs iterations/sec of the auxiliary-mixture hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One step = one Gibbs iteration of the named workload: device step (latent draws + X'WX, X'Wz on this
+rank's rows) -> NCCL all-reduce of the packed statistics (N > 1) -> device->host copy of the statistics ->
+host small-state step (inclusion sweep + Cholesky draw of beta, as in the reference) -> beta host->device.
+Nothing is skipped or cached between steps (W changes every iteration).
+
+  value  iterations/s with the rows adopted from device tensors (resident in HBM before the timed region),
+         timed with CUDA events on the context's stream around the K steps, max over ranks.
+  e2e    the same iterations/s through the public sampler surface (model.set_method(sampler);
+         model.sample_posterior()) on a model built from HOST arrays, host wall clock around K steps;
+         every step copies beta host->device and the statistics device->host.  The rows themselves are
+         uploaded once by the first draw (they are the model's data, not a per-step input); that one-time
+         copy is reported beside it (upload_once_*), not hidden.
+  roofline      the dominant kernel of the workload, from CUDA events around every launch of that kernel
+                inside the timed region (boomgpu option "timing").
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref/boom_ref_driver, built from /root/reference by
+                oracle/build_ref.sh) on this box's host cores, on a bounded row sample of the same workload.
+
+Strong scaling: the workload's n is fixed; N ranks hold n/N rows each (BASELINE.json: "n=10M,p=500 at 1/2/4/8 GPU").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# name: (kind, sampler, n, p, nonzero) -- BASELINE.json configs[0..4]
+WORKLOADS = {
+    "c1": ("logit", "auxmix", 100_000, 20, 5),
+    "c2": ("poisson", "auxmix", 1_000_000, 50, 5),
+    "c3": ("logit", "spike", 10_000_000, 500, 20),
+    "c4": ("logit", "spike", 2_000_000, 4000, 40),
+    "c5": ("logit", "auxmix", 200_000_000, 16, 5),
+}
+DESCR = {
+    "c1": "BinomialLogitAuxmixSampler n=100k p=20 (BASELINE.json configs[0])",
+    "c2": "PoissonRegressionAuxMixSampler n=1M p=50 (configs[1])",
+    "c3": "BinomialLogitSpikeSlabSampler n=10M p=500, 20 true nonzeros (configs[2], the config the metric is quoted on)",
+    "c4": "BinomialLogitSpikeSlabSampler n=2M p=4000 (configs[3])",
+    "c5": "BinomialLogitAuxmixSampler n=200M p=16 (configs[4])",
+}
+SEED = 20261017
+CHUNK = 50_000                 # rows per generator chunk: the data do not depend on the sharding
+FP64_DMMA_PEAK_TFLOPS = 37.0   # measured on this pool's B200 (profiles/r01_microbench_fp64.jsonl, DMMA issue-rate test)
+HBM_FALLBACK_GBS = 6650.0
+
+
+def beta_true(kind, p, nonzero):
+    import numpy as np
+    b = np.zeros(p)
+    b[0] = -1.0 if kind == "logit" else 0.5
+    for j in range(1, min(p - 1, nonzero) + 1):
+        b[j] = 0.5 if j % 2 else -0.5
+    return b
+
+
+def make_shard(kind, n, p, nonzero, row0, row1, dev):
+    """Rows [row0, row1) of the synthetic data set, generated on the device chunk by chunk."""
+    import torch
+    rows = row1 - row0
+    X = torch.empty((rows, p), dtype=torch.float64, device=dev)
+    y = torch.empty(rows, dtype=torch.float64 if kind == "logit" else torch.int64, device=dev)
+    bt = torch.tensor(beta_true(kind, p, nonzero), dtype=torch.float64, device=dev)
+    g = torch.Generator(device=dev)
+    for c in range(row0 // CHUNK, (row1 + CHUNK - 1) // CHUNK):
+        g.manual_seed(SEED + c)
+        c0, c1 = c * CHUNK, min(n, (c + 1) * CHUNK)
+        xc = torch.empty((c1 - c0, p), dtype=torch.float64, device=dev).normal_(generator=g)
+        if kind == "poisson":
+            xc.mul_(0.3)
+        xc[:, 0] = 1.0
+        eta = xc @ bt
+        if kind == "logit":
+            yc = (torch.rand(c1 - c0, dtype=torch.float64, device=dev, generator=g) < torch.sigmoid(eta)).double()
+        else:
+            yc = torch.poisson(torch.exp(eta), generator=g).long()
+        a, b = max(c0, row0), min(c1, row1)
+        X[a - row0:b - row0] = xc[a - c0:b - c0]
+        y[a - row0:b - row0] = yc[a - c0:b - c0]
+        del xc, eta, yc
+    aux = torch.ones(rows, dtype=torch.float64, device=dev)  # trials / exposure
+    return X, y, aux
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [f.strip() for f in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for (_, r) in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [nm for k, nm in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "MEASURED_PEAKS.json"
+    except (OSError, ValueError):
+        return {"hbm_gbs": HBM_FALLBACK_GBS}, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(kind, sampler, n, p, nonzero, steps, warmup, sample_rows=None, threads=None):
+    """The unmodified reference on the host cores, on the first sample_rows rows' worth of the workload."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "boom_ref_driver")
+    if not os.path.exists(exe):
+        return None, "oracle/_ref/boom_ref_driver missing (build with __graft_entry__.build() where /root/reference exists)"
+    cores = threads or os.cpu_count() or 1
+    if sample_rows is None:
+        # ~1-2 s per reference iteration on 16 cores: per-row cost ~ (0.5 + 0.26 p^2 / 1000) us single threaded
+        per_row_us = 0.6 + 0.00026 * p * p
+        sample_rows = int(min(n, 2_000_000, max(20_000, 1.5e6 * cores / per_row_us)))
+    mode = {"auxmix": "logit", "spike": "spike"}[sampler] if kind == "logit" else "poisson"
+    out = subprocess.run([exe, "bench", mode, str(sample_rows), str(p), str(nonzero), str(cores), str(steps), str(warmup)],
+                         capture_output=True, text=True, timeout=3000)
+    if out.returncode != 0:
+        return None, "reference driver failed: " + out.stderr.strip()[-200:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    r["sample_rows"] = sample_rows
+    r["cores"] = cores
+    # per-row cost is constant (Imputer.hpp:177-179) and the host small-state step is negligible beside it,
+    # so iterations/s at the workload's n = iterations/s on the sample * sample_rows / n
+    r["iters_per_sec_at_n"] = r["iters_per_sec"] * sample_rows / n
+    return r, None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-array e2e leg (development aid)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rows", type=int, default=0, help="override n (development aid; the line then names the override)")
+    args = ap.parse_args()
+    kind, sampler, n, p, nonzero = WORKLOADS[args.workload]
+    if args.rows:
+        n = args.rows
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    steps, warmup = args.steps, max(args.warmup, 0)
+    metric = "gibbs_iterations_per_sec"
+    cfg = {"workload": DESCR[args.workload] + (" [rows overridden to %d]" % n if args.rows else ""), "n": n, "p": p,
+           "true_nonzeros": nonzero, "sampler": sampler, "prior": "slab N(0, I); spike pi_j = %d/%d" % (nonzero, p)
+           if sampler == "spike" else "N(0, I)", "parallelism": "rows sharded over %d GPU(s), one all-reduce of p*p+p+4 doubles per iteration" % world}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r, why = run_reference(kind, sampler, n, p, nonzero, steps, warmup)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": why}))
+            return 0
+        v = r["iters_per_sec_at_n"]
+        sample = "first %d of %d rows (same generator), %d iterations after %d warm-up, scaled linearly in n" % (
+            r["sample_rows"], n, steps, warmup)
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": v, "unit": "iter/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": cfg, "obs_per_sec": v * n,
+            "cpu_baseline": {"value": v, "unit": "iter/s", "cores": r["cores"], "kind": "reference", "sample": sample,
+                             "measured_iters_per_sec_on_sample": r["iters_per_sec"]},
+            "e2e": {"value": v, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import boom_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: boom_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+
+    from boom_b200 import distributed as shard
+    row0, row1 = shard.shard_range(n, world, rank)
+    X, y, aux = make_shard(kind, n, p, nonzero, row0, row1, dev)
+    torch.cuda.synchronize()
+    if kind == "poisson":
+        boom_b200.load_poisson_mixture_table()
+
+    def build(model):
+        prior = boom_b200.MvnModel(np.zeros(p), np.eye(p))
+        rng = boom_b200.RNG(SEED)
+        if sampler == "spike":
+            model.drop_all()
+            model.add(0)   # chains start with only the intercept (GlmCoefs(p, all=false), as R's InitializeCoefficients does)
+            spike = boom_b200.VariableSelectionPrior(p, min(1.0, max(nonzero, 1) / p))
+            s = boom_b200.BinomialLogitSpikeSlabSampler(model, prior, spike, 10, rng)
+        elif kind == "logit":
+            s = boom_b200.BinomialLogitAuxmixSampler(model, prior, 10, rng)
+        else:
+            s = boom_b200.PoissonRegressionAuxMixSampler(model, prior, 1, rng)
+        model.set_method(s)
+        shard.attach(model, n, stream, dev, rank, world)
+        model.set_device_option("timing", 1)
+        return s
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- leg 1: rows resident in HBM (adopted device tensors), CUDA-event timed
+    Model = boom_b200.BinomialLogitModel if kind == "logit" else boom_b200.PoissonRegressionModel
+    model = Model(p)
+    model.adopt_device_data(row1 - row0, X.data_ptr(), p, y.data_ptr(), aux.data_ptr())
+    smp = build(model)
+    for _ in range(warmup):
+        model.sample_posterior()
+    barrier()
+    model.kernel_timings(True)
+    launches0 = model.kernel_launches()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(steps):
+        model.sample_posterior()
+    e1.record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = model.kernel_launches() - launches0
+    tm = model.kernel_timings(False)
+    clk = clocks.stop(t0, t1) if clocks else None
+    beta_end = np.array(model.Beta)
+    nvars = int(np.count_nonzero(np.array(model.inc)))
+    if world > 1:   # every rank runs the same host chain on the same all-reduced statistics
+        b = torch.tensor(beta_end, device=dev)
+        lo, hi = b.clone(), b.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi), "ranks diverged"
+    value = steps / (dev_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel; per-rank rows, this rank's launches
+    peaks, peak_src = measured_peaks()
+    my_rows = row1 - row0
+    per = {k: (v[0] / max(v[1], 1), v[1]) for k, v in tm.items()}
+    if p > 64:
+        k_ms = per["syrk_dmma"][0]
+        flops = float(my_rows) * p * (p + 1) + 2.0 * my_rows * p   # weighted SYRK (upper triangle) + X'Wz, FMA = 2
+        roof = {"kernel": "syrk_dmma_kernel", "bound": "tensor", "achieved": flops / (k_ms * 1e-3) * 1e-12,
+                "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "peak_source": "FP64 DMMA issue-rate microbenchmark on this pool "
+                "(profiles/r01_microbench_fp64.jsonl; cuBLAS DGEMM 8192^3 = 35.4); MEASURED_PEAKS.json has no FP64 entry",
+                "algorithmic_flops_per_launch": flops}
+    else:
+        k_ms = per["fused_small"][0]
+        nbytes = 8.0 * my_rows * (p + 2)
+        roof = {"kernel": "fused_small_kernel", "bound": "hbm", "achieved": nbytes / (k_ms * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "peak_source": peak_src, "algorithmic_bytes_per_launch": nbytes}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["kernel_ms"] = k_ms
+    roof["traffic"] = None   # filled from the committed ncu capture (profiles/), see DESIGN.md
+    roof["kernel_ms_per_step"] = {k: round(v[0] * v[1] / steps, 4) for k, v in per.items() if v[1]}
+
+    # ---- leg 2: e2e through the sampler surface on a model built from HOST arrays
+    e2e = None
+    if not args.no_e2e:
+        del model, smp
+        Xh = X.cpu().numpy()
+        yh = y.cpu().numpy()
+        ah = aux.cpu().numpy()
+        del X, y, aux
+        torch.cuda.empty_cache()
+        model = Model(Xh, yh, ah)
+        nbytes_up = Xh.nbytes + yh.nbytes + ah.nbytes
+        del Xh
+        smp = build(model)
+        barrier()
+        tu = time.perf_counter()
+        model.sample_posterior()     # packs and uploads the rows (once), then the first iteration
+        barrier()
+        first = time.perf_counter() - tu
+        for _ in range(max(warmup - 1, 0)):
+            model.sample_posterior()
+        barrier()
+        ta = time.perf_counter()
+        for _ in range(steps):
+            model.sample_posterior()
+        barrier()
+        wall = max_over_ranks(time.perf_counter() - ta)
+        e2e = {"value": steps / wall, "unit": "iter/s", "h2d_bytes_per_step": 8 * p * world,
+               "d2h_bytes_per_step": 8 * (p * p + p + 4) * world, "timer": "host wall clock, max over ranks",
+               "upload_once_bytes": nbytes_up * 1, "first_iteration_with_upload_s": max_over_ranks(first)}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r, why = run_reference(kind, sampler, n, p, nonzero, 3, 1)
+        if r is None:
+            cpu = {"unavailable": why}
+        else:
+            cpu = {"value": r["iters_per_sec_at_n"], "unit": "iter/s", "cores": r["cores"], "kind": "reference",
+                   "sample": "first %d of %d rows, 3 iterations after 1 warm-up, %d worker threads, scaled linearly in n" % (
+                       r["sample_rows"], n, r["cores"]), "measured_iters_per_sec_on_sample": r["iters_per_sec"]}
+
+    if rank == 0:
+        cfg["timing"] = "inputs (%.1f GB per GPU) larger than L2; CUDA events on the context stream; max over ranks" % (
+            8e-9 * my_rows * (p + 2))
+        line = {"metric": metric, "value": value, "unit": "iter/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": cfg, "obs_per_sec": value * n, "gpu_launches": int(launches) * world,
+                "clocks": clk, "roofline": roof, "model_size_at_end": nvars}
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,131 @@
+// adapter_demo.cpp -- TEST DRIVER (links the compiled reference; the binary lands in oracle/_ref/).
+//
+// The drop-in claim, executed: a BOOM program builds BOOM's own BinomialLogitModel / PoissonRegressionModel,
+// then attaches EITHER the reference sampler OR the B200 sampler with model->set_method(sampler) and calls
+// model->sample_posterior().  Prints one JSON line with the posterior summaries of both chains on the same
+// data; tests/test_gpu_adapter.py compares them within Monte Carlo error.
+//   usage: boom_adapter_demo <logit|spike|poisson|pspike> n p nonzero iters burn
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "Models/Glm/BinomialLogitModel.hpp"
+#include "Models/Glm/BinomialRegressionData.hpp"
+#include "Models/Glm/PoissonRegressionData.hpp"
+#include "Models/Glm/PoissonRegressionModel.hpp"
+#include "Models/Glm/PosteriorSamplers/BinomialLogitAuxmixSampler.hpp"
+#include "Models/Glm/PosteriorSamplers/BinomialLogitSpikeSlabSampler.hpp"
+#include "Models/Glm/PosteriorSamplers/PoissonRegressionAuxMixSampler.hpp"
+#include "Models/Glm/PosteriorSamplers/PoissonRegressionSpikeSlabSampler.hpp"
+#include "Models/Glm/VariableSelectionPrior.hpp"
+#include "Models/MvnModel.hpp"
+#include "distributions.hpp"
+
+#include "boom_b200_adapter.hpp"
+
+using namespace BOOM;
+
+namespace {
+struct Summary { Vector mean, sd, inc; double secs; };
+
+template <class MODEL>
+Summary run(const Ptr<MODEL> &model, int iters, int burn) {
+  const int p = model->xdim();
+  Vector s1(p, 0.0), s2(p, 0.0), inc(p, 0.0);
+  auto t0 = std::chrono::steady_clock::now();
+  for (int it = 0; it < iters; ++it) {
+    model->sample_posterior();
+    if (it >= burn) {
+      const Vector &b(model->Beta());
+      for (int j = 0; j < p; ++j) { s1[j] += b[j]; s2[j] += b[j] * b[j]; inc[j] += model->coef().inc()[j]; }
+    }
+  }
+  Summary out;
+  out.secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  const double m = iters - burn;
+  out.mean = s1 / m; out.sd = Vector(p); out.inc = inc / m;
+  for (int j = 0; j < p; ++j) out.sd[j] = std::sqrt(std::max(0.0, s2[j] / m - out.mean[j] * out.mean[j]));
+  return out;
+}
+
+void print_vec(const char *name, const Vector &v, bool comma = true) {
+  printf("\"%s\": [", name);
+  for (size_t i = 0; i < v.size(); ++i) printf("%s%.10g", i ? ", " : "", v[i]);
+  printf("]%s", comma ? ", " : "");
+}
+void print_summary(const char *tag, const Summary &s) {
+  printf("\"%s\": {", tag);
+  print_vec("mean", s.mean); print_vec("sd", s.sd); print_vec("inclusion", s.inc);
+  printf("\"seconds\": %.4f}", s.secs);
+}
+}  // namespace
+
+int main(int argc, char **argv) {
+  if (argc < 7) { fprintf(stderr, "usage: %s <logit|spike|poisson|pspike> n p nonzero iters burn\n", argv[0]); return 2; }
+  const std::string kind = argv[1];
+  const int n = atoi(argv[2]), p = atoi(argv[3]), nonzero = atoi(argv[4]), iters = atoi(argv[5]), burn = atoi(argv[6]);
+  try {
+    GlobalRng::rng.seed(20261017);
+    const bool poisson = kind == "poisson" || kind == "pspike";
+    Vector beta(p, 0.0);
+    beta[0] = poisson ? 0.5 : -1.0;
+    for (int j = 1; j <= nonzero && j < p; ++j) beta[j] = (j % 2) ? 0.5 : -0.5;
+    std::vector<Vector> xs;
+    std::vector<double> ys;
+    for (int i = 0; i < n; ++i) {
+      Vector x(p);
+      x[0] = 1.0;
+      for (int j = 1; j < p; ++j) x[j] = rnorm(0, poisson ? 0.3 : 1.0);
+      const double eta = x.dot(beta);
+      xs.push_back(x);
+      ys.push_back(poisson ? rpois(exp(eta)) : (runif() < plogis(eta) ? 1.0 : 0.0));
+    }
+    NEW(MvnModel, slab)(Vector(p, 0.0), SpdMatrix(p, 1.0));
+    NEW(VariableSelectionPrior, spike)(p, std::min(1.0, (nonzero + 1.0) / p));
+    Summary ref, gpu;
+    for (int arm = 0; arm < 2; ++arm) {
+      if (!poisson) {
+        NEW(BinomialLogitModel, model)(p);
+        for (int i = 0; i < n; ++i) model->add_data(new BinomialRegressionData(ys[i], 1.0, xs[i]));
+        if (kind == "spike") { model->coef().drop_all(); model->coef().add(0); }
+        Ptr<PosteriorSampler> sampler;
+        RNG seeder(arm == 0 ? 11 : 12);
+        if (kind == "spike") {
+          if (arm == 0) sampler = new BinomialLogitSpikeSlabSampler(model.get(), slab, spike, 10, seeder);
+          else sampler = new B200::BinomialLogitSpikeSlabSampler(model.get(), slab, spike, 10, seeder);
+        } else {
+          if (arm == 0) sampler = new BinomialLogitAuxmixSampler(model.get(), slab, 10, seeder);
+          else sampler = new B200::BinomialLogitAuxmixSampler(model.get(), slab, 10, seeder);
+        }
+        model->set_method(sampler);
+        (arm == 0 ? ref : gpu) = run(model, iters, burn);
+      } else {
+        NEW(PoissonRegressionModel, model)(p);
+        for (int i = 0; i < n; ++i) model->add_data(new PoissonRegressionData((int64_t)ys[i], xs[i], 1.0));
+        if (kind == "pspike") { model->coef().drop_all(); model->coef().add(0); }
+        Ptr<PosteriorSampler> sampler;
+        RNG seeder(arm == 0 ? 21 : 22);
+        if (kind == "pspike") {
+          if (arm == 0) sampler = new PoissonRegressionSpikeSlabSampler(model.get(), slab, spike, 1, seeder);
+          else sampler = new B200::PoissonRegressionSpikeSlabSampler(model.get(), slab, spike, 1, seeder);
+        } else {
+          if (arm == 0) sampler = new PoissonRegressionAuxMixSampler(model.get(), slab, 1, seeder);
+          else sampler = new B200::PoissonRegressionAuxMixSampler(model.get(), slab, 1, seeder);
+        }
+        model->set_method(sampler);
+        (arm == 0 ? ref : gpu) = run(model, iters, burn);
+      }
+    }
+    printf("{\"kind\": \"%s\", \"n\": %d, \"p\": %d, \"iters\": %d, \"burn\": %d, ", kind.c_str(), n, p, iters, burn);
+    print_vec("beta_true", beta);
+    print_summary("reference", ref); printf(", ");
+    print_summary("b200", gpu);
+    printf("}\n");
+  } catch (std::exception &e) {
+    fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "fused_tma.cuh"
 
 using namespace boomgpu;
 
@@ -41,7 +42,9 @@ struct boomgpu_ctx {
   uint64_t row_offset = 0;
 
   // mixtures
-  LogitMixture mix{};
+  LogitMixture mix{};        // host copy
+  LogitHot hot{};
+  LogitMixture *mix_dev = nullptr;
   bool have_mix = false;
   PoissonTable tab{};
   bool have_tab = false;
@@ -58,8 +61,13 @@ struct boomgpu_ctx {
   int *err_dev = nullptr;
   int *err_pin = nullptr;
 
+  // TMA descriptor of X for the single-pass kernel (re-encoded when the data or the tile shape change)
+  CUtensorMap xmap;
+  const double *xmap_X = nullptr; int64_t xmap_n = -1, xmap_ldx = -1; int xmap_p = -1, xmap_nb = -1;
+
   // options / instrumentation
   int path = 0;
+  int small_variant = 0;  // 0 auto (TMA kernel when X qualifies), 1 force the cp.async kernel
   bool timing = false;
   int64_t launches = 0;
   std::vector<TimedLaunch> timed;
@@ -228,6 +236,73 @@ struct SmallLauncher {
   }
 };
 
+// ---- TMA descriptor: row-major X as a 2-D tensor {p, n}, box {8 NB + 4, 32} (wider than p: pad columns read as zero)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int ensure_xmap(boomgpu_ctx *ctx, int nb) {
+  if (ctx->xmap_X == ctx->X && ctx->xmap_n == ctx->n && ctx->xmap_ldx == ctx->ldx && ctx->xmap_p == ctx->p && ctx->xmap_nb == nb)
+    return 0;
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, BOOMGPU_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)ctx->p, (cuuint64_t)ctx->n};
+  const cuuint64_t strides[1] = {(cuuint64_t)ctx->ldx * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)tma_padw(nb), 32u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = encode(&ctx->xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(ctx->X), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, BOOMGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for n=%lld p=%d ldx=%lld", (int)r,
+                                     (long long)ctx->n, ctx->p, (long long)ctx->ldx);
+  ctx->xmap_X = ctx->X; ctx->xmap_n = ctx->n; ctx->xmap_ldx = ctx->ldx; ctx->xmap_p = ctx->p; ctx->xmap_nb = nb;
+  return 0;
+}
+
+// X can be described to TMA: 16-byte aligned base and row pitch, rows addressable with 32-bit coordinates
+bool tma_ok(const boomgpu_ctx *ctx) { return (ctx->ldx % 2 == 0) && aligned16(ctx->X) && ctx->n < (int64_t)0x7fffffc0; }
+
+template <int MODEL>
+struct TmaLauncher {
+  template <int NB>
+  static int go(boomgpu_ctx *ctx, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts) {
+    auto kern = fused_tma_kernel<NB, MODEL>;
+    constexpr int NW = tma_warps(NB);
+    const size_t smem = tma_smem_bytes(NB);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = ensure_xmap(ctx, NB)) return rc;
+    const int64_t nslices = (d.n + 31) / 32;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nslices + NW - 1) / NW, (int64_t)ctx->sms));
+    if (ensure(ctx, &ctx->partials, &ctx->partials_cap, (int64_t)grid * tma_partial_len(NB))) return BOOMGPU_ERR_CUDA;
+    {
+      LaunchScope ls(ctx, 0);
+      kern<<<grid, 32 * NW, smem, ctx->stream>>>(ctx->xmap, d, prm, out, ctx->beta_dev, ctx->partials, ctx->err_dev);
+    }
+    CU(cudaGetLastError());
+    *nparts = grid;
+    return 0;
+  }
+  static int dispatch(boomgpu_ctx *ctx, int nb, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts) {
+    switch (nb) {
+      case 1: return go<1>(ctx, d, prm, out, nparts);
+      case 2: return go<2>(ctx, d, prm, out, nparts);
+      case 3: return go<3>(ctx, d, prm, out, nparts);
+      case 4: return go<4>(ctx, d, prm, out, nparts);
+      case 5: return go<5>(ctx, d, prm, out, nparts);
+      case 6: return go<6>(ctx, d, prm, out, nparts);
+      case 7: return go<7>(ctx, d, prm, out, nparts);
+      case 8: return go<8>(ctx, d, prm, out, nparts);
+    }
+    return fail(ctx, BOOMGPU_ERR_ARG, "bad column block count %d", nb);
+  }
+};
+
 template <int MODEL>
 cudaError_t launch_impute_rows(boomgpu_ctx *ctx, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts) {
   const bool vec2 = (d.ldx % 2 == 0) && aligned16(d.X);
@@ -343,12 +418,18 @@ int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, c
   if (path == 1) {
     int nparts = 0;
     const int nb = (p + 7) / 8;
-    cudaError_t e = SmallLauncher<MODEL>::dispatch(ctx, nb, d, prm, out, &nparts);
-    if (e != cudaSuccess) return fail(ctx, BOOMGPU_ERR_CUDA, "fused_small_kernel launch failed: %s", cudaGetErrorString(e));
+    if (tma_ok(ctx) && ctx->small_variant != 1) {
+      // TMA-fed warp-autonomous kernel (fused_tma.cuh)
+      if (int rc = TmaLauncher<MODEL>::dispatch(ctx, nb, d, prm, out, &nparts)) return rc;
+    } else {
+      // X cannot be described to TMA (odd leading dimension / unaligned adopted pointer): cp.async variant
+      cudaError_t e = SmallLauncher<MODEL>::dispatch(ctx, nb, d, prm, out, &nparts);
+      if (e != cudaSuccess) return fail(ctx, BOOMGPU_ERR_CUDA, "fused_small_kernel launch failed: %s", cudaGetErrorString(e));
+    }
     {
       LaunchScope ls(ctx, 3);
-      const int total = p * p + p + 4;
-      reduce_small_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->partials, nparts, nb, p, suf);
+      const int total = p * (p + 1) / 2 + p + 4;   // one warp per output element
+      reduce_partials_kernel<<<(total + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, nparts, nb, p, suf);
     }
     CU(cudaGetLastError());
   } else {
@@ -406,7 +487,8 @@ int finish_and_check(boomgpu_ctx *ctx) {
 
 DrawParams make_prm(boomgpu_ctx *ctx, int clt, uint64_t seed, uint64_t iteration) {
   DrawParams prm;
-  prm.mix = ctx->mix;
+  prm.hot = ctx->hot;
+  prm.mix = ctx->mix_dev;
   prm.tab = ctx->tab;
   prm.key.seed = seed;
   prm.key.iteration = iteration;
@@ -495,6 +577,7 @@ void boomgpu_destroy(boomgpu_ctx *ctx) {
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   free_data(ctx);
   for (void *q : ctx->tab_owned) cudaFree(q);
+  cudaFree(ctx->mix_dev);
   cudaFree(ctx->beta_dev); cudaFreeHost(ctx->beta_pin);
   cudaFree(ctx->suf_dev); cudaFreeHost(ctx->suf_pin);
   cudaFree(ctx->partials); cudaFree(ctx->scal_partials);
@@ -529,6 +612,11 @@ int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value) {
     return 0;
   }
   if (!strcmp(name, "timing")) { ctx->timing = value != 0; return 0; }
+  if (!strcmp(name, "small_variant")) {
+    if (value < 0 || value > 1) return fail(ctx, BOOMGPU_ERR_ARG, "small_variant must be 0 or 1");
+    ctx->small_variant = (int)value;
+    return 0;
+  }
   return fail(ctx, BOOMGPU_ERR_ARG, "unknown option '%s'", name);
 }
 
@@ -587,7 +675,7 @@ int boomgpu_adopt_poisson(boomgpu_ctx *ctx, int64_t n, int p, const double *dX, 
 int boomgpu_set_logit_mixture(boomgpu_ctx *ctx, int K, const double *mu, const double *sigma, const double *weights) {
   if (!ctx) return BOOMGPU_ERR_ARG;
   if (K < 1 || K > kMaxLogitK || !sigma || !weights) return fail(ctx, BOOMGPU_ERR_ARG, "mixture needs 1 <= K <= %d", kMaxLogitK);
-  LogitMixture &m = ctx->mix;
+  LogitMixture m;
   memset(&m, 0, sizeof(m));
   m.K = K;
   for (int k = 0; k < K; ++k) {
@@ -599,6 +687,23 @@ int boomgpu_set_logit_mixture(boomgpu_ctx *ctx, int K, const double *mu, const d
     m.lconst[k] = std::log(weights[k]) - kLnSqrt2Pi - std::log(sigma[k]);
     m.inv_sigsq[k] = 1.0 / (sigma[k] * sigma[k]);
   }
+  if (ctx->have_mix && !memcmp(&m, &ctx->mix, sizeof(m))) return 0;   // unchanged (samplers re-state it every draw)
+  ctx->mix = m;
+  ctx->have_mix = false;
+  LogitHot &h = ctx->hot;
+  memset(&h, 0, sizeof(h));
+  h.K = K;
+  h.center = m.mu[0];
+  for (int k = 0; k < K; ++k) {
+    h.lconst2[k] = (float)(m.lconst[k] * 1.4426950408889634);
+    h.hs2[k] = (float)(-0.5 * 1.4426950408889634 * m.inv_sigsq[k]);
+    h.mu_c[k] = (float)(m.mu[k] - h.center);
+    h.inv_sigsq[k] = m.inv_sigsq[k];
+  }
+  DeviceGuard g(ctx->device);
+  if (!ctx->mix_dev) CU(cudaMalloc((void **)&ctx->mix_dev, sizeof(LogitMixture)));
+  CU(cudaStreamSynchronize(ctx->stream));   // no step may still be reading the old mixture
+  CU(cudaMemcpy(ctx->mix_dev, &m, sizeof(LogitMixture), cudaMemcpyHostToDevice));
   ctx->have_mix = true;
   return 0;
 }
@@ -617,11 +722,16 @@ int boomgpu_set_poisson_table(boomgpu_ctx *ctx, int ntab, const int64_t *nu, con
   if (e1 < 0) return fail(ctx, BOOMGPU_ERR_ARG, "Poisson table has no entry for nu = 1");
   const int total = offset[ntab];
   std::vector<double> inv_sigma(total), lconst(total);
+  std::vector<float> mu_f(total), lconst2_f(total), hs2_f(total);
   for (int i = 0; i < total; ++i) {
     if (!(sigma[i] > 0) || !(weights[i] > 0)) return fail(ctx, BOOMGPU_ERR_ARG, "table sigma and weights must be positive");
     inv_sigma[i] = 1.0 / sigma[i];
     lconst[i] = std::log(weights[i]) - kLnSqrt2Pi - std::log(sigma[i]);
+    lconst2_f[i] = (float)(lconst[i] * 1.4426950408889634);
+    hs2_f[i] = (float)(-0.5 * 1.4426950408889634 * inv_sigma[i] * inv_sigma[i]);
   }
+  for (int e = 0; e < ntab; ++e)
+    for (int i = offset[e]; i < offset[e + 1]; ++i) mu_f[i] = (float)(mu[i] - mu[offset[e]]);
   DeviceGuard g(ctx->device);
   CU(cudaStreamSynchronize(ctx->stream));
   for (void *q : ctx->tab_owned) cudaFree(q);
@@ -640,6 +750,9 @@ int boomgpu_set_poisson_table(boomgpu_ctx *ctx, int ntab, const int64_t *nu, con
   CU(up(sigma, sizeof(double) * total, (void **)&t.sigma));
   CU(up(inv_sigma.data(), sizeof(double) * total, (void **)&t.inv_sigma));
   CU(up(lconst.data(), sizeof(double) * total, (void **)&t.lconst));
+  CU(up(mu_f.data(), sizeof(float) * total, (void **)&t.mu_f));
+  CU(up(lconst2_f.data(), sizeof(float) * total, (void **)&t.lconst2_f));
+  CU(up(hs2_f.data(), sizeof(float) * total, (void **)&t.hs2_f));
   ctx->have_tab = true;
   return 0;
 }

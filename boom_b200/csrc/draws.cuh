@@ -53,7 +53,7 @@ __device__ __forceinline__ void uniform_pair(const RngKey &key, uint64_t row, ui
 }
 
 // ---- mixtures -------------------------------------------------------------------------
-// Passed by value as a kernel parameter (constant bank: every lane reads the same entry).
+// Full-precision mixture (global memory, owned by the context): the FP64 statement of unmix and the CLT branch read it.
 struct LogitMixture {
   int K;
   double mu[kMaxLogitK];
@@ -62,6 +62,18 @@ struct LogitMixture {
   double weights[kMaxLogitK];
   double lconst[kMaxLogitK];     // log w - ln sqrt(2 pi) - log sigma
   double inv_sigsq[kMaxLogitK];  // 1 / (sigma * sigma)
+};
+
+// What the per-trial hot loop needs, passed by value as a kernel parameter (constant bank: every lane reads the
+// same entry): single-precision log2-density coefficients for the certified selection below, and 1/sigma^2.
+constexpr float kLog2e = 1.4426950408889634f;
+struct LogitHot {
+  int K;
+  float lconst2[kMaxLogitK];     // log2(e) * lconst
+  float hs2[kMaxLogitK];         // -0.5 * log2(e) / sigma^2
+  float mu_c[kMaxLogitK];        // mu[k] - center
+  double center;                 // = mu[0]: residuals are centred in FP64 before they are rounded to FP32
+  double inv_sigsq[kMaxLogitK];
 };
 
 // Poisson table in global memory (per-row nu makes the lookups divergent).
@@ -73,6 +85,9 @@ struct PoissonTable {
   const double *inv_sigma;
   const double *lconst;
   const double *sigma;
+  const float *mu_f;       // single-precision copies for the certified selection: mu[k] - mu[first component of the entry]
+  const float *lconst2_f;
+  const float *hs2_f;
   int64_t gaussian_cutoff;
   int e1;  // entry index of nu == 1 (every row uses it)
 };
@@ -106,11 +121,76 @@ __device__ __forceinline__ int unmix_generic(int K, double unif, F lp_of) {
   return k;
 }
 
-__device__ __forceinline__ int unmix_logit(const LogitMixture &m, double resid, double unif) {
-  return unmix_generic(m.K, unif, [&](int s) {
-    double x = (resid - m.mu[s]) * m.inv_sigma[s];
-    return m.lconst[s] - 0.5 * x * x;
+// Certified single-precision selection.  The component chosen by unmix depends on the FP64 probabilities only
+// through the comparisons  U * sum_j q_j <= q_0 + ... + q_k.  Evaluating the q_k in FP32 (ex2.approx: K MUFU instead
+// of K FP64 exp) perturbs every cumulative sum by less than ~(2e-6 + 3e-7 |log2 q_max|) * sum: the residual is
+// centred in FP64 before it is rounded, so what is lost is 2^-24 of its distance to the components, i.e. a relative
+// 2^-22 of the exponents.  Whenever U * sum is farther than margin = 4e-5 (1 + |log2 q_max| / 20) * sum from EVERY
+// boundary, the FP32 decision therefore equals the FP64 one; otherwise (probability ~ 2 (K-1) 4e-5 per draw) the
+// caller falls back to the FP64 statement.  The result is always the indicator the FP64 rule gives, so the bit-exact
+// indicator counts against the oracle survive.
+constexpr float kUnmixMargin = 4e-5f;
+
+// r_c: residual minus the mixture's centre, rounded to FP32 by the caller; mu_of(s) is relative to the same centre.
+template <int KMAX, class FMU, class FL, class FH>
+__device__ __forceinline__ bool unmix_certified(int K, float r_c, double unif, FMU mu_of, FL lconst2_of, FH hs2_of, int &kout) {
+  float q[KMAX];
+  float mx = -3.0e38f;
+#pragma unroll
+  for (int s = 0; s < KMAX; ++s) {
+    if (KMAX == kMaxLogitK && s >= K) { q[s] = -3.0e38f; continue; }
+    const float dlt = r_c - mu_of(s);
+    q[s] = fmaf(hs2_of(s), dlt * dlt, lconst2_of(s));
+    mx = fmaxf(mx, q[s]);
+  }
+  float tot = 0.f;
+#pragma unroll
+  for (int s = 0; s < KMAX; ++s) {
+    q[s] = exp2f(q[s] - mx);
+    tot += q[s];
+  }
+  const float v = (float)unif * tot;
+  float cs = 0.f, margin = 3.0e38f;
+  int k = K - 1;
+  bool found = false;
+#pragma unroll
+  for (int s = 0; s < KMAX - 1; ++s) {
+    if (KMAX == kMaxLogitK && s >= K - 1) break;
+    cs += q[s];
+    const float dd = v - cs;
+    margin = fminf(margin, fabsf(dd));
+    if (!found && dd <= 0.f) { k = s; found = true; }
+  }
+  kout = k;
+  return margin > kUnmixMargin * tot * fmaf(0.05f, fabsf(mx), 1.f);
+}
+
+// the FP64 statements of the selection, out of line: taken by ~1e-3 of the draws
+__device__ __noinline__ int unmix_logit_fp64(const LogitMixture *__restrict__ m, double resid, double unif) {
+  return unmix_generic(m->K, unif, [&](int s) {
+    double x = (resid - __ldg(m->mu + s)) * __ldg(m->inv_sigma + s);
+    return __ldg(m->lconst + s) - 0.5 * x * x;
   });
+}
+__device__ __noinline__ int unmix_table_fp64(const double *__restrict__ mu, const double *__restrict__ inv_sigma,
+                                             const double *__restrict__ lconst, int K, double resid, double unif) {
+  return unmix_generic(K, unif, [&](int s) {
+    double x = (resid - __ldg(mu + s)) * __ldg(inv_sigma + s);
+    return __ldg(lconst + s) - 0.5 * x * x;
+  });
+}
+
+__device__ __forceinline__ int unmix_logit(const LogitHot &h, const LogitMixture *__restrict__ m, double resid, double unif) {
+  int k;
+  bool ok;
+  auto mu_of = [&](int s) { return h.mu_c[s]; };
+  auto lc_of = [&](int s) { return h.lconst2[s]; };
+  auto hs_of = [&](int s) { return h.hs2[s]; };
+  const float r_c = (float)(resid - h.center);
+  if (h.K == 9) ok = unmix_certified<9>(9, r_c, unif, mu_of, lc_of, hs_of, k);
+  else ok = unmix_certified<kMaxLogitK>(h.K, r_c, unif, mu_of, lc_of, hs_of, k);
+  if (!ok) k = unmix_logit_fp64(m, resid, unif);
+  return k;
 }
 
 __device__ __forceinline__ double rtrun_logit(double eta, bool success, double unif) {
@@ -190,8 +270,9 @@ __device__ inline void multinomial_from_uniforms(int64_t n, int K, const double 
 }
 
 // CLT branch, kept out of line: Bernoulli data never take it.
-__device__ __noinline__ void logit_impute_large(const LogitMixture &m, double ntrials, double y, double eta,
+__device__ __noinline__ void logit_impute_large(const LogitMixture *__restrict__ mp, double ntrials, double y, double eta,
                                                 const RngKey &key, uint64_t row, double &sum, double &info) {
+  const LogitMixture &m = *mp;
   const int K = m.K;
   double p0[kMaxLogitK], p1[kMaxLogitK], un0[8], un1[8];
   int64_t N0[kMaxLogitK], N1[kMaxLogitK];
@@ -236,12 +317,13 @@ __device__ __noinline__ void logit_impute_large(const LogitMixture &m, double nt
 }
 
 // BinomialLogitCltDataImputer::impute.  Returns false on invalid input (y > n, negative, NaN eta).
-__device__ __forceinline__ bool logit_impute(const LogitMixture &m, int clt_threshold, double ntrials, double y,
-                                             double eta, const RngKey &key, uint64_t row, double &sum, double &info) {
+__device__ __forceinline__ bool logit_impute(const LogitHot &h, const LogitMixture *__restrict__ m, int clt_threshold,
+                                             double ntrials, double y, double eta, const RngKey &key, uint64_t row,
+                                             double &sum, double &info) {
   sum = 0; info = 0;
   if (!(y <= ntrials) || y < 0 || ntrials < 0 || !isfinite(eta)) return false;
   if (ntrials > (double)clt_threshold) {
-    if (m.K > 9) return false;  // slot layout of the CLT branch: K - 1 <= 8 conditional binomials per side
+    if (h.K > 9) return false;  // slot layout of the CLT branch: K - 1 <= 8 conditional binomials per side
     logit_impute_large(m, ntrials, y, eta, key, row, sum, info);
     return true;
   }
@@ -249,8 +331,8 @@ __device__ __forceinline__ bool logit_impute(const LogitMixture &m, int clt_thre
     double u0, u1;
     uniform_pair(key, row, (uint32_t)i, u0, u1);
     double z = rtrun_logit(eta, i < y, u0);
-    int k = unmix_logit(m, z - eta, u1);
-    double cw = m.inv_sigsq[k];
+    int k = unmix_logit(h, m, z - eta, u1);
+    double cw = h.inv_sigsq[k];
     info += cw;
     sum += z * cw;
   }
@@ -277,10 +359,15 @@ __device__ __forceinline__ bool unmix_poisson(const PoissonTable &t, int entry, 
   if (entry < 0) return false;
   int a = __ldg(t.offset + entry), K = __ldg(t.offset + entry + 1) - a;
   if (K > kMaxLogitK) return false;
-  int k = unmix_generic(K, unif, [&](int s) {
-    double x = (resid - __ldg(t.mu + a + s)) * __ldg(t.inv_sigma + a + s);
-    return __ldg(t.lconst + a + s) - 0.5 * x * x;
-  });
+  int k;
+  auto mu_of = [&](int s) { return __ldg(t.mu_f + a + s); };
+  auto lc_of = [&](int s) { return __ldg(t.lconst2_f + a + s); };
+  auto hs_of = [&](int s) { return __ldg(t.hs2_f + a + s); };
+  bool ok;
+  const float r_c = (float)(resid - __ldg(t.mu + a));
+  if (K == 10) ok = unmix_certified<10>(10, r_c, unif, mu_of, lc_of, hs_of, k);
+  else ok = unmix_certified<kMaxLogitK>(K, r_c, unif, mu_of, lc_of, hs_of, k);
+  if (!ok) k = unmix_table_fp64(t.mu + a, t.inv_sigma + a, t.lconst + a, K, resid, unif);
   mu = __ldg(t.mu + a + k);
   double sg = __ldg(t.sigma + a + k);
   weight = 1.0 / (sg * sg);

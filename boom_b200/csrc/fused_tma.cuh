@@ -1,0 +1,244 @@
+// fused_tma.cuh -- the single-pass kernel for p <= 64 (configs C1, C2, C5): TMA-fed, warp-autonomous.
+//
+//   One persistent CTA per SM, NW warps, no block-wide barrier in the steady state.  Every warp owns a ring of
+//   S slices in shared memory; a slice is 32 consecutive observations x (8 NB + 4) doubles, written by ONE
+//   cp.async.bulk.tensor.2d (TMA tile of the row-major X; the box is wider than p, so the pad columns arrive as
+//   zeros, and rows beyond n arrive as zeros too) that completes on the slice's mbarrier.  The warp that consumes a
+//   slice also re-arms it (lane 0 issues the copy S slices ahead right after the warp's last read), so there is no
+//   producer warp and no "empty" barrier.
+//   Per slice, lane r owns observation r:  eta = x_r . beta from shared memory (conflict free: the row stride is
+//   4 mod 8 doubles and the start column is rotated by (r >> 2) & 3), the latent draw (Philox keyed by the global
+//   row), then the warp accumulates its 32 rank-1 updates with FP64 DMMA (m8n8k4; A = w_k x_k fragments, B = x_k
+//   fragments straight from the slice, w_k by shuffle) into the upper triangle of X'WX held in registers
+//   (NB (NB + 1) / 2 atoms), and X'Wz with NB DFMA per 4 rows.
+//   Epilogue: warps add their fragments into one shared tile in warp order, the CTA writes one partial, and
+//   reduce_partials_kernel sums the partials in CTA order (deterministic: no floating point atomics).
+//
+//   Algorithmic traffic: 8 (p + 2) bytes per observation, read once.
+//   Reference equivalent: Imputer.hpp:175-180 over BinomialLogitAuxmixSampler.cpp:61-97 /
+//   PoissonRegressionAuxMixSampler.cpp:58-81.
+#pragma once
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace boomgpu {
+
+// warps / ring depth per NB: a slice is 32 * (8 NB + 4) * 8 bytes = 2048 NB + 1024
+__host__ __device__ constexpr int tma_warps(int nb) { return nb <= 2 ? 12 : (nb <= 4 ? 8 : 6); }
+__host__ __device__ constexpr int tma_stages(int nb) { return nb <= 1 ? 4 : (nb <= 3 ? 3 : 2); }
+__host__ __device__ constexpr int tma_padw(int nb) { return 8 * nb + 4; }
+__host__ __device__ constexpr int tma_slice_doubles(int nb) { return 32 * tma_padw(nb); }
+__host__ __device__ constexpr size_t tma_smem_bytes(int nb) {
+  return sizeof(double) * ((size_t)tma_warps(nb) * tma_stages(nb) * tma_slice_doubles(nb) + 8 * nb + 64) +
+         sizeof(uint64_t) * tma_warps(nb) * tma_stages(nb) + 128;
+}
+__host__ __device__ constexpr int64_t tma_partial_len(int nb) { return 64 * nb * nb + 8 * nb + 8; }
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int NB, int MODEL>
+__global__ void __launch_bounds__(32 * tma_warps(NB), 1)
+fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams prm, RowOut out, const double *__restrict__ beta,
+                 double *__restrict__ partials, int *err) {
+  constexpr int NW = tma_warps(NB);
+  constexpr int S = tma_stages(NB);
+  constexpr int PADW = tma_padw(NB);
+  constexpr int SLICE = tma_slice_doubles(NB);
+  constexpr int P8 = 8 * NB;
+  constexpr int NA = NB * (NB + 1) / 2;
+  constexpr uint32_t kSliceBytes = SLICE * sizeof(double);
+  extern __shared__ __align__(128) double smem[];
+  double *ring = smem;                                  // [NW][S][SLICE]
+  double *beta_s = smem + (size_t)NW * S * SLICE;       // P8
+  double *red_s = beta_s + P8;                          // 64
+  uint64_t *bars = reinterpret_cast<uint64_t *>(red_s + 64);  // [NW][S]
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int p = d.p;
+  if (tid < P8) beta_s[tid] = tid < p ? beta[tid] : 0.0;
+  if (tid == 0) {
+    for (int i = 0; i < NW * S; ++i) mbar_init(bars + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  // slices of 32 rows are dealt to (CTA, warp): the k-th slice of this warp is ((blockIdx + k grid) NW + wid)
+  const int64_t nslices = (d.n + 31) >> 5;
+  const int64_t stride = (int64_t)gridDim.x * NW;
+  const int64_t first = (int64_t)blockIdx.x * NW + wid;
+  double *my_ring = ring + (size_t)wid * S * SLICE;
+  uint64_t *my_bars = bars + wid * S;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int64_t q = first + s * stride;
+      if (q < nslices) {
+        mbar_expect_tx(my_bars + s, kSliceBytes);
+        tma_load_2d(my_ring + s * SLICE, &xmap, 0, (int)(q << 5), my_bars + s);
+      }
+    }
+  }
+
+  double c[NA][2];
+#pragma unroll
+  for (int a = 0; a < NA; ++a) { c[a][0] = 0.0; c[a][1] = 0.0; }
+  double xty_acc[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) xty_acc[b] = 0.0;
+  double sc_count = 0, sc_ywy = 0, sc_sumw = 0, sc_sumlogw = 0;
+  const int rot = (lane >> 2) & 3;
+
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int64_t q = first; q < nslices; q += stride) {
+    const int64_t i = (q << 5) + lane;
+    const bool valid = i < d.n;
+    RowObs obs;
+    obs.y = 0; obs.aux = 0; obs.yi = 0;
+    if (valid) obs = load_obs<MODEL>(d, i);   // in flight while the slice lands
+    mbar_wait(my_bars + slot, phase);
+    const double *xs = my_ring + slot * SLICE;
+
+    // ---- lane r: eta of observation r, then its latent draw
+    double wv = 0, sv = 0;
+    {
+      const double *xr = xs + lane * PADW;
+      double e0 = 0, e1 = 0;
+#pragma unroll
+      for (int j = 0; j < P8; j += 2) {
+        int j0 = j + rot, j1 = j + 1 + rot;
+        j0 = j0 >= P8 ? j0 - P8 : j0;
+        j1 = j1 >= P8 ? j1 - P8 : j1;
+        e0 = fma(xr[j0], beta_s[j0], e0);
+        e1 = fma(xr[j1], beta_s[j1], e1);
+      }
+      if (valid) {
+        RowLatent r = impute_row<MODEL>(d, prm, out, obs, i, e0 + e1, err);
+        wv = r.w; sv = r.s;
+        sc_count += r.count; sc_ywy += r.yWy; sc_sumw += r.w; sc_sumlogw += r.sumlogw;
+      }
+    }
+
+    // ---- the warp's 32 rank-1 updates: 8 DMMA k-steps of 4 rows
+#pragma unroll 2
+    for (int kk = 0; kk < 8; ++kk) {
+      const int row = kk * 4 + (lane & 3);
+      const double wk = __shfl_sync(0xffffffffu, wv, row);
+      const double sk = __shfl_sync(0xffffffffu, sv, row);
+      const double *xr = xs + row * PADW + (lane >> 2);
+      double xa[NB], xw[NB];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        xa[b] = xr[8 * b];
+        xw[b] = xa[b] * wk;
+        xty_acc[b] = fma(xa[b], sk, xty_acc[b]);
+      }
+      int a = 0;
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < NB; ++bj) { dmma884(c[a][0], c[a][1], xw[bi], xa[bj]); ++a; }
+    }
+
+    // ---- re-arm the slot S slices ahead (all lanes are done reading it)
+    __syncwarp();
+    if (lane == 0) {
+      const int64_t qn = q + (int64_t)S * stride;
+      if (qn < nslices) {
+        mbar_expect_tx(my_bars + slot, kSliceBytes);
+        tma_load_2d(my_ring + slot * SLICE, &xmap, 0, (int)(qn << 5), my_bars + slot);
+      }
+    }
+    if (++slot == S) { slot = 0; phase ^= 1; }
+  }
+
+  // ---- CTA reduction in warp order (deterministic), one partial per CTA
+  __syncthreads();  // every issued copy has been consumed: the ring is free
+  double *tile = smem;                  // P8 * P8
+  double *xty_s = smem + P8 * P8;       // P8
+  for (int e = tid; e < P8 * P8 + P8; e += 32 * NW) smem[e] = 0.0;
+  // X'Wz: lanes with the same (lane >> 2) hold the rows = lane & 3 (mod 4) of the same columns
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    xty_acc[b] += __shfl_xor_sync(0xffffffffu, xty_acc[b], 1);
+    xty_acc[b] += __shfl_xor_sync(0xffffffffu, xty_acc[b], 2);
+  }
+  __syncthreads();
+  for (int w = 0; w < NW; ++w) {
+    if (wid == w) {
+      int a = 0;
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < NB; ++bj) {
+          double *t = tile + (8 * bi + (lane >> 2)) * P8 + 8 * bj + 2 * (lane & 3);
+          t[0] += c[a][0];
+          t[1] += c[a][1];
+          ++a;
+        }
+      if ((lane & 3) == 0) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) xty_s[8 * b + (lane >> 2)] += xty_acc[b];
+      }
+    }
+    __syncthreads();
+  }
+  double *my = partials + (int64_t)blockIdx.x * tma_partial_len(NB);
+  for (int e = tid; e < P8 * P8 + P8; e += 32 * NW) my[e] = smem[e];
+  double v0 = warp_sum(sc_count), v1 = warp_sum(sc_ywy), v2 = warp_sum(sc_sumw), v3 = warp_sum(sc_sumlogw);
+  if (lane == 0) { red_s[wid * 4 + 0] = v0; red_s[wid * 4 + 1] = v1; red_s[wid * 4 + 2] = v2; red_s[wid * 4 + 3] = v3; }
+  __syncthreads();
+  if (tid < 4) {
+    double s = 0;
+    for (int w = 0; w < NW; ++w) s += red_s[w * 4 + tid];
+    my[P8 * P8 + P8 + tid] = s;
+  }
+}
+
+// One warp per output element: lanes stride over the per-CTA partials, then a fixed shuffle tree.
+// suf layout [p*p | p | 4]; writes both triangles.  Partial layout: [P8*P8 tile | P8 | 8].
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double *__restrict__ partials, int nparts, int nb, int p,
+                                                             double *__restrict__ suf) {
+  const int P8 = 8 * nb;
+  const int64_t plen = 64 * (int64_t)nb * nb + 8 * nb + 8;
+  const int ntri = p * (p + 1) / 2;
+  const int total = ntri + p + 4;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int e = warp; e < total; e += nwarps) {
+    int a = 0, b = 0;
+    int64_t src;
+    if (e < ntri) {
+      // e -> (a, b), a <= b, rows of the upper triangle laid end to end
+      int rem = e;
+      while (rem >= p - a) { rem -= p - a; ++a; }
+      b = a + rem;
+      src = (int64_t)a * P8 + b;
+    } else if (e < ntri + p) {
+      src = (int64_t)P8 * P8 + (e - ntri);
+    } else {
+      src = (int64_t)P8 * P8 + P8 + (e - ntri - p);
+    }
+    double s = 0;
+    for (int cta = lane; cta < nparts; cta += 32) s += partials[cta * plen + src];
+    s = warp_sum(s);
+    if (lane == 0) {
+      if (e < ntri) {
+        suf[a + (int64_t)b * p] = s;
+        suf[b + (int64_t)a * p] = s;
+      } else {
+        suf[(int64_t)p * p + (e - ntri)] = s;
+      }
+    }
+  }
+}
+
+}  // namespace boomgpu

@@ -45,7 +45,8 @@ struct RowOut {           // optional per-row outputs (test hooks); any may be n
 };
 
 struct DrawParams {
-  LogitMixture mix;
+  LogitHot hot;             // constant bank
+  const LogitMixture *mix;  // global memory (FP64 fallback of the selection, CLT branch)
   PoissonTable tab;
   RngKey key;
   int clt_threshold;
@@ -76,26 +77,38 @@ __device__ __forceinline__ double warp_sum(double v) {
 // single rank-1 update the row contributes, plus the scalar statistics WeightedRegSuf keeps.
 struct RowLatent { double w, s, yWy, sumlogw, count; };
 
+// The per-observation inputs besides x: loaded early (before waiting on staged rows) to hide their latency.
+struct RowObs { double y, aux; int64_t yi; };   // logit: (successes, trials); Poisson: (yi, exposure); supplied: (w, s)
+
 template <int MODEL>
-__device__ __forceinline__ RowLatent impute_row(const RowData &d, const DrawParams &prm, const RowOut &out,
+__device__ __forceinline__ RowObs load_obs(const RowData &d, int64_t i) {
+  RowObs o;
+  o.y = 0; o.aux = 0; o.yi = 0;
+  if (MODEL == kLogit) { o.y = __ldg(d.y + i); o.aux = __ldg(d.ntrials + i); }
+  else if (MODEL == kPoisson) { o.yi = __ldg(d.yi + i); o.aux = __ldg(d.exposure + i); }
+  else { o.y = __ldg(d.w_in + i); o.aux = __ldg(d.s_in + i); }
+  return o;
+}
+
+template <int MODEL>
+__device__ __forceinline__ RowLatent impute_row(const RowData &d, const DrawParams &prm, const RowOut &out, const RowObs &obs,
                                                 int64_t i, double eta, int *err) {
   RowLatent r;
   r.w = r.s = r.yWy = r.sumlogw = 0; r.count = 1;
   if (MODEL == kLogit) {
     double sum, info;
-    bool ok = logit_impute(prm.mix, prm.clt_threshold, d.ntrials[i], d.y[i], eta, prm.key, d.row_offset + (uint64_t)i,
-                           sum, info);
+    bool ok = logit_impute(prm.hot, prm.mix, prm.clt_threshold, obs.aux, obs.y, eta, prm.key, d.row_offset + (uint64_t)i, sum, info);
     if (!ok) { atomicOr(err, 2); sum = 0; info = 0; }
     r.w = info; r.s = sum;
   } else if (MODEL == kPoisson) {
     PoissonLatent o;
-    int rc = poisson_impute(prm.tab, d.yi[i], d.exposure[i], eta, prm.key, d.row_offset + (uint64_t)i, o);
+    int rc = poisson_impute(prm.tab, obs.yi, obs.aux, eta, prm.key, d.row_offset + (uint64_t)i, o);
     if (rc) {
       atomicOr(err, rc == 1 ? 1 : 2);
     } else {
       double re = o.z_ext - o.mu_ext;
       r.w = o.w_ext; r.s = o.w_ext * re; r.yWy = o.w_ext * re * re; r.sumlogw = log(o.w_ext);
-      if (d.yi[i] > 0) {
+      if (obs.yi > 0) {
         double ri = o.z_int - o.mu_int;
         r.w += o.w_int; r.s += o.w_int * ri; r.yWy += o.w_int * ri * ri; r.sumlogw += log(o.w_int);
         r.count = 2;
@@ -107,11 +120,17 @@ __device__ __forceinline__ RowLatent impute_row(const RowData &d, const DrawPara
       if (out.k2) { out.k2[2 * i] = o.k_int; out.k2[2 * i + 1] = o.k_ext; }
     }
   } else {
-    r.w = d.w_in[i]; r.s = d.s_in[i];
+    r.w = obs.y; r.s = obs.aux;
   }
   if (out.w) out.w[i] = r.w;
   if (out.s) out.s[i] = r.s;
   return r;
+}
+
+template <int MODEL>
+__device__ __forceinline__ RowLatent impute_row(const RowData &d, const DrawParams &prm, const RowOut &out, int64_t i, double eta,
+                                                int *err) {
+  return impute_row<MODEL>(d, prm, out, load_obs<MODEL>(d, i), i, eta, err);
 }
 
 // =============================================================================================

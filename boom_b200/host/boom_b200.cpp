@@ -186,6 +186,14 @@ double VariableSelectionPrior::logp(const Selector &inc) const {
   return ans;
 }
 
+// change of logp when variable j flips (included_now: its current state); -inf / nan never escape:
+// a flip into a zero-probability state returns -inf
+double VariableSelectionPrior::flip_delta(int j, bool included_now) const {
+  const double to = included_now ? log_q_[j] : log_p_[j], from = included_now ? log_p_[j] : log_q_[j];
+  if (!std::isfinite(to)) return -std::numeric_limits<double>::infinity();
+  return to - from;
+}
+
 void VariableSelectionPrior::make_valid(Selector &inc) const {
   if (inc.nvars_possible() != (int)probs_.size()) report_error("Wrong size Selector passed to make_valid.");
   for (size_t i = 0; i < probs_.size(); ++i) {
@@ -247,6 +255,7 @@ DeviceData &GlmModelBase::device_data() {
     dev_.reset(new DeviceData(device_));
     uploaded_version_ = 0;
     if (have_stream_) dev_->check(boomgpu_set_stream(dev_->ctx(), stream_));
+    for (auto &o : options_) dev_->check(boomgpu_set_option(dev_->ctx(), o.first.c_str(), o.second));
   }
   if (uploaded_version_ != data_version_) {
     upload(*dev_);
@@ -254,6 +263,18 @@ DeviceData &GlmModelBase::device_data() {
     uploaded_version_ = data_version_;
   }
   return *dev_;
+}
+
+void GlmModelBase::set_device_option(const std::string &name, int64_t value) {
+  bool known = false;
+  for (auto &o : options_) if (o.first == name) { o.second = value; known = true; }
+  if (!known) options_.emplace_back(name, value);
+  if (dev_) dev_->check(boomgpu_set_option(dev_->ctx(), name.c_str(), value));
+}
+int64_t GlmModelBase::kernel_launches() { return dev_ ? boomgpu_kernel_launches(dev_->ctx()) : 0; }
+void GlmModelBase::kernel_timings(double ms[5], int64_t launches[5], bool reset) {
+  for (int c = 0; c < 5; ++c) { ms[c] = 0; launches[c] = 0; }
+  if (dev_) dev_->check(boomgpu_get_timings(dev_->ctx(), ms, launches, reset ? 1 : 0));
 }
 
 BinomialLogitModel::BinomialLogitModel(int64_t n, int p, const double *X, const double *y, const double *nt)
@@ -393,6 +414,219 @@ double SpikeSlabCore::log_model_prob(const Selector &g, const WeightedRegSuf &su
   return num - denom;
 }
 
+// log_model_prob along a path of single flips.  The value is the one log_model_prob() computes from
+// scratch (the posterior only depends on the SET of included variables), but an "add j" proposal -- all
+// but a handful of the p proposals of a sweep at a sparse model -- is evaluated by bordering the two
+// Cholesky factors of the current model with one row: O(k^2) instead of two O(k^3) factorisations and
+// a handful of heap allocations.  Included variables are kept in insertion order.
+class SpikeSlabCore::FlipEvaluator {
+ public:
+  FlipEvaluator(const SpikeSlabCore &core, const WeightedRegSuf &suf, const Selector &g)
+      : slab_mu_(core.slab_->mu()), siginv_(core.slab_->siginv()), spike_(*core.spike_), xtx_(suf.xtx()), xty_(suf.xty()),
+        g_(g), p_(g.nvars_possible()) {
+    pos_ = g.included_positions();
+    reserve(std::min(p_, std::max(32, 2 * (int)pos_.size() + 8)));
+    logp_ = rebuild();
+  }
+  double logp() const { return logp_; }
+  const Selector &selector() const { return g_; }
+
+  // log_model_prob of the current model with variable j flipped; commit() makes it current
+  double propose(int j) {
+    prop_ = j;
+    const double neg_inf = -std::numeric_limits<double>::infinity();
+    const int k_new = (int)pos_.size() + (g_[j] ? -1 : 1);
+    prop_spike_ = (spike_.max_model_size() >= 0 && k_new > spike_.max_model_size()) ? neg_inf
+                                                                                   : spike_logp_ + spike_.flip_delta(j, g_[j]);
+    if (g_[j]) {  // drop: evaluated from scratch on the smaller model
+      prop_is_add_ = false;
+      return prop_logp_ = neg_inf == prop_spike_ ? neg_inf : scratch_without(j);
+    }
+    prop_is_add_ = true;
+    if (prop_spike_ == neg_inf) return prop_logp_ = neg_inf;
+    const int k = (int)pos_.size();
+    const double *sj = siginv_.a.data() + (size_t)j * p_;
+    const double *xj = xtx_.a.data() + (size_t)j * p_;
+    // border rows: l1 = Lp^-1 Siginv[gamma, j], l2 = Lq^-1 (Siginv + XtX)[gamma, j]
+    double n1 = 0, n2 = 0, cross = 0;
+    for (int i = 0; i < k; ++i) {
+      const int pi = pos_[i];
+      double s1 = sj[pi], s2 = sj[pi] + xj[pi];
+      const double *r1 = Lp_.data() + (size_t)i * ld_, *r2 = Lq_.data() + (size_t)i * ld_;
+      for (int c = 0; c < i; ++c) { s1 -= r1[c] * l1_[c]; s2 -= r2[c] * l2_[c]; }
+      l1_[i] = s1 / r1[i]; l2_[i] = s2 / r2[i];
+      n1 += l1_[i] * l1_[i]; n2 += l2_[i] * l2_[i];
+      cross += sj[pi] * slab_mu_[pi];   // Siginv[j, gamma] mu_gamma
+    }
+    const double d1 = sj[j] - n1, d2 = sj[j] + xj[j] - n2;
+    if (!(d1 > 0) || !(d2 > 0)) return prop_logp_ = neg_inf;
+    d1_ = std::sqrt(d1); d2_ = std::sqrt(d2);
+    const double mj = slab_mu_[j];
+    const double q_new = q_ + 2 * mj * cross + sj[j] * mj * mj;
+    double nsq;
+    if (mj == 0.0) {  // b_gamma unchanged: only the last forward-substitution row is new
+      bj_ = xty_[j] + cross;
+      double t = bj_;
+      for (int c = 0; c < k; ++c) t -= l2_[c] * u_[c];
+      uj_ = t / d2_;
+      nsq = usq_ + uj_ * uj_;
+    } else {  // every entry of b changes: b_i += Siginv[i, j] mu_j, then a full forward solve
+      bj_ = xty_[j] + cross + sj[j] * mj;
+      nsq = 0;
+      for (int i = 0; i < k; ++i) {
+        double t = b_[i] + sj[pos_[i]] * mj;
+        const double *r2 = Lq_.data() + (size_t)i * ld_;
+        for (int c = 0; c < i; ++c) t -= r2[c] * tmp_[c];
+        tmp_[i] = t / r2[i];
+        nsq += tmp_[i] * tmp_[i];
+      }
+      double t = bj_;
+      for (int c = 0; c < k; ++c) t -= l2_[c] * tmp_[c];
+      uj_ = t / d2_;
+      nsq += uj_ * uj_;
+    }
+    prop_q_ = q_new; prop_usq_ = nsq;
+    prop_hldp_ = hldp_ + std::log(d1_); prop_hldq_ = hldq_ + std::log(d2_);
+    return prop_logp_ = prop_spike_ + prop_hldp_ - .5 * q_new - (prop_hldq_ - .5 * nsq);
+  }
+
+  void commit() {
+    const int j = prop_;
+    if (!prop_is_add_) {
+      g_.drop(j);
+      pos_.erase(std::find(pos_.begin(), pos_.end(), j));
+      logp_ = rebuild();   // also re-sums the spike prior from scratch: no drift along the path
+      return;
+    }
+    const int k = (int)pos_.size();
+    const double mj = slab_mu_[j];
+    if (k + 1 > ld_) grow(std::min(p_, 2 * ld_));
+    double *r1 = Lp_.data() + (size_t)k * ld_, *r2 = Lq_.data() + (size_t)k * ld_;
+    for (int c = 0; c < k; ++c) { r1[c] = l1_[c]; r2[c] = l2_[c]; }
+    r1[k] = d1_; r2[k] = d2_;
+    if (mj != 0.0) {
+      const double *sj = siginv_.a.data() + (size_t)j * p_;
+      for (int i = 0; i < k; ++i) { b_[i] += sj[pos_[i]] * mj; u_[i] = tmp_[i]; }
+    }
+    b_[k] = bj_; u_[k] = uj_;
+    g_.add(j);
+    pos_.push_back(j);
+    q_ = prop_q_; usq_ = prop_usq_; hldp_ = prop_hldp_; hldq_ = prop_hldq_;
+    spike_logp_ = prop_spike_;
+    logp_ = prop_logp_;
+  }
+
+ private:
+  // workspace for models of up to cap variables (the factors are cap x cap, lower triangles)
+  void reserve(int cap) {
+    ld_ = cap;
+    Lp_.resize((size_t)cap * cap); Lq_.resize((size_t)cap * cap);
+    b_.resize(cap); u_.resize(cap); l1_.resize(cap); l2_.resize(cap); im_.resize(cap); tmp_.resize(cap);
+  }
+  void grow(int cap) {  // re-lays the factors out with the new leading dimension; pending border rows live in l1_/l2_
+    const int k = (int)pos_.size(), old = ld_;
+    Vector Lp(std::move(Lp_)), Lq(std::move(Lq_)), l1(l1_), l2(l2_), b(b_), u(u_), tmp(tmp_);
+    Lp_.clear(); Lq_.clear();
+    reserve(cap);
+    for (int i = 0; i < k; ++i)
+      for (int c = 0; c <= i; ++c) { Lp_[(size_t)i * ld_ + c] = Lp[(size_t)i * old + c]; Lq_[(size_t)i * ld_ + c] = Lq[(size_t)i * old + c]; }
+    std::copy(l1.begin(), l1.end(), l1_.begin()); std::copy(l2.begin(), l2.end(), l2_.begin());
+    std::copy(b.begin(), b.end(), b_.begin()); std::copy(u.begin(), u.end(), u_.begin());
+    std::copy(tmp.begin(), tmp.end(), tmp_.begin());
+  }
+  // factorises the current model from scratch into the workspace; returns log_model_prob
+  double rebuild() {
+    const double neg_inf = -std::numeric_limits<double>::infinity();
+    spike_logp_ = spike_.logp(g_);
+    const int k = (int)pos_.size();
+    q_ = usq_ = hldp_ = hldq_ = 0;
+    if (spike_logp_ == neg_inf || k == 0) return spike_logp_;
+    return factor(pos_, Lp_.data(), Lq_.data(), b_.data(), u_.data(), &q_, &usq_, &hldp_, &hldq_, spike_logp_);
+  }
+  double scratch_without(int j) {
+    scratch_pos_.clear();
+    for (int v : pos_) if (v != j) scratch_pos_.push_back(v);
+    if (scratch_pos_.empty()) return prop_spike_;
+    const size_t need = (size_t)ld_ * ld_;
+    if (S1_.size() < need) { S1_.resize(need); S2_.resize(need); sb_.resize(ld_); su_.resize(ld_); }
+    double q, usq, h1, h2;
+    return factor(scratch_pos_, S1_.data(), S2_.data(), sb_.data(), su_.data(), &q, &usq, &h1, &h2, prop_spike_);
+  }
+  double factor(const std::vector<int> &pos, double *Lp, double *Lq, double *b, double *u, double *q, double *usq, double *hldp,
+                double *hldq, double spike_logp) {
+    const double neg_inf = -std::numeric_limits<double>::infinity();
+    const int k = (int)pos.size();
+    *q = 0;
+    for (int i = 0; i < k; ++i) {
+      const double *si = siginv_.a.data() + (size_t)pos[i] * p_;
+      const double *xi = xtx_.a.data() + (size_t)pos[i] * p_;
+      double m = 0;
+      for (int c = 0; c < k; ++c) m += si[pos[c]] * slab_mu_[pos[c]];
+      im_[i] = m;
+      *q += m * slab_mu_[pos[i]];
+      b[i] = xty_[pos[i]] + m;
+      for (int c = 0; c <= i; ++c) { Lp[(size_t)i * ld_ + c] = si[pos[c]]; Lq[(size_t)i * ld_ + c] = si[pos[c]] + xi[pos[c]]; }
+    }
+    if (!chol_ld(Lp, k) || !chol_ld(Lq, k)) return neg_inf;
+    *hldp = *hldq = *usq = 0;
+    for (int i = 0; i < k; ++i) {
+      *hldp += std::log(Lp[(size_t)i * ld_ + i]);
+      *hldq += std::log(Lq[(size_t)i * ld_ + i]);
+      double t = b[i];
+      const double *r = Lq + (size_t)i * ld_;
+      for (int c = 0; c < i; ++c) t -= r[c] * u[c];
+      u[i] = t / r[i];
+      *usq += u[i] * u[i];
+    }
+    return spike_logp + *hldp - .5 * *q - (*hldq - .5 * *usq);
+  }
+  // in-place lower Cholesky of the leading k x k block (lower triangle stored, leading dimension ld_)
+  bool chol_ld(double *a, int k) const {
+    for (int j = 0; j < k; ++j) {
+      double *rj = a + (size_t)j * ld_;
+      double d = rj[j];
+      for (int c = 0; c < j; ++c) d -= rj[c] * rj[c];
+      if (!(d > 0) || !std::isfinite(d)) return false;
+      d = std::sqrt(d);
+      rj[j] = d;
+      for (int i = j + 1; i < k; ++i) {
+        double *ri = a + (size_t)i * ld_;
+        double s = ri[j];
+        for (int c = 0; c < j; ++c) s -= ri[c] * rj[c];
+        ri[j] = s / d;
+      }
+    }
+    return true;
+  }
+
+  const Vector &slab_mu_;
+  const SpdMatrix &siginv_;
+  const VariableSelectionPrior &spike_;
+  const SpdMatrix &xtx_;
+  const Vector &xty_;
+  Selector g_;
+  int p_, ld_;
+  std::vector<int> pos_, scratch_pos_;
+  Vector Lp_, Lq_, b_, u_, l1_, l2_, im_, tmp_, S1_, S2_, sb_, su_;
+  double q_ = 0, usq_ = 0, hldp_ = 0, hldq_ = 0, spike_logp_ = 0, logp_ = 0;
+  // pending proposal
+  int prop_ = -1;
+  bool prop_is_add_ = false;
+  double prop_logp_ = 0, prop_spike_ = 0, prop_q_ = 0, prop_usq_ = 0, prop_hldp_ = 0, prop_hldq_ = 0, d1_ = 0, d2_ = 0, bj_ = 0, uj_ = 0;
+};
+
+Vector SpikeSlabCore::flip_path_log_probs(const Selector &start, const WeightedRegSuf &suf, const std::vector<int> &flips,
+                                          const std::vector<bool> &accept) const {
+  FlipEvaluator ev(*this, suf, start);
+  Vector out;
+  for (size_t i = 0; i < flips.size(); ++i) {
+    out.push_back(ev.propose(flips[i]));
+    if (accept[i] && std::isfinite(out.back())) ev.commit();
+  }
+  out.push_back(ev.logp());
+  return out;
+}
+
 void SpikeSlabCore::draw_model_indicators(RNG &rng, GlmCoefs &coef, const WeightedRegSuf &suf) const {
   if (!allow_model_selection_) return;
   Selector g = coef.inc();
@@ -418,14 +652,13 @@ void SpikeSlabCore::draw_model_indicators(RNG &rng, GlmCoefs &coef, const Weight
   if (!std::isfinite(logp)) report_error("The spike and slab sampler did not start with a legal configuration.");
   int n = nv;
   if (max_flips_ > 0) n = std::min(n, max_flips_);
+  FlipEvaluator ev(*this, suf, g);
   for (int i = 0; i < n; ++i) {  // mcmc_one_flip (.cpp:213-222)
-    g.flip(indx[i]);
-    const double logp_new = log_model_prob(g, suf);
+    const double logp_new = ev.propose(indx[i]);
     const double u = runif_mt(rng, 0, 1);
-    if (std::log(u) > logp_new - logp) g.flip(indx[i]);
-    else logp = logp_new;
+    if (std::log(u) <= logp_new - ev.logp()) ev.commit();
   }
-  coef.set_inc(g);
+  coef.set_inc(ev.selector());
 }
 
 // BinomialLogitSpikeSlabSampler::draw_beta (.cpp:56-75)

@@ -125,6 +125,8 @@ class VariableSelectionPrior {
   VariableSelectionPrior(int n, double inclusion_probability = 1.0);
   explicit VariableSelectionPrior(const Vector &prior_inclusion_probabilities);
   double logp(const Selector &inc) const;
+  double flip_delta(int j, bool included_now) const;
+  int max_model_size() const { return max_model_size_; }
   void make_valid(Selector &inc) const;
   const Vector &prior_inclusion_probabilities() const { return probs_; }
   void set_max_model_size(int m) { max_model_size_ = m; }
@@ -210,6 +212,11 @@ class GlmModelBase {
   DeviceData &device_data();              // packs / uploads when stale
   const Vector &x_rows() const { return x_; }
   uint64_t data_version() const { return data_version_; }
+  // instrumentation of the device context (include/boomgpu.h: boomgpu_set_option / _kernel_launches / _get_timings)
+  void set_device_option(const std::string &name, int64_t value);
+  int64_t kernel_launches();
+  // per kernel class {fused small-p, imputer pass, DMMA SYRK, reductions, other}: CUDA-event ms and launch counts
+  void kernel_timings(double ms[5], int64_t launches[5], bool reset);
 
  protected:
   virtual void upload(DeviceData &dev) = 0;
@@ -228,6 +235,7 @@ class GlmModelBase {
   AllReduceFn allreduce_;
   void *stream_ = nullptr;
   bool have_stream_ = false;
+  std::vector<std::pair<std::string, int64_t>> options_;
 };
 
 class BinomialLogitModel : public GlmModelBase {
@@ -331,8 +339,13 @@ class SpikeSlabCore {
   void allow_model_selection(bool tf) { allow_model_selection_ = tf; }
   void limit_model_selection(int max_flips) { max_flips_ = max_flips; }
   bool model_selection_allowed() const { return allow_model_selection_; }
+  // test hook: log_model_prob of every proposal along a path of flips (accept[i]: commit flip i), evaluated the
+  // way the sweep evaluates it (bordered Cholesky factors); the last entry is the final model's value
+  Vector flip_path_log_probs(const Selector &start, const WeightedRegSuf &suf, const std::vector<int> &flips,
+                             const std::vector<bool> &accept) const;
 
  private:
+  class FlipEvaluator;
   std::shared_ptr<MvnBase> slab_;
   std::shared_ptr<VariableSelectionPrior> spike_;
   bool fisher_yates_;

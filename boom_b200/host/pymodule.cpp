@@ -65,6 +65,16 @@ void bind_model_common(py::class_<M, std::shared_ptr<M>> &c) {
           fn(reinterpret_cast<uintptr_t>(dev), count);
         });
       })
+      .def("set_device_option", &M::set_device_option)
+      .def("kernel_launches", &M::kernel_launches)
+      .def("kernel_timings", [](M &m, bool reset) {
+        double ms[5]; int64_t cnt[5];
+        m.kernel_timings(ms, cnt, reset);
+        static const char *names[5] = {"fused_small", "impute_rows", "syrk_dmma", "reduce", "other"};
+        py::dict out;
+        for (int c = 0; c < 5; ++c) out[names[c]] = py::make_tuple(ms[c], cnt[c]);
+        return out;
+      }, py::arg("reset") = false)
       .def("log_likelihood", [](M &m) { return m.log_likelihood(); })
       .def("log_likelihood", [](M &m, const NpD &b) { return m.log_likelihood(to_vec(b)); });
 }
@@ -229,6 +239,19 @@ PYBIND11_MODULE(_host, m) {
     }
     for (int i = 0; i < p; ++i) { inc_sum[i] /= sweeps; beta_sum[i] /= sweeps; }
     return py::make_tuple(from_vec(inc_sum), from_vec(beta_sum));
+  });
+  m.def("flip_path_log_probs", [](const NpD &xtx, const NpD &xty, const std::shared_ptr<MvnBase> &slab,
+                                  const std::shared_ptr<VariableSelectionPrior> &spike, std::vector<bool> bits,
+                                  std::vector<int> flips, std::vector<bool> accept) {
+    const int p = (int)xty.size();
+    Vector packed((size_t)p * p + p + 4, 0.0);
+    std::copy(xtx.data(), xtx.data() + (size_t)p * p, packed.begin());
+    std::copy(xty.data(), xty.data() + p, packed.begin() + (size_t)p * p);
+    WeightedRegSuf suf(p);
+    suf.reset(packed.data(), p);
+    Selector g(p, false);
+    for (int i = 0; i < p; ++i) if (bits[i]) g.add(i);
+    return from_vec(SpikeSlabCore(slab, spike, false).flip_path_log_probs(g, suf, flips, accept));
   });
   m.def("log_model_prob", [](const NpD &xtx, const NpD &xty, const std::shared_ptr<MvnBase> &slab,
                              const std::shared_ptr<VariableSelectionPrior> &spike, std::vector<bool> bits) {

@@ -1,0 +1,55 @@
+"""The drop-in claim, executed on the GPU box: oracle/_ref/boom_adapter_demo (built here from
+boom_b200/boom_adapter + the compiled, unmodified reference) constructs BOOM's OWN model classes, attaches first the
+reference sampler and then the B200 sampler with model->set_method(), and runs model->sample_posterior() on the same
+data.  Posterior means / sds / inclusion probabilities of the two chains must agree within Monte Carlo error
+(BASELINE.json north_star, 'Posterior')."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "oracle", "_ref", "boom_adapter_demo")
+TAU = 10.0   # integrated autocorrelation time assumed for the standard errors
+
+
+def _demo(kind, n, p, nonzero, iters, burn):
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/boom_adapter_demo not built (needs the reference sources: __graft_entry__.build())")
+    out = subprocess.run([EXE, kind, str(n), str(p), str(nonzero), str(iters), str(burn)], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def _agree(r, iters, burn, strong_only=False):
+    ref, gpu = r["reference"], r["b200"]
+    m0, m1 = np.array(ref["mean"]), np.array(gpu["mean"])
+    s0, s1 = np.array(ref["sd"]), np.array(gpu["sd"])
+    i0, i1 = np.array(ref["inclusion"]), np.array(gpu["inclusion"])
+    # inclusion indicators of borderline variables are sticky: allow 5 standard errors at an autocorrelation time of 30 sweeps
+    pi = 0.5 * (i0 + i1)
+    tol = 5 * np.sqrt(pi * (1 - pi) * 30.0 / (iters - burn)) + 0.01
+    assert np.all(np.abs(i0 - i1) < tol), (i0, i1, tol)
+    sel = (i0 > 0.95) if strong_only else np.ones_like(i0, dtype=bool)
+    se = np.sqrt((s0 ** 2 + s1 ** 2) * TAU / (iters - burn))
+    assert np.all(np.abs(m0 - m1)[sel] < 4 * se[sel] + 1e-3), (m0, m1, se)
+    big = sel & (s0 > 0.01)
+    np.testing.assert_allclose(s1[big], s0[big], rtol=0.2)
+
+
+@pytest.mark.parametrize("kind,n,p,nonzero", [("logit", 3000, 5, 3), ("poisson", 2000, 4, 2)])
+def test_full_model_samplers_on_boom_models(kind, n, p, nonzero):
+    iters, burn = 3000, 500
+    _agree(_demo(kind, n, p, nonzero, iters, burn), iters, burn)
+
+
+@pytest.mark.parametrize("kind,n,p,nonzero,iters", [("spike", 3000, 8, 3, 20000), ("pspike", 1500, 8, 3, 12000)])
+def test_spike_slab_samplers_on_boom_models(kind, n, p, nonzero, iters):
+    burn = 2000
+    r = _demo(kind, n, p, nonzero, iters, burn)
+    _agree(r, iters, burn, strong_only=True)
+    inc = np.array(r["b200"]["inclusion"])
+    assert np.all(inc[:nonzero + 1] > 0.9)    # the true variables are found

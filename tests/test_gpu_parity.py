@@ -187,3 +187,52 @@ def test_state_errors():
         ctx.p = 3
         ctx.logit_step(np.zeros(3), 10, 1, 0)
     ctx.close()
+
+
+# ---------------------------------------------------------------- certified FP32 selection of the mixture indicator
+def test_logit_indicators_exact_at_scale():
+    """draws.cuh selects the indicator in FP32 when the decision is provably the FP64 one and falls back to the
+    FP64 rule otherwise: over 400k draws (several hundred of them on the fallback) EVERY indicator equals the oracle's."""
+    n, p = 400_000, 3
+    X, y, nt, beta = O.synth_binomial(n, p, 2, seed=77)
+    ctx, mix = logit_ctx(X, y, nt)
+    _, w = ctx.logit_draw(beta, 10, seed=5, iteration=11)
+    _, rw = O.logit_draw(X, y, nt, beta, 10, mix, 5, 11)
+    np.testing.assert_array_equal(w, rw)     # info = 1/sigma_k^2 of the drawn k: bitwise equal or a different k
+    ctx.close()
+
+
+def test_poisson_indicators_exact_at_scale():
+    n, p = 200_000, 3
+    X, y, ex, beta = O.synth_poisson(n, p, 2, seed=78)
+    y[:20000] = np.random.default_rng(1).integers(0, 300, size=20000)    # every table size K = 10, 4, 3 and off-grid counts
+    ctx, tab = poisson_ctx(X, y, ex)
+    _, k2 = ctx.poisson_draw(beta, seed=6, iteration=4)
+    _, rk2 = O.poisson_draw(X, y, ex, beta, tab, 6, 4)
+    assert np.array_equal(k2, rk2)
+    ctx.close()
+
+
+@pytest.mark.parametrize("n,p,kind", [(5003, 20, "logit"), (40_000, 16, "logit"), (3000, 64, "logit"), (7001, 50, "poisson"),
+                                      (33, 1, "logit"), (100_000, 7, "logit")])
+def test_small_p_variants_agree_with_oracle(n, p, kind):
+    """p <= 64: the TMA-fed warp-autonomous kernel (default) and the cp.async kernel (X that TMA cannot describe)."""
+    for variant in (0, 1):
+        if kind == "logit":
+            X, y, nt, beta = O.synth_binomial(n, p, min(3, p - 1), seed=50 + p, max_trials=2)
+            ctx, mix = logit_ctx(X, y, nt)
+            ctx.set_option("small_variant", variant)
+            xtx, xty, ss = ctx.logit_step(beta, 10, seed=3, iteration=2)
+            rxtx, rxty, rss, _ = O.logit_step(X, y, nt, beta, 10, mix, 3, 2)
+            assert ss == rss == n
+        else:
+            X, y, ex, beta = O.synth_poisson(n, p, 3, seed=60 + p)
+            ctx, tab = poisson_ctx(X, y, ex)
+            ctx.set_option("small_variant", variant)
+            xtx, xty, sc = ctx.poisson_step(beta, seed=3, iteration=2)
+            rxtx, rxty, rsc = O.poisson_step(X, y, ex, beta, tab, 3, 2)
+            np.testing.assert_allclose(sc, rsc, rtol=1e-10)
+        assert normwise_err(xtx, rxtx) < 1e-11
+        assert vec_err(xty, rxty) < 1e-10
+        np.testing.assert_array_equal(xtx, xtx.T)
+        ctx.close()
