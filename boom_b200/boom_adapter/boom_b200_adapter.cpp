@@ -59,7 +59,9 @@ void DeviceImputerBase::impute_latent_data() {
   packed_.resize((size_t)len);
   double *suf_dev = nullptr;
   check(boomgpu_suf_buffer(ctx_, &suf_dev));
-  const uint64_t seed = seed_rng(rng());   // fresh Philox key from the sampler's own stream: set_seed() repeats the chain
+  // fresh Philox key from the sampler's own stream (set_seed() repeats the chain).  Raw generator bits, not
+  // BOOM::seed_rng: its llround(U * 2^64) overflows for half of all U and returns one fixed value for them.
+  const uint64_t seed = rng().generator()();
   check(device_step(ctx_, current_beta().data(), seed, iteration_++, suf_dev));
   if (allreduce_) allreduce_(suf_dev, len);
   check(boomgpu_download(ctx_, suf_dev, packed_.data(), len));
@@ -99,7 +101,7 @@ void DeviceImputerBase::spike_slab_draw(GlmCoefs &coef, const MvnBase &slab, con
   BOOM_B200::Selector g(xdim_, false);
   for (int i = 0; i < xdim_; ++i) if (coef.inc()[i]) g.add(i);
   hcoef.set_inc(g);
-  BOOM_B200::RNG local(seed_rng(rng()));
+  BOOM_B200::RNG local(rng().generator()());   // see impute_latent_data() on why not seed_rng()
   core.draw_model_indicators(local, hcoef, hsuf);
   core.draw_beta(local, hcoef, hsuf);
   std::vector<bool> bits(xdim_);

@@ -31,7 +31,8 @@ class BoomGpuError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libboomgpu.so")
+    # BOOMGPU_LIBRARY: a differently tuned build of the same library (profiles/tune_small.sh); never a fallback
+    return os.environ.get("BOOMGPU_LIBRARY") or os.path.join(_HERE, "libboomgpu.so")
 
 
 def load_library():

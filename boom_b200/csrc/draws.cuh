@@ -194,11 +194,11 @@ __device__ __forceinline__ int unmix_logit(const LogitHot &h, const LogitMixture
 }
 
 __device__ __forceinline__ double rtrun_logit(double eta, bool success, double unif) {
-  double c = 1.0 / (1.0 + exp(eta));  // plogis(0 - eta)
+  double c = __drcp_rn(1.0 + exp(eta));  // plogis(0 - eta)
   double u = success ? c + (1.0 - c) * unif : c * unif;
   u = fmin(u, 1.0 - 0x1p-53);
   u = fmax(u, 2.2250738585072014e-308);
-  return log(u / (1.0 - u)) + eta;
+  return log(u * __drcp_rn(1.0 - u)) + eta;
 }
 
 // log(1 - Phi(a)) and the hazard phi(a) / (1 - Phi(a)) through erfcx (stable in both tails)
@@ -327,10 +327,11 @@ __device__ __forceinline__ bool logit_impute(const LogitHot &h, const LogitMixtu
     logit_impute_large(m, ntrials, y, eta, key, row, sum, info);
     return true;
   }
-  for (int i = 0; i < ntrials; ++i) {
+  const int nt = (int)ceil(ntrials), ns = (int)ceil(y);   // i < ntrials, i < y for integer i (the reference's loop bounds are doubles)
+  for (int i = 0; i < nt; ++i) {
     double u0, u1;
     uniform_pair(key, row, (uint32_t)i, u0, u1);
-    double z = rtrun_logit(eta, i < y, u0);
+    double z = rtrun_logit(eta, i < ns, u0);
     int k = unmix_logit(h, m, z - eta, u1);
     double cw = h.inv_sigsq[k];
     info += cw;

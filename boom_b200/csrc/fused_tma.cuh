@@ -25,8 +25,15 @@
 namespace boomgpu {
 
 // warps / ring depth per NB: a slice is 32 * (8 NB + 4) * 8 bytes = 2048 NB + 1024
-__host__ __device__ constexpr int tma_warps(int nb) { return nb <= 2 ? 12 : (nb <= 4 ? 8 : 6); }
-__host__ __device__ constexpr int tma_stages(int nb) { return nb <= 1 ? 4 : (nb <= 3 ? 3 : 2); }
+// (tuning knobs for the smallest tiles: -DBOOMGPU_TMA_NW_SMALL=.. -DBOOMGPU_TMA_S_SMALL=..)
+#ifndef BOOMGPU_TMA_NW_SMALL
+#define BOOMGPU_TMA_NW_SMALL 12
+#endif
+#ifndef BOOMGPU_TMA_S_SMALL
+#define BOOMGPU_TMA_S_SMALL 3
+#endif
+__host__ __device__ constexpr int tma_warps(int nb) { return nb <= 2 ? BOOMGPU_TMA_NW_SMALL : (nb == 3 ? 12 : (nb == 4 ? 10 : 6)); }
+__host__ __device__ constexpr int tma_stages(int nb) { return nb <= 2 ? BOOMGPU_TMA_S_SMALL : 2; }
 __host__ __device__ constexpr int tma_padw(int nb) { return 8 * nb + 4; }
 __host__ __device__ constexpr int tma_slice_doubles(int nb) { return 32 * tma_padw(nb); }
 __host__ __device__ constexpr size_t tma_smem_bytes(int nb) {
@@ -97,14 +104,21 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
 
   int slot = 0;
   uint32_t phase = 0;
+  // y_i / n_i (or exposure, or supplied latents) are fetched one slice ahead: a global load per lane whose latency
+  // the previous slice's arithmetic covers
+  RowObs obs_next;
+  obs_next.y = 0; obs_next.aux = 0; obs_next.yi = 0;
+  if (first < nslices && (first << 5) + lane < d.n) obs_next = load_obs<MODEL>(d, (first << 5) + lane);
   for (int64_t q = first; q < nslices; q += stride) {
     const int64_t i = (q << 5) + lane;
     const bool valid = i < d.n;
-    RowObs obs;
-    obs.y = 0; obs.aux = 0; obs.yi = 0;
-    if (valid) obs = load_obs<MODEL>(d, i);   // in flight while the slice lands
+    const RowObs obs = obs_next;
+    {
+      const int64_t in = ((q + stride) << 5) + lane;
+      if (in < d.n) obs_next = load_obs<MODEL>(d, in);
+    }
     mbar_wait(my_bars + slot, phase);
-    const double *xs = my_ring + slot * SLICE;
+    double *xs = my_ring + slot * SLICE;
 
     // ---- lane r: eta of observation r, then its latent draw
     double wv = 0, sv = 0;
@@ -124,14 +138,17 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
         wv = r.w; sv = r.s;
         sc_count += r.count; sc_ywy += r.yWy; sc_sumw += r.w; sc_sumlogw += r.sumlogw;
       }
+      // (w_r, s_r) go to the two pad columns of row r: the k-steps below read them back with one 16-byte load
+      *reinterpret_cast<double2 *>(xs + lane * PADW + P8) = make_double2(wv, sv);
     }
+    __syncwarp();
 
     // ---- the warp's 32 rank-1 updates: 8 DMMA k-steps of 4 rows
 #pragma unroll 2
     for (int kk = 0; kk < 8; ++kk) {
       const int row = kk * 4 + (lane & 3);
-      const double wk = __shfl_sync(0xffffffffu, wv, row);
-      const double sk = __shfl_sync(0xffffffffu, sv, row);
+      const double2 ws = *reinterpret_cast<const double2 *>(xs + row * PADW + P8);
+      const double wk = ws.x, sk = ws.y;
       const double *xr = xs + row * PADW + (lane >> 2);
       double xa[NB], xw[NB];
 #pragma unroll
@@ -147,7 +164,9 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
         for (int bj = bi; bj < NB; ++bj) { dmma884(c[a][0], c[a][1], xw[bi], xa[bj]); ++a; }
     }
 
-    // ---- re-arm the slot S slices ahead (all lanes are done reading it)
+    // ---- re-arm the slot S slices ahead (all lanes are done with it; the generic-proxy writes of (w, s) are
+    // ordered before the async-proxy overwrite)
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncwarp();
     if (lane == 0) {
       const int64_t qn = q + (int64_t)S * stride;

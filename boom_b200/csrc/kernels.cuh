@@ -184,7 +184,7 @@ fused_small_kernel(RowData d, DrawParams prm, RowOut out, const double *__restri
       const int total = R * p / 2;
       for (int q = tid; q < total; q += kSmallThreads) {
         int e = 2 * q;
-        int i = __umulhi((uint32_t)e, div_magic);
+        int i = __umulhi((uint32_t)e, div_magic);   // vec2 implies p >= 2
         int j = e - i * p;
         double *dst = xs + i * LDS + j;
         if (i < valid_rows) cp_async16(dst, src0 + (int64_t)i * d.ldx + j);
@@ -193,7 +193,7 @@ fused_small_kernel(RowData d, DrawParams prm, RowOut out, const double *__restri
     } else {
       const int total = R * p;
       for (int e = tid; e < total; e += kSmallThreads) {
-        int i = __umulhi((uint32_t)e, div_magic);
+        int i = p == 1 ? e : __umulhi((uint32_t)e, div_magic);   // 2^32 / 1 + 1 does not fit the magic
         int j = e - i * p;
         double *dst = xs + i * LDS + j;
         if (i < valid_rows) cp_async8(dst, src0 + (int64_t)i * d.ldx + j);

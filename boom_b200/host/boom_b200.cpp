@@ -15,12 +15,12 @@ void report_error(const std::string &msg) { throw std::runtime_error(msg); }
 
 RNG GlobalRng::rng(8675309);
 
+// distributions/rng.cpp:39-47 draws the seed as llround(U * 2^64), which overflows long long for half of all U
+// (every such seed collapses to one value).  Same contract here -- a seed > 2 from the parent stream -- but taken
+// from the generator's 64 raw bits.
 RNG::RngIntType seed_rng(RNG &rng) {
   RNG::RngIntType ans = 0;
-  while (ans <= 2) {
-    double u = rng() * static_cast<double>(std::numeric_limits<RNG::RngIntType>::max());
-    ans = (RNG::RngIntType)std::llround(std::min(u, 9.2e18));
-  }
+  while (ans <= 2) ans = rng.generator()();
   return ans;
 }
 

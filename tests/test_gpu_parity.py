@@ -232,7 +232,7 @@ def test_small_p_variants_agree_with_oracle(n, p, kind):
             xtx, xty, sc = ctx.poisson_step(beta, seed=3, iteration=2)
             rxtx, rxty, rsc = O.poisson_step(X, y, ex, beta, tab, 3, 2)
             np.testing.assert_allclose(sc, rsc, rtol=1e-10)
-        assert normwise_err(xtx, rxtx) < 1e-11
-        assert vec_err(xty, rxty) < 1e-10
+        assert normwise_err(xtx, rxtx) < 1e-11, ("variant", variant)
+        assert vec_err(xty, rxty) < 1e-10, ("variant", variant)
         np.testing.assert_array_equal(xtx, xtx.T)
         ctx.close()
