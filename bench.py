@@ -55,6 +55,15 @@ SEED = 20261017
 CHUNK = 50_000                 # rows per generator chunk: the data do not depend on the sharding
 FP64_DMMA_PEAK_TFLOPS = 37.0   # measured on this pool's B200 (profiles/r01_microbench_fp64.jsonl, DMMA issue-rate test)
 HBM_FALLBACK_GBS = 6650.0
+# DRAM bytes per observation measured by ncu (read + write), keyed by (kernel, p); see profiles/README.md
+NCU_TRAFFIC_BYTES_PER_ROW = {
+    ("syrk_dmma_kernel", 500): (87.874330e9 + 0.420380e9) / 10_000_000,
+    ("fused_tma_kernel", 16): (7.200950e9 + 0.006381e9) / 50_000_000,
+}
+NCU_TRAFFIC_SOURCE = {
+    ("syrk_dmma_kernel", 500): "profiles/r01_syrk_c3.summary.txt (n=10M, p=500: 87.87 GB read + 0.42 GB written per launch)",
+    ("fused_tma_kernel", 16): "profiles/r01b_fused_c5.summary.txt (n=50M, p=16: 7.20 GB read per launch)",
+}
 
 
 def beta_true(kind, p, nonzero):
@@ -103,7 +112,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -118,14 +127,22 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for (_, r) in self.rows if len(r) >= 7]
+        ok = [(t, r) for (t, r) in self.rows if len(r) >= 7]
+        rows = [r for (t, r) in ok if t0 <= t <= t1]
+        note = None
+        if not rows and ok:   # timed region shorter than the sampling period: the sample nearest to it
+            rows = [min(ok, key=lambda tr: min(abs(tr[0] - t0), abs(tr[0] - t1)))[1]]
+            note = "timed region shorter than the sampling period; nearest sample"
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm = sorted(float(r[0]) for r in rows)
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         reasons = [nm for k, nm in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
-                "samples": len(rows), "reasons": reasons}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+               "samples": len(rows), "reasons": reasons}
+        if note:
+            out["note"] = note
+        return out
 
 
 def measured_peaks():
@@ -260,12 +277,12 @@ def main():
     model = Model(p)
     model.adopt_device_data(row1 - row0, X.data_ptr(), p, y.data_ptr(), aux.data_ptr())
     smp = build(model)
+    clocks = ClockSampler(local_rank) if rank == 0 else None   # started before the warm-up so that it is sampling by the timed region
     for _ in range(warmup):
         model.sample_posterior()
     barrier()
     model.kernel_timings(True)
     launches0 = model.kernel_launches()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)
@@ -302,11 +319,14 @@ def main():
     else:
         k_ms = per["fused_small"][0]
         nbytes = 8.0 * my_rows * (p + 2)
-        roof = {"kernel": "fused_small_kernel", "bound": "hbm", "achieved": nbytes / (k_ms * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"],
+        roof = {"kernel": "fused_tma_kernel", "bound": "hbm", "achieved": nbytes / (k_ms * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "peak_source": peak_src, "algorithmic_bytes_per_launch": nbytes}
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["kernel_ms"] = k_ms
-    roof["traffic"] = None   # filled from the committed ncu capture (profiles/), see DESIGN.md
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
+    # kernel on the same workload (profiles/*.summary.txt), scaled to this rank's rows; null when no capture matches
+    roof["traffic"] = NCU_TRAFFIC_BYTES_PER_ROW.get((roof["kernel"], p), 0) * my_rows or None
+    roof["traffic_source"] = NCU_TRAFFIC_SOURCE.get((roof["kernel"], p))
     roof["kernel_ms_per_step"] = {k: round(v[0] * v[1] / steps, 4) for k, v in per.items() if v[1]}
 
     # ---- leg 2: e2e through the sampler surface on a model built from HOST arrays
