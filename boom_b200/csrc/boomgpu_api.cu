@@ -62,8 +62,10 @@ struct boomgpu_ctx {
   int *err_pin = nullptr;
 
   // TMA descriptor of X for the single-pass kernel (re-encoded when the data or the tile shape change)
-  CUtensorMap xmap;
-  const double *xmap_X = nullptr; int64_t xmap_n = -1, xmap_ldx = -1; int xmap_p = -1, xmap_nb = -1;
+  struct XMap {
+    CUtensorMap map;
+    const double *X = nullptr; int64_t n = -1, ldx = -1; int p = -1, box_cols = -1, box_rows = -1;
+  } xmap_small, xmap_syrk;
 
   // options / instrumentation
   int path = 0;
@@ -183,9 +185,10 @@ int choose_path(boomgpu_ctx *ctx, int *path) {
   } else {
     *path = ctx->p <= 64 ? 1 : 2;
   }
-  if (*path == 2 && ((ctx->ldx & 1) || !aligned16(ctx->X)))
-    return fail(ctx, BOOMGPU_ERR_ARG, "the two-pass path needs an even leading dimension and a 16-byte aligned X "
-                "(ldx = %lld); boomgpu_upload_* pads for you", (long long)ctx->ldx);
+  if (*path == 2 && ((ctx->ldx & 1) || !aligned16(ctx->X) || ctx->n >= (int64_t)0x7fffffc0))
+    return fail(ctx, BOOMGPU_ERR_ARG, "the two-pass path describes X to TMA: it needs an even leading dimension, a 16-byte aligned X "
+                "and fewer than 2^31 rows per context (ldx = %lld, n = %lld); boomgpu_upload_* pads for you", (long long)ctx->ldx,
+                (long long)ctx->n);
   return 0;
 }
 
@@ -241,9 +244,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int ensure_xmap(boomgpu_ctx *ctx, int nb) {
-  if (ctx->xmap_X == ctx->X && ctx->xmap_n == ctx->n && ctx->xmap_ldx == ctx->ldx && ctx->xmap_p == ctx->p && ctx->xmap_nb == nb)
-    return 0;
+int ensure_xmap(boomgpu_ctx *ctx, boomgpu_ctx::XMap &m, int box_cols, int box_rows) {
+  if (m.X == ctx->X && m.n == ctx->n && m.ldx == ctx->ldx && m.p == ctx->p && m.box_cols == box_cols && m.box_rows == box_rows) return 0;
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void *fn = nullptr;
@@ -254,14 +256,14 @@ int ensure_xmap(boomgpu_ctx *ctx, int nb) {
   }
   const cuuint64_t dims[2] = {(cuuint64_t)ctx->p, (cuuint64_t)ctx->n};
   const cuuint64_t strides[1] = {(cuuint64_t)ctx->ldx * sizeof(double)};
-  const cuuint32_t box[2] = {(cuuint32_t)tma_padw(nb), 32u};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = encode(&ctx->xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(ctx->X), dims, strides, box, estr,
+  CUresult r = encode(&m.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(ctx->X), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(ctx, BOOMGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for n=%lld p=%d ldx=%lld", (int)r,
-                                     (long long)ctx->n, ctx->p, (long long)ctx->ldx);
-  ctx->xmap_X = ctx->X; ctx->xmap_n = ctx->n; ctx->xmap_ldx = ctx->ldx; ctx->xmap_p = ctx->p; ctx->xmap_nb = nb;
+  if (r != CUDA_SUCCESS) return fail(ctx, BOOMGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for n=%lld p=%d ldx=%lld box=%dx%d", (int)r,
+                                     (long long)ctx->n, ctx->p, (long long)ctx->ldx, box_cols, box_rows);
+  m.X = ctx->X; m.n = ctx->n; m.ldx = ctx->ldx; m.p = ctx->p; m.box_cols = box_cols; m.box_rows = box_rows;
   return 0;
 }
 
@@ -276,13 +278,13 @@ struct TmaLauncher {
     constexpr int NW = tma_warps(NB);
     const size_t smem = tma_smem_bytes(NB);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (int rc = ensure_xmap(ctx, NB)) return rc;
+    if (int rc = ensure_xmap(ctx, ctx->xmap_small, tma_padw(NB), 32)) return rc;
     const int64_t nslices = (d.n + 31) / 32;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nslices + NW - 1) / NW, (int64_t)ctx->sms));
     if (ensure(ctx, &ctx->partials, &ctx->partials_cap, (int64_t)grid * tma_partial_len(NB))) return BOOMGPU_ERR_CUDA;
     {
       LaunchScope ls(ctx, 0);
-      kern<<<grid, 32 * NW, smem, ctx->stream>>>(ctx->xmap, d, prm, out, ctx->beta_dev, ctx->partials, ctx->err_dev);
+      kern<<<grid, 32 * NW, smem, ctx->stream>>>(ctx->xmap_small.map, d, prm, out, ctx->beta_dev, ctx->partials, ctx->err_dev);
     }
     CU(cudaGetLastError());
     *nparts = grid;
@@ -370,10 +372,11 @@ int launch_syrk(boomgpu_ctx *ctx, double *suf) {
   if (ensure(ctx, &ctx->partials, &ctx->partials_cap, need)) return BOOMGPU_ERR_CUDA;
   sp.partials = ctx->partials;
   static const SyrkUnitTable table = make_unit_table();
+  if (int rc = ensure_xmap(ctx, ctx->xmap_syrk, kSyrkPanelLd, kSyrkKB)) return rc;
   CU(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmemBytes));
   {
     LaunchScope ls(ctx, 2);
-    syrk_dmma_kernel<<<(unsigned)(ksplit * sp.nregions), kSyrkThreads, kSyrkSmemBytes, ctx->stream>>>(sp, table);
+    syrk_dmma_kernel<<<(unsigned)(ksplit * sp.nregions), kSyrkThreads, kSyrkSmemBytes, ctx->stream>>>(ctx->xmap_syrk.map, sp, table);
   }
   CU(cudaGetLastError());
   {

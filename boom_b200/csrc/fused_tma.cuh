@@ -42,13 +42,6 @@ __host__ __device__ constexpr size_t tma_smem_bytes(int nb) {
 }
 __host__ __device__ constexpr int64_t tma_partial_len(int nb) { return 64 * nb * nb + 8 * nb + 8; }
 
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
-                   smem_u32(dst)),
-               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-               : "memory");
-}
-
 template <int NB, int MODEL>
 __global__ void __launch_bounds__(32 * tma_warps(NB), 1)
 fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams prm, RowOut out, const double *__restrict__ beta,

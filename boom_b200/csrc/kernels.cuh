@@ -15,6 +15,7 @@
 // WeightedRegSuf::add_data (Models/Glm/WeightedRegressionModel.cpp:161-169) inside.
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "draws.cuh"
@@ -434,8 +435,14 @@ impute_rows_kernel(RowData d, DrawParams prm, RowOut out, const double *__restri
 // =============================================================================================
 constexpr int kSyrkConsumerWarps = 8;
 constexpr int kSyrkThreads = 32 * (kSyrkConsumerWarps + 4);  // + a producer warpgroup (1 TMA warp, 3 idle)
-constexpr int kSyrkKB = 16;        // rows per stage
-constexpr int kSyrkStages = 6;
+#ifndef BOOMGPU_SYRK_KB
+#define BOOMGPU_SYRK_KB 16
+#endif
+#ifndef BOOMGPU_SYRK_STAGES
+#define BOOMGPU_SYRK_STAGES 6
+#endif
+constexpr int kSyrkKB = BOOMGPU_SYRK_KB;        // rows per stage
+constexpr int kSyrkStages = BOOMGPU_SYRK_STAGES;
 constexpr int kSyrkPanelLd = 132;  // doubles
 constexpr int kSyrkStageDoubles = 2 * kSyrkKB * kSyrkPanelLd + 2 * kSyrkKB;  // panels A, B, then w[KB], s[KB]
 constexpr size_t kSyrkSmemBytes = sizeof(double) * kSyrkStages * kSyrkStageDoubles + 8 * 2 * kSyrkStages + 64;
@@ -467,6 +474,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// 2-D TMA tile load: box of the tensor map at (c0 = column, c1 = row) -> shared memory, completes on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                : "memory");
 }
 
@@ -538,10 +553,10 @@ __device__ __forceinline__ void syrk_consume(const SyrkWarpCtx &wc) {
 #pragma unroll
           for (int n = 0; n < 4; ++n)
             if (T0 == 1 || n >= m) dmma884(c0[m][n][0], c0[m][n][1], aw[m], b[n]);
-        if (DUTY == 1) {
-          const double sv = (lane >> 2) == 0 ? s_s[row] : 0.0;
+        if (DUTY == 1) {  // X's: four DFMA on the A fragments already in registers (a DMMA with B = [s, 0, ..] wasted 7/8 of it)
+          const double sv = s_s[row];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) dmma884(cx[m][0], cx[m][1], a[m], sv);
+          for (int m = 0; m < 4; ++m) cx[m][0] = fma(a[m], sv, cx[m][0]);
         }
         if (T1 != 0) {
           if (!kSameA) {
@@ -556,9 +571,9 @@ __device__ __forceinline__ void syrk_consume(const SyrkWarpCtx &wc) {
             for (int n = 0; n < 4; ++n)
               if (T1 == 1 || n >= m) dmma884(c1[m][n][0], c1[m][n][1], aw[m], b[n]);
           if (DUTY == 2) {
-            const double sv = (lane >> 2) == 0 ? s_s[row] : 0.0;
+            const double sv = s_s[row];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) dmma884(cx[m][0], cx[m][1], a[m], sv);
+            for (int m = 0; m < 4; ++m) cx[m][0] = fma(a[m], sv, cx[m][0]);
           }
         }
       }
@@ -585,6 +600,12 @@ __device__ __forceinline__ void syrk_consume(const SyrkWarpCtx &wc) {
   if (DUTY != 0) {
     const int ui = DUTY == 1 ? wc.u0.ui : wc.u1.ui;
     const int mmax = DUTY == 1 ? wc.mmax0 : wc.mmax1;
+    // lane holds the rows = lane & 3 (mod 4) of column 32 ui + 8 m + (lane >> 2): sum the four row classes
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      cx[m][0] += __shfl_xor_sync(0xffffffffu, cx[m][0], 1);
+      cx[m][0] += __shfl_xor_sync(0xffffffffu, cx[m][0], 2);
+    }
     if ((lane & 3) == 0) {
 #pragma unroll
       for (int m = 0; m < 4; ++m)
@@ -593,7 +614,8 @@ __device__ __forceinline__ void syrk_consume(const SyrkWarpCtx &wc) {
   }
 }
 
-__global__ void __launch_bounds__(kSyrkThreads, 1) syrk_dmma_kernel(SyrkParams prm, SyrkUnitTable table) {
+__global__ void __launch_bounds__(kSyrkThreads, 1)
+syrk_dmma_kernel(const __grid_constant__ CUtensorMap xmap, SyrkParams prm, SyrkUnitTable table) {
   extern __shared__ __align__(128) double smem[];
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kSyrkStages * kSyrkStageDoubles);
   uint64_t *empty_bar = full_bar + kSyrkStages;
@@ -614,29 +636,22 @@ __global__ void __launch_bounds__(kSyrkThreads, 1) syrk_dmma_kernel(SyrkParams p
   }
   __syncthreads();
 
-  // valid columns of each panel (bytes to copy); X rows are ldx doubles apart and ldx is even
-  const int colsA = min(128, (int)min((int64_t)prm.ldx, (int64_t)((prm.p + 7) & ~7)) - 128 * I);
-  const int colsB = min(128, (int)min((int64_t)prm.ldx, (int64_t)((prm.p + 7) & ~7)) - 128 * J);
-
-  // ===== producer role (warp 0): lanes 0..15 copy the rows of panel A, lanes 16..31 those of panel B
-  const uint32_t bytesA = (uint32_t)colsA * 8, bytesB = diag ? 0u : (uint32_t)colsB * 8;
-  const uint32_t stage_bytes = kSyrkKB * (bytesA + bytesB) + 2 * kSyrkKB * 8;
+  // ===== producer role: ONE TMA tile per panel and stage.  The box is {132 columns, 16 rows}: four columns wider
+  // than the panel, so the tile lands with the 132-double row pitch the fragment loads want (4 mod 8: conflict free)
+  // without any per-row copy; columns beyond p and rows beyond n arrive as zeros.  (Per-row bulk copies kept the TMA
+  // unit at ~34 requests per stage, one per ~55 cycles: 13 % of the consumers' samples were waits for data.)
+  constexpr uint32_t kPanelBytes = kSyrkKB * kSyrkPanelLd * sizeof(double);
+  const uint32_t stage_bytes = (diag ? 1u : 2u) * kPanelBytes + 2 * kSyrkKB * 8;
   auto produce = [&](int it) {
     const int s = it % kSyrkStages;
     const uint32_t phase = (it / kSyrkStages) & 1;
     mbar_wait(empty_bar + s, phase ^ 1);
     double *stage = smem + s * kSyrkStageDoubles;
     const int64_t r0 = row_begin + (int64_t)it * kSyrkKB;
-    if (lane == 0) mbar_expect_tx(full_bar + s, stage_bytes);
-    __syncwarp();
-    const int rr = lane & 15;
-    const int64_t row = min(r0 + rr, prm.n - 1);  // clamp: padded rows carry w = 0
-    if (lane < 16) {
-      tma_bulk_g2s(stage + rr * kSyrkPanelLd, prm.X + row * prm.ldx + 128 * I, bytesA, full_bar + s);
-    } else if (!diag) {
-      tma_bulk_g2s(stage + (kSyrkKB + rr) * kSyrkPanelLd, prm.X + row * prm.ldx + 128 * J, bytesB, full_bar + s);
-    }
     if (lane == 0) {
+      mbar_expect_tx(full_bar + s, stage_bytes);
+      tma_load_2d(stage, &xmap, 128 * I, (int)r0, full_bar + s);
+      if (!diag) tma_load_2d(stage + kSyrkKB * kSyrkPanelLd, &xmap, 128 * J, (int)r0, full_bar + s);
       tma_bulk_g2s(stage + 2 * kSyrkKB * kSyrkPanelLd, prm.w + r0, kSyrkKB * 8, full_bar + s);
       tma_bulk_g2s(stage + 2 * kSyrkKB * kSyrkPanelLd + kSyrkKB, prm.s + r0, kSyrkKB * 8, full_bar + s);
     }

@@ -16,6 +16,7 @@ CFG = {
     "c1": ("logit", 100_000, 20), "c2": ("poisson", 1_000_000, 50), "c3": ("logit", 10_000_000, 500),
     "c4": ("logit", 2_000_000, 4000), "c5": ("logit", 25_000_000, 16), "c3s": ("logit", 1_000_000, 500),
     "p128": ("logit", 4_000_000, 128), "p64": ("logit", 8_000_000, 64), "p32": ("logit", 8_000_000, 32),
+    "c4s": ("logit", 500_000, 4000), "p1000": ("logit", 2_000_000, 1000), "p260": ("logit", 4_000_000, 260),
     "p8": ("logit", 25_000_000, 8), "p24": ("logit", 12_000_000, 24), "p48": ("poisson", 4_000_000, 48),
 }
 
