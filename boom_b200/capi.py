@@ -21,7 +21,8 @@ SYMBOLS = (
     "boomgpu_adopt_binomial", "boomgpu_adopt_poisson", "boomgpu_set_logit_mixture", "boomgpu_set_poisson_table",
     "boomgpu_logit_step", "boomgpu_poisson_step", "boomgpu_suf_len", "boomgpu_logit_step_device",
     "boomgpu_poisson_step_device", "boomgpu_synchronize", "boomgpu_suf_buffer", "boomgpu_download", "boomgpu_accumulate", "boomgpu_logit_draw",
-    "boomgpu_poisson_draw", "boomgpu_binomial_loglike", "boomgpu_poisson_loglike", "boomgpu_kernel_launches",
+    "boomgpu_poisson_draw", "boomgpu_binomial_loglike", "boomgpu_poisson_loglike", "boomgpu_binomial_loglike_derivs",
+    "boomgpu_poisson_loglike_derivs", "boomgpu_kernel_launches",
     "boomgpu_get_timings",
 )
 
@@ -236,6 +237,20 @@ class Context:
         out = C.c_double()
         self._check(self._lib.boomgpu_poisson_loglike(self._h, _dp(beta), C.byref(out)))
         return out.value
+
+    def binomial_loglike_derivs(self, beta, log_alpha=0.0):
+        beta = _f64(beta)
+        ll = C.c_double()
+        g, h = np.empty(self.p), np.empty((self.p, self.p))
+        self._check(self._lib.boomgpu_binomial_loglike_derivs(self._h, _dp(beta), C.c_double(log_alpha), C.byref(ll), _dp(g), _dp(h)))
+        return ll.value, g, h
+
+    def poisson_loglike_derivs(self, beta):
+        beta = _f64(beta)
+        ll = C.c_double()
+        g, h = np.empty(self.p), np.empty((self.p, self.p))
+        self._check(self._lib.boomgpu_poisson_loglike_derivs(self._h, _dp(beta), C.byref(ll), _dp(g), _dp(h)))
+        return ll.value, g, h
 
     # ---- instrumentation
     def kernel_launches(self):

@@ -496,6 +496,7 @@ DrawParams make_prm(boomgpu_ctx *ctx, int clt, uint64_t seed, uint64_t iteration
   prm.key.seed = seed;
   prm.key.iteration = iteration;
   prm.clt_threshold = clt;
+  prm.log_alpha = 0.0;
   return prm;
 }
 
@@ -528,6 +529,29 @@ int check_dims(boomgpu_ctx *ctx, int64_t n, int p, int64_t ldx, const void *X) {
   if (!ctx) return BOOMGPU_ERR_ARG;
   if (n < 0 || p <= 0 || ldx < p || (!X && n > 0)) return fail(ctx, BOOMGPU_ERR_ARG, "bad dimensions n=%lld p=%d ldx=%lld", (long long)n, p, (long long)ldx);
   if (p > 16384) return fail(ctx, BOOMGPU_ERR_ARG, "p = %d exceeds the supported maximum 16384", p);
+  return 0;
+}
+
+// log likelihood + gradient + Hessian in ONE pass of the step kernels (MODEL = kLogitLL / kPoissonLL):
+// gradient = X's with s = dl/d eta, Hessian = -X'WX with w = -d2l/d eta2, log likelihood in the y'Wy slot.
+template <int MODEL>
+int loglike_derivs_impl(boomgpu_ctx *ctx, int model, const double *beta, double log_alpha, double *loglike, double *gradient,
+                               double *hessian) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (ctx->model != model || !ctx->X) return fail(ctx, BOOMGPU_ERR_STATE, "no matching data uploaded to this context");
+  if (!beta || !loglike) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
+  DeviceGuard g(ctx->device);
+  if (int rc = ensure_suf(ctx)) return rc;
+  DrawParams prm = make_prm(ctx, 0, 0, 0);
+  prm.log_alpha = log_alpha;
+  RowOut out{nullptr, nullptr, nullptr, nullptr};
+  if (int rc = run_step<MODEL>(ctx, beta, prm, out, nullptr, nullptr, ctx->suf_dev)) return rc;
+  const int p = ctx->p;
+  CU(cudaMemcpyAsync(ctx->suf_pin, ctx->suf_dev, sizeof(double) * (size_t)boomgpu_suf_len(p), cudaMemcpyDeviceToHost, ctx->stream));
+  if (int rc = finish_and_check(ctx)) return rc;
+  *loglike = ctx->n == 0 ? 0.0 : ctx->suf_pin[(size_t)p * p + p + 1];
+  if (gradient) memcpy(gradient, ctx->suf_pin + (size_t)p * p, sizeof(double) * p);
+  if (hessian) for (size_t e = 0; e < (size_t)p * p; ++e) hessian[e] = -ctx->suf_pin[e];
   return 0;
 }
 
@@ -942,6 +966,14 @@ static int loglike_impl(boomgpu_ctx *ctx, int model, const double *beta, double 
   if (e != cudaSuccess) return fail(ctx, BOOMGPU_ERR_CUDA, "log likelihood failed: %s", cudaGetErrorString(e));
   *loglike = ctx->n == 0 ? 0.0 : result;
   return 0;
+}
+
+int boomgpu_binomial_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double log_alpha, double *loglike, double *gradient,
+                                    double *hessian) {
+  return loglike_derivs_impl<kLogitLL>(ctx, kLogit, beta, log_alpha, loglike, gradient, hessian);
+}
+int boomgpu_poisson_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *gradient, double *hessian) {
+  return loglike_derivs_impl<kPoissonLL>(ctx, kPoisson, beta, 0.0, loglike, gradient, hessian);
 }
 
 int boomgpu_binomial_loglike(boomgpu_ctx *ctx, const double *beta, double *loglike) { return loglike_impl(ctx, kLogit, beta, loglike); }

@@ -22,7 +22,9 @@
 
 namespace boomgpu {
 
-enum Model : int { kLogit = 0, kPoisson = 1, kSupplied = 2 };
+// kLogitLL / kPoissonLL: no draw; the row's "latent" is its log-likelihood curvature, so the same kernels return
+// log likelihood, gradient and (minus) Hessian in one pass (BinomialLogitModel.cpp:140-180, PoissonRegressionModel.cpp:56-95)
+enum Model : int { kLogit = 0, kPoisson = 1, kSupplied = 2, kLogitLL = 3, kPoissonLL = 4 };
 
 struct RowData {
   const double *X;
@@ -51,6 +53,7 @@ struct DrawParams {
   PoissonTable tab;
   RngKey key;
   int clt_threshold;
+  double log_alpha;         // kLogitLL: eta = x'beta - log_alpha (BinomialLogitModel.cpp:168)
 };
 
 // ---- small helpers ------------------------------------------------------------------------
@@ -85,8 +88,8 @@ template <int MODEL>
 __device__ __forceinline__ RowObs load_obs(const RowData &d, int64_t i) {
   RowObs o;
   o.y = 0; o.aux = 0; o.yi = 0;
-  if (MODEL == kLogit) { o.y = __ldg(d.y + i); o.aux = __ldg(d.ntrials + i); }
-  else if (MODEL == kPoisson) { o.yi = __ldg(d.yi + i); o.aux = __ldg(d.exposure + i); }
+  if (MODEL == kLogit || MODEL == kLogitLL) { o.y = __ldg(d.y + i); o.aux = __ldg(d.ntrials + i); }
+  else if (MODEL == kPoisson || MODEL == kPoissonLL) { o.yi = __ldg(d.yi + i); o.aux = __ldg(d.exposure + i); }
   else { o.y = __ldg(d.w_in + i); o.aux = __ldg(d.s_in + i); }
   return o;
 }
@@ -120,6 +123,20 @@ __device__ __forceinline__ RowLatent impute_row(const RowData &d, const DrawPara
       }
       if (out.k2) { out.k2[2 * i] = o.k_int; out.k2[2 * i + 1] = o.k_ext; }
     }
+  } else if (MODEL == kLogitLL) {
+    // w = n p q (so that -X'WX is the Hessian), s = y - n p (X's is the gradient), the log density rides in the yWy slot
+    const double e = eta - prm.log_alpha;
+    const double pr = 1.0 / (1.0 + exp(-e));
+    r.w = obs.aux * pr * (1.0 - pr);
+    r.s = obs.y - obs.aux * pr;
+    r.yWy = dbinom_log(obs.y, obs.aux, e);
+    if (!(obs.y <= obs.aux) || obs.y < 0 || !isfinite(eta)) atomicOr(err, 2);
+  } else if (MODEL == kPoissonLL) {
+    const double lambda = exp(eta);
+    r.w = lambda;                                  // the reference's Hessian weight has no exposure (PoissonRegressionModel.cpp:84)
+    r.s = (double)obs.yi - obs.aux * lambda;
+    r.yWy = dpois_log((double)obs.yi, obs.aux * lambda);
+    if (obs.yi < 0 || !(obs.aux >= 0) || !isfinite(eta)) atomicOr(err, 2);
   } else {
     r.w = obs.y; r.s = obs.aux;
   }

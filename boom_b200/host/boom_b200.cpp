@@ -304,10 +304,26 @@ void BinomialLogitModel::upload(DeviceData &dev) {
 }
 double BinomialLogitModel::log_likelihood(const Vector &beta) {
   if ((int)beta.size() != xdim()) report_error("log_likelihood: wrong size beta");
+  if (log_alpha_ != 0.0) return log_likelihood_derivs(beta, nullptr, nullptr);   // the offset enters eta (BinomialLogitModel.cpp:168)
   DeviceData &dev(device_data());
   double ans = 0;
   dev.check(boomgpu_binomial_loglike(dev.ctx(), beta.data(), &ans));
   return ans;
+}
+
+double BinomialLogitModel::log_likelihood_derivs(const Vector &beta, Vector *g, SpdMatrix *h) {
+  if ((int)beta.size() != xdim()) report_error("log_likelihood: wrong size beta");
+  DeviceData &dev(device_data());
+  double ans = 0;
+  if (g) g->assign(xdim(), 0.0);
+  if (h && h->dim != xdim()) *h = SpdMatrix(xdim());
+  dev.check(boomgpu_binomial_loglike_derivs(dev.ctx(), beta.data(), log_alpha_, &ans, g ? g->data() : nullptr,
+                                            h ? h->a.data() : nullptr));
+  return ans;
+}
+void BinomialLogitModel::set_nonevent_sampling_prob(double alpha) {
+  if (!(alpha > 0 && alpha <= 1)) report_error("alpha (proportion of non-events retained in the data) must be in (0, 1]");
+  log_alpha_ = std::log(alpha);
 }
 
 PoissonRegressionModel::PoissonRegressionModel(int64_t n, int p, const double *X, const int64_t *y, const double *ex)
@@ -338,6 +354,16 @@ double PoissonRegressionModel::log_likelihood(const Vector &beta) {
   DeviceData &dev(device_data());
   double ans = 0;
   dev.check(boomgpu_poisson_loglike(dev.ctx(), beta.data(), &ans));
+  return ans;
+}
+
+double PoissonRegressionModel::log_likelihood_derivs(const Vector &beta, Vector *g, SpdMatrix *h) {
+  if ((int)beta.size() != xdim()) report_error("log_likelihood: wrong size beta");
+  DeviceData &dev(device_data());
+  double ans = 0;
+  if (g) g->assign(xdim(), 0.0);
+  if (h && h->dim != xdim()) *h = SpdMatrix(xdim());
+  dev.check(boomgpu_poisson_loglike_derivs(dev.ctx(), beta.data(), &ans, g ? g->data() : nullptr, h ? h->a.data() : nullptr));
   return ans;
 }
 
@@ -688,6 +714,67 @@ void SpikeSlabCore::draw_beta(RNG &rng, GlmCoefs &coef, const WeightedRegSuf &su
   coef.set_included_coefficients(z);
 }
 
+bool SpikeSlabCore::find_posterior_mode(GlmModelBase &model, double epsilon, double *log_posterior_at_mode) const {
+  const double neg_inf = -std::numeric_limits<double>::infinity();
+  *log_posterior_at_mode = neg_inf;
+  GlmCoefs &coef(model.coef());
+  const Selector g = coef.inc();
+  const int k = g.nvars(), p = g.nvars_possible();
+  if (k == 0) return false;   // the reference declines the empty model as well (.cpp:154-159)
+  const std::vector<int> pos = g.included_positions();
+  const MvnModel slab_g(g.select(slab_->mu()), g.select(slab_->siginv()), true);
+  Vector beta = coef.included_coefficients();
+  Vector grad_full;
+  SpdMatrix hess_full;
+  // objective, gradient and NEGATIVE Hessian on the included coordinates
+  auto evaluate = [&](const Vector &b, Vector *grad, Vector *neg_hess) {
+    const Vector full = g.expand(b);
+    double f = model.log_likelihood_derivs(full, grad ? &grad_full : nullptr, neg_hess ? &hess_full : nullptr);
+    f += slab_g.logp(b);
+    if (grad) {
+      grad->assign(k, 0.0);
+      for (int i = 0; i < k; ++i) {
+        double s = 0;
+        for (int j = 0; j < k; ++j) s += slab_g.siginv()(i, j) * (b[j] - slab_g.mu()[j]);
+        (*grad)[i] = grad_full[pos[i]] - s;
+      }
+    }
+    if (neg_hess) {
+      neg_hess->assign((size_t)k * k, 0.0);
+      for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) (*neg_hess)[(size_t)i * k + j] = slab_g.siginv()(i, j) - hess_full.a[(size_t)pos[i] * p + pos[j]];
+    }
+    return f;
+  };
+  Vector grad, nh;
+  double f = evaluate(beta, &grad, &nh);
+  if (!std::isfinite(f)) return false;
+  for (int iter = 0; iter < 100; ++iter) {
+    if (!cholesky_lower(nh.data(), k)) return false;   // the log posterior is concave: -H is positive definite
+    Vector step(grad);
+    lsolve_inplace(nh.data(), k, step.data());
+    ltsolve_inplace(nh.data(), k, step.data());        // step = (-H)^-1 grad
+    double decrement = 0;
+    for (int i = 0; i < k; ++i) decrement += step[i] * grad[i];
+    double scale = 1.0, f_new = neg_inf;
+    Vector cand(k), grad_new, nh_new;
+    for (int half = 0; half < 40; ++half, scale *= 0.5) {
+      for (int i = 0; i < k; ++i) cand[i] = beta[i] + scale * step[i];
+      f_new = evaluate(cand, &grad_new, &nh_new);
+      if (std::isfinite(f_new) && f_new >= f - 1e-12 * std::fabs(f)) break;
+    }
+    if (!std::isfinite(f_new) || f_new < f - 1e-12 * std::fabs(f)) return false;
+    const double gain = f_new - f;
+    beta = cand; f = f_new; grad = grad_new; nh = nh_new;
+    if (gain < epsilon && decrement < 2 * epsilon) {
+      *log_posterior_at_mode = f;
+      coef.set_included_coefficients(beta);
+      return true;
+    }
+  }
+  return false;
+}
+
 double SpikeSlabCore::logpri(const GlmCoefs &coef) const {
   const Selector &g(coef.inc());
   double ans = spike_->logp(g);
@@ -807,6 +894,9 @@ double BinomialLogitSpikeSlabSampler::logpri() const { return core_.logpri(model
 void BinomialLogitSpikeSlabSampler::draw_model_indicators() { core_.draw_model_indicators(rng(), model_->coef(), suf()); }
 void BinomialLogitSpikeSlabSampler::draw_beta() { core_.draw_beta(rng(), model_->coef(), suf()); }
 double BinomialLogitSpikeSlabSampler::log_model_prob(const Selector &g) const { return core_.log_model_prob(g, suf()); }
+void BinomialLogitSpikeSlabSampler::find_posterior_mode(double epsilon) {
+  posterior_mode_found_ = core_.find_posterior_mode(*model_, epsilon, &log_posterior_at_mode_);
+}
 
 // ---------------------------------------------------------------------------------------------
 void PoissonRegressionAuxMixSampler::set_mixture_table(const Vector &ser, int64_t largest_index) {
@@ -890,5 +980,8 @@ void PoissonRegressionSpikeSlabSampler::draw() {
   core_.draw_beta(rng(), model_->coef(), suf_);
 }
 double PoissonRegressionSpikeSlabSampler::logpri() const { return core_.logpri(model_->coef()); }
+void PoissonRegressionSpikeSlabSampler::find_posterior_mode(double epsilon) {
+  core_.find_posterior_mode(*model_, epsilon, &log_posterior_at_mode_);
+}
 
 }  // namespace BOOM_B200

@@ -202,6 +202,10 @@ class GlmModelBase {
   void sample_posterior();
   double logpri() const;
 
+  // log likelihood at a FULL coefficient vector with gradient (p) and Hessian (p x p) from one device pass
+  // (BinomialLogitModel.cpp:140-180, PoissonRegressionModel.cpp:56-95); g / h may be null
+  virtual double log_likelihood_derivs(const Vector &beta, Vector *g, SpdMatrix *h) = 0;
+
   // ---- device residency
   void set_device(int device);            // which GPU holds this model's rows (default 0)
   void set_row_offset(uint64_t first_global_row);  // this shard's first global row (multi-GPU)
@@ -250,11 +254,16 @@ class BinomialLogitModel : public GlmModelBase {
   // Models/Glm/BinomialLogitModel.cpp:140-180, value only, evaluated on the device
   double log_likelihood(const Vector &beta);
   double log_likelihood() { return log_likelihood(Beta()); }
+  double log_likelihood_derivs(const Vector &beta, Vector *g, SpdMatrix *h) override;
+  // nonevent down-sampling offset (BinomialLogitModel.hpp:82-86): enters the likelihood, not the auxmix draws
+  void set_nonevent_sampling_prob(double alpha);
+  double log_alpha() const { return log_alpha_; }
 
  protected:
   void upload(DeviceData &dev) override;
 
  private:
+  double log_alpha_ = 0.0;
   Vector y_, n_;
   const double *dX_ = nullptr, *dy_ = nullptr, *dn_ = nullptr;
   int64_t dldx_ = 0;
@@ -270,6 +279,7 @@ class PoissonRegressionModel : public GlmModelBase {
   int64_t nobs() const { return adopted_ ? adopted_n_ : (int64_t)y_.size(); }
   double log_likelihood(const Vector &beta);
   double log_likelihood() { return log_likelihood(Beta()); }
+  double log_likelihood_derivs(const Vector &beta, Vector *g, SpdMatrix *h) override;
   const std::vector<int64_t> &y() const { return y_; }
 
  protected:
@@ -339,6 +349,10 @@ class SpikeSlabCore {
   void allow_model_selection(bool tf) { allow_model_selection_ = tf; }
   void limit_model_selection(int max_flips) { max_flips_ = max_flips; }
   bool model_selection_allowed() const { return allow_model_selection_; }
+  // Newton-Raphson (with step halving) on the included coefficients of log slab(beta_gamma) + log likelihood, the
+  // objective of BinomialLogitSpikeSlabSampler::find_posterior_mode (.cpp:123-177) / PoissonRegressionSpikeSlabSampler
+  // (.cpp:69-106); sets the model's included coefficients on success.  Returns false when gamma is empty or on failure.
+  bool find_posterior_mode(GlmModelBase &model, double epsilon, double *log_posterior_at_mode) const;
   // test hook: log_model_prob of every proposal along a path of flips (accept[i]: commit flip i), evaluated the
   // way the sweep evaluates it (bordered Cholesky factors); the last entry is the final model's value
   Vector flip_path_log_probs(const Selector &start, const WeightedRegSuf &suf, const std::vector<int> &flips,
@@ -399,9 +413,15 @@ class BinomialLogitSpikeSlabSampler : public BinomialLogitAuxmixSampler {
   void allow_model_selection(bool tf) { core_.allow_model_selection(tf); }
   void limit_model_selection(int max_flips) { core_.limit_model_selection(max_flips); }
   int xdim() const { return model_->xdim(); }
+  void find_posterior_mode(double epsilon = 1e-5);   // .cpp:147-177
+  bool can_find_posterior_mode() const { return true; }
+  bool posterior_mode_found() const { return posterior_mode_found_; }
+  double log_posterior_at_mode() const { return log_posterior_at_mode_; }
 
  private:
   SpikeSlabCore core_;
+  bool posterior_mode_found_ = false;
+  double log_posterior_at_mode_ = -1.0 / 0.0;
 };
 
 class PoissonRegressionAuxMixSampler : public PosteriorSampler {
@@ -447,9 +467,13 @@ class PoissonRegressionSpikeSlabSampler : public PoissonRegressionAuxMixSampler 
   double logpri() const override;
   void allow_model_selection(bool tf) { core_.allow_model_selection(tf); }
   void limit_model_selection(int max_flips) { core_.limit_model_selection(max_flips); }
+  void find_posterior_mode(double epsilon = 1e-5);   // PoissonRegressionSpikeSlabSampler.cpp:69-106
+  bool can_find_posterior_mode() const { return true; }
+  double log_posterior_at_mode() const { return log_posterior_at_mode_; }
 
  private:
   SpikeSlabCore core_;
+  double log_posterior_at_mode_ = -1.0 / 0.0;
 };
 
 // The logit mixture every BinomialLogit sampler uploads; defaults to the 9-component table of

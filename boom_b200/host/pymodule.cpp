@@ -75,6 +75,11 @@ void bind_model_common(py::class_<M, std::shared_ptr<M>> &c) {
         for (int c = 0; c < 5; ++c) out[names[c]] = py::make_tuple(ms[c], cnt[c]);
         return out;
       }, py::arg("reset") = false)
+      .def("log_likelihood_derivs", [](M &m, const NpD &b) {
+        Vector g; SpdMatrix h;
+        double ll = m.log_likelihood_derivs(to_vec(b), &g, &h);
+        return py::make_tuple(ll, from_vec(g), from_spd(h));
+      })
       .def("log_likelihood", [](M &m) { return m.log_likelihood(); })
       .def("log_likelihood", [](M &m, const NpD &b) { return m.log_likelihood(to_vec(b)); });
 }
@@ -114,6 +119,7 @@ PYBIND11_MODULE(_host, m) {
         mo.adopt_device_data(n, reinterpret_cast<const double *>(dX), ldx, reinterpret_cast<const double *>(dy),
                              reinterpret_cast<const double *>(dn));
       });
+  blm.def("set_nonevent_sampling_prob", &BinomialLogitModel::set_nonevent_sampling_prob);
   bind_model_common(blm);
 
   py::class_<PoissonRegressionModel, std::shared_ptr<PoissonRegressionModel>> prm(m, "PoissonRegressionModel");
@@ -177,6 +183,9 @@ PYBIND11_MODULE(_host, m) {
         for (size_t i = 0; i < bits.size(); ++i) if (bits[i]) g.add((int)i);
         return s.log_model_prob(g);
       })
+      .def("find_posterior_mode", &BinomialLogitSpikeSlabSampler::find_posterior_mode, py::arg("epsilon") = 1e-5)
+      .def_property_readonly("posterior_mode_found", &BinomialLogitSpikeSlabSampler::posterior_mode_found)
+      .def_property_readonly("log_posterior_at_mode", &BinomialLogitSpikeSlabSampler::log_posterior_at_mode)
       .def("allow_model_selection", &BinomialLogitSpikeSlabSampler::allow_model_selection)
       .def("limit_model_selection", &BinomialLogitSpikeSlabSampler::limit_model_selection);
 
@@ -207,6 +216,8 @@ PYBIND11_MODULE(_host, m) {
            }),
            py::arg("model"), py::arg("slab"), py::arg("spike"), py::arg("number_of_threads") = 1,
            py::arg("seeding_rng") = std::ref(GlobalRng::rng), py::keep_alive<1, 2>())
+      .def("find_posterior_mode", &PoissonRegressionSpikeSlabSampler::find_posterior_mode, py::arg("epsilon") = 1e-5)
+      .def_property_readonly("log_posterior_at_mode", &PoissonRegressionSpikeSlabSampler::log_posterior_at_mode)
       .def("allow_model_selection", &PoissonRegressionSpikeSlabSampler::allow_model_selection)
       .def("limit_model_selection", &PoissonRegressionSpikeSlabSampler::limit_model_selection);
 

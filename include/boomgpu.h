@@ -31,9 +31,9 @@
  *       (PoissonRegressionAuxMixSampler.cpp:58-81): PoissonDataImputer::impute
  *       (PoissonDataImputer.cpp:36-98) and WeightedRegSuf::add_data/combine
  *       (Models/Glm/WeightedRegressionModel.cpp:69-87,161-169).
- *   boomgpu_binomial_loglike / boomgpu_poisson_loglike
+ *   boomgpu_binomial_loglike / boomgpu_poisson_loglike (value only), boomgpu_*_loglike_derivs (value, gradient, Hessian)
  *       BinomialLogitModel::log_likelihood (Models/Glm/BinomialLogitModel.cpp:140-180),
- *       PoissonRegressionModel::log_likelihood (Models/Glm/PoissonRegressionModel.cpp:56-95), value only.
+ *       PoissonRegressionModel::log_likelihood (Models/Glm/PoissonRegressionModel.cpp:56-95).
  *
  * Threading: one host thread per context; a context is bound to one CUDA device.
  * Multi-GPU = one context (one process) per GPU, rows sharded, the packed
@@ -130,6 +130,14 @@ int boomgpu_poisson_draw(boomgpu_ctx *ctx, const double *beta, uint64_t seed, ui
                          double *out6, int32_t *kout2);
 int boomgpu_binomial_loglike(boomgpu_ctx *ctx, const double *beta, double *loglike);
 int boomgpu_poisson_loglike(boomgpu_ctx *ctx, const double *beta, double *loglike);
+/* log likelihood with gradient (p, may be NULL) and Hessian (p x p, symmetric, may be NULL) in one pass over the rows:
+ * BinomialLogitModel::log_likelihood(beta, g, h) (Models/Glm/BinomialLogitModel.cpp:140-180; eta = x'beta - log_alpha,
+ * g = sum (y - n p) x, h = -sum n p q x x') and PoissonRegressionModel::log_likelihood(beta, g, h)
+ * (Models/Glm/PoissonRegressionModel.cpp:56-95; g = sum (y - E lambda) x, h = -sum lambda x x', exposure-free as there).
+ * beta is the FULL coefficient vector (zeros at excluded positions); callers select the included sub-blocks. */
+int boomgpu_binomial_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double log_alpha, double *loglike, double *gradient,
+                                    double *hessian);
+int boomgpu_poisson_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *gradient, double *hessian);
 
 /* ---- instrumentation ------------------------------------------------------------------- */
 /* number of kernels this context has launched so far */

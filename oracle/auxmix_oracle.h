@@ -122,6 +122,12 @@ double bo_binomial_logit_loglike(int64_t n, int p, const double *X, int64_t ldx,
 double bo_poisson_loglike(int64_t n, int p, const double *X, int64_t ldx, const int64_t *y,
                           const double *exposure, const double *beta);
 
+/* the same with gradient g (p) and Hessian h (p x p): BinomialLogitModel.cpp:140-180, PoissonRegressionModel.cpp:56-95 */
+double bo_binomial_logit_loglike_derivs(int64_t n, int p, const double *X, int64_t ldx, const double *y,
+                                        const double *ntrials, const double *beta, double log_alpha, double *g, double *h);
+double bo_poisson_loglike_derivs(int64_t n, int p, const double *X, int64_t ldx, const int64_t *y, const double *exposure,
+                                 const double *beta, double *g, double *h);
+
 /* ---- synthetic data shared by every arm -------------------------- */
 void bo_synth_beta(int p, int nonzero, double intercept, double *beta);
 void bo_synth_x(int64_t n, int p, uint64_t seed, double xscale, uint64_t row_offset, double *X, int64_t ldx);

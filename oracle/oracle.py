@@ -55,6 +55,8 @@ def lib():
         _lib.bo_dbinom_log.argtypes = [C.c_double] * 3
         _lib.bo_binomial_logit_loglike.restype = C.c_double
         _lib.bo_poisson_loglike.restype = C.c_double
+        _lib.bo_binomial_logit_loglike_derivs.restype = C.c_double
+        _lib.bo_poisson_loglike_derivs.restype = C.c_double
     return _lib
 
 
@@ -255,6 +257,26 @@ def poisson_loglike(X, y, exposure, beta):
     n, p = X.shape
     return lib().bo_poisson_loglike(C.c_int64(n), C.c_int(p), _dp(X), C.c_int64(p), y.ctypes.data_as(c_i64_p),
                                     _dp(exposure), _dp(beta))
+
+
+def binomial_logit_loglike_derivs(X, y, ntrials, beta, log_alpha=0.0):
+    """(loglike, gradient, hessian) as BinomialLogitModel::log_likelihood(beta, &g, &h) (BinomialLogitModel.cpp:140-180)."""
+    X, y, ntrials, beta = _f64(X), _f64(y), _f64(ntrials), _f64(beta)
+    n, p = X.shape
+    g, h = np.empty(p), np.empty((p, p))
+    ll = lib().bo_binomial_logit_loglike_derivs(C.c_int64(n), C.c_int(p), _dp(X), C.c_int64(p), _dp(y), _dp(ntrials), _dp(beta),
+                                                C.c_double(log_alpha), _dp(g), _dp(h))
+    return ll, g, h
+
+
+def poisson_loglike_derivs(X, y, exposure, beta):
+    X, exposure, beta = _f64(X), _f64(exposure), _f64(beta)
+    y = np.ascontiguousarray(y, dtype=np.int64)
+    n, p = X.shape
+    g, h = np.empty(p), np.empty((p, p))
+    ll = lib().bo_poisson_loglike_derivs(C.c_int64(n), C.c_int(p), _dp(X), C.c_int64(p), y.ctypes.data_as(c_i64_p), _dp(exposure),
+                                         _dp(beta), _dp(g), _dp(h))
+    return ll, g, h
 
 
 # ---------------------------------------------------------------------------- synthetic data

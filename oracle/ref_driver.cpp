@@ -249,6 +249,17 @@ void golden_loglike(const std::string &dir) {
   Json j;
   j.num("n", n); j.num("p", p); j.arr("X", X); j.arr("y", y); j.arr("ntrials", nt); j.arr("beta", b);
   j.num("binomial_loglike", model->log_likelihood(b, nullptr, nullptr));
+  {
+    Vector g; Matrix h;
+    double ll = model->log_likelihood(b, &g, &h);
+    j.num("binomial_loglike_d", ll); j.arr("binomial_gradient", g);
+    std::vector<double> hh; for (int a = 0; a < p; ++a) for (int c = 0; c < p; ++c) hh.push_back(h(a, c));
+    j.arr("binomial_hessian", hh);
+    model->set_nonevent_sampling_prob(0.25);   // log_alpha = log(0.25): BinomialLogitModel.cpp:168
+    double ll2 = model->log_likelihood(b, &g, &h);
+    j.num("binomial_log_alpha", std::log(0.25)); j.num("binomial_loglike_alpha", ll2); j.arr("binomial_gradient_alpha", g);
+    model->set_nonevent_sampling_prob(1.0);
+  }
 
   std::vector<int64_t> yp(n); std::vector<double> ex(n), bp(p);
   bo_synth_beta(p, 2, 0.5, bp.data());
@@ -265,6 +276,13 @@ void golden_loglike(const std::string &dir) {
   Vector b2(p); for (int jj = 0; jj < p; ++jj) b2[jj] = bp[jj] * 0.9 - 0.02;
   j.arr("poisson_X", Xp); j.arr("poisson_y", yp); j.arr("poisson_exposure", ex); j.arr("poisson_beta", b2);
   j.num("poisson_loglike", pm->log_likelihood(b2, nullptr, nullptr));
+  {
+    Vector g; Matrix h;
+    double ll = pm->log_likelihood(b2, &g, &h);
+    j.num("poisson_loglike_d", ll); j.arr("poisson_gradient", g);
+    std::vector<double> hh; for (int a = 0; a < p; ++a) for (int c = 0; c < p; ++c) hh.push_back(h(a, c));
+    j.arr("poisson_hessian", hh);
+  }
 
   std::vector<std::string> rows;
   double ns[] = {1, 1, 2, 5, 12, 16, 30, 40, 100, 700};

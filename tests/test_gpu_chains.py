@@ -159,3 +159,54 @@ def test_data_added_after_construction_is_picked_up():
     model.sample_posterior()
     assert sampler.suf.sample_size == 500
     assert model.log_likelihood() == pytest.approx(O.binomial_logit_loglike(X, y, nt, model.Beta), rel=1e-12)
+
+
+def test_find_posterior_mode_matches_newton_on_oracle_derivatives():
+    """BinomialLogitSpikeSlabSampler::find_posterior_mode (.cpp:123-177): the mode of log slab + log likelihood over the
+    included coefficients; checked against Newton-Raphson in numpy on the oracle's gradient / Hessian."""
+    n, p = 4000, 9
+    X, y, nt, _ = O.synth_binomial(n, p, 4, seed=15, max_trials=3)
+    inc = np.array([1, 1, 0, 1, 1, 0, 0, 1, 0], dtype=bool)
+    mu = np.linspace(-0.1, 0.1, p)
+    A = np.random.default_rng(2).normal(size=(p, p)); siginv = A @ A.T / p + np.eye(p)
+    model = boom_b200.BinomialLogitModel(X, y, nt)
+    model.set_inc(list(inc))
+    sampler = boom_b200.BinomialLogitSpikeSlabSampler(model, boom_b200.MvnModel(mu, siginv, True),
+                                                      boom_b200.VariableSelectionPrior(p, 0.5), 10, boom_b200.RNG(1))
+    model.set_method(sampler)
+    sampler.find_posterior_mode(1e-8)
+    assert sampler.posterior_mode_found
+    idx = np.flatnonzero(inc)
+    b = np.zeros(len(idx))
+    P = siginv[np.ix_(idx, idx)]
+    for _ in range(50):
+        full = np.zeros(p); full[idx] = b
+        _, g, h = O.binomial_logit_loglike_derivs(X, y, nt, full)
+        grad = g[idx] - P @ (b - mu[idx])
+        step = np.linalg.solve(P - h[np.ix_(idx, idx)], grad)
+        b = b + step
+        if np.max(np.abs(step)) < 1e-13:
+            break
+    beta = np.array(model.Beta)
+    np.testing.assert_allclose(beta[idx], b, rtol=1e-7, atol=1e-9)
+    assert np.all(beta[~inc] == 0)
+    full = np.zeros(p); full[idx] = b
+    ll = O.binomial_logit_loglike(X, y, nt, full)
+    k = len(idx)
+    logprior = -0.5 * k * np.log(2 * np.pi) + 0.5 * np.linalg.slogdet(P)[1] - 0.5 * (b - mu[idx]) @ P @ (b - mu[idx])
+    assert sampler.log_posterior_at_mode == pytest.approx(ll + logprior, rel=1e-10)
+
+
+def test_poisson_find_posterior_mode_zero_gradient():
+    n, p = 3000, 6
+    X, y, ex, _ = O.synth_poisson(n, p, 3, seed=16)
+    boom_b200.load_poisson_mixture_table()
+    model = boom_b200.PoissonRegressionModel(X, y, ex)
+    sampler = boom_b200.PoissonRegressionSpikeSlabSampler(model, boom_b200.MvnModel(np.zeros(p), np.eye(p)),
+                                                          boom_b200.VariableSelectionPrior(p, 0.5), 1, boom_b200.RNG(1))
+    model.set_method(sampler)
+    sampler.find_posterior_mode(1e-9)
+    beta = np.array(model.Beta)
+    _, g, _ = O.poisson_loglike_derivs(X, y, ex, beta)
+    assert np.max(np.abs(g - beta)) < 1e-5 * n     # gradient of the log posterior: g - Siginv (beta - 0) = 0
+    assert np.isfinite(sampler.log_posterior_at_mode)

@@ -236,3 +236,46 @@ def test_small_p_variants_agree_with_oracle(n, p, kind):
         assert vec_err(xty, rxty) < 1e-10, ("variant", variant)
         np.testing.assert_array_equal(xtx, xtx.T)
         ctx.close()
+
+
+# ---------------------------------------------------------------- log likelihood with gradient and Hessian
+@pytest.mark.parametrize("n,p", [(3000, 6), (2500, 50), (2000, 130)])
+def test_loglike_derivatives_match_oracle(n, p):
+    X, y, nt, beta = O.synth_binomial(n, p, 3, seed=70 + p, max_trials=6)
+    ctx, _ = logit_ctx(X, y, nt)
+    for log_alpha in (0.0, np.log(0.3)):
+        ll, g, h = ctx.binomial_loglike_derivs(beta * 0.7, log_alpha)
+        rll, rg, rh = O.binomial_logit_loglike_derivs(X, y, nt, beta * 0.7, log_alpha)
+        assert ll == pytest.approx(rll, rel=1e-12)
+        assert vec_err(g, rg) < 1e-12
+        assert normwise_err(-h, -rh) < 1e-12
+    ctx.close()
+    Xp, yp, ex, bp = O.synth_poisson(n, p, 3, seed=80 + p)
+    ex = 0.5 + 0.1 * (np.arange(n) % 7)
+    ctx, _ = poisson_ctx(Xp, yp, ex)
+    ll, g, h = ctx.poisson_loglike_derivs(bp * 0.9)
+    rll, rg, rh = O.poisson_loglike_derivs(Xp, yp, ex, bp * 0.9)
+    assert ll == pytest.approx(rll, rel=1e-12)
+    assert vec_err(g, rg) < 1e-12
+    assert normwise_err(-h, -rh) < 1e-12
+    ctx.close()
+
+
+def test_loglike_derivatives_golden(golden):
+    g = golden("loglike.json")
+    n, p = int(g["n"]), int(g["p"])
+    ctx, _ = logit_ctx(np.array(g["X"]).reshape(n, p), g["y"], g["ntrials"])
+    ll, gr, h = ctx.binomial_loglike_derivs(g["beta"])
+    assert ll == pytest.approx(g["binomial_loglike_d"], rel=1e-12)
+    np.testing.assert_allclose(gr, g["binomial_gradient"], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(h, np.array(g["binomial_hessian"]).reshape(p, p), rtol=1e-11, atol=1e-11)
+    ll, gr, _ = ctx.binomial_loglike_derivs(g["beta"], g["binomial_log_alpha"])
+    assert ll == pytest.approx(g["binomial_loglike_alpha"], rel=1e-12)
+    np.testing.assert_allclose(gr, g["binomial_gradient_alpha"], rtol=1e-11, atol=1e-11)
+    ctx.close()
+    ctx, _ = poisson_ctx(np.array(g["poisson_X"]).reshape(n, p), g["poisson_y"], g["poisson_exposure"])
+    ll, gr, h = ctx.poisson_loglike_derivs(g["poisson_beta"])
+    assert ll == pytest.approx(g["poisson_loglike_d"], rel=1e-12)
+    np.testing.assert_allclose(gr, g["poisson_gradient"], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(h, np.array(g["poisson_hessian"]).reshape(p, p), rtol=1e-11, atol=1e-11)
+    ctx.close()

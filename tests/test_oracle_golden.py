@@ -158,3 +158,23 @@ def test_binomial_from_uniform_is_the_inverse_cdf():
         if keep.sum() > 1:
             chi2 = ((cnt[keep] - expect[keep]) ** 2 / expect[keep]).sum()
             assert chi2 < stats.chi2.ppf(1 - 1e-6, keep.sum())
+
+
+def test_loglike_derivatives_match_reference(golden):
+    """gradient / Hessian of the log likelihood as the reference computes them (incl. the log_alpha offset of
+    BinomialLogitModel.cpp:168 and the exposure-free Hessian weight of PoissonRegressionModel.cpp:84)."""
+    g = golden("loglike.json")
+    n, p = int(g["n"]), int(g["p"])
+    X = np.array(g["X"]).reshape(n, p)
+    ll, gr, h = O.binomial_logit_loglike_derivs(X, g["y"], g["ntrials"], g["beta"])
+    assert ll == pytest.approx(g["binomial_loglike_d"], rel=1e-13)
+    np.testing.assert_allclose(gr, g["binomial_gradient"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(h, np.array(g["binomial_hessian"]).reshape(p, p), rtol=1e-12, atol=1e-12)
+    ll, gr, _ = O.binomial_logit_loglike_derivs(X, g["y"], g["ntrials"], g["beta"], g["binomial_log_alpha"])
+    assert ll == pytest.approx(g["binomial_loglike_alpha"], rel=1e-13)
+    np.testing.assert_allclose(gr, g["binomial_gradient_alpha"], rtol=1e-12, atol=1e-12)
+    Xp = np.array(g["poisson_X"]).reshape(n, p)
+    ll, gr, h = O.poisson_loglike_derivs(Xp, g["poisson_y"], g["poisson_exposure"], g["poisson_beta"])
+    assert ll == pytest.approx(g["poisson_loglike_d"], rel=1e-13)
+    np.testing.assert_allclose(gr, g["poisson_gradient"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(h, np.array(g["poisson_hessian"]).reshape(p, p), rtol=1e-12, atol=1e-12)
