@@ -7,6 +7,7 @@
 // The binary lands in oracle/_ref/ (git-ignored, travels to the GPU box).
 // Synthetic data come from the oracle's bo_synth_* helpers so every arm sees
 // the same numbers; nothing else of the oracle is used here.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -298,6 +299,15 @@ void golden_loglike(const std::string &dir) {
 
 // ------------------------------------------------------------------------------------
 // Monte Carlo summaries of the reference's own imputers (their RNG, their algorithms).
+// 19 quantiles (5 %, ..., 95 %) of a sample, for two-sample chi-square tests on quantile bins
+std::string quantiles_json(std::vector<double> v) {
+  std::sort(v.begin(), v.end());
+  std::ostringstream o; o << std::setprecision(17) << "[";
+  for (int j = 1; j < 20; ++j) o << (j > 1 ? ", " : "") << v[(size_t)((double)j / 20.0 * (v.size() - 1))];
+  o << "]";
+  return o.str();
+}
+
 void golden_draw_stats(const std::string &dir) {
   const LogitMixtureApproximation &m(BinomialLogitDataImputer::mixture_approximation);
   RNG rng(424242);
@@ -307,10 +317,12 @@ void golden_draw_stats(const std::string &dir) {
   for (double eta : {-3.0, -1.0, 0.0, 0.5, 2.0}) {
     for (int y = 0; y < 2; ++y) {
       std::vector<double> kc(9, 0.0);
+      std::vector<double> zs; zs.reserve(N);
       double s1 = 0, s2 = 0, w1 = 0, w2 = 0;
       for (int i = 0; i < N; ++i) {
         std::pair<double, double> a = imputer.impute(rng, 1, y, eta);
         double info = a.second, z = a.first / info;
+        zs.push_back(z);
         kc[sigma_index(m.sigma(), 1.0 / info)] += 1;
         s1 += z; s2 += z * z; w1 += info; w2 += info * info;
       }
@@ -319,7 +331,7 @@ void golden_draw_stats(const std::string &dir) {
         << ", \"z_var\": " << s2 / N - (s1 / N) * (s1 / N) << ", \"info_mean\": " << w1 / N << ", \"info_var\": "
         << w2 / N - (w1 / N) * (w1 / N) << ", \"kcount\": [";
       for (int k = 0; k < 9; ++k) o << (k ? ", " : "") << kc[k];
-      o << "]}";
+      o << "], \"z_quantiles\": " << quantiles_json(zs) << "}";
       rows.push_back(o.str());
     }
   }
@@ -330,13 +342,18 @@ void golden_draw_stats(const std::string &dir) {
   const int N2 = 200000;
   for (C c : {C{25, 7, -0.8}, C{200, 150, 1.2}, C{12, 0, -2.0}, C{11, 11, 3.0}, C{1000, 480, -0.1}}) {
     double s1 = 0, s2 = 0, w1 = 0, w2 = 0;
+    std::vector<double> sums, infos;
     for (int i = 0; i < N2; ++i) {
       std::pair<double, double> a = imputer.impute(rng, c.n, c.y, c.eta);
       s1 += a.first; s2 += a.first * a.first; w1 += a.second; w2 += a.second * a.second;
+      sums.push_back(a.first); infos.push_back(a.second);
     }
-    rows.push_back(row_json({{"ntrials", c.n}, {"y", c.y}, {"eta", c.eta}, {"N", (double)N2}, {"sum_mean", s1 / N2},
-                             {"sum_var", s2 / N2 - (s1 / N2) * (s1 / N2)}, {"info_mean", w1 / N2},
-                             {"info_var", w2 / N2 - (w1 / N2) * (w1 / N2)}}));
+    std::string r = row_json({{"ntrials", c.n}, {"y", c.y}, {"eta", c.eta}, {"N", (double)N2}, {"sum_mean", s1 / N2},
+                              {"sum_var", s2 / N2 - (s1 / N2) * (s1 / N2)}, {"info_mean", w1 / N2},
+                              {"info_var", w2 / N2 - (w1 / N2) * (w1 / N2)}});
+    r.pop_back();
+    r += ", \"sum_quantiles\": " + quantiles_json(sums) + ", \"info_quantiles\": " + quantiles_json(infos) + "}";
+    rows.push_back(r);
   }
   write_file(dir + "/ref_logit_clt_stats.json", list_json(rows));
 
@@ -346,17 +363,24 @@ void golden_draw_stats(const std::string &dir) {
   for (P c : {P{0, 1.0, -1.0}, P{0, 2.5, 0.7}, P{1, 1.0, 0.0}, P{3, 1.0, 0.7}, P{3, 2.5, -1.0}, P{12, 1.0, 2.0},
               P{60, 2.5, 3.0}, P{150, 1.0, 5.0}}) {
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<double> zes, zis;
     for (int i = 0; i < N2; ++i) {
       double zi = 0, mi = 0, wi = 0, ze = 0, me = 0, we = 0;
       pimp.impute(rng, c.y, c.E, c.eta, &zi, &mi, &wi, &ze, &me, &we);
+      zes.push_back(ze); if (c.y > 0) zis.push_back(zi);
       acc[0] += ze; acc[1] += ze * ze; acc[2] += we; acc[3] += (ze - me) * we;
       if (c.y > 0) { acc[4] += zi; acc[5] += zi * zi; acc[6] += wi; acc[7] += (zi - mi) * wi; }
     }
     for (double &a : acc) a /= N2;
-    rows.push_back(row_json({{"y", (double)c.y}, {"exposure", c.E}, {"eta", c.eta}, {"N", (double)N2},
-                             {"zext_mean", acc[0]}, {"zext_var", acc[1] - acc[0] * acc[0]}, {"wext_mean", acc[2]},
-                             {"rwext_mean", acc[3]}, {"zint_mean", acc[4]}, {"zint_var", acc[5] - acc[4] * acc[4]},
-                             {"wint_mean", acc[6]}, {"rwint_mean", acc[7]}}));
+    std::string r = row_json({{"y", (double)c.y}, {"exposure", c.E}, {"eta", c.eta}, {"N", (double)N2},
+                              {"zext_mean", acc[0]}, {"zext_var", acc[1] - acc[0] * acc[0]}, {"wext_mean", acc[2]},
+                              {"rwext_mean", acc[3]}, {"zint_mean", acc[4]}, {"zint_var", acc[5] - acc[4] * acc[4]},
+                              {"wint_mean", acc[6]}, {"rwint_mean", acc[7]}});
+    r.pop_back();
+    r += ", \"zext_quantiles\": " + quantiles_json(zes);
+    if (c.y > 0) r += ", \"zint_quantiles\": " + quantiles_json(zis);
+    r += "}";
+    rows.push_back(r);
   }
   write_file(dir + "/ref_poisson_stats.json", list_json(rows));
 }
