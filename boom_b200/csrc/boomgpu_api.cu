@@ -44,7 +44,7 @@ struct boomgpu_ctx {
   // mixtures
   LogitMixture mix{};        // host copy
   LogitHot hot{};
-  LogitMixture *mix_dev = nullptr;
+  LogitMixtureDev *mix_dev = nullptr;
   bool have_mix = false;
   PoissonTable tab{};
   bool have_tab = false;
@@ -278,8 +278,8 @@ struct TmaLauncher {
     constexpr int NW = tma_warps(NB);
     const size_t smem = tma_smem_bytes(NB);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (int rc = ensure_xmap(ctx, ctx->xmap_small, tma_padw(NB), 32)) return rc;
-    const int64_t nslices = (d.n + 31) / 32;
+    if (int rc = ensure_xmap(ctx, ctx->xmap_small, tma_padw(NB), tma_slice_rows(NB))) return rc;
+    const int64_t nslices = (d.n + tma_slice_rows(NB) - 1) / tma_slice_rows(NB);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nslices + NW - 1) / NW, (int64_t)ctx->sms));
     if (ensure(ctx, &ctx->partials, &ctx->partials_cap, (int64_t)grid * tma_partial_len(NB))) return BOOMGPU_ERR_CUDA;
     {
@@ -728,9 +728,11 @@ int boomgpu_set_logit_mixture(boomgpu_ctx *ctx, int K, const double *mu, const d
     h.inv_sigsq[k] = m.inv_sigsq[k];
   }
   DeviceGuard g(ctx->device);
-  if (!ctx->mix_dev) CU(cudaMalloc((void **)&ctx->mix_dev, sizeof(LogitMixture)));
+  if (!ctx->mix_dev) CU(cudaMalloc((void **)&ctx->mix_dev, sizeof(LogitMixtureDev)));
   CU(cudaStreamSynchronize(ctx->stream));   // no step may still be reading the old mixture
-  CU(cudaMemcpy(ctx->mix_dev, &m, sizeof(LogitMixture), cudaMemcpyHostToDevice));
+  LogitMixtureDev both;
+  both.full = m; both.hot = h;
+  CU(cudaMemcpy(ctx->mix_dev, &both, sizeof(both), cudaMemcpyHostToDevice));
   ctx->have_mix = true;
   return 0;
 }

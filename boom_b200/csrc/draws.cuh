@@ -201,6 +201,75 @@ __device__ __forceinline__ double rtrun_logit(double eta, bool success, double u
   return log(u * __drcp_rn(1.0 - u)) + eta;
 }
 
+// ---- branch-free FP64 elementary functions for the Bernoulli fast path ------------------------------------------
+// libdevice's exp / log / reciprocal carry range checks that end basic blocks; with the argument ranges known
+// here they are unnecessary, and straight-line code lets the scheduler interleave the two observations a lane owns.
+
+// exp(x) for |x| <= 708: Cody-Waite reduction by ln 2, degree-13 Taylor polynomial on |r| <= ln2 / 2 (truncation
+// 4e-18), scaling by 2^k through the exponent field (the result is a normal number over the whole range).
+__device__ __forceinline__ double exp_nobranch(double x) {
+  const double kd = rint(x * 1.4426950408889634074);
+  double r = fma(kd, -6.93147180369123816490e-01, x);    // ln2_hi (fdlibm split)
+  r = fma(kd, -1.90821492927058770002e-10, r);           // ln2_lo
+  double p = 1.6059043836821613e-10;                     // 1/13!
+  p = fma(p, r, 2.08767569878680990e-09);                // 1/12!
+  p = fma(p, r, 2.50521083854417188e-08);                // 1/11!
+  p = fma(p, r, 2.75573192239858907e-07);                // 1/10!
+  p = fma(p, r, 2.75573192239858907e-06);                // 1/9!
+  p = fma(p, r, 2.48015873015873016e-05);                // 1/8!
+  p = fma(p, r, 1.98412698412698413e-04);                // 1/7!
+  p = fma(p, r, 1.38888888888888894e-03);                // 1/6!
+  p = fma(p, r, 8.33333333333333322e-03);                // 1/5!
+  p = fma(p, r, 4.16666666666666644e-02);                // 1/4!
+  p = fma(p, r, 1.66666666666666657e-01);                // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int k = (int)kd;
+  return __hiloint2double(__double2hiint(p) + k * 1048576, __double2loint(p));
+}
+
+// 1 / d for a positive normal d away from the exponent limits: MUFU seed + two Newton steps (<= 1 ulp)
+__device__ __forceinline__ double rcp_nobranch(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
+
+// log(v) for a positive normal v: fdlibm e_log.c (m in [sqrt(1/2), sqrt 2), s = f / (2 + f), Lg1..Lg7), < 1 ulp
+__device__ __forceinline__ double log_nobranch(double v) {
+  int hi = __double2hiint(v);
+  const int lo = __double2loint(v);
+  int e = (hi >> 20) - 1023;
+  hi &= 0x000fffff;
+  const int adj = (hi + 0x95f64) & 0x100000;   // mantissa above sqrt 2: halve it, bump the exponent
+  e += adj >> 20;
+  const double m = __hiloint2double(hi | (adj ^ 0x3ff00000), lo);
+  const double f = m - 1.0;
+  const double s = f * rcp_nobranch(2.0 + f);
+  const double z = s * s, w = z * z;
+  const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+  const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
+                            6.666666666666735130e-01);
+  const double R = t1 + t2, hfsq = 0.5 * f * f, dk = (double)e;
+  return fma(dk, 6.93147180369123816490e-01, f - (hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)));
+}
+
+// rtrun_logit for |eta| < 600, algebraically: with E = exp(eta), c = 1 / (1 + E),
+//   success: u = c + (1 - c) U,  u / (1 - u) = (1 + E U) / (E (1 - U))   =>  z = log((1 + E U) / (1 - U))
+//   failure: u = c U,            u / (1 - u) = U / (1 + E - U)           =>  z = eta + log(U / (1 + E - U))
+// one exp, one reciprocal, one log (trun_logit.cpp:163-174 evaluates three quotients); U in (0, 1) strictly.
+__device__ __forceinline__ double rtrun_logit_fast(double eta, bool success, double unif) {
+  const double E = exp_nobranch(eta);
+  const double num = success ? fma(E, unif, 1.0) : unif;
+  const double den = success ? 1.0 - unif : (1.0 + E) - unif;
+  const double lg = log_nobranch(num * rcp_nobranch(den));
+  return success ? lg : lg + eta;
+}
+
 // log(1 - Phi(a)) and the hazard phi(a) / (1 - Phi(a)) through erfcx (stable in both tails)
 __device__ __forceinline__ double normal_hazard(double a) {
   return 0.7978845608028654 / erfcx(a * 0.7071067811865476);  // sqrt(2/pi) / erfcx(a / sqrt 2)
@@ -316,28 +385,96 @@ __device__ __noinline__ void logit_impute_large(const LogitMixture *__restrict__
   info = w;
 }
 
+// What lives in global memory for the out-of-line paths: the FP64 mixture and a copy of the hot-loop constants.
+struct LogitMixtureDev { LogitMixture full; LogitHot hot; };
+
+// One trial: truncated-logistic draw + indicator.  Shared by the Bernoulli fast path (h in the constant bank) and
+// the general path (h in global memory).
+__device__ __forceinline__ void logit_trial(const LogitHot &h, const LogitMixture *__restrict__ m, double eta, bool success,
+                                            double u0, double u1, double &sum, double &info) {
+  const double z = rtrun_logit(eta, success, u0);
+  const int k = unmix_logit(h, m, z - eta, u1);
+  const double cw = h.inv_sigsq[k];
+  info += cw;
+  sum += z * cw;
+}
+
+// Everything that is not a Bernoulli observation: validation, the per-trial loop for 1 < n_i <= clt_threshold
+// (BinomialLogitDataImputer.cpp:134-152), the CLT branch (:155-210).  Out of line so that the Bernoulli path keeps
+// its registers; reads the mixture from global memory.
+__device__ __noinline__ bool logit_impute_general(const LogitMixtureDev *__restrict__ md, int clt_threshold, double ntrials, double y,
+                                                  double eta, uint64_t seed, uint64_t iteration, uint64_t row, double *sum_out,
+                                                  double *info_out) {
+  double sum = 0, info = 0;
+  *sum_out = 0; *info_out = 0;
+  if (!(y <= ntrials) || y < 0 || ntrials < 0 || !isfinite(eta)) return false;
+  RngKey key;
+  key.seed = seed; key.iteration = iteration;
+  if (ntrials > (double)clt_threshold) {
+    if (md->full.K > 9) return false;  // slot layout of the CLT branch: K - 1 <= 8 conditional binomials per side
+    logit_impute_large(&md->full, ntrials, y, eta, key, row, sum, info);
+  } else {
+    const int nt = (int)ceil(ntrials), ns = (int)ceil(y);   // i < ntrials, i < y for integer i (the reference's loop bounds are doubles)
+    for (int i = 0; i < nt; ++i) {
+      double u0, u1;
+      uniform_pair(key, row, (uint32_t)i, u0, u1);
+      logit_trial(md->hot, &md->full, eta, i < ns, u0, u1, sum, info);
+    }
+  }
+  *sum_out = sum; *info_out = info;
+  return true;
+}
+
+// the Bernoulli fast path applies: one trial, a 0/1 response, |eta| < 600 (so that nothing in it can overflow)
+__device__ __forceinline__ bool logit_is_bernoulli_fast(double ntrials, double y, double eta) {
+  return ntrials == 1.0 && (y == 0.0 || y == 1.0) && fabs(eta) < 600.0;
+}
+
+// R Bernoulli observations of one lane, written operation by operation across the R so that each stage is R
+// independent instruction streams in ONE basic block (the scheduler interleaves them: ILP R on the dependent FP64
+// chains of exp / reciprocal / log).  The FP64 fallbacks of the certified selection come after the straight-line part.
+template <int R>
+__device__ __forceinline__ void logit_bernoulli_draws(const LogitHot &h, const LogitMixtureDev *__restrict__ md, const double (&eta)[R],
+                                                      const double (&y)[R], const RngKey &key, const uint64_t (&row)[R],
+                                                      double (&sum)[R], double (&info)[R]) {
+  double u0[R], u1[R], z[R];
+  int k[R];
+  bool ok[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) uniform_pair(key, row[j], 0u, u0[j], u1[j]);
+#pragma unroll
+  for (int j = 0; j < R; ++j) z[j] = rtrun_logit_fast(eta[j], y[j] != 0.0, u0[j]);
+  auto mu_of = [&](int s) { return h.mu_c[s]; };
+  auto lc_of = [&](int s) { return h.lconst2[s]; };
+  auto hs_of = [&](int s) { return h.hs2[s]; };
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const float r_c = (float)((z[j] - eta[j]) - h.center);
+    if (h.K == 9) ok[j] = unmix_certified<9>(9, r_c, u1[j], mu_of, lc_of, hs_of, k[j]);
+    else ok[j] = unmix_certified<kMaxLogitK>(h.K, r_c, u1[j], mu_of, lc_of, hs_of, k[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    if (!ok[j]) k[j] = unmix_logit_fp64(&md->full, z[j] - eta[j], u1[j]);
+    info[j] = h.inv_sigsq[k[j]];
+    sum[j] = z[j] * info[j];
+  }
+}
+
 // BinomialLogitCltDataImputer::impute.  Returns false on invalid input (y > n, negative, NaN eta).
-__device__ __forceinline__ bool logit_impute(const LogitHot &h, const LogitMixture *__restrict__ m, int clt_threshold,
+__device__ __forceinline__ bool logit_impute(const LogitHot &h, const LogitMixtureDev *__restrict__ md, int clt_threshold,
                                              double ntrials, double y, double eta, const RngKey &key, uint64_t row,
                                              double &sum, double &info) {
-  sum = 0; info = 0;
-  if (!(y <= ntrials) || y < 0 || ntrials < 0 || !isfinite(eta)) return false;
-  if (ntrials > (double)clt_threshold) {
-    if (h.K > 9) return false;  // slot layout of the CLT branch: K - 1 <= 8 conditional binomials per side
-    logit_impute_large(m, ntrials, y, eta, key, row, sum, info);
+  if (logit_is_bernoulli_fast(ntrials, y, eta)) {   // Bernoulli: one trial, straight line
+    double u0, u1;
+    uniform_pair(key, row, 0u, u0, u1);
+    const double z = rtrun_logit_fast(eta, y != 0.0, u0);
+    const int k = unmix_logit(h, &md->full, z - eta, u1);
+    info = h.inv_sigsq[k];
+    sum = z * info;
     return true;
   }
-  const int nt = (int)ceil(ntrials), ns = (int)ceil(y);   // i < ntrials, i < y for integer i (the reference's loop bounds are doubles)
-  for (int i = 0; i < nt; ++i) {
-    double u0, u1;
-    uniform_pair(key, row, (uint32_t)i, u0, u1);
-    double z = rtrun_logit(eta, i < ns, u0);
-    int k = unmix_logit(h, m, z - eta, u1);
-    double cw = h.inv_sigsq[k];
-    info += cw;
-    sum += z * cw;
-  }
-  return true;
+  return logit_impute_general(md, clt_threshold, ntrials, y, eta, key.seed, key.iteration, row, &sum, &info);
 }
 
 // ---- Poisson --------------------------------------------------------------------------

@@ -24,18 +24,26 @@
 
 namespace boomgpu {
 
-// warps / ring depth per NB: a slice is 32 * (8 NB + 4) * 8 bytes = 2048 NB + 1024
-// (tuning knobs for the smallest tiles: -DBOOMGPU_TMA_NW_SMALL=.. -DBOOMGPU_TMA_S_SMALL=..)
+// Tile shape per NB.  A slice is 32 RPL consecutive observations x (8 NB + 4) doubles; lane r owns the RPL observations
+// r, r + 32, ... of the slice.  Measured at p = 16 / 25 M rows: (12 warps, RPL 1) 0.893 ms = (8 warps, RPL 2) 0.894 ms:
+// the shared FP64 / DMMA pipe (48 % busy) and the issue slots (45 %) bound it, not latency, so RPL stays 1 (finer slices
+// balance short data sets better).
+// (tuning knobs for the narrow tiles: -DBOOMGPU_TMA_NW_SMALL=.. -DBOOMGPU_TMA_S_SMALL=.. -DBOOMGPU_TMA_RPL_SMALL=..)
 #ifndef BOOMGPU_TMA_NW_SMALL
 #define BOOMGPU_TMA_NW_SMALL 12
 #endif
 #ifndef BOOMGPU_TMA_S_SMALL
-#define BOOMGPU_TMA_S_SMALL 3
+#define BOOMGPU_TMA_S_SMALL 2
 #endif
+#ifndef BOOMGPU_TMA_RPL_SMALL
+#define BOOMGPU_TMA_RPL_SMALL 1
+#endif
+__host__ __device__ constexpr int tma_rpl(int nb) { return nb <= 2 ? BOOMGPU_TMA_RPL_SMALL : 1; }
 __host__ __device__ constexpr int tma_warps(int nb) { return nb <= 2 ? BOOMGPU_TMA_NW_SMALL : (nb == 3 ? 12 : (nb == 4 ? 10 : 6)); }
 __host__ __device__ constexpr int tma_stages(int nb) { return nb <= 2 ? BOOMGPU_TMA_S_SMALL : 2; }
 __host__ __device__ constexpr int tma_padw(int nb) { return 8 * nb + 4; }
-__host__ __device__ constexpr int tma_slice_doubles(int nb) { return 32 * tma_padw(nb); }
+__host__ __device__ constexpr int tma_slice_rows(int nb) { return 32 * tma_rpl(nb); }
+__host__ __device__ constexpr int tma_slice_doubles(int nb) { return tma_slice_rows(nb) * tma_padw(nb); }
 __host__ __device__ constexpr size_t tma_smem_bytes(int nb) {
   return sizeof(double) * ((size_t)tma_warps(nb) * tma_stages(nb) * tma_slice_doubles(nb) + 8 * nb + 64) +
          sizeof(uint64_t) * tma_warps(nb) * tma_stages(nb) + 128;
@@ -48,6 +56,8 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
                  double *__restrict__ partials, int *err) {
   constexpr int NW = tma_warps(NB);
   constexpr int S = tma_stages(NB);
+  constexpr int RPL = tma_rpl(NB);
+  constexpr int ROWS = 32 * RPL;
   constexpr int PADW = tma_padw(NB);
   constexpr int SLICE = tma_slice_doubles(NB);
   constexpr int P8 = 8 * NB;
@@ -68,8 +78,8 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
   }
   __syncthreads();
 
-  // slices of 32 rows are dealt to (CTA, warp): the k-th slice of this warp is ((blockIdx + k grid) NW + wid)
-  const int64_t nslices = (d.n + 31) >> 5;
+  // slices of ROWS rows are dealt to (CTA, warp): the k-th slice of this warp is ((blockIdx + k grid) NW + wid)
+  const int64_t nslices = (d.n + ROWS - 1) / ROWS;
   const int64_t stride = (int64_t)gridDim.x * NW;
   const int64_t first = (int64_t)blockIdx.x * NW + wid;
   double *my_ring = ring + (size_t)wid * S * SLICE;
@@ -81,7 +91,7 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
       const int64_t q = first + s * stride;
       if (q < nslices) {
         mbar_expect_tx(my_bars + s, kSliceBytes);
-        tma_load_2d(my_ring + s * SLICE, &xmap, 0, (int)(q << 5), my_bars + s);
+        tma_load_2d(my_ring + s * SLICE, &xmap, 0, (int)(q * ROWS), my_bars + s);
       }
     }
   }
@@ -99,46 +109,93 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
   uint32_t phase = 0;
   // y_i / n_i (or exposure, or supplied latents) are fetched one slice ahead: a global load per lane whose latency
   // the previous slice's arithmetic covers
-  RowObs obs_next;
-  obs_next.y = 0; obs_next.aux = 0; obs_next.yi = 0;
-  if (first < nslices && (first << 5) + lane < d.n) obs_next = load_obs<MODEL>(d, (first << 5) + lane);
+  RowObs obs_next[RPL];
+#pragma unroll
+  for (int j = 0; j < RPL; ++j) {
+    obs_next[j].y = 0; obs_next[j].aux = 0; obs_next[j].yi = 0;
+    const int64_t i0 = first * ROWS + 32 * j + lane;
+    if (first < nslices && i0 < d.n) obs_next[j] = load_obs<MODEL>(d, i0);
+  }
   for (int64_t q = first; q < nslices; q += stride) {
-    const int64_t i = (q << 5) + lane;
-    const bool valid = i < d.n;
-    const RowObs obs = obs_next;
-    {
-      const int64_t in = ((q + stride) << 5) + lane;
-      if (in < d.n) obs_next = load_obs<MODEL>(d, in);
+    int64_t i[RPL];
+    bool valid[RPL];
+    RowObs obs[RPL];
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) {
+      i[j] = q * ROWS + 32 * j + lane;
+      valid[j] = i[j] < d.n;
+      obs[j] = obs_next[j];
+      const int64_t in = (q + stride) * ROWS + 32 * j + lane;
+      if (in < d.n) obs_next[j] = load_obs<MODEL>(d, in);
     }
     mbar_wait(my_bars + slot, phase);
     double *xs = my_ring + slot * SLICE;
 
-    // ---- lane r: eta of observation r, then its latent draw
-    double wv = 0, sv = 0;
+    // ---- lane r: eta of its RPL observations, then their latent draws
+    double eta[RPL];
     {
-      const double *xr = xs + lane * PADW;
-      double e0 = 0, e1 = 0;
+      double e0[RPL], e1[RPL];
 #pragma unroll
-      for (int j = 0; j < P8; j += 2) {
-        int j0 = j + rot, j1 = j + 1 + rot;
+      for (int j = 0; j < RPL; ++j) { e0[j] = 0; e1[j] = 0; }
+#pragma unroll
+      for (int col = 0; col < P8; col += 2) {
+        int j0 = col + rot, j1 = col + 1 + rot;
         j0 = j0 >= P8 ? j0 - P8 : j0;
         j1 = j1 >= P8 ? j1 - P8 : j1;
-        e0 = fma(xr[j0], beta_s[j0], e0);
-        e1 = fma(xr[j1], beta_s[j1], e1);
+        const double b0 = beta_s[j0], b1 = beta_s[j1];
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+          const double *xr = xs + (32 * j + lane) * PADW;
+          e0[j] = fma(xr[j0], b0, e0[j]);
+          e1[j] = fma(xr[j1], b1, e1[j]);
+        }
       }
-      if (valid) {
-        RowLatent r = impute_row<MODEL>(d, prm, out, obs, i, e0 + e1, err);
-        wv = r.w; sv = r.s;
-        sc_count += r.count; sc_ywy += r.yWy; sc_sumw += r.w; sc_sumlogw += r.sumlogw;
-      }
-      // (w_r, s_r) go to the two pad columns of row r: the k-steps below read them back with one 16-byte load
-      *reinterpret_cast<double2 *>(xs + lane * PADW + P8) = make_double2(wv, sv);
+#pragma unroll
+      for (int j = 0; j < RPL; ++j) eta[j] = e0[j] + e1[j];
     }
+    double wv[RPL], sv[RPL];
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) { wv[j] = 0; sv[j] = 0; }
+    bool done = false;
+    if (MODEL == kLogit && RPL > 1) {
+      // all of this warp's observations are Bernoulli with a moderate eta: RPL straight-line draws per lane, interleaved
+      bool fast = true;
+#pragma unroll
+      for (int j = 0; j < RPL; ++j) fast = fast && valid[j] && logit_is_bernoulli_fast(obs[j].aux, obs[j].y, eta[j]);
+      if (__all_sync(0xffffffffu, fast)) {
+        uint64_t rows[RPL];
+        double ys[RPL];
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) { rows[j] = d.row_offset + (uint64_t)i[j]; ys[j] = obs[j].y; }
+        logit_bernoulli_draws<RPL>(prm.hot, prm.mix, eta, ys, prm.key, rows, sv, wv);
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+          sc_count += 1.0; sc_sumw += wv[j];
+          if (out.w) out.w[i[j]] = wv[j];
+          if (out.s) out.s[i[j]] = sv[j];
+        }
+        done = true;
+      }
+    }
+    if (!done) {
+#pragma unroll
+      for (int j = 0; j < RPL; ++j) {
+        if (valid[j]) {
+          RowLatent r = impute_row<MODEL>(d, prm, out, obs[j], i[j], eta[j], err);
+          wv[j] = r.w; sv[j] = r.s;
+          sc_count += r.count; sc_ywy += r.yWy; sc_sumw += r.w; sc_sumlogw += r.sumlogw;
+        }
+      }
+    }
+    // (w_r, s_r) go to the two pad columns of row r: the k-steps below read them back with one 16-byte load
+#pragma unroll
+    for (int j = 0; j < RPL; ++j)
+      *reinterpret_cast<double2 *>(xs + (32 * j + lane) * PADW + P8) = make_double2(wv[j], sv[j]);
     __syncwarp();
 
-    // ---- the warp's 32 rank-1 updates: 8 DMMA k-steps of 4 rows
+    // ---- the warp's rank-1 updates: DMMA k-steps of 4 rows
 #pragma unroll 2
-    for (int kk = 0; kk < 8; ++kk) {
+    for (int kk = 0; kk < ROWS / 4; ++kk) {
       const int row = kk * 4 + (lane & 3);
       const double2 ws = *reinterpret_cast<const double2 *>(xs + row * PADW + P8);
       const double wk = ws.x, sk = ws.y;
@@ -165,7 +222,7 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
       const int64_t qn = q + (int64_t)S * stride;
       if (qn < nslices) {
         mbar_expect_tx(my_bars + slot, kSliceBytes);
-        tma_load_2d(my_ring + slot * SLICE, &xmap, 0, (int)(qn << 5), my_bars + slot);
+        tma_load_2d(my_ring + slot * SLICE, &xmap, 0, (int)(qn * ROWS), my_bars + slot);
       }
     }
     if (++slot == S) { slot = 0; phase ^= 1; }

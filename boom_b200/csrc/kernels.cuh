@@ -49,7 +49,7 @@ struct RowOut {           // optional per-row outputs (test hooks); any may be n
 
 struct DrawParams {
   LogitHot hot;             // constant bank
-  const LogitMixture *mix;  // global memory (FP64 fallback of the selection, CLT branch)
+  const LogitMixtureDev *mix;  // global memory (FP64 fallback of the selection, general / CLT path)
   PoissonTable tab;
   RngKey key;
   int clt_threshold;
