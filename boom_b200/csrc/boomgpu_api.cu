@@ -44,6 +44,7 @@ struct boomgpu_ctx {
   // mixtures
   LogitMixture mix{};        // host copy
   LogitHot hot{};
+  LogitHot ext_hot{};   // Poisson table entry nu = 1
   LogitMixtureDev *mix_dev = nullptr;
   bool have_mix = false;
   PoissonTable tab{};
@@ -491,6 +492,7 @@ int finish_and_check(boomgpu_ctx *ctx) {
 DrawParams make_prm(boomgpu_ctx *ctx, int clt, uint64_t seed, uint64_t iteration) {
   DrawParams prm;
   prm.hot = ctx->hot;
+  prm.ext = ctx->ext_hot;
   prm.mix = ctx->mix_dev;
   prm.tab = ctx->tab;
   prm.key.seed = seed;
@@ -726,6 +728,8 @@ int boomgpu_set_logit_mixture(boomgpu_ctx *ctx, int K, const double *mu, const d
     h.hs2[k] = (float)(-0.5 * 1.4426950408889634 * m.inv_sigsq[k]);
     h.mu_c[k] = (float)(m.mu[k] - h.center);
     h.inv_sigsq[k] = m.inv_sigsq[k];
+    h.mu_d[k] = m.mu[k];
+    h.logw[k] = std::log(m.inv_sigsq[k]);
   }
   DeviceGuard g(ctx->device);
   if (!ctx->mix_dev) CU(cudaMalloc((void **)&ctx->mix_dev, sizeof(LogitMixtureDev)));
@@ -752,12 +756,28 @@ int boomgpu_set_poisson_table(boomgpu_ctx *ctx, int ntab, const int64_t *nu, con
   const int total = offset[ntab];
   std::vector<double> inv_sigma(total), lconst(total);
   std::vector<float> mu_f(total), lconst2_f(total), hs2_f(total);
+  std::vector<double> inv_sigsq(total), logw(total);
   for (int i = 0; i < total; ++i) {
     if (!(sigma[i] > 0) || !(weights[i] > 0)) return fail(ctx, BOOMGPU_ERR_ARG, "table sigma and weights must be positive");
     inv_sigma[i] = 1.0 / sigma[i];
     lconst[i] = std::log(weights[i]) - kLnSqrt2Pi - std::log(sigma[i]);
     lconst2_f[i] = (float)(lconst[i] * 1.4426950408889634);
     hs2_f[i] = (float)(-0.5 * 1.4426950408889634 * inv_sigma[i] * inv_sigma[i]);
+    inv_sigsq[i] = 1.0 / (sigma[i] * sigma[i]);
+    logw[i] = std::log(inv_sigsq[i]);
+  }
+  // dense index for the small counts, and the nu = 1 entry in kernel-parameter form
+  const int dense_n = (int)std::min<int64_t>(nu[ntab - 1] + 1, 1 << 16);
+  std::vector<int32_t> dense((size_t)std::max(dense_n, 1), -1);
+  for (int e = ntab - 1; e >= 0; --e) if (nu[e] >= 0 && nu[e] < dense_n) dense[(size_t)nu[e]] = e;   // first of duplicates wins
+  LogitHot &xh = ctx->ext_hot;
+  memset(&xh, 0, sizeof(xh));
+  xh.K = offset[e1 + 1] - offset[e1];
+  xh.center = mu[offset[e1]];
+  for (int k = 0; k < xh.K; ++k) {
+    const int i = offset[e1] + k;
+    xh.lconst2[k] = lconst2_f[i]; xh.hs2[k] = hs2_f[i]; xh.mu_c[k] = (float)(mu[i] - xh.center);
+    xh.inv_sigsq[k] = inv_sigsq[i]; xh.mu_d[k] = mu[i]; xh.logw[k] = logw[i];
   }
   for (int e = 0; e < ntab; ++e)
     for (int i = offset[e]; i < offset[e + 1]; ++i) mu_f[i] = (float)(mu[i] - mu[offset[e]]);
@@ -782,6 +802,10 @@ int boomgpu_set_poisson_table(boomgpu_ctx *ctx, int ntab, const int64_t *nu, con
   CU(up(mu_f.data(), sizeof(float) * total, (void **)&t.mu_f));
   CU(up(lconst2_f.data(), sizeof(float) * total, (void **)&t.lconst2_f));
   CU(up(hs2_f.data(), sizeof(float) * total, (void **)&t.hs2_f));
+  CU(up(inv_sigsq.data(), sizeof(double) * total, (void **)&t.inv_sigsq));
+  CU(up(logw.data(), sizeof(double) * total, (void **)&t.logw));
+  CU(up(dense.data(), sizeof(int32_t) * dense.size(), (void **)&t.dense));
+  t.dense_n = dense_n;
   ctx->have_tab = true;
   return 0;
 }

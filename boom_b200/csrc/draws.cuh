@@ -74,6 +74,8 @@ struct LogitHot {
   float mu_c[kMaxLogitK];        // mu[k] - center
   double center;                 // = mu[0]: residuals are centred in FP64 before they are rounded to FP32
   double inv_sigsq[kMaxLogitK];
+  double mu_d[kMaxLogitK];       // FP64 component means and log(1 / sigma^2): what the Poisson statistics add per draw
+  double logw[kMaxLogitK];
 };
 
 // Poisson table in global memory (per-row nu makes the lookups divergent).
@@ -88,6 +90,10 @@ struct PoissonTable {
   const float *mu_f;       // single-precision copies for the certified selection: mu[k] - mu[first component of the entry]
   const float *lconst2_f;
   const float *hs2_f;
+  const double *inv_sigsq;  // 1 / sigma^2 and its log, per component
+  const double *logw;
+  const int32_t *dense;     // dense[nu] = entry index (or -1) for nu < dense_n: no search for the common small counts
+  int dense_n;
   int64_t gaussian_cutoff;
   int e1;  // entry index of nu == 1 (every row uses it)
 };
@@ -132,13 +138,15 @@ __device__ __forceinline__ int unmix_generic(int K, double unif, F lp_of) {
 constexpr float kUnmixMargin = 4e-5f;
 
 // r_c: residual minus the mixture's centre, rounded to FP32 by the caller; mu_of(s) is relative to the same centre.
+// KMAX: compile-time bound on K (K == KMAX exactly unless KMAX is one of the open-ended sizes 4 and kMaxLogitK)
 template <int KMAX, class FMU, class FL, class FH>
 __device__ __forceinline__ bool unmix_certified(int K, float r_c, double unif, FMU mu_of, FL lconst2_of, FH hs2_of, int &kout) {
+  constexpr bool kOpen = (KMAX == kMaxLogitK || KMAX == 4);
   float q[KMAX];
   float mx = -3.0e38f;
 #pragma unroll
   for (int s = 0; s < KMAX; ++s) {
-    if (KMAX == kMaxLogitK && s >= K) { q[s] = -3.0e38f; continue; }
+    if (kOpen && s >= K) { q[s] = -3.0e38f; continue; }
     const float dlt = r_c - mu_of(s);
     q[s] = fmaf(hs2_of(s), dlt * dlt, lconst2_of(s));
     mx = fmaxf(mx, q[s]);
@@ -155,7 +163,7 @@ __device__ __forceinline__ bool unmix_certified(int K, float r_c, double unif, F
   bool found = false;
 #pragma unroll
   for (int s = 0; s < KMAX - 1; ++s) {
-    if (KMAX == kMaxLogitK && s >= K - 1) break;
+    if (kOpen && s >= K - 1) break;
     cs += q[s];
     const float dd = v - cs;
     margin = fminf(margin, fabsf(dd));
@@ -479,6 +487,7 @@ __device__ __forceinline__ bool logit_impute(const LogitHot &h, const LogitMixtu
 
 // ---- Poisson --------------------------------------------------------------------------
 __device__ __forceinline__ int poisson_table_find(const PoissonTable &t, int64_t nu) {
+  if (nu < (int64_t)t.dense_n) return nu >= 0 ? __ldg(t.dense + nu) : -1;
   int lo = 0, hi = t.ntab - 1;
   while (lo <= hi) {
     int mid = (lo + hi) >> 1;
@@ -492,8 +501,9 @@ __device__ __forceinline__ int poisson_table_find(const PoissonTable &t, int64_t
   return -1;
 }
 
+// unmix against table entry `entry` (global memory); logw = log(1 / sigma_k^2)
 __device__ __forceinline__ bool unmix_poisson(const PoissonTable &t, int entry, double resid, double unif,
-                                              double &mu, double &weight, int &kout) {
+                                              double &mu, double &weight, double &logw, int &kout) {
   if (entry < 0) return false;
   int a = __ldg(t.offset + entry), K = __ldg(t.offset + entry + 1) - a;
   if (K > kMaxLogitK) return false;
@@ -504,49 +514,85 @@ __device__ __forceinline__ bool unmix_poisson(const PoissonTable &t, int entry, 
   bool ok;
   const float r_c = (float)(resid - __ldg(t.mu + a));
   if (K == 10) ok = unmix_certified<10>(10, r_c, unif, mu_of, lc_of, hs_of, k);
+  else if (K <= 4) ok = unmix_certified<4>(K, r_c, unif, mu_of, lc_of, hs_of, k);
   else ok = unmix_certified<kMaxLogitK>(K, r_c, unif, mu_of, lc_of, hs_of, k);
   if (!ok) k = unmix_table_fp64(t.mu + a, t.inv_sigma + a, t.lconst + a, K, resid, unif);
   mu = __ldg(t.mu + a + k);
-  double sg = __ldg(t.sigma + a + k);
-  weight = 1.0 / (sg * sg);
+  weight = __ldg(t.inv_sigsq + a + k);
+  logw = __ldg(t.logw + a + k);
   kout = k;
   return true;
 }
 
-struct PoissonLatent { double z_int, mu_int, w_int, z_ext, mu_ext, w_ext; int k_int, k_ext; };
+// the nu = 1 entry (every observation draws from it) from the constant bank
+__device__ __forceinline__ void unmix_poisson_ext(const LogitHot &h, const PoissonTable &t, double resid, double unif,
+                                                  double &mu, double &weight, double &logw, int &kout) {
+  int k;
+  bool ok;
+  auto mu_of = [&](int s) { return h.mu_c[s]; };
+  auto lc_of = [&](int s) { return h.lconst2[s]; };
+  auto hs_of = [&](int s) { return h.hs2[s]; };
+  const float r_c = (float)(resid - h.center);
+  if (h.K == 10) ok = unmix_certified<10>(10, r_c, unif, mu_of, lc_of, hs_of, k);
+  else ok = unmix_certified<kMaxLogitK>(h.K, r_c, unif, mu_of, lc_of, hs_of, k);
+  if (!ok) {
+    const int a = __ldg(t.offset + t.e1);
+    k = unmix_table_fp64(t.mu + a, t.inv_sigma + a, t.lconst + a, h.K, resid, unif);
+  }
+  mu = h.mu_d[k]; weight = h.inv_sigsq[k]; logw = h.logw[k]; kout = k;
+}
+
+struct PoissonLatent { double z_int, mu_int, w_int, z_ext, mu_ext, w_ext, lw_int, lw_ext; int k_int, k_ext; };
+
+// The extreme-eta statement of PoissonDataImputer::impute (PoissonDataImputer.cpp:55-79), out of line.
+__device__ __noinline__ double poisson_zext_extreme(double eta, double delta, double e1) {
+  if (delta > 0) {
+    double err = -log(e1);
+    double a = log(delta), b = -err - eta;
+    if (a < b) { double tmp = a; a = b; b = tmp; }
+    return -(a + log1p(exp(b - a)));
+  }
+  return eta + (-log(e1));
+}
 
 // PoissonDataImputer::impute.  rc: 0 ok, 1 nu missing from the table, 2 invalid input.
-__device__ __forceinline__ int poisson_impute(const PoissonTable &t, int64_t y, double exposure, double eta,
+//   tau = E * Beta(y, 1) = E * U^(1/y) = E * exp(log U / y);   z_int = -log tau = -(log E + log U / y)
+//   z_ext = -log(delta + Exp(1) / exp(eta)),  delta = E - tau
+// For exposures and eta in the ordinary range every elementary function is the branch-free kind of the logit path.
+__device__ __forceinline__ int poisson_impute(const LogitHot &ext, const PoissonTable &t, int64_t y, double exposure, double eta,
                                               const RngKey &key, uint64_t row, PoissonLatent &o) {
-  o.z_int = o.mu_int = o.w_int = 0; o.k_int = o.k_ext = -1;
+  o.z_int = o.mu_int = o.w_int = o.lw_int = 0; o.k_int = o.k_ext = -1;
   if (y < 0 || !(exposure >= 0) || !isfinite(eta)) return 2;
   double ua0, ua1, ub0, ub1;
   uniform_pair(key, row, 0, ua0, ua1);
   uniform_pair(key, row, 1, ub0, ub1);
-  double tau = y > 0 ? exposure * pow(ua0, 1.0 / (double)y) : 0.0;  // Beta(y, 1) by inversion
-  double delta = exposure - tau;
-  double e1 = -log(ua1);
-  double z_ext;
-  if (fabs(eta) < 600) {
-    z_ext = -log(delta + (1.0 / exp(eta)) * e1);
-  } else if (delta > 0) {
-    double err = -log(e1);
-    double a = log(delta), b = -err - eta;
-    if (a < b) { double tmp = a; a = b; b = tmp; }
-    z_ext = -(a + log1p(exp(b - a)));
+  const bool ordinary = fabs(eta) < 600 && exposure > 1e-280 && exposure < 1e280;
+  double tau = 0.0, z_int = 0.0, z_ext;
+  if (ordinary) {
+    if (y > 0) {
+      const double t1 = log_nobranch(ua0) * rcp_nobranch((double)y);
+      tau = exposure * exp_nobranch(t1);
+      z_int = -(log_nobranch(exposure) + t1);
+    }
+    const double delta = exposure - tau;
+    const double e1 = -log_nobranch(ua1);
+    z_ext = -log_nobranch(fma(exp_nobranch(-eta), e1, delta));
   } else {
-    z_ext = eta + (-log(e1));
+    if (y > 0) { tau = exposure * pow(ua0, 1.0 / (double)y); z_int = -log(tau); }
+    const double delta = exposure - tau;
+    const double e1 = -log(ua1);
+    z_ext = fabs(eta) < 600 ? -log(delta + (1.0 / exp(eta)) * e1) : poisson_zext_extreme(eta, delta, e1);
   }
-  if (!unmix_poisson(t, t.e1, z_ext - eta, ub0, o.mu_ext, o.w_ext, o.k_ext)) return 1;
+  unmix_poisson_ext(ext, t, z_ext - eta, ub0, o.mu_ext, o.w_ext, o.lw_ext, o.k_ext);
   o.z_ext = z_ext;
   if (y > 0) {
-    double z_int = -log(tau);
     o.z_int = z_int;
     if (y >= t.gaussian_cutoff) {
       o.mu_int = -log((double)y);
       o.w_int = 1.0 / (1.0 / (double)y);
+      o.lw_int = log(o.w_int);
     } else {
-      if (!unmix_poisson(t, poisson_table_find(t, y), z_int - eta, ub1, o.mu_int, o.w_int, o.k_int)) return 1;
+      if (!unmix_poisson(t, poisson_table_find(t, y), z_int - eta, ub1, o.mu_int, o.w_int, o.lw_int, o.k_int)) return 1;
     }
   }
   return 0;

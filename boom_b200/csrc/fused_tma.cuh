@@ -39,8 +39,16 @@ namespace boomgpu {
 #define BOOMGPU_TMA_RPL_SMALL 1
 #endif
 __host__ __device__ constexpr int tma_rpl(int nb) { return nb <= 2 ? BOOMGPU_TMA_RPL_SMALL : 1; }
-__host__ __device__ constexpr int tma_warps(int nb) { return nb <= 2 ? BOOMGPU_TMA_NW_SMALL : (nb == 3 ? 12 : (nb == 4 ? 10 : 6)); }
-__host__ __device__ constexpr int tma_stages(int nb) { return nb <= 2 ? BOOMGPU_TMA_S_SMALL : 2; }
+// wide tiles (40 < p <= 64): 8 warps with a SINGLE slice each beat 6 warps with two (p = 64: 1.59 vs 2.15 ms per 8 M rows):
+// the per-slice DMMA work is long enough that the other warp of the sub-partition covers the reload bubble.
+#ifndef BOOMGPU_TMA_NW_WIDE
+#define BOOMGPU_TMA_NW_WIDE 8
+#endif
+#ifndef BOOMGPU_TMA_S_WIDE
+#define BOOMGPU_TMA_S_WIDE 1
+#endif
+__host__ __device__ constexpr int tma_warps(int nb) { return nb <= 2 ? BOOMGPU_TMA_NW_SMALL : (nb == 3 ? 12 : (nb == 4 ? 10 : BOOMGPU_TMA_NW_WIDE)); }
+__host__ __device__ constexpr int tma_stages(int nb) { return nb <= 2 ? BOOMGPU_TMA_S_SMALL : (nb <= 4 ? 2 : BOOMGPU_TMA_S_WIDE); }
 __host__ __device__ constexpr int tma_padw(int nb) { return 8 * nb + 4; }
 __host__ __device__ constexpr int tma_slice_rows(int nb) { return 32 * tma_rpl(nb); }
 __host__ __device__ constexpr int tma_slice_doubles(int nb) { return tma_slice_rows(nb) * tma_padw(nb); }

@@ -48,7 +48,8 @@ struct RowOut {           // optional per-row outputs (test hooks); any may be n
 };
 
 struct DrawParams {
-  LogitHot hot;             // constant bank
+  LogitHot hot;             // constant bank: the logit mixture
+  LogitHot ext;             // constant bank: the Poisson table's nu = 1 entry (every observation draws from it)
   const LogitMixtureDev *mix;  // global memory (FP64 fallback of the selection, general / CLT path)
   PoissonTable tab;
   RngKey key;
@@ -106,15 +107,15 @@ __device__ __forceinline__ RowLatent impute_row(const RowData &d, const DrawPara
     r.w = info; r.s = sum;
   } else if (MODEL == kPoisson) {
     PoissonLatent o;
-    int rc = poisson_impute(prm.tab, obs.yi, obs.aux, eta, prm.key, d.row_offset + (uint64_t)i, o);
+    int rc = poisson_impute(prm.ext, prm.tab, obs.yi, obs.aux, eta, prm.key, d.row_offset + (uint64_t)i, o);
     if (rc) {
       atomicOr(err, rc == 1 ? 1 : 2);
     } else {
       double re = o.z_ext - o.mu_ext;
-      r.w = o.w_ext; r.s = o.w_ext * re; r.yWy = o.w_ext * re * re; r.sumlogw = log(o.w_ext);
+      r.w = o.w_ext; r.s = o.w_ext * re; r.yWy = o.w_ext * re * re; r.sumlogw = o.lw_ext;
       if (obs.yi > 0) {
         double ri = o.z_int - o.mu_int;
-        r.w += o.w_int; r.s += o.w_int * ri; r.yWy += o.w_int * ri * ri; r.sumlogw += log(o.w_int);
+        r.w += o.w_int; r.s += o.w_int * ri; r.yWy += o.w_int * ri * ri; r.sumlogw += o.lw_int;
         r.count = 2;
       }
       if (out.out6) {
