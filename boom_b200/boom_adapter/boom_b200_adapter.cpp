@@ -49,6 +49,11 @@ void DeviceImputerBase::impute_latent_data() {
   if (!ctx_) {
     if (boomgpu_create(&ctx_, device_)) report_error(std::string("boomgpu_create: ") + boomgpu_last_error(nullptr));
     stale_ = true;
+    comm_dirty_ = !comm_id_.empty();
+  }
+  if (comm_dirty_) {
+    check(boomgpu_comm_init(ctx_, comm_id_.data(), comm_ranks_, comm_rank_));
+    comm_dirty_ = false;
   }
   if (stale_ || repack_each_time_) {
     pack_and_upload(ctx_);
@@ -64,6 +69,7 @@ void DeviceImputerBase::impute_latent_data() {
   const uint64_t seed = rng().generator()();
   check(device_step(ctx_, current_beta().data(), seed, iteration_++, suf_dev));
   if (allreduce_) allreduce_(suf_dev, len);
+  else check(boomgpu_allreduce(ctx_, suf_dev, len));   // no-op without a communicator
   check(boomgpu_download(ctx_, suf_dev, packed_.data(), len));
   const int p = xdim_;
   SpdMatrix xtx(p);

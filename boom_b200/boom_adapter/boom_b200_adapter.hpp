@@ -53,6 +53,8 @@ class DeviceImputerBase : public PosteriorSampler {
   void set_device(int device);
   void set_row_offset(uint64_t first_global_row) { row_offset_ = first_global_row; stale_ = true; }
   void set_allreduce(const BOOM_B200::AllReduceFn &fn) { allreduce_ = fn; }
+  // or natively: join an NCCL communicator (id from BOOM_B200::GlmModelBase::comm_unique_id() on rank 0)
+  void set_communicator(const std::string &id, int nranks, int rank) { comm_id_ = id; comm_ranks_ = nranks; comm_rank_ = rank; comm_dirty_ = true; }
 
  protected:
   DeviceImputerBase(int xdim, RNG &seeding_rng);
@@ -76,6 +78,9 @@ class DeviceImputerBase : public PosteriorSampler {
   bool stale_ = true, latent_data_fixed_ = false, repack_each_time_ = false;
   uint64_t row_offset_ = 0, iteration_ = 0;
   BOOM_B200::AllReduceFn allreduce_;
+  std::string comm_id_;
+  int comm_ranks_ = 1, comm_rank_ = 0;
+  bool comm_dirty_ = false;
   std::vector<double> packed_;
 };
 

@@ -22,7 +22,7 @@ SYMBOLS = (
     "boomgpu_logit_step", "boomgpu_poisson_step", "boomgpu_suf_len", "boomgpu_logit_step_device",
     "boomgpu_poisson_step_device", "boomgpu_synchronize", "boomgpu_suf_buffer", "boomgpu_download", "boomgpu_accumulate", "boomgpu_logit_draw",
     "boomgpu_poisson_draw", "boomgpu_binomial_loglike", "boomgpu_poisson_loglike", "boomgpu_binomial_loglike_derivs",
-    "boomgpu_poisson_loglike_derivs", "boomgpu_kernel_launches",
+    "boomgpu_poisson_loglike_derivs", "boomgpu_comm_unique_id", "boomgpu_comm_init", "boomgpu_comm_destroy", "boomgpu_allreduce", "boomgpu_kernel_launches",
     "boomgpu_get_timings",
 )
 
@@ -152,6 +152,25 @@ class Context:
                                                     C.c_void_p(dy), C.c_void_p(dexposure)))
         self.n, self.p = n, p
         self._keep = list(keepalive)
+
+    # ---- multi-GPU (NCCL bound at run time inside the library)
+    @staticmethod
+    def comm_unique_id():
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.boomgpu_comm_unique_id(buf)
+        if rc:
+            raise BoomGpuError(lib.boomgpu_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, unique_id, nranks, rank):
+        self._check(self._lib.boomgpu_comm_init(self._h, C.c_char_p(unique_id), C.c_int(nranks), C.c_int(rank)))
+
+    def comm_destroy(self):
+        self._check(self._lib.boomgpu_comm_destroy(self._h))
+
+    def allreduce(self, dev_ptr, count):
+        self._check(self._lib.boomgpu_allreduce(self._h, C.c_void_p(dev_ptr), C.c_int64(int(count))))
 
     # ---- hot path
     def logit_step(self, beta, clt_threshold, seed, iteration):

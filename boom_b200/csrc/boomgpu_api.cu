@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <dlfcn.h>
 #include <string>
 #include <vector>
 
@@ -67,6 +68,10 @@ struct boomgpu_ctx {
     CUtensorMap map;
     const double *X = nullptr; int64_t n = -1, ldx = -1; int p = -1, box_cols = -1, box_rows = -1;
   } xmap_small, xmap_syrk;
+
+  // NCCL communicator (opaque ncclComm_t), null = single GPU
+  void *comm = nullptr;
+  int comm_ranks = 1;
 
   // options / instrumentation
   int path = 0;
@@ -151,6 +156,45 @@ void drain_timings(boomgpu_ctx *ctx) {
     ctx->event_pool.push_back(t.b);
   }
   ctx->timed.clear();
+}
+
+// ---- NCCL, bound at run time ------------------------------------------------------------------
+// Minimal mirror of nccl.h (stable ABI since NCCL 2.0): the 128-byte unique id, result code 0 = success,
+// ncclDouble = 8 (ncclFloat64), ncclSum = 0.
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi {
+  int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+  int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+const NcclApi &nccl() {
+  static NcclApi api = [] {
+    NcclApi a;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { a.why = std::string("cannot load libnccl.so.2: ") + dlerror(); return a; }
+    a.GetUniqueId = (int (*)(NcclUniqueId *))dlsym(h, "ncclGetUniqueId");
+    a.CommInitRank = (int (*)(void **, int, NcclUniqueId, int))dlsym(h, "ncclCommInitRank");
+    a.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+    a.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclAllReduce");
+    a.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.GetErrorString;
+    if (!a.ok) a.why = "libnccl.so.2 lacks an expected symbol";
+    return a;
+  }();
+  return api;
+}
+constexpr int kNcclDouble = 8, kNcclSum = 0;
+
+int allreduce_on_stream(boomgpu_ctx *ctx, double *dev, int64_t count) {
+  if (!ctx->comm || ctx->comm_ranks <= 1) return 0;
+  const int rc = nccl().AllReduce(dev, dev, (size_t)count, kNcclDouble, kNcclSum, ctx->comm, ctx->stream);
+  if (rc) return fail(ctx, BOOMGPU_ERR_CUDA, "ncclAllReduce failed: %s", nccl().GetErrorString(rc));
+  return 0;
 }
 
 SyrkUnitTable make_unit_table() {
@@ -604,6 +648,7 @@ void boomgpu_destroy(boomgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   drain_timings(ctx);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  if (ctx->comm) nccl().CommDestroy(ctx->comm);
   free_data(ctx);
   for (void *q : ctx->tab_owned) cudaFree(q);
   cudaFree(ctx->mix_dev);
@@ -699,6 +744,47 @@ int boomgpu_adopt_poisson(boomgpu_ctx *ctx, int64_t n, int p, const double *dX, 
   ctx->X = dX; ctx->ldx = ldx; ctx->n = n; ctx->p = p; ctx->yi = dy; ctx->exposure = dexposure;
   ctx->model = kPoisson;
   return 0;
+}
+
+int boomgpu_comm_unique_id(char id[BOOMGPU_COMM_ID_BYTES]) {
+  if (!id) return fail(nullptr, BOOMGPU_ERR_ARG, "null id");
+  if (!nccl().ok) return fail(nullptr, BOOMGPU_ERR_STATE, "%s", nccl().why.c_str());
+  NcclUniqueId u;
+  const int rc = nccl().GetUniqueId(&u);
+  if (rc) return fail(nullptr, BOOMGPU_ERR_CUDA, "ncclGetUniqueId failed: %s", nccl().GetErrorString(rc));
+  memcpy(id, u.internal, BOOMGPU_COMM_ID_BYTES);
+  return 0;
+}
+
+int boomgpu_comm_init(boomgpu_ctx *ctx, const char id[BOOMGPU_COMM_ID_BYTES], int nranks, int rank) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (!id || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, BOOMGPU_ERR_ARG, "bad communicator request (rank %d of %d)", rank, nranks);
+  if (!nccl().ok) return fail(ctx, BOOMGPU_ERR_STATE, "%s", nccl().why.c_str());
+  DeviceGuard g(ctx->device);
+  if (ctx->comm) { nccl().CommDestroy(ctx->comm); ctx->comm = nullptr; ctx->comm_ranks = 1; }
+  NcclUniqueId u;
+  memcpy(u.internal, id, BOOMGPU_COMM_ID_BYTES);
+  const int rc = nccl().CommInitRank(&ctx->comm, nranks, u, rank);
+  if (rc) { ctx->comm = nullptr; return fail(ctx, BOOMGPU_ERR_CUDA, "ncclCommInitRank failed: %s", nccl().GetErrorString(rc)); }
+  ctx->comm_ranks = nranks;
+  return 0;
+}
+
+int boomgpu_comm_destroy(boomgpu_ctx *ctx) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  if (ctx->comm) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    nccl().CommDestroy(ctx->comm);
+    ctx->comm = nullptr; ctx->comm_ranks = 1;
+  }
+  return 0;
+}
+
+int boomgpu_allreduce(boomgpu_ctx *ctx, double *dev, int64_t count) {
+  if (!ctx || !dev || count < 0) return BOOMGPU_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  return allreduce_on_stream(ctx, dev, count);
 }
 
 int boomgpu_set_logit_mixture(boomgpu_ctx *ctx, int K, const double *mu, const double *sigma, const double *weights) {
@@ -865,6 +951,7 @@ int boomgpu_logit_step(boomgpu_ctx *ctx, const double *beta, int clt_threshold, 
   DeviceGuard g(ctx->device);
   if (int rc = ensure_suf(ctx)) return rc;
   if (int rc = boomgpu_logit_step_device(ctx, beta, clt_threshold, seed, iteration, ctx->suf_dev)) return rc;
+  if (int rc = allreduce_on_stream(ctx, ctx->suf_dev, boomgpu_suf_len(ctx->p))) return rc;
   const int p = ctx->p;
   CU(cudaMemcpyAsync(ctx->suf_pin, ctx->suf_dev, sizeof(double) * (size_t)boomgpu_suf_len(p), cudaMemcpyDeviceToHost, ctx->stream));
   if (int rc = finish_and_check(ctx)) return rc;
@@ -881,6 +968,7 @@ int boomgpu_poisson_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, ui
   DeviceGuard g(ctx->device);
   if (int rc = ensure_suf(ctx)) return rc;
   if (int rc = boomgpu_poisson_step_device(ctx, beta, seed, iteration, ctx->suf_dev)) return rc;
+  if (int rc = allreduce_on_stream(ctx, ctx->suf_dev, boomgpu_suf_len(ctx->p))) return rc;
   const int p = ctx->p;
   CU(cudaMemcpyAsync(ctx->suf_pin, ctx->suf_dev, sizeof(double) * (size_t)boomgpu_suf_len(p), cudaMemcpyDeviceToHost, ctx->stream));
   if (int rc = finish_and_check(ctx)) return rc;

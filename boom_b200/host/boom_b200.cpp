@@ -256,6 +256,7 @@ DeviceData &GlmModelBase::device_data() {
     uploaded_version_ = 0;
     if (have_stream_) dev_->check(boomgpu_set_stream(dev_->ctx(), stream_));
     for (auto &o : options_) dev_->check(boomgpu_set_option(dev_->ctx(), o.first.c_str(), o.second));
+    if (!comm_id_.empty()) dev_->check(boomgpu_comm_init(dev_->ctx(), comm_id_.data(), comm_ranks_, comm_rank_));
   }
   if (uploaded_version_ != data_version_) {
     upload(*dev_);
@@ -265,6 +266,16 @@ DeviceData &GlmModelBase::device_data() {
   return *dev_;
 }
 
+std::string GlmModelBase::comm_unique_id() {
+  std::string id(BOOMGPU_COMM_ID_BYTES, '\0');
+  if (boomgpu_comm_unique_id(&id[0])) report_error(std::string("boomgpu_comm_unique_id: ") + boomgpu_last_error(nullptr));
+  return id;
+}
+void GlmModelBase::set_communicator(const std::string &id, int nranks, int rank) {
+  if ((int)id.size() != BOOMGPU_COMM_ID_BYTES) report_error("set_communicator: the id must be the 128 bytes of comm_unique_id()");
+  comm_id_ = id; comm_ranks_ = nranks; comm_rank_ = rank;
+  if (dev_) dev_->check(boomgpu_comm_init(dev_->ctx(), comm_id_.data(), comm_ranks_, comm_rank_));
+}
 void GlmModelBase::set_device_option(const std::string &name, int64_t value) {
   bool known = false;
   for (auto &o : options_) if (o.first == name) { o.second = value; known = true; }
@@ -819,6 +830,7 @@ void run_device_step(GlmModelBase &model, Vector &packed, StepFn step) {
   dev.check(boomgpu_suf_buffer(dev.ctx(), &suf_dev));
   dev.check(step(dev.ctx(), suf_dev));
   if (model.allreduce()) model.allreduce()(suf_dev, len);
+  else dev.check(boomgpu_allreduce(dev.ctx(), suf_dev, len));   // no-op without a communicator
   dev.check(boomgpu_download(dev.ctx(), suf_dev, packed.data(), len));
 }
 }  // namespace

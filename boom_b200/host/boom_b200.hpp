@@ -211,6 +211,10 @@ class GlmModelBase {
   void set_row_offset(uint64_t first_global_row);  // this shard's first global row (multi-GPU)
   void set_stream(void *cuda_stream);     // cudaStream_t the device step (and the all-reduce hook) runs on
   void set_allreduce(const AllReduceFn &fn) { allreduce_ = fn; }
+  // native alternative to the hook: join an NCCL communicator through the C ABI (boomgpu_comm_init); id = the 128 bytes
+  // rank 0 obtained from comm_unique_id() and handed to the other ranks
+  static std::string comm_unique_id();
+  void set_communicator(const std::string &id, int nranks, int rank);
   const AllReduceFn &allreduce() const { return allreduce_; }
   // rows already resident in HBM (device pointers): nothing is copied; the caller keeps them alive
   DeviceData &device_data();              // packs / uploads when stale
@@ -240,6 +244,8 @@ class GlmModelBase {
   void *stream_ = nullptr;
   bool have_stream_ = false;
   std::vector<std::pair<std::string, int64_t>> options_;
+  std::string comm_id_;
+  int comm_ranks_ = 1, comm_rank_ = 0;
 };
 
 class BinomialLogitModel : public GlmModelBase {

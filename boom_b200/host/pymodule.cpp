@@ -65,6 +65,8 @@ void bind_model_common(py::class_<M, std::shared_ptr<M>> &c) {
           fn(reinterpret_cast<uintptr_t>(dev), count);
         });
       })
+      .def_static("comm_unique_id", []() { return py::bytes(M::comm_unique_id()); })
+      .def("set_communicator", [](M &m, const py::bytes &id, int nranks, int rank) { m.set_communicator(std::string(id), nranks, rank); })
       .def("set_device_option", &M::set_device_option)
       .def("kernel_launches", &M::kernel_launches)
       .def("kernel_timings", [](M &m, bool reset) {

@@ -118,6 +118,22 @@ int boomgpu_suf_buffer(boomgpu_ctx *ctx, double **suf_dev);
  * boomgpu_synchronize: the read side of a step_device + all-reduce sequence */
 int boomgpu_download(boomgpu_ctx *ctx, const double *src_dev, double *dst_host, int64_t count);
 
+/* ---- multi-GPU: one context per GPU, rows sharded, ONE all-reduce of the packed statistics per iteration ---------
+ * The reference combines its workers' statistics under a mutex (Models/PosteriorSamplers/Imputer.cpp:40-64 over
+ * BinomialLogitAuxmixSampler.cpp:44-49 / WeightedRegressionModel.cpp:79-87); here a worker is a GPU and combine() is
+ * ncclAllReduce(ncclDouble, ncclSum) over NVLink.  NCCL is loaded at run time (libnccl.so.2, whichever copy the process
+ * already holds), so the library has no link-time dependency on it.
+ *   boomgpu_comm_unique_id   rank 0 makes the 128-byte id and hands it to the other ranks by its own means
+ *   boomgpu_comm_init        every rank, after boomgpu_create: joins the communicator (ncclCommInitRank)
+ *   boomgpu_allreduce        sums count doubles at a device pointer over all ranks, in place, on the context's stream
+ * With a communicator attached, the synchronous boomgpu_logit_step / boomgpu_poisson_step all-reduce before they copy
+ * the statistics to the host; the *_step_device variants leave that to the caller (boomgpu_allreduce). */
+#define BOOMGPU_COMM_ID_BYTES 128
+int boomgpu_comm_unique_id(char id[BOOMGPU_COMM_ID_BYTES]);
+int boomgpu_comm_init(boomgpu_ctx *ctx, const char id[BOOMGPU_COMM_ID_BYTES], int nranks, int rank);
+int boomgpu_comm_destroy(boomgpu_ctx *ctx);
+int boomgpu_allreduce(boomgpu_ctx *ctx, double *dev, int64_t count);
+
 /* ---- parity / test hooks --------------------------------------------------------------- */
 /* deterministic accumulation from caller supplied latents (host arrays of length n) */
 int boomgpu_accumulate(boomgpu_ctx *ctx, const double *weight, const double *weighted_value,

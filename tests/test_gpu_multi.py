@@ -92,3 +92,55 @@ def test_two_gpu_chain_matches_one_gpu():
     assert np.max(np.abs(res[0][2][0] - sufs1[0]) / np.outer(d, d)) < 1e-12
     # the whole chain stays together (the host steps see statistics that differ in the last bits only)
     np.testing.assert_allclose(res[0][1], betas1, rtol=1e-6, atol=1e-8)
+
+
+def _native_worker(rank, world, uid, q):
+    sys.path.insert(0, ROOT)
+    import boom_b200
+    from boom_b200.distributed import shard_range
+    from oracle import oracle as O
+    try:
+        n, p = 30_011, 24
+        X, y, nt, beta = O.synth_binomial(n, p, 4, seed=9, max_trials=1)
+        row0, row1 = shard_range(n, world, rank)
+        ctx = boom_b200.Context(rank)
+        mix = O.logit_mixture()
+        ctx.set_logit_mixture(mix.mu, mix.sigma, mix.weights)
+        ctx.upload_binomial(X[row0:row1], y[row0:row1], nt[row0:row1])
+        ctx.set_row_offset(row0)
+        ctx.comm_init(uid, world, rank)            # ncclCommInitRank inside libboomgpu (NCCL bound at run time)
+        xtx, xty, ss = ctx.logit_step(beta, 10, seed=21, iteration=4)   # all-reduces before the copy to the host
+        ctx.comm_destroy()
+        ctx.close()
+        q.put((rank, xtx, xty, ss))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, "FAIL: %r" % (e,), None, None))
+
+
+def test_native_nccl_allreduce_through_the_c_abi():
+    """boomgpu_comm_unique_id / boomgpu_comm_init / the all-reducing boomgpu_logit_step: no torch in the loop."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    import boom_b200
+    from oracle import oracle as O
+    uid = boom_b200.Context.comm_unique_id()
+    assert len(uid) == 128
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_native_worker, args=(r, 2, uid, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted((q.get(timeout=600) for _ in procs), key=lambda t: t[0])
+    for pr in procs:
+        pr.join(timeout=60)
+    assert not isinstance(res[0][1], str) and not isinstance(res[1][1], str), res
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    n, p = 30_011, 24
+    X, y, nt, beta = O.synth_binomial(n, p, 4, seed=9, max_trials=1)
+    rxtx, rxty, rss, _ = O.logit_step(X, y, nt, beta, 10, O.logit_mixture(), 21, 4)
+    d = np.sqrt(np.diag(rxtx))
+    assert res[0][3] == rss == n
+    assert np.max(np.abs(res[0][1] - rxtx) / np.outer(d, d)) < 1e-11
+    assert np.max(np.abs(res[0][2] - rxty)) < 1e-9 * np.max(np.abs(rxty))
