@@ -338,9 +338,9 @@ def main():
         ah = aux.cpu().numpy()
         del X, y, aux
         torch.cuda.empty_cache()
-        model = Model(Xh, yh, ah)
+        model = Model(p)
+        model.borrow_host_data(Xh, yh, ah)   # the rows stay in this process's host arrays; uploaded by the first draw
         nbytes_up = Xh.nbytes + yh.nbytes + ah.nbytes
-        del Xh
         smp = build(model)
         barrier()
         tu = time.perf_counter()

@@ -299,7 +299,7 @@ BinomialLogitModel::BinomialLogitModel(int64_t n, int p, const double *X, const 
 void BinomialLogitModel::add_data(double y, double n, const Vector &x) {
   if ((int)x.size() != xdim()) report_error("BinomialLogitModel::add_data: wrong size x");
   if (y > n || y < 0 || n < 0) report_error("BinomialRegressionData: y must lie in [0, n]");
-  if (adopted_) report_error("add_data on a model whose data live in adopted device memory");
+  if (adopted_ || borrowed_) report_error("add_data on a model whose data live in adopted / borrowed memory");
   x_.insert(x_.end(), x.begin(), x.end());
   y_.push_back(y);
   n_.push_back(n);
@@ -309,7 +309,14 @@ void BinomialLogitModel::adopt_device_data(int64_t n, const double *dX, int64_t 
   adopted_ = true; adopted_n_ = n; dX_ = dX; dldx_ = ldx; dy_ = dy; dn_ = dn;
   touch();
 }
+void BinomialLogitModel::borrow_host_data(int64_t n, const double *X, int64_t ldx, const double *y, const double *nt,
+                                          std::shared_ptr<void> keepalive) {
+  borrowed_ = true; adopted_ = false; adopted_n_ = n; dX_ = X; dldx_ = ldx; dy_ = y; dn_ = nt;
+  keepalive_ = std::move(keepalive);
+  touch();
+}
 void BinomialLogitModel::upload(DeviceData &dev) {
+  if (borrowed_) { dev.check(boomgpu_upload_binomial(dev.ctx(), adopted_n_, xdim(), dX_, dldx_, dy_, dn_)); return; }
   if (adopted_) dev.check(boomgpu_adopt_binomial(dev.ctx(), adopted_n_, xdim(), dX_, dldx_, dy_, dn_));
   else dev.check(boomgpu_upload_binomial(dev.ctx(), (int64_t)y_.size(), xdim(), x_.data(), xdim(), y_.data(), n_.data()));
 }
@@ -346,7 +353,7 @@ PoissonRegressionModel::PoissonRegressionModel(int64_t n, int p, const double *X
 void PoissonRegressionModel::add_data(int64_t y, const Vector &x, double exposure) {
   if ((int)x.size() != xdim()) report_error("PoissonRegressionModel::add_data: wrong size x");
   if (y < 0 || exposure < 0) report_error("PoissonRegressionData: y and exposure must be non-negative");
-  if (adopted_) report_error("add_data on a model whose data live in adopted device memory");
+  if (adopted_ || borrowed_) report_error("add_data on a model whose data live in adopted / borrowed memory");
   x_.insert(x_.end(), x.begin(), x.end());
   y_.push_back(y);
   exposure_.push_back(exposure);
@@ -356,7 +363,14 @@ void PoissonRegressionModel::adopt_device_data(int64_t n, const double *dX, int6
   adopted_ = true; adopted_n_ = n; dX_ = dX; dldx_ = ldx; dy_ = dy; dexp_ = dex;
   touch();
 }
+void PoissonRegressionModel::borrow_host_data(int64_t n, const double *X, int64_t ldx, const int64_t *y, const double *ex,
+                                              std::shared_ptr<void> keepalive) {
+  borrowed_ = true; adopted_ = false; adopted_n_ = n; dX_ = X; dldx_ = ldx; dy_ = y; dexp_ = ex;
+  keepalive_ = std::move(keepalive);
+  touch();
+}
 void PoissonRegressionModel::upload(DeviceData &dev) {
+  if (borrowed_) { dev.check(boomgpu_upload_poisson(dev.ctx(), adopted_n_, xdim(), dX_, dldx_, dy_, dexp_)); return; }
   if (adopted_) dev.check(boomgpu_adopt_poisson(dev.ctx(), adopted_n_, xdim(), dX_, dldx_, dy_, dexp_));
   else dev.check(boomgpu_upload_poisson(dev.ctx(), (int64_t)y_.size(), xdim(), x_.data(), xdim(), y_.data(), exposure_.data()));
 }

@@ -230,8 +230,9 @@ class GlmModelBase {
   virtual void upload(DeviceData &dev) = 0;
   void touch() { ++data_version_; }
   Vector x_;  // row major n x p
-  bool adopted_ = false;
+  bool adopted_ = false, borrowed_ = false;
   int64_t adopted_n_ = 0;
+  std::shared_ptr<void> keepalive_;
 
  private:
   GlmCoefs coef_;
@@ -256,7 +257,11 @@ class BinomialLogitModel : public GlmModelBase {
   // model->add_data(new BinomialRegressionData(y, n, x))  (BinomialRegressionData.hpp:25-55)
   void add_data(double y, double n, const Vector &x);
   void adopt_device_data(int64_t n, const double *dX, int64_t ldx, const double *dy, const double *dntrials);
-  int64_t nobs() const { return adopted_ ? adopted_n_ : (int64_t)y_.size(); }
+  // rows that stay in the CALLER's host memory (no copy into the model: at n = 1e7, p = 500 a second 40 GB copy matters);
+  // read when the rows are uploaded; keepalive owns whatever keeps the three arrays alive
+  void borrow_host_data(int64_t n, const double *X, int64_t ldx, const double *y, const double *ntrials,
+                        std::shared_ptr<void> keepalive);
+  int64_t nobs() const { return (adopted_ || borrowed_) ? adopted_n_ : (int64_t)y_.size(); }
   // Models/Glm/BinomialLogitModel.cpp:140-180, value only, evaluated on the device
   double log_likelihood(const Vector &beta);
   double log_likelihood() { return log_likelihood(Beta()); }
@@ -282,7 +287,9 @@ class PoissonRegressionModel : public GlmModelBase {
   // model->add_data(new PoissonRegressionData(y, x, exposure))  (PoissonRegressionData.hpp:25-62)
   void add_data(int64_t y, const Vector &x, double exposure = 1.0);
   void adopt_device_data(int64_t n, const double *dX, int64_t ldx, const int64_t *dy, const double *dexposure);
-  int64_t nobs() const { return adopted_ ? adopted_n_ : (int64_t)y_.size(); }
+  void borrow_host_data(int64_t n, const double *X, int64_t ldx, const int64_t *y, const double *exposure,
+                        std::shared_ptr<void> keepalive);
+  int64_t nobs() const { return (adopted_ || borrowed_) ? adopted_n_ : (int64_t)y_.size(); }
   double log_likelihood(const Vector &beta);
   double log_likelihood() { return log_likelihood(Beta()); }
   double log_likelihood_derivs(const Vector &beta, Vector *g, SpdMatrix *h) override;

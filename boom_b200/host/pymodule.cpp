@@ -6,6 +6,8 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <tuple>
+
 #include "boom_b200.hpp"
 
 namespace py = pybind11;
@@ -117,6 +119,15 @@ PYBIND11_MODULE(_host, m) {
         return std::make_shared<BinomialLogitModel>((int64_t)X.shape(0), (int)X.shape(1), X.data(), y.data(), n.data());
       }))
       .def("add_data", [](BinomialLogitModel &mo, double y, double n, const NpD &x) { mo.add_data(y, n, to_vec(x)); })
+      .def("borrow_host_data", [](BinomialLogitModel &mo, NpD X, NpD y, NpD n) {
+        // zero copy: the model keeps references to the three arrays (they must already be C-contiguous float64:
+        // forcecast would otherwise have made private copies, which is fine too) and reads them when it uploads
+        if (X.ndim() != 2 || (int)X.shape(1) != mo.xdim() || y.size() != X.shape(0) || n.size() != X.shape(0))
+          report_error("borrow_host_data(X, y, n): shape mismatch");
+        auto keep = std::make_shared<std::tuple<NpD, NpD, NpD>>(X, y, n);
+        mo.borrow_host_data((int64_t)X.shape(0), X.data(), (int64_t)X.shape(1), y.data(), n.data(),
+                            std::shared_ptr<void>(keep, keep.get()));
+      })
       .def("adopt_device_data", [](BinomialLogitModel &mo, int64_t n, uintptr_t dX, int64_t ldx, uintptr_t dy, uintptr_t dn) {
         mo.adopt_device_data(n, reinterpret_cast<const double *>(dX), ldx, reinterpret_cast<const double *>(dy),
                              reinterpret_cast<const double *>(dn));
@@ -132,6 +143,13 @@ PYBIND11_MODULE(_host, m) {
       }))
       .def("add_data", [](PoissonRegressionModel &mo, int64_t y, const NpD &x, double e) { mo.add_data(y, to_vec(x), e); },
            py::arg("y"), py::arg("x"), py::arg("exposure") = 1.0)
+      .def("borrow_host_data", [](PoissonRegressionModel &mo, NpD X, NpI y, NpD e) {
+        if (X.ndim() != 2 || (int)X.shape(1) != mo.xdim() || y.size() != X.shape(0) || e.size() != X.shape(0))
+          report_error("borrow_host_data(X, y, exposure): shape mismatch");
+        auto keep = std::make_shared<std::tuple<NpD, NpI, NpD>>(X, y, e);
+        mo.borrow_host_data((int64_t)X.shape(0), X.data(), (int64_t)X.shape(1), y.data(), e.data(),
+                            std::shared_ptr<void>(keep, keep.get()));
+      })
       .def("adopt_device_data", [](PoissonRegressionModel &mo, int64_t n, uintptr_t dX, int64_t ldx, uintptr_t dy, uintptr_t de) {
         mo.adopt_device_data(n, reinterpret_cast<const double *>(dX), ldx, reinterpret_cast<const int64_t *>(dy),
                              reinterpret_cast<const double *>(de));

@@ -210,3 +210,20 @@ def test_poisson_find_posterior_mode_zero_gradient():
     _, g, _ = O.poisson_loglike_derivs(X, y, ex, beta)
     assert np.max(np.abs(g - beta)) < 1e-5 * n     # gradient of the log posterior: g - Siginv (beta - 0) = 0
     assert np.isfinite(sampler.log_posterior_at_mode)
+
+
+def test_borrowed_host_rows_give_the_same_chain():
+    """borrow_host_data: rows stay in the caller's arrays (no second host copy); same chain as the copying constructor."""
+    X, y, nt, _ = O.synth_binomial(3000, 5, 2, seed=12)
+    out = []
+    for borrow in (False, True):
+        if borrow:
+            model = boom_b200.BinomialLogitModel(5)
+            model.borrow_host_data(X, y, nt)
+        else:
+            model = boom_b200.BinomialLogitModel(X, y, nt)
+        sampler = boom_b200.BinomialLogitAuxmixSampler(model, boom_b200.MvnModel(np.zeros(5), np.eye(5)), 10, boom_b200.RNG(9))
+        model.set_method(sampler)
+        out.append(_run(model, 20, 0))
+        assert model.sample_size == 3000
+    np.testing.assert_array_equal(out[0], out[1])
