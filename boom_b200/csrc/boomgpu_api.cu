@@ -69,6 +69,8 @@ struct boomgpu_ctx {
     const double *X = nullptr; int64_t n = -1, ldx = -1; int p = -1, box_cols = -1, box_rows = -1;
   } xmap_small, xmap_syrk;
 
+  bool host_out_written = false;   // the last step's reduction wrote the statistics straight into suf_pin (zero copy)
+
   // NCCL communicator (opaque ncclComm_t), null = single GPU
   void *comm = nullptr;
   int comm_ranks = 1;
@@ -321,6 +323,9 @@ struct TmaLauncher {
   static int go(boomgpu_ctx *ctx, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts) {
     auto kern = fused_tma_kernel<NB, MODEL>;
     constexpr int NW = tma_warps(NB);
+    BetaParam bp;
+    memset(&bp, 0, sizeof(bp));
+    memcpy(bp.b, ctx->beta_pin, sizeof(double) * d.p);
     const size_t smem = tma_smem_bytes(NB);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (int rc = ensure_xmap(ctx, ctx->xmap_small, tma_padw(NB), tma_slice_rows(NB))) return rc;
@@ -329,7 +334,7 @@ struct TmaLauncher {
     if (ensure(ctx, &ctx->partials, &ctx->partials_cap, (int64_t)grid * tma_partial_len(NB))) return BOOMGPU_ERR_CUDA;
     {
       LaunchScope ls(ctx, 0);
-      kern<<<grid, 32 * NW, smem, ctx->stream>>>(ctx->xmap_small.map, d, prm, out, ctx->beta_dev, ctx->partials, ctx->err_dev);
+      kern<<<grid, 32 * NW, smem, ctx->stream>>>(ctx->xmap_small.map, d, prm, out, bp, ctx->partials, ctx->err_dev);
     }
     CU(cudaGetLastError());
     *nparts = grid;
@@ -436,10 +441,12 @@ int launch_syrk(boomgpu_ctx *ctx, double *suf) {
 // The whole device step for MODEL; leaves the packed statistics at suf (device).
 template <int MODEL>
 int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, const RowOut &out,
-             const double *w_in, const double *s_in, double *suf) {
+             const double *w_in, const double *s_in, double *suf, double *host_out = nullptr) {
   int path = 0;
   if (int rc = choose_path(ctx, &path)) return rc;
   const int p = ctx->p;
+  ctx->host_out_written = false;
+  const bool tma_small = path == 1 && tma_ok(ctx) && ctx->small_variant != 1;
   if (ctx->beta_cap < p + 2) {
     if (ctx->beta_dev) { CU(cudaFree(ctx->beta_dev)); ctx->beta_dev = nullptr; }
     if (ctx->beta_pin) { CU(cudaFreeHost(ctx->beta_pin)); ctx->beta_pin = nullptr; }
@@ -452,7 +459,8 @@ int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, c
   } else {
     memset(ctx->beta_pin, 0, sizeof(double) * p);
   }
-  CU(cudaMemcpyAsync(ctx->beta_dev, ctx->beta_pin, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+  if (!tma_small)   // the TMA small-p kernel takes beta as a kernel parameter
+    CU(cudaMemcpyAsync(ctx->beta_dev, ctx->beta_pin, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
 
   RowData d;
   d.X = ctx->X; d.ldx = ctx->ldx; d.n = ctx->n; d.p = p;
@@ -466,7 +474,7 @@ int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, c
   if (path == 1) {
     int nparts = 0;
     const int nb = (p + 7) / 8;
-    if (tma_ok(ctx) && ctx->small_variant != 1) {
+    if (tma_small) {
       // TMA-fed warp-autonomous kernel (fused_tma.cuh)
       if (int rc = TmaLauncher<MODEL>::dispatch(ctx, nb, d, prm, out, &nparts)) return rc;
     } else {
@@ -477,7 +485,8 @@ int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, c
     {
       LaunchScope ls(ctx, 3);
       const int total = p * (p + 1) / 2 + p + 4;   // one warp per output element
-      reduce_partials_kernel<<<(total + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, nparts, nb, p, suf);
+      reduce_partials_kernel<<<(total + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, nparts, nb, p, suf, host_out, ctx->err_dev);
+      ctx->host_out_written = host_out != nullptr;
     }
     CU(cudaGetLastError());
   } else {
@@ -511,10 +520,10 @@ int check_ready(boomgpu_ctx *ctx, int model) {
 int ensure_suf(boomgpu_ctx *ctx) {
   const int64_t len = boomgpu_suf_len(ctx->p);
   if (ensure(ctx, &ctx->suf_dev, &ctx->suf_cap, len)) return BOOMGPU_ERR_CUDA;
-  if (ctx->suf_pin_cap < len) {
+  if (ctx->suf_pin_cap < len + 1) {   // + 1: the validation flag rides behind the statistics on the zero-copy path
     if (ctx->suf_pin) { CU(cudaFreeHost(ctx->suf_pin)); ctx->suf_pin = nullptr; }
-    CU(cudaMallocHost((void **)&ctx->suf_pin, sizeof(double) * (size_t)len));
-    ctx->suf_pin_cap = len;
+    CU(cudaMallocHost((void **)&ctx->suf_pin, sizeof(double) * (size_t)(len + 1)));
+    ctx->suf_pin_cap = len + 1;
   }
   return 0;
 }
@@ -531,6 +540,27 @@ int finish_and_check(boomgpu_ctx *ctx) {
                 "or a non-finite linear predictor");
   }
   return 0;
+}
+
+// statistics of the step just launched -> suf_pin, then wait and report device-side validation errors.
+// Single GPU + small-p kernel: the reduction already wrote them (and the flag) into the host-mapped suf_pin.
+int fetch_suf(boomgpu_ctx *ctx) {
+  const int p = ctx->p;
+  const int64_t len = boomgpu_suf_len(p);
+  if (ctx->host_out_written) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    const int flag = (int)ctx->suf_pin[len];
+    if (flag) {
+      CU(cudaMemsetAsync(ctx->err_dev, 0, sizeof(int), ctx->stream));
+      if (flag & 1) return fail(ctx, BOOMGPU_ERR_DATA, "a count y is missing from the Poisson mixture table "
+                                "(call NormalMixtureApproximationTable::approximate(y) for every distinct y before upload)");
+      return fail(ctx, BOOMGPU_ERR_DATA, "invalid observation on the device: successes > trials, a negative count/exposure, "
+                  "or a non-finite linear predictor");
+    }
+    return 0;
+  }
+  CU(cudaMemcpyAsync(ctx->suf_pin, ctx->suf_dev, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish_and_check(ctx);
 }
 
 DrawParams make_prm(boomgpu_ctx *ctx, int clt, uint64_t seed, uint64_t iteration) {
@@ -591,10 +621,9 @@ int loglike_derivs_impl(boomgpu_ctx *ctx, int model, const double *beta, double 
   DrawParams prm = make_prm(ctx, 0, 0, 0);
   prm.log_alpha = log_alpha;
   RowOut out{nullptr, nullptr, nullptr, nullptr};
-  if (int rc = run_step<MODEL>(ctx, beta, prm, out, nullptr, nullptr, ctx->suf_dev)) return rc;
+  if (int rc = run_step<MODEL>(ctx, beta, prm, out, nullptr, nullptr, ctx->suf_dev, ctx->suf_pin)) return rc;
   const int p = ctx->p;
-  CU(cudaMemcpyAsync(ctx->suf_pin, ctx->suf_dev, sizeof(double) * (size_t)boomgpu_suf_len(p), cudaMemcpyDeviceToHost, ctx->stream));
-  if (int rc = finish_and_check(ctx)) return rc;
+  if (int rc = fetch_suf(ctx)) return rc;
   *loglike = ctx->n == 0 ? 0.0 : ctx->suf_pin[(size_t)p * p + p + 1];
   if (gradient) memcpy(gradient, ctx->suf_pin + (size_t)p * p, sizeof(double) * p);
   if (hessian) for (size_t e = 0; e < (size_t)p * p; ++e) hessian[e] = -ctx->suf_pin[e];
@@ -950,11 +979,14 @@ int boomgpu_logit_step(boomgpu_ctx *ctx, const double *beta, int clt_threshold, 
   if (!beta || !xtx || !xty) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
   DeviceGuard g(ctx->device);
   if (int rc = ensure_suf(ctx)) return rc;
-  if (int rc = boomgpu_logit_step_device(ctx, beta, clt_threshold, seed, iteration, ctx->suf_dev)) return rc;
+  const bool sharded = ctx->comm && ctx->comm_ranks > 1;
+  RowOut out{nullptr, nullptr, nullptr, nullptr};
+  if (int rc = run_step<kLogit>(ctx, beta, make_prm(ctx, clt_threshold, seed, iteration), out, nullptr, nullptr, ctx->suf_dev,
+                                sharded ? nullptr : ctx->suf_pin))
+    return rc;
   if (int rc = allreduce_on_stream(ctx, ctx->suf_dev, boomgpu_suf_len(ctx->p))) return rc;
+  if (int rc = fetch_suf(ctx)) return rc;
   const int p = ctx->p;
-  CU(cudaMemcpyAsync(ctx->suf_pin, ctx->suf_dev, sizeof(double) * (size_t)boomgpu_suf_len(p), cudaMemcpyDeviceToHost, ctx->stream));
-  if (int rc = finish_and_check(ctx)) return rc;
   memcpy(xtx, ctx->suf_pin, sizeof(double) * (size_t)p * p);
   memcpy(xty, ctx->suf_pin + (size_t)p * p, sizeof(double) * p);
   if (sample_size) *sample_size = (int64_t)llround(ctx->suf_pin[(size_t)p * p + p]);
@@ -967,11 +999,14 @@ int boomgpu_poisson_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, ui
   if (!beta || !xtwx || !xtwy) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
   DeviceGuard g(ctx->device);
   if (int rc = ensure_suf(ctx)) return rc;
-  if (int rc = boomgpu_poisson_step_device(ctx, beta, seed, iteration, ctx->suf_dev)) return rc;
+  const bool sharded = ctx->comm && ctx->comm_ranks > 1;
+  RowOut out{nullptr, nullptr, nullptr, nullptr};
+  if (int rc = run_step<kPoisson>(ctx, beta, make_prm(ctx, 0, seed, iteration), out, nullptr, nullptr, ctx->suf_dev,
+                                  sharded ? nullptr : ctx->suf_pin))
+    return rc;
   if (int rc = allreduce_on_stream(ctx, ctx->suf_dev, boomgpu_suf_len(ctx->p))) return rc;
+  if (int rc = fetch_suf(ctx)) return rc;
   const int p = ctx->p;
-  CU(cudaMemcpyAsync(ctx->suf_pin, ctx->suf_dev, sizeof(double) * (size_t)boomgpu_suf_len(p), cudaMemcpyDeviceToHost, ctx->stream));
-  if (int rc = finish_and_check(ctx)) return rc;
   memcpy(xtwx, ctx->suf_pin, sizeof(double) * (size_t)p * p);
   memcpy(xtwy, ctx->suf_pin + (size_t)p * p, sizeof(double) * p);
   if (scalars) memcpy(scalars, ctx->suf_pin + (size_t)p * p + p, sizeof(double) * 4);

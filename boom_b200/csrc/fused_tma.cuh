@@ -58,9 +58,12 @@ __host__ __device__ constexpr size_t tma_smem_bytes(int nb) {
 }
 __host__ __device__ constexpr int64_t tma_partial_len(int nb) { return 64 * nb * nb + 8 * nb + 8; }
 
+// beta travels as a kernel parameter (p <= 64: 512 bytes of the constant bank): no host->device copy per step
+struct BetaParam { double b[64]; };
+
 template <int NB, int MODEL>
 __global__ void __launch_bounds__(32 * tma_warps(NB), 1)
-fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams prm, RowOut out, const double *__restrict__ beta,
+fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams prm, RowOut out, const __grid_constant__ BetaParam beta,
                  double *__restrict__ partials, int *err) {
   constexpr int NW = tma_warps(NB);
   constexpr int S = tma_stages(NB);
@@ -79,7 +82,7 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int p = d.p;
-  if (tid < P8) beta_s[tid] = tid < p ? beta[tid] : 0.0;
+  if (tid < P8) beta_s[tid] = tid < p ? beta.b[tid] : 0.0;
   if (tid == 0) {
     for (int i = 0; i < NW * S; ++i) mbar_init(bars + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -281,8 +284,11 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
 
 // One warp per output element: lanes stride over the per-CTA partials, then a fixed shuffle tree.
 // suf layout [p*p | p | 4]; writes both triangles.  Partial layout: [P8*P8 tile | P8 | 8].
+// host_out (optional): a host-mapped pinned buffer of suf_len + 1 doubles that receives the statistics and, in its last
+// slot, the device-side validation flag -- the synchronous steps then need no device->host copy call at all.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double *__restrict__ partials, int nparts, int nb, int p,
-                                                             double *__restrict__ suf) {
+                                                             double *__restrict__ suf, double *__restrict__ host_out,
+                                                             const int *__restrict__ err) {
   const int P8 = 8 * nb;
   const int64_t plen = 64 * (int64_t)nb * nb + 8 * nb + 8;
   const int ntri = p * (p + 1) / 2;
@@ -311,11 +317,14 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double *__re
       if (e < ntri) {
         suf[a + (int64_t)b * p] = s;
         suf[b + (int64_t)a * p] = s;
+        if (host_out) { host_out[a + (int64_t)b * p] = s; host_out[b + (int64_t)a * p] = s; }
       } else {
         suf[(int64_t)p * p + (e - ntri)] = s;
+        if (host_out) host_out[(int64_t)p * p + (e - ntri)] = s;
       }
     }
   }
+  if (host_out && blockIdx.x == 0 && threadIdx.x == 0) host_out[(int64_t)p * p + p + 4] = (double)*err;
 }
 
 }  // namespace boomgpu

@@ -833,19 +833,25 @@ struct PoissonTableStore {
 };
 PoissonTableStore &poisson_table_store() { static PoissonTableStore s; return s; }
 
-// device step -> allreduce hook -> packed statistics on the host
-template <class StepFn>
-void run_device_step(GlmModelBase &model, Vector &packed, StepFn step) {
+// device step -> all-reduce -> packed statistics [p*p | p | 4] on the host.
+// With a caller-supplied all-reduce hook the statistics stay on the device for it (step_device + hook + download);
+// otherwise the synchronous C-ABI step does everything (native NCCL when a communicator is attached, and for p <= 64 on
+// one GPU the reduction writes straight into pinned host memory).
+template <class StepDeviceFn, class StepSyncFn>
+void run_device_step(GlmModelBase &model, Vector &packed, StepDeviceFn step_device, StepSyncFn step_sync) {
   DeviceData &dev(model.device_data());
   const int p = model.xdim();
   const int64_t len = boomgpu_suf_len(p);
   packed.resize((size_t)len);
-  double *suf_dev = nullptr;
-  dev.check(boomgpu_suf_buffer(dev.ctx(), &suf_dev));
-  dev.check(step(dev.ctx(), suf_dev));
-  if (model.allreduce()) model.allreduce()(suf_dev, len);
-  else dev.check(boomgpu_allreduce(dev.ctx(), suf_dev, len));   // no-op without a communicator
-  dev.check(boomgpu_download(dev.ctx(), suf_dev, packed.data(), len));
+  if (model.allreduce()) {
+    double *suf_dev = nullptr;
+    dev.check(boomgpu_suf_buffer(dev.ctx(), &suf_dev));
+    dev.check(step_device(dev.ctx(), suf_dev));
+    model.allreduce()(suf_dev, len);
+    dev.check(boomgpu_download(dev.ctx(), suf_dev, packed.data(), len));
+  } else {
+    dev.check(step_sync(dev.ctx(), packed.data(), packed.data() + (size_t)p * p, packed.data() + (size_t)p * p + p));
+  }
 }
 }  // namespace
 
@@ -881,11 +887,21 @@ void BinomialLogitAuxmixSampler::impute_latent_data() {
   const int clt = clt_threshold_;
   const uint64_t seed = device_seed_, it = iteration_++;
   const Vector &beta(model_->Beta());
-  run_device_step(*model_, packed_, [&](boomgpu_ctx *ctx, double *suf_dev) {
-    int rc = boomgpu_set_logit_mixture(ctx, (int)mix.sigma.size(), mix.mu.data(), mix.sigma.data(), mix.weights.data());
-    if (rc) return rc;
-    return boomgpu_logit_step_device(ctx, beta.data(), clt, seed, it, suf_dev);
-  });
+  run_device_step(
+      *model_, packed_,
+      [&](boomgpu_ctx *ctx, double *suf_dev) {
+        int rc = boomgpu_set_logit_mixture(ctx, (int)mix.sigma.size(), mix.mu.data(), mix.sigma.data(), mix.weights.data());
+        if (rc) return rc;
+        return boomgpu_logit_step_device(ctx, beta.data(), clt, seed, it, suf_dev);
+      },
+      [&](boomgpu_ctx *ctx, double *xtx, double *xty, double *scalars) {
+        int rc = boomgpu_set_logit_mixture(ctx, (int)mix.sigma.size(), mix.mu.data(), mix.sigma.data(), mix.weights.data());
+        if (rc) return rc;
+        int64_t ss = 0;
+        rc = boomgpu_logit_step(ctx, beta.data(), clt, seed, it, xtx, xty, &ss);
+        scalars[0] = (double)ss; scalars[1] = scalars[2] = scalars[3] = 0.0;
+        return rc;
+      });
   suf_.reset(packed_.data(), model_->xdim());
 }
 
@@ -968,15 +984,23 @@ void PoissonRegressionAuxMixSampler::impute_latent_data() {
                  "NormalMixtureApproximationTable (see boom_b200/data/poisson_mixture_table.json)");
   const uint64_t seed = device_seed_, it = iteration_++;
   const Vector &beta(model_->Beta());
-  run_device_step(*model_, packed_, [&](boomgpu_ctx *ctx, double *suf_dev) {
-    if (table_version_seen_ != t.version) {
-      int rc = boomgpu_set_poisson_table(ctx, (int)t.nu.size(), t.nu.data(), t.offset.data(), t.weights.data(), t.mu.data(),
-                                         t.sigma.data(), t.largest);
-      if (rc) return rc;
-      table_version_seen_ = t.version;
-    }
-    return boomgpu_poisson_step_device(ctx, beta.data(), seed, it, suf_dev);
-  });
+  auto ensure_table = [&](boomgpu_ctx *ctx) {
+    if (table_version_seen_ == t.version) return 0;
+    int rc = boomgpu_set_poisson_table(ctx, (int)t.nu.size(), t.nu.data(), t.offset.data(), t.weights.data(), t.mu.data(),
+                                       t.sigma.data(), t.largest);
+    if (!rc) table_version_seen_ = t.version;
+    return rc;
+  };
+  run_device_step(
+      *model_, packed_,
+      [&](boomgpu_ctx *ctx, double *suf_dev) {
+        if (int rc = ensure_table(ctx)) return rc;
+        return boomgpu_poisson_step_device(ctx, beta.data(), seed, it, suf_dev);
+      },
+      [&](boomgpu_ctx *ctx, double *xtwx, double *xtwy, double *scalars) {
+        if (int rc = ensure_table(ctx)) return rc;
+        return boomgpu_poisson_step(ctx, beta.data(), seed, it, xtwx, xtwy, scalars);
+      });
   suf_.reset(packed_.data(), model_->xdim());
 }
 void PoissonRegressionAuxMixSampler::draw_beta_given_complete_data() {
