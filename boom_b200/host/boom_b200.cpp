@@ -414,6 +414,10 @@ void WeightedRegSuf::add_data(const Vector &x, double y, double w) {
   sumw_ += w;
   sumlogw_ += std::log(w);
 }
+double *WeightedRegSuf::xtx_storage(int p) {
+  if (xtx_.dim != p) { xtx_ = SpdMatrix(p); xty_.assign(p, 0.0); }
+  return xtx_.a.data();
+}
 void WeightedRegSuf::reset(const double *packed, int p) {
   if (xtx_.dim != p) { xtx_ = SpdMatrix(p); xty_.assign(p, 0.0); }
   std::copy(packed, packed + (size_t)p * p, xtx_.a.begin());
@@ -838,19 +842,22 @@ PoissonTableStore &poisson_table_store() { static PoissonTableStore s; return s;
 // otherwise the synchronous C-ABI step does everything (native NCCL when a communicator is attached, and for p <= 64 on
 // one GPU the reduction writes straight into pinned host memory).
 template <class StepDeviceFn, class StepSyncFn>
-void run_device_step(GlmModelBase &model, Vector &packed, StepDeviceFn step_device, StepSyncFn step_sync) {
+void run_device_step(GlmModelBase &model, WeightedRegSuf &suf, Vector &packed, StepDeviceFn step_device, StepSyncFn step_sync) {
   DeviceData &dev(model.device_data());
   const int p = model.xdim();
   const int64_t len = boomgpu_suf_len(p);
-  packed.resize((size_t)len);
   if (model.allreduce()) {
+    packed.resize((size_t)len);
     double *suf_dev = nullptr;
     dev.check(boomgpu_suf_buffer(dev.ctx(), &suf_dev));
     dev.check(step_device(dev.ctx(), suf_dev));
     model.allreduce()(suf_dev, len);
     dev.check(boomgpu_download(dev.ctx(), suf_dev, packed.data(), len));
+    suf.reset(packed.data(), p);
   } else {
-    dev.check(step_sync(dev.ctx(), packed.data(), packed.data() + (size_t)p * p, packed.data() + (size_t)p * p + p));
+    double scalars[4] = {0, 0, 0, 0};
+    dev.check(step_sync(dev.ctx(), suf.xtx_storage(p), suf.xty_storage(), scalars));   // straight into the statistics object
+    suf.set_scalars(scalars[0], scalars[1], scalars[2], scalars[3]);
   }
 }
 }  // namespace
@@ -888,7 +895,7 @@ void BinomialLogitAuxmixSampler::impute_latent_data() {
   const uint64_t seed = device_seed_, it = iteration_++;
   const Vector &beta(model_->Beta());
   run_device_step(
-      *model_, packed_,
+      *model_, suf_, packed_,
       [&](boomgpu_ctx *ctx, double *suf_dev) {
         int rc = boomgpu_set_logit_mixture(ctx, (int)mix.sigma.size(), mix.mu.data(), mix.sigma.data(), mix.weights.data());
         if (rc) return rc;
@@ -902,7 +909,6 @@ void BinomialLogitAuxmixSampler::impute_latent_data() {
         scalars[0] = (double)ss; scalars[1] = scalars[2] = scalars[3] = 0.0;
         return rc;
       });
-  suf_.reset(packed_.data(), model_->xdim());
 }
 
 void BinomialLogitAuxmixSampler::draw_params() {
@@ -992,7 +998,7 @@ void PoissonRegressionAuxMixSampler::impute_latent_data() {
     return rc;
   };
   run_device_step(
-      *model_, packed_,
+      *model_, suf_, packed_,
       [&](boomgpu_ctx *ctx, double *suf_dev) {
         if (int rc = ensure_table(ctx)) return rc;
         return boomgpu_poisson_step_device(ctx, beta.data(), seed, it, suf_dev);
@@ -1001,7 +1007,6 @@ void PoissonRegressionAuxMixSampler::impute_latent_data() {
         if (int rc = ensure_table(ctx)) return rc;
         return boomgpu_poisson_step(ctx, beta.data(), seed, it, xtwx, xtwy, scalars);
       });
-  suf_.reset(packed_.data(), model_->xdim());
 }
 void PoissonRegressionAuxMixSampler::draw_beta_given_complete_data() {
   const int p = model_->xdim();

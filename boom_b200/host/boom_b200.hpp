@@ -334,6 +334,11 @@ class WeightedRegSuf {
   void update(const Vector &x, double weighted_value, double weight);  // BinomialLogitAuxmixSampler.cpp:61-67
   // bulk load of a device result (WeightedRegSuf::reset, WeightedRegressionModel.cpp:148-157)
   void reset(const double *packed, int p);
+  // in-place bulk load: the device step writes X'WX and X'Wz straight into this object's storage
+  // (at p = 4000 the matrix is 128 MB: every intermediate copy costs ~10 ms)
+  double *xtx_storage(int p);
+  double *xty_storage() { return xty_.data(); }
+  void set_scalars(double n, double yty, double sumw, double sumlogw) { n_ = n; yty_ = yty; sumw_ = sumw; sumlogw_ = sumlogw; }
   const SpdMatrix &xtx() const { return xtx_; }
   const Vector &xty() const { return xty_; }
   double n() const { return n_; }

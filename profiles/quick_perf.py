@@ -10,7 +10,6 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import boom_b200  # noqa: E402
-from oracle import oracle as O  # noqa: E402  (mixture constants only)
 
 CFG = {
     "c1": ("logit", 100_000, 20), "c2": ("poisson", 1_000_000, 50), "c3": ("logit", 10_000_000, 500),
@@ -54,12 +53,10 @@ def main():
         ctx = boom_b200.Context(0)
         ctx.set_option("timing", 1)
         if kind == "logit":
-            mix = O.logit_mixture()
-            ctx.set_logit_mixture(mix.mu, mix.sigma, mix.weights)
+            ctx.set_logit_mixture(*boom_b200.default_logit_mixture())
             ctx.adopt_binomial(n, p, X.data_ptr(), p, y.data_ptr(), aux.data_ptr(), keepalive=(X, y, aux))
         else:
-            tab = O.poisson_table()
-            ctx.set_poisson_table(tab.nu, tab.offset, tab.weights, tab.mu, tab.sigma, tab.gaussian_cutoff)
+            ctx.set_poisson_table(*boom_b200.poisson_mixture_table_arrays())
             ctx.adopt_poisson(n, p, X.data_ptr(), p, y.data_ptr(), aux.data_ptr(), keepalive=(X, y, aux))
         suf = torch.empty(ctx.suf_len(), dtype=torch.float64, device=dev)
         iters = 3 if n * p > 1e9 else 20
