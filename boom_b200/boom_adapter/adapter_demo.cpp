@@ -4,7 +4,7 @@
 // then attaches EITHER the reference sampler OR the B200 sampler with model->set_method(sampler) and calls
 // model->sample_posterior().  Prints one JSON line with the posterior summaries of both chains on the same
 // data; tests/test_gpu_adapter.py compares them within Monte Carlo error.
-//   usage: boom_adapter_demo <logit|spike|poisson|pspike> n p nonzero iters burn
+//   usage: boom_adapter_demo <logit|spike|poisson|pspike|mode|pmode> n p nonzero iters burn   (mode / pmode: find_posterior_mode)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -68,7 +68,7 @@ int main(int argc, char **argv) {
   const int n = atoi(argv[2]), p = atoi(argv[3]), nonzero = atoi(argv[4]), iters = atoi(argv[5]), burn = atoi(argv[6]);
   try {
     GlobalRng::rng.seed(20261017);
-    const bool poisson = kind == "poisson" || kind == "pspike";
+    const bool poisson = kind == "poisson" || kind == "pspike" || kind == "pmode";
     Vector beta(p, 0.0);
     beta[0] = poisson ? 0.5 : -1.0;
     for (int j = 1; j <= nonzero && j < p; ++j) beta[j] = (j % 2) ? 0.5 : -0.5;
@@ -84,6 +84,43 @@ int main(int argc, char **argv) {
     }
     NEW(MvnModel, slab)(Vector(p, 0.0), SpdMatrix(p, 1.0));
     NEW(VariableSelectionPrior, spike)(p, std::min(1.0, (nonzero + 1.0) / p));
+    if (kind == "mode" || kind == "pmode") {
+      // find_posterior_mode of both spike-and-slab samplers from the same start, on the model with the first
+      // nonzero + 1 coefficients included
+      Vector bref, bgpu;
+      double vref = 0, vgpu = 0;
+      for (int arm = 0; arm < 2; ++arm) {
+        if (kind == "mode") {
+          NEW(BinomialLogitModel, model)(p);
+          for (int i = 0; i < n; ++i) model->add_data(new BinomialRegressionData(ys[i], 1.0, xs[i]));
+          model->coef().drop_all();
+          for (int j = 0; j <= nonzero && j < p; ++j) model->coef().add(j);
+          if (arm == 0) {
+            NEW(BinomialLogitSpikeSlabSampler, s)(model.get(), slab, spike, 10);
+            s->find_posterior_mode(1e-9); bref = model->Beta(); vref = s->log_posterior_at_mode();
+          } else {
+            Ptr<B200::BinomialLogitSpikeSlabSampler> s(new B200::BinomialLogitSpikeSlabSampler(model.get(), slab, spike, 10));
+            s->find_posterior_mode(1e-9); bgpu = model->Beta(); vgpu = s->log_posterior_at_mode();
+          }
+        } else {
+          NEW(PoissonRegressionModel, model)(p);
+          for (int i = 0; i < n; ++i) model->add_data(new PoissonRegressionData((int64_t)ys[i], xs[i], 1.0));
+          model->coef().drop_all();
+          for (int j = 0; j <= nonzero && j < p; ++j) model->coef().add(j);
+          if (arm == 0) {
+            NEW(PoissonRegressionSpikeSlabSampler, s)(model.get(), slab, spike, 1);
+            s->find_posterior_mode(1e-9); bref = model->Beta(); vref = s->log_posterior_at_mode();
+          } else {
+            Ptr<B200::PoissonRegressionSpikeSlabSampler> s(new B200::PoissonRegressionSpikeSlabSampler(model.get(), slab, spike, 1));
+            s->find_posterior_mode(1e-9); bgpu = model->Beta(); vgpu = s->log_posterior_at_mode();
+          }
+        }
+      }
+      printf("{\"kind\": \"%s\", ", kind.c_str());
+      print_vec("reference_mode", bref); print_vec("b200_mode", bgpu);
+      printf("\"reference_log_posterior\": %.12g, \"b200_log_posterior\": %.12g}\n", vref, vgpu);
+      return 0;
+    }
     Summary ref, gpu;
     for (int arm = 0; arm < 2; ++arm) {
       if (!poisson) {

@@ -44,8 +44,7 @@ void DeviceImputerBase::set_device(int device) {
   stale_ = true;
 }
 
-void DeviceImputerBase::impute_latent_data() {
-  if (latent_data_fixed_) return;  // statistics are under external control (Imputer.hpp:282-299)
+void DeviceImputerBase::ensure_device_rows() {
   if (!ctx_) {
     if (boomgpu_create(&ctx_, device_)) report_error(std::string("boomgpu_create: ") + boomgpu_last_error(nullptr));
     stale_ = true;
@@ -60,6 +59,49 @@ void DeviceImputerBase::impute_latent_data() {
     check(boomgpu_set_row_offset(ctx_, row_offset_));
     stale_ = false;
   }
+}
+
+namespace {
+// SpikeSlabCore::find_posterior_mode works on a BOOM_B200::GlmModelBase: a proxy whose derivatives come from the adapter
+class DerivsProxy : public BOOM_B200::GlmModelBase {
+ public:
+  typedef std::function<double(const BOOM_B200::Vector &, BOOM_B200::Vector *, BOOM_B200::SpdMatrix *)> Fn;
+  DerivsProxy(int p, Fn f) : BOOM_B200::GlmModelBase(p, false), f_(std::move(f)) {}
+  double log_likelihood_derivs(const BOOM_B200::Vector &b, BOOM_B200::Vector *g, BOOM_B200::SpdMatrix *h) override { return f_(b, g, h); }
+
+ protected:
+  void upload(BOOM_B200::DeviceData &) override {}
+
+ private:
+  Fn f_;
+};
+}  // namespace
+
+bool DeviceImputerBase::find_mode(GlmCoefs &coef, const MvnBase &slab, const VariableSelectionPrior &spike, double epsilon,
+                                  double *value) {
+  ensure_device_rows();
+  const int p = xdim_;
+  DerivsProxy proxy(p, [&](const BOOM_B200::Vector &b, BOOM_B200::Vector *g, BOOM_B200::SpdMatrix *h) {
+    double ll = 0;
+    if (g) g->assign(p, 0.0);
+    if (h && h->dim != p) *h = BOOM_B200::SpdMatrix(p);
+    check(device_loglike_derivs(ctx_, b.data(), &ll, g ? g->data() : nullptr, h ? h->a.data() : nullptr));
+    return ll;
+  });
+  BOOM_B200::Selector g(p, false);
+  for (int i = 0; i < p; ++i) if (coef.inc()[i]) g.add(i);
+  proxy.coef().set_inc(g);
+  proxy.coef().set_Beta(to_host(coef.Beta()));
+  auto hslab = std::make_shared<BOOM_B200::MvnModel>(to_host(slab.mu()), to_host(slab.siginv()), true);
+  BOOM_B200::SpikeSlabCore core(hslab, to_host(spike), false);
+  const bool ok = core.find_posterior_mode(proxy, epsilon, value);
+  if (ok) coef.set_Beta(Vector(proxy.Beta().begin(), proxy.Beta().end()));
+  return ok;
+}
+
+void DeviceImputerBase::impute_latent_data() {
+  if (latent_data_fixed_) return;  // statistics are under external control (Imputer.hpp:282-299)
+  ensure_device_rows();
   const int64_t len = boomgpu_suf_len(xdim_);
   packed_.resize((size_t)len);
   double *suf_dev = nullptr;
@@ -155,6 +197,10 @@ int BinomialLogitAuxmixSampler::device_step(boomgpu_ctx *ctx, const double *beta
   return boomgpu_logit_step_device(ctx, beta, clt_threshold_, seed, iteration, suf_dev);
 }
 
+int BinomialLogitAuxmixSampler::device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) {
+  return boomgpu_binomial_loglike_derivs(ctx, beta, model_->log_alpha(), loglike, g, h);   // BinomialLogitModel.cpp:168
+}
+
 void BinomialLogitAuxmixSampler::draw() {
   impute_latent_data();
   draw_params();
@@ -182,6 +228,9 @@ void BinomialLogitSpikeSlabSampler::draw() {   // BinomialLogitSpikeSlabSampler.
   spike_slab_draw(model_->coef(), *slab_, *spike_, allow_model_selection_, max_flips_, false);
 }
 double BinomialLogitSpikeSlabSampler::logpri() const { return spike_slab_logpri(model_->coef(), *slab_, *spike_); }
+void BinomialLogitSpikeSlabSampler::find_posterior_mode(double epsilon) {
+  posterior_mode_found_ = find_mode(model_->coef(), *slab_, *spike_, epsilon, &log_posterior_at_mode_);
+}
 void BinomialLogitSpikeSlabSampler::set_spike(const Ptr<VariableSelectionPrior> &spike) {
   if ((int)spike->potential_nvars() != model_->xdim()) report_error("Spike does not match model dimension.");
   spike_ = spike;
@@ -244,6 +293,9 @@ int PoissonRegressionAuxMixSampler::device_step(boomgpu_ctx *ctx, const double *
                                                 double *suf_dev) {
   return boomgpu_poisson_step_device(ctx, beta, seed, iteration, suf_dev);
 }
+int PoissonRegressionAuxMixSampler::device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) {
+  return boomgpu_poisson_loglike_derivs(ctx, beta, loglike, g, h);
+}
 void PoissonRegressionAuxMixSampler::draw() {
   impute_latent_data();
   draw_beta_given_complete_data();
@@ -266,6 +318,16 @@ void PoissonRegressionSpikeSlabSampler::draw() {   // PoissonRegressionSpikeSlab
   spike_slab_draw(model_->coef(), *slab_, *spike_, allow_model_selection_, max_flips_, true);
 }
 double PoissonRegressionSpikeSlabSampler::logpri() const { return spike_slab_logpri(model_->coef(), *slab_, *spike_); }
+PoissonRegressionSpikeSlabSampler *PoissonRegressionSpikeSlabSampler::clone_to_new_host(Model *new_host) const {
+  auto *s = new PoissonRegressionSpikeSlabSampler(dynamic_cast<PoissonRegressionModel *>(new_host), slab_->clone(), spike_->clone(),
+                                                  1, rng());
+  s->allow_model_selection(allow_model_selection_);
+  s->limit_model_selection(max_flips_);
+  return s;
+}
+void PoissonRegressionSpikeSlabSampler::find_posterior_mode(double epsilon) {
+  find_mode(model_->coef(), *slab_, *spike_, epsilon, &log_posterior_at_mode_);
+}
 
 }  // namespace B200
 }  // namespace BOOM

@@ -33,6 +33,7 @@
 #include "Models/Glm/WeightedRegressionModel.hpp"
 #include "Models/MvnBase.hpp"
 #include "Models/PosteriorSamplers/PosteriorSampler.hpp"
+#include "cpputil/math_utils.hpp"
 
 #include "../host/boom_b200.hpp"
 
@@ -61,6 +62,12 @@ class DeviceImputerBase : public PosteriorSampler {
   virtual void pack_and_upload(boomgpu_ctx *ctx) = 0;   // walks model->dat()
   virtual int device_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *suf_dev) = 0;
   virtual const Vector &current_beta() const = 0;
+  // log likelihood with gradient / Hessian at a full coefficient vector, one device pass (boomgpu_*_loglike_derivs)
+  virtual int device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) = 0;
+  void ensure_device_rows();
+  // find_posterior_mode of the spike-and-slab samplers (BinomialLogitSpikeSlabSampler.cpp:147-177,
+  // PoissonRegressionSpikeSlabSampler.cpp:69-106): Newton-Raphson on the included coefficients, derivatives from the device
+  bool find_mode(GlmCoefs &coef, const MvnBase &slab, const VariableSelectionPrior &spike, double epsilon, double *value);
   void mark_stale() { stale_ = true; }
   void check(int rc) const;
   // host steps on suf_
@@ -98,6 +105,7 @@ class BinomialLogitAuxmixSampler : public DeviceImputerBase {
  protected:
   void pack_and_upload(boomgpu_ctx *ctx) override;
   int device_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *suf_dev) override;
+  int device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) override;
   const Vector &current_beta() const override { return model_->Beta(); }
   BinomialLogitModel *model_;
   Ptr<MvnBase> prior_;
@@ -118,12 +126,18 @@ class BinomialLogitSpikeSlabSampler : public BinomialLogitAuxmixSampler {
   void set_spike(const Ptr<VariableSelectionPrior> &spike);
   void set_slab(const Ptr<MvnBase> &slab);
   int xdim() const { return model_->xdim(); }
+  void find_posterior_mode(double epsilon = 1e-5) override;
+  bool can_find_posterior_mode() const override { return true; }
+  bool posterior_mode_found() const { return posterior_mode_found_; }
+  double log_posterior_at_mode() const { return log_posterior_at_mode_; }
 
  private:
   Ptr<MvnBase> slab_;
   Ptr<VariableSelectionPrior> spike_;
   bool allow_model_selection_ = true;
   int max_flips_ = -1;
+  bool posterior_mode_found_ = false;
+  double log_posterior_at_mode_ = negative_infinity();
 };
 
 class PoissonRegressionAuxMixSampler : public DeviceImputerBase {
@@ -139,6 +153,7 @@ class PoissonRegressionAuxMixSampler : public DeviceImputerBase {
  protected:
   void pack_and_upload(boomgpu_ctx *ctx) override;
   int device_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *suf_dev) override;
+  int device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) override;
   const Vector &current_beta() const override { return model_->Beta(); }
   PoissonRegressionModel *model_;
   Ptr<MvnBase> prior_;
@@ -153,12 +168,17 @@ class PoissonRegressionSpikeSlabSampler : public PoissonRegressionAuxMixSampler 
   double logpri() const override;
   void allow_model_selection(bool tf) { allow_model_selection_ = tf; }
   void limit_model_selection(int max_flips) { max_flips_ = max_flips; }
+  PoissonRegressionSpikeSlabSampler *clone_to_new_host(Model *new_host) const override;
+  void find_posterior_mode(double epsilon = 1e-5) override;
+  bool can_find_posterior_mode() const override { return true; }
+  double log_posterior_at_mode() const { return log_posterior_at_mode_; }
 
  private:
   Ptr<MvnBase> slab_;
   Ptr<VariableSelectionPrior> spike_;
   bool allow_model_selection_ = true;
   int max_flips_ = -1;
+  double log_posterior_at_mode_ = negative_infinity();
 };
 
 }  // namespace B200

@@ -804,6 +804,15 @@ bool SpikeSlabCore::find_posterior_mode(GlmModelBase &model, double epsilon, dou
   return false;
 }
 
+void SpikeSlabCore::set_spike(const std::shared_ptr<VariableSelectionPrior> &spike) {
+  if (!spike || spike->potential_nvars() != slab_->dim()) report_error("Spike does not match model dimension.");
+  spike_ = spike;
+}
+void SpikeSlabCore::set_slab(const std::shared_ptr<MvnBase> &slab) {
+  if (!slab || slab->dim() != spike_->potential_nvars()) report_error("Slab does not match model dimension.");
+  slab_ = slab;
+}
+
 double SpikeSlabCore::logpri(const GlmCoefs &coef) const {
   const Selector &g(coef.inc());
   double ans = spike_->logp(g);
@@ -942,6 +951,12 @@ double BinomialLogitSpikeSlabSampler::logpri() const { return core_.logpri(model
 void BinomialLogitSpikeSlabSampler::draw_model_indicators() { core_.draw_model_indicators(rng(), model_->coef(), suf()); }
 void BinomialLogitSpikeSlabSampler::draw_beta() { core_.draw_beta(rng(), model_->coef(), suf()); }
 double BinomialLogitSpikeSlabSampler::log_model_prob(const Selector &g) const { return core_.log_model_prob(g, suf()); }
+std::shared_ptr<BinomialLogitSpikeSlabSampler> BinomialLogitSpikeSlabSampler::clone_to_new_host(BinomialLogitModel *new_host) const {
+  auto s = std::make_shared<BinomialLogitSpikeSlabSampler>(new_host, core_.slab(), core_.spike(), clt_threshold(), rng());
+  s->allow_model_selection(core_.model_selection_allowed());
+  s->limit_model_selection(core_.max_flips());
+  return s;
+}
 void BinomialLogitSpikeSlabSampler::find_posterior_mode(double epsilon) {
   posterior_mode_found_ = core_.find_posterior_mode(*model_, epsilon, &log_posterior_at_mode_);
 }
@@ -1035,6 +1050,13 @@ void PoissonRegressionSpikeSlabSampler::draw() {
   core_.draw_beta(rng(), model_->coef(), suf_);
 }
 double PoissonRegressionSpikeSlabSampler::logpri() const { return core_.logpri(model_->coef()); }
+std::shared_ptr<PoissonRegressionSpikeSlabSampler> PoissonRegressionSpikeSlabSampler::clone_to_new_host(
+    PoissonRegressionModel *new_host) const {
+  auto s = std::make_shared<PoissonRegressionSpikeSlabSampler>(new_host, core_.slab(), core_.spike(), 1, rng());
+  s->allow_model_selection(core_.model_selection_allowed());
+  s->limit_model_selection(core_.max_flips());
+  return s;
+}
 void PoissonRegressionSpikeSlabSampler::find_posterior_mode(double epsilon) {
   core_.find_posterior_mode(*model_, epsilon, &log_posterior_at_mode_);
 }

@@ -367,6 +367,12 @@ class SpikeSlabCore {
   void allow_model_selection(bool tf) { allow_model_selection_ = tf; }
   void limit_model_selection(int max_flips) { max_flips_ = max_flips; }
   bool model_selection_allowed() const { return allow_model_selection_; }
+  int max_flips() const { return max_flips_; }
+  // BinomialLogitSpikeSlabSampler::set_spike / set_slab (.hpp:68-74): the dimension is checked against the other prior
+  void set_spike(const std::shared_ptr<VariableSelectionPrior> &spike);
+  void set_slab(const std::shared_ptr<MvnBase> &slab);
+  const std::shared_ptr<MvnBase> &slab() const { return slab_; }
+  const std::shared_ptr<VariableSelectionPrior> &spike() const { return spike_; }
   // Newton-Raphson (with step halving) on the included coefficients of log slab(beta_gamma) + log likelihood, the
   // objective of BinomialLogitSpikeSlabSampler::find_posterior_mode (.cpp:123-177) / PoissonRegressionSpikeSlabSampler
   // (.cpp:69-106); sets the model's included coefficients on success.  Returns false when gamma is empty or on failure.
@@ -430,6 +436,10 @@ class BinomialLogitSpikeSlabSampler : public BinomialLogitAuxmixSampler {
   double log_model_prob(const Selector &g) const;  // .cpp:88-117
   void allow_model_selection(bool tf) { core_.allow_model_selection(tf); }
   void limit_model_selection(int max_flips) { core_.limit_model_selection(max_flips); }
+  void set_spike(const std::shared_ptr<VariableSelectionPrior> &spike) { core_.set_spike(spike); }
+  void set_slab(const std::shared_ptr<MvnBase> &slab) { core_.set_slab(slab); prior_ = slab; }
+  // clone_to_new_host (.cpp:42-48): the same priors and settings on another model, seeded from this sampler's stream
+  std::shared_ptr<BinomialLogitSpikeSlabSampler> clone_to_new_host(BinomialLogitModel *new_host) const;
   int xdim() const { return model_->xdim(); }
   void find_posterior_mode(double epsilon = 1e-5);   // .cpp:147-177
   bool can_find_posterior_mode() const { return true; }
@@ -485,6 +495,7 @@ class PoissonRegressionSpikeSlabSampler : public PoissonRegressionAuxMixSampler 
   double logpri() const override;
   void allow_model_selection(bool tf) { core_.allow_model_selection(tf); }
   void limit_model_selection(int max_flips) { core_.limit_model_selection(max_flips); }
+  std::shared_ptr<PoissonRegressionSpikeSlabSampler> clone_to_new_host(PoissonRegressionModel *new_host) const;   // .cpp:44-50
   void find_posterior_mode(double epsilon = 1e-5);   // PoissonRegressionSpikeSlabSampler.cpp:69-106
   bool can_find_posterior_mode() const { return true; }
   double log_posterior_at_mode() const { return log_posterior_at_mode_; }

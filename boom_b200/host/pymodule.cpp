@@ -203,6 +203,9 @@ PYBIND11_MODULE(_host, m) {
         for (size_t i = 0; i < bits.size(); ++i) if (bits[i]) g.add((int)i);
         return s.log_model_prob(g);
       })
+      .def("set_spike", &BinomialLogitSpikeSlabSampler::set_spike)
+      .def("set_slab", &BinomialLogitSpikeSlabSampler::set_slab)
+      .def("clone_to_new_host", &BinomialLogitSpikeSlabSampler::clone_to_new_host, py::keep_alive<0, 2>())
       .def("find_posterior_mode", &BinomialLogitSpikeSlabSampler::find_posterior_mode, py::arg("epsilon") = 1e-5)
       .def_property_readonly("posterior_mode_found", &BinomialLogitSpikeSlabSampler::posterior_mode_found)
       .def_property_readonly("log_posterior_at_mode", &BinomialLogitSpikeSlabSampler::log_posterior_at_mode)
@@ -236,6 +239,7 @@ PYBIND11_MODULE(_host, m) {
            }),
            py::arg("model"), py::arg("slab"), py::arg("spike"), py::arg("number_of_threads") = 1,
            py::arg("seeding_rng") = std::ref(GlobalRng::rng), py::keep_alive<1, 2>())
+      .def("clone_to_new_host", &PoissonRegressionSpikeSlabSampler::clone_to_new_host, py::keep_alive<0, 2>())
       .def("find_posterior_mode", &PoissonRegressionSpikeSlabSampler::find_posterior_mode, py::arg("epsilon") = 1e-5)
       .def_property_readonly("log_posterior_at_mode", &PoissonRegressionSpikeSlabSampler::log_posterior_at_mode)
       .def("allow_model_selection", &PoissonRegressionSpikeSlabSampler::allow_model_selection)

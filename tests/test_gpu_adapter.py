@@ -53,3 +53,17 @@ def test_spike_slab_samplers_on_boom_models(kind, n, p, nonzero, iters):
     _agree(r, iters, burn, strong_only=True)
     inc = np.array(r["b200"]["inclusion"])
     assert np.all(inc[:nonzero + 1] > 0.9)    # the true variables are found
+
+
+@pytest.mark.parametrize("kind", ["mode", "pmode"])
+def test_find_posterior_mode_on_boom_models(kind):
+    """find_posterior_mode of the reference samplers (max_nd2_careful on BOOM's own derivatives) and of the B200 samplers
+    (Newton-Raphson on the device derivatives) reach the same mode and the same un-normalised log posterior."""
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/boom_adapter_demo not built")
+    out = subprocess.run([EXE, kind, "3000", "7", "3", "0", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    np.testing.assert_allclose(r["b200_mode"], r["reference_mode"], rtol=1e-5, atol=1e-6)
+    assert r["b200_log_posterior"] == pytest.approx(r["reference_log_posterior"], rel=1e-9)
+    assert np.count_nonzero(r["b200_mode"]) == 4

@@ -149,3 +149,25 @@ def test_bordered_flip_evaluator_matches_from_scratch():
                 if a:
                     g = g2
         assert vals[-1] == pytest.approx(h.log_model_prob(xtx, xty, slab, spike, g), rel=1e-12, abs=1e-10)
+
+
+def test_spike_slab_surface_setters_and_clone():
+    """set_spike / set_slab check dimensions (BinomialLogitSpikeSlabSampler.hpp:68-74, .cpp:224-240); clone_to_new_host carries
+    the priors and settings to another model (.cpp:42-48)."""
+    p = 4
+    m1, m2 = boom_b200.BinomialLogitModel(p), boom_b200.BinomialLogitModel(p)
+    slab = boom_b200.MvnModel(np.zeros(p), np.eye(p))
+    spike = boom_b200.VariableSelectionPrior(p, 0.3)
+    s = boom_b200.BinomialLogitSpikeSlabSampler(m1, slab, spike, 7, boom_b200.RNG(2))
+    s.limit_model_selection(2)
+    s.set_spike(boom_b200.VariableSelectionPrior(p, 0.5))
+    s.set_slab(boom_b200.MvnModel(np.ones(p), 2 * np.eye(p)))
+    with pytest.raises(RuntimeError, match="dimension"):
+        s.set_spike(boom_b200.VariableSelectionPrior(p + 1, 0.5))
+    with pytest.raises(RuntimeError, match="dimension"):
+        s.set_slab(boom_b200.MvnModel(np.zeros(p - 1), np.eye(p - 1)))
+    c = s.clone_to_new_host(m2)
+    assert c.clt_threshold == 7 and isinstance(c, boom_b200.BinomialLogitSpikeSlabSampler)
+    pm = boom_b200.PoissonRegressionModel(p)
+    ps = boom_b200.PoissonRegressionSpikeSlabSampler(pm, slab, spike, 1, boom_b200.RNG(3))
+    assert isinstance(ps.clone_to_new_host(boom_b200.PoissonRegressionModel(p)), boom_b200.PoissonRegressionSpikeSlabSampler)
