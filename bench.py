@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-array e2e leg (development aid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-allreduce", action="store_true",
+                    help="all-reduce through a torch.distributed hook instead of the library's own NCCL communicator")
     ap.add_argument("--rows", type=int, default=0, help="override n (development aid; the line then names the override)")
     args = ap.parse_args()
     kind, sampler, n, p, nonzero = WORKLOADS[args.workload]
@@ -198,7 +200,7 @@ def main():
     metric = "gibbs_iterations_per_sec"
     cfg = {"workload": DESCR[args.workload] + (" [rows overridden to %d]" % n if args.rows else ""), "n": n, "p": p,
            "true_nonzeros": nonzero, "sampler": sampler, "prior": "slab N(0, I); spike pi_j = %d/%d" % (nonzero, p)
-           if sampler == "spike" else "N(0, I)", "parallelism": "rows sharded over %d GPU(s), one all-reduce of p*p+p+4 doubles per iteration" % world}
+           if sampler == "spike" else "N(0, I)", "parallelism": "rows sharded over %d GPU(s), one NCCL all-reduce of p*p+p+4 doubles per iteration" % world}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -255,7 +257,7 @@ def main():
         else:
             s = boom_b200.PoissonRegressionAuxMixSampler(model, prior, 1, rng)
         model.set_method(s)
-        shard.attach(model, n, stream, dev, rank, world)
+        shard.attach(model, n, stream, dev, rank, world, native=not args.torch_allreduce)
         model.set_device_option("timing", 1)
         return s
 

@@ -1,12 +1,14 @@
 // kernels.cuh -- CUDA kernels of the auxiliary-mixture Gibbs hot path, written for sm_100a.
 //
-//   fused_small_kernel   p <= 64 : ONE pass over X. cp.async-staged row chunks in shared memory,
+//   (fused_tma_kernel    p <= 64 : the single-pass kernel in use, see fused_tma.cuh)
+//   fused_small_kernel   p <= 64 : its first version, kept for X that TMA cannot describe (odd leading dimension,
+//                        unaligned adopted pointer).  cp.async-staged row chunks in shared memory,
 //                        eta = x'beta, latent draw, weighted SYRK on FP64 DMMA with the whole upper
 //                        triangle of X'WX resident in registers.  HBM-bound (8 n (p+2) bytes).
 //   impute_rows_kernel   p  > 64 : pass 1, warp-per-row GEMV + latent draw -> (w_i, s_i).  HBM-bound.
 //   syrk_dmma_kernel     p  > 64 : pass 2, split-K weighted SYRK  X' diag(w) X  (upper triangle) and
-//                        X's on FP64 DMMA (mma.sync m8n8k4), X tiles staged by TMA bulk copies
-//                        (cp.async.bulk + mbarrier) through a 4-stage ring.  FP64-pipe-bound.
+//                        X's on FP64 DMMA (mma.sync m8n8k4), X tiles staged by TMA tensor tiles
+//                        (cp.async.bulk.tensor.2d + mbarrier) through a 6-stage ring.  FP64-pipe-bound.
 //   reduce_* kernels     deterministic (fixed order) reduction of the per-CTA partials.
 //
 // The reference equivalent of all of this is the per-observation loop

@@ -53,9 +53,11 @@ class StatisticsAllReduce:
         self.bytes += 8 * int(count)
 
 
-def attach(model, n_total, stream, device, rank=None, world=None, group=None):
+def attach(model, n_total, stream, device, rank=None, world=None, group=None, native=False):
     """Binds `model` (holding this rank's rows of an n_total-row data set) to its shard: device, stream,
-    global row offset and the all-reduce hook.  Returns (row0, row1, hook)."""
+    global row offset and the all-reduce.  native=False: a torch.distributed hook on the device buffer;
+    native=True: the library joins its own NCCL communicator (boomgpu_comm_init; the 128-byte id is made on rank 0 and
+    broadcast through torch.distributed) and all-reduces inside the C ABI step.  Returns (row0, row1, hook or None)."""
     import torch.distributed as dist
     if world is None:
         world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -66,7 +68,11 @@ def attach(model, n_total, stream, device, rank=None, world=None, group=None):
     model.set_row_offset(row0)
     model.set_stream(stream.cuda_stream)
     hook = None
-    if world > 1:
+    if world > 1 and native:
+        box = [type(model).comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        model.set_communicator(box[0], world, rank)
+    elif world > 1:
         hook = StatisticsAllReduce(stream, device, group)
         model.set_allreduce(hook)
     return row0, row1, hook

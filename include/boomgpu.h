@@ -72,6 +72,8 @@ int boomgpu_set_stream(boomgpu_ctx *ctx, void *cuda_stream);
 /* global index of this shard's first row: keys the Philox counters so draws do not depend on the sharding */
 int boomgpu_set_row_offset(boomgpu_ctx *ctx, uint64_t first_global_row);
 /* options: "path" = 0 auto | 1 fused single pass (p <= 64) | 2 two-pass imputer + DMMA SYRK;
+ *          "small_variant" = 0 auto (TMA-fed kernel when X has an even leading dimension and a 16-byte aligned base) |
+ *                            1 force the cp.async kernel;
  *          "timing" = 1 records CUDA events around every kernel (boomgpu_get_timings) */
 int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value);
 

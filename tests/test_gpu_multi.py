@@ -144,3 +144,48 @@ def test_native_nccl_allreduce_through_the_c_abi():
     assert res[0][3] == rss == n
     assert np.max(np.abs(res[0][1] - rxtx) / np.outer(d, d)) < 1e-11
     assert np.max(np.abs(res[0][2] - rxty)) < 1e-9 * np.max(np.abs(rxty))
+
+
+def _native_attach_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import boom_b200
+    from boom_b200 import distributed as shard
+    from oracle import oracle as O
+    try:
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world, device_id=dev)
+        n, p = 20_003, 10
+        X, y, nt, _ = O.synth_binomial(n, p, 3, seed=4)
+        row0, row1 = shard.shard_range(n, world, rank)
+        stream = torch.cuda.Stream(device=dev)
+        betas, sufs, ss = _chain(lambda: boom_b200.BinomialLogitModel(X[row0:row1], y[row0:row1], nt[row0:row1]), p, 8,
+                                 lambda m: shard.attach(m, n, stream, dev, rank, world, native=True))
+        assert ss == n
+        q.put((rank, betas, sufs))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, "FAIL: %r" % (e,), None))
+
+
+def test_sampler_surface_with_the_native_communicator():
+    """distributed.attach(native=True): the id travels through torch.distributed, the all-reduce runs inside the C ABI step."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_native_attach_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted((q.get(timeout=600) for _ in procs), key=lambda t: t[0])
+    for pr in procs:
+        pr.join(timeout=60)
+    assert not isinstance(res[0][1], str) and not isinstance(res[1][1], str), res
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    np.testing.assert_array_equal(res[0][2], res[1][2])
