@@ -202,22 +202,32 @@ int allreduce_on_stream(boomgpu_ctx *ctx, double *dev, int64_t count) {
 SyrkUnitTable make_unit_table() {
   SyrkUnitTable t;
   memset(&t, 0, sizeof(t));
-  // off-diagonal region: warp w owns units (w/2, 2(w%2)) and (w/2, 2(w%2)+1) (shared A fragments)
-  for (int w = 0; w < kSyrkConsumerWarps; ++w) {
-    t.u[0][w][0] = {(int8_t)(w / 2), (int8_t)(2 * (w % 2)), 1};
-    t.u[0][w][1] = {(int8_t)(w / 2), (int8_t)(2 * (w % 2) + 1), 1};
+  const int8_t V = 1, D = 2, Y = 4, F = 8;  // valid, diagonal unit, X's duty, fallback X's duty (when unit (ui, ui+1) is cut off by p)
+  if (kSyrkConsumerWarps == 8) {
+    // off-diagonal region: warp w owns units (w/2, 2(w%2)) and (w/2, 2(w%2)+1) (shared A fragments)
+    for (int w = 0; w < 8; ++w) {
+      t.u[0][w][0] = {(int8_t)(w / 2), (int8_t)(2 * (w % 2)), 1};
+      t.u[0][w][1] = {(int8_t)(w / 2), (int8_t)(2 * (w % 2) + 1), 1};
+    }
+    // diagonal region: 6 full units (16 DMMA / k-step), 4 diagonal units (10), balanced over the four SM
+    // sub-partitions (warp w issues on sub-partition w % 4): 36/36/36/36 + the DFMA of the X's duties.
+    t.u[1][0][0] = {0, 1, (int8_t)(V | Y)};
+    t.u[1][4][0] = {0, 0, (int8_t)(V | D | F)}; t.u[1][4][1] = {1, 1, (int8_t)(V | D | F)};
+    t.u[1][1][0] = {1, 2, (int8_t)(V | Y)};
+    t.u[1][5][0] = {0, 2, V};
+    t.u[1][2][0] = {2, 3, (int8_t)(V | Y)};
+    t.u[1][6][0] = {0, 3, V};
+    t.u[1][3][0] = {1, 3, V};
+    t.u[1][7][0] = {2, 2, (int8_t)(V | D | F)}; t.u[1][7][1] = {3, 3, (int8_t)(V | D | Y)};
+  } else {
+    // 16 warps x 1 unit.  Off-diagonal: warp w owns unit (w / 4, w % 4): 16 DMMA per k-step on every warp.
+    for (int w = 0; w < kSyrkConsumerWarps; ++w) t.u[0][w][0] = {(int8_t)(w / 4), (int8_t)(w % 4), 1};
+    // Diagonal: 10 of the 16 warps work; per sub-partition (w % 4): 32 / 32 / 36 / 36 DMMA per k-step.
+    t.u[1][0][0] = {0, 1, (int8_t)(V | Y)};  t.u[1][4][0] = {0, 2, V};
+    t.u[1][1][0] = {0, 3, V};                t.u[1][5][0] = {1, 2, (int8_t)(V | Y)};
+    t.u[1][2][0] = {1, 3, V};                t.u[1][6][0] = {0, 0, (int8_t)(V | D | F)};  t.u[1][10][0] = {1, 1, (int8_t)(V | D | F)};
+    t.u[1][3][0] = {2, 3, (int8_t)(V | Y)};  t.u[1][7][0] = {2, 2, (int8_t)(V | D | F)};  t.u[1][11][0] = {3, 3, (int8_t)(V | D | Y)};
   }
-  // diagonal region: 6 full units (16 DMMA / k-step), 4 diagonal units (10), 4 xty duties (+4),
-  // balanced over the four SM sub-partitions (warp w issues on sub-partition w % 4): 40/36/36/40.
-  const int8_t V = 1, D = 2, Y = 4, F = 8;  // F: fallback xty duty
-  t.u[1][0][0] = {0, 1, (int8_t)(V | Y)};
-  t.u[1][4][0] = {0, 0, (int8_t)(V | D | F)}; t.u[1][4][1] = {1, 1, (int8_t)(V | D | F)};
-  t.u[1][1][0] = {1, 2, (int8_t)(V | Y)};
-  t.u[1][5][0] = {0, 2, V};
-  t.u[1][2][0] = {2, 3, (int8_t)(V | Y)};
-  t.u[1][6][0] = {0, 3, V};
-  t.u[1][3][0] = {1, 3, V};
-  t.u[1][7][0] = {2, 2, (int8_t)(V | D | F)}; t.u[1][7][1] = {3, 3, (int8_t)(V | D | Y)};
   return t;
 }
 

@@ -453,8 +453,17 @@ impute_rows_kernel(RowData d, DrawParams prm, RowOut out, const double *__restri
 //   Per-CTA partial: 128 x 128 tile (+ 128 xty for diagonal regions), reduced by
 //   reduce_syrk_kernel in k-slice order (deterministic).
 // =============================================================================================
-constexpr int kSyrkConsumerWarps = 8;
-constexpr int kSyrkThreads = 32 * (kSyrkConsumerWarps + 4);  // + a producer warpgroup (1 TMA warp, 3 idle)
+// Consumer layout: 8 warps x 2 units (default) or 16 warps x 1 unit, plus a producer warpgroup that hands its registers
+// over with setmaxnreg.  Measured (profiles/README.md): 16 x 1 is no faster at p = 500 (8.38 vs 8.32 ms per 1 M rows) and
+// slower at p = 4000 (254 vs 239 ms per 0.5 M rows: one more fragment load per DMMA); repeating the arithmetic of every
+// stage on the same data scales the time linearly, so the kernel is bound by its own DMMA / LDS / DMUL stream (tensor
+// pipe 89 % active), not by the supply of tiles.
+#ifndef BOOMGPU_SYRK_WARPS
+#define BOOMGPU_SYRK_WARPS 8
+#endif
+constexpr int kSyrkConsumerWarps = BOOMGPU_SYRK_WARPS;
+constexpr int kSyrkProducerWarps = 4;   // a full warpgroup, so that setmaxnreg can move its registers to the consumers
+constexpr int kSyrkThreads = 32 * (kSyrkConsumerWarps + kSyrkProducerWarps);
 #ifndef BOOMGPU_SYRK_KB
 #define BOOMGPU_SYRK_KB 16
 #endif
@@ -677,14 +686,18 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap xmap, SyrkParams prm, SyrkU
     }
   };
   if (wid >= kSyrkConsumerWarps) {
-    // producer warpgroup: hands its registers to the consumers and never competes for the DMMA pipe
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    // producer warp(group): never competes for the DMMA pipe; as a full warpgroup it also hands its registers over
+    if (kSyrkConsumerWarps == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 24;\n");
     if (wid == kSyrkConsumerWarps) {
       for (int it = 0; it < nstages_total; ++it) produce(it);
     }
     return;
   }
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+  if (kSyrkConsumerWarps == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+  // what the 16 consumer warps take must fit what the 4 producer warps gave back to the CTA pool:
+  // 16 (112 - 96) <= 4 (96 - 24); asking for more (120) spins in USETMAXREG.TRY_ALLOC for ever
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
 
   // ===== consumer role: resolved ONCE per warp into compile-time unit types so that the k loop
   // carries no predicates (a predicated mma.sync costs a WARPSYNC + branch per instruction).
@@ -711,17 +724,28 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap xmap, SyrkParams prm, SyrkU
   wc.tile = prm.partials + ((int64_t)kslice * prm.nregions + region) * kSyrkTileLen;
 
   const int role = t0 * 100 + t1 * 10 + duty;
-  switch (role) {
-    case 0:   syrk_consume<0, 0, 0>(wc); break;
-    case 100: syrk_consume<1, 0, 0>(wc); break;
-    case 101: syrk_consume<1, 0, 1>(wc); break;
-    case 110: syrk_consume<1, 1, 0>(wc); break;
-    case 200: syrk_consume<2, 0, 0>(wc); break;
-    case 201: syrk_consume<2, 0, 1>(wc); break;
-    case 220: syrk_consume<2, 2, 0>(wc); break;
-    case 221: syrk_consume<2, 2, 1>(wc); break;
-    case 222: syrk_consume<2, 2, 2>(wc); break;
-    default: __trap();
+  if (kSyrkConsumerWarps == 8) {
+    switch (role) {
+      case 0:   syrk_consume<0, 0, 0>(wc); break;
+      case 100: syrk_consume<1, 0, 0>(wc); break;
+      case 101: syrk_consume<1, 0, 1>(wc); break;
+      case 110: syrk_consume<1, 1, 0>(wc); break;
+      case 200: syrk_consume<2, 0, 0>(wc); break;
+      case 201: syrk_consume<2, 0, 1>(wc); break;
+      case 220: syrk_consume<2, 2, 0>(wc); break;
+      case 221: syrk_consume<2, 2, 1>(wc); break;
+      case 222: syrk_consume<2, 2, 2>(wc); break;
+      default: __trap();
+    }
+  } else {   // one unit per warp: the two-unit roles are not instantiated (they would set the kernel's register count)
+    switch (role) {
+      case 0:   syrk_consume<0, 0, 0>(wc); break;
+      case 100: syrk_consume<1, 0, 0>(wc); break;
+      case 101: syrk_consume<1, 0, 1>(wc); break;
+      case 200: syrk_consume<2, 0, 0>(wc); break;
+      case 201: syrk_consume<2, 0, 1>(wc); break;
+      default: __trap();
+    }
   }
 }
 
