@@ -57,12 +57,12 @@ FP64_DMMA_PEAK_TFLOPS = 37.0   # measured on this pool's B200 (profiles/r01_micr
 HBM_FALLBACK_GBS = 6650.0
 # DRAM bytes per observation measured by ncu (read + write), keyed by (kernel, p); see profiles/README.md
 NCU_TRAFFIC_BYTES_PER_ROW = {
-    ("syrk_dmma_kernel", 500): (87.874330e9 + 0.420380e9) / 10_000_000,
-    ("fused_tma_kernel", 16): (7.200950e9 + 0.006381e9) / 50_000_000,
+    ("syrk_dmma_kernel", 500): (81.832943e9 + 0.419426e9) / 10_000_000,
+    ("fused_tma_kernel", 16): (28.812235e9 + 0.005138e9) / 200_000_000,
 }
 NCU_TRAFFIC_SOURCE = {
-    ("syrk_dmma_kernel", 500): "profiles/r01_syrk_c3.summary.txt (n=10M, p=500: 87.87 GB read + 0.42 GB written per launch)",
-    ("fused_tma_kernel", 16): "profiles/r01b_fused_c5.summary.txt (n=50M, p=16: 7.20 GB read per launch)",
+    ("syrk_dmma_kernel", 500): "profiles/r01f_syrk_c3.summary.txt (n=10M, p=500: 81.83 GB read + 0.42 GB written per launch)",
+    ("fused_tma_kernel", 16): "profiles/r01f_fused_c5.summary.txt (n=200M, p=16: 28.81 GB read per launch)",
 }
 
 

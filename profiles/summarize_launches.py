@@ -7,6 +7,9 @@ import csv
 import sys
 
 
+OURS = ("fused_small_kernel", "fused_tma_kernel", "impute_rows_kernel", "syrk_dmma_kernel", "reduce_", "loglike_kernel")
+
+
 def main():
     rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 5]
     hdr = rows[0]
@@ -16,7 +19,7 @@ def main():
     for r in rows[1:]:
         ms = float(r[vi].replace(",", "")) * scale.get(r[ui], 1e-6)
         name = r[ki].split("(")[0].replace("void ", "")
-        if "boomgpu::" in name:
+        if "boomgpu::" in name or any(k in name for k in OURS):
             ours.append((name, r[gi], r[bi], ms))
         else:
             other[0] += 1
