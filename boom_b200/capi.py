@@ -22,7 +22,7 @@ SYMBOLS = (
     "boomgpu_logit_step", "boomgpu_poisson_step", "boomgpu_suf_len", "boomgpu_logit_step_device",
     "boomgpu_poisson_step_device", "boomgpu_synchronize", "boomgpu_suf_buffer", "boomgpu_download", "boomgpu_accumulate", "boomgpu_logit_draw",
     "boomgpu_poisson_draw", "boomgpu_binomial_loglike", "boomgpu_poisson_loglike", "boomgpu_binomial_loglike_derivs",
-    "boomgpu_poisson_loglike_derivs", "boomgpu_comm_unique_id", "boomgpu_comm_init", "boomgpu_comm_destroy", "boomgpu_allreduce", "boomgpu_kernel_launches",
+    "boomgpu_poisson_loglike_derivs", "boomgpu_pin_host", "boomgpu_unpin_host", "boomgpu_comm_unique_id", "boomgpu_comm_init", "boomgpu_comm_destroy", "boomgpu_allreduce", "boomgpu_kernel_launches",
     "boomgpu_get_timings",
 )
 
@@ -153,6 +153,21 @@ class Context:
         self.n, self.p = n, p
         self._keep = list(keepalive)
 
+    @staticmethod
+    def pin_host(array):
+        """Page-locks a numpy array's buffer (boomgpu_pin_host); pair with unpin_host."""
+        lib = load_library()
+        rc = lib.boomgpu_pin_host(C.c_void_p(array.ctypes.data), C.c_uint64(array.nbytes))
+        if rc:
+            raise BoomGpuError(lib.boomgpu_last_error(None).decode())
+
+    @staticmethod
+    def unpin_host(array):
+        lib = load_library()
+        rc = lib.boomgpu_unpin_host(C.c_void_p(array.ctypes.data))
+        if rc:
+            raise BoomGpuError(lib.boomgpu_last_error(None).decode())
+
     # ---- multi-GPU (NCCL bound at run time inside the library)
     @staticmethod
     def comm_unique_id():
@@ -173,10 +188,14 @@ class Context:
         self._check(self._lib.boomgpu_allreduce(self._h, C.c_void_p(dev_ptr), C.c_int64(int(count))))
 
     # ---- hot path
-    def logit_step(self, beta, clt_threshold, seed, iteration):
+    def logit_step(self, beta, clt_threshold, seed, iteration, xtx=None):
+        """xtx: optional preallocated (p, p) float64 array; when it is page-locked (pin_host) and at least 1 MB the matrix
+        is copied device->host straight into it."""
         p = self.p
         beta = _f64(beta)
-        xtx = np.empty((p, p))
+        if xtx is None:
+            xtx = np.empty((p, p))
+        assert xtx.shape == (p, p) and xtx.dtype == np.float64 and xtx.flags.c_contiguous
         xty = np.empty(p)
         ss = C.c_int64()
         self._check(self._lib.boomgpu_logit_step(self._h, _dp(beta), C.c_int(clt_threshold), C.c_uint64(seed),

@@ -552,11 +552,20 @@ int finish_and_check(boomgpu_ctx *ctx) {
   return 0;
 }
 
-// statistics of the step just launched -> suf_pin, then wait and report device-side validation errors.
-// Single GPU + small-p kernel: the reduction already wrote them (and the flag) into the host-mapped suf_pin.
-int fetch_suf(boomgpu_ctx *ctx) {
+bool is_pinned_host(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// statistics of the step just launched -> host, then wait and report device-side validation errors.
+//   * single GPU + small-p kernel: the reduction already wrote them (and the flag) into the host-mapped suf_pin;
+//   * xtx_direct (a page-locked destination for the p x p matrix, large p): the matrix is copied straight into it and
+//     only the [p | 4] tail goes through suf_pin; *matrix_in_place tells the caller not to copy the matrix again.
+int fetch_suf(boomgpu_ctx *ctx, double *xtx_direct = nullptr, bool *matrix_in_place = nullptr) {
   const int p = ctx->p;
   const int64_t len = boomgpu_suf_len(p);
+  if (matrix_in_place) *matrix_in_place = false;
   if (ctx->host_out_written) {
     CU(cudaStreamSynchronize(ctx->stream));
     const int flag = (int)ctx->suf_pin[len];
@@ -568,6 +577,13 @@ int fetch_suf(boomgpu_ctx *ctx) {
                   "or a non-finite linear predictor");
     }
     return 0;
+  }
+  const size_t mat = (size_t)p * p;
+  if (xtx_direct && mat * sizeof(double) >= ((size_t)1 << 20) && is_pinned_host(xtx_direct)) {
+    CU(cudaMemcpyAsync(xtx_direct, ctx->suf_dev, sizeof(double) * mat, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->suf_pin + mat, ctx->suf_dev + mat, sizeof(double) * (size_t)(p + 4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (matrix_in_place) *matrix_in_place = true;
+    return finish_and_check(ctx);
   }
   CU(cudaMemcpyAsync(ctx->suf_pin, ctx->suf_dev, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, ctx->stream));
   return finish_and_check(ctx);
@@ -935,6 +951,19 @@ int boomgpu_set_poisson_table(boomgpu_ctx *ctx, int ntab, const int64_t *nu, con
   return 0;
 }
 
+int boomgpu_pin_host(void *ptr, uint64_t bytes) {
+  if (!ptr || !bytes) return fail(nullptr, BOOMGPU_ERR_ARG, "boomgpu_pin_host: null range");
+  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, BOOMGPU_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e)); }
+  return 0;
+}
+int boomgpu_unpin_host(void *ptr) {
+  if (!ptr) return 0;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, BOOMGPU_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e)); }
+  return 0;
+}
+
 int64_t boomgpu_suf_len(int p) { return (int64_t)p * p + p + 4; }
 
 int boomgpu_logit_step_device(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
@@ -995,9 +1024,10 @@ int boomgpu_logit_step(boomgpu_ctx *ctx, const double *beta, int clt_threshold, 
                                 sharded ? nullptr : ctx->suf_pin))
     return rc;
   if (int rc = allreduce_on_stream(ctx, ctx->suf_dev, boomgpu_suf_len(ctx->p))) return rc;
-  if (int rc = fetch_suf(ctx)) return rc;
+  bool in_place = false;
+  if (int rc = fetch_suf(ctx, xtx, &in_place)) return rc;
   const int p = ctx->p;
-  memcpy(xtx, ctx->suf_pin, sizeof(double) * (size_t)p * p);
+  if (!in_place) memcpy(xtx, ctx->suf_pin, sizeof(double) * (size_t)p * p);
   memcpy(xty, ctx->suf_pin + (size_t)p * p, sizeof(double) * p);
   if (sample_size) *sample_size = (int64_t)llround(ctx->suf_pin[(size_t)p * p + p]);
   return 0;
@@ -1015,9 +1045,10 @@ int boomgpu_poisson_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, ui
                                   sharded ? nullptr : ctx->suf_pin))
     return rc;
   if (int rc = allreduce_on_stream(ctx, ctx->suf_dev, boomgpu_suf_len(ctx->p))) return rc;
-  if (int rc = fetch_suf(ctx)) return rc;
+  bool in_place = false;
+  if (int rc = fetch_suf(ctx, xtwx, &in_place)) return rc;
   const int p = ctx->p;
-  memcpy(xtwx, ctx->suf_pin, sizeof(double) * (size_t)p * p);
+  if (!in_place) memcpy(xtwx, ctx->suf_pin, sizeof(double) * (size_t)p * p);
   memcpy(xtwy, ctx->suf_pin + (size_t)p * p, sizeof(double) * p);
   if (scalars) memcpy(scalars, ctx->suf_pin + (size_t)p * p + p, sizeof(double) * 4);
   return 0;

@@ -414,12 +414,28 @@ void WeightedRegSuf::add_data(const Vector &x, double y, double w) {
   sumw_ += w;
   sumlogw_ += std::log(w);
 }
+WeightedRegSuf::~WeightedRegSuf() { unpin(); }
+void WeightedRegSuf::unpin() {
+  if (pinned_) { boomgpu_unpin_host(pinned_); pinned_ = nullptr; }
+}
+WeightedRegSuf &WeightedRegSuf::operator=(const WeightedRegSuf &rhs) {
+  if (this != &rhs) {
+    if (rhs.xtx_.a.size() != xtx_.a.size()) unpin();   // the assignment below may reallocate
+    xtx_ = rhs.xtx_; xty_ = rhs.xty_;
+    n_ = rhs.n_; yty_ = rhs.yty_; sumw_ = rhs.sumw_; sumlogw_ = rhs.sumlogw_;
+    if (pinned_ && pinned_ != xtx_.a.data()) unpin();
+  }
+  return *this;
+}
 double *WeightedRegSuf::xtx_storage(int p) {
-  if (xtx_.dim != p) { xtx_ = SpdMatrix(p); xty_.assign(p, 0.0); }
+  if (xtx_.dim != p) { unpin(); xtx_ = SpdMatrix(p); xty_.assign(p, 0.0); }
+  // from 1 MB up the device->host copy of the matrix lands here directly: page-lock the storage once
+  const size_t bytes = xtx_.a.size() * sizeof(double);
+  if (!pinned_ && bytes >= ((size_t)1 << 20) && boomgpu_pin_host(xtx_.a.data(), bytes) == 0) pinned_ = xtx_.a.data();
   return xtx_.a.data();
 }
 void WeightedRegSuf::reset(const double *packed, int p) {
-  if (xtx_.dim != p) { xtx_ = SpdMatrix(p); xty_.assign(p, 0.0); }
+  if (xtx_.dim != p) { unpin(); xtx_ = SpdMatrix(p); xty_.assign(p, 0.0); }
   std::copy(packed, packed + (size_t)p * p, xtx_.a.begin());
   std::copy(packed + (size_t)p * p, packed + (size_t)p * p + p, xty_.begin());
   const double *sc = packed + (size_t)p * p + p;

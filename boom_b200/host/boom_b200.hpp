@@ -328,6 +328,10 @@ class PosteriorSampler {
 class WeightedRegSuf {
  public:
   explicit WeightedRegSuf(int p = 0) : xtx_(p), xty_(p, 0.0) {}
+  WeightedRegSuf(const WeightedRegSuf &rhs) : xtx_(rhs.xtx_), xty_(rhs.xty_), n_(rhs.n_), yty_(rhs.yty_), sumw_(rhs.sumw_),
+                                              sumlogw_(rhs.sumlogw_) {}   // a copy is never page-locked
+  WeightedRegSuf &operator=(const WeightedRegSuf &rhs);
+  ~WeightedRegSuf();
   void clear();
   // rank-1 update on the host: the path state-space callers drive (fix_latent_data(true))
   void add_data(const Vector &x, double y, double w);            // WeightedRegressionModel.cpp:161-169
@@ -348,9 +352,11 @@ class WeightedRegSuf {
   int64_t sample_size() const { return (int64_t)(n_ + 0.5); }
 
  private:
+  void unpin();
   SpdMatrix xtx_;
   Vector xty_;
   double n_ = 0, yty_ = 0, sumw_ = 0, sumlogw_ = 0;
+  double *pinned_ = nullptr;   // xtx_'s storage while it is page-locked for direct device->host copies (large p)
 };
 typedef WeightedRegSuf SufficientStatistics;
 

@@ -104,6 +104,12 @@ int boomgpu_logit_step(boomgpu_ctx *ctx, const double *beta, int clt_threshold, 
 int boomgpu_poisson_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration,
                          double *xtwx, double *xtwy, double scalars[4]);
 
+/* Page-locks a caller-owned host range (cudaHostRegister).  When the xtx / xtwx argument of the synchronous steps points
+ * into such a range, the p x p matrix is copied device->host straight into it (at p = 4000 it is 128 MB: the staging
+ * copy it saves costs ~15 ms per iteration and per rank).  ctx-free: errors are reported through boomgpu_last_error(NULL). */
+int boomgpu_pin_host(void *ptr, uint64_t bytes);
+int boomgpu_unpin_host(void *ptr);
+
 /* Asynchronous variants: the packed statistics stay in HBM at suf_dev (device pointer,
  * boomgpu_suf_len(p) doubles: [p*p matrix | p vector | 4 scalars]; logit scalars = {sample_size,0,0,0}),
  * ready for an in-place all-reduce on the same stream.  beta is a HOST pointer. */

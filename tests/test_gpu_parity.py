@@ -279,3 +279,23 @@ def test_loglike_derivatives_golden(golden):
     np.testing.assert_allclose(gr, g["poisson_gradient"], rtol=1e-11, atol=1e-11)
     np.testing.assert_allclose(h, np.array(g["poisson_hessian"]).reshape(p, p), rtol=1e-11, atol=1e-11)
     ctx.close()
+
+
+def test_matrix_lands_directly_in_page_locked_host_memory():
+    """Large p: when the caller's X'WX buffer is page-locked the matrix is copied device->host straight into it
+    (no staging copy); the result is bit-identical to the staged path."""
+    import boom_b200
+    n, p = 3000, 400          # p * p * 8 = 1.28 MB >= the 1 MB threshold
+    X, y, nt, beta = O.synth_binomial(n, p, 5, seed=90)
+    ctx, _ = logit_ctx(X, y, nt)
+    ref_xtx, ref_xty, ref_ss = ctx.logit_step(beta, 10, seed=4, iteration=1)
+    out = np.full((p, p), np.nan)
+    boom_b200.Context.pin_host(out)
+    try:
+        xtx, xty, ss = ctx.logit_step(beta, 10, seed=4, iteration=1, xtx=out)
+    finally:
+        boom_b200.Context.unpin_host(out)
+    assert xtx is out and ss == ref_ss
+    np.testing.assert_array_equal(out, ref_xtx)
+    np.testing.assert_array_equal(xty, ref_xty)
+    ctx.close()
