@@ -8,9 +8,10 @@
 //   producer warp and no "empty" barrier.
 //   Per slice, lane r owns observation r:  eta = x_r . beta from shared memory (conflict free: the row stride is
 //   4 mod 8 doubles and the start column is rotated by (r >> 2) & 3), the latent draw (Philox keyed by the global
-//   row), then the warp accumulates its 32 rank-1 updates with FP64 DMMA (m8n8k4; A = w_k x_k fragments, B = x_k
-//   fragments straight from the slice, w_k by shuffle) into the upper triangle of X'WX held in registers
-//   (NB (NB + 1) / 2 atoms), and X'Wz with NB DFMA per 4 rows.
+//   row; y_r / n_r were fetched one slice ahead), then the warp accumulates its 32 rank-1 updates with FP64 DMMA
+//   (m8n8k4; A = w_k x_k fragments, B = x_k fragments straight from the slice; (w_k, s_k) sit in the two pad columns
+//   of row k) into the upper triangle of X'WX held in registers (NB (NB + 1) / 2 atoms), and X'Wz with NB DFMA per
+//   4 rows.  beta arrives as a kernel parameter.
 //   Epilogue: warps add their fragments into one shared tile in warp order, the CTA writes one partial, and
 //   reduce_partials_kernel sums the partials in CTA order (deterministic: no floating point atomics).
 //
