@@ -4,7 +4,8 @@
 // then attaches EITHER the reference sampler OR the B200 sampler with model->set_method(sampler) and calls
 // model->sample_posterior().  Prints one JSON line with the posterior summaries of both chains on the same
 // data; tests/test_gpu_adapter.py compares them within Monte Carlo error.
-//   usage: boom_adapter_demo <logit|spike|poisson|pspike|mode|pmode> n p nonzero iters burn   (mode / pmode: find_posterior_mode)
+//   usage: boom_adapter_demo <logit|spike|poisson|pspike|mode|pmode|fixed|pfixed> n p nonzero iters burn
+//          (mode / pmode: find_posterior_mode; fixed / pfixed: externally driven statistics, host steps only, no GPU)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -68,7 +69,7 @@ int main(int argc, char **argv) {
   const int n = atoi(argv[2]), p = atoi(argv[3]), nonzero = atoi(argv[4]), iters = atoi(argv[5]), burn = atoi(argv[6]);
   try {
     GlobalRng::rng.seed(20261017);
-    const bool poisson = kind == "poisson" || kind == "pspike" || kind == "pmode";
+    const bool poisson = kind == "poisson" || kind == "pspike" || kind == "pmode" || kind == "pfixed";
     Vector beta(p, 0.0);
     beta[0] = poisson ? 0.5 : -1.0;
     for (int j = 1; j <= nonzero && j < p; ++j) beta[j] = (j % 2) ? 0.5 : -0.5;
@@ -119,6 +120,49 @@ int main(int argc, char **argv) {
       printf("{\"kind\": \"%s\", ", kind.c_str());
       print_vec("reference_mode", bref); print_vec("b200_mode", bgpu);
       printf("\"reference_log_posterior\": %.12g, \"b200_log_posterior\": %.12g}\n", vref, vgpu);
+      return 0;
+    }
+    if (kind == "fixed" || kind == "pfixed") {
+      // The state-space callers' mode (fix_latent_data(true), statistics pushed from outside): both samplers run their
+      // host steps only -- no device needed -- on the SAME externally driven complete-data statistics.
+      Summary out[2];
+      for (int arm = 0; arm < 2; ++arm) {
+        RNG seeder(arm == 0 ? 31 : 32), data_rng(77);
+        auto push = [&](auto &sampler) {
+          sampler->fix_latent_data(true);
+          sampler->clear_complete_data_sufficient_statistics();
+          for (int i = 0; i < n; ++i) {
+            const double w = 0.1 + runif_mt(data_rng), z = xs[i].dot(beta) + rnorm_mt(data_rng) / sqrt(w);
+            sampler->update_complete_data_sufficient_statistics(w * z, w, xs[i]);
+          }
+        };
+        if (kind == "fixed") {
+          NEW(BinomialLogitModel, model)(p);
+          model->coef().drop_all(); model->coef().add(0);
+          if (arm == 0) {
+            NEW(BinomialLogitSpikeSlabSampler, s)(model.get(), slab, spike, 10, seeder);
+            push(s); model->set_method(s); out[arm] = run(model, iters, burn);
+          } else {
+            Ptr<B200::BinomialLogitSpikeSlabSampler> s(new B200::BinomialLogitSpikeSlabSampler(model.get(), slab, spike, 10, seeder));
+            push(s); model->set_method(s); out[arm] = run(model, iters, burn);
+          }
+        } else {
+          NEW(PoissonRegressionModel, model)(p);
+          model->coef().drop_all(); model->coef().add(0);
+          if (arm == 0) {
+            NEW(PoissonRegressionSpikeSlabSampler, s)(model.get(), slab, spike, 1, seeder);
+            push(s); model->set_method(s); out[arm] = run(model, iters, burn);
+          } else {
+            Ptr<B200::PoissonRegressionSpikeSlabSampler> s(new B200::PoissonRegressionSpikeSlabSampler(model.get(), slab, spike, 1, seeder));
+            push(s); model->set_method(s); out[arm] = run(model, iters, burn);
+          }
+        }
+      }
+      printf("{\"kind\": \"%s\", \"n\": %d, \"p\": %d, \"iters\": %d, \"burn\": %d, ", kind.c_str(), n, p, iters, burn);
+      print_vec("beta_true", beta);
+      print_summary("reference", out[0]); printf(", ");
+      print_summary("b200", out[1]);
+      printf("}\n");
       return 0;
     }
     Summary ref, gpu;
