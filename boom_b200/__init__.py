@@ -43,6 +43,8 @@ def host():
 
 def __getattr__(name):
     if name in _HOST_NAMES:
+        if name.startswith("PoissonRegression") and name.endswith("Sampler") and not host().poisson_mixture_table_is_set():
+            load_poisson_mixture_table()   # the reference's table ships with the package: install it on first use
         return getattr(host(), name)
     raise AttributeError(name)
 

@@ -96,6 +96,7 @@ PYBIND11_MODULE(_host, m) {
       .def("__call__", [](RNG &r) { return r(); });
   m.def("global_rng", []() -> RNG & { return GlobalRng::rng; }, py::return_value_policy::reference);
   m.def("set_logit_mixture", [](const NpD &mu, const NpD &sigma, const NpD &w) { set_logit_mixture(to_vec(mu), to_vec(sigma), to_vec(w)); });
+  m.def("poisson_mixture_table_is_set", []() { return PoissonRegressionAuxMixSampler::mixture_table_is_set(); });
   m.def("set_poisson_mixture_table", [](const NpD &ser, int64_t largest) {
     PoissonRegressionAuxMixSampler::set_mixture_table(to_vec(ser), largest);
   });
