@@ -161,7 +161,7 @@ __device__ __forceinline__ RowLatent impute_row(const RowData &d, const DrawPara
 // Shared memory row stride LDS = 8 NB + 4 doubles: LDS = 4 (mod 8) makes the DMMA fragment loads
 // (4 rows x 8 columns per instruction) conflict free; the eta loop rotates its start column by
 // (r >> 2) & 3 to be conflict free with the same stride.
-// Per-CTA partial: [P8*P8 tile | P8 xty | 8 scalars], reduced by reduce_small_kernel.
+// Per-CTA partial: [P8*P8 tile | P8 xty | 8 scalars], reduced by reduce_partials_kernel (fused_tma.cuh).
 // =============================================================================================
 constexpr int kSmallThreads = 256;
 __host__ __device__ constexpr int small_rows(int nb) { return nb <= 4 ? 256 : 128; }
@@ -327,34 +327,6 @@ fused_small_kernel(RowData d, DrawParams prm, RowOut out, const double *__restri
     double s = 0;
     for (int w = 0; w < 8; ++w) s += red_s[w * 4 + tid];
     my[P8 * P8 + P8 + tid] = s;
-  }
-}
-
-// suf layout: [p*p | p | 4]; sums the per-CTA partials in CTA order and writes BOTH triangles.
-__global__ void reduce_small_kernel(const double *__restrict__ partials, int nparts, int nb, int p, double *__restrict__ suf) {
-  const int P8 = 8 * nb;
-  const int64_t plen = small_partial_len(nb);
-  const int total = p * p + p + 4;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    int64_t src;
-    bool skip = false;
-    int a = 0, b = 0;
-    if (e < p * p) {
-      a = e / p; b = e - a * p;
-      if (a > b) skip = true;
-      src = (int64_t)a * P8 + b;
-    } else {
-      src = (int64_t)P8 * P8 + (e - p * p < p ? (e - p * p) : P8 + (e - p * p - p));
-    }
-    if (skip) continue;
-    double s = 0;
-    for (int c = 0; c < nparts; ++c) s += partials[c * plen + src];
-    if (e < p * p) {
-      suf[a + (int64_t)b * p] = s;
-      suf[b + (int64_t)a * p] = s;
-    } else {
-      suf[e] = s;
-    }
   }
 }
 
