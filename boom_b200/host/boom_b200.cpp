@@ -5,6 +5,7 @@
 #include <cmath>
 #include <limits>
 #include <mutex>
+#include <thread>
 #include <sstream>
 
 #include "../../include/boomgpu.h"
@@ -37,20 +38,112 @@ double rnorm_mt(RNG &rng, double mu, double sd) {
 int random_int_mt(RNG &rng, int lo, int hi) { return (int)std::floor(runif_mt(rng, lo, hi + 1)); }
 
 // ---------------------------------------------------------------------------------------------
+// ---- Cholesky ---------------------------------------------------------------------------------
+// Left-looking, blocked, row major (every inner product runs over contiguous memory).  For block column J:
+//   (1) A[i][J] -= L[i][0:jb] . L[J][0:jb]'   for all rows i >= jb  -- p^3 / 3 of the flops, as 4 x 4 register tiles of
+//       dot products (vectorised over k; AVX-512 / AVX2 clones chosen at load time), split over threads when large;
+//   (2) unblocked factorisation of the diagonal block;  (3) triangular solve of the rows below it.
+// The full-model beta draw needs it at p = 500 (42 MFLOP) to p = 4000 (21 GFLOP); the reference leans on Eigen's LLT.
+namespace {
+constexpr int kCholBlock = 64;
+
+// C[i][j] -= sum_k A[i][k] B[j][k]  for i in [0, mi), j in [0, nj): rows of A, B and C are lda / ldb / ldc apart
+__attribute__((target_clones("avx512f", "avx2,fma", "default")))
+void gemm_nt_minus(int mi, int nj, int kk, const double *A, size_t lda, const double *B, size_t ldb, double *C, size_t ldc,
+                   bool lower_only, int i_off, int j_off) {
+  for (int i0 = 0; i0 < mi; i0 += 4) {
+    const int ib = std::min(4, mi - i0);
+    for (int j0 = 0; j0 < nj; j0 += 4) {
+      if (lower_only && j_off + j0 > i_off + i0 + ib - 1) break;   // the tile lies strictly above the diagonal
+      const int jb = std::min(4, nj - j0);
+      if (ib == 4 && jb == 4) {
+        const double *a0 = A + (size_t)i0 * lda, *a1 = a0 + lda, *a2 = a1 + lda, *a3 = a2 + lda;
+        const double *b0 = B + (size_t)j0 * ldb, *b1 = b0 + ldb, *b2 = b1 + ldb, *b3 = b2 + ldb;
+        double c00 = 0, c01 = 0, c02 = 0, c03 = 0, c10 = 0, c11 = 0, c12 = 0, c13 = 0;
+        double c20 = 0, c21 = 0, c22 = 0, c23 = 0, c30 = 0, c31 = 0, c32 = 0, c33 = 0;
+#pragma omp simd reduction(+ : c00, c01, c02, c03, c10, c11, c12, c13, c20, c21, c22, c23, c30, c31, c32, c33)
+        for (int k = 0; k < kk; ++k) {
+          const double x0 = a0[k], x1 = a1[k], x2 = a2[k], x3 = a3[k];
+          const double y0 = b0[k], y1 = b1[k], y2 = b2[k], y3 = b3[k];
+          c00 += x0 * y0; c01 += x0 * y1; c02 += x0 * y2; c03 += x0 * y3;
+          c10 += x1 * y0; c11 += x1 * y1; c12 += x1 * y2; c13 += x1 * y3;
+          c20 += x2 * y0; c21 += x2 * y1; c22 += x2 * y2; c23 += x2 * y3;
+          c30 += x3 * y0; c31 += x3 * y1; c32 += x3 * y2; c33 += x3 * y3;
+        }
+        double *c = C + (size_t)i0 * ldc + j0;
+        c[0] -= c00; c[1] -= c01; c[2] -= c02; c[3] -= c03; c += ldc;
+        c[0] -= c10; c[1] -= c11; c[2] -= c12; c[3] -= c13; c += ldc;
+        c[0] -= c20; c[1] -= c21; c[2] -= c22; c[3] -= c23; c += ldc;
+        c[0] -= c30; c[1] -= c31; c[2] -= c32; c[3] -= c33;
+      } else {
+        for (int i = 0; i < ib; ++i)
+          for (int j = 0; j < jb; ++j) {
+            const double *ar = A + (size_t)(i0 + i) * lda, *br = B + (size_t)(j0 + j) * ldb;
+            double acc = 0;
+            for (int k = 0; k < kk; ++k) acc += ar[k] * br[k];
+            C[(size_t)(i0 + i) * ldc + j0 + j] -= acc;
+          }
+      }
+    }
+  }
+}
+
+template <class F>
+void parallel_rows(int begin, int end, int chunk, double work, F f) {
+  const int nchunks = (end - begin + chunk - 1) / chunk;
+  unsigned hw = std::thread::hardware_concurrency();
+  int nthreads = (int)std::min<unsigned>(hw ? hw : 1, 16);
+  if (work < 2e7 || nchunks < 2 || nthreads < 2) { f(begin, end); return; }   // small: thread start-up would dominate
+  nthreads = std::min(nthreads, nchunks);
+  std::vector<std::thread> pool;
+  const int per = (nchunks + nthreads - 1) / nthreads * chunk;
+  for (int t = 0; t < nthreads; ++t) {
+    const int b = begin + t * per, e = std::min(end, b + per);
+    if (b >= e) break;
+    pool.emplace_back([=]() { f(b, e); });
+  }
+  for (auto &th : pool) th.join();
+}
+}  // namespace
+
 bool cholesky_lower(double *a, int n) {
-  for (int j = 0; j < n; ++j) {
-    double *rj = a + (size_t)j * n;
-    double d = rj[j];
-    for (int k = 0; k < j; ++k) d -= rj[k] * rj[k];
-    if (!(d > 0) || !std::isfinite(d)) return false;
-    d = std::sqrt(d);
-    rj[j] = d;
-    const double inv = 1.0 / d;
-    for (int i = j + 1; i < n; ++i) {
-      double *ri = a + (size_t)i * n;
-      double s = ri[j];
-      for (int k = 0; k < j; ++k) s -= ri[k] * rj[k];
-      ri[j] = s * inv;
+  const size_t ld = (size_t)n;
+  for (int jb = 0; jb < n; jb += kCholBlock) {
+    const int bw = std::min(kCholBlock, n - jb);
+    // (1) rows jb .. n of block column J minus the contribution of the columns already factorised
+    if (jb > 0) {
+      // rows of the diagonal block first (lower triangle only), then the rows below it in parallel
+      gemm_nt_minus(bw, bw, jb, a + (size_t)jb * ld, ld, a + (size_t)jb * ld, ld, a + (size_t)jb * ld + jb, ld, true, 0, 0);
+      const int below = jb + bw;
+      parallel_rows(below, n, 64, 2.0 * (double)(n - below) * bw * jb, [&](int r0, int r1) {
+        gemm_nt_minus(r1 - r0, bw, jb, a + (size_t)r0 * ld, ld, a + (size_t)jb * ld, ld, a + (size_t)r0 * ld + jb, ld, false, 0, 0);
+      });
+    }
+    // (2) the diagonal block, unblocked
+    for (int j = jb; j < jb + bw; ++j) {
+      double *rj = a + (size_t)j * ld;
+      double d = rj[j];
+      for (int k = jb; k < j; ++k) d -= rj[k] * rj[k];
+      if (!(d > 0) || !std::isfinite(d)) return false;
+      d = std::sqrt(d);
+      rj[j] = d;
+      const double inv = 1.0 / d;
+      for (int i = j + 1; i < jb + bw; ++i) {
+        double *ri = a + (size_t)i * ld;
+        double s = ri[j];
+        for (int k = jb; k < j; ++k) s -= ri[k] * rj[k];
+        ri[j] = s * inv;
+      }
+    }
+    // (3) rows below: L[i][J] = A[i][J] L[J][J]^-T
+    for (int i = jb + bw; i < n; ++i) {
+      double *ri = a + (size_t)i * ld;
+      for (int j = jb; j < jb + bw; ++j) {
+        const double *rj = a + (size_t)j * ld;
+        double s = ri[j];
+        for (int k = jb; k < j; ++k) s -= ri[k] * rj[k];
+        ri[j] = s / rj[j];
+      }
     }
   }
   for (int i = 0; i < n; ++i)

@@ -25,6 +25,15 @@ def test_cholesky_matches_numpy():
     ok, L = h.cholesky_lower(xtx)
     assert ok
     np.testing.assert_allclose(L, np.linalg.cholesky(xtx), rtol=1e-12, atol=1e-12)
+    # the blocked / vectorised / threaded code paths: sizes around the 64-wide block, ragged 4 x 4 tiles, and large
+    # enough (p = 900) for the row-parallel update
+    for p in (1, 3, 63, 64, 65, 130, 259, 900):
+        xtx, _ = _suf(p, n=p + 30, seed=p)
+        xtx += np.eye(p)
+        ok, L = h.cholesky_lower(xtx)
+        ref = np.linalg.cholesky(xtx)
+        assert ok and np.max(np.abs(L - ref)) < 1e-11 * np.max(np.abs(ref)), p
+        assert np.all(np.triu(L, 1) == 0)
     ok, _ = h.cholesky_lower(-np.eye(3))
     assert not ok
 
