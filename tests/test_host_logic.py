@@ -28,8 +28,8 @@ def test_cholesky_matches_numpy():
     # the blocked / vectorised / threaded code paths: sizes around the 64-wide block, ragged 4 x 4 tiles, and large
     # enough (p = 900) for the row-parallel update
     for p in (1, 3, 63, 64, 65, 130, 259, 900):
-        xtx, _ = _suf(p, n=p + 30, seed=p)
-        xtx += np.eye(p)
+        A = np.random.default_rng(p).normal(size=(p + 30, p))
+        xtx = A.T @ A + np.eye(p)
         ok, L = h.cholesky_lower(xtx)
         ref = np.linalg.cholesky(xtx)
         assert ok and np.max(np.abs(L - ref)) < 1e-11 * np.max(np.abs(ref)), p
