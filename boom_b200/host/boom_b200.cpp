@@ -247,12 +247,29 @@ MvnModel::MvnModel(const Vector &mean, const SpdMatrix &V, bool ivar) : mu_(mean
   if ((int)mean.size() != V.dim) report_error("MvnModel: mean and variance dimensions differ");
   if (!ivar) {
     const int p = V.dim;
+    bool diagonal = true;
+    for (int i = 0; i < p && diagonal; ++i)
+      for (int j = 0; j < p; ++j)
+        if (i != j && V(i, j) != 0.0) { diagonal = false; break; }
+    if (diagonal) {   // the usual N(0, s^2 I) slab: no factorisation needed (at p = 4000 the general path is 10^11 flops)
+      for (int i = 0; i < p; ++i) {
+        if (!(V(i, i) > 0)) report_error("MvnModel: variance matrix is not positive definite");
+        siginv_(i, i) = 1.0 / V(i, i);
+      }
+      return;
+    }
     Vector L(V.a);
     if (!cholesky_lower(L.data(), p)) report_error("MvnModel: variance matrix is not positive definite");
+    // V^-1 = L^-T L^-1, column by column; column c of L^-1 is zero above row c
     for (int c = 0; c < p; ++c) {
       Vector e(p, 0.0);
       e[c] = 1.0;
-      lsolve_inplace(L.data(), p, e.data());
+      for (int i = c; i < p; ++i) {   // forward substitution from row c
+        const double *ri = L.data() + (size_t)i * p;
+        double t = e[i];
+        for (int k = c; k < i; ++k) t -= ri[k] * e[k];
+        e[i] = t / ri[i];
+      }
       ltsolve_inplace(L.data(), p, e.data());
       for (int r = 0; r < p; ++r) siginv_(r, c) = e[r];
     }
