@@ -20,7 +20,9 @@ Nothing is skipped or cached between steps (W changes every iteration).
   roofline      the dominant kernel of the workload, from CUDA events around every launch of that kernel
                 inside the timed region (boomgpu option "timing").
   cpu_baseline  the UNMODIFIED reference (oracle/_ref/boom_ref_driver, built from /root/reference by
-                oracle/build_ref.sh) on this box's host cores, on a bounded row sample of the same workload.
+                oracle/build_ref.sh) on this box's host cores, on a bounded row sample of the same workload
+                (kind "reference"); only if that binary did not travel to the box: the oracle's C port, one thread
+                (kind "port").  The same for --impl reference.
 
 Strong scaling: the workload's n is fixed; N ranks hold n/N rows each (BASELINE.json: "n=10M,p=500 at 1/2/4/8 GPU").
 """
@@ -153,11 +155,51 @@ def measured_peaks():
         return {"hbm_gbs": HBM_FALLBACK_GBS}, "fallback (B200_PROFILING.md)"
 
 
+def run_oracle_port(kind, sampler, n, p, nonzero, steps, warmup):
+    """Fallback CPU baseline when the compiled reference is not on this box: the oracle's C restatement of the imputation
+    pass (one thread) + the host small-state step, on a bounded row sample (kind "port")."""
+    import numpy as np
+
+    import boom_b200
+    from oracle import oracle as O
+    per_row_us = (0.6 if kind == "logit" else 1.5) + 0.00026 * p * p
+    rows = int(min(n, max(2_000, 1.0e6 / per_row_us)))
+    h = boom_b200.host()
+    rng = boom_b200.RNG(SEED)
+    slab = boom_b200.MvnModel(np.zeros(p), np.eye(p))
+    spike = boom_b200.VariableSelectionPrior(p, min(1.0, max(nonzero, 1) / p))
+    if kind == "logit":
+        X, y, aux, _ = O.synth_binomial(rows, p, nonzero, SEED)
+        mix = O.logit_mixture()
+    else:
+        X, y, aux, _ = O.synth_poisson(rows, p, nonzero, SEED)
+        tab = O.poisson_table()
+    beta = np.zeros(p)
+    bits = [True] + [False] * (p - 1)
+    t0 = None
+    for it in range(warmup + steps):
+        if it == warmup:
+            t0 = time.perf_counter()
+        if kind == "logit":
+            xtx, xty, _, _ = O.logit_step(X, y, aux, beta, 10, mix, 1, it)
+        else:
+            xtx, xty, _ = O.poisson_step(X, y, aux, beta, tab, 1, it)
+        if sampler == "spike":
+            inc, beta = h.spike_slab_sweep(rng, xtx, xty, slab, spike, bits, 1, kind != "logit")
+            bits = [bool(v) for v in inc > 0.5]
+        else:
+            beta = h.rmvn_suf(rng, xtx + np.eye(p), xty)
+    secs = time.perf_counter() - t0
+    ips = steps / secs
+    return {"iters_per_sec": ips, "sample_rows": rows, "cores": 1, "kind": "port", "iters_per_sec_at_n": ips * rows / n}, None
+
+
 def run_reference(kind, sampler, n, p, nonzero, steps, warmup, sample_rows=None, threads=None):
-    """The unmodified reference on the host cores, on the first sample_rows rows' worth of the workload."""
+    """The unmodified reference on the host cores, on the first sample_rows rows' worth of the workload
+    (the oracle port, one thread, when the compiled reference did not travel to this box)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "boom_ref_driver")
     if not os.path.exists(exe):
-        return None, "oracle/_ref/boom_ref_driver missing (build with __graft_entry__.build() where /root/reference exists)"
+        return run_oracle_port(kind, sampler, n, p, nonzero, steps, warmup)
     cores = threads or os.cpu_count() or 1
     if sample_rows is None:
         # ~1-2 s per reference iteration on 16 cores: per-row cost ~ (0.5 + 0.26 p^2 / 1000) us single threaded (SURVEY.md 6)
@@ -171,6 +213,7 @@ def run_reference(kind, sampler, n, p, nonzero, steps, warmup, sample_rows=None,
     r = json.loads(out.stdout.strip().splitlines()[-1])
     r["sample_rows"] = sample_rows
     r["cores"] = cores
+    r["kind"] = "reference"
     # per-row cost is constant (Imputer.hpp:177-179) and the host small-state step is negligible beside it,
     # so iterations/s at the workload's n = iterations/s on the sample * sample_rows / n
     r["iters_per_sec_at_n"] = r["iters_per_sec"] * sample_rows / n
@@ -217,7 +260,7 @@ def main():
             "impl": "reference", "metric": metric, "value": v, "unit": "iter/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": cfg, "obs_per_sec": v * n,
-            "cpu_baseline": {"value": v, "unit": "iter/s", "cores": r["cores"], "kind": "reference", "sample": sample,
+            "cpu_baseline": {"value": v, "unit": "iter/s", "cores": r["cores"], "kind": r["kind"], "sample": sample,
                              "measured_iters_per_sec_on_sample": r["iters_per_sec"]},
             "e2e": {"value": v, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
@@ -368,7 +411,7 @@ def main():
         if r is None:
             cpu = {"unavailable": why}
         else:
-            cpu = {"value": r["iters_per_sec_at_n"], "unit": "iter/s", "cores": r["cores"], "kind": "reference",
+            cpu = {"value": r["iters_per_sec_at_n"], "unit": "iter/s", "cores": r["cores"], "kind": r["kind"],
                    "sample": "first %d of %d rows, 3 iterations after 1 warm-up, %d worker threads, scaled linearly in n" % (
                        r["sample_rows"], n, r["cores"]), "measured_iters_per_sec_on_sample": r["iters_per_sec"]}
 
