@@ -246,6 +246,33 @@ PYBIND11_MODULE(_host, m) {
       .def("allow_model_selection", &PoissonRegressionSpikeSlabSampler::allow_model_selection)
       .def("limit_model_selection", &PoissonRegressionSpikeSlabSampler::limit_model_selection);
 
+  // CPU-side test hook for the mode finder: the derivatives come from a Python callable (tests pass the oracle's), so
+  // SpikeSlabCore::find_posterior_mode runs without a device
+  m.def("find_posterior_mode_with", [](py::function derivs, const std::shared_ptr<MvnBase> &slab,
+                                       const std::shared_ptr<VariableSelectionPrior> &spike, std::vector<bool> bits, const NpD &start,
+                                       double epsilon) {
+    struct CallbackModel : GlmModelBase {
+      py::function f;
+      CallbackModel(int p, py::function fn) : GlmModelBase(p, false), f(std::move(fn)) {}
+      double log_likelihood_derivs(const Vector &b, Vector *g, SpdMatrix *h) override {
+        py::tuple r = f(from_vec(b));
+        if (g) *g = to_vec(r[1].cast<NpD>());
+        if (h) *h = to_spd(r[2].cast<NpD>());
+        return r[0].cast<double>();
+      }
+      void upload(DeviceData &) override {}
+    };
+    const int p = (int)bits.size();
+    CallbackModel model(p, derivs);
+    Selector g(p, false);
+    for (int i = 0; i < p; ++i) if (bits[i]) g.add(i);
+    model.coef().set_inc(g);
+    model.coef().set_Beta(to_vec(start));
+    double value = 0;
+    const bool ok = SpikeSlabCore(slab, spike, false).find_posterior_mode(model, epsilon, &value);
+    return py::make_tuple(ok, from_vec(model.Beta()), value);
+  });
+
   // host linear algebra, exposed for the CPU-side tests
   m.def("cholesky_lower", [](const NpD &a) {
     SpdMatrix s = to_spd(a);

@@ -180,3 +180,46 @@ def test_spike_slab_surface_setters_and_clone():
     pm = boom_b200.PoissonRegressionModel(p)
     ps = boom_b200.PoissonRegressionSpikeSlabSampler(pm, slab, spike, 1, boom_b200.RNG(3))
     assert isinstance(ps.clone_to_new_host(boom_b200.PoissonRegressionModel(p)), boom_b200.PoissonRegressionSpikeSlabSampler)
+
+
+def test_find_posterior_mode_on_oracle_derivatives():
+    """SpikeSlabCore::find_posterior_mode (the objective of BinomialLogitSpikeSlabSampler.cpp:123-177) driven by the ORACLE's
+    log likelihood / gradient / Hessian instead of the device's: the Newton iteration, the step halving and the selection
+    of the included sub-blocks are checked on CPU against numpy."""
+    from oracle import oracle as O
+    h = boom_b200.host()
+    n, p = 1500, 7
+    X, y, nt, _ = O.synth_binomial(n, p, 3, seed=33, max_trials=4)
+    inc = np.array([1, 0, 1, 1, 0, 1, 0], dtype=bool)
+    mu = np.linspace(-0.2, 0.2, p)
+    A = np.random.default_rng(3).normal(size=(p, p)); siginv = A @ A.T / p + np.eye(p)
+    slab = boom_b200.MvnModel(mu, siginv, True)
+    spike = boom_b200.VariableSelectionPrior(p, 0.5)
+    ok, beta, value = h.find_posterior_mode_with(lambda b: O.binomial_logit_loglike_derivs(X, y, nt, b), slab, spike, list(inc),
+                                                 np.zeros(p), 1e-10)
+    assert ok
+    idx = np.flatnonzero(inc)
+    P = siginv[np.ix_(idx, idx)]
+    b = np.zeros(len(idx))
+    for _ in range(60):
+        full = np.zeros(p); full[idx] = b
+        _, g, hh = O.binomial_logit_loglike_derivs(X, y, nt, full)
+        step = np.linalg.solve(P - hh[np.ix_(idx, idx)], g[idx] - P @ (b - mu[idx]))
+        b = b + step
+        if np.max(np.abs(step)) < 1e-13:
+            break
+    np.testing.assert_allclose(beta[idx], b, rtol=1e-8, atol=1e-10)
+    assert np.all(beta[~inc] == 0)
+    full = np.zeros(p); full[idx] = b
+    k = len(idx)
+    logprior = -0.5 * k * np.log(2 * np.pi) + 0.5 * np.linalg.slogdet(P)[1] - 0.5 * (b - mu[idx]) @ P @ (b - mu[idx])
+    assert value == pytest.approx(O.binomial_logit_loglike(X, y, nt, full) + logprior, rel=1e-11)
+    # a far-away start still converges (the full Newton step overshoots into -inf likelihood values: step halving), an
+    # empty model is declined as in the reference
+    ok2, beta2, _ = h.find_posterior_mode_with(lambda b: O.binomial_logit_loglike_derivs(X, y, nt, b), slab, spike, list(inc),
+                                               np.where(inc, 3.0, 0.0), 1e-10)
+    assert ok2
+    np.testing.assert_allclose(beta2[idx], b, rtol=1e-7, atol=1e-9)
+    ok3, _, _ = h.find_posterior_mode_with(lambda b: O.binomial_logit_loglike_derivs(X, y, nt, b), slab, spike, [False] * p,
+                                           np.zeros(p), 1e-10)
+    assert not ok3
