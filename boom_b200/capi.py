@@ -22,7 +22,8 @@ SYMBOLS = (
     "boomgpu_logit_step", "boomgpu_poisson_step", "boomgpu_suf_len", "boomgpu_logit_step_device",
     "boomgpu_poisson_step_device", "boomgpu_synchronize", "boomgpu_suf_buffer", "boomgpu_download", "boomgpu_accumulate", "boomgpu_logit_draw",
     "boomgpu_poisson_draw", "boomgpu_binomial_loglike", "boomgpu_poisson_loglike", "boomgpu_binomial_loglike_derivs",
-    "boomgpu_poisson_loglike_derivs", "boomgpu_pin_host", "boomgpu_unpin_host", "boomgpu_comm_unique_id", "boomgpu_comm_init", "boomgpu_comm_destroy", "boomgpu_allreduce", "boomgpu_kernel_launches",
+    "boomgpu_poisson_loglike_derivs", "boomgpu_binomial_loglike_derivs_device", "boomgpu_poisson_loglike_derivs_device",
+    "boomgpu_poisson_counts_present", "boomgpu_pin_host", "boomgpu_unpin_host", "boomgpu_comm_unique_id", "boomgpu_comm_init", "boomgpu_comm_destroy", "boomgpu_allreduce", "boomgpu_kernel_launches",
     "boomgpu_get_timings",
 )
 
@@ -289,6 +290,11 @@ class Context:
         g, h = np.empty(self.p), np.empty((self.p, self.p))
         self._check(self._lib.boomgpu_poisson_loglike_derivs(self._h, _dp(beta), C.byref(ll), _dp(g), _dp(h)))
         return ll.value, g, h
+
+    def poisson_counts_present(self, length):
+        out = np.zeros(int(length), dtype=np.uint8)
+        self._check(self._lib.boomgpu_poisson_counts_present(self._h, out.ctypes.data_as(C.c_void_p), C.c_int64(int(length))))
+        return out
 
     # ---- instrumentation
     def kernel_launches(self):

@@ -41,6 +41,11 @@ struct boomgpu_ctx {
   const int64_t *yi = nullptr;
   std::vector<void *> owned;  // device allocations made for uploaded data
   uint64_t row_offset = 0;
+  // what the TMA-fed kernels read: X itself, or -- for adopted rows whose pointer / leading dimension TMA cannot describe
+  // (odd ldx, base not 16-byte aligned) and p > 64 -- a padded device copy made once per adoption
+  const double *Xt = nullptr;
+  int64_t ldxt = 0;
+  double *Xt_owned = nullptr;
 
   // mixtures
   LogitMixture mix{};        // host copy
@@ -51,6 +56,9 @@ struct boomgpu_ctx {
   PoissonTable tab{};
   bool have_tab = false;
   std::vector<void *> tab_owned;
+  // host copy of the table as last installed: re-stating an unchanged table (samplers do, every draw) uploads nothing
+  std::vector<int64_t> tab_nu_h; std::vector<int32_t> tab_off_h; std::vector<double> tab_w_h, tab_mu_h, tab_sig_h;
+  int64_t tab_cut_h = -1;
 
   // workspaces
   double *beta_dev = nullptr; int beta_cap = 0;
@@ -125,6 +133,8 @@ void free_data(boomgpu_ctx *ctx) {
   ctx->owned.clear();
   ctx->X = ctx->y = ctx->ntrials = ctx->exposure = nullptr;
   ctx->yi = nullptr;
+  if (ctx->Xt_owned) { cudaFree(ctx->Xt_owned); ctx->Xt_owned = nullptr; }
+  ctx->Xt = nullptr; ctx->ldxt = 0;
   ctx->n = 0; ctx->p = 0; ctx->model = -1;
 }
 
@@ -242,10 +252,24 @@ int choose_path(boomgpu_ctx *ctx, int *path) {
   } else {
     *path = ctx->p <= 64 ? 1 : 2;
   }
-  if (*path == 2 && ((ctx->ldx & 1) || !aligned16(ctx->X) || ctx->n >= (int64_t)0x7fffffc0))
-    return fail(ctx, BOOMGPU_ERR_ARG, "the two-pass path describes X to TMA: it needs an even leading dimension, a 16-byte aligned X "
-                "and fewer than 2^31 rows per context (ldx = %lld, n = %lld); boomgpu_upload_* pads for you", (long long)ctx->ldx,
-                (long long)ctx->n);
+  if (*path == 2 && ctx->n >= (int64_t)0x7fffffc0)
+    return fail(ctx, BOOMGPU_ERR_ARG, "the two-pass path addresses rows with 32-bit TMA coordinates: fewer than 2^31 rows per context "
+                "(n = %lld); shard the rows over more contexts", (long long)ctx->n);
+  return 0;
+}
+
+// The two-pass path describes X to TMA, which needs a 16-byte aligned base and row pitch.  Uploaded rows are padded for
+// that; ADOPTED rows that do not qualify (e.g. a contiguous n x 501 tensor) are copied once into a padded device buffer
+// (a second copy of X in HBM -- the price of an unaligned adoption; documented in boomgpu.h).
+int ensure_tma_view(boomgpu_ctx *ctx) {
+  if (ctx->Xt) return 0;
+  if ((ctx->ldx % 2 == 0) && aligned16(ctx->X)) { ctx->Xt = ctx->X; ctx->ldxt = ctx->ldx; return 0; }
+  const int64_t ldd = ((int64_t)ctx->p + 7) / 8 * 8;
+  CU(cudaMalloc((void **)&ctx->Xt_owned, sizeof(double) * (size_t)std::max<int64_t>(ctx->n * ldd, 1)));
+  if (ldd != ctx->p) CU(cudaMemsetAsync(ctx->Xt_owned, 0, sizeof(double) * (size_t)(ctx->n * ldd), ctx->stream));
+  CU(cudaMemcpy2DAsync(ctx->Xt_owned, sizeof(double) * ldd, ctx->X, sizeof(double) * ctx->ldx, sizeof(double) * ctx->p, (size_t)ctx->n,
+                       cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->Xt = ctx->Xt_owned; ctx->ldxt = ldd;
   return 0;
 }
 
@@ -301,8 +325,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int ensure_xmap(boomgpu_ctx *ctx, boomgpu_ctx::XMap &m, int box_cols, int box_rows) {
-  if (m.X == ctx->X && m.n == ctx->n && m.ldx == ctx->ldx && m.p == ctx->p && m.box_cols == box_cols && m.box_rows == box_rows) return 0;
+int ensure_xmap(boomgpu_ctx *ctx, boomgpu_ctx::XMap &m, const double *X, int64_t ldx, int box_cols, int box_rows) {
+  if (m.X == X && m.n == ctx->n && m.ldx == ldx && m.p == ctx->p && m.box_cols == box_cols && m.box_rows == box_rows) return 0;
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void *fn = nullptr;
@@ -312,15 +336,15 @@ int ensure_xmap(boomgpu_ctx *ctx, boomgpu_ctx::XMap &m, int box_cols, int box_ro
     encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
   const cuuint64_t dims[2] = {(cuuint64_t)ctx->p, (cuuint64_t)ctx->n};
-  const cuuint64_t strides[1] = {(cuuint64_t)ctx->ldx * sizeof(double)};
+  const cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(double)};
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = encode(&m.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(ctx->X), dims, strides, box, estr,
+  CUresult r = encode(&m.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(X), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ctx, BOOMGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for n=%lld p=%d ldx=%lld box=%dx%d", (int)r,
-                                     (long long)ctx->n, ctx->p, (long long)ctx->ldx, box_cols, box_rows);
-  m.X = ctx->X; m.n = ctx->n; m.ldx = ctx->ldx; m.p = ctx->p; m.box_cols = box_cols; m.box_rows = box_rows;
+                                     (long long)ctx->n, ctx->p, (long long)ldx, box_cols, box_rows);
+  m.X = X; m.n = ctx->n; m.ldx = ldx; m.p = ctx->p; m.box_cols = box_cols; m.box_rows = box_rows;
   return 0;
 }
 
@@ -338,7 +362,7 @@ struct TmaLauncher {
     memcpy(bp.b, ctx->beta_pin, sizeof(double) * d.p);
     const size_t smem = tma_smem_bytes(NB);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (int rc = ensure_xmap(ctx, ctx->xmap_small, tma_padw(NB), tma_slice_rows(NB))) return rc;
+    if (int rc = ensure_xmap(ctx, ctx->xmap_small, ctx->X, ctx->ldx, tma_padw(NB), tma_slice_rows(NB))) return rc;
     const int64_t nslices = (d.n + tma_slice_rows(NB) - 1) / tma_slice_rows(NB);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nslices + NW - 1) / NW, (int64_t)ctx->sms));
     if (ensure(ctx, &ctx->partials, &ctx->partials_cap, (int64_t)grid * tma_partial_len(NB))) return BOOMGPU_ERR_CUDA;
@@ -415,7 +439,7 @@ int ensure_ws(boomgpu_ctx *ctx) {
 // pass 2 + reduction into suf (device)
 int launch_syrk(boomgpu_ctx *ctx, double *suf) {
   SyrkParams sp;
-  sp.X = ctx->X; sp.ldx = ctx->ldx; sp.n = ctx->n; sp.p = ctx->p;
+  sp.X = ctx->Xt; sp.ldx = ctx->ldxt; sp.n = ctx->n; sp.p = ctx->p;
   sp.w = ctx->w_buf; sp.s = ctx->s_buf;
   sp.nblk = (ctx->p + 127) / 128;
   sp.nregions = sp.nblk * (sp.nblk + 1) / 2;
@@ -432,7 +456,7 @@ int launch_syrk(boomgpu_ctx *ctx, double *suf) {
   if (ensure(ctx, &ctx->partials, &ctx->partials_cap, need)) return BOOMGPU_ERR_CUDA;
   sp.partials = ctx->partials;
   static const SyrkUnitTable table = make_unit_table();
-  if (int rc = ensure_xmap(ctx, ctx->xmap_syrk, kSyrkPanelLd, kSyrkKB)) return rc;
+  if (int rc = ensure_xmap(ctx, ctx->xmap_syrk, ctx->Xt, ctx->ldxt, kSyrkPanelLd, kSyrkKB)) return rc;
   CU(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmemBytes));
   {
     LaunchScope ls(ctx, 2);
@@ -500,6 +524,8 @@ int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, c
     }
     CU(cudaGetLastError());
   } else {
+    if (int rc = ensure_tma_view(ctx)) return rc;
+    d.X = ctx->Xt; d.ldx = ctx->ldxt;
     if (int rc = ensure_ws(ctx)) return rc;
     int nparts = 0;
     if (MODEL == kSupplied) {
@@ -515,6 +541,14 @@ int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, c
     CU(cudaGetLastError());
     if (int rc = launch_syrk(ctx, suf)) return rc;
   }
+  return 0;
+}
+
+// the Philox counter carries 16 bits of the per-row slot (draws.cuh: uniform_pair) and the per-trial branch uses slot = trial
+// index, so a row may run at most 65535 trials one by one; larger n_i must take the CLT branch
+int check_clt(boomgpu_ctx *ctx, int clt_threshold) {
+  if (clt_threshold < 0 || clt_threshold >= 65536)
+    return fail(ctx, BOOMGPU_ERR_ARG, "clt_threshold = %d: must lie in [0, 65535] (the random stream has 16 bits of per-row trial index)", clt_threshold);
   return 0;
 }
 
@@ -647,13 +681,29 @@ int loglike_derivs_impl(boomgpu_ctx *ctx, int model, const double *beta, double 
   DrawParams prm = make_prm(ctx, 0, 0, 0);
   prm.log_alpha = log_alpha;
   RowOut out{nullptr, nullptr, nullptr, nullptr};
-  if (int rc = run_step<MODEL>(ctx, beta, prm, out, nullptr, nullptr, ctx->suf_dev, ctx->suf_pin)) return rc;
+  // rows sharded over ranks: every rank must see the likelihood of ALL rows (the mode finder and the MH moves built on it
+  // run replicated on every rank and must stay in step), so the packed result is all-reduced like a Gibbs step's statistics
+  const bool sharded = ctx->comm && ctx->comm_ranks > 1;
+  if (int rc = run_step<MODEL>(ctx, beta, prm, out, nullptr, nullptr, ctx->suf_dev, sharded ? nullptr : ctx->suf_pin)) return rc;
   const int p = ctx->p;
+  if (int rc = allreduce_on_stream(ctx, ctx->suf_dev, boomgpu_suf_len(p))) return rc;
   if (int rc = fetch_suf(ctx)) return rc;
   *loglike = ctx->n == 0 ? 0.0 : ctx->suf_pin[(size_t)p * p + p + 1];
   if (gradient) memcpy(gradient, ctx->suf_pin + (size_t)p * p, sizeof(double) * p);
   if (hessian) for (size_t e = 0; e < (size_t)p * p; ++e) hessian[e] = -ctx->suf_pin[e];
   return 0;
+}
+
+template <int MODEL>
+int loglike_derivs_device_impl(boomgpu_ctx *ctx, int model, const double *beta, double log_alpha, double *suf_dev) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (ctx->model != model || !ctx->X) return fail(ctx, BOOMGPU_ERR_STATE, "no matching data uploaded to this context");
+  if (!beta || !suf_dev) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
+  DeviceGuard g(ctx->device);
+  DrawParams prm = make_prm(ctx, 0, 0, 0);
+  prm.log_alpha = log_alpha;
+  RowOut out{nullptr, nullptr, nullptr, nullptr};
+  return run_step<MODEL>(ctx, beta, prm, out, nullptr, nullptr, suf_dev);
 }
 
 }  // namespace
@@ -895,6 +945,11 @@ int boomgpu_set_poisson_table(boomgpu_ctx *ctx, int ntab, const int64_t *nu, con
   }
   if (e1 < 0) return fail(ctx, BOOMGPU_ERR_ARG, "Poisson table has no entry for nu = 1");
   const int total = offset[ntab];
+  if (ctx->have_tab && gaussian_cutoff == ctx->tab_cut_h && (size_t)ntab == ctx->tab_nu_h.size() && (size_t)total == ctx->tab_w_h.size() &&
+      !memcmp(nu, ctx->tab_nu_h.data(), sizeof(int64_t) * ntab) && !memcmp(offset, ctx->tab_off_h.data(), sizeof(int32_t) * (ntab + 1)) &&
+      !memcmp(weights, ctx->tab_w_h.data(), sizeof(double) * total) && !memcmp(mu, ctx->tab_mu_h.data(), sizeof(double) * total) &&
+      !memcmp(sigma, ctx->tab_sig_h.data(), sizeof(double) * total))
+    return 0;   // unchanged
   std::vector<double> inv_sigma(total), lconst(total);
   std::vector<float> mu_f(total), lconst2_f(total), hs2_f(total);
   std::vector<double> inv_sigsq(total), logw(total);
@@ -926,6 +981,7 @@ int boomgpu_set_poisson_table(boomgpu_ctx *ctx, int ntab, const int64_t *nu, con
   CU(cudaStreamSynchronize(ctx->stream));
   for (void *q : ctx->tab_owned) cudaFree(q);
   ctx->tab_owned.clear();
+  ctx->have_tab = false;
   auto up = [&](const void *src, size_t bytes, void **dst) -> cudaError_t {
     cudaError_t e = cudaMalloc(dst, bytes);
     if (e != cudaSuccess) return e;
@@ -948,6 +1004,29 @@ int boomgpu_set_poisson_table(boomgpu_ctx *ctx, int ntab, const int64_t *nu, con
   CU(up(dense.data(), sizeof(int32_t) * dense.size(), (void **)&t.dense));
   t.dense_n = dense_n;
   ctx->have_tab = true;
+  ctx->tab_nu_h.assign(nu, nu + ntab); ctx->tab_off_h.assign(offset, offset + ntab + 1);
+  ctx->tab_w_h.assign(weights, weights + total); ctx->tab_mu_h.assign(mu, mu + total); ctx->tab_sig_h.assign(sigma, sigma + total);
+  ctx->tab_cut_h = gaussian_cutoff;
+  return 0;
+}
+
+int boomgpu_poisson_counts_present(boomgpu_ctx *ctx, unsigned char *present, int64_t len) {
+  if (!ctx || !present || len <= 0) return BOOMGPU_ERR_ARG;
+  if (ctx->model != kPoisson || (!ctx->yi && ctx->n > 0)) return fail(ctx, BOOMGPU_ERR_STATE, "no Poisson data uploaded to this context");
+  DeviceGuard g(ctx->device);
+  unsigned char *d = nullptr;
+  CU(cudaMalloc((void **)&d, (size_t)len));
+  cudaError_t e = cudaMemsetAsync(d, 0, (size_t)len, ctx->stream);
+  if (e == cudaSuccess && ctx->n > 0) {
+    LaunchScope ls(ctx, 4);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->n + 255) / 256, (int64_t)ctx->sms * 8));
+    counts_present_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->yi, ctx->n, d, len);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(present, d, (size_t)len, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); else cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, BOOMGPU_ERR_CUDA, "counts_present failed: %s", cudaGetErrorString(e));
   return 0;
 }
 
@@ -969,6 +1048,7 @@ int64_t boomgpu_suf_len(int p) { return (int64_t)p * p + p + 4; }
 int boomgpu_logit_step_device(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
                               double *suf_dev) {
   if (int rc = check_ready(ctx, kLogit)) return rc;
+  if (int rc = check_clt(ctx, clt_threshold)) return rc;
   if (!beta || !suf_dev) return fail(ctx, BOOMGPU_ERR_ARG, "null beta / suf_dev");
   DeviceGuard g(ctx->device);
   RowOut out{nullptr, nullptr, nullptr, nullptr};
@@ -1015,6 +1095,7 @@ int boomgpu_download(boomgpu_ctx *ctx, const double *src_dev, double *dst_host, 
 int boomgpu_logit_step(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
                        double *xtx, double *xty, int64_t *sample_size) {
   if (int rc = check_ready(ctx, kLogit)) return rc;
+  if (int rc = check_clt(ctx, clt_threshold)) return rc;
   if (!beta || !xtx || !xty) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
   DeviceGuard g(ctx->device);
   if (int rc = ensure_suf(ctx)) return rc;
@@ -1086,6 +1167,7 @@ int boomgpu_accumulate(boomgpu_ctx *ctx, const double *weight, const double *wei
 int boomgpu_logit_draw(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
                        double *sum_out, double *info_out) {
   if (int rc = check_ready(ctx, kLogit)) return rc;
+  if (int rc = check_clt(ctx, clt_threshold)) return rc;
   if (!beta || !sum_out || !info_out) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
   DeviceGuard g(ctx->device);
   if (int rc = ensure_suf(ctx)) return rc;
@@ -1150,6 +1232,7 @@ static int loglike_impl(boomgpu_ctx *ctx, int model, const double *beta, double 
   }
   cudaError_t e = cudaGetLastError();
   double result = 0;
+  if (e == cudaSuccess && allreduce_on_stream(ctx, parts + grid, 1)) { cudaStreamSynchronize(ctx->stream); cudaFree(dbeta); cudaFree(parts); return BOOMGPU_ERR_CUDA; }
   if (e == cudaSuccess) e = cudaMemcpyAsync(&result, parts + grid, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   cudaFree(dbeta); cudaFree(parts);
@@ -1164,6 +1247,13 @@ int boomgpu_binomial_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double
 }
 int boomgpu_poisson_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *gradient, double *hessian) {
   return loglike_derivs_impl<kPoissonLL>(ctx, kPoisson, beta, 0.0, loglike, gradient, hessian);
+}
+
+int boomgpu_binomial_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double log_alpha, double *suf_dev) {
+  return loglike_derivs_device_impl<kLogitLL>(ctx, kLogit, beta, log_alpha, suf_dev);
+}
+int boomgpu_poisson_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) {
+  return loglike_derivs_device_impl<kPoissonLL>(ctx, kPoisson, beta, 0.0, suf_dev);
 }
 
 int boomgpu_binomial_loglike(boomgpu_ctx *ctx, const double *beta, double *loglike) { return loglike_impl(ctx, kLogit, beta, loglike); }

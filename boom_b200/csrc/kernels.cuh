@@ -793,6 +793,15 @@ __global__ void __launch_bounds__(256) loglike_kernel(RowData d, const double *_
   }
 }
 
+// present[v] = 1 iff some row has count y == v, 0 <= v < len (benign same-value races).  What the host needs to know which
+// entries NormalMixtureApproximationTable::approximate would have to add for this data (NormalMixtureApproximation.cpp:472-532).
+__global__ void counts_present_kernel(const int64_t *__restrict__ y, int64_t n, unsigned char *__restrict__ present, int64_t len) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = __ldg(y + i);
+    if (v >= 0 && v < len) present[v] = 1;
+  }
+}
+
 __global__ void reduce_sum_kernel(const double *__restrict__ partials, int nparts, double *__restrict__ dst) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double s = 0;

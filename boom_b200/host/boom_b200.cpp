@@ -430,9 +430,32 @@ void BinomialLogitModel::upload(DeviceData &dev) {
   if (adopted_) dev.check(boomgpu_adopt_binomial(dev.ctx(), adopted_n_, xdim(), dX_, dldx_, dy_, dn_));
   else dev.check(boomgpu_upload_binomial(dev.ctx(), (int64_t)y_.size(), xdim(), x_.data(), xdim(), y_.data(), n_.data()));
 }
+// Rows sharded over ranks with a caller-supplied all-reduce hook: this rank's packed [ -H | g | {., ll, ., .} ] stays on the
+// device for the hook, exactly like a Gibbs step's statistics (with a native communicator the C ABI all-reduces itself).
+// Every rank therefore sees the likelihood of ALL rows: the mode finder and the MH moves run replicated and stay in step.
+template <class StepDeviceFn>
+static double loglike_through_hook(GlmModelBase &model, StepDeviceFn step_device, Vector *g, SpdMatrix *h) {
+  DeviceData &dev(model.device_data());
+  const int p = model.xdim();
+  const int64_t len = boomgpu_suf_len(p);
+  Vector packed((size_t)len);
+  double *suf_dev = nullptr;
+  dev.check(boomgpu_suf_buffer(dev.ctx(), &suf_dev));
+  dev.check(step_device(dev.ctx(), suf_dev));
+  model.allreduce()(suf_dev, len);
+  dev.check(boomgpu_download(dev.ctx(), suf_dev, packed.data(), len));
+  const size_t mat = (size_t)p * p;
+  if (g) g->assign(packed.begin() + mat, packed.begin() + mat + p);
+  if (h) {
+    if (h->dim != p) *h = SpdMatrix(p);
+    for (size_t e = 0; e < mat; ++e) h->a[e] = -packed[e];
+  }
+  return packed[mat + p + 1];
+}
+
 double BinomialLogitModel::log_likelihood(const Vector &beta) {
   if ((int)beta.size() != xdim()) report_error("log_likelihood: wrong size beta");
-  if (log_alpha_ != 0.0) return log_likelihood_derivs(beta, nullptr, nullptr);   // the offset enters eta (BinomialLogitModel.cpp:168)
+  if (log_alpha_ != 0.0 || allreduce()) return log_likelihood_derivs(beta, nullptr, nullptr);   // the offset enters eta (BinomialLogitModel.cpp:168)
   DeviceData &dev(device_data());
   double ans = 0;
   dev.check(boomgpu_binomial_loglike(dev.ctx(), beta.data(), &ans));
@@ -441,6 +464,11 @@ double BinomialLogitModel::log_likelihood(const Vector &beta) {
 
 double BinomialLogitModel::log_likelihood_derivs(const Vector &beta, Vector *g, SpdMatrix *h) {
   if ((int)beta.size() != xdim()) report_error("log_likelihood: wrong size beta");
+  if (allreduce()) {
+    const double la = log_alpha_;
+    return loglike_through_hook(*this, [&](boomgpu_ctx *ctx, double *suf_dev) {
+      return boomgpu_binomial_loglike_derivs_device(ctx, beta.data(), la, suf_dev); }, g, h);
+  }
   DeviceData &dev(device_data());
   double ans = 0;
   if (g) g->assign(xdim(), 0.0);
@@ -486,6 +514,7 @@ void PoissonRegressionModel::upload(DeviceData &dev) {
 }
 double PoissonRegressionModel::log_likelihood(const Vector &beta) {
   if ((int)beta.size() != xdim()) report_error("log_likelihood: wrong size beta");
+  if (allreduce()) return log_likelihood_derivs(beta, nullptr, nullptr);
   DeviceData &dev(device_data());
   double ans = 0;
   dev.check(boomgpu_poisson_loglike(dev.ctx(), beta.data(), &ans));
@@ -494,6 +523,10 @@ double PoissonRegressionModel::log_likelihood(const Vector &beta) {
 
 double PoissonRegressionModel::log_likelihood_derivs(const Vector &beta, Vector *g, SpdMatrix *h) {
   if ((int)beta.size() != xdim()) report_error("log_likelihood: wrong size beta");
+  if (allreduce()) {
+    return loglike_through_hook(*this, [&](boomgpu_ctx *ctx, double *suf_dev) {
+      return boomgpu_poisson_loglike_derivs_device(ctx, beta.data(), suf_dev); }, g, h);
+  }
   DeviceData &dev(device_data());
   double ans = 0;
   if (g) g->assign(xdim(), 0.0);
@@ -963,12 +996,28 @@ struct LogitMixtureStore {
 };
 LogitMixtureStore &logit_mixture_store() { static LogitMixtureStore s; return s; }
 
+// PoissonDataImputer::mixture_table_ (PoissonDataImputer.hpp:99): one table per process, grown on demand, plus its
+// flattened (CSR) form for boomgpu_set_poisson_table
 struct PoissonTableStore {
+  NormalMixtureApproximationTable table;
   std::vector<int64_t> nu;
   std::vector<int32_t> offset;
   Vector weights, mu, sigma;
   int64_t largest = 0;
   uint64_t version = 0;
+  std::mutex lock;
+  void flatten() {
+    nu = table.index();
+    offset.assign(1, 0);
+    weights.clear(); mu.clear(); sigma.clear();
+    for (size_t e = 0; e < table.size(); ++e) {
+      const NormalMixtureApproximation &a(table.entry(e));
+      weights.insert(weights.end(), a.weights.begin(), a.weights.end());
+      mu.insert(mu.end(), a.mu.begin(), a.mu.end());
+      sigma.insert(sigma.end(), a.sigma.begin(), a.sigma.end());
+      offset.push_back(offset.back() + a.dim());
+    }
+  }
 };
 PoissonTableStore &poisson_table_store() { static PoissonTableStore s; return s; }
 
@@ -1089,26 +1138,31 @@ void BinomialLogitSpikeSlabSampler::find_posterior_mode(double epsilon) {
 
 // ---------------------------------------------------------------------------------------------
 void PoissonRegressionAuxMixSampler::set_mixture_table(const Vector &ser, int64_t largest_index) {
-  PoissonTableStore t;
-  t.offset.push_back(0);
-  size_t i = 0;
-  while (i < ser.size()) {
-    if (i + 1 >= ser.size()) report_error("set_mixture_table: truncated table");
-    const int64_t nu = std::llround(ser[i]);
-    const int K = (int)std::llround(ser[i + 1]);
-    if (K < 1 || i + 2 + 3 * (size_t)K > ser.size()) report_error("set_mixture_table: malformed table");
-    t.nu.push_back(nu);
-    for (int k = 0; k < K; ++k) t.weights.push_back(ser[i + 2 + k]);
-    for (int k = 0; k < K; ++k) t.sigma.push_back(ser[i + 2 + K + k]);
-    for (int k = 0; k < K; ++k) t.mu.push_back(ser[i + 2 + 2 * K + k]);
-    t.offset.push_back(t.offset.back() + K);
-    i += 2 + 3 * (size_t)K;
-  }
-  t.largest = largest_index;
-  t.version = poisson_table_store().version + 1;
-  poisson_table_store() = t;
+  NormalMixtureApproximationTable t;
+  t.deserialize(ser);
+  if (t.empty()) report_error("set_mixture_table: empty table");
+  PoissonTableStore &st(poisson_table_store());
+  std::lock_guard<std::mutex> guard(st.lock);
+  st.table = t;
+  st.largest = largest_index;
+  st.flatten();
+  ++st.version;
 }
-bool PoissonRegressionAuxMixSampler::mixture_table_is_set() { return !poisson_table_store().nu.empty(); }
+Vector PoissonRegressionAuxMixSampler::mixture_table() {
+  PoissonTableStore &st(poisson_table_store());
+  std::lock_guard<std::mutex> guard(st.lock);
+  return st.table.serialize();
+}
+NormalMixtureApproximation PoissonRegressionAuxMixSampler::approximate(int64_t nu) {
+  PoissonTableStore &st(poisson_table_store());
+  std::lock_guard<std::mutex> guard(st.lock);
+  if (st.table.empty()) report_error("PoissonRegressionAuxMixSampler: no mixture table");
+  const size_t before = st.table.size();
+  NormalMixtureApproximation a = st.table.approximate(nu);
+  if (st.table.size() != before) { st.flatten(); ++st.version; }
+  return a;
+}
+bool PoissonRegressionAuxMixSampler::mixture_table_is_set() { return !poisson_table_store().table.empty(); }
 
 PoissonRegressionAuxMixSampler::PoissonRegressionAuxMixSampler(PoissonRegressionModel *model, const std::shared_ptr<MvnBase> &prior,
                                                                int, RNG &seeding_rng)
@@ -1125,18 +1179,28 @@ void PoissonRegressionAuxMixSampler::draw() {
 }
 void PoissonRegressionAuxMixSampler::impute_latent_data() {
   if (latent_data_fixed_) return;
-  const PoissonTableStore &t(poisson_table_store());
+  PoissonTableStore &t(poisson_table_store());
   if (t.nu.empty())
     report_error("PoissonRegressionAuxMixSampler: no mixture table; call set_mixture_table with the serialized "
                  "NormalMixtureApproximationTable (see boom_b200/data/poisson_mixture_table.json)");
   const uint64_t seed = device_seed_, it = iteration_++;
   const Vector &beta(model_->Beta());
+  // The reference extends its table per observation inside the draw (NormalMixtureApproximationTable::approximate,
+  // NormalMixtureApproximation.cpp:472-532).  Here: once per (data, table, context), ask the device which counts occur,
+  // add the entries the grid lacks by the same rule, then state the table (the C side skips an unchanged upload).
   auto ensure_table = [&](boomgpu_ctx *ctx) {
-    if (table_version_seen_ == t.version) return 0;
-    int rc = boomgpu_set_poisson_table(ctx, (int)t.nu.size(), t.nu.data(), t.offset.data(), t.weights.data(), t.mu.data(),
-                                       t.sigma.data(), t.largest);
-    if (!rc) table_version_seen_ = t.version;
-    return rc;
+    std::lock_guard<std::mutex> guard(t.lock);
+    if (counts_checked_ctx_ != ctx || counts_checked_data_version_ != model_->data_version() || counts_checked_table_version_ != t.version) {
+      std::vector<unsigned char> present((size_t)std::max<int64_t>(t.largest, 1), 0);
+      if (int rc = boomgpu_poisson_counts_present(ctx, present.data(), (int64_t)present.size())) return rc;
+      const size_t before = t.table.size();
+      for (int64_t v = std::max<int64_t>(1, t.table.smallest_index()); v < (int64_t)present.size() && v < t.table.largest_index(); ++v)
+        if (present[(size_t)v] && !t.table.contains(v)) t.table.approximate(v);
+      if (t.table.size() != before) { t.flatten(); ++t.version; }
+      counts_checked_ctx_ = ctx; counts_checked_data_version_ = model_->data_version(); counts_checked_table_version_ = t.version;
+    }
+    return boomgpu_set_poisson_table(ctx, (int)t.nu.size(), t.nu.data(), t.offset.data(), t.weights.data(), t.mu.data(),
+                                     t.sigma.data(), t.largest);
   };
   run_device_step(
       *model_, suf_, packed_,

@@ -458,6 +458,41 @@ class BinomialLogitSpikeSlabSampler : public BinomialLogitAuxmixSampler {
   double log_posterior_at_mode_ = -1.0 / 0.0;
 };
 
+// NormalMixtureApproximation / NormalMixtureApproximationTable (Models/Glm/PosteriorSamplers/NormalMixtureApproximation.hpp:
+// 60-200, 262-330), as far as the Poisson samplers use them: a table of finite normal mixtures approximating the
+// -log Gamma(nu, 1) densities, extended on demand for counts off its grid (mixture_table.cpp).
+struct NormalMixtureApproximation {
+  Vector mu, sigma, weights;
+  double kullback_leibler = -1.0 / 0.0;
+  int number_of_function_evaluations = -1;
+  int dim() const { return (int)mu.size(); }
+  void order_by_mu();
+};
+double kullback_leibler_neg_log_gamma(double nu, const NormalMixtureApproximation &approx);   // .cpp:296-319 with NegLogGamma(nu)
+NormalMixtureApproximation fit_neg_log_gamma(double nu, const NormalMixtureApproximation &start, double precision, int max_evals,
+                                             double stepsize);
+class NormalMixtureApproximationTable {
+ public:
+  void deserialize(const Vector &serialized);   // [nu, K, w[K], sigma[K], mu[K]] ... (.cpp:393-399, 544-558)
+  Vector serialize() const;
+  void add(int64_t nu, const NormalMixtureApproximation &approximation);
+  bool contains(int64_t nu) const;
+  bool empty() const { return index_.empty(); }
+  size_t size() const { return index_.size(); }
+  int64_t smallest_index() const { return index_.front(); }
+  int64_t largest_index() const { return index_.back(); }
+  // the entry for nu; when nu is off the grid it is interpolated or fitted, ADDED to the table, and returned (.cpp:472-532)
+  const NormalMixtureApproximation &approximate(int64_t nu);
+  const std::vector<int64_t> &index() const { return index_; }
+  const NormalMixtureApproximation &entry(size_t e) const { return approximations_[e]; }
+
+ private:
+  void insert(int64_t nu, const NormalMixtureApproximation &approximation, bool derived);
+  std::vector<int64_t> index_;
+  std::vector<NormalMixtureApproximation> approximations_;
+  std::vector<char> derived_;   // entries approximate() added (never used as interpolation neighbours: see mixture_table.cpp)
+};
+
 class PoissonRegressionAuxMixSampler : public PosteriorSampler {
  public:
   PoissonRegressionAuxMixSampler(PoissonRegressionModel *model, const std::shared_ptr<MvnBase> &prior,
@@ -479,6 +514,11 @@ class PoissonRegressionAuxMixSampler : public PosteriorSampler {
   // Must hold every distinct count of the data below largest_index.
   static void set_mixture_table(const Vector &serialized, int64_t largest_index);
   static bool mixture_table_is_set();
+  // the table as it stands now (entries added for off-grid counts included), in the reference's serialize() layout
+  static Vector mixture_table();
+  // PoissonDataImputer's use of NormalMixtureApproximationTable::approximate (poisson_mixture_approximation_table.cpp:44-61)
+  // for one count: returns the entry, adding it to the table when nu is off the grid
+  static NormalMixtureApproximation approximate(int64_t nu);
 
  protected:
   void on_seed() override;
@@ -488,7 +528,9 @@ class PoissonRegressionAuxMixSampler : public PosteriorSampler {
 
  private:
   bool latent_data_fixed_ = false;
-  uint64_t device_seed_, iteration_ = 0, table_version_seen_ = 0;
+  uint64_t device_seed_, iteration_ = 0;
+  uint64_t counts_checked_data_version_ = 0, counts_checked_table_version_ = 0;
+  const void *counts_checked_ctx_ = nullptr;
   Vector packed_;
 };
 

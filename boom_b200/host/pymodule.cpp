@@ -101,6 +101,13 @@ PYBIND11_MODULE(_host, m) {
     PoissonRegressionAuxMixSampler::set_mixture_table(to_vec(ser), largest);
   });
 
+  m.def("poisson_mixture_table", []() { return from_vec(PoissonRegressionAuxMixSampler::mixture_table()); });
+  // (mu, sigma, weights, kl) of the table entry for nu, interpolated / fitted and added when nu is off the grid
+  m.def("poisson_mixture_approximate", [](int64_t nu) {
+    NormalMixtureApproximation a = PoissonRegressionAuxMixSampler::approximate(nu);
+    return py::make_tuple(from_vec(a.mu), from_vec(a.sigma), from_vec(a.weights), kullback_leibler_neg_log_gamma((double)nu, a));
+  });
+
   py::class_<MvnBase, std::shared_ptr<MvnBase>>(m, "MvnBase");
   py::class_<MvnModel, MvnBase, std::shared_ptr<MvnModel>>(m, "MvnModel")
       .def(py::init([](const NpD &mu, const NpD &V, bool ivar) { return std::make_shared<MvnModel>(to_vec(mu), to_spd(V), ivar); }),

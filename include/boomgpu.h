@@ -83,7 +83,9 @@ int boomgpu_upload_binomial(boomgpu_ctx *ctx, int64_t n, int p, const double *X,
                             const double *y, const double *ntrials);
 int boomgpu_upload_poisson(boomgpu_ctx *ctx, int64_t n, int p, const double *X, int64_t ldx,
                            const int64_t *y, const double *exposure);
-/* data already resident in HBM (device pointers; caller keeps them alive) */
+/* data already resident in HBM (device pointers; caller keeps them alive).  Used in place when TMA can describe them
+ * (16-byte aligned base, even ldx); for p > 64 rows that do not qualify (e.g. a contiguous n x 501 tensor) are copied ONCE,
+ * at the first step, into a padded device buffer owned by the context -- a second copy of X in HBM. */
 int boomgpu_adopt_binomial(boomgpu_ctx *ctx, int64_t n, int p, const double *dX, int64_t ldx,
                            const double *dy, const double *dntrials);
 int boomgpu_adopt_poisson(boomgpu_ctx *ctx, int64_t n, int p, const double *dX, int64_t ldx,
@@ -95,6 +97,12 @@ int boomgpu_set_logit_mixture(boomgpu_ctx *ctx, int K, const double *mu, const d
 int boomgpu_set_poisson_table(boomgpu_ctx *ctx, int ntab, const int64_t *nu, const int32_t *offset,
                               const double *weights, const double *mu, const double *sigma,
                               int64_t gaussian_cutoff);
+
+/* present[v] = 1 iff some uploaded / adopted Poisson row has count y == v, for 0 <= v < len (host array of len bytes).
+ * The reference extends its table lazily, per observation, inside the draw (NormalMixtureApproximationTable::approximate,
+ * NormalMixtureApproximation.cpp:472-532); here the host asks once per data set which counts occur, adds the missing
+ * entries by the same rule, and re-states the table. */
+int boomgpu_poisson_counts_present(boomgpu_ctx *ctx, unsigned char *present, int64_t len);
 
 /* ---- the hot path -------------------------------------------------------------------- */
 /* One imputation pass.  xtx: p x p (symmetric, both triangles filled), xty: p.  Synchronous. */
@@ -162,6 +170,11 @@ int boomgpu_poisson_loglike(boomgpu_ctx *ctx, const double *beta, double *loglik
 int boomgpu_binomial_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double log_alpha, double *loglike, double *gradient,
                                     double *hessian);
 int boomgpu_poisson_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *gradient, double *hessian);
+/* With a communicator attached (boomgpu_comm_init) the four log-likelihood entry points above all-reduce over the ranks
+ * before they answer: every rank gets the likelihood of ALL rows.  The *_device variants leave this rank's packed result
+ * [ -(Hessian) p*p | gradient p | {., log likelihood, ., .} ] at suf_dev for a caller-driven all-reduce. */
+int boomgpu_binomial_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double log_alpha, double *suf_dev);
+int boomgpu_poisson_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev);
 
 /* ---- instrumentation ------------------------------------------------------------------- */
 /* number of kernels this context has launched so far */

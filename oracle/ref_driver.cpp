@@ -234,6 +234,39 @@ void golden_poisson_table(const std::string &dir) {
 }
 
 // ------------------------------------------------------------------------------------
+// Off-grid counts: what NormalMixtureApproximationTable::approximate(nu) (NormalMixtureApproximation.cpp:472-532) returns from a
+// FRESH table (neighbours = grid entries) -- interpolated entries, Powell re-fits -- with its Kullback-Leibler divergence.
+void golden_poisson_offgrid(const std::string &dir) {
+  std::vector<std::string> rows;
+  int nus[] = {305, 333, 477, 495, 777, 1234, 2950, 4321, 5500, 12345, 29500};
+  for (int nu : nus) {
+    NormalMixtureApproximationTable table = create_poisson_mixture_approximation_table();
+    std::vector<int> idx;
+    {
+      Vector ser = table.serialize();
+      size_t i = 0;
+      while (i < ser.size()) { idx.push_back((int)lround(ser[i])); i += 2 + 3 * (size_t)lround(ser[i + 1]); }
+    }
+    auto ub = std::upper_bound(idx.begin(), idx.end(), nu);
+    int nu1 = *ub, nu0 = *(ub - 1);
+    int k0 = table.approximate(nu0).dim(), k1 = table.approximate(nu1).dim();
+    NormalMixtureApproximation a = table.approximate(nu);
+    NegLogGamma target(nu);
+    double kl = a.kullback_leibler(target);
+    std::ostringstream o; o << std::setprecision(17) << "{\"nu\": " << nu << ", \"nu0\": " << nu0 << ", \"nu1\": " << nu1
+                            << ", \"k0\": " << k0 << ", \"k1\": " << k1 << ", \"kl\": " << kl << ", \"mu\": [";
+    for (int k = 0; k < a.dim(); ++k) o << (k ? ", " : "") << a.mu()[k];
+    o << "], \"sigma\": [";
+    for (int k = 0; k < a.dim(); ++k) o << (k ? ", " : "") << a.sigma()[k];
+    o << "], \"weights\": [";
+    for (int k = 0; k < a.dim(); ++k) o << (k ? ", " : "") << a.weights()[k];
+    o << "]}";
+    rows.push_back(o.str());
+  }
+  write_file(dir + "/poisson_offgrid.json", list_json(rows));
+}
+
+// ------------------------------------------------------------------------------------
 void golden_loglike(const std::string &dir) {
   const int n = 48, p = 4;
   std::vector<double> X(n * p), y(n), nt(n), beta(p);
@@ -553,6 +586,7 @@ int main(int argc, char **argv) {
       if (what == "all" || what == "mixture") golden_mixture(dir);
       if (what == "all" || what == "suf") golden_suf(dir);
       if (what == "all" || what == "table") golden_poisson_table(dir);
+      if (what == "all" || what == "offgrid") golden_poisson_offgrid(dir);
       if (what == "all" || what == "loglike") golden_loglike(dir);
       if (what == "all" || what == "stats") golden_draw_stats(dir);
       if (what == "all" || what == "chains") golden_chains(dir);

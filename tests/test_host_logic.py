@@ -223,3 +223,40 @@ def test_find_posterior_mode_on_oracle_derivatives():
     ok3, _, _ = h.find_posterior_mode_with(lambda b: O.binomial_logit_loglike_derivs(X, y, nt, b), slab, spike, [False] * p,
                                            np.zeros(p), 1e-10)
     assert not ok3
+
+
+# ---------------------------------------------------------------- Poisson mixture table: counts off the shipped grid
+def test_poisson_table_offgrid_entries_follow_the_reference_rule(golden):
+    """NormalMixtureApproximationTable::approximate (NormalMixtureApproximation.cpp:472-532) restated on the host
+    (boom_b200/host/mixture_table.cpp) against the reference's own answers from a fresh table
+    (tests/golden/poisson_offgrid.json, oracle/ref_driver.cpp: golden_poisson_offgrid): the same branch is taken for every
+    count; interpolated entries are the reference's numbers; directly fitted entries (the reference runs Powell, here
+    Nelder-Mead from the rescaled lower neighbour) reach a Kullback-Leibler divergence at least as small."""
+    import boom_b200
+    boom_b200.load_poisson_mixture_table()
+    h = boom_b200.host()
+    nu_grid, off, w, mu, sig, cut = boom_b200.poisson_mixture_table_arrays()
+    for r in golden("poisson_offgrid.json"):
+        nu = int(r["nu"])
+        m, s, wt, kl = h.poisson_mixture_approximate(nu)
+        K = len(r["mu"])
+        assert len(m) == K == int(r["k0"])            # the lower neighbour's number of components
+        assert abs(wt.sum() - 1.0) < 1e-6 and np.all(s > 0) and np.all(np.diff(m) >= 0)
+        i0, i1 = np.searchsorted(nu_grid, int(r["nu0"])), np.searchsorted(nu_grid, int(r["nu1"]))
+        t = (nu - r["nu0"]) / (r["nu1"] - r["nu0"])
+        interp_mu = ((1 - t) * mu[off[i0]:off[i0 + 1]] + t * mu[off[i1]:off[i1 + 1]]) if r["k0"] == r["k1"] else None
+        interpolated_in_ref = interp_mu is not None and np.allclose(interp_mu, r["mu"], atol=1e-12)
+        if interpolated_in_ref:
+            np.testing.assert_allclose(m, r["mu"], rtol=0, atol=1e-13)
+            np.testing.assert_allclose(s, r["sigma"], rtol=0, atol=1e-13)
+            np.testing.assert_allclose(wt, r["weights"], rtol=0, atol=1e-13)
+            assert kl == pytest.approx(r["kl"], abs=2e-8) and kl < 1e-5
+        else:
+            assert interp_mu is None or not np.allclose(m, interp_mu, atol=1e-9)     # fitted here as well
+            assert kl <= max(r["kl"], 1e-7) * 1.05
+    # the table now holds the added entries, and asking again returns them unchanged
+    ser = h.poisson_mixture_table()
+    again = h.poisson_mixture_approximate(1234)
+    assert np.array_equal(h.poisson_mixture_table(), ser)
+    assert again[3] < 1e-6
+    boom_b200.load_poisson_mixture_table()    # back to the shipped table for the other tests
