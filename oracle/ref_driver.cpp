@@ -533,10 +533,11 @@ void golden_chains(const std::string &dir) {
 // ------------------------------------------------------------------------------------
 // bench <logit|spike|poisson> n p nonzero threads iters warmup
 int run_bench(int argc, char **argv) {
-  if (argc < 9) { fprintf(stderr, "usage: bench model n p nonzero threads iters warmup\n"); return 2; }
+  if (argc < 9) { fprintf(stderr, "usage: bench model n p nonzero threads iters warmup [zellner]\n"); return 2; }
   std::string kind = argv[2];
   int64_t n = atoll(argv[3]); int p = atoi(argv[4]); int nonzero = atoi(argv[5]);
   int threads = atoi(argv[6]); int iters = atoi(argv[7]); int warm = atoi(argv[8]);
+  const bool zellner = argc >= 10 && std::string(argv[9]) == "zellner";
   auto t0 = std::chrono::steady_clock::now();
   double secs = 0;
   GlobalRng::rng.seed(8675309);
@@ -554,7 +555,39 @@ int run_bench(int argc, char **argv) {
     timed(model);
   } else {
     Ptr<BinomialLogitModel> model = make_logit_model(n, p, nonzero, 20261017, 1, nullptr);
-    NEW(MvnModel, prior)(Vector(p, 0.0), SpdMatrix(p, 1.0));
+    Ptr<MvnModel> prior(new MvnModel(Vector(p, 0.0), SpdMatrix(p, 1.0)));
+    if (zellner) {
+      // LogitZellnerPrior (Interfaces/python/spikeslab/BayesBoom/spikeslab/priors.py:385-462) with its defaults:
+      // precision = X'X / n with the off-diagonal halved (diagonal_shrinkage = .5), mean = (trimmed logit of mean(y/n), 0, ...)
+      const std::vector<Ptr<BinomialRegressionData>> &dat(model->dat());
+      int nt = std::max(1, threads);
+      std::vector<std::vector<double>> part(nt, std::vector<double>((size_t)p * p, 0.0));
+      std::vector<double> ysum(nt, 0.0);
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nt; ++t) pool.emplace_back([&, t]() {
+        std::vector<double> &a(part[t]);
+        for (int64_t r = n * t / nt; r < n * (t + 1) / nt; ++r) {
+          const Vector &x(dat[r]->x());
+          ysum[t] += dat[r]->y() / dat[r]->n();
+          for (int i = 0; i < p; ++i) { const double xi = x[i]; double *row = a.data() + (size_t)i * p; for (int j = 0; j <= i; ++j) row[j] += xi * x[j]; }
+        }
+      });
+      for (auto &th : pool) th.join();
+      SpdMatrix prec(p, 0.0);
+      double ys = 0;
+      for (int t = 0; t < nt; ++t) ys += ysum[t];
+      for (int i = 0; i < p; ++i) for (int j = 0; j <= i; ++j) {
+        double v = 0;
+        for (int t = 0; t < nt; ++t) v += part[t][(size_t)i * p + j];
+        v /= (double)n;
+        if (i != j) v *= 0.5;
+        prec(i, j) = v; prec(j, i) = v;
+      }
+      Vector mean(p, 0.0);
+      double ph = std::min(.999, std::max(.001, ys / (double)n));
+      mean[0] = std::log(ph / (1 - ph));
+      prior = new MvnModel(mean, prec, true);
+    }
     if (kind == "spike") {
       model->coef().drop_all(); model->coef().add(0);
       NEW(VariableSelectionPrior, spike)(p, std::min(1.0, (double)std::max(nonzero, 1) / p));

@@ -44,15 +44,15 @@ def test_our_arm_needs_a_gpu():
 def test_our_arm_line_carries_the_contract_keys():
     """One short run of our arm (C1 is the CPU-sized config): the JSON line has every key of the bench contract and the
     numbers hang together (launches counted, roofline fraction = achieved / peak, e2e measured with host buffers)."""
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "c1", "--steps", "5", "--warmup", "3"],
-                         capture_output=True, text=True, timeout=900)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "c1", "--steps", "5", "--warmup", "3",
+                          "--no-secondary"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads(out.stdout.strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
                 "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert key in d, key
     assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] == 3 and d["dtype"] == "f64" and d["vs_baseline"] is None
-    assert d["gpu_launches"] >= 2 * d["steps"]
+    assert d["gpu_launches"] >= d["steps"]
     r = d["roofline"]
     assert r["bound"] in ("hbm", "tensor") and r["frac"] == pytest.approx(r["achieved"] / r["peak"]) and r["achieved"] > 0
     e = d["e2e"]

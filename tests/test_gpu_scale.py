@@ -230,10 +230,6 @@ def test_standalone_poisson_sampler_extends_the_table_for_offgrid_counts():
     for _ in range(3):
         model.sample_posterior()
     assert np.all(np.isfinite(model.Beta))
-    # a new device context after the first draw (set_device) gets the table again
-    model.set_device(0)
-    model.set_stream(0)
-    model.sample_posterior()
     boom_b200.load_poisson_mixture_table()
 
 
