@@ -61,8 +61,9 @@ struct boomgpu_ctx {
   int64_t tab_cut_h = -1;
 
   // workspaces
-  double *beta_dev = nullptr; int beta_cap = 0;
+  double *beta_dev = nullptr; int beta_cap = 0;   // [p + 2 doubles | p ints: indices of beta's non-zeros (gather pass)]
   double *beta_pin = nullptr;
+  int gather = 0;                                  // option: 0 auto (sparse beta -> gather pass), 1 never, 2 whenever beta has a zero
   double *suf_dev = nullptr; int64_t suf_cap = 0;
   double *suf_pin = nullptr; int64_t suf_pin_cap = 0;
   double *partials = nullptr; int64_t partials_cap = 0;
@@ -390,13 +391,15 @@ struct TmaLauncher {
 };
 
 template <int MODEL>
-cudaError_t launch_impute_rows(boomgpu_ctx *ctx, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts) {
+cudaError_t launch_impute_rows(boomgpu_ctx *ctx, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts, int nnz) {
   const bool vec2 = (d.ldx % 2 == 0) && aligned16(d.X);
-  const size_t smem = sizeof(double) * (size_t)(d.p + 2);
+  const bool gather = nnz >= 0;
+  const size_t smem = gather ? sizeof(double) * (size_t)(nnz + 1) + sizeof(int) * (size_t)(nnz + 2) : sizeof(double) * (size_t)(d.p + 2);
   const int64_t ngroups = (d.n + 31) / 32;
   int occ = 1;
   cudaError_t e;
-  if (vec2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, impute_rows_kernel<MODEL, true>, kImputeThreads, smem);
+  if (gather) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, impute_rows_gather_kernel<MODEL>, kImputeThreads, smem);
+  else if (vec2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, impute_rows_kernel<MODEL, true>, kImputeThreads, smem);
   else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, impute_rows_kernel<MODEL, false>, kImputeThreads, smem);
   if (e != cudaSuccess) return e;
   occ = std::max(occ, 1);
@@ -410,7 +413,11 @@ cudaError_t launch_impute_rows(boomgpu_ctx *ctx, const RowData &d, const DrawPar
   }
   {
     LaunchScope ls(ctx, 1);
-    if (vec2)
+    if (gather)
+      impute_rows_gather_kernel<MODEL><<<grid, kImputeThreads, smem, ctx->stream>>>(
+          d, prm, out, ctx->beta_dev, reinterpret_cast<const int *>(ctx->beta_dev + d.p + 2), nnz, ctx->w_buf, ctx->s_buf,
+          ctx->scal_partials, ctx->err_dev);
+    else if (vec2)
       impute_rows_kernel<MODEL, true><<<grid, kImputeThreads, smem, ctx->stream>>>(d, prm, out, ctx->beta_dev, ctx->w_buf,
                                                                                   ctx->s_buf, ctx->scal_partials, ctx->err_dev);
     else
@@ -484,8 +491,9 @@ int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, c
   if (ctx->beta_cap < p + 2) {
     if (ctx->beta_dev) { CU(cudaFree(ctx->beta_dev)); ctx->beta_dev = nullptr; }
     if (ctx->beta_pin) { CU(cudaFreeHost(ctx->beta_pin)); ctx->beta_pin = nullptr; }
-    CU(cudaMalloc((void **)&ctx->beta_dev, sizeof(double) * (size_t)(p + 2)));
-    CU(cudaMallocHost((void **)&ctx->beta_pin, sizeof(double) * (size_t)(p + 2)));
+    const size_t bytes = sizeof(double) * (size_t)(p + 2) + sizeof(int) * (size_t)(p + 2);
+    CU(cudaMalloc((void **)&ctx->beta_dev, bytes));
+    CU(cudaMallocHost((void **)&ctx->beta_pin, bytes));
     ctx->beta_cap = p + 2;
   }
   if (MODEL != kSupplied) {
@@ -493,8 +501,18 @@ int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, c
   } else {
     memset(ctx->beta_pin, 0, sizeof(double) * p);
   }
+  // sparse beta (spike and slab): the included columns, for the gather pass.  Worth it while nnz 32-byte sectors per row
+  // are fewer bytes than the 8 p byte row, i.e. nnz < p / 4 (auto); the dense pass otherwise.
+  int nnz = -1;
+  if (path == 2 && MODEL != kSupplied && ctx->gather != 1) {
+    int *idx = reinterpret_cast<int *>(ctx->beta_pin + p + 2);
+    int c = 0;
+    for (int j = 0; j < p; ++j) if (ctx->beta_pin[j] != 0.0) idx[c++] = j;
+    if (ctx->gather == 2 ? c < p : 4 * c < p) nnz = c;
+  }
   if (!tma_small)   // the TMA small-p kernel takes beta as a kernel parameter
-    CU(cudaMemcpyAsync(ctx->beta_dev, ctx->beta_pin, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->beta_dev, ctx->beta_pin, sizeof(double) * (size_t)(p + 2) + (nnz >= 0 ? sizeof(int) * (size_t)nnz : 0),
+                       cudaMemcpyHostToDevice, ctx->stream));
 
   RowData d;
   d.X = ctx->X; d.ldx = ctx->ldx; d.n = ctx->n; d.p = p;
@@ -533,7 +551,7 @@ int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, c
       CU(cudaMemcpyAsync(ctx->s_buf, s_in, sizeof(double) * (size_t)ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
       CU(cudaMemsetAsync(suf + (int64_t)p * p + p, 0, sizeof(double) * 4, ctx->stream));
     } else {
-      cudaError_t e = launch_impute_rows<MODEL>(ctx, d, prm, out, &nparts);
+      cudaError_t e = launch_impute_rows<MODEL>(ctx, d, prm, out, &nparts, nnz);
       if (e != cudaSuccess) return fail(ctx, BOOMGPU_ERR_CUDA, "impute_rows_kernel launch failed: %s", cudaGetErrorString(e));
       LaunchScope ls(ctx, 3);
       reduce_scalars_kernel<<<1, 32, 0, ctx->stream>>>(ctx->scal_partials, nparts, suf + (int64_t)p * p + p);
@@ -791,6 +809,11 @@ int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value) {
     return 0;
   }
   if (!strcmp(name, "timing")) { ctx->timing = value != 0; return 0; }
+  if (!strcmp(name, "gather")) {
+    if (value < 0 || value > 2) return fail(ctx, BOOMGPU_ERR_ARG, "gather must be 0 (auto), 1 (never) or 2 (whenever beta has a zero)");
+    ctx->gather = (int)value;
+    return 0;
+  }
   if (!strcmp(name, "small_variant")) {
     if (value < 0 || value > 1) return fail(ctx, BOOMGPU_ERR_ARG, "small_variant must be 0 or 1");
     ctx->small_variant = (int)value;

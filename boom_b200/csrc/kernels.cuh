@@ -411,6 +411,54 @@ impute_rows_kernel(RowData d, DrawParams prm, RowOut out, const double *__restri
   }
 }
 
+// Pass 1 when beta is sparse (spike-and-slab: beta is EXACTLY zero off the included set, GlmCoefs.cpp:304-309, and the
+// included set is ~20 of 500 columns at C3): lane r owns row r of the warp's 32 rows and reads only the included columns --
+// one 32-byte sector per column and row (fewer when included columns are neighbours: the sector stays in L1) instead of
+// the whole 8 p byte row.  eta is the same sum with the zero terms left out.  nnz indices / values sit in shared memory.
+template <int MODEL>
+__global__ void __launch_bounds__(kImputeThreads)
+impute_rows_gather_kernel(RowData d, DrawParams prm, RowOut out, const double *__restrict__ beta, const int *__restrict__ nz_idx, int nnz,
+                          double *__restrict__ w_buf, double *__restrict__ s_buf, double *__restrict__ scalar_partials, int *err) {
+  extern __shared__ __align__(128) double smem[];
+  double *b_s = smem;                                   // nnz values
+  int *i_s = reinterpret_cast<int *>(smem + nnz);       // nnz column indices
+  __shared__ double red_s[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int j = tid; j < nnz; j += kImputeThreads) { const int c = nz_idx[j]; i_s[j] = c; b_s[j] = beta[c]; }
+  __syncthreads();
+
+  double sc_count = 0, sc_ywy = 0, sc_sumw = 0, sc_sumlogw = 0;
+  const int64_t ngroups = (d.n + 31) / 32;
+  const int warps_per_grid = gridDim.x * (kImputeThreads / 32);
+  for (int64_t g = (int64_t)blockIdx.x * (kImputeThreads / 32) + wid; g < ngroups; g += warps_per_grid) {
+    const int64_t i = g * 32 + lane;
+    if (i < d.n) {
+      const RowObs obs = load_obs<MODEL>(d, i);
+      const double *xr = d.X + i * d.ldx;
+      double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+      int j = 0;
+      for (; j + 4 <= nnz; j += 4) {
+        const double x0 = __ldg(xr + i_s[j]), x1 = __ldg(xr + i_s[j + 1]), x2 = __ldg(xr + i_s[j + 2]), x3 = __ldg(xr + i_s[j + 3]);
+        e0 = fma(x0, b_s[j], e0); e1 = fma(x1, b_s[j + 1], e1); e2 = fma(x2, b_s[j + 2], e2); e3 = fma(x3, b_s[j + 3], e3);
+      }
+      for (; j < nnz; ++j) e0 = fma(__ldg(xr + i_s[j]), b_s[j], e0);
+      const double eta = (e0 + e1) + (e2 + e3);
+      RowLatent r = impute_row<MODEL>(d, prm, out, obs, i, eta, err);
+      sc_count += r.count; sc_ywy += r.yWy; sc_sumw += r.w; sc_sumlogw += r.sumlogw;
+      w_buf[i] = r.w;
+      s_buf[i] = r.s;
+    }
+  }
+  double v0 = warp_sum(sc_count), v1 = warp_sum(sc_ywy), v2 = warp_sum(sc_sumw), v3 = warp_sum(sc_sumlogw);
+  if (lane == 0) { red_s[wid * 4 + 0] = v0; red_s[wid * 4 + 1] = v1; red_s[wid * 4 + 2] = v2; red_s[wid * 4 + 3] = v3; }
+  __syncthreads();
+  if (tid < 4) {
+    double s = 0;
+    for (int w = 0; w < kImputeThreads / 32; ++w) s += red_s[w * 4 + tid];
+    scalar_partials[(int64_t)blockIdx.x * 4 + tid] = s;
+  }
+}
+
 // =============================================================================================
 // Pass 2 for p > 64: split-K weighted SYRK on FP64 DMMA.
 //
@@ -519,8 +567,14 @@ struct SyrkWarpCtx {
 // The k loop of one consumer warp.  T0/T1: unit type (0 none, 1 full 4x4 atoms, 2 diagonal unit: the 10
 // atoms with n >= m); DUTY: which unit (1 or 2; 0 none) also accumulates X's for its row block.
 // Two full units of one warp always share their A fragments (same row block).
-template <int T0, int T1, int DUTY>
+// NM (1..4): how many 8-column atoms of the warp's LAST unit lie inside X.  p that is not a multiple of 32 leaves the last
+// unit column ragged (p = 500: 3 of 4 atoms); only a warp's last unit can be ragged (the unit table lists a warp's units
+// left to right), a full unit is then cut in n only, a diagonal unit in m and n.  Compile-time so that the cut atoms are
+// neither loaded nor multiplied (they used to be computed and masked at the store: 3 % of the DMMAs at p = 500).
+template <int T0, int T1, int DUTY, int NM>
 __device__ __forceinline__ void syrk_consume(const SyrkWarpCtx &wc) {
+  constexpr int M0 = (T1 == 0 && T0 == 2) ? NM : 4, N0 = (T1 == 0) ? NM : 4;   // atom limits of unit 0
+  constexpr int M1 = (T1 == 2) ? NM : 4, N1 = NM;                               // ... of unit 1
   const int lane = wc.lane;
   double c0[4][4][2], c1[4][4][2], cx[4][2];
 #pragma unroll
@@ -548,33 +602,35 @@ __device__ __forceinline__ void syrk_consume(const SyrkWarpCtx &wc) {
         const double *xr = stage + row * kSyrkPanelLd;
         double a[4], aw[4], b[4];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) { a[m] = xr[a0_off + 8 * m]; aw[m] = a[m] * wv; b[m] = xr[b0_off + 8 * m]; }
+        for (int m = 0; m < M0; ++m) { a[m] = xr[a0_off + 8 * m]; aw[m] = a[m] * wv; }
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
+        for (int n = 0; n < N0; ++n) b[n] = xr[b0_off + 8 * n];
 #pragma unroll
-          for (int n = 0; n < 4; ++n)
+        for (int m = 0; m < M0; ++m)
+#pragma unroll
+          for (int n = 0; n < N0; ++n)
             if (T0 == 1 || n >= m) dmma884(c0[m][n][0], c0[m][n][1], aw[m], b[n]);
         if (DUTY == 1) {  // X's: four DFMA on the A fragments already in registers (a DMMA with B = [s, 0, ..] wasted 7/8 of it)
           const double sv = s_s[row];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) cx[m][0] = fma(a[m], sv, cx[m][0]);
+          for (int m = 0; m < M0; ++m) cx[m][0] = fma(a[m], sv, cx[m][0]);
         }
         if (T1 != 0) {
           if (!kSameA) {
 #pragma unroll
-            for (int m = 0; m < 4; ++m) { a[m] = xr[a1_off + 8 * m]; aw[m] = a[m] * wv; }
+            for (int m = 0; m < M1; ++m) { a[m] = xr[a1_off + 8 * m]; aw[m] = a[m] * wv; }
           }
 #pragma unroll
-          for (int m = 0; m < 4; ++m) b[m] = xr[b1_off + 8 * m];
+          for (int n = 0; n < N1; ++n) b[n] = xr[b1_off + 8 * n];
 #pragma unroll
-          for (int m = 0; m < 4; ++m)
+          for (int m = 0; m < M1; ++m)
 #pragma unroll
-            for (int n = 0; n < 4; ++n)
+            for (int n = 0; n < N1; ++n)
               if (T1 == 1 || n >= m) dmma884(c1[m][n][0], c1[m][n][1], aw[m], b[n]);
           if (DUTY == 2) {
             const double sv = s_s[row];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) cx[m][0] = fma(a[m], sv, cx[m][0]);
+            for (int m = 0; m < M1; ++m) cx[m][0] = fma(a[m], sv, cx[m][0]);
           }
         }
       }
@@ -612,6 +668,42 @@ __device__ __forceinline__ void syrk_consume(const SyrkWarpCtx &wc) {
       for (int m = 0; m < 4; ++m)
         if (m < mmax) tile[128 * 128 + 32 * ui + 8 * m + (lane >> 2)] = cx[m][0];
     }
+  }
+}
+
+template <int NM>
+__device__ __forceinline__ void syrk_dispatch_nm(int role, const SyrkWarpCtx &wc) {
+  if (kSyrkConsumerWarps == 8) {
+    switch (role) {
+      case 0:   syrk_consume<0, 0, 0, 4>(wc); break;
+      case 100: syrk_consume<1, 0, 0, NM>(wc); break;
+      case 101: syrk_consume<1, 0, 1, NM>(wc); break;
+      case 110: syrk_consume<1, 1, 0, NM>(wc); break;
+      case 200: syrk_consume<2, 0, 0, NM>(wc); break;
+      case 201: syrk_consume<2, 0, 1, NM>(wc); break;
+      case 220: syrk_consume<2, 2, 0, NM>(wc); break;
+      case 221: syrk_consume<2, 2, 1, NM>(wc); break;
+      case 222: syrk_consume<2, 2, 2, NM>(wc); break;
+      default: __trap();
+    }
+  } else {   // one unit per warp: the two-unit roles are not instantiated (they would set the kernel's register count)
+    switch (role) {
+      case 0:   syrk_consume<0, 0, 0, 4>(wc); break;
+      case 100: syrk_consume<1, 0, 0, NM>(wc); break;
+      case 101: syrk_consume<1, 0, 1, NM>(wc); break;
+      case 200: syrk_consume<2, 0, 0, NM>(wc); break;
+      case 201: syrk_consume<2, 0, 1, NM>(wc); break;
+      default: __trap();
+    }
+  }
+}
+__device__ __forceinline__ void syrk_dispatch_role(int role, int nm, const SyrkWarpCtx &wc) {
+  switch (nm) {
+    case 4: syrk_dispatch_nm<4>(role, wc); break;
+    case 3: syrk_dispatch_nm<3>(role, wc); break;
+    case 2: syrk_dispatch_nm<2>(role, wc); break;
+    case 1: syrk_dispatch_nm<1>(role, wc); break;
+    default: __trap();
   }
 }
 
@@ -695,30 +787,9 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap xmap, SyrkParams prm, SyrkU
   wc.mmax0 = mmax0; wc.nmax0 = nmax0; wc.mmax1 = mmax1; wc.nmax1 = nmax1;
   wc.tile = prm.partials + ((int64_t)kslice * prm.nregions + region) * kSyrkTileLen;
 
-  const int role = t0 * 100 + t1 * 10 + duty;
-  if (kSyrkConsumerWarps == 8) {
-    switch (role) {
-      case 0:   syrk_consume<0, 0, 0>(wc); break;
-      case 100: syrk_consume<1, 0, 0>(wc); break;
-      case 101: syrk_consume<1, 0, 1>(wc); break;
-      case 110: syrk_consume<1, 1, 0>(wc); break;
-      case 200: syrk_consume<2, 0, 0>(wc); break;
-      case 201: syrk_consume<2, 0, 1>(wc); break;
-      case 220: syrk_consume<2, 2, 0>(wc); break;
-      case 221: syrk_consume<2, 2, 1>(wc); break;
-      case 222: syrk_consume<2, 2, 2>(wc); break;
-      default: __trap();
-    }
-  } else {   // one unit per warp: the two-unit roles are not instantiated (they would set the kernel's register count)
-    switch (role) {
-      case 0:   syrk_consume<0, 0, 0>(wc); break;
-      case 100: syrk_consume<1, 0, 0>(wc); break;
-      case 101: syrk_consume<1, 0, 1>(wc); break;
-      case 200: syrk_consume<2, 0, 0>(wc); break;
-      case 201: syrk_consume<2, 0, 1>(wc); break;
-      default: __trap();
-    }
-  }
+  // atoms of the warp's last unit inside X (1..4); earlier units of the warp are whole
+  const int nm = t1 ? nmax1 : (t0 ? nmax0 : 4);
+  syrk_dispatch_role(t0 * 100 + t1 * 10 + duty, nm, wc);
 }
 
 // Sums partial tiles over k-slices (fixed order) into the p x p matrix (both triangles) and xty.

@@ -74,6 +74,8 @@ int boomgpu_set_row_offset(boomgpu_ctx *ctx, uint64_t first_global_row);
 /* options: "path" = 0 auto | 1 fused single pass (p <= 64) | 2 two-pass imputer + DMMA SYRK;
  *          "small_variant" = 0 auto (TMA-fed kernel when X has an even leading dimension and a 16-byte aligned base) |
  *                            1 force the cp.async kernel;
+ *          "gather" = 0 auto (two-pass path: a beta with fewer than p / 4 non-zeros reads only those columns of X in the
+ *                     imputer pass) | 1 never | 2 whenever beta has a zero;
  *          "timing" = 1 records CUDA events around every kernel (boomgpu_get_timings) */
 int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value);
 

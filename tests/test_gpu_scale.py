@@ -266,3 +266,27 @@ def test_clt_threshold_beyond_the_slot_field_is_rejected():
         ctx.logit_step(beta, 70000, 1, 0)
     ctx.logit_step(beta, 65535, 1, 0)
     ctx.close()
+
+
+@pytest.mark.parametrize("n,p,nnz", [(5003, 200, 0), (5003, 200, 1), (4001, 500, 21), (3000, 130, 32), (3000, 130, 129)])
+def test_gather_imputer_pass_matches_the_dense_pass(n, p, nnz):
+    """Two-pass path with a sparse beta (spike and slab): the imputer pass that reads only the included columns (option
+    gather: 0 auto, 1 never, 2 whenever beta has a zero) against the dense pass and against the oracle."""
+    X, y, nt, _ = O.synth_binomial(n, p, 5, seed=380 + nnz, max_trials=3)
+    rng = np.random.default_rng(nnz)
+    beta = np.zeros(p)
+    cols = rng.choice(p, size=min(nnz, p), replace=False)
+    beta[cols] = rng.normal(size=len(cols)) * 0.4
+    mix = O.logit_mixture()
+    rs, rw = O.logit_draw(X, y, nt, beta, 10, mix, 7, 3)
+    rxtx, rxty, rss, _ = O.logit_step(X, y, nt, beta, 10, mix, 7, 3)
+    for gather in (1, 2, 0):
+        ctx, _ = logit_ctx(X, y, nt, path=2)
+        ctx.set_option("gather", gather)
+        s, w = ctx.logit_draw(beta, 10, seed=7, iteration=3)
+        np.testing.assert_allclose(w, rw, rtol=1e-13)
+        np.testing.assert_allclose(s, rs, rtol=1e-9, atol=1e-9)
+        xtx, xty, ss = ctx.logit_step(beta, 10, seed=7, iteration=3)
+        assert ss == rss == n
+        assert normwise_err(xtx, rxtx) < 1e-11 and vec_err(xty, rxty) < 1e-10
+        ctx.close()
