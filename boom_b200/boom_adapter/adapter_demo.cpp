@@ -4,8 +4,9 @@
 // then attaches EITHER the reference sampler OR the B200 sampler with model->set_method(sampler) and calls
 // model->sample_posterior().  Prints one JSON line with the posterior summaries of both chains on the same
 // data; tests/test_gpu_adapter.py compares them within Monte Carlo error.
-//   usage: boom_adapter_demo <logit|spike|poisson|pspike|mode|pmode|fixed|pfixed> n p nonzero iters burn
-//          (mode / pmode: find_posterior_mode; fixed / pfixed: externally driven statistics, host steps only, no GPU)
+//   usage: boom_adapter_demo <logit|spike|poisson|pspike|mode|pmode|fixed|pfixed|bench|api> n p nonzero iters burn
+//          (mode / pmode: find_posterior_mode; fixed / pfixed: externally driven statistics, host steps only, no GPU;
+//           bench: ms per iteration of the adapter beside the standalone classes; api: the public surface beyond draw())
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -85,6 +86,95 @@ int main(int argc, char **argv) {
     }
     NEW(MvnModel, slab)(Vector(p, 0.0), SpdMatrix(p, 1.0));
     NEW(VariableSelectionPrior, spike)(p, std::min(1.0, (nonzero + 1.0) / p));
+    if (kind == "bench") {
+      // ms per Gibbs iteration of the adapter on BOOM's own model (n heap objects) beside the standalone host classes on
+      // the same rows: what the BOOM-typed surface costs on top of the device step (bench.py: e2e_adapter).
+      NEW(BinomialLogitModel, model)(p);
+      for (int i = 0; i < n; ++i) model->add_data(new BinomialRegressionData(ys[i], 1.0, xs[i]));
+      model->coef().drop_all(); model->coef().add(0);
+      RNG seeder(5);
+      Ptr<B200::BinomialLogitSpikeSlabSampler> s(new B200::BinomialLogitSpikeSlabSampler(model.get(), slab, spike, 10, seeder));
+      model->set_method(s);
+      auto tp = std::chrono::steady_clock::now();
+      model->sample_posterior();   // packs + uploads the rows, first iteration
+      const double first = std::chrono::duration<double>(std::chrono::steady_clock::now() - tp).count();
+      for (int i = 0; i < burn; ++i) model->sample_posterior();
+      const double d0 = s->seconds_in_device_step(), h0 = s->seconds_in_host_steps();
+      auto t0 = std::chrono::steady_clock::now();
+      for (int i = 0; i < iters; ++i) model->sample_posterior();
+      const double adapter_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      const double dev_s = s->seconds_in_device_step() - d0, host_s = s->seconds_in_host_steps() - h0;
+      const int nvars = (int)model->coef().inc().nvars();
+      // the standalone classes on the same rows
+      std::vector<double> X((size_t)n * p), y(n), nt(n, 1.0);
+      for (int i = 0; i < n; ++i) { std::copy(xs[i].begin(), xs[i].end(), X.begin() + (size_t)i * p); y[i] = ys[i]; }
+      BOOM_B200::BinomialLogitModel hm(n, p, X.data(), y.data(), nt.data());
+      hm.coef().drop_all(); hm.coef().add(0);
+      BOOM_B200::RNG hseed(5);
+      auto hslab = std::make_shared<BOOM_B200::MvnModel>(BOOM_B200::Vector(p, 0.0), BOOM_B200::SpdMatrix(p, 1.0));
+      auto hspike = std::make_shared<BOOM_B200::VariableSelectionPrior>(p, std::min(1.0, (nonzero + 1.0) / p));
+      auto hs = std::make_shared<BOOM_B200::BinomialLogitSpikeSlabSampler>(&hm, hslab, hspike, 10, hseed);
+      hm.set_method(hs);
+      for (int i = 0; i < burn + 1; ++i) hm.sample_posterior();
+      auto t1 = std::chrono::steady_clock::now();
+      for (int i = 0; i < iters; ++i) hm.sample_posterior();
+      const double standalone_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+      printf("{\"kind\": \"bench\", \"n\": %d, \"p\": %d, \"iters\": %d, \"adapter_ms_per_iter\": %.4f, \"adapter_device_ms\": %.4f, "
+             "\"adapter_host_ms\": %.4f, \"standalone_ms_per_iter\": %.4f, \"adapter_first_iteration_with_upload_s\": %.3f, "
+             "\"model_size_at_end\": %d}\n",
+             n, p, iters, 1e3 * adapter_s / iters, 1e3 * dev_s / iters, 1e3 * host_s / iters, 1e3 * standalone_s / iters, first, nvars);
+      return 0;
+    }
+    if (kind == "api") {
+      // the public surface beyond draw(): draw_model_indicators / draw_beta / log_model_prob, suf() in the reference's own
+      // type, in-place row edits.  Compared with the reference sampler fed the SAME externally driven statistics.
+      NEW(BinomialLogitModel, model)(p);
+      for (int i = 0; i < n; ++i) model->add_data(new BinomialRegressionData(ys[i], 1.0, xs[i]));
+      model->coef().drop_all(); model->coef().add(0);
+      RNG seeder(9);
+      Ptr<B200::BinomialLogitSpikeSlabSampler> s(new B200::BinomialLogitSpikeSlabSampler(model.get(), slab, spike, 10, seeder));
+      s->impute_latent_data();
+      const BinomialLogit::SufficientStatistics &suf(s->suf());          // the reference's type
+      // feed the reference sampler the same statistics through its own update hook: x = e_j pieces are not enough for a
+      // full matrix, so compare log_model_prob on statistics BOTH samplers build from the same external updates instead
+      NEW(BinomialLogitModel, m2)(p);
+      m2->coef().drop_all(); m2->coef().add(0);
+      NEW(BinomialLogitSpikeSlabSampler, r)(m2.get(), slab, spike, 10, seeder);
+      Ptr<B200::BinomialLogitSpikeSlabSampler> s2(new B200::BinomialLogitSpikeSlabSampler(m2.get(), slab, spike, 10, seeder));
+      r->fix_latent_data(true); s2->fix_latent_data(true);
+      r->clear_complete_data_sufficient_statistics(); s2->clear_complete_data_sufficient_statistics();
+      RNG data_rng(3);
+      for (int i = 0; i < n; ++i) {
+        const double w = 0.1 + runif_mt(data_rng), z = xs[i].dot(beta) + rnorm_mt(data_rng) / sqrt(w);
+        r->update_complete_data_sufficient_statistics(w * z, w, xs[i]);
+        s2->update_complete_data_sufficient_statistics(w * z, w, xs[i]);
+      }
+      Vector lref, lgpu;
+      for (int trial = 0; trial < 6; ++trial) {
+        Selector g(p, false);
+        g.add(0);
+        for (int j = 1; j < p; ++j) if ((j + trial) % 3 == 0 || j <= trial) g.add(j);
+        lref.push_back(r->log_model_prob(g)); lgpu.push_back(s2->log_model_prob(g));
+      }
+      const double xtx_diff = (r->suf().xtx() - s2->suf().xtx()).max_abs(), xty_diff = (r->suf().xty() - s2->suf().xty()).max_abs();
+      s2->draw_model_indicators();
+      s2->draw_beta();
+      const int nv = (int)m2->coef().inc().nvars();
+      // in-place edit of one row is seen after observe_rows(true)
+      s->observe_rows(true);
+      const double before = s->suf().xtx()(1, 1);
+      Vector x0 = model->dat()[0]->x();
+      x0[1] += 100.0;
+      model->dat()[0]->set_x(x0);
+      s->impute_latent_data();
+      const double after = s->suf().xtx()(1, 1);
+      printf("{\"kind\": \"api\", \"suf_sample_size\": %d, \"suf_xtx00\": %.10g, ", suf.sample_size(), before);
+      print_vec("log_model_prob_reference", lref); print_vec("log_model_prob_b200", lgpu);
+      printf("\"external_xtx_max_abs_diff\": %.3g, \"external_xty_max_abs_diff\": %.3g, \"nvars_after_sweep\": %d, "
+             "\"xtx11_before_edit\": %.10g, \"xtx11_after_edit\": %.10g, \"reference_sample_size\": %d, \"b200_sample_size\": %d}\n",
+             xtx_diff, xty_diff, nv, before, after, r->suf().sample_size(), s2->suf().sample_size());
+      return 0;
+    }
     if (kind == "mode" || kind == "pmode") {
       // find_posterior_mode of both spike-and-slab samplers from the same start, on the model with the first
       // nonzero + 1 coefficients included

@@ -1,6 +1,7 @@
 // boom_b200_adapter.cpp -- see boom_b200_adapter.hpp.
 #include "boom_b200_adapter.hpp"
 
+#include <chrono>
 #include <map>
 #include <set>
 
@@ -8,6 +9,7 @@
 #include "Models/Glm/PosteriorSamplers/BinomialLogitDataImputer.hpp"
 #include "Models/Glm/PosteriorSamplers/NormalMixtureApproximation.hpp"
 #include "Models/Glm/PosteriorSamplers/poisson_mixture_approximation_table.hpp"
+#include "Models/MvnModel.hpp"
 #include "cpputil/report_error.hpp"
 #include "distributions.hpp"
 
@@ -30,9 +32,30 @@ std::shared_ptr<BOOM_B200::VariableSelectionPrior> to_host(const VariableSelecti
 }
 }  // namespace
 
-DeviceImputerBase::DeviceImputerBase(int xdim, RNG &seeding_rng) : PosteriorSampler(seeding_rng), suf_(xdim), xdim_(xdim) {}
+// What the host steps need from the BOOM priors, converted once and kept until the priors change.  The reference reads
+// slab_->siginv() / spike_ live in every draw; here the p x p precision is copied into the host layout only when (a) the
+// sampler is handed another prior object (set_slab / set_spike), or (b) the slab is a BOOM::MvnModel whose parameters
+// signal a change (observers on Mu_prm / Sigma_prm), or (c) the slab is some other MvnBase, whose changes cannot be
+// observed -- then it is re-read every draw, as the reference does.
+struct DeviceImputerBase::PriorCache {
+  const MvnBase *slab = nullptr;
+  const VariableSelectionPrior *spike = nullptr;
+  uint64_t version = 0;
+  bool fisher_yates = false, observable = false;
+  Ptr<VectorParams> mu_prm;
+  Ptr<SpdParams> sigma_prm;
+  std::unique_ptr<BOOM_B200::SpikeSlabCore> core;
+};
 
-DeviceImputerBase::~DeviceImputerBase() { boomgpu_destroy(ctx_); }
+DeviceImputerBase::DeviceImputerBase(int xdim, RNG &seeding_rng) : PosteriorSampler(seeding_rng), hsuf_(xdim), xdim_(xdim) {}
+
+DeviceImputerBase::~DeviceImputerBase() {
+  if (prior_cache_ && prior_cache_->observable) {
+    prior_cache_->mu_prm->remove_observer(observer_key());
+    prior_cache_->sigma_prm->remove_observer(observer_key());
+  }
+  boomgpu_destroy(ctx_);
+}
 
 void DeviceImputerBase::check(int rc) const {
   if (rc) report_error(std::string("boomgpu: ") + boomgpu_last_error(ctx_));
@@ -42,6 +65,12 @@ void DeviceImputerBase::set_device(int device) {
   if (ctx_ && device != device_) { boomgpu_destroy(ctx_); ctx_ = nullptr; }
   device_ = device;
   stale_ = true;
+}
+
+void DeviceImputerBase::observe_rows(bool tf) {
+  if (tf == observing_rows_) return;
+  observe_row_objects(tf);
+  observing_rows_ = tf;
 }
 
 void DeviceImputerBase::ensure_device_rows() {
@@ -55,9 +84,23 @@ void DeviceImputerBase::ensure_device_rows() {
     comm_dirty_ = false;
   }
   if (stale_ || repack_each_time_) {
-    pack_and_upload(ctx_);
+    install_tables(ctx_);
+    // rows go to the device a chunk at a time (about 32 MB of X): no second n x p copy on the host
+    const int64_t n = row_count();
+    const int p = xdim_;
+    const int64_t chunk = std::max<int64_t>(1024, (int64_t)(32u << 20) / (8 * (int64_t)p));
+    std::vector<double> X((size_t)std::min(n, chunk) * p), aux((size_t)std::min(n, chunk));
+    std::vector<int64_t> y((size_t)std::min(n, chunk));   // 8 bytes per row: doubles (binomial) or int64 (poisson)
+    check(boomgpu_upload_begin(ctx_, rows_are_poisson() ? 1 : 0, n, p));
+    for (int64_t row0 = 0; row0 < n; row0 += chunk) {
+      const int64_t rows = std::min(chunk, n - row0);
+      pack_rows(row0, rows, X.data(), y.data(), aux.data());
+      check(boomgpu_upload_rows(ctx_, row0, rows, X.data(), p, y.data(), aux.data()));
+    }
+    check(boomgpu_upload_end(ctx_));
     check(boomgpu_set_row_offset(ctx_, row_offset_));
     stale_ = false;
+    if (observing_rows_) observe_row_objects(true);   // rows added since the last pack are observed too
   }
 }
 
@@ -75,87 +118,157 @@ class DerivsProxy : public BOOM_B200::GlmModelBase {
  private:
   Fn f_;
 };
+
+struct Stopwatch {
+  double &acc;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit Stopwatch(double &a) : acc(a) {}
+  ~Stopwatch() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
 }  // namespace
 
-bool DeviceImputerBase::find_mode(GlmCoefs &coef, const MvnBase &slab, const VariableSelectionPrior &spike, double epsilon,
+// log likelihood, gradient and Hessian over ALL ranks' rows: natively all-reduced inside the C ABI when a communicator is
+// attached; through the caller's hook otherwise (packed [-H | g | {., ll, ., .}] on the device, like a Gibbs step)
+double DeviceImputerBase::loglike_derivs(const BOOM_B200::Vector &b, BOOM_B200::Vector *g, BOOM_B200::SpdMatrix *h) {
+  const int p = xdim_;
+  double ll = 0;
+  if (g) g->assign(p, 0.0);
+  if (h && h->dim != p) *h = BOOM_B200::SpdMatrix(p);
+  if (!allreduce_) {
+    check(device_loglike_derivs(ctx_, b.data(), &ll, g ? g->data() : nullptr, h ? h->a.data() : nullptr));
+    return ll;
+  }
+  const int64_t len = boomgpu_suf_len(p);
+  packed_.resize((size_t)len);
+  double *suf_dev = nullptr;
+  check(boomgpu_suf_buffer(ctx_, &suf_dev));
+  check(device_loglike_derivs_device(ctx_, b.data(), suf_dev));
+  allreduce_(suf_dev, len);
+  check(boomgpu_download(ctx_, suf_dev, packed_.data(), len));
+  const size_t mat = (size_t)p * p;
+  if (g) g->assign(packed_.begin() + mat, packed_.begin() + mat + p);
+  if (h) for (size_t e = 0; e < mat; ++e) h->a[e] = -packed_[e];
+  return packed_[mat + p + 1];
+}
+
+bool DeviceImputerBase::find_mode(GlmCoefs &coef, const Ptr<MvnBase> &slab, const Ptr<VariableSelectionPrior> &spike, double epsilon,
                                   double *value) {
   ensure_device_rows();
   const int p = xdim_;
-  DerivsProxy proxy(p, [&](const BOOM_B200::Vector &b, BOOM_B200::Vector *g, BOOM_B200::SpdMatrix *h) {
-    double ll = 0;
-    if (g) g->assign(p, 0.0);
-    if (h && h->dim != p) *h = BOOM_B200::SpdMatrix(p);
-    check(device_loglike_derivs(ctx_, b.data(), &ll, g ? g->data() : nullptr, h ? h->a.data() : nullptr));
-    return ll;
-  });
+  DerivsProxy proxy(p, [&](const BOOM_B200::Vector &b, BOOM_B200::Vector *g, BOOM_B200::SpdMatrix *h) { return loglike_derivs(b, g, h); });
   BOOM_B200::Selector g(p, false);
   for (int i = 0; i < p; ++i) if (coef.inc()[i]) g.add(i);
   proxy.coef().set_inc(g);
   proxy.coef().set_Beta(to_host(coef.Beta()));
-  auto hslab = std::make_shared<BOOM_B200::MvnModel>(to_host(slab.mu()), to_host(slab.siginv()), true);
-  BOOM_B200::SpikeSlabCore core(hslab, to_host(spike), false);
-  const bool ok = core.find_posterior_mode(proxy, epsilon, value);
+  const bool ok = core(slab, spike, false).find_posterior_mode(proxy, epsilon, value);
   if (ok) coef.set_Beta(Vector(proxy.Beta().begin(), proxy.Beta().end()));
   return ok;
 }
 
 void DeviceImputerBase::impute_latent_data() {
   if (latent_data_fixed_) return;  // statistics are under external control (Imputer.hpp:282-299)
+  Stopwatch sw(secs_device_);
   ensure_device_rows();
-  const int64_t len = boomgpu_suf_len(xdim_);
-  packed_.resize((size_t)len);
-  double *suf_dev = nullptr;
-  check(boomgpu_suf_buffer(ctx_, &suf_dev));
+  const int p = xdim_;
   // fresh Philox key from the sampler's own stream (set_seed() repeats the chain).  Raw generator bits, not
   // BOOM::seed_rng: its llround(U * 2^64) overflows for half of all U and returns one fixed value for them.
   const uint64_t seed = rng().generator()();
-  check(device_step(ctx_, current_beta().data(), seed, iteration_++, suf_dev));
-  if (allreduce_) allreduce_(suf_dev, len);
-  else check(boomgpu_allreduce(ctx_, suf_dev, len));   // no-op without a communicator
-  check(boomgpu_download(ctx_, suf_dev, packed_.data(), len));
-  const int p = xdim_;
-  SpdMatrix xtx(p);
-  std::copy(packed_.begin(), packed_.begin() + (size_t)p * p, xtx.data());
-  Vector xty(packed_.begin() + (size_t)p * p, packed_.begin() + (size_t)p * p + p);
-  const double *sc = packed_.data() + (size_t)p * p + p;
-  suf_.reset(xtx, xty, sc[1], sc[0], sc[2], sc[3]);   // WeightedRegressionModel.cpp:148-157
+  if (allreduce_) {   // caller-supplied all-reduce: the packed statistics stay on the device for the hook
+    const int64_t len = boomgpu_suf_len(p);
+    packed_.resize((size_t)len);
+    double *suf_dev = nullptr;
+    check(boomgpu_suf_buffer(ctx_, &suf_dev));
+    check(device_step(ctx_, current_beta().data(), seed, iteration_++, suf_dev));
+    allreduce_(suf_dev, len);
+    check(boomgpu_download(ctx_, suf_dev, packed_.data(), len));
+    hsuf_.reset(packed_.data(), p);
+  } else {            // straight into the statistics object (native all-reduce inside when a communicator is attached)
+    double sc[4] = {0, 0, 0, 0};
+    check(device_step_sync(ctx_, current_beta().data(), seed, iteration_++, hsuf_.xtx_storage(p), hsuf_.xty_storage(), sc));
+    hsuf_.set_scalars(sc[0], sc[1], sc[2], sc[3]);
+  }
+  statistics_changed();
 }
 
 void DeviceImputerBase::draw_beta_full_model(GlmCoefs &coef, const MvnBase &prior) {
-  SpdMatrix ivar = prior.siginv() + suf_.xtx();
-  Vector ivar_mu = suf_.xty() + prior.siginv() * prior.mu();
-  coef.set_Beta(rmvn_suf_mt(rng(), ivar, ivar_mu));   // distributions/mvn.cpp:128-136, BOOM's own
+  Stopwatch sw(secs_host_);
+  // ivar = Omega^-1 + X'WX, ivar_mu = X'Wz + Omega^-1 mu_0, then BOOM's own rmvn_suf_mt (distributions/mvn.cpp:128-136).
+  // BOOM::SpdMatrix is column major and symmetric: the same bytes as the row-major host matrix.
+  const int p = xdim_;
+  SpdMatrix ivar = prior.siginv();
+  Vector ivar_mu = prior.siginv() * prior.mu();
+  const double *xtx = hsuf_.xtx().a.data();
+  double *iv = ivar.data();
+  for (size_t e = 0; e < (size_t)p * p; ++e) iv[e] += xtx[e];
+  for (int i = 0; i < p; ++i) ivar_mu[i] += hsuf_.xty()[i];
+  coef.set_Beta(rmvn_suf_mt(rng(), ivar, ivar_mu));
 }
 
-void DeviceImputerBase::spike_slab_draw(GlmCoefs &coef, const MvnBase &slab, const VariableSelectionPrior &spike, bool select,
-                                        int max_flips, bool fisher_yates) {
-  // host small-state step on BOOM's objects through the shared evaluator of boom_b200/host
-  auto hslab = std::make_shared<BOOM_B200::MvnModel>(to_host(slab.mu()), to_host(slab.siginv()), true);
-  BOOM_B200::SpikeSlabCore core(hslab, to_host(spike), fisher_yates);
-  core.allow_model_selection(select);
-  core.limit_model_selection(max_flips);
-  // from suf_ (not the last device result): externally driven statistics (fix_latent_data) must be honoured
-  const int p = xdim_;
-  packed_.resize((size_t)p * p + p + 4);
-  const SpdMatrix xtx = suf_.xtx();   // by value in the reference (WeightedRegressionModel.cpp:192-195): once per draw here
-  std::copy(xtx.data(), xtx.data() + (size_t)p * p, packed_.begin());
-  const Vector xty = suf_.xty();
-  std::copy(xty.begin(), xty.end(), packed_.begin() + (size_t)p * p);
-  double *sc = packed_.data() + (size_t)p * p + p;
-  sc[0] = suf_.n(); sc[1] = suf_.yty(); sc[2] = suf_.sumw(); sc[3] = suf_.sumlogw();
-  BOOM_B200::WeightedRegSuf hsuf(xdim_);
-  hsuf.reset(packed_.data(), xdim_);
-  BOOM_B200::GlmCoefs hcoef(xdim_, false);
-  BOOM_B200::Selector g(xdim_, false);
-  for (int i = 0; i < xdim_; ++i) if (coef.inc()[i]) g.add(i);
-  hcoef.set_inc(g);
-  BOOM_B200::RNG local(rng().generator()());   // see impute_latent_data() on why not seed_rng()
-  core.draw_model_indicators(local, hcoef, hsuf);
-  core.draw_beta(local, hcoef, hsuf);
-  std::vector<bool> bits(xdim_);
-  for (int i = 0; i < xdim_; ++i) bits[i] = hcoef.inc()[i];
+const BOOM_B200::SpikeSlabCore &DeviceImputerBase::core(const Ptr<MvnBase> &slab, const Ptr<VariableSelectionPrior> &spike,
+                                                      bool fisher_yates) const {
+  if (!prior_cache_) prior_cache_.reset(new PriorCache);
+  PriorCache &c(*prior_cache_);
+  const bool same = c.core && c.slab == slab.get() && c.spike == spike.get() && c.fisher_yates == fisher_yates && c.observable &&
+                    c.version == prior_version_;
+  if (same) return *c.core;
+  DeviceImputerBase *self = const_cast<DeviceImputerBase *>(this);
+  if (c.observable && c.slab != slab.get()) {
+    c.mu_prm->remove_observer(self->observer_key());
+    c.sigma_prm->remove_observer(self->observer_key());
+    c.observable = false;
+  }
+  if (!c.observable) {
+    if (MvnModel *mvn = dynamic_cast<MvnModel *>(slab.get())) {   // its parameters signal when they are set
+      c.mu_prm = mvn->Mu_prm();
+      c.sigma_prm = mvn->Sigma_prm();
+      c.mu_prm->add_observer(self->observer_key(), [self]() { self->priors_changed(); });
+      c.sigma_prm->add_observer(self->observer_key(), [self]() { self->priors_changed(); });
+      c.observable = true;
+    }
+  }
+  auto hslab = std::make_shared<BOOM_B200::MvnModel>(to_host(slab->mu()), to_host(slab->siginv()), true);
+  c.core.reset(new BOOM_B200::SpikeSlabCore(hslab, to_host(*spike), fisher_yates));
+  c.slab = slab.get(); c.spike = spike.get(); c.fisher_yates = fisher_yates; c.version = prior_version_;
+  return *c.core;
+}
+
+namespace {
+BOOM_B200::GlmCoefs host_coefs(const GlmCoefs &coef, int p, bool with_beta) {
+  BOOM_B200::GlmCoefs h(p, false);
+  BOOM_B200::Selector g(p, false);
+  for (int i = 0; i < p; ++i) if (coef.inc()[i]) g.add(i);
+  h.set_inc(g);
+  if (with_beta) h.set_Beta(to_host(coef.Beta()));
+  return h;
+}
+void write_back(GlmCoefs &coef, const BOOM_B200::GlmCoefs &h, int p, bool beta) {
+  std::vector<bool> bits(p);
+  for (int i = 0; i < p; ++i) bits[i] = h.inc()[i];
   coef.set_inc(Selector(bits));
-  coef.set_Beta(Vector(hcoef.Beta().begin(), hcoef.Beta().end()));
+  if (beta) coef.set_Beta(Vector(h.Beta().begin(), h.Beta().end()));
+}
+}  // namespace
+
+void DeviceImputerBase::sweep_indicators(GlmCoefs &coef, const BOOM_B200::SpikeSlabCore &c) {
+  Stopwatch sw(secs_host_);
+  BOOM_B200::GlmCoefs h = host_coefs(coef, xdim_, true);
+  BOOM_B200::RNG local(rng().generator()());   // see impute_latent_data() on why not seed_rng()
+  c.draw_model_indicators(local, h, hsuf_);    // reads the statistics in place: externally driven ones (fix_latent_data) too
+  write_back(coef, h, xdim_, false);
+}
+
+void DeviceImputerBase::draw_included_beta(GlmCoefs &coef, const BOOM_B200::SpikeSlabCore &c) {
+  Stopwatch sw(secs_host_);
+  BOOM_B200::GlmCoefs h = host_coefs(coef, xdim_, false);
+  BOOM_B200::RNG local(rng().generator()());
+  c.draw_beta(local, h, hsuf_);
+  write_back(coef, h, xdim_, true);
+}
+
+double DeviceImputerBase::model_log_prob(const Selector &g, const BOOM_B200::SpikeSlabCore &c) const {
+  BOOM_B200::Selector h((int)g.nvars_possible(), false);
+  for (int i = 0; i < (int)g.nvars_possible(); ++i) if (g[i]) h.add(i);
+  return c.log_model_prob(h, hsuf_);
 }
 
 double DeviceImputerBase::spike_slab_logpri(const GlmCoefs &coef, const MvnBase &slab, const VariableSelectionPrior &spike) const {
@@ -168,28 +281,75 @@ double DeviceImputerBase::spike_slab_logpri(const GlmCoefs &coef, const MvnBase 
   return ans;
 }
 
+// ---- the reference's statistics types, filled in bulk ------------------------------------------------------------
+// BinomialLogit::SufficientStatistics (BinomialLogitAuxmixSampler.hpp:39-67) keeps xtx_, xty_, sym_ and sample_size_ private
+// and offers only per-observation update(): there is no way to hand it a finished p x p matrix through its interface.  The
+// drop-in must nevertheless return THAT type from suf().  The members are reached through explicit template instantiation,
+// whose arguments are exempt from access checking ([temp.explicit]): standard C++, no change to the BOOM sources, and a
+// compile error -- not silent misbehaviour -- should BOOM ever rename a member.
+namespace {
+template <class Tag, typename Tag::type Member>
+struct MemberAccess { friend typename Tag::type member_pointer(Tag) { return Member; } };
+struct SufXtx { typedef SpdMatrix BinomialLogit::SufficientStatistics::*type; friend type member_pointer(SufXtx); };
+struct SufXty { typedef Vector BinomialLogit::SufficientStatistics::*type; friend type member_pointer(SufXty); };
+struct SufSym { typedef bool BinomialLogit::SufficientStatistics::*type; friend type member_pointer(SufSym); };
+struct SufSize { typedef int BinomialLogit::SufficientStatistics::*type; friend type member_pointer(SufSize); };
+template struct MemberAccess<SufXtx, &BinomialLogit::SufficientStatistics::xtx_>;
+template struct MemberAccess<SufXty, &BinomialLogit::SufficientStatistics::xty_>;
+template struct MemberAccess<SufSym, &BinomialLogit::SufficientStatistics::sym_>;
+template struct MemberAccess<SufSize, &BinomialLogit::SufficientStatistics::sample_size_>;
+}  // namespace
+
 // ---------------------------------------------------------------------------------------------
 BinomialLogitAuxmixSampler::BinomialLogitAuxmixSampler(BinomialLogitModel *model, const Ptr<MvnBase> &prior, int clt_threshold,
                                                        RNG &seeding_rng)
-    : DeviceImputerBase(model->xdim(), seeding_rng), model_(model), prior_(prior), clt_threshold_(clt_threshold) {
+    : DeviceImputerBase(model->xdim(), seeding_rng), model_(model), prior_(prior), clt_threshold_(clt_threshold), suf_(model->xdim()) {
   if (prior_->dim() != model_->xdim()) report_error("Prior does not match model dimension.");
   model_->add_observer([this]() { this->mark_stale(); });
 }
 
-void BinomialLogitAuxmixSampler::pack_and_upload(boomgpu_ctx *ctx) {
-  const std::vector<Ptr<BinomialRegressionData>> &data(model_->dat());
-  const int64_t n = (int64_t)data.size();
-  const int p = xdim_;
-  std::vector<double> X((size_t)n * p), y(n), nt(n);
-  for (int64_t i = 0; i < n; ++i) {
-    const Vector &x(data[i]->x());
-    std::copy(x.begin(), x.end(), X.begin() + (size_t)i * p);
-    y[i] = data[i]->y();
-    nt[i] = data[i]->n();
+const BinomialLogit::SufficientStatistics &BinomialLogitAuxmixSampler::suf() const {
+  if (!suf_synced_) {
+    const int p = xdim_;
+    SpdMatrix &xtx(suf_.*member_pointer(SufXtx()));
+    Vector &xty(suf_.*member_pointer(SufXty()));
+    if ((int)xtx.nrow() != p) { xtx = SpdMatrix(p); xty = Vector(p); }
+    std::copy(hsuf_.xtx().a.begin(), hsuf_.xtx().a.end(), xtx.data());   // symmetric: row major == column major
+    std::copy(hsuf_.xty().begin(), hsuf_.xty().end(), xty.begin());
+    suf_.*member_pointer(SufSym()) = true;                                // both triangles are filled
+    suf_.*member_pointer(SufSize()) = (int)hsuf_.sample_size();
+    suf_synced_ = true;
   }
+  return suf_;
+}
+
+void BinomialLogitAuxmixSampler::install_tables(boomgpu_ctx *ctx) {
   const NormalMixtureApproximation &mix(BinomialLogitDataImputer::mixture_approximation);   // BinomialLogitDataImputer.hpp:51
   check(boomgpu_set_logit_mixture(ctx, mix.dim(), mix.mu().data(), mix.sigma().data(), mix.weights().data()));
-  check(boomgpu_upload_binomial(ctx, n, p, X.data(), p, y.data(), nt.data()));
+}
+
+void BinomialLogitAuxmixSampler::pack_rows(int64_t row0, int64_t nrows, double *X, void *y, double *aux) const {
+  const std::vector<Ptr<BinomialRegressionData>> &data(model_->dat());
+  const int p = xdim_;
+  double *yd = static_cast<double *>(y);
+  for (int64_t i = 0; i < nrows; ++i) {
+    const BinomialRegressionData &d(*data[row0 + i]);
+    const Vector &x(d.x());
+    std::copy(x.begin(), x.end(), X + (size_t)i * p);
+    yd[i] = d.y();
+    aux[i] = d.n();
+  }
+}
+
+void BinomialLogitAuxmixSampler::observe_row_objects(bool tf) {
+  for (const Ptr<BinomialRegressionData> &d : model_->dat()) {
+    d->remove_observer(observer_key());
+    d->Xptr()->remove_observer(observer_key());
+    if (tf) {
+      d->add_observer(observer_key(), [this]() { this->mark_stale(); });            // set_y / set_n signal on the observation
+      d->Xptr()->add_observer(observer_key(), [this]() { this->mark_stale(); });    // set_x signals on its VectorData
+    }
+  }
 }
 
 int BinomialLogitAuxmixSampler::device_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration,
@@ -197,8 +357,19 @@ int BinomialLogitAuxmixSampler::device_step(boomgpu_ctx *ctx, const double *beta
   return boomgpu_logit_step_device(ctx, beta, clt_threshold_, seed, iteration, suf_dev);
 }
 
+int BinomialLogitAuxmixSampler::device_step_sync(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *xtx,
+                                                 double *xty, double scalars[4]) {
+  int64_t ss = 0;
+  const int rc = boomgpu_logit_step(ctx, beta, clt_threshold_, seed, iteration, xtx, xty, &ss);
+  scalars[0] = (double)ss; scalars[1] = scalars[2] = scalars[3] = 0.0;
+  return rc;
+}
+
 int BinomialLogitAuxmixSampler::device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) {
   return boomgpu_binomial_loglike_derivs(ctx, beta, model_->log_alpha(), loglike, g, h);   // BinomialLogitModel.cpp:168
+}
+int BinomialLogitAuxmixSampler::device_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) {
+  return boomgpu_binomial_loglike_derivs_device(ctx, beta, model_->log_alpha(), suf_dev);
 }
 
 void BinomialLogitAuxmixSampler::draw() {
@@ -210,7 +381,8 @@ double BinomialLogitAuxmixSampler::logpri() const { return prior_->logp(model_->
 void BinomialLogitAuxmixSampler::update_complete_data_sufficient_statistics(double precision_weighted_sum, double total_precision,
                                                                             const Vector &x) {
   // the logit statistics are (sum, information): BinomialLogitAuxmixSampler.cpp:61-67
-  suf_.add_data(x, total_precision > 0 ? precision_weighted_sum / total_precision : 0.0, total_precision);
+  hsuf_.update(to_host(x), precision_weighted_sum, total_precision);
+  statistics_changed();
 }
 
 BinomialLogitSpikeSlabSampler::BinomialLogitSpikeSlabSampler(BinomialLogitModel *model, const Ptr<MvnBase> &slab,
@@ -225,47 +397,61 @@ BinomialLogitSpikeSlabSampler *BinomialLogitSpikeSlabSampler::clone_to_new_host(
 }
 void BinomialLogitSpikeSlabSampler::draw() {   // BinomialLogitSpikeSlabSampler.cpp:50-54
   impute_latent_data();
-  spike_slab_draw(model_->coef(), *slab_, *spike_, allow_model_selection_, max_flips_, false);
+  if (allow_model_selection_) draw_model_indicators();
+  draw_beta();
+}
+void BinomialLogitSpikeSlabSampler::draw_model_indicators() {
+  BOOM_B200::SpikeSlabCore c(core(slab_, spike_, false));   // a copy: the sweep limits are per call
+  c.allow_model_selection(true);
+  c.limit_model_selection(max_flips_);
+  sweep_indicators(model_->coef(), c);
+}
+void BinomialLogitSpikeSlabSampler::draw_beta() { draw_included_beta(model_->coef(), core(slab_, spike_, false)); }
+double BinomialLogitSpikeSlabSampler::log_model_prob(const Selector &gamma) const {
+  return model_log_prob(gamma, core(slab_, spike_, false));
 }
 double BinomialLogitSpikeSlabSampler::logpri() const { return spike_slab_logpri(model_->coef(), *slab_, *spike_); }
 void BinomialLogitSpikeSlabSampler::find_posterior_mode(double epsilon) {
-  posterior_mode_found_ = find_mode(model_->coef(), *slab_, *spike_, epsilon, &log_posterior_at_mode_);
+  posterior_mode_found_ = find_mode(model_->coef(), slab_, spike_, epsilon, &log_posterior_at_mode_);
 }
 void BinomialLogitSpikeSlabSampler::set_spike(const Ptr<VariableSelectionPrior> &spike) {
   if ((int)spike->potential_nvars() != model_->xdim()) report_error("Spike does not match model dimension.");
   spike_ = spike;
+  priors_changed();
 }
 void BinomialLogitSpikeSlabSampler::set_slab(const Ptr<MvnBase> &slab) {
   if (slab->dim() != model_->xdim()) report_error("Slab does not match model dimension.");
   slab_ = slab;
+  priors_changed();
 }
 
 // ---------------------------------------------------------------------------------------------
 PoissonRegressionAuxMixSampler::PoissonRegressionAuxMixSampler(PoissonRegressionModel *model, const Ptr<MvnBase> &prior, int,
                                                                RNG &seeding_rng)
-    : DeviceImputerBase(model->xdim(), seeding_rng), model_(model), prior_(prior) {
+    : DeviceImputerBase(model->xdim(), seeding_rng), model_(model), prior_(prior), suf_(model->xdim()) {
   if (prior_->dim() != model_->xdim()) report_error("Prior does not match model dimension.");
   model_->add_observer([this]() { this->mark_stale(); });
 }
 
-void PoissonRegressionAuxMixSampler::pack_and_upload(boomgpu_ctx *ctx) {
-  const std::vector<Ptr<PoissonRegressionData>> &data(model_->dat());
-  const int64_t n = (int64_t)data.size();
-  const int p = xdim_;
-  std::vector<double> X((size_t)n * p), ex(n);
-  std::vector<int64_t> y(n);
-  std::set<int64_t> distinct;
-  for (int64_t i = 0; i < n; ++i) {
-    const Vector &x(data[i]->x());
-    std::copy(x.begin(), x.end(), X.begin() + (size_t)i * p);
-    y[i] = data[i]->y();
-    ex[i] = data[i]->exposure();
-    if (y[i] > 0) distinct.insert(y[i]);
+const WeightedRegSuf &PoissonRegressionAuxMixSampler::complete_data_sufficient_statistics() const {
+  if (!suf_synced_) {
+    const int p = xdim_;
+    SpdMatrix xtx(p);
+    std::copy(hsuf_.xtx().a.begin(), hsuf_.xtx().a.end(), xtx.data());
+    Vector xty(hsuf_.xty().begin(), hsuf_.xty().end());
+    suf_.reset(xtx, xty, hsuf_.yty(), hsuf_.n(), hsuf_.sumw(), hsuf_.sumlogw());   // WeightedRegressionModel.cpp:148-157
+    suf_synced_ = true;
   }
+  return suf_;
+}
+
+void PoissonRegressionAuxMixSampler::install_tables(boomgpu_ctx *ctx) {
   // The table is materialised by the reference's own code for every count in the data (first touch of an
-  // off-grid value may run its Powell re-fit on the host), then uploaded in its serialized layout.
+  // off-grid value may run its Powell re-fit on the host), then stated in its serialized layout.
   static NormalMixtureApproximationTable table = create_poisson_mixture_approximation_table();
   table.approximate(1);
+  std::set<int64_t> distinct;
+  for (const Ptr<PoissonRegressionData> &d : model_->dat()) if (d->y() > 0) distinct.insert(d->y());
   for (int64_t v : distinct) if (v < table.largest_index()) table.approximate((int)v);
   const Vector ser = table.serialize();   // [nu, K, w[K], sigma[K], mu[K]] ...  NormalMixtureApproximation.cpp:393-399,534-542
   std::map<int64_t, size_t> entries;      // last entry wins for duplicate keys, like the reference's lookup
@@ -286,15 +472,45 @@ void PoissonRegressionAuxMixSampler::pack_and_upload(boomgpu_ctx *ctx) {
   }
   check(boomgpu_set_poisson_table(ctx, (int)nu.size(), nu.data(), offset.data(), w.data(), mu.data(), sigma.data(),
                                   table.largest_index()));
-  check(boomgpu_upload_poisson(ctx, n, p, X.data(), p, y.data(), ex.data()));
+}
+
+void PoissonRegressionAuxMixSampler::pack_rows(int64_t row0, int64_t nrows, double *X, void *y, double *aux) const {
+  const std::vector<Ptr<PoissonRegressionData>> &data(model_->dat());
+  const int p = xdim_;
+  int64_t *yi = static_cast<int64_t *>(y);
+  for (int64_t i = 0; i < nrows; ++i) {
+    const PoissonRegressionData &d(*data[row0 + i]);
+    const Vector &x(d.x());
+    std::copy(x.begin(), x.end(), X + (size_t)i * p);
+    yi[i] = d.y();
+    aux[i] = d.exposure();
+  }
+}
+
+void PoissonRegressionAuxMixSampler::observe_row_objects(bool tf) {
+  for (const Ptr<PoissonRegressionData> &d : model_->dat()) {
+    d->remove_observer(observer_key());
+    d->Xptr()->remove_observer(observer_key());
+    if (tf) {
+      d->add_observer(observer_key(), [this]() { this->mark_stale(); });
+      d->Xptr()->add_observer(observer_key(), [this]() { this->mark_stale(); });
+    }
+  }
 }
 
 int PoissonRegressionAuxMixSampler::device_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration,
                                                 double *suf_dev) {
   return boomgpu_poisson_step_device(ctx, beta, seed, iteration, suf_dev);
 }
+int PoissonRegressionAuxMixSampler::device_step_sync(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration,
+                                                     double *xtx, double *xty, double scalars[4]) {
+  return boomgpu_poisson_step(ctx, beta, seed, iteration, xtx, xty, scalars);
+}
 int PoissonRegressionAuxMixSampler::device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) {
   return boomgpu_poisson_loglike_derivs(ctx, beta, loglike, g, h);
+}
+int PoissonRegressionAuxMixSampler::device_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) {
+  return boomgpu_poisson_loglike_derivs_device(ctx, beta, suf_dev);
 }
 void PoissonRegressionAuxMixSampler::draw() {
   impute_latent_data();
@@ -304,7 +520,8 @@ void PoissonRegressionAuxMixSampler::draw_beta_given_complete_data() { draw_beta
 double PoissonRegressionAuxMixSampler::logpri() const { return prior_->logp(model_->Beta()); }
 void PoissonRegressionAuxMixSampler::update_complete_data_sufficient_statistics(double precision_weighted_sum,
                                                                                 double total_precision, const Vector &x) {
-  suf_.add_data(x, precision_weighted_sum / total_precision, total_precision);   // PoissonRegressionAuxMixSampler.cpp:153-158
+  hsuf_.add_data(to_host(x), precision_weighted_sum / total_precision, total_precision);   // PoissonRegressionAuxMixSampler.cpp:153-158
+  statistics_changed();
 }
 
 PoissonRegressionSpikeSlabSampler::PoissonRegressionSpikeSlabSampler(PoissonRegressionModel *model, const Ptr<MvnBase> &slab,
@@ -315,7 +532,18 @@ PoissonRegressionSpikeSlabSampler::PoissonRegressionSpikeSlabSampler(PoissonRegr
 }
 void PoissonRegressionSpikeSlabSampler::draw() {   // PoissonRegressionSpikeSlabSampler.cpp:55-59
   impute_latent_data();
-  spike_slab_draw(model_->coef(), *slab_, *spike_, allow_model_selection_, max_flips_, true);
+  if (allow_model_selection_) draw_model_indicators();
+  draw_beta();
+}
+void PoissonRegressionSpikeSlabSampler::draw_model_indicators() {
+  BOOM_B200::SpikeSlabCore c(core(slab_, spike_, true));
+  c.allow_model_selection(true);
+  c.limit_model_selection(max_flips_);
+  sweep_indicators(model_->coef(), c);
+}
+void PoissonRegressionSpikeSlabSampler::draw_beta() { draw_included_beta(model_->coef(), core(slab_, spike_, true)); }
+double PoissonRegressionSpikeSlabSampler::log_model_prob(const Selector &gamma) const {
+  return model_log_prob(gamma, core(slab_, spike_, true));
 }
 double PoissonRegressionSpikeSlabSampler::logpri() const { return spike_slab_logpri(model_->coef(), *slab_, *spike_); }
 PoissonRegressionSpikeSlabSampler *PoissonRegressionSpikeSlabSampler::clone_to_new_host(Model *new_host) const {
@@ -326,7 +554,7 @@ PoissonRegressionSpikeSlabSampler *PoissonRegressionSpikeSlabSampler::clone_to_n
   return s;
 }
 void PoissonRegressionSpikeSlabSampler::find_posterior_mode(double epsilon) {
-  find_mode(model_->coef(), *slab_, *spike_, epsilon, &log_posterior_at_mode_);
+  find_mode(model_->coef(), slab_, spike_, epsilon, &log_posterior_at_mode_);
 }
 
 }  // namespace B200

@@ -10,15 +10,23 @@
 //
 // Same constructor arguments and public methods as the originals
 // (Models/Glm/PosteriorSamplers/BinomialLogitAuxmixSampler.hpp:109-152, BinomialLogitSpikeSlabSampler.hpp:27-96,
-// PoissonRegressionAuxMixSampler.hpp:60-125, PoissonRegressionSpikeSlabSampler.hpp).  They cannot subclass the
-// originals: the statistics those fill are private with no bulk setter, so they derive from
-// PosteriorSampler directly and keep their statistics in a BOOM::WeightedRegSuf (bulk-loaded with reset()).
+// PoissonRegressionAuxMixSampler.hpp:60-125, PoissonRegressionSpikeSlabSampler.hpp), the public accessors included:
+// suf() returns the reference's own BinomialLogit::SufficientStatistics, complete_data_sufficient_statistics() its
+// WeightedRegSuf.  They cannot subclass the originals (the worker-pool base LatentDataSampler<...> would come along),
+// so they derive from PosteriorSampler directly.
 //
-// impute_latent_data() is one device step through the C ABI (include/boomgpu.h) on rows packed once from
-// model->dat() (re-packed when the model's data change: IID_DataPolicy::add_observer, IID_DataPolicy.hpp:43-45);
-// the small-state steps run on the host: beta by BOOM's own rmvn_suf_mt, the inclusion sweep by the shared
-// bordered-Cholesky evaluator of boom_b200/host.  All randomness derives from the sampler's BOOM::RNG, so
-// set_seed() repeats a chain.  Mixture tables are read from the live reference objects
+// Where the statistics live.  The device step lands X'WX / X'Wz in ONE host object, a BOOM_B200::WeightedRegSuf whose
+// p x p storage is page-locked once for large p (the device->host copy goes straight into it), and the host steps --
+// beta | statistics, the inclusion sweep -- read that object in place: no p x p matrix is copied per draw (at p = 4000
+// each copy is 128 MB).  The reference-typed objects behind suf() / complete_data_sufficient_statistics() are filled
+// from it on demand, when somebody asks.
+//
+// impute_latent_data() is one device step through the C ABI (include/boomgpu.h) on rows packed from model->dat() a chunk
+// at a time (no second n x p host copy), re-packed when the model's data change (IID_DataPolicy::add_observer,
+// IID_DataPolicy.hpp:43-45); in-place edits of a row (set_x / set_y / set_n) are seen after observe_rows(true), or
+// with reassign_data_each_time(true), or after refresh_data().  The small-state steps run on the host: beta by BOOM's own
+// rmvn_suf_mt, the inclusion sweep by the shared bordered-Cholesky evaluator of boom_b200/host.  All randomness derives
+// from the sampler's BOOM::RNG, so set_seed() repeats a chain.  Mixture tables are read from the live reference objects
 // (BinomialLogitDataImputer::mixture_approximation, create_poisson_mixture_approximation_table()).
 //
 // Needs the BOOM headers and library: built only where the reference exists.
@@ -29,6 +37,7 @@
 
 #include "Models/Glm/BinomialLogitModel.hpp"
 #include "Models/Glm/PoissonRegressionModel.hpp"
+#include "Models/Glm/PosteriorSamplers/BinomialLogitAuxmixSampler.hpp"
 #include "Models/Glm/VariableSelectionPrior.hpp"
 #include "Models/Glm/WeightedRegressionModel.hpp"
 #include "Models/MvnBase.hpp"
@@ -49,46 +58,75 @@ class DeviceImputerBase : public PosteriorSampler {
   void fix_latent_data(bool fixed = true) { latent_data_fixed_ = fixed; }
   void set_number_of_workers(int) {}
   void reassign_data_each_time(bool tf) { repack_each_time_ = tf; }
-  void clear_complete_data_sufficient_statistics() { suf_.clear(); }
+  void clear_complete_data_sufficient_statistics() { hsuf_.clear(); statistics_changed(); }
+  // the rows are re-packed before the next draw (use after editing observations in place)
+  void refresh_data() { stale_ = true; }
+  // true: every observation (and its x / y parts) gets an observer, so in-place edits (set_x, set_y, set_n) re-pack the
+  // rows before the next draw -- three map nodes per observation, meant for data sets that fit that comfortably
+  void observe_rows(bool tf);
   // multi-GPU / placement
   void set_device(int device);
   void set_row_offset(uint64_t first_global_row) { row_offset_ = first_global_row; stale_ = true; }
   void set_allreduce(const BOOM_B200::AllReduceFn &fn) { allreduce_ = fn; }
   // or natively: join an NCCL communicator (id from BOOM_B200::GlmModelBase::comm_unique_id() on rank 0)
   void set_communicator(const std::string &id, int nranks, int rank) { comm_id_ = id; comm_ranks_ = nranks; comm_rank_ = rank; comm_dirty_ = true; }
+  // wall-clock seconds this sampler has spent in: the device step (incl. copies), the host small-state steps
+  double seconds_in_device_step() const { return secs_device_; }
+  double seconds_in_host_steps() const { return secs_host_; }
 
  protected:
   DeviceImputerBase(int xdim, RNG &seeding_rng);
-  virtual void pack_and_upload(boomgpu_ctx *ctx) = 0;   // walks model->dat()
+  // walks model->dat(): n rows, handed to the device a chunk at a time through emit(row0, nrows, X, y, aux)
+  typedef std::function<void(int64_t row0, int64_t nrows, const double *X, const void *y, const double *aux)> ChunkSink;
+  virtual int64_t row_count() const = 0;
+  virtual bool rows_are_poisson() const = 0;
+  virtual void install_tables(boomgpu_ctx *ctx) = 0;                     // mixture tables, before the rows
+  virtual void pack_rows(int64_t row0, int64_t nrows, double *X, void *y, double *aux) const = 0;
+  virtual void observe_row_objects(bool tf) = 0;
   virtual int device_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *suf_dev) = 0;
+  // the synchronous form: all-reduces natively when a communicator is attached, lands the statistics at xtx / xty / scalars
+  virtual int device_step_sync(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *xtx, double *xty,
+                               double scalars[4]) = 0;
   virtual const Vector &current_beta() const = 0;
   // log likelihood with gradient / Hessian at a full coefficient vector, one device pass (boomgpu_*_loglike_derivs)
   virtual int device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) = 0;
+  virtual int device_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) = 0;
+  double loglike_derivs(const BOOM_B200::Vector &beta, BOOM_B200::Vector *g, BOOM_B200::SpdMatrix *h);   // all ranks' rows
   void ensure_device_rows();
   // find_posterior_mode of the spike-and-slab samplers (BinomialLogitSpikeSlabSampler.cpp:147-177,
   // PoissonRegressionSpikeSlabSampler.cpp:69-106): Newton-Raphson on the included coefficients, derivatives from the device
-  bool find_mode(GlmCoefs &coef, const MvnBase &slab, const VariableSelectionPrior &spike, double epsilon, double *value);
+  bool find_mode(GlmCoefs &coef, const Ptr<MvnBase> &slab, const Ptr<VariableSelectionPrior> &spike, double epsilon, double *value);
   void mark_stale() { stale_ = true; }
   void check(int rc) const;
-  // host steps on suf_
+  virtual void statistics_changed() {}   // the reference-typed views are out of date
+  // host steps on hsuf_
   void draw_beta_full_model(GlmCoefs &coef, const MvnBase &prior);
-  void spike_slab_draw(GlmCoefs &coef, const MvnBase &slab, const VariableSelectionPrior &spike, bool select, int max_flips,
-                       bool fisher_yates);
+  // the shared spike-and-slab core over the CURRENT slab / spike (host copies cached; see prior_cache())
+  const BOOM_B200::SpikeSlabCore &core(const Ptr<MvnBase> &slab, const Ptr<VariableSelectionPrior> &spike, bool fisher_yates) const;
+  void sweep_indicators(GlmCoefs &coef, const BOOM_B200::SpikeSlabCore &core);
+  void draw_included_beta(GlmCoefs &coef, const BOOM_B200::SpikeSlabCore &core);
+  double model_log_prob(const Selector &g, const BOOM_B200::SpikeSlabCore &core) const;
   double spike_slab_logpri(const GlmCoefs &coef, const MvnBase &slab, const VariableSelectionPrior &spike) const;
+  void priors_changed() { ++prior_version_; }
+  void *observer_key() { return static_cast<void *>(this); }
 
-  WeightedRegSuf suf_;
+  BOOM_B200::WeightedRegSuf hsuf_;   // where the device step lands and the host steps read
   int xdim_;
 
  private:
+  struct PriorCache;
   boomgpu_ctx *ctx_ = nullptr;
   int device_ = 0;
-  bool stale_ = true, latent_data_fixed_ = false, repack_each_time_ = false;
+  bool stale_ = true, latent_data_fixed_ = false, repack_each_time_ = false, observing_rows_ = false;
   uint64_t row_offset_ = 0, iteration_ = 0;
   BOOM_B200::AllReduceFn allreduce_;
   std::string comm_id_;
   int comm_ranks_ = 1, comm_rank_ = 0;
   bool comm_dirty_ = false;
   std::vector<double> packed_;
+  mutable std::unique_ptr<PriorCache> prior_cache_;
+  uint64_t prior_version_ = 1;
+  double secs_device_ = 0, secs_host_ = 0;
 };
 
 class BinomialLogitAuxmixSampler : public DeviceImputerBase {
@@ -98,20 +136,31 @@ class BinomialLogitAuxmixSampler : public DeviceImputerBase {
   void draw() override;
   double logpri() const override;
   void draw_params();
-  const WeightedRegSuf &suf() const { return suf_; }
+  // the reference's own statistics type (BinomialLogitAuxmixSampler.hpp:39-67), filled from the device result on demand
+  const BinomialLogit::SufficientStatistics &suf() const;
   int clt_threshold() const { return clt_threshold_; }
   void update_complete_data_sufficient_statistics(double precision_weighted_sum, double total_precision, const Vector &x);
 
  protected:
-  void pack_and_upload(boomgpu_ctx *ctx) override;
+  int64_t row_count() const override { return (int64_t)model_->dat().size(); }
+  bool rows_are_poisson() const override { return false; }
+  void install_tables(boomgpu_ctx *ctx) override;
+  void pack_rows(int64_t row0, int64_t nrows, double *X, void *y, double *aux) const override;
+  void observe_row_objects(bool tf) override;
   int device_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *suf_dev) override;
+  int device_step_sync(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *xtx, double *xty,
+                       double scalars[4]) override;
   int device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) override;
+  int device_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) override;
   const Vector &current_beta() const override { return model_->Beta(); }
+  void statistics_changed() override { suf_synced_ = false; }
   BinomialLogitModel *model_;
   Ptr<MvnBase> prior_;
 
  private:
   int clt_threshold_;
+  mutable BinomialLogit::SufficientStatistics suf_;
+  mutable bool suf_synced_ = false;
 };
 
 class BinomialLogitSpikeSlabSampler : public BinomialLogitAuxmixSampler {
@@ -121,6 +170,9 @@ class BinomialLogitSpikeSlabSampler : public BinomialLogitAuxmixSampler {
   BinomialLogitSpikeSlabSampler *clone_to_new_host(Model *model) const override;
   void draw() override;
   double logpri() const override;
+  void draw_model_indicators();                         // BinomialLogitSpikeSlabSampler.cpp:180-211
+  virtual void draw_beta();                             // .cpp:56-75
+  double log_model_prob(const Selector &gamma) const;   // .cpp:88-117
   void allow_model_selection(bool tf) { allow_model_selection_ = tf; }
   void limit_model_selection(int max_flips) { max_flips_ = max_flips; }
   void set_spike(const Ptr<VariableSelectionPrior> &spike);
@@ -147,16 +199,28 @@ class PoissonRegressionAuxMixSampler : public DeviceImputerBase {
   void draw() override;
   double logpri() const override;
   void draw_beta_given_complete_data();
-  const WeightedRegSuf &complete_data_sufficient_statistics() const { return suf_; }
+  const WeightedRegSuf &complete_data_sufficient_statistics() const;   // BOOM's own type, filled on demand
   void update_complete_data_sufficient_statistics(double precision_weighted_sum, double total_precision, const Vector &x);
 
  protected:
-  void pack_and_upload(boomgpu_ctx *ctx) override;
+  int64_t row_count() const override { return (int64_t)model_->dat().size(); }
+  bool rows_are_poisson() const override { return true; }
+  void install_tables(boomgpu_ctx *ctx) override;
+  void pack_rows(int64_t row0, int64_t nrows, double *X, void *y, double *aux) const override;
+  void observe_row_objects(bool tf) override;
   int device_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *suf_dev) override;
+  int device_step_sync(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *xtx, double *xty,
+                       double scalars[4]) override;
   int device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) override;
+  int device_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) override;
   const Vector &current_beta() const override { return model_->Beta(); }
+  void statistics_changed() override { suf_synced_ = false; }
   PoissonRegressionModel *model_;
   Ptr<MvnBase> prior_;
+
+ private:
+  mutable WeightedRegSuf suf_;
+  mutable bool suf_synced_ = false;
 };
 
 class PoissonRegressionSpikeSlabSampler : public PoissonRegressionAuxMixSampler {
@@ -168,6 +232,9 @@ class PoissonRegressionSpikeSlabSampler : public PoissonRegressionAuxMixSampler 
   double logpri() const override;
   void allow_model_selection(bool tf) { allow_model_selection_ = tf; }
   void limit_model_selection(int max_flips) { max_flips_ = max_flips; }
+  void draw_model_indicators();                         // SpikeSlabSampler.cpp:40-100 with sigsq = 1
+  void draw_beta();
+  double log_model_prob(const Selector &gamma) const;
   PoissonRegressionSpikeSlabSampler *clone_to_new_host(Model *new_host) const override;
   void find_posterior_mode(double epsilon = 1e-5) override;
   bool can_find_posterior_mode() const override { return true; }

@@ -18,7 +18,7 @@ KERNEL_CLASSES = ("fused_small", "impute_rows", "syrk_dmma", "reduce", "other")
 SYMBOLS = (
     "boomgpu_create", "boomgpu_destroy", "boomgpu_last_error", "boomgpu_version", "boomgpu_set_stream",
     "boomgpu_set_row_offset", "boomgpu_set_option", "boomgpu_upload_binomial", "boomgpu_upload_poisson",
-    "boomgpu_adopt_binomial", "boomgpu_adopt_poisson", "boomgpu_set_logit_mixture", "boomgpu_set_poisson_table",
+    "boomgpu_upload_begin", "boomgpu_upload_rows", "boomgpu_upload_end", "boomgpu_adopt_binomial", "boomgpu_adopt_poisson", "boomgpu_set_logit_mixture", "boomgpu_set_poisson_table",
     "boomgpu_logit_step", "boomgpu_poisson_step", "boomgpu_suf_len", "boomgpu_logit_step_device",
     "boomgpu_poisson_step_device", "boomgpu_synchronize", "boomgpu_suf_buffer", "boomgpu_download", "boomgpu_accumulate", "boomgpu_logit_draw",
     "boomgpu_poisson_draw", "boomgpu_binomial_loglike", "boomgpu_poisson_loglike", "boomgpu_binomial_loglike_derivs",
@@ -139,6 +139,20 @@ class Context:
         n, p = X.shape
         self._check(self._lib.boomgpu_upload_poisson(self._h, C.c_int64(n), C.c_int(p), _dp(X), C.c_int64(p),
                                                      y.ctypes.data_as(c_i64_p), _dp(exposure)))
+        self.n, self.p = n, p
+
+    def upload_chunked(self, X, y, aux, chunk_rows, poisson=False):
+        """boomgpu_upload_begin / _rows / _end over row chunks (what the BOOM adapter does while walking model->dat())."""
+        X, aux = _f64(X), _f64(aux)
+        y = np.ascontiguousarray(y, dtype=np.int64 if poisson else np.float64)
+        n, p = X.shape
+        self._check(self._lib.boomgpu_upload_begin(self._h, C.c_int(int(poisson)), C.c_int64(n), C.c_int(p)))
+        for a in range(0, n, chunk_rows):
+            b = min(n, a + chunk_rows)
+            xc, yc, ac = np.ascontiguousarray(X[a:b]), np.ascontiguousarray(y[a:b]), np.ascontiguousarray(aux[a:b])
+            self._check(self._lib.boomgpu_upload_rows(self._h, C.c_int64(a), C.c_int64(b - a), _dp(xc), C.c_int64(p),
+                                                      yc.ctypes.data_as(C.c_void_p), _dp(ac)))
+        self._check(self._lib.boomgpu_upload_end(self._h))
         self.n, self.p = n, p
 
     def adopt_binomial(self, n, p, dX, ldx, dy, dntrials, keepalive=()):

@@ -33,6 +33,7 @@ struct boomgpu_ctx {
 
   // data
   int model = -1;  // kLogit / kPoisson
+  int upload_kind = -1;  // between boomgpu_upload_begin and _end: the model the chunks belong to
   int64_t n = 0;
   int p = 0;
   int64_t ldx = 0;
@@ -63,6 +64,8 @@ struct boomgpu_ctx {
   // workspaces
   double *beta_dev = nullptr; int beta_cap = 0;   // [p + 2 doubles | p ints: indices of beta's non-zeros (gather pass)]
   double *beta_pin = nullptr;
+  int syrk_diag = 0;                               // 0 strip form for whole diagonal regions, 1 unit form everywhere
+  int syrk_filter = 0;                             // profiling aid: time the off-diagonal / diagonal regions of the SYRK alone
   int gather = 0;                                  // option: 0 auto (sparse beta -> gather pass), 1 never, 2 whenever beta has a zero
   double *suf_dev = nullptr; int64_t suf_cap = 0;
   double *suf_pin = nullptr; int64_t suf_pin_cap = 0;
@@ -136,7 +139,7 @@ void free_data(boomgpu_ctx *ctx) {
   ctx->yi = nullptr;
   if (ctx->Xt_owned) { cudaFree(ctx->Xt_owned); ctx->Xt_owned = nullptr; }
   ctx->Xt = nullptr; ctx->ldxt = 0;
-  ctx->n = 0; ctx->p = 0; ctx->model = -1;
+  ctx->n = 0; ctx->p = 0; ctx->model = -1; ctx->upload_kind = -1;
 }
 
 // ---- launch bookkeeping -------------------------------------------------------------------
@@ -230,6 +233,19 @@ SyrkUnitTable make_unit_table() {
     t.u[1][6][0] = {0, 3, V};
     t.u[1][3][0] = {1, 3, V};
     t.u[1][7][0] = {2, 2, (int8_t)(V | D | F)}; t.u[1][7][1] = {3, 3, (int8_t)(V | D | Y)};
+    // ragged last unit column (units (., 3) hold NM < 4 atoms in n).  Off-diagonal: the warps of row blocks 2, 3 take their
+    // column pairs in the other order, so each sub-partition (w % 4) gets one whole pair (32 DMMA / k-step) and one cut pair
+    // (16 + 4 NM) instead of two of a kind: the region's pace is the busiest sub-partition's.
+    for (int w = 0; w < 8; ++w) {
+      const int c = (w % 2) ^ (w >= 4 ? 1 : 0);
+      t.u[2][w][0] = {(int8_t)(w / 2), (int8_t)(2 * c), 1};
+      t.u[2][w][1] = {(int8_t)(w / 2), (int8_t)(2 * c + 1), 1};
+    }
+    // Diagonal (NM = 3: 28 / 28 / 32 / 32 DMMA per k-step and sub-partition instead of 36 / 32 / 24 / 28)
+    t.u[3][0][0] = {0, 1, (int8_t)(V | Y)};  t.u[3][4][0] = {0, 3, V};
+    t.u[3][1][0] = {0, 2, V};                t.u[3][5][0] = {1, 3, V};
+    t.u[3][2][0] = {1, 2, (int8_t)(V | Y)};  t.u[3][6][0] = {2, 2, (int8_t)(V | D | F)}; t.u[3][6][1] = {3, 3, (int8_t)(V | D | Y)};
+    t.u[3][3][0] = {2, 3, (int8_t)(V | Y)};  t.u[3][7][0] = {0, 0, (int8_t)(V | D | F)}; t.u[3][7][1] = {1, 1, (int8_t)(V | D | F)};
   } else {
     // 16 warps x 1 unit.  Off-diagonal: warp w owns unit (w / 4, w % 4): 16 DMMA per k-step on every warp.
     for (int w = 0; w < kSyrkConsumerWarps; ++w) t.u[0][w][0] = {(int8_t)(w / 4), (int8_t)(w % 4), 1};
@@ -238,6 +254,7 @@ SyrkUnitTable make_unit_table() {
     t.u[1][1][0] = {0, 3, V};                t.u[1][5][0] = {1, 2, (int8_t)(V | Y)};
     t.u[1][2][0] = {1, 3, V};                t.u[1][6][0] = {0, 0, (int8_t)(V | D | F)};  t.u[1][10][0] = {1, 1, (int8_t)(V | D | F)};
     t.u[1][3][0] = {2, 3, (int8_t)(V | Y)};  t.u[1][7][0] = {2, 2, (int8_t)(V | D | F)};  t.u[1][11][0] = {3, 3, (int8_t)(V | D | Y)};
+    for (int w = 0; w < kSyrkConsumerWarps; ++w) { t.u[2][w][0] = t.u[0][w][0]; t.u[2][w][1] = t.u[0][w][1]; t.u[3][w][0] = t.u[1][w][0]; t.u[3][w][1] = t.u[1][w][1]; }
   }
   return t;
 }
@@ -462,6 +479,8 @@ int launch_syrk(boomgpu_ctx *ctx, double *suf) {
   const int64_t need = ksplit * sp.nregions * kSyrkTileLen;
   if (ensure(ctx, &ctx->partials, &ctx->partials_cap, need)) return BOOMGPU_ERR_CUDA;
   sp.partials = ctx->partials;
+  sp.filter = ctx->syrk_filter;
+  sp.diag_form = ctx->syrk_diag;
   static const SyrkUnitTable table = make_unit_table();
   if (int rc = ensure_xmap(ctx, ctx->xmap_syrk, ctx->Xt, ctx->ldxt, kSyrkPanelLd, kSyrkKB)) return rc;
   CU(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmemBytes));
@@ -649,6 +668,7 @@ DrawParams make_prm(boomgpu_ctx *ctx, int clt, uint64_t seed, uint64_t iteration
   prm.tab = ctx->tab;
   prm.key.seed = seed;
   prm.key.iteration = iteration;
+  philox_round_keys(prm.key);
   prm.clt_threshold = clt;
   prm.log_alpha = 0.0;
   return prm;
@@ -809,6 +829,8 @@ int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value) {
     return 0;
   }
   if (!strcmp(name, "timing")) { ctx->timing = value != 0; return 0; }
+  if (!strcmp(name, "syrk_diag")) { ctx->syrk_diag = value != 0; return 0; }
+  if (!strcmp(name, "syrk_filter")) { ctx->syrk_filter = (int)value; return 0; }
   if (!strcmp(name, "gather")) {
     if (value < 0 || value > 2) return fail(ctx, BOOMGPU_ERR_ARG, "gather must be 0 (auto), 1 (never) or 2 (whenever beta has a zero)");
     ctx->gather = (int)value;
@@ -849,6 +871,60 @@ int boomgpu_upload_poisson(boomgpu_ctx *ctx, int64_t n, int p, const double *X, 
   if (int rc = upload_array(ctx, exposure, n, &ctx->exposure)) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->model = kPoisson;
+  return 0;
+}
+
+// Chunked upload: the caller packs a few thousand rows at a time out of its own representation (BOOM keeps one heap object
+// per observation) instead of materialising a second n x p copy on the host.
+int boomgpu_upload_begin(boomgpu_ctx *ctx, int poisson, int64_t n, int p) {
+  if (int rc = check_dims(ctx, n, p, p, n > 0 ? (const void *)ctx : nullptr)) return rc;
+  DeviceGuard g(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  free_data(ctx);
+  const int64_t ldd = ((int64_t)p + 7) / 8 * 8;
+  double *dX = nullptr, *daux = nullptr;
+  void *dy = nullptr;
+  const size_t n1 = (size_t)std::max<int64_t>(n, 1);
+  CU(cudaMalloc((void **)&dX, sizeof(double) * n1 * ldd));
+  ctx->owned.push_back(dX);
+  CU(cudaMalloc(&dy, 8 * n1));
+  ctx->owned.push_back(dy);
+  CU(cudaMalloc((void **)&daux, sizeof(double) * n1));
+  ctx->owned.push_back(daux);
+  if (ldd != p && n) CU(cudaMemsetAsync(dX, 0, sizeof(double) * (size_t)(n * ldd), ctx->stream));
+  ctx->X = dX; ctx->ldx = ldd; ctx->n = n; ctx->p = p;
+  if (poisson) { ctx->yi = (const int64_t *)dy; ctx->exposure = daux; }
+  else { ctx->y = (const double *)dy; ctx->ntrials = daux; }
+  ctx->model = -1;                 // not usable until boomgpu_upload_end
+  ctx->upload_kind = poisson ? kPoisson : kLogit;
+  return 0;
+}
+
+int boomgpu_upload_rows(boomgpu_ctx *ctx, int64_t row0, int64_t nrows, const double *X, int64_t ldx, const void *y, const double *aux) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (ctx->upload_kind < 0 || !ctx->X) return fail(ctx, BOOMGPU_ERR_STATE, "boomgpu_upload_rows without boomgpu_upload_begin");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > ctx->n || ldx < ctx->p || (nrows > 0 && (!X || !y || !aux)))
+    return fail(ctx, BOOMGPU_ERR_ARG, "bad row range [%lld, %lld) of %lld", (long long)row0, (long long)(row0 + nrows), (long long)ctx->n);
+  if (nrows == 0) return 0;
+  DeviceGuard g(ctx->device);
+  double *dX = const_cast<double *>(ctx->X) + row0 * ctx->ldx;
+  CU(cudaMemcpy2DAsync(dX, sizeof(double) * ctx->ldx, X, sizeof(double) * ldx, sizeof(double) * ctx->p, (size_t)nrows,
+                       cudaMemcpyHostToDevice, ctx->stream));
+  void *dy = ctx->upload_kind == kPoisson ? (void *)(const_cast<int64_t *>(ctx->yi) + row0) : (void *)(const_cast<double *>(ctx->y) + row0);
+  double *da = const_cast<double *>(ctx->upload_kind == kPoisson ? ctx->exposure : ctx->ntrials) + row0;
+  CU(cudaMemcpyAsync(dy, y, 8 * (size_t)nrows, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(da, aux, sizeof(double) * (size_t)nrows, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));   // the caller re-uses its chunk buffers
+  return 0;
+}
+
+int boomgpu_upload_end(boomgpu_ctx *ctx) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (ctx->upload_kind < 0 || !ctx->X) return fail(ctx, BOOMGPU_ERR_STATE, "boomgpu_upload_end without boomgpu_upload_begin");
+  DeviceGuard g(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->model = ctx->upload_kind;
+  ctx->upload_kind = -1;
   return 0;
 }
 
@@ -937,14 +1013,21 @@ int boomgpu_set_logit_mixture(boomgpu_ctx *ctx, int K, const double *mu, const d
   memset(&h, 0, sizeof(h));
   h.K = K;
   h.center = m.mu[0];
+  double lmax = -1e300;
+  for (int k = 0; k < K; ++k) lmax = std::max(lmax, m.lconst[k] * 1.4426950408889634);
+  h.zero_mean = 1; h.wide = 0;
   for (int k = 0; k < K; ++k) {
     h.lconst2[k] = (float)(m.lconst[k] * 1.4426950408889634);
+    h.l0[k] = (float)(m.lconst[k] * 1.4426950408889634 - lmax);
     h.hs2[k] = (float)(-0.5 * 1.4426950408889634 * m.inv_sigsq[k]);
     h.mu_c[k] = (float)(m.mu[k] - h.center);
     h.inv_sigsq[k] = m.inv_sigsq[k];
     h.mu_d[k] = m.mu[k];
     h.logw[k] = std::log(m.inv_sigsq[k]);
+    if (m.mu[k] != m.mu[0]) h.zero_mean = 0;
+    if (m.sigma[k] > m.sigma[h.wide]) h.wide = k;
   }
+  if (h.wide != K - 1) h.zero_mean = 0;   // the scale-mixture fast path takes the LAST component as the widest (the logit table is sorted by sigma)
   DeviceGuard g(ctx->device);
   if (!ctx->mix_dev) CU(cudaMalloc((void **)&ctx->mix_dev, sizeof(LogitMixtureDev)));
   CU(cudaStreamSynchronize(ctx->stream));   // no step may still be reading the old mixture

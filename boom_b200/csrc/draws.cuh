@@ -35,21 +35,38 @@ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
   return c;
 }
 
+// (k + 1/2) 2^-52 for the 52-bit integer k = hi : top 20 bits of lo -- exact, strictly inside (0, 1).  The 52 bits are dropped
+// into the mantissa of a double in [1, 2) and 1 - 2^-53 is subtracted: one exact DADD instead of a 64-bit integer -> double
+// conversion, an add and a multiply (same value, bit for bit, as the oracle's ((double)k + 0.5) * 2^-52).
 __device__ __forceinline__ double bits_to_open01(uint32_t hi, uint32_t lo) {
-  uint64_t k = ((uint64_t)hi << 20) | (uint64_t)(lo >> 12);
-  return ((double)k + 0.5) * 0x1p-52;  // (k + 1/2) 2^-52, exact, strictly inside (0,1)
+  const double d = __hiloint2double((int)(0x3ff00000u | (hi >> 12)), (int)__funnelshift_r(lo, hi, 12));
+  return d - 0x1.fffffffffffffp-1;
 }
 
-struct RngKey { uint64_t seed, iteration; };
+// seed / iteration key the stream; rk holds the ten Philox round keys (k0 + r 0x9E3779B9, k1 + r 0xBB67AE85) so that the
+// kernels read them as constants instead of re-deriving them per observation
+struct RngKey { uint64_t seed, iteration; uint32_t rk[20]; };
+
+__host__ __device__ inline void philox_round_keys(RngKey &key) {
+  uint32_t k0 = (uint32_t)key.seed, k1 = (uint32_t)(key.seed >> 32);
+  for (int r = 0; r < 10; ++r) { key.rk[2 * r] = k0; key.rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
 
 __device__ __forceinline__ void uniform_pair(const RngKey &key, uint64_t row, uint32_t slot, double &u0, double &u1) {
   U4 c;
   c.x = (uint32_t)row; c.y = (uint32_t)(row >> 32);
   c.z = (uint32_t)key.iteration;
   c.w = (((uint32_t)(key.iteration >> 32) & 0xFFFFu) << 16) | (slot & 0xFFFFu);
-  U4 o = philox4x32_10(c, (uint32_t)key.seed, (uint32_t)(key.seed >> 32));
-  u0 = bits_to_open01(o.x, o.y);
-  u1 = bits_to_open01(o.z, o.w);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    U4 n;
+    n.x = hi1 ^ c.y ^ key.rk[2 * r]; n.y = lo1; n.z = hi0 ^ c.w ^ key.rk[2 * r + 1]; n.w = lo0;
+    c = n;
+  }
+  u0 = bits_to_open01(c.x, c.y);
+  u1 = bits_to_open01(c.z, c.w);
 }
 
 // ---- mixtures -------------------------------------------------------------------------
@@ -76,6 +93,10 @@ struct LogitHot {
   double inv_sigsq[kMaxLogitK];
   double mu_d[kMaxLogitK];       // FP64 component means and log(1 / sigma^2): what the Poisson statistics add per draw
   double logw[kMaxLogitK];
+  // scale mixtures (every component mean equal -- the logit table): lconst2 shifted so that its maximum is 0, and the
+  // index of the widest component.  exp2(hs2 d^2 + l0) then cannot overflow and needs no per-draw maximum.
+  int zero_mean, wide;
+  float l0[kMaxLogitK];
 };
 
 // Poisson table in global memory (per-row nu makes the lookups divergent).
@@ -173,6 +194,41 @@ __device__ __forceinline__ bool unmix_certified(int K, float r_c, double unif, F
   return margin > kUnmixMargin * tot * fmaf(0.05f, fabsf(mx), 1.f);
 }
 
+// The same certificate for a SCALE mixture (all means equal: the 9-component logit table), K known at compile time.
+// log2 q_s = hs2_s d^2 + l0_s with l0 <= 0, so every exponent is <= 0 (no maximum to find, no overflow) and the largest one
+// is at least the widest component's: |log2 q_max| <= |log2 q_wide| bounds the error scale of the certificate.  The
+// indicator is the number of cumulative sums below U sum q -- the first k with U sum q <= q_0 + .. + q_k of the FP64 rule.
+// 2^x by the SFU alone (MUFU.EX2, ~2 ulp, denormal results flushed to zero): exp2f() wraps the same instruction in a range
+// test and two scalings that the exponents here (<= 0, and a flushed tail term is a zero probability) do not need
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int K>
+__device__ __forceinline__ bool unmix_certified_scale(const LogitHot &h, float r_c, double unif, int &kout) {
+  const float d2 = r_c * r_c;
+  float cs[K];
+#pragma unroll
+  for (int s = 0; s < K; ++s) cs[s] = ex2_approx(fmaf(h.hs2[s], d2, h.l0[s]));
+#pragma unroll
+  for (int s = 1; s < K; ++s) cs[s] += cs[s - 1];
+  const float tot = cs[K - 1];
+  const float v = (float)unif * tot;
+  int k = 0;
+  float margin = 3.0e38f;
+#pragma unroll
+  for (int s = 0; s < K - 1; ++s) {
+    const float dd = v - cs[s];
+    k += dd > 0.f ? 1 : 0;
+    margin = fminf(margin, fabsf(dd));
+  }
+  kout = k;
+  const float qw = fmaf(h.hs2[K - 1], d2, h.l0[K - 1]);   // host orders nothing: `wide` is checked to be K - 1 when zero_mean is set
+  return d2 < 2000.f && margin > kUnmixMargin * tot * fmaf(-0.05f, qw, 1.f);
+}
+
 // the FP64 statements of the selection, out of line: taken by ~1e-3 of the draws
 __device__ __noinline__ int unmix_logit_fp64(const LogitMixture *__restrict__ m, double resid, double unif) {
   return unmix_generic(m->K, unif, [&](int s) {
@@ -195,7 +251,8 @@ __device__ __forceinline__ int unmix_logit(const LogitHot &h, const LogitMixture
   auto lc_of = [&](int s) { return h.lconst2[s]; };
   auto hs_of = [&](int s) { return h.hs2[s]; };
   const float r_c = (float)(resid - h.center);
-  if (h.K == 9) ok = unmix_certified<9>(9, r_c, unif, mu_of, lc_of, hs_of, k);
+  if (h.K == 9 && h.zero_mean) ok = unmix_certified_scale<9>(h, r_c, unif, k);
+  else if (h.K == 9) ok = unmix_certified<9>(9, r_c, unif, mu_of, lc_of, hs_of, k);
   else ok = unmix_certified<kMaxLogitK>(h.K, r_c, unif, mu_of, lc_of, hs_of, k);
   if (!ok) k = unmix_logit_fp64(m, resid, unif);
   return k;
@@ -215,24 +272,20 @@ __device__ __forceinline__ double rtrun_logit(double eta, bool success, double u
 
 // exp(x) for |x| <= 708: Cody-Waite reduction by ln 2, degree-13 Taylor polynomial on |r| <= ln2 / 2 (truncation
 // 4e-18), scaling by 2^k through the exponent field (the result is a normal number over the whole range).
+// The coefficients live in constant memory: a DFMA takes one operand straight from the constant bank, whereas a literal
+// FP64 constant costs two UMOV to assemble in a uniform register (38 of the 434 instructions of a Bernoulli draw).
+static __constant__ double kExpC[17] = {
+    1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10,   // log2 e, -ln2_hi, -ln2_lo (fdlibm split)
+    1.6059043836821613e-10, 2.08767569878680990e-09, 2.50521083854417188e-08, 2.75573192239858907e-07,   // 1/13! .. 1/10!
+    2.75573192239858907e-06, 2.48015873015873016e-05, 1.98412698412698413e-04, 1.38888888888888894e-03,  // 1/9! .. 1/6!
+    8.33333333333333322e-03, 4.16666666666666644e-02, 1.66666666666666657e-01, 0.5, 1.0, 1.0};
 __device__ __forceinline__ double exp_nobranch(double x) {
-  const double kd = rint(x * 1.4426950408889634074);
-  double r = fma(kd, -6.93147180369123816490e-01, x);    // ln2_hi (fdlibm split)
-  r = fma(kd, -1.90821492927058770002e-10, r);           // ln2_lo
-  double p = 1.6059043836821613e-10;                     // 1/13!
-  p = fma(p, r, 2.08767569878680990e-09);                // 1/12!
-  p = fma(p, r, 2.50521083854417188e-08);                // 1/11!
-  p = fma(p, r, 2.75573192239858907e-07);                // 1/10!
-  p = fma(p, r, 2.75573192239858907e-06);                // 1/9!
-  p = fma(p, r, 2.48015873015873016e-05);                // 1/8!
-  p = fma(p, r, 1.98412698412698413e-04);                // 1/7!
-  p = fma(p, r, 1.38888888888888894e-03);                // 1/6!
-  p = fma(p, r, 8.33333333333333322e-03);                // 1/5!
-  p = fma(p, r, 4.16666666666666644e-02);                // 1/4!
-  p = fma(p, r, 1.66666666666666657e-01);                // 1/3!
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
+  const double kd = rint(x * kExpC[0]);
+  double r = fma(kd, kExpC[1], x);
+  r = fma(kd, kExpC[2], r);
+  double p = kExpC[3];
+#pragma unroll
+  for (int i = 4; i < 17; ++i) p = fma(p, r, kExpC[i]);
   const int k = (int)kd;
   return __hiloint2double(__double2hiint(p) + k * 1048576, __double2loint(p));
 }
@@ -247,6 +300,9 @@ __device__ __forceinline__ double rcp_nobranch(double d) {
   return fma(r, e, r);
 }
 
+static __constant__ double kLogC[9] = {1.531383769920937332e-01, 2.222219843214978396e-01, 3.999999999940941908e-01,   // Lg6, Lg4, Lg2
+                                       1.479819860511658591e-01, 1.818357216161805012e-01, 2.857142874366239149e-01,   // Lg7, Lg5, Lg3
+                                       6.666666666666735130e-01, 6.93147180369123816490e-01, 1.90821492927058770002e-10};  // Lg1, ln2_hi, ln2_lo
 // log(v) for a positive normal v: fdlibm e_log.c (m in [sqrt(1/2), sqrt 2), s = f / (2 + f), Lg1..Lg7), < 1 ulp
 __device__ __forceinline__ double log_nobranch(double v) {
   int hi = __double2hiint(v);
@@ -259,11 +315,10 @@ __device__ __forceinline__ double log_nobranch(double v) {
   const double f = m - 1.0;
   const double s = f * rcp_nobranch(2.0 + f);
   const double z = s * s, w = z * z;
-  const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
-  const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
-                            6.666666666666735130e-01);
+  const double t1 = w * fma(w, fma(w, kLogC[0], kLogC[1]), kLogC[2]);
+  const double t2 = z * fma(w, fma(w, fma(w, kLogC[3], kLogC[4]), kLogC[5]), kLogC[6]);
   const double R = t1 + t2, hfsq = 0.5 * f * f, dk = (double)e;
-  return fma(dk, 6.93147180369123816490e-01, f - (hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)));
+  return fma(dk, kLogC[7], f - (hfsq - fma(s, hfsq + R, dk * kLogC[8])));
 }
 
 // rtrun_logit for |eta| < 600, algebraically: with E = exp(eta), c = 1 / (1 + E),
@@ -418,6 +473,7 @@ __device__ __noinline__ bool logit_impute_general(const LogitMixtureDev *__restr
   if (!(y <= ntrials) || y < 0 || ntrials < 0 || !isfinite(eta)) return false;
   RngKey key;
   key.seed = seed; key.iteration = iteration;
+  philox_round_keys(key);
   if (ntrials > (double)clt_threshold) {
     if (md->full.K > 9) return false;  // slot layout of the CLT branch: K - 1 <= 8 conditional binomials per side
     logit_impute_large(&md->full, ntrials, y, eta, key, row, sum, info);
@@ -458,7 +514,8 @@ __device__ __forceinline__ void logit_bernoulli_draws(const LogitHot &h, const L
 #pragma unroll
   for (int j = 0; j < R; ++j) {
     const float r_c = (float)((z[j] - eta[j]) - h.center);
-    if (h.K == 9) ok[j] = unmix_certified<9>(9, r_c, u1[j], mu_of, lc_of, hs_of, k[j]);
+    if (h.K == 9 && h.zero_mean) ok[j] = unmix_certified_scale<9>(h, r_c, u1[j], k[j]);
+    else if (h.K == 9) ok[j] = unmix_certified<9>(9, r_c, u1[j], mu_of, lc_of, hs_of, k[j]);
     else ok[j] = unmix_certified<kMaxLogitK>(h.K, r_c, u1[j], mu_of, lc_of, hs_of, k[j]);
   }
 #pragma unroll

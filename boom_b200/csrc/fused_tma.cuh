@@ -50,7 +50,13 @@ __host__ __device__ constexpr int tma_rpl(int nb) { return nb <= 2 ? BOOMGPU_TMA
 #endif
 __host__ __device__ constexpr int tma_warps(int nb) { return nb <= 2 ? BOOMGPU_TMA_NW_SMALL : (nb == 3 ? 12 : (nb == 4 ? 10 : BOOMGPU_TMA_NW_WIDE)); }
 __host__ __device__ constexpr int tma_stages(int nb) { return nb <= 2 ? BOOMGPU_TMA_S_SMALL : (nb <= 4 ? 2 : BOOMGPU_TMA_S_WIDE); }
-__host__ __device__ constexpr int tma_padw(int nb) { return 8 * nb + 4; }
+// Row pitch of a slice in shared memory: 8 NB + 2 doubles = 16 NB + 4 words.  (a) lane r reads row r with 16-byte loads:
+// a quarter warp's rows start 4 r (NB even) or 20 r (NB odd) words apart mod 32 -- eight distinct 4-bank groups, conflict
+// free with NO per-lane rotation of the column order, so beta comes straight from the constant bank with compile-time
+// indices.  (b) the four rows of a DMMA k-step are taken two apart (rows 8 t + u + 2 k, see the k loop): 2 pitches =
+// 32 NB + 8 words = 8 mod 32, so the 16 lanes of a fragment load (4 rows x 4 columns x 8 bytes) cover 32 distinct banks.
+// The two pad columns of row r hold (w_r, s_r).
+__host__ __device__ constexpr int tma_padw(int nb) { return 8 * nb + 2; }
 __host__ __device__ constexpr int tma_slice_rows(int nb) { return 32 * tma_rpl(nb); }
 __host__ __device__ constexpr int tma_slice_doubles(int nb) { return tma_slice_rows(nb) * tma_padw(nb); }
 __host__ __device__ constexpr size_t tma_smem_bytes(int nb) {
@@ -83,7 +89,6 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int p = d.p;
-  if (tid < P8) beta_s[tid] = tid < p ? beta.b[tid] : 0.0;
   if (tid == 0) {
     for (int i = 0; i < NW * S; ++i) mbar_init(bars + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -115,7 +120,6 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
 #pragma unroll
   for (int b = 0; b < NB; ++b) xty_acc[b] = 0.0;
   double sc_count = 0, sc_ywy = 0, sc_sumw = 0, sc_sumlogw = 0;
-  const int rot = (lane >> 2) & 3;
 
   int slot = 0;
   uint32_t phase = 0;
@@ -151,15 +155,11 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
       for (int j = 0; j < RPL; ++j) { e0[j] = 0; e1[j] = 0; }
 #pragma unroll
       for (int col = 0; col < P8; col += 2) {
-        int j0 = col + rot, j1 = col + 1 + rot;
-        j0 = j0 >= P8 ? j0 - P8 : j0;
-        j1 = j1 >= P8 ? j1 - P8 : j1;
-        const double b0 = beta_s[j0], b1 = beta_s[j1];
 #pragma unroll
         for (int j = 0; j < RPL; ++j) {
-          const double *xr = xs + (32 * j + lane) * PADW;
-          e0[j] = fma(xr[j0], b0, e0[j]);
-          e1[j] = fma(xr[j1], b1, e1[j]);
+          const double2 x = *reinterpret_cast<const double2 *>(xs + (32 * j + lane) * PADW + col);
+          e0[j] = fma(x.x, beta.b[col], e0[j]);        // beta: kernel parameter, constant-bank operand
+          e1[j] = fma(x.y, beta.b[col + 1], e1[j]);
         }
       }
 #pragma unroll
@@ -206,9 +206,9 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
     __syncwarp();
 
     // ---- the warp's rank-1 updates: DMMA k-steps of 4 rows
-#pragma unroll 2
+#pragma unroll(NB <= 2 ? 8 : (NB <= 4 ? 4 : 2))
     for (int kk = 0; kk < ROWS / 4; ++kk) {
-      const int row = kk * 4 + (lane & 3);
+      const int row = 8 * (kk >> 1) + (kk & 1) + 2 * (lane & 3);   // the k-step's four rows, two apart (bank layout: tma_padw)
       const double2 ws = *reinterpret_cast<const double2 *>(xs + row * PADW + P8);
       const double wk = ws.x, sk = ws.y;
       const double *xr = xs + row * PADW + (lane >> 2);

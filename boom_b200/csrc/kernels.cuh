@@ -498,7 +498,9 @@ constexpr size_t kSyrkSmemBytes = sizeof(double) * kSyrkStages * kSyrkStageDoubl
 constexpr int64_t kSyrkTileLen = 128 * 128 + 128;
 
 struct SyrkUnit { int8_t ui, uj, flags; };  // flags: 1 valid, 2 diagonal unit, 4 xty duty, 8 xty duty when unit (ui, ui+1) is cut off by p
-struct SyrkUnitTable { SyrkUnit u[2][kSyrkConsumerWarps][2]; };  // [region type: 0 off-diagonal, 1 diagonal]
+// [region type: 0 off-diagonal, 1 diagonal, 2 / 3 the same when the region's LAST unit column is ragged (p mod 128 in
+// (96, 128): the p = 500 case), where the work is dealt so that every SM sub-partition gets its share of the cut units]
+struct SyrkUnitTable { SyrkUnit u[4][kSyrkConsumerWarps][2]; };
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
@@ -546,6 +548,8 @@ struct SyrkParams {
   int ksplit;
   int64_t rows_per_slice;  // multiple of kSyrkKB
   double *partials;  // [ksplit][nregions][kSyrkTileLen]
+  int diag_form;     // option "syrk_diag": 0 strip form for whole diagonal regions (default), 1 unit form everywhere
+  int filter;        // profiling aid (option "syrk_filter"): 0 all regions, 1 off-diagonal regions only, 2 diagonal only
 };
 
 __device__ __forceinline__ void region_to_blocks(int region, int nblk, int &I, int &J) {
@@ -671,6 +675,63 @@ __device__ __forceinline__ void syrk_consume(const SyrkWarpCtx &wc) {
   }
 }
 
+// The k loop of one consumer warp in a WHOLE diagonal region (all 128 columns inside X), strip form.  In 8 x 8 atoms the
+// region is a 16 x 16 grid of which the 136 atoms on or above the diagonal are wanted; warp W owns atom rows W and 15 - W:
+// (16 - W) + (W + 1) = 17 atoms for every warp, so the four SM sub-partitions carry 34 DMMA per k-step each (the unit
+// form deals 36 / 32 / 32 / 36 and leaves the two-diagonal-unit warps on the critical path with 16 fragment loads and
+// 8 DMUL per 20 DMMA).  The A fragment of atom row r is the B fragment of atom column r, so a k-step loads the B fragments
+// of columns W .. 15 once and nothing else; X's for atom rows W and 15 - W rides on the same fragments (two DFMA).
+template <int W>
+__device__ __forceinline__ void syrk_consume_strip(const SyrkWarpCtx &wc) {
+  constexpr int R1 = W, R2 = 15 - W, N1 = 16 - R1, N2 = 16 - R2;
+  const int lane = wc.lane;
+  double c1[N1][2], c2[N2][2], cx1 = 0.0, cx2 = 0.0;
+#pragma unroll
+  for (int n = 0; n < N1; ++n) c1[n][0] = c1[n][1] = 0.0;
+#pragma unroll
+  for (int n = 0; n < N2; ++n) c2[n][0] = c2[n][1] = 0.0;
+  const int off = lane >> 2;
+  for (int it = 0; it < wc.nstages_total; ++it) {
+    const int s = it % kSyrkStages;
+    const uint32_t phase = (it / kSyrkStages) & 1;
+    mbar_wait(wc.full_bar + s, phase);
+    const double *stage = wc.smem + s * kSyrkStageDoubles;
+    const double *w_s = stage + 2 * kSyrkKB * kSyrkPanelLd;
+    const double *s_s = w_s + kSyrkKB;
+#pragma unroll
+    for (int kk = 0; kk < kSyrkKB / 4; ++kk) {
+      const int row = kk * 4 + (lane & 3);
+      const double wv = w_s[row], sv = s_s[row];
+      const double *xr = stage + row * kSyrkPanelLd + off;
+      double b[N1];
+#pragma unroll
+      for (int n = 0; n < N1; ++n) b[n] = xr[8 * (R1 + n)];
+      const double a1 = b[0] * wv, a2 = b[R2 - R1] * wv;
+#pragma unroll
+      for (int n = 0; n < N1; ++n) dmma884(c1[n][0], c1[n][1], a1, b[n]);
+#pragma unroll
+      for (int n = 0; n < N2; ++n) dmma884(c2[n][0], c2[n][1], a2, b[R2 - R1 + n]);
+      cx1 = fma(b[0], sv, cx1);
+      cx2 = fma(b[R2 - R1], sv, cx2);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(wc.empty_bar + s);
+  }
+  double *tile = wc.tile;
+#pragma unroll
+  for (int n = 0; n < N1; ++n)
+    *reinterpret_cast<double2 *>(tile + (8 * R1 + off) * 128 + 8 * (R1 + n) + 2 * (lane & 3)) = make_double2(c1[n][0], c1[n][1]);
+#pragma unroll
+  for (int n = 0; n < N2; ++n)
+    *reinterpret_cast<double2 *>(tile + (8 * R2 + off) * 128 + 8 * (R2 + n) + 2 * (lane & 3)) = make_double2(c2[n][0], c2[n][1]);
+  cx1 += __shfl_xor_sync(0xffffffffu, cx1, 1); cx1 += __shfl_xor_sync(0xffffffffu, cx1, 2);
+  cx2 += __shfl_xor_sync(0xffffffffu, cx2, 1); cx2 += __shfl_xor_sync(0xffffffffu, cx2, 2);
+  if ((lane & 3) == 0) {
+    tile[128 * 128 + 8 * R1 + off] = cx1;
+    tile[128 * 128 + 8 * R2 + off] = cx2;
+  }
+}
+
 template <int NM>
 __device__ __forceinline__ void syrk_dispatch_nm(int role, const SyrkWarpCtx &wc) {
   if (kSyrkConsumerWarps == 8) {
@@ -719,6 +780,7 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap xmap, SyrkParams prm, SyrkU
   int I, J;
   region_to_blocks(region, prm.nblk, I, J);
   const bool diag = (I == J);
+  if (prm.filter && (prm.filter == 1) == diag) return;   // profiling aid: results are incomplete on purpose
   const int64_t row_begin = (int64_t)kslice * prm.rows_per_slice;
   const int64_t row_end = min(prm.n, row_begin + prm.rows_per_slice);
   const int nstages_total = row_end > row_begin ? (int)((row_end - row_begin + kSyrkKB - 1) / kSyrkKB) : 0;
@@ -765,9 +827,29 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap xmap, SyrkParams prm, SyrkU
 
   // ===== consumer role: resolved ONCE per warp into compile-time unit types so that the k loop
   // carries no predicates (a predicated mma.sync costs a WARPSYNC + branch per instruction).
-  SyrkUnit u0 = table.u[diag ? 1 : 0][wid][0];
-  SyrkUnit u1 = table.u[diag ? 1 : 0][wid][1];
   const int P8 = (prm.p + 7) & ~7;
+  const int remJ = P8 - 128 * J;   // columns (whole 8-column atoms) of column block J inside X
+  if (kSyrkConsumerWarps == 8 && diag && remJ >= 128 && prm.diag_form == 0) {   // whole diagonal region: strip form
+    SyrkWarpCtx wc;
+    wc.smem = smem; wc.full_bar = full_bar; wc.empty_bar = empty_bar; wc.nstages_total = nstages_total;
+    wc.lane = lane;
+    wc.panelB_off = 0;
+    wc.tile = prm.partials + ((int64_t)kslice * prm.nregions + region) * kSyrkTileLen;
+    switch (wid) {
+      case 0: syrk_consume_strip<0>(wc); break;
+      case 1: syrk_consume_strip<1>(wc); break;
+      case 2: syrk_consume_strip<2>(wc); break;
+      case 3: syrk_consume_strip<3>(wc); break;
+      case 4: syrk_consume_strip<4>(wc); break;
+      case 5: syrk_consume_strip<5>(wc); break;
+      case 6: syrk_consume_strip<6>(wc); break;
+      default: syrk_consume_strip<7>(wc); break;
+    }
+    return;
+  }
+  const int ttype = (diag ? 1 : 0) + ((remJ > 96 && remJ < 128) ? 2 : 0);
+  SyrkUnit u0 = table.u[ttype][wid][0];
+  SyrkUnit u1 = table.u[ttype][wid][1];
   // 8-column atoms of each unit that lie inside X (<= 0: the whole unit is cut off by p)
   const int mmax0 = min(4, (P8 - 128 * I - 32 * u0.ui) / 8), nmax0 = min(4, (P8 - 128 * J - 32 * u0.uj) / 8);
   const int mmax1 = min(4, (P8 - 128 * I - 32 * u1.ui) / 8), nmax1 = min(4, (P8 - 128 * J - 32 * u1.uj) / 8);

@@ -85,6 +85,13 @@ int boomgpu_upload_binomial(boomgpu_ctx *ctx, int64_t n, int p, const double *X,
                             const double *y, const double *ntrials);
 int boomgpu_upload_poisson(boomgpu_ctx *ctx, int64_t n, int p, const double *X, int64_t ldx,
                            const int64_t *y, const double *exposure);
+/* The same upload a chunk of rows at a time, for callers whose rows are not one contiguous host matrix (BOOM: one heap
+ * object per observation, IID_DataPolicy.hpp:57-58): begin allocates, rows copies rows [row0, row0 + nrows) and returns when
+ * the caller's chunk buffers may be re-used, end makes the data usable.  y: nrows doubles (binomial) or int64 (poisson);
+ * aux: trials / exposure. */
+int boomgpu_upload_begin(boomgpu_ctx *ctx, int poisson, int64_t n, int p);
+int boomgpu_upload_rows(boomgpu_ctx *ctx, int64_t row0, int64_t nrows, const double *X, int64_t ldx, const void *y, const double *aux);
+int boomgpu_upload_end(boomgpu_ctx *ctx);
 /* data already resident in HBM (device pointers; caller keeps them alive).  Used in place when TMA can describe them
  * (16-byte aligned base, even ldx); for p > 64 rows that do not qualify (e.g. a contiguous n x 501 tensor) are copied ONCE,
  * at the first step, into a padded device buffer owned by the context -- a second copy of X in HBM. */
