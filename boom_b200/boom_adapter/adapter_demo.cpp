@@ -10,6 +10,8 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -18,6 +20,7 @@
 #include "Models/Glm/PoissonRegressionData.hpp"
 #include "Models/Glm/PoissonRegressionModel.hpp"
 #include "Models/Glm/PosteriorSamplers/BinomialLogitAuxmixSampler.hpp"
+#include "Models/Glm/PosteriorSamplers/BinomialLogitCompositeSpikeSlabSampler.hpp"
 #include "Models/Glm/PosteriorSamplers/BinomialLogitSpikeSlabSampler.hpp"
 #include "Models/Glm/PosteriorSamplers/PoissonRegressionAuxMixSampler.hpp"
 #include "Models/Glm/PosteriorSamplers/PoissonRegressionSpikeSlabSampler.hpp"
@@ -123,6 +126,74 @@ int main(int argc, char **argv) {
              "\"adapter_host_ms\": %.4f, \"standalone_ms_per_iter\": %.4f, \"adapter_first_iteration_with_upload_s\": %.3f, "
              "\"model_size_at_end\": %d}\n",
              n, p, iters, 1e3 * adapter_s / iters, 1e3 * dev_s / iters, 1e3 * host_s / iters, 1e3 * standalone_s / iters, first, nvars);
+      return 0;
+    }
+    if (kind == "composite" || kind == "chunk") {
+      // BinomialLogitCompositeSpikeSlabSampler (what R's logit.spike builds): reference vs B200 on the same data.
+      // "chunk": the chunk log posterior with gradient and Hessian, value by value; "composite": the chains.
+      const double tdf = 3.0;
+      const int max_tim = 4, max_rwm = 2;
+      if (kind == "chunk") {
+        NEW(BinomialLogitModel, model)(p);
+        for (int i = 0; i < n; ++i) model->add_data(new BinomialRegressionData(ys[i], 1.0 + (i % 3), xs[i]));
+        model->coef().drop_all();
+        for (int j = 0; j < p; j += 2) model->coef().add(j);
+        Vector b = model->included_coefficients();
+        for (size_t j = 0; j < b.size(); ++j) b[j] = 0.1 * (j % 3) - 0.1;
+        model->set_included_coefficients(b);
+        NEW(BinomialLogitCompositeSpikeSlabSampler, r)(model.get(), slab, spike, 10, tdf, max_tim, max_rwm);
+        Ptr<B200::BinomialLogitCompositeSpikeSlabSampler> g(
+            new B200::BinomialLogitCompositeSpikeSlabSampler(model.get(), slab, spike, 10, tdf, max_tim, max_rwm));
+        printf("{\"kind\": \"chunk\", \"cases\": [");
+        const int nvars = (int)model->coef().nvars();
+        bool first = true;
+        for (int max_chunk : {2, 3, 0}) {
+          const int nchunks = max_chunk <= 0 ? 1 : (nvars + max_chunk - 1) / max_chunk;
+          for (int chunk = 0; chunk < nchunks; ++chunk) {
+            BinomialLogitLogPostChunk fr = r->log_posterior(chunk, max_chunk);
+            B200::BinomialLogitLogPostChunk fg = g->log_posterior(chunk, max_chunk);
+            // chunk size as the samplers compute it
+            Vector gr, gg; Matrix hr, hg;
+            int cs = 0;
+            { Vector probe = model->included_coefficients(); int per = max_chunk <= 0 ? nvars : (nvars + nchunks - 1) / nchunks;
+              cs = std::min(per, nvars - per * chunk); }
+            Vector bc(cs);
+            for (int j = 0; j < cs; ++j) bc[j] = 0.05 * j - 0.02 * chunk;
+            const double vr = fr(bc, gr, hr, 2), vg = fg(bc, gg, hg, 2);
+            printf("%s{\"value_ref\": %.15g, \"value_b200\": %.15g, \"grad_diff\": %.3g, \"hess_diff\": %.3g, \"hess_scale\": %.3g}",
+                   first ? "" : ", ", vr, vg, (gr - gg).max_abs(), (hr - hg).max_abs(), hr.max_abs());
+            first = false;
+          }
+        }
+        printf("]}\n");
+        return 0;
+      }
+      Summary out[2];
+      std::string report;
+      for (int arm = 0; arm < 2; ++arm) {
+        NEW(BinomialLogitModel, model)(p);
+        for (int i = 0; i < n; ++i) model->add_data(new BinomialRegressionData(ys[i], 1.0, xs[i]));
+        model->coef().drop_all(); model->coef().add(0);
+        RNG seeder(arm == 0 ? 41 : 42);
+        if (arm == 0) {
+          NEW(BinomialLogitCompositeSpikeSlabSampler, s)(model.get(), slab, spike, 10, tdf, max_tim, max_rwm, 1.0, seeder);
+          model->set_method(s);
+          out[arm] = run(model, iters, burn);
+        } else {
+          Ptr<B200::BinomialLogitCompositeSpikeSlabSampler> s(
+              new B200::BinomialLogitCompositeSpikeSlabSampler(model.get(), slab, spike, 10, tdf, max_tim, max_rwm, 1.0, seeder));
+          model->set_method(s);
+          out[arm] = run(model, iters, burn);
+          std::ostringstream os;
+          s->time_report(os);
+          report = os.str();
+        }
+      }
+      printf("{\"kind\": \"composite\", \"n\": %d, \"p\": %d, \"iters\": %d, \"burn\": %d, ", n, p, iters, burn);
+      print_vec("beta_true", beta);
+      print_summary("reference", out[0]); printf(", ");
+      print_summary("b200", out[1]);
+      printf(", \"time_report_lines\": %d}\n", (int)std::count(report.begin(), report.end(), '\n'));
       return 0;
     }
     if (kind == "api") {

@@ -10,6 +10,8 @@
 #include "Models/Glm/PosteriorSamplers/NormalMixtureApproximation.hpp"
 #include "Models/Glm/PosteriorSamplers/poisson_mixture_approximation_table.hpp"
 #include "Models/MvnModel.hpp"
+#include "Samplers/TIM.hpp"
+#include "cpputil/math_utils.hpp"
 #include "cpputil/report_error.hpp"
 #include "distributions.hpp"
 
@@ -149,6 +151,39 @@ double DeviceImputerBase::loglike_derivs(const BOOM_B200::Vector &b, BOOM_B200::
   if (g) g->assign(packed_.begin() + mat, packed_.begin() + mat + p);
   if (h) for (size_t e = 0; e < mat; ++e) h->a[e] = -packed_[e];
   return packed_[mat + p + 1];
+}
+
+double DeviceImputerBase::included_loglike_derivs(const Selector &inc, const Vector &beta_included, Vector *g, Matrix *h) {
+  Stopwatch sw(secs_device_);
+  ensure_device_rows();
+  const int k = (int)inc.nvars();
+  if ((int)beta_included.size() != k) report_error("included_loglike_derivs: beta does not match the inclusion pattern");
+  std::vector<int32_t> cols;
+  for (int j = 0; j < (int)inc.nvars_possible(); ++j) if (inc[j]) cols.push_back(j);
+  check(boomgpu_select_columns(ctx_, cols.data(), k));   // gathers X_gamma only when the pattern (or the data) changed
+  double ll = 0;
+  std::vector<double> hbuf(h ? (size_t)k * k : 0);
+  if (g) g->resize(k);
+  if (!allreduce_) {
+    check(device_loglike_derivs_selected(ctx_, beta_included.data(), &ll, g ? g->data() : nullptr, h ? hbuf.data() : nullptr));
+  } else {
+    const int64_t len = boomgpu_suf_len(k);
+    packed_.resize((size_t)len);
+    double *suf_dev = nullptr;
+    check(boomgpu_suf_buffer(ctx_, &suf_dev));   // sized for the full p: large enough for k <= p
+    check(device_loglike_derivs_selected_device(ctx_, beta_included.data(), suf_dev));
+    allreduce_(suf_dev, len);
+    check(boomgpu_download(ctx_, suf_dev, packed_.data(), len));
+    const size_t mat = (size_t)k * k;
+    ll = packed_[mat + k + 1];
+    if (g) std::copy(packed_.begin() + mat, packed_.begin() + mat + k, g->begin());
+    if (h) for (size_t e = 0; e < mat; ++e) hbuf[e] = -packed_[e];
+  }
+  if (h) {
+    *h = Matrix(k, k);
+    std::copy(hbuf.begin(), hbuf.end(), h->data());   // symmetric: row major == column major
+  }
+  return ll;
 }
 
 bool DeviceImputerBase::find_mode(GlmCoefs &coef, const Ptr<MvnBase> &slab, const Ptr<VariableSelectionPrior> &spike, double epsilon,
@@ -371,6 +406,12 @@ int BinomialLogitAuxmixSampler::device_loglike_derivs(boomgpu_ctx *ctx, const do
 int BinomialLogitAuxmixSampler::device_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) {
   return boomgpu_binomial_loglike_derivs_device(ctx, beta, model_->log_alpha(), suf_dev);
 }
+int BinomialLogitAuxmixSampler::device_loglike_derivs_selected(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) {
+  return boomgpu_binomial_loglike_derivs_selected(ctx, beta, model_->log_alpha(), loglike, g, h);
+}
+int BinomialLogitAuxmixSampler::device_loglike_derivs_selected_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) {
+  return boomgpu_binomial_loglike_derivs_selected_device(ctx, beta, model_->log_alpha(), suf_dev);
+}
 
 void BinomialLogitAuxmixSampler::draw() {
   impute_latent_data();
@@ -423,6 +464,187 @@ void BinomialLogitSpikeSlabSampler::set_slab(const Ptr<MvnBase> &slab) {
   if (slab->dim() != model_->xdim()) report_error("Slab does not match model dimension.");
   slab_ = slab;
   priors_changed();
+}
+
+// ---------------------------------------------------------------------------------------------
+BinomialLogitLogPostChunk::BinomialLogitLogPostChunk(BinomialLogitCompositeSpikeSlabSampler *sampler, int chunk_size, int chunk_number)
+    : sampler_(sampler), start_(chunk_size * chunk_number) {
+  const int nvars = (int)sampler_->m_->coef().nvars();
+  chunk_size_ = std::min(chunk_size, nvars - start_);
+}
+
+double BinomialLogitLogPostChunk::operator()(const Vector &beta_chunk) const {
+  Vector g;
+  Matrix h;
+  return (*this)(beta_chunk, g, h, 0);
+}
+
+// .cpp:34-74: log prior of ALL included coefficients with the chunk replaced + log likelihood; derivatives w.r.t. the chunk
+double BinomialLogitLogPostChunk::operator()(const Vector &beta_chunk, Vector &grad, Matrix &hess, int nd) const {
+  BinomialLogitModel *m = sampler_->m_;
+  Vector nonzero_beta = m->included_coefficients();
+  VectorView(nonzero_beta, start_, chunk_size_) = beta_chunk;
+  const Selector &inc(m->coef().inc());
+  const SpdMatrix siginv(inc.select(sampler_->pri_->siginv()));
+  const Vector mu(inc.select(sampler_->pri_->mu()));
+  double ans = dmvn(nonzero_beta, mu, siginv, 0.0, true);
+  Selector chunk_selector(nonzero_beta.size(), false);
+  for (int i = start_; i < start_ + chunk_size_; ++i) chunk_selector.add(i);
+  Vector g_full;
+  Matrix h_full;
+  ans += sampler_->chunk_loglike(nonzero_beta, nd > 0 ? &g_full : nullptr, nd > 1 ? &h_full : nullptr);
+  if (nd > 0) {
+    grad = -1 * chunk_selector.select(siginv * (nonzero_beta - mu));
+    grad += chunk_selector.select(g_full);
+    if (nd > 1) {
+      hess = chunk_selector.select(siginv);
+      hess *= -1;
+      for (int i = 0; i < chunk_size_; ++i)
+        for (int j = 0; j < chunk_size_; ++j) hess(i, j) += h_full(start_ + i, start_ + j);
+    }
+  }
+  return ans;
+}
+
+typedef BinomialLogitCompositeSpikeSlabSampler BLCSSS;
+BLCSSS::BinomialLogitCompositeSpikeSlabSampler(BinomialLogitModel *model, const Ptr<MvnBase> &prior,
+                                               const Ptr<VariableSelectionPrior> &vpri, int clt_threshold, double tdf,
+                                               int max_tim_chunk_size, int max_rwm_chunk_size, double rwm_variance_scale_factor,
+                                               RNG &seeding_rng)
+    : BinomialLogitSpikeSlabSampler(model, prior, vpri, clt_threshold, seeding_rng), m_(model), pri_(prior), tdf_(tdf),
+      max_tim_chunk_size_(max_tim_chunk_size), max_rwm_chunk_size_(max_rwm_chunk_size),
+      rwm_variance_scale_factor_(rwm_variance_scale_factor) {
+  set_sampler_weights(1.0, 1.0, 1.0);
+}
+
+void BLCSSS::draw() {   // .cpp:93-116
+  enum SamplingMethod { DATA_AUGMENTATION = 0, RWM = 1, TIM_METHOD = 2 };
+  const SamplingMethod method = SamplingMethod(rmulti_mt(rng(), sampler_weights_));
+  switch (method) {
+    case DATA_AUGMENTATION: {
+      MoveTimer timer = move_accounting_.start_time("auxmix");
+      BinomialLogitSpikeSlabSampler::draw();
+      move_accounting_.record_acceptance("auxmix");
+      break;
+    }
+    case RWM: {
+      MoveTimer timer = move_accounting_.start_time("rwm (total time)");
+      rwm_draw();
+      break;
+    }
+    case TIM_METHOD: {
+      MoveTimer timer = move_accounting_.start_time("TIM (total time)");
+      tim_draw();
+      break;
+    }
+    default:
+      report_error("Unknown method in BinomialLogitSpikeSlabSampler::draw.");
+  }
+}
+
+void BLCSSS::rwm_draw() {
+  if (m_->coef().nvars() == 0) return;
+  const int total_number_of_chunks = compute_number_of_chunks(max_rwm_chunk_size_);
+  for (int chunk = 0; chunk < total_number_of_chunks; ++chunk) rwm_draw_chunk(chunk);
+}
+
+// .cpp:127-184.  The proposal precision is the chunk of the negative log-posterior Hessian at the current beta (prior
+// precision + sum_i n_i p_i q_i x x'; the reference's loop weights by p_i q_i, which is the same thing for Bernoulli rows),
+// from the same device pass that gives the current log posterior.
+void BLCSSS::rwm_draw_chunk(int chunk) {
+  const Selector &inc(m_->coef().inc());
+  const int nvars = (int)inc.nvars();
+  Vector full_nonzero_beta = m_->included_coefficients();
+  const Vector mu(inc.select(pri_->mu()));
+  const SpdMatrix siginv(inc.select(pri_->siginv()));
+  double original_logpost = dmvn(full_nonzero_beta, mu, siginv, 0, true);
+  const int full_chunk_size = compute_chunk_size(max_rwm_chunk_size_);
+  const int chunk_start = chunk * full_chunk_size;
+  const int this_chunk_size = std::min(nvars - chunk_start, full_chunk_size);
+  Selector chunk_selector(nvars, false);
+  for (int i = chunk_start; i < chunk_start + this_chunk_size; ++i) chunk_selector.add(i);
+  SpdMatrix proposal_ivar = chunk_selector.select(siginv);
+  Matrix h_full;
+  original_logpost += chunk_loglike(full_nonzero_beta, nullptr, &h_full);
+  for (int i = 0; i < this_chunk_size; ++i)
+    for (int j = 0; j < this_chunk_size; ++j) proposal_ivar(i, j) -= h_full(chunk_start + i, chunk_start + j);
+  VectorView beta_chunk(full_nonzero_beta, chunk_start, this_chunk_size);
+  if (tdf_ > 0) beta_chunk = rmvt_ivar_mt(rng(), beta_chunk, proposal_ivar / rwm_variance_scale_factor_, tdf_);
+  else beta_chunk = rmvn_ivar_mt(rng(), beta_chunk, proposal_ivar / rwm_variance_scale_factor_);
+  double logpost = dmvn(full_nonzero_beta, mu, siginv, 0, true);
+  logpost += chunk_loglike(full_nonzero_beta, nullptr, nullptr);
+  const double log_alpha = logpost - original_logpost;
+  const double logu = log(runif_mt(rng()));
+  if (logu < log_alpha) {
+    m_->set_included_coefficients(full_nonzero_beta);
+    move_accounting_.record_acceptance("rwm_chunk");
+  } else {
+    move_accounting_.record_rejection("rwm_chunk");
+  }
+}
+
+void BLCSSS::tim_draw() {   // .cpp:187-221
+  const int nvars = (int)m_->coef().nvars();
+  if (nvars == 0) return;
+  const int chunk_size = compute_chunk_size(max_tim_chunk_size_);
+  const int number_of_chunks = compute_number_of_chunks(max_tim_chunk_size_);
+  for (int chunk = 0; chunk < number_of_chunks; ++chunk) {
+    clock_t mode_start = clock();
+    TIM tim_sampler(log_posterior(chunk, max_tim_chunk_size_), tdf_, &rng());
+    Vector beta = m_->included_coefficients();
+    const int start = chunk_size * chunk;
+    VectorView beta_chunk(beta, start, std::min(nvars - start, chunk_size));
+    const bool ok = tim_sampler.locate_mode(beta_chunk);
+    move_accounting_.stop_time("tim mode finding", mode_start);
+    if (ok) {
+      move_accounting_.record_acceptance("tim mode finding");
+      tim_sampler.fix_mode(true);
+      MoveTimer timer = move_accounting_.start_time("TIM chunk");
+      beta_chunk = tim_sampler.draw(beta_chunk);
+      m_->set_included_coefficients(beta);
+      if (tim_sampler.last_draw_was_accepted()) move_accounting_.record_acceptance("TIM chunk");
+      else move_accounting_.record_rejection("TIM chunk");
+    } else {
+      move_accounting_.record_rejection("tim mode finding");
+      rwm_draw_chunk(chunk);
+    }
+  }
+}
+
+BinomialLogitLogPostChunk BLCSSS::log_posterior(int chunk, int max_chunk_size) const {
+  return BinomialLogitLogPostChunk(const_cast<BLCSSS *>(this), compute_chunk_size(max_chunk_size), chunk);
+}
+
+void BLCSSS::set_sampler_weights(double da_weight, double rwm_weight, double tim_weight) {
+  if (da_weight < 0 || rwm_weight < 0 || tim_weight < 0) report_error("All three weights must be non-negative.");
+  if (da_weight <= 0 && rwm_weight <= 0 && tim_weight <= 0) report_error("At least one weight must be positive.");
+  sampler_weights_.resize(3);
+  sampler_weights_[0] = da_weight;
+  sampler_weights_[1] = rwm_weight;
+  sampler_weights_[2] = tim_weight;
+  sampler_weights_ /= sum(sampler_weights_);
+}
+
+int BLCSSS::compute_chunk_size(int max_chunk_size) const {
+  const int nvars = (int)m_->coef().nvars();
+  if (max_chunk_size <= 0) return nvars;
+  const int number_of_full_chunks = nvars / max_chunk_size;
+  const bool has_partial_chunk = number_of_full_chunks * max_chunk_size < nvars;
+  const int total_chunks = number_of_full_chunks + has_partial_chunk;
+  return divide_rounding_up(nvars, total_chunks);
+}
+
+int BLCSSS::compute_number_of_chunks(int max_chunk_size) const {
+  if (max_chunk_size <= 0) return 1;
+  const int nvars = (int)m_->coef().nvars();
+  const int number_of_full_chunks = nvars / max_chunk_size;
+  const bool has_partial_chunk = number_of_full_chunks * max_chunk_size < nvars;
+  return number_of_full_chunks + has_partial_chunk;
+}
+
+std::ostream &BLCSSS::time_report(std::ostream &out) const {
+  out << move_accounting_.to_matrix();
+  return out;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -511,6 +733,13 @@ int PoissonRegressionAuxMixSampler::device_loglike_derivs(boomgpu_ctx *ctx, cons
 }
 int PoissonRegressionAuxMixSampler::device_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) {
   return boomgpu_poisson_loglike_derivs_device(ctx, beta, suf_dev);
+}
+int PoissonRegressionAuxMixSampler::device_loglike_derivs_selected(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) {
+  return boomgpu_poisson_loglike_derivs_selected(ctx, beta, loglike, g, h);
+}
+int PoissonRegressionAuxMixSampler::device_loglike_derivs_selected_device(boomgpu_ctx *, const double *, double *) {
+  report_error("the selected-column Poisson derivatives have no hook-driven form; attach a native communicator instead");
+  return 1;
 }
 void PoissonRegressionAuxMixSampler::draw() {
   impute_latent_data();

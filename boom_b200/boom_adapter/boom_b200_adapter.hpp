@@ -5,6 +5,7 @@
 //
 //   BOOM::BinomialLogitAuxmixSampler        -> BOOM::B200::BinomialLogitAuxmixSampler
 //   BOOM::BinomialLogitSpikeSlabSampler     -> BOOM::B200::BinomialLogitSpikeSlabSampler
+//   BOOM::BinomialLogitCompositeSpikeSlabSampler -> BOOM::B200::BinomialLogitCompositeSpikeSlabSampler  (what R's logit.spike builds)
 //   BOOM::PoissonRegressionAuxMixSampler    -> BOOM::B200::PoissonRegressionAuxMixSampler
 //   BOOM::PoissonRegressionSpikeSlabSampler -> BOOM::B200::PoissonRegressionSpikeSlabSampler
 //
@@ -42,6 +43,7 @@
 #include "Models/Glm/WeightedRegressionModel.hpp"
 #include "Models/MvnBase.hpp"
 #include "Models/PosteriorSamplers/PosteriorSampler.hpp"
+#include "Samplers/MoveAccounting.hpp"
 #include "cpputil/math_utils.hpp"
 
 #include "../host/boom_b200.hpp"
@@ -92,6 +94,11 @@ class DeviceImputerBase : public PosteriorSampler {
   virtual int device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) = 0;
   virtual int device_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) = 0;
   double loglike_derivs(const BOOM_B200::Vector &beta, BOOM_B200::Vector *g, BOOM_B200::SpdMatrix *h);   // all ranks' rows
+  // the same over the INCLUDED columns only (k = inc.nvars(); beta, g: k, h: k x k): X_gamma is gathered on the device once
+  // per inclusion pattern, an evaluation is one pass over it (boomgpu_select_columns / boomgpu_*_loglike_derivs_selected)
+  double included_loglike_derivs(const Selector &inc, const Vector &beta_included, Vector *g, Matrix *h);
+  virtual int device_loglike_derivs_selected(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) = 0;
+  virtual int device_loglike_derivs_selected_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) = 0;
   void ensure_device_rows();
   // find_posterior_mode of the spike-and-slab samplers (BinomialLogitSpikeSlabSampler.cpp:147-177,
   // PoissonRegressionSpikeSlabSampler.cpp:69-106): Newton-Raphson on the included coefficients, derivatives from the device
@@ -152,6 +159,8 @@ class BinomialLogitAuxmixSampler : public DeviceImputerBase {
                        double scalars[4]) override;
   int device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) override;
   int device_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) override;
+  int device_loglike_derivs_selected(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) override;
+  int device_loglike_derivs_selected_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) override;
   const Vector &current_beta() const override { return model_->Beta(); }
   void statistics_changed() override { suf_synced_ = false; }
   BinomialLogitModel *model_;
@@ -192,6 +201,52 @@ class BinomialLogitSpikeSlabSampler : public BinomialLogitAuxmixSampler {
   double log_posterior_at_mode_ = negative_infinity();
 };
 
+// BinomialLogitLogPostChunk (BinomialLogitCompositeSpikeSlabSampler.hpp:27-47, .cpp:26-74): log posterior of a chunk of the
+// included coefficients given the rest, with gradient and Hessian with respect to the chunk.  The reference walks all n
+// observations on the host per evaluation; here an evaluation is one device pass over the included columns.
+class BinomialLogitCompositeSpikeSlabSampler;
+class BinomialLogitLogPostChunk {
+ public:
+  BinomialLogitLogPostChunk(BinomialLogitCompositeSpikeSlabSampler *sampler, int chunk_size, int chunk_number);
+  double operator()(const Vector &beta_chunk) const;
+  double operator()(const Vector &beta_chunk, Vector &grad, Matrix &hess, int nd) const;
+
+ private:
+  BinomialLogitCompositeSpikeSlabSampler *sampler_;
+  int start_, chunk_size_;
+};
+
+// BinomialLogitCompositeSpikeSlabSampler (.hpp:49-103, .cpp:76-265): every draw() is, with the given weights, a
+// data-augmentation move (the auxiliary-mixture Gibbs step above), a random-walk Metropolis sweep over chunks of the included
+// coefficients, or a tailored-independence-Metropolis sweep (BOOM's own TIM, Samplers/TIM.cpp, driven by the device-evaluated
+// chunk log posterior).
+class BinomialLogitCompositeSpikeSlabSampler : public BinomialLogitSpikeSlabSampler {
+ public:
+  BinomialLogitCompositeSpikeSlabSampler(BinomialLogitModel *model, const Ptr<MvnBase> &prior, const Ptr<VariableSelectionPrior> &vpri,
+                                         int clt_threshold, double tdf, int max_tim_chunk_size, int max_rwm_chunk_size = 1,
+                                         double rwm_variance_scale_factor = 1.0, RNG &seeding_rng = GlobalRng::rng);
+  void draw() override;
+  void rwm_draw();
+  void tim_draw();
+  void rwm_draw_chunk(int chunk);
+  BinomialLogitLogPostChunk log_posterior(int chunk_number, int max_chunk_size) const;
+  void set_sampler_weights(double da_weight, double rwm_weight, double tim_weight);
+  std::ostream &time_report(std::ostream &out) const;
+
+ private:
+  friend class BinomialLogitLogPostChunk;
+  double chunk_loglike(const Vector &beta_included, Vector *g, Matrix *h) { return included_loglike_derivs(m_->coef().inc(), beta_included, g, h); }
+  BinomialLogitModel *m_;
+  Ptr<MvnBase> pri_;
+  double tdf_;
+  int max_tim_chunk_size_, max_rwm_chunk_size_;
+  double rwm_variance_scale_factor_;
+  MoveAccounting move_accounting_;
+  Vector sampler_weights_;
+  int compute_chunk_size(int max_chunk_size) const;
+  int compute_number_of_chunks(int max_chunk_size) const;
+};
+
 class PoissonRegressionAuxMixSampler : public DeviceImputerBase {
  public:
   PoissonRegressionAuxMixSampler(PoissonRegressionModel *model, const Ptr<MvnBase> &prior, int number_of_threads = 1,
@@ -213,6 +268,8 @@ class PoissonRegressionAuxMixSampler : public DeviceImputerBase {
                        double scalars[4]) override;
   int device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) override;
   int device_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) override;
+  int device_loglike_derivs_selected(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) override;
+  int device_loglike_derivs_selected_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) override;
   const Vector &current_beta() const override { return model_->Beta(); }
   void statistics_changed() override { suf_synced_ = false; }
   PoissonRegressionModel *model_;

@@ -19,11 +19,12 @@ SYMBOLS = (
     "boomgpu_create", "boomgpu_destroy", "boomgpu_last_error", "boomgpu_version", "boomgpu_set_stream",
     "boomgpu_set_row_offset", "boomgpu_set_option", "boomgpu_upload_binomial", "boomgpu_upload_poisson",
     "boomgpu_upload_begin", "boomgpu_upload_rows", "boomgpu_upload_end", "boomgpu_adopt_binomial", "boomgpu_adopt_poisson", "boomgpu_set_logit_mixture", "boomgpu_set_poisson_table",
-    "boomgpu_logit_step", "boomgpu_poisson_step", "boomgpu_suf_len", "boomgpu_logit_step_device",
+    "boomgpu_logit_step", "boomgpu_poisson_step", "boomgpu_probit_step", "boomgpu_probit_step_device", "boomgpu_probit_draw", "boomgpu_suf_len", "boomgpu_logit_step_device",
     "boomgpu_poisson_step_device", "boomgpu_synchronize", "boomgpu_suf_buffer", "boomgpu_download", "boomgpu_accumulate", "boomgpu_logit_draw",
     "boomgpu_poisson_draw", "boomgpu_binomial_loglike", "boomgpu_poisson_loglike", "boomgpu_binomial_loglike_derivs",
     "boomgpu_poisson_loglike_derivs", "boomgpu_binomial_loglike_derivs_device", "boomgpu_poisson_loglike_derivs_device",
-    "boomgpu_poisson_counts_present", "boomgpu_pin_host", "boomgpu_unpin_host", "boomgpu_comm_unique_id", "boomgpu_comm_init", "boomgpu_comm_destroy", "boomgpu_allreduce", "boomgpu_kernel_launches",
+    "boomgpu_poisson_counts_present", "boomgpu_select_columns", "boomgpu_binomial_loglike_derivs_selected",
+    "boomgpu_poisson_loglike_derivs_selected", "boomgpu_binomial_loglike_derivs_selected_device", "boomgpu_pin_host", "boomgpu_unpin_host", "boomgpu_comm_unique_id", "boomgpu_comm_init", "boomgpu_comm_destroy", "boomgpu_allreduce", "boomgpu_kernel_launches",
     "boomgpu_get_timings",
 )
 
@@ -227,6 +228,24 @@ class Context:
                                                    _dp(xty), _dp(sc)))
         return xtx, xty, sc
 
+    def probit_step(self, beta, clt_threshold, seed, iteration, want_xtx=True):
+        """(xtx or None, xtz, sample_size) of the probit sibling; want_xtx=False computes X'z alone."""
+        p = self.p
+        beta = _f64(beta)
+        xtx = np.empty((p, p)) if want_xtx else None
+        xtz = np.empty(p)
+        ss = C.c_int64()
+        self._check(self._lib.boomgpu_probit_step(self._h, _dp(beta), C.c_int(clt_threshold), C.c_uint64(seed), C.c_uint64(iteration),
+                                                  _dp(xtx) if want_xtx else None, _dp(xtz), C.byref(ss)))
+        return xtx, xtz, ss.value
+
+    def probit_draw(self, beta, clt_threshold, seed, iteration):
+        beta = _f64(beta)
+        out = np.empty(self.n)
+        self._check(self._lib.boomgpu_probit_draw(self._h, _dp(beta), C.c_int(clt_threshold), C.c_uint64(seed), C.c_uint64(iteration),
+                                                  _dp(out)))
+        return out
+
     def suf_len(self):
         return int(self._lib.boomgpu_suf_len(C.c_int(self.p)))
 
@@ -303,6 +322,27 @@ class Context:
         ll = C.c_double()
         g, h = np.empty(self.p), np.empty((self.p, self.p))
         self._check(self._lib.boomgpu_poisson_loglike_derivs(self._h, _dp(beta), C.byref(ll), _dp(g), _dp(h)))
+        return ll.value, g, h
+
+    def select_columns(self, cols):
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        self._check(self._lib.boomgpu_select_columns(self._h, cols.ctypes.data_as(c_i32_p), C.c_int(len(cols))))
+        self._k = len(cols)
+
+    def binomial_loglike_derivs_selected(self, beta_selected, log_alpha=0.0):
+        b = _f64(beta_selected)
+        k = len(b)
+        ll = C.c_double()
+        g, h = np.empty(k), np.empty((k, k))
+        self._check(self._lib.boomgpu_binomial_loglike_derivs_selected(self._h, _dp(b), C.c_double(log_alpha), C.byref(ll), _dp(g), _dp(h)))
+        return ll.value, g, h
+
+    def poisson_loglike_derivs_selected(self, beta_selected):
+        b = _f64(beta_selected)
+        k = len(b)
+        ll = C.c_double()
+        g, h = np.empty(k), np.empty((k, k))
+        self._check(self._lib.boomgpu_poisson_loglike_derivs_selected(self._h, _dp(b), C.byref(ll), _dp(g), _dp(h)))
         return ll.value, g, h
 
     def poisson_counts_present(self, length):

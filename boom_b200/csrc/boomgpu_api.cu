@@ -48,6 +48,12 @@ struct boomgpu_ctx {
   int64_t ldxt = 0;
   double *Xt_owned = nullptr;
 
+  // X_gamma: the columns last named by boomgpu_select_columns, as an n x sel_ld matrix owned by the context
+  double *Xsel = nullptr; int64_t sel_cap = 0; int sel_ld = 0;
+  std::vector<int> sel_cols;
+  const double *sel_src = nullptr;   // the X it was gathered from (a new upload / adoption invalidates it)
+  int *sel_cols_dev = nullptr; int sel_cols_cap = 0;
+
   // mixtures
   LogitMixture mix{};        // host copy
   LogitHot hot{};
@@ -64,6 +70,7 @@ struct boomgpu_ctx {
   // workspaces
   double *beta_dev = nullptr; int beta_cap = 0;   // [p + 2 doubles | p ints: indices of beta's non-zeros (gather pass)]
   double *beta_pin = nullptr;
+  bool xty_only = false;                           // this step wants X'z alone (probit: X'WX is constant)
   int syrk_diag = 0;                               // 0 strip form for whole diagonal regions, 1 unit form everywhere
   int syrk_filter = 0;                             // profiling aid: time the off-diagonal / diagonal regions of the SYRK alone
   int gather = 0;                                  // option: 0 auto (sparse beta -> gather pass), 1 never, 2 whenever beta has a zero
@@ -74,6 +81,8 @@ struct boomgpu_ctx {
   double *w_buf = nullptr, *s_buf = nullptr; int64_t ws_cap = 0;
   int *err_dev = nullptr;
   int *err_pin = nullptr;
+  unsigned int *tail_counter = nullptr;   // single-launch small-p step: CTAs that have written their partial
+  int single_launch = 1;                  // option: 0 = separate reduction kernel (two launches)
 
   // TMA descriptor of X for the single-pass kernel (re-encoded when the data or the tile shape change)
   struct XMap {
@@ -372,7 +381,7 @@ bool tma_ok(const boomgpu_ctx *ctx) { return (ctx->ldx % 2 == 0) && aligned16(ct
 template <int MODEL>
 struct TmaLauncher {
   template <int NB>
-  static int go(boomgpu_ctx *ctx, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts) {
+  static int go(boomgpu_ctx *ctx, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts, const TailParams &tail) {
     auto kern = fused_tma_kernel<NB, MODEL>;
     constexpr int NW = tma_warps(NB);
     BetaParam bp;
@@ -386,22 +395,23 @@ struct TmaLauncher {
     if (ensure(ctx, &ctx->partials, &ctx->partials_cap, (int64_t)grid * tma_partial_len(NB))) return BOOMGPU_ERR_CUDA;
     {
       LaunchScope ls(ctx, 0);
-      kern<<<grid, 32 * NW, smem, ctx->stream>>>(ctx->xmap_small.map, d, prm, out, bp, ctx->partials, ctx->err_dev);
+      kern<<<grid, 32 * NW, smem, ctx->stream>>>(ctx->xmap_small.map, d, prm, out, bp, ctx->partials, ctx->err_dev, tail);
     }
     CU(cudaGetLastError());
     *nparts = grid;
     return 0;
   }
-  static int dispatch(boomgpu_ctx *ctx, int nb, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts) {
+  static int dispatch(boomgpu_ctx *ctx, int nb, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts,
+                      const TailParams &tail) {
     switch (nb) {
-      case 1: return go<1>(ctx, d, prm, out, nparts);
-      case 2: return go<2>(ctx, d, prm, out, nparts);
-      case 3: return go<3>(ctx, d, prm, out, nparts);
-      case 4: return go<4>(ctx, d, prm, out, nparts);
-      case 5: return go<5>(ctx, d, prm, out, nparts);
-      case 6: return go<6>(ctx, d, prm, out, nparts);
-      case 7: return go<7>(ctx, d, prm, out, nparts);
-      case 8: return go<8>(ctx, d, prm, out, nparts);
+      case 1: return go<1>(ctx, d, prm, out, nparts, tail);
+      case 2: return go<2>(ctx, d, prm, out, nparts, tail);
+      case 3: return go<3>(ctx, d, prm, out, nparts, tail);
+      case 4: return go<4>(ctx, d, prm, out, nparts, tail);
+      case 5: return go<5>(ctx, d, prm, out, nparts, tail);
+      case 6: return go<6>(ctx, d, prm, out, nparts, tail);
+      case 7: return go<7>(ctx, d, prm, out, nparts, tail);
+      case 8: return go<8>(ctx, d, prm, out, nparts, tail);
     }
     return fail(ctx, BOOMGPU_ERR_ARG, "bad column block count %d", nb);
   }
@@ -498,6 +508,37 @@ int launch_syrk(boomgpu_ctx *ctx, double *suf) {
   return 0;
 }
 
+// X's alone into suf[p*p .. p*p + p) (the matrix part is zeroed: it is not recomputed)
+int launch_xts(boomgpu_ctx *ctx, double *suf) {
+  const int p = ctx->p;
+  const int p2 = (p + 1) / 2;
+  const int pairs = (p2 + kXtsThreads - 1) / kXtsThreads;
+  if (pairs > kXtsMaxPairs) return fail(ctx, BOOMGPU_ERR_ARG, "p = %d is too wide for the X's kernel", p);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->n + 255) / 256, (int64_t)ctx->sms * 4));
+  if (ensure(ctx, &ctx->partials, &ctx->partials_cap, (int64_t)grid * 2 * p2)) return BOOMGPU_ERR_CUDA;
+  CU(cudaMemsetAsync(suf, 0, sizeof(double) * (size_t)p * p, ctx->stream));
+  {
+    LaunchScope ls(ctx, 2);
+    auto go = [&](auto tag) {
+      constexpr int P = decltype(tag)::value;
+      xts_kernel<P><<<grid, kXtsThreads, 0, ctx->stream>>>(ctx->Xt, ctx->ldxt, ctx->n, p, ctx->s_buf, ctx->partials);
+    };
+    if (pairs <= 1) go(std::integral_constant<int, 1>());
+    else if (pairs <= 2) go(std::integral_constant<int, 2>());
+    else if (pairs <= 4) go(std::integral_constant<int, 4>());
+    else if (pairs <= 8) go(std::integral_constant<int, 8>());
+    else if (pairs <= 16) go(std::integral_constant<int, 16>());
+    else go(std::integral_constant<int, 32>());
+  }
+  CU(cudaGetLastError());
+  {
+    LaunchScope ls(ctx, 3);
+    reduce_xts_kernel<<<(p + 255) / 256, 256, 0, ctx->stream>>>(ctx->partials, grid, p, suf + (int64_t)p * p);
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
 // The whole device step for MODEL; leaves the packed statistics at suf (device).
 template <int MODEL>
 int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, const RowOut &out,
@@ -545,15 +586,19 @@ int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, c
   if (path == 1) {
     int nparts = 0;
     const int nb = (p + 7) / 8;
+    bool reduced = false;
     if (tma_small) {
-      // TMA-fed warp-autonomous kernel (fused_tma.cuh)
-      if (int rc = TmaLauncher<MODEL>::dispatch(ctx, nb, d, prm, out, &nparts)) return rc;
+      // TMA-fed warp-autonomous kernel (fused_tma.cuh); single launch: its last CTA also sums the partials
+      TailParams tail{suf, host_out, ctx->single_launch ? ctx->tail_counter : nullptr};
+      if (int rc = TmaLauncher<MODEL>::dispatch(ctx, nb, d, prm, out, &nparts, tail)) return rc;
+      reduced = tail.counter != nullptr;
+      if (reduced) ctx->host_out_written = host_out != nullptr;
     } else {
       // X cannot be described to TMA (odd leading dimension / unaligned adopted pointer): cp.async variant
       cudaError_t e = SmallLauncher<MODEL>::dispatch(ctx, nb, d, prm, out, &nparts);
       if (e != cudaSuccess) return fail(ctx, BOOMGPU_ERR_CUDA, "fused_small_kernel launch failed: %s", cudaGetErrorString(e));
     }
-    {
+    if (!reduced) {
       LaunchScope ls(ctx, 3);
       const int total = p * (p + 1) / 2 + p + 4;   // one warp per output element
       reduce_partials_kernel<<<(total + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, nparts, nb, p, suf, host_out, ctx->err_dev);
@@ -576,7 +621,8 @@ int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, c
       reduce_scalars_kernel<<<1, 32, 0, ctx->stream>>>(ctx->scal_partials, nparts, suf + (int64_t)p * p + p);
     }
     CU(cudaGetLastError());
-    if (int rc = launch_syrk(ctx, suf)) return rc;
+    if (ctx->xty_only && MODEL == kProbit) { if (int rc = launch_xts(ctx, suf)) return rc; }
+    else if (int rc = launch_syrk(ctx, suf)) return rc;
   }
   return 0;
 }
@@ -744,6 +790,20 @@ int loglike_derivs_device_impl(boomgpu_ctx *ctx, int model, const double *beta, 
   return run_step<MODEL>(ctx, beta, prm, out, nullptr, nullptr, suf_dev);
 }
 
+// Runs f with the context looking at X_gamma (n x k) instead of X, then restores it.
+template <class F>
+int with_selected_columns(boomgpu_ctx *ctx, F f) {
+  if (!ctx->Xsel || ctx->sel_src != ctx->X || ctx->sel_cols.empty())
+    return fail(ctx, BOOMGPU_ERR_STATE, "no columns selected for the current data (boomgpu_select_columns)");
+  const double *X = ctx->X, *Xt = ctx->Xt; const int64_t ldx = ctx->ldx, ldxt = ctx->ldxt; const int p = ctx->p;
+  double *Xt_owned = ctx->Xt_owned;
+  ctx->X = ctx->Xsel; ctx->ldx = ctx->sel_ld; ctx->p = (int)ctx->sel_cols.size();
+  ctx->Xt = nullptr; ctx->ldxt = 0; ctx->Xt_owned = nullptr;    // the selected matrix is padded: TMA describes it in place
+  const int rc = f();
+  ctx->X = X; ctx->ldx = ldx; ctx->p = p; ctx->Xt = Xt; ctx->ldxt = ldxt; ctx->Xt_owned = Xt_owned;
+  return rc;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -776,6 +836,8 @@ int boomgpu_create(boomgpu_ctx **out, int device) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc((void **)&ctx->err_dev, sizeof(int)) != cudaSuccess ||
       cudaMallocHost((void **)&ctx->err_pin, sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void **)&ctx->tail_counter, sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(ctx->tail_counter, 0, sizeof(unsigned int)) != cudaSuccess ||
       cudaMemset(ctx->err_dev, 0, sizeof(int)) != cudaSuccess) {
     delete ctx;
     return fail(nullptr, BOOMGPU_ERR_CUDA, "context set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -799,7 +861,8 @@ void boomgpu_destroy(boomgpu_ctx *ctx) {
   cudaFree(ctx->suf_dev); cudaFreeHost(ctx->suf_pin);
   cudaFree(ctx->partials); cudaFree(ctx->scal_partials);
   cudaFree(ctx->w_buf); cudaFree(ctx->s_buf);
-  cudaFree(ctx->err_dev); cudaFreeHost(ctx->err_pin);
+  cudaFree(ctx->Xsel); cudaFree(ctx->sel_cols_dev);
+  cudaFree(ctx->err_dev); cudaFreeHost(ctx->err_pin); cudaFree(ctx->tail_counter);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -829,6 +892,7 @@ int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value) {
     return 0;
   }
   if (!strcmp(name, "timing")) { ctx->timing = value != 0; return 0; }
+  if (!strcmp(name, "single_launch")) { ctx->single_launch = value != 0; return 0; }
   if (!strcmp(name, "syrk_diag")) { ctx->syrk_diag = value != 0; return 0; }
   if (!strcmp(name, "syrk_filter")) { ctx->syrk_filter = (int)value; return 0; }
   if (!strcmp(name, "gather")) {
@@ -1241,6 +1305,73 @@ int boomgpu_poisson_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, ui
   return 0;
 }
 
+// ---- probit sibling (BinomialProbitSpikeSlabSampler) ---------------------------------------------------
+static int check_probit(boomgpu_ctx *ctx, int clt_threshold) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (ctx->model != kLogit || !ctx->X) return fail(ctx, BOOMGPU_ERR_STATE, "no binomial data uploaded to this context");
+  return check_clt(ctx, clt_threshold);
+}
+
+int boomgpu_probit_step_device(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
+                               double *suf_dev, int xty_only) {
+  if (int rc = check_probit(ctx, clt_threshold)) return rc;
+  if (!beta || !suf_dev) return fail(ctx, BOOMGPU_ERR_ARG, "null beta / suf_dev");
+  DeviceGuard g(ctx->device);
+  RowOut out{nullptr, nullptr, nullptr, nullptr};
+  ctx->xty_only = xty_only != 0;
+  const int rc = run_step<kProbit>(ctx, beta, make_prm(ctx, clt_threshold, seed, iteration), out, nullptr, nullptr, suf_dev);
+  ctx->xty_only = false;
+  return rc;
+}
+
+int boomgpu_probit_step(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration, double *xtx,
+                        double *xtz, int64_t *sample_size) {
+  if (int rc = check_probit(ctx, clt_threshold)) return rc;
+  if (!beta || !xtz) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
+  DeviceGuard g(ctx->device);
+  if (int rc = ensure_suf(ctx)) return rc;
+  const bool sharded = ctx->comm && ctx->comm_ranks > 1;
+  RowOut out{nullptr, nullptr, nullptr, nullptr};
+  ctx->xty_only = xtx == nullptr;
+  int rc = run_step<kProbit>(ctx, beta, make_prm(ctx, clt_threshold, seed, iteration), out, nullptr, nullptr, ctx->suf_dev,
+                             sharded ? nullptr : ctx->suf_pin);
+  ctx->xty_only = false;
+  if (rc) return rc;
+  const int p = ctx->p;
+  const size_t mat = (size_t)p * p;
+  if (xtx) {
+    if ((rc = allreduce_on_stream(ctx, ctx->suf_dev, boomgpu_suf_len(p)))) return rc;
+    bool in_place = false;
+    if ((rc = fetch_suf(ctx, xtx, &in_place))) return rc;
+    if (!in_place) memcpy(xtx, ctx->suf_pin, sizeof(double) * mat);
+  } else {   // X'z and the scalars only: p + 4 doubles travel
+    if ((rc = allreduce_on_stream(ctx, ctx->suf_dev + mat, p + 4))) return rc;
+    if (!ctx->host_out_written)
+      CU(cudaMemcpyAsync(ctx->suf_pin + mat, ctx->suf_dev + mat, sizeof(double) * (size_t)(p + 4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->host_out_written) { if ((rc = fetch_suf(ctx))) return rc; }
+    else if ((rc = finish_and_check(ctx))) return rc;
+  }
+  memcpy(xtz, ctx->suf_pin + mat, sizeof(double) * p);
+  if (sample_size) *sample_size = (int64_t)llround(ctx->suf_pin[mat + p]);
+  return 0;
+}
+
+int boomgpu_probit_draw(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration, double *sum_z_out) {
+  if (int rc = check_probit(ctx, clt_threshold)) return rc;
+  if (!beta || !sum_z_out) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
+  DeviceGuard g(ctx->device);
+  if (int rc = ensure_suf(ctx)) return rc;
+  double *ds = nullptr;
+  CU(cudaMalloc((void **)&ds, sizeof(double) * (size_t)std::max<int64_t>(ctx->n, 1)));
+  RowOut out{nullptr, ds, nullptr, nullptr};
+  int rc = run_step<kProbit>(ctx, beta, make_prm(ctx, clt_threshold, seed, iteration), out, nullptr, nullptr, ctx->suf_dev);
+  if (!rc && cudaMemcpyAsync(sum_z_out, ds, sizeof(double) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+    rc = fail(ctx, BOOMGPU_ERR_CUDA, "copy of draws failed");
+  if (!rc) rc = finish_and_check(ctx); else cudaStreamSynchronize(ctx->stream);
+  cudaFree(ds);
+  return rc;
+}
+
 int boomgpu_accumulate(boomgpu_ctx *ctx, const double *weight, const double *weighted_value, double *xtx, double *xty) {
   if (!ctx) return BOOMGPU_ERR_ARG;
   if (!ctx->X) return fail(ctx, BOOMGPU_ERR_STATE, "no data uploaded to this context");
@@ -1360,6 +1491,53 @@ int boomgpu_binomial_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta,
 }
 int boomgpu_poisson_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) {
   return loglike_derivs_device_impl<kPoissonLL>(ctx, kPoisson, beta, 0.0, suf_dev);
+}
+
+int boomgpu_select_columns(boomgpu_ctx *ctx, const int32_t *cols, int k) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (!ctx->X || ctx->model < 0) return fail(ctx, BOOMGPU_ERR_STATE, "no data uploaded to this context");
+  if (k < 0 || k > ctx->p || (k > 0 && !cols)) return fail(ctx, BOOMGPU_ERR_ARG, "bad column selection (k = %d of p = %d)", k, ctx->p);
+  for (int j = 0; j < k; ++j)
+    if (cols[j] < 0 || cols[j] >= ctx->p) return fail(ctx, BOOMGPU_ERR_ARG, "selected column %d out of range", cols[j]);
+  if (ctx->Xsel && ctx->sel_src == ctx->X && (int)ctx->sel_cols.size() == k && (k == 0 || !memcmp(cols, ctx->sel_cols.data(), sizeof(int) * k)))
+    return 0;   // already there
+  ctx->sel_cols.assign(cols, cols + k);
+  ctx->sel_src = ctx->X;
+  if (k == 0) return 0;
+  DeviceGuard g(ctx->device);
+  const int ld = (k + 7) / 8 * 8;
+  if (int rc = ensure(ctx, &ctx->Xsel, &ctx->sel_cap, std::max<int64_t>(ctx->n, 1) * ld)) { ctx->sel_cols.clear(); return rc; }
+  if (ctx->sel_cols_cap < k) {
+    if (ctx->sel_cols_dev) { CU(cudaFree(ctx->sel_cols_dev)); ctx->sel_cols_dev = nullptr; ctx->sel_cols_cap = 0; }
+    CU(cudaMalloc((void **)&ctx->sel_cols_dev, sizeof(int) * (size_t)ctx->p));
+    ctx->sel_cols_cap = ctx->p;
+  }
+  ctx->sel_ld = ld;
+  CU(cudaMemcpyAsync(ctx->sel_cols_dev, cols, sizeof(int) * k, cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->n > 0) {
+    LaunchScope ls(ctx, 4);
+    const int64_t total = ctx->n * ld;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sms * 16));
+    select_columns_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->X, ctx->ldx, ctx->n, ctx->sel_cols_dev, k, ctx->Xsel, ld);
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));   // cols is the caller's buffer
+  return 0;
+}
+
+int boomgpu_binomial_loglike_derivs_selected(boomgpu_ctx *ctx, const double *beta_selected, double log_alpha, double *loglike,
+                                             double *gradient, double *hessian) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  return with_selected_columns(ctx, [&]() { return loglike_derivs_impl<kLogitLL>(ctx, kLogit, beta_selected, log_alpha, loglike, gradient, hessian); });
+}
+int boomgpu_poisson_loglike_derivs_selected(boomgpu_ctx *ctx, const double *beta_selected, double *loglike, double *gradient,
+                                            double *hessian) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  return with_selected_columns(ctx, [&]() { return loglike_derivs_impl<kPoissonLL>(ctx, kPoisson, beta_selected, 0.0, loglike, gradient, hessian); });
+}
+int boomgpu_binomial_loglike_derivs_selected_device(boomgpu_ctx *ctx, const double *beta_selected, double log_alpha, double *suf_dev) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  return with_selected_columns(ctx, [&]() { return loglike_derivs_device_impl<kLogitLL>(ctx, kLogit, beta_selected, log_alpha, suf_dev); });
 }
 
 int boomgpu_binomial_loglike(boomgpu_ctx *ctx, const double *beta, double *loglike) { return loglike_impl(ctx, kLogit, beta, loglike); }

@@ -542,6 +542,49 @@ __device__ __forceinline__ bool logit_impute(const LogitHot &h, const LogitMixtu
   return logit_impute_general(md, clt_threshold, ntrials, y, eta, key.seed, key.iteration, row, &sum, &info);
 }
 
+// ---- probit sibling ---------------------------------------------------------------------
+// N(eta, 1) truncated to z > 0 (positive) or z < 0 by inversion from one uniform, on the tail that does not cancel:
+//   z > 0:  z = eta - Phi^-1(u Phi(eta));   z < 0:  z = eta + Phi^-1(u Phi(-eta))
+// (BinomialProbitDataImputer.cpp:55-66 calls rtrun_norm_mt, distributions/trun_norm.cpp:36-110 -- rejection samplers: the
+// same law from another stream).  Beyond 30 standard deviations the exponential limit of the normal tail is used.
+__device__ __forceinline__ double rtrun_norm_unit(double eta, bool positive, double unif) {
+  const double m = positive ? eta : -eta;
+  double t = (m < -30.0) ? -log(unif) / (-m) : m - normcdfinv(unif * normcdf(m));
+  t = fmax(t, 0.0);
+  return positive ? t : -t;
+}
+
+// BinomialProbitDataImputer::impute (BinomialProbitDataImputer.cpp:31-68): the sum of the n_i latent normals of an
+// observation -- y_i of them positive, n_i - y_i negative -- drawn one by one, or in one normal draw from the truncated
+// moments when a side has more than clt_threshold members.  Philox slots as in the oracle (bo_probit_impute).
+__device__ __noinline__ bool probit_impute(int clt_threshold, double ntrials, double nsuccess, double eta, uint64_t seed,
+                                           uint64_t iteration, uint64_t row, double *sum_z) {
+  *sum_z = 0;
+  const long long n = llround(ntrials), y = llround(nsuccess);
+  if (y < 0 || n < 0 || y > n || !isfinite(eta)) return false;
+  RngKey key;
+  key.seed = seed; key.iteration = iteration;
+  philox_round_keys(key);
+  double ans = 0, mean, var, u0, u1;
+  uint32_t slot = 0;
+  if (y > clt_threshold) {
+    trun_norm_moments(eta, 1.0, true, mean, var);
+    uniform_pair(key, row, slot++, u0, u1);
+    ans += (double)y * mean + sqrt((double)y * var) * (sqrt(-2.0 * log(u0)) * cos(kTwoPi * u1));
+  } else {
+    for (long long i = 0; i < y; ++i) { uniform_pair(key, row, slot++, u0, u1); ans += rtrun_norm_unit(eta, true, u0); }
+  }
+  if (n - y > clt_threshold) {
+    trun_norm_moments(eta, 1.0, false, mean, var);
+    uniform_pair(key, row, slot++, u0, u1);
+    ans += (double)(n - y) * mean + sqrt((double)(n - y) * var) * (sqrt(-2.0 * log(u0)) * cos(kTwoPi * u1));
+  } else {
+    for (long long i = 0; i < n - y; ++i) { uniform_pair(key, row, slot++, u0, u1); ans += rtrun_norm_unit(eta, false, u0); }
+  }
+  *sum_z = ans;
+  return true;
+}
+
 // ---- Poisson --------------------------------------------------------------------------
 __device__ __forceinline__ int poisson_table_find(const PoissonTable &t, int64_t nu) {
   if (nu < (int64_t)t.dense_n) return nu >= 0 ? __ldg(t.dense + nu) : -1;

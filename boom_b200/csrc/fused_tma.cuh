@@ -30,6 +30,10 @@ namespace boomgpu {
 // the shared FP64 / DMMA pipe (48 % busy) and the issue slots (45 %) bound it, not latency, so RPL stays 1 (finer slices
 // balance short data sets better).
 // (tuning knobs for the narrow tiles: -DBOOMGPU_TMA_NW_SMALL=.. -DBOOMGPU_TMA_S_SMALL=.. -DBOOMGPU_TMA_RPL_SMALL=..)
+// Round 2, after the draw diet (fewer instructions, same dependent chains): the kernel is bound by the LATENCY of a lane's
+// serial chain (Philox rounds -> exp -> reciprocal -> log -> selection), not by issue slots or the FP64 pipe, so two
+// observations per lane (two independent chains the scheduler interleaves) now pay: p = 16 / 25 M rows 0.854 -> 0.749 ms
+// with (12 warps, RPL 2); (16 warps, RPL 1) spills at 128 registers and is slower (0.902).
 #ifndef BOOMGPU_TMA_NW_SMALL
 #define BOOMGPU_TMA_NW_SMALL 12
 #endif
@@ -37,9 +41,27 @@ namespace boomgpu {
 #define BOOMGPU_TMA_S_SMALL 2
 #endif
 #ifndef BOOMGPU_TMA_RPL_SMALL
-#define BOOMGPU_TMA_RPL_SMALL 1
+#define BOOMGPU_TMA_RPL_SMALL 2
 #endif
-__host__ __device__ constexpr int tma_rpl(int nb) { return nb <= 2 ? BOOMGPU_TMA_RPL_SMALL : 1; }
+#ifndef BOOMGPU_TMA_NW_3
+#define BOOMGPU_TMA_NW_3 12
+#endif
+#ifndef BOOMGPU_TMA_S_3
+#define BOOMGPU_TMA_S_3 2
+#endif
+#ifndef BOOMGPU_TMA_RPL_3
+#define BOOMGPU_TMA_RPL_3 1
+#endif
+#ifndef BOOMGPU_TMA_NW_4
+#define BOOMGPU_TMA_NW_4 10
+#endif
+#ifndef BOOMGPU_TMA_S_4
+#define BOOMGPU_TMA_S_4 1
+#endif
+#ifndef BOOMGPU_TMA_RPL_4
+#define BOOMGPU_TMA_RPL_4 2     // p = 32 / 8 M rows: 0.747 -> 0.688 ms (NB = 3 prefers RPL 1: 0.594 vs 0.611)
+#endif
+__host__ __device__ constexpr int tma_rpl(int nb) { return nb <= 2 ? BOOMGPU_TMA_RPL_SMALL : (nb == 3 ? BOOMGPU_TMA_RPL_3 : (nb == 4 ? BOOMGPU_TMA_RPL_4 : 1)); }
 // wide tiles (40 < p <= 64): 8 warps with a SINGLE slice each beat 6 warps with two (p = 64: 1.59 vs 2.15 ms per 8 M rows):
 // the per-slice DMMA work is long enough that the other warp of the sub-partition covers the reload bubble.
 #ifndef BOOMGPU_TMA_NW_WIDE
@@ -48,8 +70,8 @@ __host__ __device__ constexpr int tma_rpl(int nb) { return nb <= 2 ? BOOMGPU_TMA
 #ifndef BOOMGPU_TMA_S_WIDE
 #define BOOMGPU_TMA_S_WIDE 1
 #endif
-__host__ __device__ constexpr int tma_warps(int nb) { return nb <= 2 ? BOOMGPU_TMA_NW_SMALL : (nb == 3 ? 12 : (nb == 4 ? 10 : BOOMGPU_TMA_NW_WIDE)); }
-__host__ __device__ constexpr int tma_stages(int nb) { return nb <= 2 ? BOOMGPU_TMA_S_SMALL : (nb <= 4 ? 2 : BOOMGPU_TMA_S_WIDE); }
+__host__ __device__ constexpr int tma_warps(int nb) { return nb <= 2 ? BOOMGPU_TMA_NW_SMALL : (nb == 3 ? BOOMGPU_TMA_NW_3 : (nb == 4 ? BOOMGPU_TMA_NW_4 : BOOMGPU_TMA_NW_WIDE)); }
+__host__ __device__ constexpr int tma_stages(int nb) { return nb <= 2 ? BOOMGPU_TMA_S_SMALL : (nb == 3 ? BOOMGPU_TMA_S_3 : (nb == 4 ? BOOMGPU_TMA_S_4 : BOOMGPU_TMA_S_WIDE)); }
 // Row pitch of a slice in shared memory: 8 NB + 2 doubles = 16 NB + 4 words.  (a) lane r reads row r with 16-byte loads:
 // a quarter warp's rows start 4 r (NB even) or 20 r (NB odd) words apart mod 32 -- eight distinct 4-bank groups, conflict
 // free with NO per-lane rotation of the column order, so beta comes straight from the constant bank with compile-time
@@ -68,10 +90,58 @@ __host__ __device__ constexpr int64_t tma_partial_len(int nb) { return 64 * nb *
 // beta travels as a kernel parameter (p <= 64: 512 bytes of the constant bank): no host->device copy per step
 struct BetaParam { double b[64]; };
 
+// Sum of the per-CTA partials in CTA order (deterministic), by warp `warp` of `nwarps`: one warp per output element, lanes
+// stride over the CTAs, then a fixed shuffle tree.  Partials are read around L1 (__ldcg): in the single-launch form they
+// were written by other CTAs of the same grid.
+__device__ __forceinline__ void reduce_partials_body(const double *__restrict__ partials, int nparts, int nb, int p,
+                                                     double *__restrict__ suf, double *__restrict__ host_out, const int *err, int warp,
+                                                     int nwarps, int lane, bool writes_flag) {
+  const int P8 = 8 * nb;
+  const int64_t plen = 64 * (int64_t)nb * nb + 8 * nb + 8;
+  const int ntri = p * (p + 1) / 2;
+  const int total = ntri + p + 4;
+  for (int e = warp; e < total; e += nwarps) {
+    int a = 0, b = 0;
+    int64_t src;
+    if (e < ntri) {
+      // e -> (a, b), a <= b, rows of the upper triangle laid end to end
+      int rem = e;
+      while (rem >= p - a) { rem -= p - a; ++a; }
+      b = a + rem;
+      src = (int64_t)a * P8 + b;
+    } else if (e < ntri + p) {
+      src = (int64_t)P8 * P8 + (e - ntri);
+    } else {
+      src = (int64_t)P8 * P8 + P8 + (e - ntri - p);
+    }
+    double s = 0;
+    for (int cta = lane; cta < nparts; cta += 32) s += __ldcg(partials + cta * plen + src);
+    s = warp_sum(s);
+    if (lane == 0) {
+      if (e < ntri) {
+        suf[a + (int64_t)b * p] = s;
+        suf[b + (int64_t)a * p] = s;
+        if (host_out) { host_out[a + (int64_t)b * p] = s; host_out[b + (int64_t)a * p] = s; }
+      } else {
+        suf[(int64_t)p * p + (e - ntri)] = s;
+        if (host_out) host_out[(int64_t)p * p + (e - ntri)] = s;
+      }
+    }
+  }
+  if (host_out && writes_flag) host_out[(int64_t)p * p + p + 4] = (double)__ldcg(err);
+}
+
+// what the last CTA of the single-launch form needs to finish the step
+struct TailParams {
+  double *suf;             // device: [p*p | p | 4]
+  double *host_out;        // host-mapped copy (or null)
+  unsigned int *counter;   // CTAs that have written their partial; reset by the last one
+};
+
 template <int NB, int MODEL>
 __global__ void __launch_bounds__(32 * tma_warps(NB), 1)
 fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams prm, RowOut out, const __grid_constant__ BetaParam beta,
-                 double *__restrict__ partials, int *err) {
+                 double *__restrict__ partials, int *err, TailParams tail) {
   constexpr int NW = tma_warps(NB);
   constexpr int S = tma_stages(NB);
   constexpr int RPL = tma_rpl(NB);
@@ -242,37 +312,66 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
 
   // ---- CTA reduction in warp order (deterministic), one partial per CTA
   __syncthreads();  // every issued copy has been consumed: the ring is free
-  double *tile = smem;                  // P8 * P8
-  double *xty_s = smem + P8 * P8;       // P8
-  for (int e = tid; e < P8 * P8 + P8; e += 32 * NW) smem[e] = 0.0;
+  constexpr int TILE = P8 * P8 + P8;    // [P8 x P8 | X'Wz P8]
   // X'Wz: lanes with the same (lane >> 2) hold the rows = lane & 3 (mod 4) of the same columns
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     xty_acc[b] += __shfl_xor_sync(0xffffffffu, xty_acc[b], 1);
     xty_acc[b] += __shfl_xor_sync(0xffffffffu, xty_acc[b], 2);
   }
-  __syncthreads();
-  for (int w = 0; w < NW; ++w) {
-    if (wid == w) {
-      int a = 0;
+  double *my = partials + (int64_t)blockIdx.x * tma_partial_len(NB);
+  constexpr bool kWarpTiles = (size_t)NW * TILE <= (size_t)NW * S * SLICE;   // every warp's fragments fit the (free) ring
+  if (kWarpTiles) {
+    // each warp lays its fragments into its own tile, then every thread sums one element over the warps in warp order:
+    // two block barriers instead of one per warp (the epilogue is most of the kernel when n is small: C1)
+    for (int e = tid; e < NW * TILE; e += 32 * NW) smem[e] = 0.0;
+    __syncthreads();
+    double *tile = smem + (size_t)wid * TILE;
+    int a = 0;
 #pragma unroll
-      for (int bi = 0; bi < NB; ++bi)
+    for (int bi = 0; bi < NB; ++bi)
 #pragma unroll
-        for (int bj = bi; bj < NB; ++bj) {
-          double *t = tile + (8 * bi + (lane >> 2)) * P8 + 8 * bj + 2 * (lane & 3);
-          t[0] += c[a][0];
-          t[1] += c[a][1];
-          ++a;
-        }
-      if ((lane & 3) == 0) {
-#pragma unroll
-        for (int b = 0; b < NB; ++b) xty_s[8 * b + (lane >> 2)] += xty_acc[b];
+      for (int bj = bi; bj < NB; ++bj) {
+        *reinterpret_cast<double2 *>(tile + (8 * bi + (lane >> 2)) * P8 + 8 * bj + 2 * (lane & 3)) = make_double2(c[a][0], c[a][1]);
+        ++a;
       }
+    if ((lane & 3) == 0) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) tile[P8 * P8 + 8 * b + (lane >> 2)] = xty_acc[b];
     }
     __syncthreads();
+    for (int e = tid; e < TILE; e += 32 * NW) {
+      double s = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s += smem[(size_t)w * TILE + e];
+      my[e] = s;
+    }
+  } else {
+    double *tile = smem;                  // P8 * P8
+    double *xty_s = smem + P8 * P8;       // P8
+    for (int e = tid; e < TILE; e += 32 * NW) smem[e] = 0.0;
+    __syncthreads();
+    for (int w = 0; w < NW; ++w) {
+      if (wid == w) {
+        int a = 0;
+#pragma unroll
+        for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+          for (int bj = bi; bj < NB; ++bj) {
+            double *t = tile + (8 * bi + (lane >> 2)) * P8 + 8 * bj + 2 * (lane & 3);
+            t[0] += c[a][0];
+            t[1] += c[a][1];
+            ++a;
+          }
+        if ((lane & 3) == 0) {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) xty_s[8 * b + (lane >> 2)] += xty_acc[b];
+        }
+      }
+      __syncthreads();
+    }
+    for (int e = tid; e < TILE; e += 32 * NW) my[e] = smem[e];
   }
-  double *my = partials + (int64_t)blockIdx.x * tma_partial_len(NB);
-  for (int e = tid; e < P8 * P8 + P8; e += 32 * NW) my[e] = smem[e];
   double v0 = warp_sum(sc_count), v1 = warp_sum(sc_ywy), v2 = warp_sum(sc_sumw), v3 = warp_sum(sc_sumlogw);
   if (lane == 0) { red_s[wid * 4 + 0] = v0; red_s[wid * 4 + 1] = v1; red_s[wid * 4 + 2] = v2; red_s[wid * 4 + 3] = v3; }
   __syncthreads();
@@ -281,6 +380,58 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
     for (int w = 0; w < NW; ++w) s += red_s[w * 4 + tid];
     my[P8 * P8 + P8 + tid] = s;
   }
+
+  // ---- single launch: the CTA that writes the LAST partial sums them all (in CTA order: deterministic) into the packed
+  // statistics -- no second kernel, no launch gap (a third of the C1 iteration)
+  if (tail.counter == nullptr) return;
+  __shared__ unsigned int ticket_s;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) ticket_s = atomicAdd(tail.counter, 1u);
+  __syncthreads();
+  if (ticket_s != gridDim.x - 1) return;
+  __threadfence();
+  // one THREAD per output element, the partials summed in CTA order with 16 independent loads in flight (a warp per
+  // element serialises ~20 elements x 5 dependent L2 round trips on every warp: 28 us at C1; this form is ~3 us)
+  {
+    const int p = d.p, nparts = (int)gridDim.x;
+    const int ntri = p * (p + 1) / 2, total = ntri + p + 4;
+    constexpr int64_t plen = tma_partial_len(NB);
+    for (int e = tid; e < total; e += 32 * NW) {
+      int a = 0, b = 0;
+      int64_t src;
+      if (e < ntri) {
+        int rem = e;
+        while (rem >= p - a) { rem -= p - a; ++a; }
+        b = a + rem;
+        src = (int64_t)a * P8 + b;
+      } else if (e < ntri + p) {
+        src = (int64_t)P8 * P8 + (e - ntri);
+      } else {
+        src = (int64_t)P8 * P8 + P8 + (e - ntri - p);
+      }
+      double s = 0;
+      int cta = 0;
+      for (; cta + 16 <= nparts; cta += 16) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldcg(partials + (int64_t)(cta + u) * plen + src);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s += v[u];
+      }
+      for (; cta < nparts; ++cta) s += __ldcg(partials + (int64_t)cta * plen + src);
+      if (e < ntri) {
+        tail.suf[a + (int64_t)b * p] = s;
+        tail.suf[b + (int64_t)a * p] = s;
+        if (tail.host_out) { tail.host_out[a + (int64_t)b * p] = s; tail.host_out[b + (int64_t)a * p] = s; }
+      } else {
+        tail.suf[(int64_t)p * p + (e - ntri)] = s;
+        if (tail.host_out) tail.host_out[(int64_t)p * p + (e - ntri)] = s;
+      }
+    }
+    if (tail.host_out && tid == 0) tail.host_out[(int64_t)p * p + p + 4] = (double)__ldcg(err);
+  }
+  if (tid == 0) *tail.counter = 0u;
 }
 
 // One warp per output element: lanes stride over the per-CTA partials, then a fixed shuffle tree.
@@ -290,42 +441,8 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double *__restrict__ partials, int nparts, int nb, int p,
                                                              double *__restrict__ suf, double *__restrict__ host_out,
                                                              const int *__restrict__ err) {
-  const int P8 = 8 * nb;
-  const int64_t plen = 64 * (int64_t)nb * nb + 8 * nb + 8;
-  const int ntri = p * (p + 1) / 2;
-  const int total = ntri + p + 4;
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int e = warp; e < total; e += nwarps) {
-    int a = 0, b = 0;
-    int64_t src;
-    if (e < ntri) {
-      // e -> (a, b), a <= b, rows of the upper triangle laid end to end
-      int rem = e;
-      while (rem >= p - a) { rem -= p - a; ++a; }
-      b = a + rem;
-      src = (int64_t)a * P8 + b;
-    } else if (e < ntri + p) {
-      src = (int64_t)P8 * P8 + (e - ntri);
-    } else {
-      src = (int64_t)P8 * P8 + P8 + (e - ntri - p);
-    }
-    double s = 0;
-    for (int cta = lane; cta < nparts; cta += 32) s += partials[cta * plen + src];
-    s = warp_sum(s);
-    if (lane == 0) {
-      if (e < ntri) {
-        suf[a + (int64_t)b * p] = s;
-        suf[b + (int64_t)a * p] = s;
-        if (host_out) { host_out[a + (int64_t)b * p] = s; host_out[b + (int64_t)a * p] = s; }
-      } else {
-        suf[(int64_t)p * p + (e - ntri)] = s;
-        if (host_out) host_out[(int64_t)p * p + (e - ntri)] = s;
-      }
-    }
-  }
-  if (host_out && blockIdx.x == 0 && threadIdx.x == 0) host_out[(int64_t)p * p + p + 4] = (double)*err;
+  reduce_partials_body(partials, nparts, nb, p, suf, host_out, err, (blockIdx.x * blockDim.x + threadIdx.x) >> 5,
+                       (gridDim.x * blockDim.x) >> 5, threadIdx.x & 31, blockIdx.x == 0 && threadIdx.x == 0);
 }
 
 }  // namespace boomgpu

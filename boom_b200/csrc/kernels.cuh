@@ -26,7 +26,8 @@ namespace boomgpu {
 
 // kLogitLL / kPoissonLL: no draw; the row's "latent" is its log-likelihood curvature, so the same kernels return
 // log likelihood, gradient and (minus) Hessian in one pass (BinomialLogitModel.cpp:140-180, PoissonRegressionModel.cpp:56-95)
-enum Model : int { kLogit = 0, kPoisson = 1, kSupplied = 2, kLogitLL = 3, kPoissonLL = 4 };
+// kProbit: the probit sibling (BinomialProbitSpikeSlabSampler): weight n_i, weighted value = sum of the latent normals
+enum Model : int { kLogit = 0, kPoisson = 1, kSupplied = 2, kLogitLL = 3, kPoissonLL = 4, kProbit = 5 };
 
 struct RowData {
   const double *X;
@@ -91,7 +92,7 @@ template <int MODEL>
 __device__ __forceinline__ RowObs load_obs(const RowData &d, int64_t i) {
   RowObs o;
   o.y = 0; o.aux = 0; o.yi = 0;
-  if (MODEL == kLogit || MODEL == kLogitLL) { o.y = __ldg(d.y + i); o.aux = __ldg(d.ntrials + i); }
+  if (MODEL == kLogit || MODEL == kLogitLL || MODEL == kProbit) { o.y = __ldg(d.y + i); o.aux = __ldg(d.ntrials + i); }
   else if (MODEL == kPoisson || MODEL == kPoissonLL) { o.yi = __ldg(d.yi + i); o.aux = __ldg(d.exposure + i); }
   else { o.y = __ldg(d.w_in + i); o.aux = __ldg(d.s_in + i); }
   return o;
@@ -126,6 +127,12 @@ __device__ __forceinline__ RowLatent impute_row(const RowData &d, const DrawPara
       }
       if (out.k2) { out.k2[2 * i] = o.k_int; out.k2[2 * i + 1] = o.k_ext; }
     }
+  } else if (MODEL == kProbit) {
+    double sz;
+    const bool ok = probit_impute(prm.clt_threshold, obs.aux, obs.y, eta, prm.key.seed, prm.key.iteration, d.row_offset + (uint64_t)i, &sz);
+    if (!ok) { atomicOr(err, 2); sz = 0; }
+    r.w = ok ? obs.aux : 0.0;    // refresh_xtx: xtx += n_i x x' (BinomialProbitSpikeSlabSampler.cpp:72-78)
+    r.s = sz;
   } else if (MODEL == kLogitLL) {
     // w = n p q (so that -X'WX is the Hessian), s = y - n p (X's is the gradient), the log density rides in the yWy slot
     const double e = eta - prm.log_alpha;
@@ -946,12 +953,68 @@ __global__ void __launch_bounds__(256) loglike_kernel(RowData d, const double *_
   }
 }
 
+// X's alone (the probit sibling: X'WX does not change from one iteration to the next, only X'z does): thread t owns column
+// pairs t, t + 256, ... (coalesced 16-byte loads along a row), a CTA walks its block of rows; per-CTA partials, fixed-order sum.
+constexpr int kXtsThreads = 256;
+constexpr int kXtsMaxPairs = 32;   // column pairs per thread: p <= 2 * 256 * 32 = 16384
+template <int PAIRS>
+__global__ void __launch_bounds__(kXtsThreads) xts_kernel(const double *__restrict__ X, int64_t ldx, int64_t n, int p,
+                                                           const double *__restrict__ s, double *__restrict__ partials) {
+  const int tid = threadIdx.x;
+  const int64_t rows_per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per, r1 = min(n, r0 + rows_per);
+  double2 acc[PAIRS];
+#pragma unroll
+  for (int q = 0; q < PAIRS; ++q) acc[q] = make_double2(0.0, 0.0);
+  const int p2 = (p + 1) >> 1;   // ldx is even and the pad column (if p is odd) holds zeros or is never stored
+  for (int64_t i = r0; i < r1; ++i) {
+    const double sv = __ldg(s + i);
+    const double2 *xr = reinterpret_cast<const double2 *>(X + i * ldx);
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q) {
+      const int c = tid + q * kXtsThreads;
+      if (c < p2) {
+        const double2 x = __ldg(xr + c);
+        acc[q].x = fma(x.x, sv, acc[q].x);
+        acc[q].y = fma(x.y, sv, acc[q].y);
+      }
+    }
+  }
+  double *my = partials + (int64_t)blockIdx.x * (2 * (int64_t)p2);
+#pragma unroll
+  for (int q = 0; q < PAIRS; ++q) {
+    const int c = tid + q * kXtsThreads;
+    if (c < p2) { my[2 * c] = acc[q].x; my[2 * c + 1] = acc[q].y; }
+  }
+}
+__global__ void reduce_xts_kernel(const double *__restrict__ partials, int nparts, int p, double *__restrict__ xty) {
+  const int p2x2 = 2 * ((p + 1) >> 1);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p; j += gridDim.x * blockDim.x) {
+    double sum = 0;
+    for (int c = 0; c < nparts; ++c) sum += partials[(int64_t)c * p2x2 + j];
+    xty[j] = sum;
+  }
+}
+
 // present[v] = 1 iff some row has count y == v, 0 <= v < len (benign same-value races).  What the host needs to know which
 // entries NormalMixtureApproximationTable::approximate would have to add for this data (NormalMixtureApproximation.cpp:472-532).
 __global__ void counts_present_kernel(const int64_t *__restrict__ y, int64_t n, unsigned char *__restrict__ present, int64_t len) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t v = __ldg(y + i);
     if (v >= 0 && v < len) present[v] = 1;
+  }
+}
+
+// out (n x ldo, pad columns zero) = the k listed columns of X: the included-variable design matrix X_gamma that the
+// chunk log posteriors of the composite sampler walk (BinomialLogitCompositeSpikeSlabSampler.cpp:34-74 selects the same
+// columns from every observation on every evaluation)
+__global__ void select_columns_kernel(const double *__restrict__ X, int64_t ldx, int64_t n, const int *__restrict__ cols, int k,
+                                      double *__restrict__ out, int ldo) {
+  const int64_t total = n * ldo;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / ldo;
+    const int j = (int)(e - i * ldo);
+    out[e] = j < k ? __ldg(X + i * ldx + __ldg(cols + j)) : 0.0;
   }
 }
 

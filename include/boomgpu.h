@@ -121,6 +121,16 @@ int boomgpu_logit_step(boomgpu_ctx *ctx, const double *beta, int clt_threshold, 
 int boomgpu_poisson_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration,
                          double *xtwx, double *xtwy, double scalars[4]);
 
+/* The probit sibling -- BinomialProbitSpikeSlabSampler::impute_latent_data / refresh_xtx
+ * (Models/Glm/PosteriorSamplers/BinomialProbitSpikeSlabSampler.cpp:58-83) over BinomialProbitDataImputer::impute
+ * (BinomialProbitDataImputer.cpp:31-68), on binomial data uploaded with boomgpu_upload_binomial / _adopt_binomial:
+ * xtx = sum n_i x x' (it does not depend on beta: pass xtx = NULL after the first call and only X'z -- one HBM-bound
+ * pass over X -- is computed), xtz = sum x_i (sum of the n_i latent normals of observation i). */
+int boomgpu_probit_step(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
+                        double *xtx, double *xtz, int64_t *sample_size);
+int boomgpu_probit_step_device(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
+                               double *suf_dev, int xtz_only);
+
 /* Page-locks a caller-owned host range (cudaHostRegister).  When the xtx / xtwx argument of the synchronous steps points
  * into such a range, the p x p matrix is copied device->host straight into it (at p = 4000 it is 128 MB: the staging
  * copy it saves costs ~15 ms per iteration and per rank).  ctx-free: errors are reported through boomgpu_last_error(NULL). */
@@ -169,6 +179,9 @@ int boomgpu_logit_draw(boomgpu_ctx *ctx, const double *beta, int clt_threshold, 
 /* out6 (n x 6) = {z_int, mu_int, w_int, z_ext, mu_ext, w_ext}; kout2 (n x 2, may be NULL) component indices */
 int boomgpu_poisson_draw(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration,
                          double *out6, int32_t *kout2);
+/* per-row sums of the latent probit normals (host array of length n) */
+int boomgpu_probit_draw(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
+                        double *sum_z_out);
 int boomgpu_binomial_loglike(boomgpu_ctx *ctx, const double *beta, double *loglike);
 int boomgpu_poisson_loglike(boomgpu_ctx *ctx, const double *beta, double *loglike);
 /* log likelihood with gradient (p, may be NULL) and Hessian (p x p, symmetric, may be NULL) in one pass over the rows:
@@ -184,6 +197,19 @@ int boomgpu_poisson_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double 
  * [ -(Hessian) p*p | gradient p | {., log likelihood, ., .} ] at suf_dev for a caller-driven all-reduce. */
 int boomgpu_binomial_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double log_alpha, double *suf_dev);
 int boomgpu_poisson_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev);
+
+/* The same restricted to a set of columns -- the included variables of a spike-and-slab model.  The reference's chunk log
+ * posterior (BinomialLogitLogPostChunk, Models/Glm/PosteriorSamplers/BinomialLogitCompositeSpikeSlabSampler.cpp:34-74) selects
+ * the included columns from every observation on every evaluation; here boomgpu_select_columns gathers X_gamma (n x k) once
+ * per model (cached until another selection or new data), and every evaluation is one pass over those k columns:
+ * beta_selected, gradient: k; hessian: k x k.  With a communicator attached the results are all-reduced over the ranks;
+ * the _device variant leaves [ -H k*k | g k | {., log likelihood, ., .} ] (boomgpu_suf_len(k) doubles) at suf_dev. */
+int boomgpu_select_columns(boomgpu_ctx *ctx, const int32_t *columns, int k);
+int boomgpu_binomial_loglike_derivs_selected(boomgpu_ctx *ctx, const double *beta_selected, double log_alpha, double *loglike,
+                                             double *gradient, double *hessian);
+int boomgpu_poisson_loglike_derivs_selected(boomgpu_ctx *ctx, const double *beta_selected, double *loglike, double *gradient,
+                                            double *hessian);
+int boomgpu_binomial_loglike_derivs_selected_device(boomgpu_ctx *ctx, const double *beta_selected, double log_alpha, double *suf_dev);
 
 /* ---- instrumentation ------------------------------------------------------------------- */
 /* number of kernels this context has launched so far */

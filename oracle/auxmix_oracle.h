@@ -114,6 +114,14 @@ int bo_poisson_draw(int64_t n, int p, const double *X, int64_t ldx, const int64_
                     const double *beta, const bo_poisson_table *tab, uint64_t seed, uint64_t iteration,
                     uint64_t row_offset, double *out6, int32_t *kout2);
 
+/* ---- probit sibling (BinomialProbitSpikeSlabSampler) ---------------------------------- */
+double bo_rtrun_norm_unit(double eta, int positive, double unif);
+int bo_probit_impute(int clt_threshold, double ntrials, double nsuccess, double eta, uint64_t seed, uint64_t iteration,
+                     uint64_t row, double *sum_z);
+int bo_probit_step(int64_t n, int p, const double *X, int64_t ldx, const double *y, const double *ntrials, const double *beta,
+                   int clt_threshold, uint64_t seed, uint64_t iteration, uint64_t row_offset, double *xtx, double *xtz,
+                   double *draws);
+
 /* BinomialLogitModel::log_likelihood (value only, log_alpha = 0) */
 double bo_dbinom_log(double x, double n, double p);
 double bo_binomial_logit_loglike(int64_t n, int p, const double *X, int64_t ldx, const double *y,

@@ -244,6 +244,25 @@ def poisson_draw(X, y, exposure, beta, tab, seed, iteration, row_offset=0):
     return out, k2
 
 
+def rtrun_norm_unit(eta, positive, unif):
+    lib().bo_rtrun_norm_unit.restype = C.c_double
+    return lib().bo_rtrun_norm_unit(C.c_double(eta), C.c_int(int(positive)), C.c_double(unif))
+
+
+def probit_step(X, y, ntrials, beta, clt_threshold, seed, iteration, row_offset=0):
+    """(xtx, xtz, per-row sum of latent z) of BinomialProbitSpikeSlabSampler::impute_latent_data on the shared Philox stream."""
+    X, y, ntrials, beta = _f64(X), _f64(y), _f64(ntrials), _f64(beta)
+    n, p = X.shape
+    xtx = np.zeros((p, p))
+    xtz = np.zeros(p)
+    draws = np.zeros(n)
+    rc = lib().bo_probit_step(C.c_int64(n), C.c_int(p), _dp(X), C.c_int64(p), _dp(y), _dp(ntrials), _dp(beta), C.c_int(clt_threshold),
+                              C.c_uint64(seed), C.c_uint64(iteration), C.c_uint64(row_offset), _dp(xtx), _dp(xtz), _dp(draws))
+    if rc:
+        raise ValueError("bo_probit_step rc=%d" % rc)
+    return xtx.T.copy(), xtz, draws
+
+
 def binomial_logit_loglike(X, y, ntrials, beta):
     X, y, ntrials, beta = _f64(X), _f64(y), _f64(ntrials), _f64(beta)
     n, p = X.shape

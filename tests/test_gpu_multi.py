@@ -189,3 +189,76 @@ def test_sampler_surface_with_the_native_communicator():
     assert not isinstance(res[0][1], str) and not isinstance(res[1][1], str), res
     np.testing.assert_array_equal(res[0][1], res[1][1])
     np.testing.assert_array_equal(res[0][2], res[1][2])
+
+
+def _loglike_worker(rank, world, port, native, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import boom_b200
+    from boom_b200 import distributed as shard
+    from oracle import oracle as O
+    try:
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world, device_id=dev)
+        n, p = 20_003, 9
+        X, y, nt, beta = O.synth_binomial(n, p, 3, seed=14, max_trials=3)
+        row0, row1 = shard.shard_range(n, world, rank)
+        stream = torch.cuda.Stream(device=dev)
+        model = boom_b200.BinomialLogitModel(X[row0:row1], y[row0:row1], nt[row0:row1])
+        s = boom_b200.BinomialLogitSpikeSlabSampler(model, boom_b200.MvnModel(np.zeros(p), np.eye(p)),
+                                                    boom_b200.VariableSelectionPrior(p, 0.5), 10, boom_b200.RNG(3))
+        model.set_method(s)
+        shard.attach(model, n, stream, dev, rank, world, native=native)
+        ll = model.log_likelihood(beta * 0.8)
+        ll2, g, h = model.log_likelihood_derivs(beta * 0.8)
+        model.drop_all()
+        for j in range(4):
+            model.add(j)
+        s.find_posterior_mode(1e-8)
+        q.put((rank, ll, ll2, g, h, np.array(model.Beta), s.log_posterior_at_mode))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, "FAIL: %r" % (e,), None, None, None, None, None))
+
+
+@pytest.mark.parametrize("native", [False, True])
+def test_log_likelihood_and_mode_are_all_reduced_under_sharding(native):
+    """with rows sharded, log_likelihood / log_likelihood_derivs / find_posterior_mode must see ALL rows on every
+    rank (hook path and native communicator): equal on both ranks and equal to the one-GPU values."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    import boom_b200
+    from oracle import oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_loglike_worker, args=(r, 2, port, native, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted((q.get(timeout=600) for _ in procs), key=lambda t: t[0])
+    for pr in procs:
+        pr.join(timeout=60)
+    assert not isinstance(res[0][1], str) and not isinstance(res[1][1], str), res
+    for k in range(1, 7):
+        np.testing.assert_array_equal(res[0][k], res[1][k])
+    n, p = 20_003, 9
+    X, y, nt, beta = O.synth_binomial(n, p, 3, seed=14, max_trials=3)
+    rll, rg, rh = O.binomial_logit_loglike_derivs(X, y, nt, beta * 0.8)
+    assert res[0][1] == pytest.approx(rll, rel=1e-12) and res[0][2] == pytest.approx(rll, rel=1e-12)
+    np.testing.assert_allclose(res[0][3], rg, rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(res[0][4], rh, rtol=1e-10, atol=1e-9)
+    model = boom_b200.BinomialLogitModel(X, y, nt)
+    s = boom_b200.BinomialLogitSpikeSlabSampler(model, boom_b200.MvnModel(np.zeros(p), np.eye(p)),
+                                                boom_b200.VariableSelectionPrior(p, 0.5), 10, boom_b200.RNG(3))
+    model.set_method(s)
+    model.drop_all()
+    for j in range(4):
+        model.add(j)
+    s.find_posterior_mode(1e-8)
+    np.testing.assert_allclose(res[0][5], np.array(model.Beta), rtol=1e-7, atol=1e-9)
+    assert res[0][6] == pytest.approx(s.log_posterior_at_mode, rel=1e-10)
