@@ -22,6 +22,8 @@
 #include "Models/Glm/PosteriorSamplers/BinomialLogitAuxmixSampler.hpp"
 #include "Models/Glm/PosteriorSamplers/BinomialLogitCompositeSpikeSlabSampler.hpp"
 #include "Models/Glm/PosteriorSamplers/BinomialLogitSpikeSlabSampler.hpp"
+#include "Models/Glm/BinomialProbitModel.hpp"
+#include "Models/Glm/PosteriorSamplers/BinomialProbitSpikeSlabSampler.hpp"
 #include "Models/Glm/PosteriorSamplers/PoissonRegressionAuxMixSampler.hpp"
 #include "Models/Glm/PosteriorSamplers/PoissonRegressionSpikeSlabSampler.hpp"
 #include "Models/Glm/VariableSelectionPrior.hpp"
@@ -194,6 +196,33 @@ int main(int argc, char **argv) {
       print_summary("reference", out[0]); printf(", ");
       print_summary("b200", out[1]);
       printf(", \"time_report_lines\": %d}\n", (int)std::count(report.begin(), report.end(), '\n'));
+      return 0;
+    }
+    if (kind == "probit") {
+      // the sibling sampler: BinomialProbitSpikeSlabSampler on BOOM's BinomialProbitModel, reference vs B200 (binomial rows,
+      // n_i in {1, 2, 3, 15}: both the per-trial draws and the CLT branch)
+      Summary out[2];
+      std::vector<double> yp(n), np_(n);
+      for (int i = 0; i < n; ++i) {
+        np_[i] = (i % 7 == 0) ? 15.0 : 1.0 + (i % 3);
+        yp[i] = rbinom((int)np_[i], pnorm(xs[i].dot(beta)));
+      }
+      for (int arm = 0; arm < 2; ++arm) {
+        NEW(BinomialProbitModel, model)(p);
+        for (int i = 0; i < n; ++i) model->add_data(new BinomialRegressionData(yp[i], np_[i], xs[i]));
+        model->coef().drop_all(); model->coef().add(0);
+        RNG seeder(arm == 0 ? 51 : 52);
+        Ptr<PosteriorSampler> sampler;
+        if (arm == 0) sampler = new BinomialProbitSpikeSlabSampler(model.get(), slab, spike, 10, seeder);
+        else sampler = new B200::BinomialProbitSpikeSlabSampler(model.get(), slab, spike, 10, seeder);
+        model->set_method(sampler);
+        out[arm] = run(model, iters, burn);
+      }
+      printf("{\"kind\": \"probit\", \"n\": %d, \"p\": %d, \"iters\": %d, \"burn\": %d, ", n, p, iters, burn);
+      print_vec("beta_true", beta);
+      print_summary("reference", out[0]); printf(", ");
+      print_summary("b200", out[1]);
+      printf("}\n");
       return 0;
     }
     if (kind == "api") {

@@ -648,6 +648,88 @@ std::ostream &BLCSSS::time_report(std::ostream &out) const {
 }
 
 // ---------------------------------------------------------------------------------------------
+BinomialProbitSpikeSlabSampler::BinomialProbitSpikeSlabSampler(BinomialProbitModel *model, const Ptr<MvnBase> &slab,
+                                                               const Ptr<VariableSelectionPrior> &spike, int clt_threshold,
+                                                               RNG &seeding_rng)
+    : DeviceImputerBase(model->xdim(), seeding_rng), model_(model), slab_(slab), spike_(spike), clt_threshold_(clt_threshold) {
+  if (slab_->dim() != model_->xdim() || (int)spike_->potential_nvars() != model_->xdim())
+    report_error("Prior does not match model dimension.");
+  model_->add_observer([this]() { this->mark_stale(); });
+}
+void BinomialProbitSpikeSlabSampler::pack_rows(int64_t row0, int64_t nrows, double *X, void *y, double *aux) const {
+  const std::vector<Ptr<BinomialRegressionData>> &data(model_->dat());
+  const int p = xdim_;
+  double *yd = static_cast<double *>(y);
+  for (int64_t i = 0; i < nrows; ++i) {
+    const BinomialRegressionData &d(*data[row0 + i]);
+    const Vector &x(d.x());
+    std::copy(x.begin(), x.end(), X + (size_t)i * p);
+    yd[i] = d.y();
+    aux[i] = d.n();
+  }
+}
+void BinomialProbitSpikeSlabSampler::observe_row_objects(bool tf) {
+  for (const Ptr<BinomialRegressionData> &d : model_->dat()) {
+    d->remove_observer(observer_key());
+    d->Xptr()->remove_observer(observer_key());
+    if (tf) {
+      d->add_observer(observer_key(), [this]() { this->mark_stale(); });
+      d->Xptr()->add_observer(observer_key(), [this]() { this->mark_stale(); });
+    }
+  }
+}
+int BinomialProbitSpikeSlabSampler::device_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *suf_dev) {
+  return boomgpu_probit_step_device(ctx, beta, clt_threshold_, seed, iteration, suf_dev, 0);   // hook path: the full statistics
+}
+int BinomialProbitSpikeSlabSampler::device_step_sync(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *xtx,
+                                                     double *xty, double scalars[4]) {
+  int64_t ss = 0;
+  const int rc = boomgpu_probit_step(ctx, beta, clt_threshold_, seed, iteration, want_xtx_ ? xtx : nullptr, xty, &ss);
+  scalars[0] = (double)ss; scalars[1] = scalars[2] = scalars[3] = 0.0;
+  return rc;
+}
+int BinomialProbitSpikeSlabSampler::device_loglike_derivs(boomgpu_ctx *, const double *, double *, double *, double *) {
+  report_error("the probit sibling provides the Gibbs step only");
+  return 1;
+}
+int BinomialProbitSpikeSlabSampler::device_loglike_derivs_device(boomgpu_ctx *, const double *, double *) {
+  report_error("the probit sibling provides the Gibbs step only");
+  return 1;
+}
+int BinomialProbitSpikeSlabSampler::device_loglike_derivs_selected(boomgpu_ctx *, const double *, double *, double *, double *) {
+  report_error("the probit sibling provides the Gibbs step only");
+  return 1;
+}
+int BinomialProbitSpikeSlabSampler::device_loglike_derivs_selected_device(boomgpu_ctx *, const double *, double *) {
+  report_error("the probit sibling provides the Gibbs step only");
+  return 1;
+}
+void BinomialProbitSpikeSlabSampler::impute_latent_data() {
+  DeviceImputerBase::impute_latent_data();   // (re)packs when needed -> install_tables() -> want_xtx_
+  want_xtx_ = false;
+}
+void BinomialProbitSpikeSlabSampler::draw() {   // BinomialProbitSpikeSlabSampler.cpp:42-47
+  impute_latent_data();
+  if (allow_model_selection_) {
+    BOOM_B200::SpikeSlabCore c(core(slab_, spike_, true));
+    c.allow_model_selection(true);
+    c.limit_model_selection(max_flips_);
+    sweep_indicators(model_->coef(), c);
+  }
+  draw_included_beta(model_->coef(), core(slab_, spike_, true));
+}
+double BinomialProbitSpikeSlabSampler::logpri() const { return spike_slab_logpri(model_->coef(), *slab_, *spike_); }
+WeightedRegSuf BinomialProbitSpikeSlabSampler::complete_data_sufficient_statistics() const {
+  const int p = xdim_;
+  WeightedRegSuf suf(p);
+  SpdMatrix xtx(p);
+  std::copy(hsuf_.xtx().a.begin(), hsuf_.xtx().a.end(), xtx.data());
+  suf.set_xtwx(xtx);
+  suf.set_xtwy(Vector(hsuf_.xty().begin(), hsuf_.xty().end()));
+  return suf;
+}
+
+// ---------------------------------------------------------------------------------------------
 PoissonRegressionAuxMixSampler::PoissonRegressionAuxMixSampler(PoissonRegressionModel *model, const Ptr<MvnBase> &prior, int,
                                                                RNG &seeding_rng)
     : DeviceImputerBase(model->xdim(), seeding_rng), model_(model), prior_(prior), suf_(model->xdim()) {

@@ -6,6 +6,7 @@
 //   BOOM::BinomialLogitAuxmixSampler        -> BOOM::B200::BinomialLogitAuxmixSampler
 //   BOOM::BinomialLogitSpikeSlabSampler     -> BOOM::B200::BinomialLogitSpikeSlabSampler
 //   BOOM::BinomialLogitCompositeSpikeSlabSampler -> BOOM::B200::BinomialLogitCompositeSpikeSlabSampler  (what R's logit.spike builds)
+//   BOOM::BinomialProbitSpikeSlabSampler    -> BOOM::B200::BinomialProbitSpikeSlabSampler   (sibling)
 //   BOOM::PoissonRegressionAuxMixSampler    -> BOOM::B200::PoissonRegressionAuxMixSampler
 //   BOOM::PoissonRegressionSpikeSlabSampler -> BOOM::B200::PoissonRegressionSpikeSlabSampler
 //
@@ -37,6 +38,7 @@
 #include <memory>
 
 #include "Models/Glm/BinomialLogitModel.hpp"
+#include "Models/Glm/BinomialProbitModel.hpp"
 #include "Models/Glm/PoissonRegressionModel.hpp"
 #include "Models/Glm/PosteriorSamplers/BinomialLogitAuxmixSampler.hpp"
 #include "Models/Glm/VariableSelectionPrior.hpp"
@@ -278,6 +280,44 @@ class PoissonRegressionAuxMixSampler : public DeviceImputerBase {
  private:
   mutable WeightedRegSuf suf_;
   mutable bool suf_synced_ = false;
+};
+
+// BinomialProbitSpikeSlabSampler (Models/Glm/PosteriorSamplers/BinomialProbitSpikeSlabSampler.hpp:34-68).  X'NX is computed
+// when the rows are (re)packed, every later iteration computes X'z alone.
+class BinomialProbitSpikeSlabSampler : public DeviceImputerBase {
+ public:
+  BinomialProbitSpikeSlabSampler(BinomialProbitModel *model, const Ptr<MvnBase> &slab_prior, const Ptr<VariableSelectionPrior> &spike_prior,
+                                 int clt_threshold = 10, RNG &seeding_rng = GlobalRng::rng);
+  void draw() override;
+  double logpri() const override;
+  void allow_model_selection(bool tf) { allow_model_selection_ = tf; }
+  void limit_model_selection(int max_flips) { max_flips_ = max_flips; }
+  void impute_latent_data();
+  void refresh_xtx() { want_xtx_ = true; }
+  WeightedRegSuf complete_data_sufficient_statistics() const;   // by value, as in the reference
+
+ protected:
+  int64_t row_count() const override { return (int64_t)model_->dat().size(); }
+  bool rows_are_poisson() const override { return false; }
+  void install_tables(boomgpu_ctx *) override { want_xtx_ = true; }   // called exactly when the rows are (re)packed
+  void pack_rows(int64_t row0, int64_t nrows, double *X, void *y, double *aux) const override;
+  void observe_row_objects(bool tf) override;
+  int device_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *suf_dev) override;
+  int device_step_sync(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *xtx, double *xty,
+                       double scalars[4]) override;
+  int device_loglike_derivs(boomgpu_ctx *, const double *, double *, double *, double *) override;
+  int device_loglike_derivs_device(boomgpu_ctx *, const double *, double *) override;
+  int device_loglike_derivs_selected(boomgpu_ctx *, const double *, double *, double *, double *) override;
+  int device_loglike_derivs_selected_device(boomgpu_ctx *, const double *, double *) override;
+  const Vector &current_beta() const override { return model_->Beta(); }
+
+ private:
+  BinomialProbitModel *model_;
+  Ptr<MvnBase> slab_;
+  Ptr<VariableSelectionPrior> spike_;
+  int clt_threshold_;
+  bool allow_model_selection_ = true, want_xtx_ = true;
+  int max_flips_ = -1;
 };
 
 class PoissonRegressionSpikeSlabSampler : public PoissonRegressionAuxMixSampler {

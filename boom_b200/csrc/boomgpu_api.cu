@@ -417,6 +417,41 @@ struct TmaLauncher {
   }
 };
 
+// the warp-specialised wide-tile kernel (fused_ws_kernel): 40 < p <= 64
+template <int MODEL>
+struct WsLauncher {
+  template <int NB>
+  static int go(boomgpu_ctx *ctx, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts, const TailParams &tail) {
+    auto kern = fused_ws_kernel<NB, MODEL>;
+    BetaParam bp;
+    memset(&bp, 0, sizeof(bp));
+    memcpy(bp.b, ctx->beta_pin, sizeof(double) * d.p);
+    const size_t smem = ws_smem_bytes(NB);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = ensure_xmap(ctx, ctx->xmap_small, ctx->X, ctx->ldx, tma_padw(NB), 32)) return rc;
+    const int64_t nslices = (d.n + 31) / 32;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nslices + kWsAccWarps - 1) / kWsAccWarps, (int64_t)ctx->sms));
+    if (ensure(ctx, &ctx->partials, &ctx->partials_cap, (int64_t)grid * tma_partial_len(NB))) return BOOMGPU_ERR_CUDA;
+    {
+      LaunchScope ls(ctx, 0);
+      kern<<<grid, 32 * ws_warps(NB), smem, ctx->stream>>>(ctx->xmap_small.map, d, prm, out, bp, ctx->partials, ctx->err_dev, tail);
+    }
+    CU(cudaGetLastError());
+    *nparts = grid;
+    return 0;
+  }
+  static int dispatch(boomgpu_ctx *ctx, int nb, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts,
+                      const TailParams &tail) {
+    switch (nb) {
+      case 5: return go<5>(ctx, d, prm, out, nparts, tail);
+      case 6: return go<6>(ctx, d, prm, out, nparts, tail);
+      case 7: return go<7>(ctx, d, prm, out, nparts, tail);
+      case 8: return go<8>(ctx, d, prm, out, nparts, tail);
+    }
+    return fail(ctx, BOOMGPU_ERR_ARG, "bad column block count %d for the warp-specialised kernel", nb);
+  }
+};
+
 template <int MODEL>
 cudaError_t launch_impute_rows(boomgpu_ctx *ctx, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts, int nnz) {
   const bool vec2 = (d.ldx % 2 == 0) && aligned16(d.X);
@@ -590,7 +625,9 @@ int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, c
     if (tma_small) {
       // TMA-fed warp-autonomous kernel (fused_tma.cuh); single launch: its last CTA also sums the partials
       TailParams tail{suf, host_out, ctx->single_launch ? ctx->tail_counter : nullptr};
-      if (int rc = TmaLauncher<MODEL>::dispatch(ctx, nb, d, prm, out, &nparts, tail)) return rc;
+      if (nb >= 5 && ctx->small_variant != 2) {   // wide tiles: accumulate warps + draw warps
+        if (int rc = WsLauncher<MODEL>::dispatch(ctx, nb, d, prm, out, &nparts, tail)) return rc;
+      } else if (int rc = TmaLauncher<MODEL>::dispatch(ctx, nb, d, prm, out, &nparts, tail)) return rc;
       reduced = tail.counter != nullptr;
       if (reduced) ctx->host_out_written = host_out != nullptr;
     } else {
@@ -901,7 +938,7 @@ int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value) {
     return 0;
   }
   if (!strcmp(name, "small_variant")) {
-    if (value < 0 || value > 1) return fail(ctx, BOOMGPU_ERR_ARG, "small_variant must be 0 or 1");
+    if (value < 0 || value > 2) return fail(ctx, BOOMGPU_ERR_ARG, "small_variant must be 0, 1 or 2");
     ctx->small_variant = (int)value;
     return 0;
   }

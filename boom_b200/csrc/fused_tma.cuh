@@ -138,6 +138,52 @@ struct TailParams {
   unsigned int *counter;   // CTAs that have written their partial; reset by the last one
 };
 
+// The last CTA of a single-launch step: one THREAD per output element, the partials summed in CTA order (deterministic)
+// with 16 independent loads in flight (a warp per element serialises ~20 elements x 5 dependent L2 round trips on every
+// warp: 28 us at C1; this form is ~3 us).  Partials are read around L1: other CTAs of the same grid wrote them.
+template <int NB>
+__device__ __forceinline__ void sum_partials_tail(const double *__restrict__ partials, int nparts, int p, const TailParams &tail,
+                                                  const int *err, int tid, int nthreads) {
+  constexpr int P8 = 8 * NB;
+  {
+    const int ntri = p * (p + 1) / 2, total = ntri + p + 4;
+    constexpr int64_t plen = tma_partial_len(NB);
+    for (int e = tid; e < total; e += nthreads) {
+      int a = 0, b = 0;
+      int64_t src;
+      if (e < ntri) {
+        int rem = e;
+        while (rem >= p - a) { rem -= p - a; ++a; }
+        b = a + rem;
+        src = (int64_t)a * P8 + b;
+      } else if (e < ntri + p) {
+        src = (int64_t)P8 * P8 + (e - ntri);
+      } else {
+        src = (int64_t)P8 * P8 + P8 + (e - ntri - p);
+      }
+      double s = 0;
+      int cta = 0;
+      for (; cta + 16 <= nparts; cta += 16) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldcg(partials + (int64_t)(cta + u) * plen + src);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s += v[u];
+      }
+      for (; cta < nparts; ++cta) s += __ldcg(partials + (int64_t)cta * plen + src);
+      if (e < ntri) {
+        tail.suf[a + (int64_t)b * p] = s;
+        tail.suf[b + (int64_t)a * p] = s;
+        if (tail.host_out) { tail.host_out[a + (int64_t)b * p] = s; tail.host_out[b + (int64_t)a * p] = s; }
+      } else {
+        tail.suf[(int64_t)p * p + (e - ntri)] = s;
+        if (tail.host_out) tail.host_out[(int64_t)p * p + (e - ntri)] = s;
+      }
+    }
+    if (tail.host_out && tid == 0) tail.host_out[(int64_t)p * p + p + 4] = (double)__ldcg(err);
+  }
+}
+
 template <int NB, int MODEL>
 __global__ void __launch_bounds__(32 * tma_warps(NB), 1)
 fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams prm, RowOut out, const __grid_constant__ BetaParam beta,
@@ -391,46 +437,213 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
   __syncthreads();
   if (ticket_s != gridDim.x - 1) return;
   __threadfence();
-  // one THREAD per output element, the partials summed in CTA order with 16 independent loads in flight (a warp per
-  // element serialises ~20 elements x 5 dependent L2 round trips on every warp: 28 us at C1; this form is ~3 us)
-  {
-    const int p = d.p, nparts = (int)gridDim.x;
-    const int ntri = p * (p + 1) / 2, total = ntri + p + 4;
-    constexpr int64_t plen = tma_partial_len(NB);
-    for (int e = tid; e < total; e += 32 * NW) {
-      int a = 0, b = 0;
-      int64_t src;
-      if (e < ntri) {
-        int rem = e;
-        while (rem >= p - a) { rem -= p - a; ++a; }
-        b = a + rem;
-        src = (int64_t)a * P8 + b;
-      } else if (e < ntri + p) {
-        src = (int64_t)P8 * P8 + (e - ntri);
-      } else {
-        src = (int64_t)P8 * P8 + P8 + (e - ntri - p);
-      }
-      double s = 0;
-      int cta = 0;
-      for (; cta + 16 <= nparts; cta += 16) {
-        double v[16];
+  sum_partials_tail<NB>(partials, (int)gridDim.x, d.p, tail, err, tid, 32 * NW);
+  if (tid == 0) *tail.counter = 0u;
+}
+
+// =============================================================================================
+// Wide tiles (40 < p <= 64), warp-specialised.  In fused_tma_kernel every warp alternates between its draw phase (a long
+// dependent chain per lane: latency bound) and its DMMA phase (28-36 atoms per k-step: pipe bound), and with the 8 warps
+// that fit (the triangle alone is 112-144 registers) the FP64 pipe idles through every draw phase: 50 % busy at C2.
+// Here the roles are split.  Per SM sub-partition: ONE accumulate warp that owns the triangle and does nothing but DMMA
+// k-steps, and TWO draw warps that take turns preparing its slices (eta, latent draw, (w, s) into the slice's pad columns).
+//   accumulate warp m (0..3)  issues the TMA loads of its ring (S slots); for slot k: waits drawn[k] -> 8 k-steps ->
+//                             re-arms full[k] and issues the TMA of slice k + S (it is the slot's last reader)
+//   draw warps 4 + m, 8 + m   slices k = 0, 2, 4, ... / 1, 3, 5, ...: wait full[k] -> eta, draw -> (w, s) -> arrive drawn[k]
+// No block-wide barrier in the steady state; mbarriers only (full: transaction count, drawn: one arrival).
+// =============================================================================================
+constexpr int kWsAccWarps = 4;
+// p <= 56: 12 warps (two draw warps per accumulate warp, 168 registers each: the 28-atom triangle is 112 of them);
+// p > 56: the 36-atom triangle needs more than 168 registers, so 8 warps (one draw warp per accumulate warp) at 255
+__host__ __device__ constexpr int ws_warps(int nb) { return nb <= 7 ? 12 : 8; }
+__host__ __device__ constexpr int ws_stages(int nb) { return 3; }
+__host__ __device__ constexpr size_t ws_smem_bytes(int nb) {
+  return sizeof(double) * ((size_t)kWsAccWarps * ws_stages(nb) * 32 * tma_padw(nb) + 64) +
+         sizeof(uint64_t) * 2 * kWsAccWarps * ws_stages(nb) + 128;
+}
+
+template <int NB, int MODEL>
+__global__ void __launch_bounds__(32 * ws_warps(NB), 1)
+fused_ws_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams prm, RowOut out, const __grid_constant__ BetaParam beta,
+                double *__restrict__ partials, int *err, TailParams tail) {
+  constexpr int S = ws_stages(NB);
+  constexpr int kWsWarps = ws_warps(NB);
+  constexpr int NDRAW = (kWsWarps - kWsAccWarps) / kWsAccWarps;   // draw warps per accumulate warp
+  constexpr int PADW = tma_padw(NB);
+  constexpr int SLICE = 32 * PADW;
+  constexpr int P8 = 8 * NB;
+  constexpr int NA = NB * (NB + 1) / 2;
+  constexpr uint32_t kSliceBytes = SLICE * sizeof(double);
+  extern __shared__ __align__(128) double smem[];
+  double *ring = smem;                                           // [4][S][SLICE]
+  double *red_s = smem + (size_t)kWsAccWarps * S * SLICE;        // 64
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(red_s + 64); // [4][S]
+  uint64_t *drawn_bar = full_bar + kWsAccWarps * S;              // [4][S]
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int m = wid & 3;                 // sub-partition / accumulate warp this warp works with
+  const bool is_acc = wid < kWsAccWarps;
+  if (tid == 0) {
+    for (int i = 0; i < kWsAccWarps * S; ++i) { mbar_init(full_bar + i, 1); mbar_init(drawn_bar + i, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  // 32-row slices are dealt to (CTA, accumulate warp): the k-th slice of ring m is (blockIdx + k grid) 4 + m
+  const int64_t nslices = (d.n + 31) / 32;
+  const int64_t stride = (int64_t)gridDim.x * kWsAccWarps;
+  const int64_t first = (int64_t)blockIdx.x * kWsAccWarps + m;
+  double *my_ring = ring + (size_t)m * S * SLICE;
+  uint64_t *my_full = full_bar + m * S, *my_drawn = drawn_bar + m * S;
+
+  double c[NA][2];
+  double xty_acc[NB];
+  double sc_count = 0, sc_ywy = 0, sc_sumw = 0, sc_sumlogw = 0;
+
+  if (is_acc) {
+    // ===== accumulate warp
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = __ldcg(partials + (int64_t)(cta + u) * plen + src);
+    for (int a = 0; a < NA; ++a) { c[a][0] = 0.0; c[a][1] = 0.0; }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) s += v[u];
-      }
-      for (; cta < nparts; ++cta) s += __ldcg(partials + (int64_t)cta * plen + src);
-      if (e < ntri) {
-        tail.suf[a + (int64_t)b * p] = s;
-        tail.suf[b + (int64_t)a * p] = s;
-        if (tail.host_out) { tail.host_out[a + (int64_t)b * p] = s; tail.host_out[b + (int64_t)a * p] = s; }
-      } else {
-        tail.suf[(int64_t)p * p + (e - ntri)] = s;
-        if (tail.host_out) tail.host_out[(int64_t)p * p + (e - ntri)] = s;
+    for (int b = 0; b < NB; ++b) xty_acc[b] = 0.0;
+    if (lane == 0) {
+#pragma unroll
+      for (int s0 = 0; s0 < S; ++s0) {
+        const int64_t q = first + s0 * stride;
+        if (q < nslices) {
+          mbar_expect_tx(my_full + s0, kSliceBytes);
+          tma_load_2d(my_ring + s0 * SLICE, &xmap, 0, (int)(q * 32), my_full + s0);
+        }
       }
     }
-    if (tail.host_out && tid == 0) tail.host_out[(int64_t)p * p + p + 4] = (double)__ldcg(err);
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int64_t q = first; q < nslices; q += stride) {
+      mbar_wait(my_drawn + slot, phase);
+      const double *xs = my_ring + slot * SLICE;
+#pragma unroll 2
+      for (int kk = 0; kk < 8; ++kk) {
+        const int row = 8 * (kk >> 1) + (kk & 1) + 2 * (lane & 3);   // the k-step's four rows, two apart (bank layout: tma_padw)
+        const double2 ws = *reinterpret_cast<const double2 *>(xs + row * PADW + P8);
+        const double *xr = xs + row * PADW + (lane >> 2);
+        double xa[NB], xw[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          xa[b] = xr[8 * b];
+          xw[b] = xa[b] * ws.x;
+          xty_acc[b] = fma(xa[b], ws.y, xty_acc[b]);
+        }
+        int a = 0;
+#pragma unroll
+        for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+          for (int bj = bi; bj < NB; ++bj) { dmma884(c[a][0], c[a][1], xw[bi], xa[bj]); ++a; }
+      }
+      // the slot's last reader re-arms it S slices ahead (the draw warp's generic-proxy writes of (w, s) are ordered
+      // before the async-proxy overwrite by the fence)
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        const int64_t qn = q + (int64_t)S * stride;
+        if (qn < nslices) {
+          mbar_expect_tx(my_full + slot, kSliceBytes);
+          tma_load_2d(my_ring + slot * SLICE, &xmap, 0, (int)(qn * 32), my_full + slot);
+        }
+      }
+      if (++slot == S) { slot = 0; phase ^= 1; }
+    }
+  } else {
+    // ===== draw warp: every NDRAW-th slice of ring m
+    const int turn = (wid - kWsAccWarps) >> 2;     // 0 .. NDRAW - 1
+    RowObs obs_next;
+    obs_next.y = 0; obs_next.aux = 0; obs_next.yi = 0;
+    {
+      const int64_t q0 = first + turn * stride;
+      const int64_t i0 = q0 * 32 + lane;
+      if (q0 < nslices && i0 < d.n) obs_next = load_obs<MODEL>(d, i0);
+    }
+    int64_t k = turn;
+    for (int64_t q = first + turn * stride; q < nslices; q += NDRAW * stride, k += NDRAW) {
+      const int slot = (int)(k % S);
+      const uint32_t phase = (uint32_t)((k / S) & 1);
+      const int64_t i = q * 32 + lane;
+      const bool valid = i < d.n;
+      const RowObs obs = obs_next;
+      const int64_t in = (q + NDRAW * stride) * 32 + lane;
+      if (in < d.n) obs_next = load_obs<MODEL>(d, in);
+      mbar_wait(my_full + slot, phase);
+      double *xs = my_ring + slot * SLICE;
+      double e0 = 0, e1 = 0;
+#pragma unroll
+      for (int col = 0; col < P8; col += 2) {
+        const double2 x = *reinterpret_cast<const double2 *>(xs + lane * PADW + col);
+        e0 = fma(x.x, beta.b[col], e0);
+        e1 = fma(x.y, beta.b[col + 1], e1);
+      }
+      double wv = 0, sv = 0;
+      if (valid) {
+        RowLatent r = impute_row<MODEL>(d, prm, out, obs, i, e0 + e1, err);
+        wv = r.w; sv = r.s;
+        sc_count += r.count; sc_ywy += r.yWy; sc_sumw += r.w; sc_sumlogw += r.sumlogw;
+      }
+      *reinterpret_cast<double2 *>(xs + lane * PADW + P8) = make_double2(wv, sv);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(my_drawn + slot);   // release: the (w, s) stores above are visible to the waiter
+    }
   }
+
+  // ---- CTA reduction: the four accumulate warps in warp order (deterministic), one partial per CTA
+  __syncthreads();  // every issued copy has been consumed: the ring is free
+  constexpr int TILE = P8 * P8 + P8;
+  double *tile = smem;
+  double *xty_s = smem + P8 * P8;
+  for (int e = tid; e < TILE; e += 32 * kWsWarps) smem[e] = 0.0;
+  if (is_acc) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      xty_acc[b] += __shfl_xor_sync(0xffffffffu, xty_acc[b], 1);
+      xty_acc[b] += __shfl_xor_sync(0xffffffffu, xty_acc[b], 2);
+    }
+  }
+  __syncthreads();
+  for (int w = 0; w < kWsAccWarps; ++w) {
+    if (wid == w) {
+      int a = 0;
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < NB; ++bj) {
+          double *t = tile + (8 * bi + (lane >> 2)) * P8 + 8 * bj + 2 * (lane & 3);
+          t[0] += c[a][0];
+          t[1] += c[a][1];
+          ++a;
+        }
+      if ((lane & 3) == 0) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) xty_s[8 * b + (lane >> 2)] += xty_acc[b];
+      }
+    }
+    __syncthreads();
+  }
+  double *my = partials + (int64_t)blockIdx.x * tma_partial_len(NB);
+  for (int e = tid; e < TILE; e += 32 * kWsWarps) my[e] = smem[e];
+  double v0 = warp_sum(sc_count), v1 = warp_sum(sc_ywy), v2 = warp_sum(sc_sumw), v3 = warp_sum(sc_sumlogw);
+  if (lane == 0) { red_s[wid * 4 + 0] = v0; red_s[wid * 4 + 1] = v1; red_s[wid * 4 + 2] = v2; red_s[wid * 4 + 3] = v3; }
+  __syncthreads();
+  if (tid < 4) {
+    double sum = 0;
+    for (int w = kWsAccWarps; w < kWsWarps; ++w) sum += red_s[w * 4 + tid];
+    my[P8 * P8 + P8 + tid] = sum;
+  }
+  if (tail.counter == nullptr) return;
+  __shared__ unsigned int ticket_s;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) ticket_s = atomicAdd(tail.counter, 1u);
+  __syncthreads();
+  if (ticket_s != gridDim.x - 1) return;
+  __threadfence();
+  sum_partials_tail<NB>(partials, (int)gridDim.x, d.p, tail, err, tid, 32 * kWsWarps);
   if (tid == 0) *tail.counter = 0u;
 }
 

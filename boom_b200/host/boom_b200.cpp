@@ -1251,4 +1251,56 @@ void PoissonRegressionSpikeSlabSampler::find_posterior_mode(double epsilon) {
   core_.find_posterior_mode(*model_, epsilon, &log_posterior_at_mode_);
 }
 
+// ---------------------------------------------------------------------------------------------
+BinomialProbitSpikeSlabSampler::BinomialProbitSpikeSlabSampler(BinomialProbitModel *model, const std::shared_ptr<MvnBase> &slab,
+                                                               const std::shared_ptr<VariableSelectionPrior> &spike, int clt_threshold,
+                                                               RNG &seeding_rng)
+    : PosteriorSampler(seeding_rng), model_(model), core_(slab, spike, true), suf_(model ? model->xdim() : 0),
+      clt_threshold_(clt_threshold) {
+  if (!model) report_error("BinomialProbitSpikeSlabSampler: null model");
+  if (slab->dim() != model->xdim() || spike->potential_nvars() != model->xdim()) report_error("Prior does not match model dimension.");
+  device_seed_ = seed_rng(rng());
+}
+void BinomialProbitSpikeSlabSampler::on_seed() { device_seed_ = seed_rng(rng()); iteration_ = 0; }
+double BinomialProbitSpikeSlabSampler::logpri() const { return core_.logpri(model_->coef()); }
+void BinomialProbitSpikeSlabSampler::refresh_xtx() { xtx_data_version_ = 0; }
+
+void BinomialProbitSpikeSlabSampler::draw() {
+  impute_latent_data();
+  core_.draw_model_indicators(rng(), model_->coef(), suf_);
+  core_.draw_beta(rng(), model_->coef(), suf_);
+}
+
+void BinomialProbitSpikeSlabSampler::impute_latent_data() {
+  DeviceData &dev(model_->device_data());
+  const int p = model_->xdim();
+  const bool want_xtx = xtx_data_version_ != model_->data_version();   // X'NX: once per data set
+  const uint64_t seed = device_seed_, it = iteration_++;
+  const Vector &beta(model_->Beta());
+  if (model_->allreduce()) {
+    const int64_t len = boomgpu_suf_len(p);
+    packed_.resize((size_t)len);
+    double *suf_dev = nullptr;
+    dev.check(boomgpu_suf_buffer(dev.ctx(), &suf_dev));
+    dev.check(boomgpu_probit_step_device(dev.ctx(), beta.data(), clt_threshold_, seed, it, suf_dev, want_xtx ? 0 : 1));
+    const size_t mat = (size_t)p * p;
+    if (want_xtx) {
+      model_->allreduce()(suf_dev, len);
+      dev.check(boomgpu_download(dev.ctx(), suf_dev, packed_.data(), len));
+      suf_.reset(packed_.data(), p);
+    } else {
+      model_->allreduce()(suf_dev + mat, p + 4);
+      dev.check(boomgpu_download(dev.ctx(), suf_dev + mat, packed_.data() + mat, p + 4));
+      std::copy(packed_.begin() + mat, packed_.begin() + mat + p, suf_.xty_storage());
+    }
+    suf_.set_scalars(packed_[mat + p], 0, 0, 0);
+  } else {
+    int64_t ss = 0;
+    dev.check(boomgpu_probit_step(dev.ctx(), beta.data(), clt_threshold_, seed, it, want_xtx ? suf_.xtx_storage(p) : nullptr,
+                                  suf_.xty_storage(), &ss));
+    suf_.set_scalars((double)ss, 0, 0, 0);
+  }
+  xtx_data_version_ = model_->data_version();
+}
+
 }  // namespace BOOM_B200

@@ -553,6 +553,45 @@ class PoissonRegressionSpikeSlabSampler : public PoissonRegressionAuxMixSampler 
   double log_posterior_at_mode_ = -1.0 / 0.0;
 };
 
+// ---- the probit sibling --------------------------------------------------------
+// BinomialProbitModel (Models/Glm/BinomialProbitModel.hpp): the same data as the logit model, probit link.  Only what the
+// sampler needs is provided here: the data, the coefficients, device residency.
+class BinomialProbitModel : public BinomialLogitModel {
+ public:
+  explicit BinomialProbitModel(int xdim, bool all = true) : BinomialLogitModel(xdim, all) {}
+  BinomialProbitModel(int64_t n, int p, const double *X, const double *y, const double *ntrials) : BinomialLogitModel(n, p, X, y, ntrials) {}
+};
+
+// BinomialProbitSpikeSlabSampler (Models/Glm/PosteriorSamplers/BinomialProbitSpikeSlabSampler.hpp:34-68, .cpp:30-92):
+// z_ij ~ N(x_i' beta, 1) truncated by the sign of trial j; the complete-data statistics are X'NX (N = diag(n_i): it does not
+// depend on beta and is computed ONCE, refresh_xtx) and X'z (one HBM-bound pass over X per iteration), followed by the
+// generic spike-and-slab steps with residual variance 1 (SpikeSlabSampler.cpp:40-216).
+class BinomialProbitSpikeSlabSampler : public PosteriorSampler {
+ public:
+  BinomialProbitSpikeSlabSampler(BinomialProbitModel *model, const std::shared_ptr<MvnBase> &slab,
+                                 const std::shared_ptr<VariableSelectionPrior> &spike, int clt_threshold = 10,
+                                 RNG &seeding_rng = GlobalRng::rng);
+  void draw() override;                 // .cpp:42-47
+  double logpri() const override;
+  void allow_model_selection(bool tf) { core_.allow_model_selection(tf); }
+  void limit_model_selection(int max_flips) { core_.limit_model_selection(max_flips); }
+  void impute_latent_data();            // .cpp:58-70: one device step
+  void refresh_xtx();                   // .cpp:72-78: the next impute_latent_data recomputes X'NX as well
+  WeightedRegSuf complete_data_sufficient_statistics() const { return suf_; }   // by value, as in the reference (.cpp:85-90)
+  int clt_threshold() const { return clt_threshold_; }
+
+ protected:
+  void on_seed() override;
+
+ private:
+  BinomialProbitModel *model_;
+  SpikeSlabCore core_;
+  WeightedRegSuf suf_;
+  int clt_threshold_;
+  uint64_t device_seed_, iteration_ = 0, xtx_data_version_ = 0;
+  Vector packed_;
+};
+
 // The logit mixture every BinomialLogit sampler uploads; defaults to the 9-component table of
 // Fruhwirth-Schnatter & Fruhwirth that the reference hard-codes (NormalMixtureApproximation.cpp:416-424);
 // the BOOM adapter overwrites it from the live BinomialLogitDataImputer::mixture_approximation.

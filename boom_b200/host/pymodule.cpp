@@ -143,6 +143,13 @@ PYBIND11_MODULE(_host, m) {
   blm.def("set_nonevent_sampling_prob", &BinomialLogitModel::set_nonevent_sampling_prob);
   bind_model_common(blm);
 
+  py::class_<BinomialProbitModel, BinomialLogitModel, std::shared_ptr<BinomialProbitModel>>(m, "BinomialProbitModel")
+      .def(py::init<int, bool>(), py::arg("xdim"), py::arg("all") = true)
+      .def(py::init([](const NpD &X, const NpD &y, const NpD &nt) {
+        if (X.ndim() != 2 || y.size() != X.shape(0) || nt.size() != X.shape(0)) report_error("BinomialProbitModel(X, y, n): shape mismatch");
+        return std::make_shared<BinomialProbitModel>((int64_t)X.shape(0), (int)X.shape(1), X.data(), y.data(), nt.data());
+      }));
+
   py::class_<PoissonRegressionModel, std::shared_ptr<PoissonRegressionModel>> prm(m, "PoissonRegressionModel");
   prm.def(py::init<int, bool>(), py::arg("xdim"), py::arg("all") = true)
       .def(py::init([](const NpD &X, const NpI &y, const NpD &e) {
@@ -219,6 +226,20 @@ PYBIND11_MODULE(_host, m) {
       .def_property_readonly("log_posterior_at_mode", &BinomialLogitSpikeSlabSampler::log_posterior_at_mode)
       .def("allow_model_selection", &BinomialLogitSpikeSlabSampler::allow_model_selection)
       .def("limit_model_selection", &BinomialLogitSpikeSlabSampler::limit_model_selection);
+
+  py::class_<BinomialProbitSpikeSlabSampler, PosteriorSampler, std::shared_ptr<BinomialProbitSpikeSlabSampler>>(
+      m, "BinomialProbitSpikeSlabSampler")
+      .def(py::init([](BinomialProbitModel *model, const std::shared_ptr<MvnBase> &slab,
+                       const std::shared_ptr<VariableSelectionPrior> &spike, int clt, RNG &rng) {
+             return std::make_shared<BinomialProbitSpikeSlabSampler>(model, slab, spike, clt, rng);
+           }),
+           py::arg("model"), py::arg("slab"), py::arg("spike"), py::arg("clt_threshold") = 10,
+           py::arg("seeding_rng") = std::ref(GlobalRng::rng), py::keep_alive<1, 2>())
+      .def("impute_latent_data", [](BinomialProbitSpikeSlabSampler &s) { py::gil_scoped_release rel; s.impute_latent_data(); })
+      .def("refresh_xtx", &BinomialProbitSpikeSlabSampler::refresh_xtx)
+      .def("complete_data_sufficient_statistics", &BinomialProbitSpikeSlabSampler::complete_data_sufficient_statistics)
+      .def("allow_model_selection", &BinomialProbitSpikeSlabSampler::allow_model_selection)
+      .def("limit_model_selection", &BinomialProbitSpikeSlabSampler::limit_model_selection);
 
   py::class_<PoissonRegressionAuxMixSampler, PosteriorSampler, std::shared_ptr<PoissonRegressionAuxMixSampler>>(
       m, "PoissonRegressionAuxMixSampler")

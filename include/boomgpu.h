@@ -72,8 +72,11 @@ int boomgpu_set_stream(boomgpu_ctx *ctx, void *cuda_stream);
 /* global index of this shard's first row: keys the Philox counters so draws do not depend on the sharding */
 int boomgpu_set_row_offset(boomgpu_ctx *ctx, uint64_t first_global_row);
 /* options: "path" = 0 auto | 1 fused single pass (p <= 64) | 2 two-pass imputer + DMMA SYRK;
- *          "small_variant" = 0 auto (TMA-fed kernel when X has an even leading dimension and a 16-byte aligned base) |
- *                            1 force the cp.async kernel;
+ *          "small_variant" = 0 auto (TMA-fed kernels when X has an even leading dimension and a 16-byte aligned base:
+ *                            warp-autonomous for p <= 40, warp-specialised above) | 1 force the cp.async kernel |
+ *                            2 the warp-autonomous TMA kernel for every p <= 64;
+ *          "single_launch" = 1 (default) the small-p step is one kernel whose last CTA sums the per-CTA partials | 0 a
+ *                            separate reduction kernel;
  *          "gather" = 0 auto (two-pass path: a beta with fewer than p / 4 non-zeros reads only those columns of X in the
  *                     imputer pass) | 1 never | 2 whenever beta has a zero;
  *          "timing" = 1 records CUDA events around every kernel (boomgpu_get_timings) */

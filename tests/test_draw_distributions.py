@@ -152,3 +152,31 @@ def test_device_poisson_draws(golden):
         ctx.close()
         return out
     check_poisson(draw, golden)
+
+
+@pytest.mark.gpu
+def test_device_probit_draws_follow_the_truncated_normal_law():
+    """The probit sibling's latent draws (one trial per row) against the exact N(eta, 1) law truncated by the response:
+    KS at 1e-6 per response class and linear-predictor bin (BinomialProbitDataImputer.cpp:55-66 draws the same law by rejection)."""
+    from scipy import stats
+    from oracle import oracle as O
+    from tests.helpers import logit_ctx
+    n, p = 200_000, 3
+    X = O.synth_x(n, p, seed=91)
+    X[:, 1] = np.repeat([-2.5, -0.7, 0.4, 3.0], n // 4)   # four linear predictors
+    X[:, 2] = 0.0
+    beta = np.array([0.2, 1.0, 0.0])
+    rng = np.random.default_rng(5)
+    y = (rng.random(n) < 0.5).astype(float)
+    nt = np.ones(n)
+    ctx, _ = logit_ctx(X, y, nt)
+    z = ctx.probit_draw(beta, 10, seed=17, iteration=1)
+    ctx.close()
+    eta = X @ beta
+    for e in np.unique(eta):
+        for resp in (0.0, 1.0):
+            sel = (eta == e) & (y == resp)
+            lo, hi = (0.0, np.inf) if resp else (-np.inf, 0.0)
+            law = stats.truncnorm(lo - e, hi - e, loc=e, scale=1.0)
+            assert np.all((z[sel] > lo) & (z[sel] < hi))
+            assert stats.kstest(z[sel], law.cdf).pvalue > 1e-6, (e, resp)

@@ -124,3 +124,12 @@ def test_composite_sampler_on_boom_models():
     inc = np.array(r["b200"]["inclusion"])
     assert np.all(inc[:4] > 0.9)
     assert r["time_report_lines"] >= 3
+
+
+def test_probit_sibling_on_boom_models():
+    """BinomialProbitSpikeSlabSampler on BOOM's BinomialProbitModel, binomial rows with n_i in {1, 2, 3, 15}:
+    reference vs B200 chains agree within Monte Carlo error."""
+    iters, burn = 8000, 1000
+    r = _demo("probit", 2500, 8, 3, iters, burn)
+    _agree(r, iters, burn, strong_only=True)
+    assert np.all(np.array(r["b200"]["inclusion"])[:4] > 0.9)

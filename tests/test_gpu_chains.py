@@ -227,3 +227,35 @@ def test_borrowed_host_rows_give_the_same_chain():
         out.append(_run(model, 20, 0))
         assert model.sample_size == 3000
     np.testing.assert_array_equal(out[0], out[1])
+
+
+def test_standalone_probit_sampler_recovers_the_coefficients():
+    """BinomialProbitModel + BinomialProbitSpikeSlabSampler through the Python surface: X'NX is computed once, every further
+    iteration is the X'z pass; the chain finds the true variables and their values."""
+    import boom_b200
+    from scipy import stats
+    rng = np.random.default_rng(3)
+    n, p = 20000, 10
+    X = rng.normal(size=(n, p))
+    X[:, 0] = 1.0
+    beta = np.zeros(p)
+    beta[:4] = [-0.5, 0.8, -0.6, 0.4]
+    nt = rng.integers(1, 4, size=n).astype(float)
+    y = rng.binomial(nt.astype(int), stats.norm.cdf(X @ beta)).astype(float)
+    model = boom_b200.BinomialProbitModel(X, y, nt)
+    s = boom_b200.BinomialProbitSpikeSlabSampler(model, boom_b200.MvnModel(np.zeros(p), np.eye(p)),
+                                                 boom_b200.VariableSelectionPrior(p, 0.3), 10, boom_b200.RNG(7))
+    model.set_method(s)
+    model.drop_all()
+    model.add(0)
+    draws = []
+    for it in range(600):
+        model.sample_posterior()
+        if it >= 100:
+            draws.append(np.array(model.Beta))
+    draws = np.array(draws)
+    suf = s.complete_data_sufficient_statistics()
+    np.testing.assert_allclose(np.array(suf.xtx), (X.T * nt) @ X, rtol=1e-11)
+    inc = np.mean(draws != 0, axis=0)
+    assert np.all(inc[:4] > 0.95) and np.all(inc[4:] < 0.3)
+    np.testing.assert_allclose(draws.mean(axis=0)[:4], beta[:4], atol=0.05)

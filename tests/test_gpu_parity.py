@@ -299,3 +299,24 @@ def test_matrix_lands_directly_in_page_locked_host_memory():
     np.testing.assert_array_equal(out, ref_xtx)
     np.testing.assert_array_equal(xty, ref_xty)
     ctx.close()
+
+
+# ---------------------------------------------------------------- probit sibling
+@pytest.mark.parametrize("n,p,max_trials,path", [(4000, 6, 1, 0), (3000, 20, 25, 0), (2500, 70, 1, 0), (2000, 130, 40, 0), (1500, 8, 3, 2)])
+def test_probit_step_matches_oracle(n, p, max_trials, path):
+    """BinomialProbitSpikeSlabSampler::impute_latent_data / refresh_xtx (BinomialProbitSpikeSlabSampler.cpp:58-83): per-row sums
+    of the latent normals value by value on the shared Philox stream, X'NX and X'z to 1e-12 / 1e-10; the X'z-only pass
+    (xtx not requested) gives the same X'z."""
+    X, y, nt, beta_true = O.synth_binomial(n, p, 3, seed=400 + p, max_trials=max_trials)
+    beta = beta_true * 0.6
+    ctx, _ = logit_ctx(X, y, nt, path=path)
+    draws = ctx.probit_draw(beta, 10, seed=5, iteration=2)
+    rxtx, rxtz, rdraws = O.probit_step(X, y, nt, beta, 10, 5, 2)
+    np.testing.assert_allclose(draws, rdraws, rtol=1e-9, atol=1e-9)
+    xtx, xtz, ss = ctx.probit_step(beta, 10, seed=5, iteration=2)
+    assert ss == n
+    assert normwise_err(xtx, rxtx) < TOL
+    assert vec_err(xtz, rxtz) < 1e-10
+    _, xtz2, ss2 = ctx.probit_step(beta, 10, seed=5, iteration=2, want_xtx=False)
+    assert ss2 == n and vec_err(xtz2, rxtz) < 1e-10
+    ctx.close()
