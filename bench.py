@@ -302,7 +302,7 @@ class Bench:
         mean[0] = np.log(ph / (1 - ph))
         return mean, G.cpu().numpy()
 
-    def build(self, model, kind, sampler, n, p, nonzero, prior_mean, prior_prec):
+    def build(self, model, kind, sampler, n, p, nonzero, prior_mean, prior_prec, active=False):
         import numpy as np
 
         import boom_b200
@@ -317,6 +317,7 @@ class Bench:
             model.add(0)   # chains start with only the intercept (GlmCoefs(p, all=false), as R's InitializeCoefficients does)
             spike = boom_b200.VariableSelectionPrior(p, min(1.0, max(nonzero, 1) / p))
             s = boom_b200.BinomialLogitSpikeSlabSampler(model, prior, spike, 10, rng)
+            s.set_active_set_statistics(bool(active))
         elif kind == "logit":
             s = boom_b200.BinomialLogitAuxmixSampler(model, prior, 10, rng)
         else:
@@ -329,7 +330,7 @@ class Bench:
         return s
 
     # ---- one workload: device-resident leg (+ optional host-array leg)
-    def run(self, name, steps, warmup, e2e, n_override=0):
+    def run(self, name, steps, warmup, e2e, n_override=0, active=False):
         import numpy as np
 
         import boom_b200
@@ -352,7 +353,10 @@ class Bench:
         Model = boom_b200.BinomialLogitModel if kind == "logit" else boom_b200.PoissonRegressionModel
         model = Model(p)
         model.adopt_device_data(row1 - row0, X.data_ptr(), p, y.data_ptr(), aux.data_ptr())
-        smp = self.build(model, kind, sampler, n, p, nonzero, pm, pp)
+        smp = self.build(model, kind, sampler, n, p, nonzero, pm, pp, active)
+        if active:
+            cfg["statistics"] = ("ACTIVE-SET option (set_active_set_statistics): X'WX for the included columns + diagonal + X'Wz per "
+                                 "iteration, further columns fetched on accepted adds; same chain as the full matrix")
         for _ in range(warmup):
             model.sample_posterior()
         self.barrier()
@@ -383,7 +387,14 @@ class Bench:
         # roofline of the dominant kernel; per-rank rows, this rank's launches
         my_rows = row1 - row0
         per = {k: (v[0] / max(v[1], 1), v[1]) for k, v in tm.items()}
-        if p > 64:
+        if p > 64 and active:
+            # one read of X per iteration bounds this form: 8 n (p + 2) algorithmic bytes against the HBM roof
+            k_ms = per["syrk_dmma"][0]
+            nbytes = 8.0 * my_rows * (p + 2)
+            roof = {"kernel": "panel_dmma_kernel", "bound": "hbm", "achieved": nbytes / (k_ms * 1e-3) * 1e-9, "peak": self.peaks["hbm_gbs"],
+                    "unit": "GB/s", "peak_source": self.peak_src, "algorithmic_bytes_per_launch": nbytes,
+                    "columns_fetched_in_timed_region": int(smp.active_set_columns_fetched)}
+        elif p > 64:
             k_ms = per["syrk_dmma"][0]
             flops = float(my_rows) * p * (p + 1) + 2.0 * my_rows * p   # weighted SYRK (upper triangle) + X'Wz, FMA = 2
             roof = {"kernel": "syrk_dmma_kernel", "bound": "tensor", "achieved": flops / (k_ms * 1e-3) * 1e-12,
@@ -422,7 +433,7 @@ class Bench:
             model = Model(p)
             model.borrow_host_data(Xh, yh, ah)   # the rows stay in this process's host arrays; uploaded by the first draw
             nbytes_up = Xh.nbytes + yh.nbytes + ah.nbytes
-            smp = self.build(model, kind, sampler, n, p, nonzero, pm, pp)
+            smp = self.build(model, kind, sampler, n, p, nonzero, pm, pp, active)
             self.barrier()
             tu = time.perf_counter()
             model.sample_posterior()     # packs and uploads the rows (once), then the first iteration
@@ -579,6 +590,7 @@ def main():
     ap.add_argument("--no-selftest", action="store_true", help="skip the N > 1 parity check before timing")
     ap.add_argument("--torch-allreduce", action="store_true",
                     help="all-reduce through a torch.distributed hook instead of the library's own NCCL communicator")
+    ap.add_argument("--active-set", action="store_true", help="headline workload with the active-set statistics option (development aid)")
     ap.add_argument("--rows", type=int, default=0, help="override n (development aid; the line then names the override)")
     ap.add_argument("--option", type=parse_option, action="append", default=[], help="boomgpu option name=value (development aid)")
     args = ap.parse_args()
@@ -618,7 +630,7 @@ def main():
     st = None
     if world > 1 and not args.no_selftest:
         st = b.selftest(args.workload)
-    head = b.run(args.workload, steps, warmup, e2e=not args.no_e2e, n_override=args.rows)
+    head = b.run(args.workload, steps, warmup, e2e=not args.no_e2e, n_override=args.rows, active=args.active_set)
     secondary = {}
     if not args.no_secondary and not args.rows:
         # (name, steps, warm-up, e2e leg).  C1: 1000 iterations.  e2e only where the host copy of the rows is small.
@@ -628,6 +640,9 @@ def main():
             if nm == args.workload:
                 continue
             secondary[nm] = b.run(nm, k, w, e2e=e)
+        # the optional active-set form of the spike-and-slab configs: same chain, fewer flops
+        secondary["c3_active_set"] = b.run("c3", 20, 25, e2e=False, active=True)
+        secondary["c4_active_set"] = b.run("c4", 10, 45, e2e=False, active=True)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_block(kind, sampler, n, p, nonzero)

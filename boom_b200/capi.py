@@ -19,7 +19,8 @@ SYMBOLS = (
     "boomgpu_create", "boomgpu_destroy", "boomgpu_last_error", "boomgpu_version", "boomgpu_set_stream",
     "boomgpu_set_row_offset", "boomgpu_set_option", "boomgpu_upload_binomial", "boomgpu_upload_poisson",
     "boomgpu_upload_begin", "boomgpu_upload_rows", "boomgpu_upload_end", "boomgpu_adopt_binomial", "boomgpu_adopt_poisson", "boomgpu_set_logit_mixture", "boomgpu_set_poisson_table",
-    "boomgpu_logit_step", "boomgpu_poisson_step", "boomgpu_probit_step", "boomgpu_probit_step_device", "boomgpu_probit_draw", "boomgpu_suf_len", "boomgpu_logit_step_device",
+    "boomgpu_logit_step", "boomgpu_poisson_step", "boomgpu_logit_step_active", "boomgpu_poisson_step_active",
+    "boomgpu_weighted_column", "boomgpu_full_statistics", "boomgpu_probit_step", "boomgpu_probit_step_device", "boomgpu_probit_draw", "boomgpu_suf_len", "boomgpu_logit_step_device",
     "boomgpu_poisson_step_device", "boomgpu_synchronize", "boomgpu_suf_buffer", "boomgpu_download", "boomgpu_accumulate", "boomgpu_logit_draw",
     "boomgpu_poisson_draw", "boomgpu_binomial_loglike", "boomgpu_poisson_loglike", "boomgpu_binomial_loglike_derivs",
     "boomgpu_poisson_loglike_derivs", "boomgpu_binomial_loglike_derivs_device", "boomgpu_poisson_loglike_derivs_device",
@@ -227,6 +228,39 @@ class Context:
         self._check(self._lib.boomgpu_poisson_step(self._h, _dp(beta), C.c_uint64(seed), C.c_uint64(iteration), _dp(xtx),
                                                    _dp(xty), _dp(sc)))
         return xtx, xty, sc
+
+    def logit_step_active(self, beta, clt_threshold, seed, iteration, active):
+        """(G p x k, diag p, xty p, sample_size): the columns `active` of X'WX, its diagonal and X'Wz."""
+        p = self.p
+        beta = _f64(beta)
+        act = np.ascontiguousarray(active, dtype=np.int32)
+        k = len(act)
+        G, diag, xty = np.empty((p, k)), np.empty(p), np.empty(p)
+        ss = C.c_int64()
+        self._check(self._lib.boomgpu_logit_step_active(self._h, _dp(beta), C.c_int(clt_threshold), C.c_uint64(seed), C.c_uint64(iteration),
+                                                        act.ctypes.data_as(c_i32_p), C.c_int(k), _dp(G), _dp(diag), _dp(xty), C.byref(ss)))
+        return G, diag, xty, ss.value
+
+    def poisson_step_active(self, beta, seed, iteration, active):
+        p = self.p
+        beta = _f64(beta)
+        act = np.ascontiguousarray(active, dtype=np.int32)
+        k = len(act)
+        G, diag, xty, sc = np.empty((p, k)), np.empty(p), np.empty(p), np.empty(4)
+        self._check(self._lib.boomgpu_poisson_step_active(self._h, _dp(beta), C.c_uint64(seed), C.c_uint64(iteration),
+                                                          act.ctypes.data_as(c_i32_p), C.c_int(k), _dp(G), _dp(diag), _dp(xty), _dp(sc)))
+        return G, diag, xty, sc
+
+    def weighted_column(self, j):
+        out = np.empty(self.p)
+        self._check(self._lib.boomgpu_weighted_column(self._h, C.c_int(int(j)), _dp(out)))
+        return out
+
+    def full_statistics(self):
+        p = self.p
+        xtx, xty = np.empty((p, p)), np.empty(p)
+        self._check(self._lib.boomgpu_full_statistics(self._h, _dp(xtx), _dp(xty)))
+        return xtx, xty
 
     def probit_step(self, beta, clt_threshold, seed, iteration, want_xtx=True):
         """(xtx or None, xtz, sample_size) of the probit sibling; want_xtx=False computes X'z alone."""

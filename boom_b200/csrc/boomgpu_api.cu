@@ -54,6 +54,13 @@ struct boomgpu_ctx {
   const double *sel_src = nullptr;   // the X it was gathered from (a new upload / adoption invalidates it)
   int *sel_cols_dev = nullptr; int sel_cols_cap = 0;
 
+  // active-set statistics: [G p x ka8 | diag p | xty p | 4 scalars] on the device and in pinned host memory
+  double *act_dev = nullptr; int64_t act_cap = 0;
+  double *act_pin = nullptr; int64_t act_pin_cap = 0;
+  double *col_buf = nullptr; int64_t col_cap = 0;   // w o x_j for boomgpu_weighted_column
+  int stats_mode = 0;                                 // 1 while an active-set step runs its imputer pass
+  bool latents_valid = false;                         // w_buf / s_buf hold the latents of the last two-pass step
+
   // mixtures
   LogitMixture mix{};        // host copy
   LogitHot hot{};
@@ -88,7 +95,7 @@ struct boomgpu_ctx {
   struct XMap {
     CUtensorMap map;
     const double *X = nullptr; int64_t n = -1, ldx = -1; int p = -1, box_cols = -1, box_rows = -1;
-  } xmap_small, xmap_syrk;
+  } xmap_small, xmap_syrk, xmap_sel;
 
   bool host_out_written = false;   // the last step's reduction wrote the statistics straight into suf_pin (zero copy)
 
@@ -149,6 +156,7 @@ void free_data(boomgpu_ctx *ctx) {
   if (ctx->Xt_owned) { cudaFree(ctx->Xt_owned); ctx->Xt_owned = nullptr; }
   ctx->Xt = nullptr; ctx->ldxt = 0;
   ctx->n = 0; ctx->p = 0; ctx->model = -1; ctx->upload_kind = -1;
+  ctx->latents_valid = false;
 }
 
 // ---- launch bookkeeping -------------------------------------------------------------------
@@ -430,11 +438,11 @@ struct WsLauncher {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (int rc = ensure_xmap(ctx, ctx->xmap_small, ctx->X, ctx->ldx, tma_padw(NB), 32)) return rc;
     const int64_t nslices = (d.n + 31) / 32;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nslices + kWsAccWarps - 1) / kWsAccWarps, (int64_t)ctx->sms));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nslices + kWsRings - 1) / kWsRings, (int64_t)ctx->sms));
     if (ensure(ctx, &ctx->partials, &ctx->partials_cap, (int64_t)grid * tma_partial_len(NB))) return BOOMGPU_ERR_CUDA;
     {
       LaunchScope ls(ctx, 0);
-      kern<<<grid, 32 * ws_warps(NB), smem, ctx->stream>>>(ctx->xmap_small.map, d, prm, out, bp, ctx->partials, ctx->err_dev, tail);
+      kern<<<grid, 32 * kWsWarps, smem, ctx->stream>>>(ctx->xmap_small.map, d, prm, out, bp, ctx->partials, ctx->err_dev, tail);
     }
     CU(cudaGetLastError());
     *nparts = grid;
@@ -543,20 +551,19 @@ int launch_syrk(boomgpu_ctx *ctx, double *suf) {
   return 0;
 }
 
-// X's alone into suf[p*p .. p*p + p) (the matrix part is zeroed: it is not recomputed)
-int launch_xts(boomgpu_ctx *ctx, double *suf) {
+// out[0 .. p) = X' svec (svec: n doubles on the device)
+int launch_xts_vec(boomgpu_ctx *ctx, const double *svec, double *out) {
   const int p = ctx->p;
   const int p2 = (p + 1) / 2;
   const int pairs = (p2 + kXtsThreads - 1) / kXtsThreads;
   if (pairs > kXtsMaxPairs) return fail(ctx, BOOMGPU_ERR_ARG, "p = %d is too wide for the X's kernel", p);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->n + 255) / 256, (int64_t)ctx->sms * 4));
   if (ensure(ctx, &ctx->partials, &ctx->partials_cap, (int64_t)grid * 2 * p2)) return BOOMGPU_ERR_CUDA;
-  CU(cudaMemsetAsync(suf, 0, sizeof(double) * (size_t)p * p, ctx->stream));
   {
     LaunchScope ls(ctx, 2);
     auto go = [&](auto tag) {
       constexpr int P = decltype(tag)::value;
-      xts_kernel<P><<<grid, kXtsThreads, 0, ctx->stream>>>(ctx->Xt, ctx->ldxt, ctx->n, p, ctx->s_buf, ctx->partials);
+      xts_kernel<P><<<grid, kXtsThreads, 0, ctx->stream>>>(ctx->Xt, ctx->ldxt, ctx->n, p, svec, ctx->partials);
     };
     if (pairs <= 1) go(std::integral_constant<int, 1>());
     else if (pairs <= 2) go(std::integral_constant<int, 2>());
@@ -568,9 +575,76 @@ int launch_xts(boomgpu_ctx *ctx, double *suf) {
   CU(cudaGetLastError());
   {
     LaunchScope ls(ctx, 3);
-    reduce_xts_kernel<<<(p + 255) / 256, 256, 0, ctx->stream>>>(ctx->partials, grid, p, suf + (int64_t)p * p);
+    reduce_xts_kernel<<<(p + 255) / 256, 256, 0, ctx->stream>>>(ctx->partials, grid, p, out);
   }
   CU(cudaGetLastError());
+  return 0;
+}
+
+// X's alone into suf[p*p .. p*p + p) (the matrix part is zeroed: it is not recomputed)
+int launch_xts(boomgpu_ctx *ctx, double *suf) {
+  CU(cudaMemsetAsync(suf, 0, sizeof(double) * (size_t)ctx->p * ctx->p, ctx->stream));
+  return launch_xts_vec(ctx, ctx->s_buf, suf + (int64_t)ctx->p * ctx->p);
+}
+
+// G = X' diag(w) X_A, diag, X's from the latents in w_buf / s_buf: [G p x ka8 | diag p | xty p] at out (device)
+int launch_panel(boomgpu_ctx *ctx, double *out, int *ka8_out) {
+  const int k = (int)ctx->sel_cols.size();
+  static const int sizes[] = {1, 2, 3, 4, 6, 8, 12, 16};
+  int nba = 0;
+  for (int v : sizes) if (8 * v >= k) { nba = v; break; }
+  if (!nba) return fail(ctx, BOOMGPU_ERR_ARG, "active set of %d columns exceeds the supported 128", k);
+  PanelParams pp;
+  pp.n = ctx->n; pp.p = ctx->p; pp.nblk = (ctx->p + 127) / 128; pp.ka8 = 8 * nba;
+  pp.w = ctx->w_buf; pp.s = ctx->s_buf;
+  int64_t ksplit = (8 * (int64_t)ctx->sms + pp.nblk - 1) / pp.nblk;
+  ksplit = std::max<int64_t>(1, std::min<int64_t>(ksplit, std::max<int64_t>(1, ctx->n / 2048)));
+  int64_t rows = (ctx->n + ksplit - 1) / ksplit;
+  rows = ((rows + kSyrkKB - 1) / kSyrkKB) * kSyrkKB;
+  ksplit = std::max<int64_t>(1, (ctx->n + rows - 1) / rows);
+  pp.ksplit = (int)ksplit; pp.rows_per_slice = rows;
+  if (ensure(ctx, &ctx->partials, &ctx->partials_cap, ksplit * pp.nblk * kPanelTileLen)) return BOOMGPU_ERR_CUDA;
+  pp.partials = ctx->partials;
+  if (int rc = ensure_xmap(ctx, ctx->xmap_syrk, ctx->Xt, ctx->ldxt, kSyrkPanelLd, kSyrkKB)) return rc;
+  {   // the gathered matrix as a tensor {k columns, n rows}: the box is wider than k, the excess reads as zero
+    boomgpu_ctx::XMap &m = ctx->xmap_sel;
+    const int p_save = ctx->p;
+    ctx->p = k;
+    const int rc = ensure_xmap(ctx, m, ctx->Xsel, ctx->sel_ld, 8 * nba + 4, kSyrkKB);
+    ctx->p = p_save;
+    if (rc) return rc;
+  }
+  const unsigned grid = (unsigned)(ksplit * pp.nblk);
+  {
+    LaunchScope ls(ctx, 2);
+    auto go = [&](auto tag) -> cudaError_t {
+      constexpr int NBA = decltype(tag)::value;
+      cudaError_t e = cudaFuncSetAttribute(panel_dmma_kernel<NBA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmemBytes);
+      if (e != cudaSuccess) return e;
+      panel_dmma_kernel<NBA><<<grid, kSyrkThreads, kSyrkSmemBytes, ctx->stream>>>(ctx->xmap_syrk.map, ctx->xmap_sel.map, pp);
+      return cudaGetLastError();
+    };
+    cudaError_t e;
+    switch (nba) {
+      case 1: e = go(std::integral_constant<int, 1>()); break;
+      case 2: e = go(std::integral_constant<int, 2>()); break;
+      case 3: e = go(std::integral_constant<int, 3>()); break;
+      case 4: e = go(std::integral_constant<int, 4>()); break;
+      case 6: e = go(std::integral_constant<int, 6>()); break;
+      case 8: e = go(std::integral_constant<int, 8>()); break;
+      case 12: e = go(std::integral_constant<int, 12>()); break;
+      default: e = go(std::integral_constant<int, 16>()); break;
+    }
+    if (e != cudaSuccess) return fail(ctx, BOOMGPU_ERR_CUDA, "panel_dmma_kernel launch failed: %s", cudaGetErrorString(e));
+  }
+  {
+    LaunchScope ls(ctx, 3);
+    const int64_t total = (int64_t)pp.nblk * 128 * (pp.ka8 + 2);
+    reduce_panel_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, ctx->stream>>>(
+        pp, out, out + (int64_t)ctx->p * pp.ka8, out + (int64_t)ctx->p * pp.ka8 + ctx->p);
+  }
+  CU(cudaGetLastError());
+  *ka8_out = pp.ka8;
   return 0;
 }
 
@@ -619,13 +693,14 @@ int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, c
     return 0;
   }
   if (path == 1) {
+    ctx->latents_valid = false;
     int nparts = 0;
     const int nb = (p + 7) / 8;
     bool reduced = false;
     if (tma_small) {
       // TMA-fed warp-autonomous kernel (fused_tma.cuh); single launch: its last CTA also sums the partials
       TailParams tail{suf, host_out, ctx->single_launch ? ctx->tail_counter : nullptr};
-      if (nb >= 5 && ctx->small_variant != 2) {   // wide tiles: accumulate warps + draw warps
+      if (nb >= 5 && ctx->small_variant == 3) {   // wide tiles, opt-in: accumulate warps + draw warps (fused_ws_kernel)
         if (int rc = WsLauncher<MODEL>::dispatch(ctx, nb, d, prm, out, &nparts, tail)) return rc;
       } else if (int rc = TmaLauncher<MODEL>::dispatch(ctx, nb, d, prm, out, &nparts, tail)) return rc;
       reduced = tail.counter != nullptr;
@@ -658,6 +733,8 @@ int run_step(boomgpu_ctx *ctx, const double *beta_host, const DrawParams &prm, c
       reduce_scalars_kernel<<<1, 32, 0, ctx->stream>>>(ctx->scal_partials, nparts, suf + (int64_t)p * p + p);
     }
     CU(cudaGetLastError());
+    ctx->latents_valid = MODEL != kSupplied;
+    if (ctx->stats_mode == 1) return 0;   // active-set step: the caller launches the panel product
     if (ctx->xty_only && MODEL == kProbit) { if (int rc = launch_xts(ctx, suf)) return rc; }
     else if (int rc = launch_syrk(ctx, suf)) return rc;
   }
@@ -828,6 +905,45 @@ int loglike_derivs_device_impl(boomgpu_ctx *ctx, int model, const double *beta, 
 }
 
 // Runs f with the context looking at X_gamma (n x k) instead of X, then restores it.
+template <int MODEL>
+int step_active_impl(boomgpu_ctx *ctx, int model, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
+                            const int32_t *active, int k, double *G, double *diag, double *xty, double scalars[4]) {
+  if (int rc = check_ready(ctx, model)) return rc;
+  if (!beta || !active || k < 1 || !G || !diag || !xty) return fail(ctx, BOOMGPU_ERR_ARG, "null / empty argument");
+  if (ctx->p <= 64) return fail(ctx, BOOMGPU_ERR_ARG, "the active-set step is for p > 64 (p = %d runs the single-pass kernel)", ctx->p);
+  if (k > 128) return fail(ctx, BOOMGPU_ERR_ARG, "active set of %d columns exceeds the supported 128", k);
+  DeviceGuard g(ctx->device);
+  if (int rc = boomgpu_select_columns(ctx, active, k)) return rc;
+  if (int rc = ensure_suf(ctx)) return rc;
+  const int p = ctx->p;
+  const int64_t cap = (int64_t)p * 128 + 2 * (int64_t)p + 4;
+  if (ensure(ctx, &ctx->act_dev, &ctx->act_cap, cap)) return BOOMGPU_ERR_CUDA;
+  if (ctx->act_pin_cap < cap) {
+    if (ctx->act_pin) { CU(cudaFreeHost(ctx->act_pin)); ctx->act_pin = nullptr; }
+    CU(cudaMallocHost((void **)&ctx->act_pin, sizeof(double) * (size_t)cap));
+    ctx->act_pin_cap = cap;
+  }
+  RowOut out{nullptr, nullptr, nullptr, nullptr};
+  const int path_save = ctx->path;
+  ctx->path = 2; ctx->stats_mode = 1;
+  int rc = run_step<MODEL>(ctx, beta, make_prm(ctx, clt_threshold, seed, iteration), out, nullptr, nullptr, ctx->suf_dev);
+  ctx->path = path_save; ctx->stats_mode = 0;
+  if (rc) return rc;
+  int ka8 = 0;
+  if ((rc = launch_panel(ctx, ctx->act_dev, &ka8))) return rc;
+  const int64_t len = (int64_t)p * ka8 + 2 * (int64_t)p;
+  // the four scalars of the imputer pass sit at suf_dev[p*p + p ..]: bring them behind the panel result
+  CU(cudaMemcpyAsync(ctx->act_dev + len, ctx->suf_dev + (int64_t)p * p + p, sizeof(double) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  if ((rc = allreduce_on_stream(ctx, ctx->act_dev, len + 4))) return rc;
+  CU(cudaMemcpyAsync(ctx->act_pin, ctx->act_dev, sizeof(double) * (size_t)(len + 4), cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = finish_and_check(ctx))) return rc;
+  for (int j = 0; j < p; ++j) memcpy(G + (size_t)j * k, ctx->act_pin + (size_t)j * ka8, sizeof(double) * k);
+  memcpy(diag, ctx->act_pin + (size_t)p * ka8, sizeof(double) * p);
+  memcpy(xty, ctx->act_pin + (size_t)p * ka8 + p, sizeof(double) * p);
+  if (scalars) memcpy(scalars, ctx->act_pin + len, sizeof(double) * 4);
+  return 0;
+}
+
 template <class F>
 int with_selected_columns(boomgpu_ctx *ctx, F f) {
   if (!ctx->Xsel || ctx->sel_src != ctx->X || ctx->sel_cols.empty())
@@ -899,6 +1015,7 @@ void boomgpu_destroy(boomgpu_ctx *ctx) {
   cudaFree(ctx->partials); cudaFree(ctx->scal_partials);
   cudaFree(ctx->w_buf); cudaFree(ctx->s_buf);
   cudaFree(ctx->Xsel); cudaFree(ctx->sel_cols_dev);
+  cudaFree(ctx->act_dev); cudaFreeHost(ctx->act_pin); cudaFree(ctx->col_buf);
   cudaFree(ctx->err_dev); cudaFreeHost(ctx->err_pin); cudaFree(ctx->tail_counter);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -938,7 +1055,7 @@ int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value) {
     return 0;
   }
   if (!strcmp(name, "small_variant")) {
-    if (value < 0 || value > 2) return fail(ctx, BOOMGPU_ERR_ARG, "small_variant must be 0, 1 or 2");
+    if (value < 0 || value > 3) return fail(ctx, BOOMGPU_ERR_ARG, "small_variant must be 0, 1, 2 or 3");
     ctx->small_variant = (int)value;
     return 0;
   }
@@ -1339,6 +1456,64 @@ int boomgpu_poisson_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, ui
   if (!in_place) memcpy(xtwx, ctx->suf_pin, sizeof(double) * (size_t)p * p);
   memcpy(xtwy, ctx->suf_pin + (size_t)p * p, sizeof(double) * p);
   if (scalars) memcpy(scalars, ctx->suf_pin + (size_t)p * p + p, sizeof(double) * 4);
+  return 0;
+}
+
+// ---- active-set statistics ----------------------------------------------------------------------------
+int boomgpu_logit_step_active(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
+                              const int32_t *active, int k, double *G, double *diag, double *xty, int64_t *sample_size) {
+  if (ctx) if (int rc = check_clt(ctx, clt_threshold)) return rc;
+  double sc[4] = {0, 0, 0, 0};
+  const int rc = step_active_impl<kLogit>(ctx, kLogit, beta, clt_threshold, seed, iteration, active, k, G, diag, xty, sc);
+  if (!rc && sample_size) *sample_size = (int64_t)llround(sc[0]);
+  return rc;
+}
+int boomgpu_poisson_step_active(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, const int32_t *active, int k,
+                                double *G, double *diag, double *xty, double scalars[4]) {
+  return step_active_impl<kPoisson>(ctx, kPoisson, beta, 0, seed, iteration, active, k, G, diag, xty, scalars);
+}
+
+int boomgpu_weighted_column(boomgpu_ctx *ctx, int j, double *column) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (!ctx->X || !ctx->latents_valid) return fail(ctx, BOOMGPU_ERR_STATE, "no latents on the device: run a two-pass / active-set step first");
+  if (j < 0 || j >= ctx->p || !column) return fail(ctx, BOOMGPU_ERR_ARG, "bad column request");
+  DeviceGuard g(ctx->device);
+  if (ensure(ctx, &ctx->col_buf, &ctx->col_cap, std::max<int64_t>(ctx->n, 1))) return BOOMGPU_ERR_CUDA;
+  const int p = ctx->p;
+  if (ensure(ctx, &ctx->act_dev, &ctx->act_cap, (int64_t)p * 128 + 2 * (int64_t)p + 4)) return BOOMGPU_ERR_CUDA;
+  if (ctx->act_pin_cap < p) {
+    if (ctx->act_pin) { CU(cudaFreeHost(ctx->act_pin)); ctx->act_pin = nullptr; }
+    CU(cudaMallocHost((void **)&ctx->act_pin, sizeof(double) * ((size_t)p * 128 + 2 * (size_t)p + 4)));
+    ctx->act_pin_cap = (int64_t)p * 128 + 2 * (int64_t)p + 4;
+  }
+  {
+    LaunchScope ls(ctx, 4);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->n + 255) / 256, (int64_t)ctx->sms * 8));
+    weight_column_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->Xt, ctx->ldxt, ctx->n, j, ctx->w_buf, ctx->col_buf);
+  }
+  CU(cudaGetLastError());
+  if (int rc = launch_xts_vec(ctx, ctx->col_buf, ctx->act_dev)) return rc;
+  if (int rc = allreduce_on_stream(ctx, ctx->act_dev, p)) return rc;
+  CU(cudaMemcpyAsync(ctx->act_pin, ctx->act_dev, sizeof(double) * (size_t)p, cudaMemcpyDeviceToHost, ctx->stream));
+  if (int rc = finish_and_check(ctx)) return rc;
+  memcpy(column, ctx->act_pin, sizeof(double) * p);
+  return 0;
+}
+
+int boomgpu_full_statistics(boomgpu_ctx *ctx, double *xtx, double *xty) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (!ctx->X || !ctx->latents_valid) return fail(ctx, BOOMGPU_ERR_STATE, "no latents on the device: run a two-pass / active-set step first");
+  if (!xtx || !xty) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
+  DeviceGuard g(ctx->device);
+  if (int rc = ensure_suf(ctx)) return rc;
+  ctx->host_out_written = false;
+  if (int rc = launch_syrk(ctx, ctx->suf_dev)) return rc;
+  const int p = ctx->p;
+  if (int rc = allreduce_on_stream(ctx, ctx->suf_dev, (int64_t)p * p + p)) return rc;
+  bool in_place = false;
+  if (int rc = fetch_suf(ctx, xtx, &in_place)) return rc;
+  if (!in_place) memcpy(xtx, ctx->suf_pin, sizeof(double) * (size_t)p * p);
+  memcpy(xty, ctx->suf_pin + (size_t)p * p, sizeof(double) * p);
   return 0;
 }
 

@@ -119,6 +119,17 @@ struct PoissonTable {
   int e1;  // entry index of nu == 1 (every row uses it)
 };
 
+// The table entries of the small counts (nu < 32: K = 10 or 4 components each), staged in SHARED memory by kernels that
+// have room for them.  Per-row nu makes the lookups divergent; in global memory every draw walks a chain of dependent
+// loads (dense index -> offsets -> components -> selected component): ~16 k cycles per 32-row slice at C2.
+constexpr int kPoisSmemNu = 32, kPoisSmemComps = 320;
+struct PoissonSmem {
+  int off[kPoisSmemNu + 1];              // components of nu: off[nu] .. off[nu + 1] - 1 (empty: nu not in the table)
+  float mu_f[kPoisSmemComps], lconst2_f[kPoisSmemComps], hs2_f[kPoisSmemComps];
+  double center[kPoisSmemNu];            // mu of the entry's first component (the FP32 residual is centred on it)
+  double mu[kPoisSmemComps], inv_sigsq[kPoisSmemComps], logw[kPoisSmemComps];
+};
+
 // NormalMixtureApproximation::unmix given its uniform.  The reference normalises the
 // probabilities before rmulti_mt draws v ~ U(0, sum); selecting on the unnormalised
 // cumulative sums with v = U * sum is the same event.
@@ -642,6 +653,56 @@ __device__ __forceinline__ void unmix_poisson_ext(const LogitHot &h, const Poiss
   mu = h.mu_d[k]; weight = h.inv_sigsq[k]; logw = h.logw[k]; kout = k;
 }
 
+// cooperative fill of the shared-memory copy (all threads of the CTA; the caller synchronises afterwards)
+__device__ __forceinline__ void poisson_smem_fill(PoissonSmem *ps, const PoissonTable &t, int tid, int nthreads) {
+  if (tid == 0) {
+    int pos = 0;
+    for (int nu = 0; nu < kPoisSmemNu; ++nu) {
+      ps->off[nu] = pos;
+      const int e = nu < t.dense_n ? __ldg(t.dense + nu) : -1;
+      if (e >= 0) {
+        const int a = __ldg(t.offset + e), K = __ldg(t.offset + e + 1) - a;
+        if (K <= kMaxLogitK && pos + K <= kPoisSmemComps) { ps->center[nu] = __ldg(t.mu + a); pos += K; }
+      }
+    }
+    ps->off[kPoisSmemNu] = pos;
+  }
+  __syncthreads();
+  for (int nu = tid; nu < kPoisSmemNu; nu += nthreads) {
+    const int K = ps->off[nu + 1] - ps->off[nu];
+    if (K > 0) {
+      const int a = __ldg(t.offset + __ldg(t.dense + nu)), b = ps->off[nu];
+      for (int k = 0; k < K; ++k) {
+        ps->mu_f[b + k] = __ldg(t.mu_f + a + k); ps->lconst2_f[b + k] = __ldg(t.lconst2_f + a + k); ps->hs2_f[b + k] = __ldg(t.hs2_f + a + k);
+        ps->mu[b + k] = __ldg(t.mu + a + k); ps->inv_sigsq[b + k] = __ldg(t.inv_sigsq + a + k); ps->logw[b + k] = __ldg(t.logw + a + k);
+      }
+    }
+  }
+}
+
+// unmix against the shared-memory copy of entry nu (nu < kPoisSmemNu, entry present); the FP64 fallback reads global memory
+__device__ __forceinline__ bool unmix_poisson_smem(const PoissonSmem *ps, const PoissonTable &t, int nu, double resid, double unif,
+                                                   double &mu, double &weight, double &logw, int &kout) {
+  const int b = ps->off[nu], K = ps->off[nu + 1] - b;
+  if (K <= 0) return false;
+  int k;
+  auto mu_of = [&](int s) { return ps->mu_f[b + s]; };
+  auto lc_of = [&](int s) { return ps->lconst2_f[b + s]; };
+  auto hs_of = [&](int s) { return ps->hs2_f[b + s]; };
+  bool ok;
+  const float r_c = (float)(resid - ps->center[nu]);
+  if (K == 10) ok = unmix_certified<10>(10, r_c, unif, mu_of, lc_of, hs_of, k);
+  else if (K <= 4) ok = unmix_certified<4>(K, r_c, unif, mu_of, lc_of, hs_of, k);
+  else ok = unmix_certified<kMaxLogitK>(K, r_c, unif, mu_of, lc_of, hs_of, k);
+  if (!ok) {
+    const int a = __ldg(t.offset + __ldg(t.dense + nu));
+    k = unmix_table_fp64(t.mu + a, t.inv_sigma + a, t.lconst + a, K, resid, unif);
+  }
+  mu = ps->mu[b + k]; weight = ps->inv_sigsq[b + k]; logw = ps->logw[b + k];
+  kout = k;
+  return true;
+}
+
 struct PoissonLatent { double z_int, mu_int, w_int, z_ext, mu_ext, w_ext, lw_int, lw_ext; int k_int, k_ext; };
 
 // The extreme-eta statement of PoissonDataImputer::impute (PoissonDataImputer.cpp:55-79), out of line.
@@ -660,7 +721,7 @@ __device__ __noinline__ double poisson_zext_extreme(double eta, double delta, do
 //   z_ext = -log(delta + Exp(1) / exp(eta)),  delta = E - tau
 // For exposures and eta in the ordinary range every elementary function is the branch-free kind of the logit path.
 __device__ __forceinline__ int poisson_impute(const LogitHot &ext, const PoissonTable &t, int64_t y, double exposure, double eta,
-                                              const RngKey &key, uint64_t row, PoissonLatent &o) {
+                                              const RngKey &key, uint64_t row, PoissonLatent &o, const PoissonSmem *ps = nullptr) {
   o.z_int = o.mu_int = o.w_int = o.lw_int = 0; o.k_int = o.k_ext = -1;
   if (y < 0 || !(exposure >= 0) || !isfinite(eta)) return 2;
   double ua0, ua1, ub0, ub1;
@@ -691,6 +752,8 @@ __device__ __forceinline__ int poisson_impute(const LogitHot &ext, const Poisson
       o.mu_int = -log((double)y);
       o.w_int = 1.0 / (1.0 / (double)y);
       o.lw_int = log(o.w_int);
+    } else if (ps != nullptr && y < kPoisSmemNu && ps->off[y + 1] > ps->off[y]) {
+      unmix_poisson_smem(ps, t, (int)y, z_int - eta, ub1, o.mu_int, o.w_int, o.lw_int, o.k_int);
     } else {
       if (!unmix_poisson(t, poisson_table_find(t, y), z_int - eta, ub1, o.mu_int, o.w_int, o.lw_int, o.k_int)) return 1;
     }

@@ -445,104 +445,83 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
 // Wide tiles (40 < p <= 64), warp-specialised.  In fused_tma_kernel every warp alternates between its draw phase (a long
 // dependent chain per lane: latency bound) and its DMMA phase (28-36 atoms per k-step: pipe bound), and with the 8 warps
 // that fit (the triangle alone is 112-144 registers) the FP64 pipe idles through every draw phase: 50 % busy at C2.
-// Here the roles are split.  Per SM sub-partition: ONE accumulate warp that owns the triangle and does nothing but DMMA
-// k-steps, and TWO draw warps that take turns preparing its slices (eta, latent draw, (w, s) into the slice's pad columns).
-//   accumulate warp m (0..3)  issues the TMA loads of its ring (S slots); for slot k: waits drawn[k] -> 8 k-steps ->
-//                             re-arms full[k] and issues the TMA of slice k + S (it is the slot's last reader)
-//   draw warps 4 + m, 8 + m   slices k = 0, 2, 4, ... / 1, 3, 5, ...: wait full[k] -> eta, draw -> (w, s) -> arrive drawn[k]
-// No block-wide barrier in the steady state; mbarriers only (full: transaction count, drawn: one arrival).
+// Here the roles are split, per SM sub-partition m (0..3), around a ring of S 32-row slices:
+//   accumulate warps m and 4 + m   own HALF of the triangle each (atoms a = h mod 2: 14-18 atoms, 56-72 registers) and do
+//                                  nothing but DMMA k-steps on the ring's slices.  Two of them, because ONE warp cannot
+//                                  keep the pipe busy: a warp that has issued a DMMA waits out the issue interval (the NOP
+//                                  after every DMMA in the SASS) and its DMUL / DFMA / LDS go in series with it -- measured
+//                                  53 % of the pipe with one accumulate warp per sub-partition.
+//   draw warps 8 + m and 12 + m    take turns preparing the ring's slices: eta, latent draw, (w, s) into the pad columns.
+// Slot k mod S: full[k] (TMA bytes landed) -> draw warp -> drawn[k] -> both accumulate warps -> empty[k] (two arrivals) ->
+// accumulate warp m re-arms full and issues the TMA load of slice k + S.  No block-wide barrier in the steady state.
+// 16 warps x 128 registers.
 // =============================================================================================
-constexpr int kWsAccWarps = 4;
-// p <= 56: 12 warps (two draw warps per accumulate warp, 168 registers each: the 28-atom triangle is 112 of them);
-// p > 56: the 36-atom triangle needs more than 168 registers, so 8 warps (one draw warp per accumulate warp) at 255
-__host__ __device__ constexpr int ws_warps(int nb) { return nb <= 7 ? 12 : 8; }
-__host__ __device__ constexpr int ws_stages(int nb) { return 3; }
+constexpr int kWsAccWarps = 8, kWsRings = 4, kWsWarps = 16;
+__host__ __device__ constexpr int ws_stages(int nb) { return nb <= 6 ? 4 : 3; }
 __host__ __device__ constexpr size_t ws_smem_bytes(int nb) {
-  return sizeof(double) * ((size_t)kWsAccWarps * ws_stages(nb) * 32 * tma_padw(nb) + 64) +
-         sizeof(uint64_t) * 2 * kWsAccWarps * ws_stages(nb) + 128;
+  return sizeof(double) * ((size_t)kWsRings * ws_stages(nb) * 32 * tma_padw(nb) + 64) +
+         sizeof(uint64_t) * 3 * kWsRings * ws_stages(nb) + 128 + sizeof(PoissonSmem);
 }
 
-template <int NB, int MODEL>
-__global__ void __launch_bounds__(32 * ws_warps(NB), 1)
-fused_ws_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams prm, RowOut out, const __grid_constant__ BetaParam beta,
-                double *__restrict__ partials, int *err, TailParams tail) {
+// The accumulate warp's loop (see fused_ws_kernel): atoms a with a mod 2 == HALF of the triangle, X's for the column blocks b
+// with b mod 2 == HALF; HALF 0 also re-arms the ring.
+template <int NB, int HALF>
+__device__ __forceinline__ void ws_accumulate(const CUtensorMap &xmap, double *my_ring, uint64_t *my_full, uint64_t *my_drawn,
+                                              uint64_t *my_empty, int64_t first, int64_t stride, int64_t nslices, int lane,
+                                              double (&c)[(NB * (NB + 1) / 2 + 1) / 2][2], double (&xty_acc)[NB]) {
   constexpr int S = ws_stages(NB);
-  constexpr int kWsWarps = ws_warps(NB);
-  constexpr int NDRAW = (kWsWarps - kWsAccWarps) / kWsAccWarps;   // draw warps per accumulate warp
   constexpr int PADW = tma_padw(NB);
   constexpr int SLICE = 32 * PADW;
   constexpr int P8 = 8 * NB;
-  constexpr int NA = NB * (NB + 1) / 2;
+  constexpr int NH = (NB * (NB + 1) / 2 + 1) / 2;
   constexpr uint32_t kSliceBytes = SLICE * sizeof(double);
-  extern __shared__ __align__(128) double smem[];
-  double *ring = smem;                                           // [4][S][SLICE]
-  double *red_s = smem + (size_t)kWsAccWarps * S * SLICE;        // 64
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(red_s + 64); // [4][S]
-  uint64_t *drawn_bar = full_bar + kWsAccWarps * S;              // [4][S]
-
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int m = wid & 3;                 // sub-partition / accumulate warp this warp works with
-  const bool is_acc = wid < kWsAccWarps;
-  if (tid == 0) {
-    for (int i = 0; i < kWsAccWarps * S; ++i) { mbar_init(full_bar + i, 1); mbar_init(drawn_bar + i, 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  __syncthreads();
-
-  // 32-row slices are dealt to (CTA, accumulate warp): the k-th slice of ring m is (blockIdx + k grid) 4 + m
-  const int64_t nslices = (d.n + 31) / 32;
-  const int64_t stride = (int64_t)gridDim.x * kWsAccWarps;
-  const int64_t first = (int64_t)blockIdx.x * kWsAccWarps + m;
-  double *my_ring = ring + (size_t)m * S * SLICE;
-  uint64_t *my_full = full_bar + m * S, *my_drawn = drawn_bar + m * S;
-
-  double c[NA][2];
-  double xty_acc[NB];
-  double sc_count = 0, sc_ywy = 0, sc_sumw = 0, sc_sumlogw = 0;
-
-  if (is_acc) {
-    // ===== accumulate warp
 #pragma unroll
-    for (int a = 0; a < NA; ++a) { c[a][0] = 0.0; c[a][1] = 0.0; }
+  for (int a = 0; a < NH; ++a) { c[a][0] = 0.0; c[a][1] = 0.0; }
 #pragma unroll
-    for (int b = 0; b < NB; ++b) xty_acc[b] = 0.0;
-    if (lane == 0) {
+  for (int b = 0; b < NB; ++b) xty_acc[b] = 0.0;
+  if (HALF == 0 && lane == 0) {
 #pragma unroll
-      for (int s0 = 0; s0 < S; ++s0) {
-        const int64_t q = first + s0 * stride;
-        if (q < nslices) {
-          mbar_expect_tx(my_full + s0, kSliceBytes);
-          tma_load_2d(my_ring + s0 * SLICE, &xmap, 0, (int)(q * 32), my_full + s0);
-        }
+    for (int s0 = 0; s0 < S; ++s0) {
+      const int64_t q = first + s0 * stride;
+      if (q < nslices) {
+        mbar_expect_tx(my_full + s0, kSliceBytes);
+        tma_load_2d(my_ring + s0 * SLICE, &xmap, 0, (int)(q * 32), my_full + s0);
       }
     }
-    int slot = 0;
-    uint32_t phase = 0;
-    for (int64_t q = first; q < nslices; q += stride) {
-      mbar_wait(my_drawn + slot, phase);
-      const double *xs = my_ring + slot * SLICE;
+  }
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int64_t q = first; q < nslices; q += stride) {
+    mbar_wait(my_drawn + slot, phase);
+    const double *xs = my_ring + slot * SLICE;
 #pragma unroll 2
-      for (int kk = 0; kk < 8; ++kk) {
-        const int row = 8 * (kk >> 1) + (kk & 1) + 2 * (lane & 3);   // the k-step's four rows, two apart (bank layout: tma_padw)
-        const double2 ws = *reinterpret_cast<const double2 *>(xs + row * PADW + P8);
-        const double *xr = xs + row * PADW + (lane >> 2);
-        double xa[NB], xw[NB];
+    for (int kk = 0; kk < 8; ++kk) {
+      const int row = 8 * (kk >> 1) + (kk & 1) + 2 * (lane & 3);   // the k-step's four rows, two apart (bank layout: tma_padw)
+      const double2 ws = *reinterpret_cast<const double2 *>(xs + row * PADW + P8);
+      const double *xr = xs + row * PADW + (lane >> 2);
+      double xa[NB], xw[NB];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          xa[b] = xr[8 * b];
-          xw[b] = xa[b] * ws.x;
-          xty_acc[b] = fma(xa[b], ws.y, xty_acc[b]);
-        }
-        int a = 0;
-#pragma unroll
-        for (int bi = 0; bi < NB; ++bi)
-#pragma unroll
-          for (int bj = bi; bj < NB; ++bj) { dmma884(c[a][0], c[a][1], xw[bi], xa[bj]); ++a; }
+      for (int b = 0; b < NB; ++b) {
+        xa[b] = xr[8 * b];
+        xw[b] = xa[b] * ws.x;
+        if ((b & 1) == HALF) xty_acc[b] = fma(xa[b], ws.y, xty_acc[b]);
       }
-      // the slot's last reader re-arms it S slices ahead (the draw warp's generic-proxy writes of (w, s) are ordered
-      // before the async-proxy overwrite by the fence)
+      int a = 0;
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < NB; ++bj) {
+          if ((a & 1) == HALF) dmma884(c[a >> 1][0], c[a >> 1][1], xw[bi], xa[bj]);
+          ++a;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(my_empty + slot);
+    if (HALF == 0) {
+      // both halves are done with the slot: re-arm it S slices ahead (the draw warp's generic-proxy writes of (w, s) are
+      // ordered before the async-proxy overwrite by the fence)
+      mbar_wait(my_empty + slot, phase);
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      __syncwarp();
       if (lane == 0) {
         const int64_t qn = q + (int64_t)S * stride;
         if (qn < nslices) {
@@ -550,26 +529,73 @@ fused_ws_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams 
           tma_load_2d(my_ring + slot * SLICE, &xmap, 0, (int)(qn * 32), my_full + slot);
         }
       }
-      if (++slot == S) { slot = 0; phase ^= 1; }
     }
+    if (++slot == S) { slot = 0; phase ^= 1; }
+  }
+}
+
+template <int NB, int MODEL>
+__global__ void __launch_bounds__(32 * kWsWarps, 1)
+fused_ws_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams prm, RowOut out, const __grid_constant__ BetaParam beta,
+                double *__restrict__ partials, int *err, TailParams tail) {
+  constexpr int S = ws_stages(NB);
+  constexpr int PADW = tma_padw(NB);
+  constexpr int SLICE = 32 * PADW;
+  constexpr int P8 = 8 * NB;
+  constexpr int NA = NB * (NB + 1) / 2;
+  constexpr int NH = (NA + 1) / 2;                                 // atoms per accumulate warp
+  constexpr uint32_t kSliceBytes = SLICE * sizeof(double);
+  extern __shared__ __align__(128) double smem[];
+  double *ring = smem;                                             // [4][S][SLICE]
+  double *red_s = smem + (size_t)kWsRings * S * SLICE;             // 64
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(red_s + 64);   // [4][S]
+  uint64_t *drawn_bar = full_bar + kWsRings * S;                   // [4][S]
+  uint64_t *empty_bar = drawn_bar + kWsRings * S;                  // [4][S]
+  PoissonSmem *tab_s = reinterpret_cast<PoissonSmem *>(empty_bar + kWsRings * S + 2);   // 16-byte aligned
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int m = wid & 3;                 // sub-partition = ring this warp works on
+  const bool is_acc = wid < kWsAccWarps;
+  const int half = (wid >> 2) & 1;       // accumulate warps: which half of the triangle; draw warps: whose turn
+  if (tid == 0) {
+    for (int i = 0; i < kWsRings * S; ++i) { mbar_init(full_bar + i, 1); mbar_init(drawn_bar + i, 1); mbar_init(empty_bar + i, 2); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (MODEL == kPoisson) poisson_smem_fill(tab_s, prm.tab, tid, 32 * kWsWarps);   // small-count table entries -> shared memory
+  __syncthreads();
+
+  // 32-row slices are dealt to (CTA, ring): the k-th slice of ring m is (blockIdx + k grid) 4 + m
+  const int64_t nslices = (d.n + 31) / 32;
+  const int64_t stride = (int64_t)gridDim.x * kWsRings;
+  const int64_t first = (int64_t)blockIdx.x * kWsRings + m;
+  double *my_ring = ring + (size_t)m * S * SLICE;
+  uint64_t *my_full = full_bar + m * S, *my_drawn = drawn_bar + m * S, *my_empty = empty_bar + m * S;
+
+  double c[NH][2];
+  double xty_acc[NB];
+  double sc_count = 0, sc_ywy = 0, sc_sumw = 0, sc_sumlogw = 0;
+
+  if (is_acc) {
+    // ===== accumulate warp (HALF at compile time: a run-time test on the atom index would issue every DMMA in both warps)
+    if (half == 0) ws_accumulate<NB, 0>(xmap, my_ring, my_full, my_drawn, my_empty, first, stride, nslices, lane, c, xty_acc);
+    else ws_accumulate<NB, 1>(xmap, my_ring, my_full, my_drawn, my_empty, first, stride, nslices, lane, c, xty_acc);
   } else {
-    // ===== draw warp: every NDRAW-th slice of ring m
-    const int turn = (wid - kWsAccWarps) >> 2;     // 0 .. NDRAW - 1
+    // ===== draw warp: every second slice of ring m
     RowObs obs_next;
     obs_next.y = 0; obs_next.aux = 0; obs_next.yi = 0;
     {
-      const int64_t q0 = first + turn * stride;
+      const int64_t q0 = first + half * stride;
       const int64_t i0 = q0 * 32 + lane;
       if (q0 < nslices && i0 < d.n) obs_next = load_obs<MODEL>(d, i0);
     }
-    int64_t k = turn;
-    for (int64_t q = first + turn * stride; q < nslices; q += NDRAW * stride, k += NDRAW) {
+    int64_t k = half;
+    for (int64_t q = first + half * stride; q < nslices; q += 2 * stride, k += 2) {
       const int slot = (int)(k % S);
       const uint32_t phase = (uint32_t)((k / S) & 1);
       const int64_t i = q * 32 + lane;
       const bool valid = i < d.n;
       const RowObs obs = obs_next;
-      const int64_t in = (q + NDRAW * stride) * 32 + lane;
+      const int64_t in = (q + 2 * stride) * 32 + lane;
       if (in < d.n) obs_next = load_obs<MODEL>(d, in);
       mbar_wait(my_full + slot, phase);
       double *xs = my_ring + slot * SLICE;
@@ -582,17 +608,17 @@ fused_ws_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams 
       }
       double wv = 0, sv = 0;
       if (valid) {
-        RowLatent r = impute_row<MODEL>(d, prm, out, obs, i, e0 + e1, err);
+        RowLatent r = impute_row<MODEL>(d, prm, out, obs, i, e0 + e1, err, MODEL == kPoisson ? tab_s : nullptr);
         wv = r.w; sv = r.s;
         sc_count += r.count; sc_ywy += r.yWy; sc_sumw += r.w; sc_sumlogw += r.sumlogw;
       }
       *reinterpret_cast<double2 *>(xs + lane * PADW + P8) = make_double2(wv, sv);
       __syncwarp();
-      if (lane == 0) mbar_arrive(my_drawn + slot);   // release: the (w, s) stores above are visible to the waiter
+      if (lane == 0) mbar_arrive(my_drawn + slot);   // release: the (w, s) stores above are visible to the waiters
     }
   }
 
-  // ---- CTA reduction: the four accumulate warps in warp order (deterministic), one partial per CTA
+  // ---- CTA reduction: the eight accumulate warps in warp order (deterministic), one partial per CTA
   __syncthreads();  // every issued copy has been consumed: the ring is free
   constexpr int TILE = P8 * P8 + P8;
   double *tile = smem;
@@ -613,14 +639,17 @@ fused_ws_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams 
       for (int bi = 0; bi < NB; ++bi)
 #pragma unroll
         for (int bj = bi; bj < NB; ++bj) {
-          double *t = tile + (8 * bi + (lane >> 2)) * P8 + 8 * bj + 2 * (lane & 3);
-          t[0] += c[a][0];
-          t[1] += c[a][1];
+          if ((a & 1) == half) {
+            double *t = tile + (8 * bi + (lane >> 2)) * P8 + 8 * bj + 2 * (lane & 3);
+            t[0] += c[a >> 1][0];
+            t[1] += c[a >> 1][1];
+          }
           ++a;
         }
       if ((lane & 3) == 0) {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) xty_s[8 * b + (lane >> 2)] += xty_acc[b];
+        for (int b = 0; b < NB; ++b)
+          if ((b & 1) == half) xty_s[8 * b + (lane >> 2)] += xty_acc[b];
       }
     }
     __syncthreads();

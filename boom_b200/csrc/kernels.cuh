@@ -100,7 +100,7 @@ __device__ __forceinline__ RowObs load_obs(const RowData &d, int64_t i) {
 
 template <int MODEL>
 __device__ __forceinline__ RowLatent impute_row(const RowData &d, const DrawParams &prm, const RowOut &out, const RowObs &obs,
-                                                int64_t i, double eta, int *err) {
+                                                int64_t i, double eta, int *err, const PoissonSmem *tab_s = nullptr) {
   RowLatent r;
   r.w = r.s = r.yWy = r.sumlogw = 0; r.count = 1;
   if (MODEL == kLogit) {
@@ -110,7 +110,7 @@ __device__ __forceinline__ RowLatent impute_row(const RowData &d, const DrawPara
     r.w = info; r.s = sum;
   } else if (MODEL == kPoisson) {
     PoissonLatent o;
-    int rc = poisson_impute(prm.ext, prm.tab, obs.yi, obs.aux, eta, prm.key, d.row_offset + (uint64_t)i, o);
+    int rc = poisson_impute(prm.ext, prm.tab, obs.yi, obs.aux, eta, prm.key, d.row_offset + (uint64_t)i, o, tab_s);
     if (rc) {
       atomicOr(err, rc == 1 ? 1 : 2);
     } else {
@@ -881,6 +881,148 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap xmap, SyrkParams prm, SyrkU
   syrk_dispatch_role(t0 * 100 + t1 * 10 + duty, nm, wc);
 }
 
+// =============================================================================================
+// Active-set statistics: G = X' diag(w) X_A for a small column set A (the included variables), plus
+// diag_j = sum_i w_i x_ij^2 and X's.  One sweep over the inclusion indicators reads of X'WX only the columns in the
+// current model and the diagonal (BinomialLogitSpikeSlabSampler.cpp:88-117,180-222 select sub-blocks of suf().xtx()), so
+// p (|A| + 2) numbers replace the p^2 of the full SYRK: n p (2 |A| + 4) flops instead of n p (p + 1) -- at C3 (p = 500,
+// |A| ~ 21) the step becomes bound by reading X once.
+//   CTA = (k-slice, 128-column block I of X); per stage one TMA tile of X (132 x 16) and one of X_A (B panel, NBA 8-column
+//   atoms + 4 pad columns, from the gathered matrix boomgpu_select_columns builds), w and s by bulk copies, through the same
+//   mbarrier ring as the SYRK.  Consumer warp q owns 16 columns of the block (2 A atoms) x all NBA B atoms.
+//   Partial per CTA: [128 x 128 (NBA * 8 columns used) | diag 128 | xty 128], reduced over k-slices in order.
+// =============================================================================================
+constexpr int64_t kPanelTileLen = 128 * 128 + 256;
+struct PanelParams {
+  int64_t n;
+  int p, nblk, ka8;        // ka8 = 8 NBA: columns of the B panel (zero padded)
+  const double *w, *s;
+  int ksplit;
+  int64_t rows_per_slice;
+  double *partials;        // [ksplit][nblk][kPanelTileLen]
+};
+
+template <int NBA, int BLD>
+__device__ __forceinline__ void panel_consume_b(const SyrkWarpCtx &wc, int wq) {
+  const int lane = wc.lane;
+  double c[2][NBA][2], dg[2] = {0.0, 0.0}, cx[2] = {0.0, 0.0};
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < NBA; ++n) c[m][n][0] = c[m][n][1] = 0.0;
+  const int a_off = 16 * wq + (lane >> 2);
+  for (int it = 0; it < wc.nstages_total; ++it) {
+    const int s = it % kSyrkStages;
+    const uint32_t phase = (it / kSyrkStages) & 1;
+    mbar_wait(wc.full_bar + s, phase);
+    const double *stage = wc.smem + s * kSyrkStageDoubles;
+    const double *w_s = stage + 2 * kSyrkKB * kSyrkPanelLd;
+    const double *s_s = w_s + kSyrkKB;
+#pragma unroll
+    for (int kk = 0; kk < kSyrkKB / 4; ++kk) {
+      const int row = kk * 4 + (lane & 3);
+      const double wv = w_s[row], sv = s_s[row];
+      const double *xr = stage + row * kSyrkPanelLd;
+      double a[2], aw[2], b[NBA];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) { a[m] = xr[a_off + 8 * m]; aw[m] = a[m] * wv; }
+#pragma unroll
+      for (int n = 0; n < NBA; ++n) b[n] = stage[wc.panelB_off + row * BLD + (lane >> 2) + 8 * n];   // pitch 8 NBA + 4: 4 mod 8, conflict free
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+#pragma unroll
+        for (int n = 0; n < NBA; ++n) dmma884(c[m][n][0], c[m][n][1], aw[m], b[n]);
+        dg[m] = fma(aw[m], a[m], dg[m]);
+        cx[m] = fma(a[m], sv, cx[m]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(wc.empty_bar + s);
+  }
+  double *tile = wc.tile;
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+#pragma unroll
+    for (int n = 0; n < NBA; ++n)
+      *reinterpret_cast<double2 *>(tile + (16 * wq + 8 * m + (lane >> 2)) * 128 + 8 * n + 2 * (lane & 3)) = make_double2(c[m][n][0], c[m][n][1]);
+    dg[m] += __shfl_xor_sync(0xffffffffu, dg[m], 1); dg[m] += __shfl_xor_sync(0xffffffffu, dg[m], 2);
+    cx[m] += __shfl_xor_sync(0xffffffffu, cx[m], 1); cx[m] += __shfl_xor_sync(0xffffffffu, cx[m], 2);
+    if ((lane & 3) == 0) {
+      tile[128 * 128 + 16 * wq + 8 * m + (lane >> 2)] = dg[m];
+      tile[128 * 128 + 128 + 16 * wq + 8 * m + (lane >> 2)] = cx[m];
+    }
+  }
+}
+
+template <int NBA>
+__global__ void __launch_bounds__(kSyrkThreads, 1)
+panel_dmma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap amap, PanelParams prm) {
+  extern __shared__ __align__(128) double smem[];
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kSyrkStages * kSyrkStageDoubles);
+  uint64_t *empty_bar = full_bar + kSyrkStages;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int kslice = blockIdx.x / prm.nblk;
+  const int I = blockIdx.x - kslice * prm.nblk;
+  const int64_t row_begin = (int64_t)kslice * prm.rows_per_slice;
+  const int64_t row_end = min(prm.n, row_begin + prm.rows_per_slice);
+  const int nstages_total = row_end > row_begin ? (int)((row_end - row_begin + kSyrkKB - 1) / kSyrkKB) : 0;
+  if (tid == 0) {
+    for (int s = 0; s < kSyrkStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, kSyrkConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  // the B tile: box {8 NBA + 4, 16} of the gathered matrix: it lands with its own row pitch 8 NBA + 4 doubles (4 mod 8)
+  constexpr int kBLd = 8 * NBA + 4;
+  constexpr uint32_t kABytes = kSyrkKB * kSyrkPanelLd * sizeof(double), kBBytes = kSyrkKB * kBLd * sizeof(double);
+  if (wid >= kSyrkConsumerWarps) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    if (wid == kSyrkConsumerWarps) {
+      for (int it = 0; it < nstages_total; ++it) {
+        const int s = it % kSyrkStages;
+        const uint32_t phase = (it / kSyrkStages) & 1;
+        mbar_wait(empty_bar + s, phase ^ 1);
+        double *stage = smem + s * kSyrkStageDoubles;
+        const int64_t r0 = row_begin + (int64_t)it * kSyrkKB;
+        if (lane == 0) {
+          mbar_expect_tx(full_bar + s, kABytes + kBBytes + 2 * kSyrkKB * 8);
+          tma_load_2d(stage, &xmap, 128 * I, (int)r0, full_bar + s);
+          tma_load_2d(stage + kSyrkKB * kSyrkPanelLd, &amap, 0, (int)r0, full_bar + s);
+          tma_bulk_g2s(stage + 2 * kSyrkKB * kSyrkPanelLd, prm.w + r0, kSyrkKB * 8, full_bar + s);
+          tma_bulk_g2s(stage + 2 * kSyrkKB * kSyrkPanelLd + kSyrkKB, prm.s + r0, kSyrkKB * 8, full_bar + s);
+        }
+      }
+    }
+    return;
+  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+  SyrkWarpCtx wc;
+  wc.smem = smem; wc.full_bar = full_bar; wc.empty_bar = empty_bar; wc.nstages_total = nstages_total;
+  wc.lane = lane;
+  wc.panelB_off = kSyrkKB * kSyrkPanelLd;
+  wc.tile = prm.partials + ((int64_t)kslice * prm.nblk + I) * kPanelTileLen;
+  panel_consume_b<NBA, kBLd>(wc, wid);
+}
+
+// G[j][a] (row major p x ka8), diag[j], xty[j] <- sums of the partial tiles over k-slices (fixed order)
+__global__ void reduce_panel_kernel(PanelParams prm, double *__restrict__ G, double *__restrict__ diag, double *__restrict__ xty) {
+  const int p = prm.p, ka8 = prm.ka8;
+  const int64_t per_blk = 128 * (int64_t)(ka8 + 2);
+  const int64_t total = (int64_t)prm.nblk * per_blk;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int I = (int)(e / per_blk);
+    const int t = (int)(e - (int64_t)I * per_blk);
+    const int r = t / (ka8 + 2), cidx = t - r * (ka8 + 2);
+    const int j = 128 * I + r;
+    if (j >= p) continue;
+    const int64_t src = cidx < ka8 ? (int64_t)r * 128 + cidx : (int64_t)128 * 128 + (cidx - ka8) * 128 + r;
+    double sum = 0;
+    for (int k = 0; k < prm.ksplit; ++k) sum += prm.partials[((int64_t)k * prm.nblk + I) * kPanelTileLen + src];
+    if (cidx < ka8) G[(int64_t)j * ka8 + cidx] = sum;
+    else if (cidx == ka8) diag[j] = sum;
+    else xty[j] = sum;
+  }
+}
+
 // Sums partial tiles over k-slices (fixed order) into the p x p matrix (both triangles) and xty.
 __global__ void reduce_syrk_kernel(SyrkParams prm, double *__restrict__ suf) {
   const int p = prm.p;
@@ -986,6 +1128,12 @@ __global__ void __launch_bounds__(kXtsThreads) xts_kernel(const double *__restri
     const int c = tid + q * kXtsThreads;
     if (c < p2) { my[2 * c] = acc[q].x; my[2 * c + 1] = acc[q].y; }
   }
+}
+// out_i = w_i x_ij: the right-hand side of column j of X'WX (boomgpu_weighted_column)
+__global__ void weight_column_kernel(const double *__restrict__ X, int64_t ldx, int64_t n, int j, const double *__restrict__ w,
+                                     double *__restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __ldg(w + i) * __ldg(X + i * ldx + j);
 }
 __global__ void reduce_xts_kernel(const double *__restrict__ partials, int nparts, int p, double *__restrict__ xty) {
   const int p2x2 = 2 * ((p + 1) >> 1);

@@ -586,6 +586,44 @@ void WeightedRegSuf::reset(const double *packed, int p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+StatView::StatView(const WeightedRegSuf &full) : full_(full.xtx().a.data()), p_(full.xtx().dim), xty_(full.xty().data()) {}
+
+StatView::StatView(int p, const std::vector<int> &cols, const Vector &G, const Vector &diag, const Vector &xty,
+                   std::function<void(int, double *)> fetch)
+    : p_(p), k_((int)cols.size()), where_(p, -1), diag_(diag), xty_(xty.data()), fetch_(std::move(fetch)), column_(p) {
+  ld_ = k_ + 16;                       // room for the columns a sweep may add
+  G_.assign((size_t)p * ld_, 0.0);
+  for (int j = 0; j < p; ++j) std::copy(G.begin() + (size_t)j * k_, G.begin() + (size_t)(j + 1) * k_, G_.begin() + (size_t)j * ld_);
+  for (int a = 0; a < k_; ++a) where_[cols[a]] = a;
+}
+
+void StatView::ensure_column(int j) {
+  if (full_ || where_[j] >= 0) return;
+  if (!fetch_) report_error("StatView: column not held and no way to fetch it");
+  fetch_(j, column_.data());
+  ++fetched_;
+  if (k_ == ld_) {                     // grow the row pitch
+    const int nld = ld_ + 32;
+    Vector G((size_t)p_ * nld, 0.0);
+    for (int r = 0; r < p_; ++r) std::copy(G_.begin() + (size_t)r * ld_, G_.begin() + (size_t)r * ld_ + k_, G.begin() + (size_t)r * nld);
+    G_.swap(G);
+    ld_ = nld;
+  }
+  for (int r = 0; r < p_; ++r) G_[(size_t)r * ld_ + k_] = column_[r];
+  where_[j] = k_++;
+}
+
+double StatView::at(int i, int j) {
+  if (full_) return full_[(size_t)i * p_ + j];
+  if (i == j) return diag_[i];
+  int a = where_[j];
+  if (a >= 0) return G_[(size_t)i * ld_ + a];
+  a = where_[i];
+  if (a >= 0) return G_[(size_t)j * ld_ + a];   // symmetric
+  ensure_column(j);
+  return G_[(size_t)i * ld_ + where_[j]];
+}
+
 SpikeSlabCore::SpikeSlabCore(const std::shared_ptr<MvnBase> &slab, const std::shared_ptr<VariableSelectionPrior> &spike,
                              bool fisher_yates)
     : slab_(slab), spike_(spike), fisher_yates_(fisher_yates) {
@@ -595,6 +633,10 @@ SpikeSlabCore::SpikeSlabCore(const std::shared_ptr<MvnBase> &slab, const std::sh
 
 // BinomialLogitSpikeSlabSampler::log_model_prob (.cpp:88-117) == SpikeSlabSampler::log_model_prob with sigsq = 1
 double SpikeSlabCore::log_model_prob(const Selector &g, const WeightedRegSuf &suf) const {
+  StatView v(suf);
+  return log_model_prob(g, v);
+}
+double SpikeSlabCore::log_model_prob(const Selector &g, StatView &stats) const {
   const double neg_inf = -std::numeric_limits<double>::infinity();
   double num = spike_->logp(g);
   if (num == neg_inf || g.nvars() == 0) return num;
@@ -611,16 +653,13 @@ double SpikeSlabCore::log_model_prob(const Selector &g, const WeightedRegSuf &su
   for (int i = 0; i < k; ++i) q += mu[i] * ivar_mu[i];
   num -= .5 * q;
   const std::vector<int> pos = g.included_positions();
-  const SpdMatrix &xtx(suf.xtx());
-  for (int i = 0; i < k; ++i) {
-    const double *row = xtx.a.data() + (size_t)pos[i] * xtx.dim;
-    for (int j = 0; j < k; ++j) ivar.a[(size_t)i * k + j] += row[pos[j]];
-  }
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) ivar.a[(size_t)i * k + j] += stats.at(pos[i], pos[j]);
   if (!cholesky_lower(ivar.a.data(), k)) return neg_inf;
   double denom = 0;
   for (int i = 0; i < k; ++i) denom += std::log(ivar(i, i));  // = .5 log |ivar|
   Vector S(k);
-  for (int i = 0; i < k; ++i) S[i] = suf.xty()[pos[i]] + ivar_mu[i];
+  for (int i = 0; i < k; ++i) S[i] = stats.xty(pos[i]) + ivar_mu[i];
   lsolve_inplace(ivar.a.data(), k, S.data());
   double nsq = 0;
   for (int i = 0; i < k; ++i) nsq += S[i] * S[i];
@@ -635,8 +674,8 @@ double SpikeSlabCore::log_model_prob(const Selector &g, const WeightedRegSuf &su
 // a handful of heap allocations.  Included variables are kept in insertion order.
 class SpikeSlabCore::FlipEvaluator {
  public:
-  FlipEvaluator(const SpikeSlabCore &core, const WeightedRegSuf &suf, const Selector &g)
-      : slab_mu_(core.slab_->mu()), siginv_(core.slab_->siginv()), spike_(*core.spike_), xtx_(suf.xtx()), xty_(suf.xty()),
+  FlipEvaluator(const SpikeSlabCore &core, StatView &stats, const Selector &g)
+      : slab_mu_(core.slab_->mu()), siginv_(core.slab_->siginv()), spike_(*core.spike_), stats_(stats),
         g_(g), p_(g.nvars_possible()) {
     pos_ = g.included_positions();
     reserve(std::min(p_, std::max(32, 2 * (int)pos_.size() + 8)));
@@ -660,32 +699,31 @@ class SpikeSlabCore::FlipEvaluator {
     if (prop_spike_ == neg_inf) return prop_logp_ = neg_inf;
     const int k = (int)pos_.size();
     const double *sj = siginv_.a.data() + (size_t)j * p_;
-    const double *xj = xtx_.a.data() + (size_t)j * p_;
     // border rows: l1 = Lp^-1 Siginv[gamma, j], l2 = Lq^-1 (Siginv + XtX)[gamma, j]
     double n1 = 0, n2 = 0, cross = 0;
     for (int i = 0; i < k; ++i) {
       const int pi = pos_[i];
-      double s1 = sj[pi], s2 = sj[pi] + xj[pi];
+      double s1 = sj[pi], s2 = sj[pi] + stats_.at(j, pi);
       const double *r1 = Lp_.data() + (size_t)i * ld_, *r2 = Lq_.data() + (size_t)i * ld_;
       for (int c = 0; c < i; ++c) { s1 -= r1[c] * l1_[c]; s2 -= r2[c] * l2_[c]; }
       l1_[i] = s1 / r1[i]; l2_[i] = s2 / r2[i];
       n1 += l1_[i] * l1_[i]; n2 += l2_[i] * l2_[i];
       cross += sj[pi] * slab_mu_[pi];   // Siginv[j, gamma] mu_gamma
     }
-    const double d1 = sj[j] - n1, d2 = sj[j] + xj[j] - n2;
+    const double d1 = sj[j] - n1, d2 = sj[j] + stats_.at(j, j) - n2;
     if (!(d1 > 0) || !(d2 > 0)) return prop_logp_ = neg_inf;
     d1_ = std::sqrt(d1); d2_ = std::sqrt(d2);
     const double mj = slab_mu_[j];
     const double q_new = q_ + 2 * mj * cross + sj[j] * mj * mj;
     double nsq;
     if (mj == 0.0) {  // b_gamma unchanged: only the last forward-substitution row is new
-      bj_ = xty_[j] + cross;
+      bj_ = stats_.xty(j) + cross;
       double t = bj_;
       for (int c = 0; c < k; ++c) t -= l2_[c] * u_[c];
       uj_ = t / d2_;
       nsq = usq_ + uj_ * uj_;
     } else {  // every entry of b changes: b_i += Siginv[i, j] mu_j, then a full forward solve
-      bj_ = xty_[j] + cross + sj[j] * mj;
+      bj_ = stats_.xty(j) + cross + sj[j] * mj;
       nsq = 0;
       for (int i = 0; i < k; ++i) {
         double t = b_[i] + sj[pos_[i]] * mj;
@@ -714,6 +752,7 @@ class SpikeSlabCore::FlipEvaluator {
     }
     const int k = (int)pos_.size();
     const double mj = slab_mu_[j];
+    stats_.ensure_column(j);   // active-set form: later proposals read X'WX[., j]
     if (k + 1 > ld_) grow(std::min(p_, 2 * ld_));
     double *r1 = Lp_.data() + (size_t)k * ld_, *r2 = Lq_.data() + (size_t)k * ld_;
     for (int c = 0; c < k; ++c) { r1[c] = l1_[c]; r2[c] = l2_[c]; }
@@ -773,13 +812,12 @@ class SpikeSlabCore::FlipEvaluator {
     *q = 0;
     for (int i = 0; i < k; ++i) {
       const double *si = siginv_.a.data() + (size_t)pos[i] * p_;
-      const double *xi = xtx_.a.data() + (size_t)pos[i] * p_;
       double m = 0;
       for (int c = 0; c < k; ++c) m += si[pos[c]] * slab_mu_[pos[c]];
       im_[i] = m;
       *q += m * slab_mu_[pos[i]];
-      b[i] = xty_[pos[i]] + m;
-      for (int c = 0; c <= i; ++c) { Lp[(size_t)i * ld_ + c] = si[pos[c]]; Lq[(size_t)i * ld_ + c] = si[pos[c]] + xi[pos[c]]; }
+      b[i] = stats_.xty(pos[i]) + m;
+      for (int c = 0; c <= i; ++c) { Lp[(size_t)i * ld_ + c] = si[pos[c]]; Lq[(size_t)i * ld_ + c] = si[pos[c]] + stats_.at(pos[i], pos[c]); }
     }
     if (!chol_ld(Lp, k) || !chol_ld(Lq, k)) return neg_inf;
     *hldp = *hldq = *usq = 0;
@@ -816,8 +854,7 @@ class SpikeSlabCore::FlipEvaluator {
   const Vector &slab_mu_;
   const SpdMatrix &siginv_;
   const VariableSelectionPrior &spike_;
-  const SpdMatrix &xtx_;
-  const Vector &xty_;
+  StatView &stats_;
   Selector g_;
   int p_, ld_;
   std::vector<int> pos_, scratch_pos_;
@@ -831,7 +868,12 @@ class SpikeSlabCore::FlipEvaluator {
 
 Vector SpikeSlabCore::flip_path_log_probs(const Selector &start, const WeightedRegSuf &suf, const std::vector<int> &flips,
                                           const std::vector<bool> &accept) const {
-  FlipEvaluator ev(*this, suf, start);
+  StatView v(suf);
+  return flip_path_log_probs(start, v, flips, accept);
+}
+Vector SpikeSlabCore::flip_path_log_probs(const Selector &start, StatView &stats, const std::vector<int> &flips,
+                                          const std::vector<bool> &accept) const {
+  FlipEvaluator ev(*this, stats, start);
   Vector out;
   for (size_t i = 0; i < flips.size(); ++i) {
     out.push_back(ev.propose(flips[i]));
@@ -842,6 +884,10 @@ Vector SpikeSlabCore::flip_path_log_probs(const Selector &start, const WeightedR
 }
 
 void SpikeSlabCore::draw_model_indicators(RNG &rng, GlmCoefs &coef, const WeightedRegSuf &suf) const {
+  StatView v(suf);
+  draw_model_indicators(rng, coef, v);
+}
+void SpikeSlabCore::draw_model_indicators(RNG &rng, GlmCoefs &coef, StatView &suf) const {
   if (!allow_model_selection_) return;
   Selector g = coef.inc();
   const int nv = g.nvars_possible();
@@ -877,6 +923,10 @@ void SpikeSlabCore::draw_model_indicators(RNG &rng, GlmCoefs &coef, const Weight
 
 // BinomialLogitSpikeSlabSampler::draw_beta (.cpp:56-75)
 void SpikeSlabCore::draw_beta(RNG &rng, GlmCoefs &coef, const WeightedRegSuf &suf) const {
+  StatView v(suf);
+  draw_beta(rng, coef, v);
+}
+void SpikeSlabCore::draw_beta(RNG &rng, GlmCoefs &coef, StatView &suf) const {
   const Selector &g(coef.inc());
   if (g.nvars() == 0) { coef.drop_all(); return; }
   SpdMatrix precision = g.select(slab_->siginv());
@@ -886,11 +936,9 @@ void SpikeSlabCore::draw_beta(RNG &rng, GlmCoefs &coef, const WeightedRegSuf &su
   for (int i = 0; i < k; ++i)
     for (int j = 0; j < k; ++j) scaled_mean[i] += precision(i, j) * mu[j];
   const std::vector<int> pos = g.included_positions();
-  const SpdMatrix &xtx(suf.xtx());
   for (int i = 0; i < k; ++i) {
-    const double *row = xtx.a.data() + (size_t)pos[i] * xtx.dim;
-    for (int j = 0; j < k; ++j) precision.a[(size_t)i * k + j] += row[pos[j]];
-    scaled_mean[i] += suf.xty()[pos[i]];
+    for (int j = 0; j < k; ++j) precision.a[(size_t)i * k + j] += suf.at(pos[i], pos[j]);
+    scaled_mean[i] += suf.xty(pos[i]);
   }
   if (!cholesky_lower(precision.a.data(), k)) report_error("Cholesky decomposition failed in draw_beta.");
   lsolve_inplace(precision.a.data(), k, scaled_mean.data());
@@ -1074,6 +1122,7 @@ void BinomialLogitAuxmixSampler::draw() {
 
 void BinomialLogitAuxmixSampler::impute_latent_data() {
   if (latent_data_fixed_) return;  // statistics are under external control (Imputer.hpp:282-299)
+  active_.valid = false;
   const LogitMixtureStore &mix(logit_mixture_store());
   const int clt = clt_threshold_;
   const uint64_t seed = device_seed_, it = iteration_++;
@@ -1095,7 +1144,47 @@ void BinomialLogitAuxmixSampler::impute_latent_data() {
       });
 }
 
+bool BinomialLogitAuxmixSampler::impute_latent_data_active(const std::vector<int> &cols_in) {
+  const int p = model_->xdim();
+  if (latent_data_fixed_ || p <= 64 || model_->allreduce() || cols_in.size() > 128) return false;
+  std::vector<int> cols(cols_in);
+  if (cols.empty()) cols.push_back(0);
+  const LogitMixtureStore &mix(logit_mixture_store());
+  DeviceData &dev(model_->device_data());
+  dev.check(boomgpu_set_logit_mixture(dev.ctx(), (int)mix.sigma.size(), mix.mu.data(), mix.sigma.data(), mix.weights.data()));
+  const int k = (int)cols.size();
+  active_.cols = cols;
+  active_.G.resize((size_t)p * k); active_.diag.resize(p); active_.xty.resize(p);
+  int64_t ss = 0;
+  std::vector<int32_t> c32(cols.begin(), cols.end());
+  dev.check(boomgpu_logit_step_active(dev.ctx(), model_->Beta().data(), clt_threshold_, device_seed_, iteration_++, c32.data(), k,
+                                      active_.G.data(), active_.diag.data(), active_.xty.data(), &ss));
+  active_.scalars[0] = (double)ss; active_.scalars[1] = active_.scalars[2] = active_.scalars[3] = 0;
+  active_.valid = true;
+  return true;
+}
+
+std::unique_ptr<StatView> BinomialLogitAuxmixSampler::statistics_view() {
+  if (!active_.valid) return std::unique_ptr<StatView>(new StatView(suf_));
+  DeviceData *dev = &model_->device_data();
+  ActiveSetState *st = &active_;
+  return std::unique_ptr<StatView>(new StatView(model_->xdim(), active_.cols, active_.G, active_.diag, active_.xty,
+                                               [dev, st](int j, double *out) {
+                                                 dev->check(boomgpu_weighted_column(dev->ctx(), j, out));
+                                                 ++st->columns_fetched;
+                                               }));
+}
+
+void BinomialLogitAuxmixSampler::materialize_full_statistics() const {
+  DeviceData &dev(model_->device_data());
+  const int p = model_->xdim();
+  dev.check(boomgpu_full_statistics(dev.ctx(), suf_.xtx_storage(p), suf_.xty_storage()));
+  suf_.set_scalars(active_.scalars[0], active_.scalars[1], active_.scalars[2], active_.scalars[3]);
+  active_.valid = false;
+}
+
 void BinomialLogitAuxmixSampler::draw_params() {
+  if (active_.valid) materialize_full_statistics();
   const int p = model_->xdim();
   SpdMatrix ivar(prior_->siginv());
   Vector ivar_mu(suf_.xty());
@@ -1118,13 +1207,24 @@ BinomialLogitSpikeSlabSampler::BinomialLogitSpikeSlabSampler(BinomialLogitModel 
 }
 
 void BinomialLogitSpikeSlabSampler::draw() {
-  impute_latent_data();
+  if (!(active_.enabled && impute_latent_data_active(model_->coef().inc().included_positions()))) impute_latent_data();
   if (core_.model_selection_allowed()) draw_model_indicators();
   draw_beta();
 }
 double BinomialLogitSpikeSlabSampler::logpri() const { return core_.logpri(model_->coef()); }
-void BinomialLogitSpikeSlabSampler::draw_model_indicators() { core_.draw_model_indicators(rng(), model_->coef(), suf()); }
-void BinomialLogitSpikeSlabSampler::draw_beta() { core_.draw_beta(rng(), model_->coef(), suf()); }
+void BinomialLogitSpikeSlabSampler::draw_model_indicators() {
+  std::unique_ptr<StatView> v(statistics_view());
+  core_.draw_model_indicators(rng(), model_->coef(), *v);
+  if (active_.valid) {   // the columns the sweep fetched stay with the state: draw_beta reads them next
+    // (the view copied the active arrays; re-run of statistics_view() for draw_beta would refetch, so keep what it holds)
+    kept_view_ = std::move(v);
+  }
+}
+void BinomialLogitSpikeSlabSampler::draw_beta() {
+  if (active_.valid && kept_view_) { core_.draw_beta(rng(), model_->coef(), *kept_view_); kept_view_.reset(); return; }
+  std::unique_ptr<StatView> v(statistics_view());
+  core_.draw_beta(rng(), model_->coef(), *v);
+}
 double BinomialLogitSpikeSlabSampler::log_model_prob(const Selector &g) const { return core_.log_model_prob(g, suf()); }
 std::shared_ptr<BinomialLogitSpikeSlabSampler> BinomialLogitSpikeSlabSampler::clone_to_new_host(BinomialLogitModel *new_host) const {
   auto s = std::make_shared<BinomialLogitSpikeSlabSampler>(new_host, core_.slab(), core_.spike(), clt_threshold(), rng());

@@ -360,6 +360,33 @@ class WeightedRegSuf {
 };
 typedef WeightedRegSuf SufficientStatistics;
 
+// What the spike-and-slab host steps read of the complete-data statistics: entries of X'WX and X'Wz.  Either the full
+// matrix (a WeightedRegSuf), or the ACTIVE-SET form: the columns of the variables in the model, the diagonal
+// and X'Wz, as an active-set device step returns them, with any further column fetched from the device on demand
+// (boomgpu_weighted_column: the latents stay in HBM until the next step).  A sweep reads X'WX[j, gamma + {j}] only, so the
+// active form answers every proposal from what it holds; a column is fetched when the sweep ADDS a variable outside it.
+class StatView {
+ public:
+  explicit StatView(const WeightedRegSuf &full);
+  // active form: cols = the columns held (G is p x cols.size(), row major), fetch(j, out) writes column j of X'WX (p doubles)
+  StatView(int p, const std::vector<int> &cols, const Vector &G, const Vector &diag, const Vector &xty,
+           std::function<void(int, double *)> fetch);
+  double at(int i, int j);               // (X'WX)[i, j]
+  double xty(int j) const { return xty_[j]; }
+  void ensure_column(int j);             // active form: make column j resident (no-op in the full form / when it is held)
+  int columns_fetched() const { return fetched_; }
+  bool is_full() const { return full_ != nullptr; }
+
+ private:
+  const double *full_ = nullptr;
+  int p_ = 0, ld_ = 0, k_ = 0, fetched_ = 0;
+  std::vector<int> where_;               // column -> slot in G_, or -1
+  Vector G_, diag_;
+  const double *xty_ = nullptr;
+  std::function<void(int, double *)> fetch_;
+  Vector column_;
+};
+
 // The host-side spike-and-slab steps shared by the logit and Poisson samplers
 // (BinomialLogitSpikeSlabSampler.cpp:56-117,180-222; SpikeSlabSampler.cpp:40-216 with sigsq = 1).
 class SpikeSlabCore {
@@ -369,6 +396,10 @@ class SpikeSlabCore {
   double log_model_prob(const Selector &g, const WeightedRegSuf &suf) const;
   void draw_model_indicators(RNG &rng, GlmCoefs &coef, const WeightedRegSuf &suf) const;
   void draw_beta(RNG &rng, GlmCoefs &coef, const WeightedRegSuf &suf) const;
+  // the same on a view of the statistics (full or active-set form)
+  double log_model_prob(const Selector &g, StatView &stats) const;
+  void draw_model_indicators(RNG &rng, GlmCoefs &coef, StatView &stats) const;
+  void draw_beta(RNG &rng, GlmCoefs &coef, StatView &stats) const;
   double logpri(const GlmCoefs &coef) const;
   void allow_model_selection(bool tf) { allow_model_selection_ = tf; }
   void limit_model_selection(int max_flips) { max_flips_ = max_flips; }
@@ -387,6 +418,8 @@ class SpikeSlabCore {
   // way the sweep evaluates it (bordered Cholesky factors); the last entry is the final model's value
   Vector flip_path_log_probs(const Selector &start, const WeightedRegSuf &suf, const std::vector<int> &flips,
                              const std::vector<bool> &accept) const;
+  Vector flip_path_log_probs(const Selector &start, StatView &stats, const std::vector<int> &flips,
+                             const std::vector<bool> &accept) const;
 
  private:
   class FlipEvaluator;
@@ -395,6 +428,17 @@ class SpikeSlabCore {
   bool fisher_yates_;
   bool allow_model_selection_ = true;
   int max_flips_ = -1;
+};
+
+// State of the active-set form of a spike-and-slab sampler's statistics (see StatView): what the last device step returned
+// for the columns of the model's included variables.
+struct ActiveSetState {
+  bool enabled = false;        // the sampler option
+  bool valid = false;          // the last imputation ran in active-set form (suf_ then lags until somebody asks for it)
+  std::vector<int> cols;
+  Vector G, diag, xty;
+  double scalars[4] = {0, 0, 0, 0};
+  int64_t columns_fetched = 0; // over the life of the sampler (a sweep fetches one per accepted add outside the set)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -406,11 +450,12 @@ class BinomialLogitAuxmixSampler : public PosteriorSampler {
   double logpri() const override;
   void impute_latent_data();           // ONE device step instead of the worker pool
   void draw_params();                  // .cpp:125-130
-  const SufficientStatistics &suf() const { return suf_; }
+  // the full statistics; after an active-set step they are computed on demand from the latents still in HBM
+  const SufficientStatistics &suf() const { if (active_.valid) materialize_full_statistics(); return suf_; }
   int clt_threshold() const { return clt_threshold_; }
-  void clear_complete_data_sufficient_statistics() { suf_.clear(); }
+  void clear_complete_data_sufficient_statistics() { active_.valid = false; suf_.clear(); }
   void update_complete_data_sufficient_statistics(double precision_weighted_sum, double total_precision,
-                                                  const Vector &x) { suf_.update(x, precision_weighted_sum, total_precision); }
+                                                  const Vector &x) { active_.valid = false; suf_.update(x, precision_weighted_sum, total_precision); }
   // LatentDataSampler surface (Models/PosteriorSamplers/Imputer.hpp:260-314)
   void fix_latent_data(bool fixed = true) { latent_data_fixed_ = fixed; }
   void set_number_of_workers(int) {}       // the device replaces the worker pool
@@ -419,11 +464,18 @@ class BinomialLogitAuxmixSampler : public PosteriorSampler {
 
  protected:
   void on_seed() override;
+  // active-set form of the imputation (p > 64, no caller-supplied all-reduce hook): statistics for the columns `cols`;
+  // returns false (and does nothing) where it does not apply, and the caller runs the full step
+  bool impute_latent_data_active(const std::vector<int> &cols);
+  // the statistics the host steps read: the active-set form when the last imputation produced it, the full matrix otherwise
+  std::unique_ptr<StatView> statistics_view();
+  void materialize_full_statistics() const;
   BinomialLogitModel *model_;
   std::shared_ptr<MvnBase> prior_;
+  mutable ActiveSetState active_;
 
  private:
-  SufficientStatistics suf_;
+  mutable SufficientStatistics suf_;
   int clt_threshold_;
   bool latent_data_fixed_ = false;
   uint64_t device_seed_, iteration_ = 0;
@@ -444,6 +496,13 @@ class BinomialLogitSpikeSlabSampler : public BinomialLogitAuxmixSampler {
   void limit_model_selection(int max_flips) { core_.limit_model_selection(max_flips); }
   void set_spike(const std::shared_ptr<VariableSelectionPrior> &spike) { core_.set_spike(spike); }
   void set_slab(const std::shared_ptr<MvnBase> &slab) { core_.set_slab(slab); prior_ = slab; }
+  // Active-set statistics (off by default): each iteration the device computes X'WX only for the columns of the
+  // variables in the model (plus the diagonal and X'Wz) and the sweep fetches a further column when it adds a variable --
+  // the same chain as with the full matrix (the sweep reads nothing else), for n p (2 |gamma| + 4) instead of n p (p + 1)
+  // flops.  suf() still answers with the full matrix (computed on demand).  Applies to p > 64 without an all-reduce hook.
+  void set_active_set_statistics(bool tf) { active_.enabled = tf; }
+  bool active_set_statistics() const { return active_.enabled; }
+  int64_t active_set_columns_fetched() const { return active_.columns_fetched; }
   // clone_to_new_host (.cpp:42-48): the same priors and settings on another model, seeded from this sampler's stream
   std::shared_ptr<BinomialLogitSpikeSlabSampler> clone_to_new_host(BinomialLogitModel *new_host) const;
   int xdim() const { return model_->xdim(); }
@@ -454,6 +513,7 @@ class BinomialLogitSpikeSlabSampler : public BinomialLogitAuxmixSampler {
 
  private:
   SpikeSlabCore core_;
+  std::unique_ptr<StatView> kept_view_;
   bool posterior_mode_found_ = false;
   double log_posterior_at_mode_ = -1.0 / 0.0;
 };

@@ -225,7 +225,10 @@ PYBIND11_MODULE(_host, m) {
       .def_property_readonly("posterior_mode_found", &BinomialLogitSpikeSlabSampler::posterior_mode_found)
       .def_property_readonly("log_posterior_at_mode", &BinomialLogitSpikeSlabSampler::log_posterior_at_mode)
       .def("allow_model_selection", &BinomialLogitSpikeSlabSampler::allow_model_selection)
-      .def("limit_model_selection", &BinomialLogitSpikeSlabSampler::limit_model_selection);
+      .def("limit_model_selection", &BinomialLogitSpikeSlabSampler::limit_model_selection)
+      .def("set_active_set_statistics", &BinomialLogitSpikeSlabSampler::set_active_set_statistics)
+      .def_property_readonly("active_set_statistics", &BinomialLogitSpikeSlabSampler::active_set_statistics)
+      .def_property_readonly("active_set_columns_fetched", &BinomialLogitSpikeSlabSampler::active_set_columns_fetched);
 
   py::class_<BinomialProbitSpikeSlabSampler, PosteriorSampler, std::shared_ptr<BinomialProbitSpikeSlabSampler>>(
       m, "BinomialProbitSpikeSlabSampler")

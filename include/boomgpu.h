@@ -72,9 +72,9 @@ int boomgpu_set_stream(boomgpu_ctx *ctx, void *cuda_stream);
 /* global index of this shard's first row: keys the Philox counters so draws do not depend on the sharding */
 int boomgpu_set_row_offset(boomgpu_ctx *ctx, uint64_t first_global_row);
 /* options: "path" = 0 auto | 1 fused single pass (p <= 64) | 2 two-pass imputer + DMMA SYRK;
- *          "small_variant" = 0 auto (TMA-fed kernels when X has an even leading dimension and a 16-byte aligned base:
- *                            warp-autonomous for p <= 40, warp-specialised above) | 1 force the cp.async kernel |
- *                            2 the warp-autonomous TMA kernel for every p <= 64;
+ *          "small_variant" = 0 auto (the TMA-fed warp-autonomous kernel when X has an even leading dimension and a 16-byte
+ *                            aligned base) | 1 force the cp.async kernel | 2 = 0 | 3 the warp-specialised kernel for
+ *                            40 < p <= 64 (accumulate warps + draw warps: measured no faster, kept as an experiment);
  *          "single_launch" = 1 (default) the small-p step is one kernel whose last CTA sums the per-CTA partials | 0 a
  *                            separate reduction kernel;
  *          "gather" = 0 auto (two-pass path: a beta with fewer than p / 4 non-zeros reads only those columns of X in the
@@ -133,6 +133,20 @@ int boomgpu_probit_step(boomgpu_ctx *ctx, const double *beta, int clt_threshold,
                         double *xtx, double *xtz, int64_t *sample_size);
 int boomgpu_probit_step_device(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
                                double *suf_dev, int xtz_only);
+
+/* ACTIVE-SET form of the step (p > 64).  A sweep over the inclusion indicators reads of X'WX only the columns of the
+ * variables in the model and the diagonal (log_model_prob selects sub-blocks, BinomialLogitSpikeSlabSampler.cpp:88-117), so the
+ * device computes, for the column set `active` (k <= 128 columns, normally the included variables):
+ *   G[j * k + a] = (X'WX)[j, active[a]]  (p x k, row major),  diag[j] = (X'WX)[j, j],  xty = X'Wz
+ * -- n p (2 k + 4) flops and one read of X instead of the n p (p + 1) flops of the full matrix.  The latents (w_i, s_i) stay
+ * in HBM until the next step: boomgpu_weighted_column returns column j of X'WX for them (what the sweep needs when it ADDS a
+ * variable outside `active`: one more pass over X), boomgpu_full_statistics the whole matrix (for suf() consumers). */
+int boomgpu_logit_step_active(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
+                              const int32_t *active, int k, double *G, double *diag, double *xty, int64_t *sample_size);
+int boomgpu_poisson_step_active(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, const int32_t *active,
+                                int k, double *G, double *diag, double *xty, double scalars[4]);
+int boomgpu_weighted_column(boomgpu_ctx *ctx, int j, double *column);
+int boomgpu_full_statistics(boomgpu_ctx *ctx, double *xtx, double *xty);
 
 /* Page-locks a caller-owned host range (cudaHostRegister).  When the xtx / xtwx argument of the synchronous steps points
  * into such a range, the p x p matrix is copied device->host straight into it (at p = 4000 it is 128 MB: the staging

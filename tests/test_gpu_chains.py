@@ -259,3 +259,42 @@ def test_standalone_probit_sampler_recovers_the_coefficients():
     inc = np.mean(draws != 0, axis=0)
     assert np.all(inc[:4] > 0.95) and np.all(inc[4:] < 0.3)
     np.testing.assert_allclose(draws.mean(axis=0)[:4], beta[:4], atol=0.05)
+
+
+def test_active_set_statistics_give_the_same_chain():
+    """set_active_set_statistics(True): the device computes X'WX only for the included columns (+ diagonal, X'Wz) and the sweep
+    fetches a column when it adds a variable.  Same seed -> the same chain as with the full matrix (the sweep reads nothing
+    else of it), and suf still answers with the full statistics, computed on demand from the latents in HBM."""
+    import boom_b200
+    from oracle import oracle as O
+    n, p = 30_000, 150
+    X, y, nt, beta_true = O.synth_binomial(n, p, 6, seed=77, max_trials=1)
+    chains = []
+    fetched = 0
+    for active in (False, True):
+        model = boom_b200.BinomialLogitModel(X, y, nt)
+        s = boom_b200.BinomialLogitSpikeSlabSampler(model, boom_b200.MvnModel(np.zeros(p), np.eye(p)),
+                                                    boom_b200.VariableSelectionPrior(p, 6.0 / p), 10, boom_b200.RNG(21))
+        s.set_active_set_statistics(active)
+        model.set_method(s)
+        model.drop_all()
+        model.add(0)
+        out = []
+        for it in range(40):
+            model.sample_posterior()
+            out.append(np.array(model.Beta))
+        chains.append(np.array(out))
+        if active:
+            fetched = s.active_set_columns_fetched
+            xtx_on_demand = np.array(s.suf.xtx)          # the full matrix of the last iteration's latents
+            assert xtx_on_demand.shape == (p, p) and np.all(np.isfinite(xtx_on_demand))
+            np.testing.assert_array_equal(xtx_on_demand, xtx_on_demand.T)
+            assert s.suf.sample_size == n
+        else:
+            full_last = np.array(s.suf.xtx)
+    # identical decisions, coefficients equal up to the summation order of the two device kernels
+    assert np.array_equal(chains[0] != 0, chains[1] != 0)
+    np.testing.assert_allclose(chains[1], chains[0], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(xtx_on_demand, full_last, rtol=1e-9, atol=1e-9)
+    assert fetched >= 6        # the six true variables entered one by one, each through a fetched column
+    assert np.count_nonzero(chains[1][-1]) >= 6

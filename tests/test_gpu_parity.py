@@ -217,7 +217,7 @@ def test_poisson_indicators_exact_at_scale():
                                       (33, 1, "logit"), (100_000, 7, "logit")])
 def test_small_p_variants_agree_with_oracle(n, p, kind):
     """p <= 64: the TMA-fed warp-autonomous kernel (default) and the cp.async kernel (X that TMA cannot describe)."""
-    for variant in (0, 1):
+    for variant in (0, 1, 3):
         if kind == "logit":
             X, y, nt, beta = O.synth_binomial(n, p, min(3, p - 1), seed=50 + p, max_trials=2)
             ctx, mix = logit_ctx(X, y, nt)

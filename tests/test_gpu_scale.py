@@ -290,3 +290,49 @@ def test_gather_imputer_pass_matches_the_dense_pass(n, p, nnz):
         assert ss == rss == n
         assert normwise_err(xtx, rxtx) < 1e-11 and vec_err(xty, rxty) < 1e-10
         ctx.close()
+
+
+# ---------------------------------------------------------------- active-set statistics
+@pytest.mark.parametrize("n,p,k", [(5003, 200, 1), (4001, 500, 21), (3000, 130, 40), (2500, 1000, 128), (6000, 300, 9)])
+def test_active_set_step_matches_the_full_statistics(n, p, k):
+    """boomgpu_logit_step_active: G = (X'WX)[:, active], the diagonal and X'Wz of the SAME latents as the full step (same seed,
+    same iteration) -- against the oracle's full matrix; boomgpu_weighted_column returns any other column for those latents,
+    boomgpu_full_statistics the whole matrix."""
+    X, y, nt, _ = O.synth_binomial(n, p, 5, seed=500 + k, max_trials=3)
+    rng = np.random.default_rng(k)
+    active = np.sort(rng.choice(p, size=k, replace=False))
+    beta = np.zeros(p)
+    beta[active] = rng.normal(size=k) * 0.3
+    mix = O.logit_mixture()
+    rxtx, rxty, rss, _ = O.logit_step(X, y, nt, beta, 10, mix, 19, 4)
+    d = np.sqrt(np.diag(rxtx))
+    ctx, _ = logit_ctx(X, y, nt)
+    G, diag, xty, ss = ctx.logit_step_active(beta, 10, 19, 4, active)
+    assert ss == rss == n
+    assert np.max(np.abs(G - rxtx[:, active]) / np.outer(d, d[active])) < 1e-11
+    assert np.max(np.abs(diag - np.diag(rxtx)) / (d * d)) < 1e-11
+    assert vec_err(xty, rxty) < 1e-10
+    for j in (0, p // 2, p - 1):
+        col = ctx.weighted_column(j)
+        assert np.max(np.abs(col - rxtx[:, j]) / (d * d[j])) < 1e-11
+    xtx, xty2 = ctx.full_statistics()
+    assert normwise_err(xtx, rxtx) < 1e-11 and vec_err(xty2, rxty) < 1e-10
+    ctx.close()
+
+
+def test_active_set_poisson_step():
+    n, p, k = 4000, 150, 12
+    X, y, ex, _ = O.synth_poisson(n, p, 4, seed=520)
+    rng = np.random.default_rng(2)
+    active = np.sort(rng.choice(p, size=k, replace=False))
+    beta = np.zeros(p)
+    beta[active] = rng.normal(size=k) * 0.2
+    ctx, tab = poisson_ctx(X, y, ex)
+    G, diag, xty, sc = ctx.poisson_step_active(beta, 23, 2, active)
+    rxtx, rxty, rsc = O.poisson_step(X, y, ex, beta, tab, 23, 2)
+    d = np.sqrt(np.diag(rxtx))
+    assert np.max(np.abs(G - rxtx[:, active]) / np.outer(d, d[active])) < 1e-11
+    assert np.max(np.abs(diag - np.diag(rxtx)) / (d * d)) < 1e-11
+    assert vec_err(xty, rxty) < 1e-10
+    np.testing.assert_allclose(sc, rsc, rtol=1e-10)
+    ctx.close()
