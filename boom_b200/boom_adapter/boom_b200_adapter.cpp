@@ -202,6 +202,8 @@ bool DeviceImputerBase::find_mode(GlmCoefs &coef, const Ptr<MvnBase> &slab, cons
 
 void DeviceImputerBase::impute_latent_data() {
   if (latent_data_fixed_) return;  // statistics are under external control (Imputer.hpp:282-299)
+  active_.valid = false;
+  view_.reset();
   Stopwatch sw(secs_device_);
   ensure_device_rows();
   const int p = xdim_;
@@ -225,7 +227,49 @@ void DeviceImputerBase::impute_latent_data() {
   statistics_changed();
 }
 
+int DeviceImputerBase::device_step_active(boomgpu_ctx *, const double *, uint64_t, uint64_t, const int32_t *, int, double *, double *,
+                                          double *, double *) {
+  return -1;   // this sampler has no active-set form
+}
+
+bool DeviceImputerBase::impute_latent_data_active(const Selector &inc) {
+  const int p = xdim_;
+  if (!active_.enabled || latent_data_fixed_ || p <= 64 || allreduce_ || inc.nvars() > 128) return false;
+  Stopwatch sw(secs_device_);
+  ensure_device_rows();
+  std::vector<int32_t> cols;
+  for (int j = 0; j < p; ++j) if (inc[j]) cols.push_back(j);
+  if (cols.empty()) cols.push_back(0);
+  const int k = (int)cols.size();
+  active_.cols.assign(cols.begin(), cols.end());
+  active_.G.resize((size_t)p * k); active_.diag.resize(p); active_.xty.resize(p);
+  const uint64_t seed = rng().generator()();
+  const int rc = device_step_active(ctx_, current_beta().data(), seed, iteration_, cols.data(), k, active_.G.data(), active_.diag.data(),
+                                    active_.xty.data(), active_.scalars);
+  if (rc == -1) return false;
+  ++iteration_;
+  check(rc);
+  active_.valid = true;
+  boomgpu_ctx *ctx = ctx_;
+  BOOM_B200::ActiveSetState *st = &active_;
+  view_.reset(new BOOM_B200::StatView(p, active_.cols, active_.G, active_.diag, active_.xty, [this, ctx, st](int j, double *out) {
+    check(boomgpu_weighted_column(ctx, j, out));
+    ++st->columns_fetched;
+  }));
+  statistics_changed();
+  return true;
+}
+
+void DeviceImputerBase::materialize_full_statistics() const {
+  if (!active_.valid) return;
+  if (int rc = boomgpu_full_statistics(ctx_, hsuf_.xtx_storage(xdim_), hsuf_.xty_storage()))
+    report_error(std::string("boomgpu: ") + boomgpu_last_error(ctx_));
+  hsuf_.set_scalars(active_.scalars[0], active_.scalars[1], active_.scalars[2], active_.scalars[3]);
+  active_.valid = false;
+}
+
 void DeviceImputerBase::draw_beta_full_model(GlmCoefs &coef, const MvnBase &prior) {
+  materialize_full_statistics();
   Stopwatch sw(secs_host_);
   // ivar = Omega^-1 + X'WX, ivar_mu = X'Wz + Omega^-1 mu_0, then BOOM's own rmvn_suf_mt (distributions/mvn.cpp:128-136).
   // BOOM::SpdMatrix is column major and symmetric: the same bytes as the row-major host matrix.
@@ -288,7 +332,8 @@ void DeviceImputerBase::sweep_indicators(GlmCoefs &coef, const BOOM_B200::SpikeS
   Stopwatch sw(secs_host_);
   BOOM_B200::GlmCoefs h = host_coefs(coef, xdim_, true);
   BOOM_B200::RNG local(rng().generator()());   // see impute_latent_data() on why not seed_rng()
-  c.draw_model_indicators(local, h, hsuf_);    // reads the statistics in place: externally driven ones (fix_latent_data) too
+  if (active_.valid && view_) c.draw_model_indicators(local, h, *view_);   // active-set form: fetches a column per accepted add
+  else c.draw_model_indicators(local, h, hsuf_);   // reads the statistics in place: externally driven ones (fix_latent_data) too
   write_back(coef, h, xdim_, false);
 }
 
@@ -296,11 +341,13 @@ void DeviceImputerBase::draw_included_beta(GlmCoefs &coef, const BOOM_B200::Spik
   Stopwatch sw(secs_host_);
   BOOM_B200::GlmCoefs h = host_coefs(coef, xdim_, false);
   BOOM_B200::RNG local(rng().generator()());
-  c.draw_beta(local, h, hsuf_);
+  if (active_.valid && view_) c.draw_beta(local, h, *view_);
+  else c.draw_beta(local, h, hsuf_);
   write_back(coef, h, xdim_, true);
 }
 
 double DeviceImputerBase::model_log_prob(const Selector &g, const BOOM_B200::SpikeSlabCore &c) const {
+  materialize_full_statistics();
   BOOM_B200::Selector h((int)g.nvars_possible(), false);
   for (int i = 0; i < (int)g.nvars_possible(); ++i) if (g[i]) h.add(i);
   return c.log_model_prob(h, hsuf_);
@@ -344,6 +391,7 @@ BinomialLogitAuxmixSampler::BinomialLogitAuxmixSampler(BinomialLogitModel *model
 }
 
 const BinomialLogit::SufficientStatistics &BinomialLogitAuxmixSampler::suf() const {
+  materialize_full_statistics();
   if (!suf_synced_) {
     const int p = xdim_;
     SpdMatrix &xtx(suf_.*member_pointer(SufXtx()));
@@ -400,6 +448,14 @@ int BinomialLogitAuxmixSampler::device_step_sync(boomgpu_ctx *ctx, const double 
   return rc;
 }
 
+int BinomialLogitAuxmixSampler::device_step_active(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration,
+                                                   const int32_t *cols, int k, double *G, double *diag, double *xty, double scalars[4]) {
+  int64_t ss = 0;
+  const int rc = boomgpu_logit_step_active(ctx, beta, clt_threshold_, seed, iteration, cols, k, G, diag, xty, &ss);
+  scalars[0] = (double)ss; scalars[1] = scalars[2] = scalars[3] = 0.0;
+  return rc;
+}
+
 int BinomialLogitAuxmixSampler::device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) {
   return boomgpu_binomial_loglike_derivs(ctx, beta, model_->log_alpha(), loglike, g, h);   // BinomialLogitModel.cpp:168
 }
@@ -437,7 +493,7 @@ BinomialLogitSpikeSlabSampler *BinomialLogitSpikeSlabSampler::clone_to_new_host(
                                            clt_threshold(), rng());
 }
 void BinomialLogitSpikeSlabSampler::draw() {   // BinomialLogitSpikeSlabSampler.cpp:50-54
-  impute_latent_data();
+  if (!impute_latent_data_active(model_->coef().inc())) impute_latent_data();
   if (allow_model_selection_) draw_model_indicators();
   draw_beta();
 }
@@ -738,6 +794,7 @@ PoissonRegressionAuxMixSampler::PoissonRegressionAuxMixSampler(PoissonRegression
 }
 
 const WeightedRegSuf &PoissonRegressionAuxMixSampler::complete_data_sufficient_statistics() const {
+  materialize_full_statistics();
   if (!suf_synced_) {
     const int p = xdim_;
     SpdMatrix xtx(p);

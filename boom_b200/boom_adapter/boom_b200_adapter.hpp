@@ -74,6 +74,12 @@ class DeviceImputerBase : public PosteriorSampler {
   void set_allreduce(const BOOM_B200::AllReduceFn &fn) { allreduce_ = fn; }
   // or natively: join an NCCL communicator (id from BOOM_B200::GlmModelBase::comm_unique_id() on rank 0)
   void set_communicator(const std::string &id, int nranks, int rank) { comm_id_ = id; comm_ranks_ = nranks; comm_rank_ = rank; comm_dirty_ = true; }
+  // Active-set statistics (off by default; spike-and-slab samplers, p > 64, no all-reduce hook): the device computes
+  // X'WX for the columns of the included variables only (+ diagonal, X'Wz), the sweep fetches a column when it adds a variable;
+  // the same chain as with the full matrix.  The reference-typed statistics accessors still answer with the full matrix,
+  // computed on demand from the latents that stay in HBM.
+  void set_active_set_statistics(bool tf) { active_.enabled = tf; }
+  int64_t active_set_columns_fetched() const { return active_.columns_fetched; }
   // wall-clock seconds this sampler has spent in: the device step (incl. copies), the host small-state steps
   double seconds_in_device_step() const { return secs_device_; }
   double seconds_in_host_steps() const { return secs_host_; }
@@ -92,6 +98,10 @@ class DeviceImputerBase : public PosteriorSampler {
   virtual int device_step_sync(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *xtx, double *xty,
                                double scalars[4]) = 0;
   virtual const Vector &current_beta() const = 0;
+  virtual int device_step_active(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, const int32_t *cols, int k,
+                                 double *G, double *diag, double *xty, double scalars[4]);   // default: not provided
+  bool impute_latent_data_active(const Selector &inc);   // false: does not apply here, run the full step
+  void materialize_full_statistics() const;              // after an active-set step: the full matrix from the latents in HBM
   // log likelihood with gradient / Hessian at a full coefficient vector, one device pass (boomgpu_*_loglike_derivs)
   virtual int device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) = 0;
   virtual int device_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) = 0;
@@ -119,7 +129,9 @@ class DeviceImputerBase : public PosteriorSampler {
   void priors_changed() { ++prior_version_; }
   void *observer_key() { return static_cast<void *>(this); }
 
-  BOOM_B200::WeightedRegSuf hsuf_;   // where the device step lands and the host steps read
+  mutable BOOM_B200::WeightedRegSuf hsuf_;   // where the device step lands and the host steps read
+  mutable BOOM_B200::ActiveSetState active_;
+  std::unique_ptr<BOOM_B200::StatView> view_;   // the active-set view of the current iteration (sweep, then beta)
   int xdim_;
 
  private:
@@ -163,6 +175,8 @@ class BinomialLogitAuxmixSampler : public DeviceImputerBase {
   int device_loglike_derivs_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) override;
   int device_loglike_derivs_selected(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) override;
   int device_loglike_derivs_selected_device(boomgpu_ctx *ctx, const double *beta, double *suf_dev) override;
+  int device_step_active(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, const int32_t *cols, int k,
+                         double *G, double *diag, double *xty, double scalars[4]) override;
   const Vector &current_beta() const override { return model_->Beta(); }
   void statistics_changed() override { suf_synced_ = false; }
   BinomialLogitModel *model_;
