@@ -121,7 +121,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -148,7 +148,7 @@ class ClockSampler:
         sm = sorted(float(r[0]) for r in rows)
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         reasons = [nm for k, nm in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
-        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_mhz_min": sm[0], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
                "samples": len(rows), "reasons": reasons}
         if note:
             out["note"] = note
@@ -262,7 +262,7 @@ class Bench:
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.stream = torch.cuda.Stream(device=self.dev)
-        self.clocks = ClockSampler(self.local_rank) if self.rank == 0 else None
+        self.clocks = ClockSampler(self.local_rank) if self.rank == 0 and not os.environ.get("BENCH_NO_CLOCK_SAMPLER") else None
         self.peaks, self.peak_src = measured_peaks()
         self.traffic = ncu_traffic()
 

@@ -1,19 +1,23 @@
 // fused_tma.cuh -- the single-pass kernel for p <= 64 (configs C1, C2, C5): TMA-fed, warp-autonomous.
 //
 //   One persistent CTA per SM, NW warps, no block-wide barrier in the steady state.  Every warp owns a ring of
-//   S slices in shared memory; a slice is 32 consecutive observations x (8 NB + 4) doubles, written by ONE
+//   S slices in shared memory; a slice is 32 RPL consecutive observations x (8 NB + 2) doubles, written by ONE
 //   cp.async.bulk.tensor.2d (TMA tile of the row-major X; the box is wider than p, so the pad columns arrive as
 //   zeros, and rows beyond n arrive as zeros too) that completes on the slice's mbarrier.  The warp that consumes a
 //   slice also re-arms it (lane 0 issues the copy S slices ahead right after the warp's last read), so there is no
 //   producer warp and no "empty" barrier.
-//   Per slice, lane r owns observation r:  eta = x_r . beta from shared memory (conflict free: the row stride is
-//   4 mod 8 doubles and the start column is rotated by (r >> 2) & 3), the latent draw (Philox keyed by the global
-//   row; y_r / n_r were fetched one slice ahead), then the warp accumulates its 32 rank-1 updates with FP64 DMMA
-//   (m8n8k4; A = w_k x_k fragments, B = x_k fragments straight from the slice; (w_k, s_k) sit in the two pad columns
-//   of row k) into the upper triangle of X'WX held in registers (NB (NB + 1) / 2 atoms), and X'Wz with NB DFMA per
-//   4 rows.  beta arrives as a kernel parameter.
-//   Epilogue: warps add their fragments into one shared tile in warp order, the CTA writes one partial, and
-//   reduce_partials_kernel sums the partials in CTA order (deterministic: no floating point atomics).
+//   Per slice, lane r owns observations r, r + 32, ... (RPL of them: independent dependency chains the scheduler
+//   interleaves):  eta = x_r . beta with 16-byte loads from shared memory (conflict free by the row pitch alone, see
+//   tma_padw; beta comes from the constant bank with compile-time indices), the latent draw (Philox keyed by the
+//   global row; y_r / n_r were fetched one slice ahead), then the warp accumulates the slice's rank-1 updates with
+//   FP64 DMMA (m8n8k4; A = w_k x_k fragments, B = x_k fragments straight from the slice; (w_k, s_k) sit in the two pad
+//   columns of row k) into the upper triangle of X'WX held in registers (NB (NB + 1) / 2 atoms), and X'Wz with NB
+//   DFMA per 4 rows.  beta arrives as a kernel parameter.
+//   Epilogue: the warps add their fragments into one shared tile (warp-tile parallel, fixed order per element), the CTA
+//   writes one partial, and the LAST CTA to finish (a counter in global memory, __threadfence on both sides) sums the
+//   partials in CTA order -- one thread per output element, 16 loads in flight -- and writes the statistics to the
+//   device buffer and to the host-mapped copy: one launch per Gibbs step, deterministic (no floating point atomics).
+//   Option single_launch = 0 keeps the separate reduce_partials_kernel.
 //
 //   Algorithmic traffic: 8 (p + 2) bytes per observation, read once.
 //   Reference equivalent: Imputer.hpp:175-180 over BinomialLogitAuxmixSampler.cpp:61-97 /

@@ -16,6 +16,7 @@ CFG = {
     "c4": ("logit", 2_000_000, 4000), "c5": ("logit", 25_000_000, 16), "c3s": ("logit", 1_000_000, 500),
     "p128": ("logit", 4_000_000, 128), "p64": ("logit", 8_000_000, 64), "p32": ("logit", 8_000_000, 32),
     "c4s": ("logit", 500_000, 4000), "p1000": ("logit", 2_000_000, 1000), "p260": ("logit", 4_000_000, 260),
+    "c5m": ("logit", 100_000_000, 16), "c5f": ("logit", 200_000_000, 16), "c2x4": ("poisson", 4_000_000, 50),
     "p8": ("logit", 25_000_000, 8), "p24": ("logit", 12_000_000, 24), "p48": ("poisson", 4_000_000, 48),
 }
 
@@ -65,16 +66,23 @@ def main():
              else ctx.poisson_step_device(beta, 1, it, suf.data_ptr()))
         ctx.synchronize(); ctx.timings(reset=True)
         t0 = time.perf_counter()
+        mode = os.environ.get("QP_MODE", "")   # "": queued back to back; "sync": wait after every step; "host": the host-result entry
         for it in range(iters):
+            if mode == "host" and kind == "logit":
+                ctx.logit_step(beta, 10, 1, 10 + it)
+                continue
             (ctx.logit_step_device(beta, 10, 1, 10 + it, suf.data_ptr()) if kind == "logit"
              else ctx.poisson_step_device(beta, 1, 10 + it, suf.data_ptr()))
+            if mode == "sync":
+                ctx.synchronize()
+                time.sleep(float(os.environ.get("QP_SLEEP", "0")))
         ctx.synchronize()
         wall = (time.perf_counter() - t0) / iters * 1e3
         tm = ctx.timings()
         per = {k: round(v[0] / max(1, iters), 4) for k, v in tm.items() if v[1]}
         bytes_ = 8.0 * n * (p + 2); flops = float(n) * p * (p + 1) + 4.0 * n * p
         dev_ms = sum(per.values())
-        print(json.dumps({"cfg": name, "kind": kind, "n": n, "p": p, "wall_ms": round(wall, 4), "kernel_ms": per,
+        print(json.dumps({"mode": mode, "cfg": name, "kind": kind, "n": n, "p": p, "wall_ms": round(wall, 4), "kernel_ms": per,
                           "GBps_alg": round(bytes_ / dev_ms * 1e-6, 1), "TFLOPs_alg": round(flops / dev_ms * 1e-9, 2)}), flush=True)
         ctx.close()
         del X, y, aux, suf
