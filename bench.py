@@ -420,6 +420,23 @@ class Bench:
         roof["traffic"] = tr["bytes_per_row"] * my_rows if tr else None
         roof["traffic_source"] = tr["source"] if tr else None
         roof["kernel_ms_per_step"] = {k: round(v[0] * v[1] / steps, 4) for k, v in per.items() if v[1]}
+        # HBM-bound kernels that also keep the FP64 pipes busy pull the board to its power cap after ~60 ms of back-to-back
+        # launches (profiles/README.md, "Burst vs sustained"): the timed region above is the sustained figure; after a 2 s
+        # pause the first launches run at the full clock -- reported beside it, never instead of it
+        # (the decision is taken on the max over ranks: the extra iterations all-reduce, every rank must run them or none)
+        if roof["bound"] == "hbm" and not self.args.no_burst and self.max_over_ranks(k_ms) >= 3.0:
+            key = "syrk_dmma" if p > 64 else "fused_small"
+            self.torch.cuda.synchronize()
+            time.sleep(2.0)
+            model.kernel_timings(True)
+            for _ in range(4):
+                model.sample_posterior()
+            self.torch.cuda.synchronize()
+            tb = model.kernel_timings(False)
+            if tb[key][1]:
+                b_ms = tb[key][0] / tb[key][1]
+                roof["burst"] = {"kernel_ms": b_ms, "achieved": roof["achieved"] * k_ms / b_ms, "frac": roof["frac"] * k_ms / b_ms,
+                                 "how": "4 iterations after a 2 s pause (board below its power cap, SM clock at maximum)"}
 
         # e2e through the sampler surface on a model built from HOST arrays
         e2e_out = None
@@ -586,6 +603,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-array e2e leg (development aid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-burst", action="store_true", help="skip the burst re-measurement of HBM-bound kernels (2 s pause + 4 iterations)")
     ap.add_argument("--no-secondary", action="store_true", help="headline workload only (development aid, profiling)")
     ap.add_argument("--no-selftest", action="store_true", help="skip the N > 1 parity check before timing")
     ap.add_argument("--torch-allreduce", action="store_true",

@@ -4,7 +4,7 @@
 // then attaches EITHER the reference sampler OR the B200 sampler with model->set_method(sampler) and calls
 // model->sample_posterior().  Prints one JSON line with the posterior summaries of both chains on the same
 // data; tests/test_gpu_adapter.py compares them within Monte Carlo error.
-//   usage: boom_adapter_demo <logit|spike|poisson|pspike|mode|pmode|fixed|pfixed|bench|api|composite|chunk|probit|active> n p nonzero iters burn
+//   usage: boom_adapter_demo <logit|spike|poisson|pspike|mode|pmode|fixed|pfixed|bench|api|composite|chunk|probit|active|pactive> n p nonzero iters burn
 //          (mode / pmode: find_posterior_mode; fixed / pfixed: externally driven statistics, host steps only, no GPU;
 //           bench: ms per iteration of the adapter beside the standalone classes; api: the public surface beyond draw())
 #include <chrono>
@@ -75,7 +75,7 @@ int main(int argc, char **argv) {
   const int n = atoi(argv[2]), p = atoi(argv[3]), nonzero = atoi(argv[4]), iters = atoi(argv[5]), burn = atoi(argv[6]);
   try {
     GlobalRng::rng.seed(20261017);
-    const bool poisson = kind == "poisson" || kind == "pspike" || kind == "pmode" || kind == "pfixed";
+    const bool poisson = kind == "poisson" || kind == "pspike" || kind == "pmode" || kind == "pfixed" || kind == "pactive";
     Vector beta(p, 0.0);
     beta[0] = poisson ? 0.5 : -1.0;
     for (int j = 1; j <= nonzero && j < p; ++j) beta[j] = (j % 2) ? 0.5 : -0.5;
@@ -198,23 +198,39 @@ int main(int argc, char **argv) {
       printf(", \"time_report_lines\": %d}\n", (int)std::count(report.begin(), report.end(), '\n'));
       return 0;
     }
-    if (kind == "active") {
-      // the active-set option on the adapter: same seed, full statistics vs active-set statistics -> the same chain
+    if (kind == "active" || kind == "pactive") {
+      // the active-set option on the adapter (logit / Poisson spike-and-slab): same seed, full statistics vs active-set
+      // statistics -> the same chain
       std::vector<Vector> chain[2];
       long long fetched = 0;
       double xtx_diff = 0;
       SpdMatrix full_last;
       for (int arm = 0; arm < 2; ++arm) {
-        NEW(BinomialLogitModel, model)(p);
-        for (int i = 0; i < n; ++i) model->add_data(new BinomialRegressionData(ys[i], 1.0, xs[i]));
-        model->coef().drop_all(); model->coef().add(0);
         RNG seeder(61);
-        Ptr<B200::BinomialLogitSpikeSlabSampler> s(new B200::BinomialLogitSpikeSlabSampler(model.get(), slab, spike, 10, seeder));
-        s->set_active_set_statistics(arm == 1);
-        model->set_method(s);
-        for (int it = 0; it < iters; ++it) { model->sample_posterior(); chain[arm].push_back(model->Beta()); }
-        if (arm == 0) full_last = s->suf().xtx();
-        else { fetched = s->active_set_columns_fetched(); xtx_diff = (s->suf().xtx() - full_last).max_abs() / full_last.max_abs(); }
+        if (poisson) {
+          NEW(PoissonRegressionModel, model)(p);
+          for (int i = 0; i < n; ++i) model->add_data(new PoissonRegressionData((int64_t)ys[i], xs[i], 1.0));
+          model->coef().drop_all(); model->coef().add(0);
+          Ptr<B200::PoissonRegressionSpikeSlabSampler> s(new B200::PoissonRegressionSpikeSlabSampler(model.get(), slab, spike, 1, seeder));
+          s->set_active_set_statistics(arm == 1);
+          model->set_method(s);
+          for (int it = 0; it < iters; ++it) { model->sample_posterior(); chain[arm].push_back(model->Beta()); }
+          if (arm == 0) full_last = s->complete_data_sufficient_statistics().xtx();
+          else {
+            fetched = s->active_set_columns_fetched();
+            xtx_diff = (s->complete_data_sufficient_statistics().xtx() - full_last).max_abs() / full_last.max_abs();
+          }
+        } else {
+          NEW(BinomialLogitModel, model)(p);
+          for (int i = 0; i < n; ++i) model->add_data(new BinomialRegressionData(ys[i], 1.0, xs[i]));
+          model->coef().drop_all(); model->coef().add(0);
+          Ptr<B200::BinomialLogitSpikeSlabSampler> s(new B200::BinomialLogitSpikeSlabSampler(model.get(), slab, spike, 10, seeder));
+          s->set_active_set_statistics(arm == 1);
+          model->set_method(s);
+          for (int it = 0; it < iters; ++it) { model->sample_posterior(); chain[arm].push_back(model->Beta()); }
+          if (arm == 0) full_last = s->suf().xtx();
+          else { fetched = s->active_set_columns_fetched(); xtx_diff = (s->suf().xtx() - full_last).max_abs() / full_last.max_abs(); }
+        }
       }
       double dmax = 0; bool same_model = true;
       for (int it = 0; it < iters; ++it)
@@ -222,8 +238,9 @@ int main(int argc, char **argv) {
           dmax = std::max(dmax, std::fabs(chain[0][it][j] - chain[1][it][j]));
           same_model = same_model && ((chain[0][it][j] != 0) == (chain[1][it][j] != 0));
         }
-      printf("{\"kind\": \"active\", \"n\": %d, \"p\": %d, \"iters\": %d, \"chain_max_abs_diff\": %.3g, \"same_model\": %s, "
-             "\"columns_fetched\": %lld, \"suf_xtx_rel_diff\": %.3g}\n", n, p, iters, dmax, same_model ? "true" : "false", fetched, xtx_diff);
+      printf("{\"kind\": \"%s\", \"n\": %d, \"p\": %d, \"iters\": %d, \"chain_max_abs_diff\": %.3g, \"same_model\": %s, "
+             "\"columns_fetched\": %lld, \"suf_xtx_rel_diff\": %.3g}\n", kind.c_str(), n, p, iters, dmax, same_model ? "true" : "false", fetched,
+             xtx_diff);
       return 0;
     }
     if (kind == "probit") {

@@ -867,6 +867,10 @@ int PoissonRegressionAuxMixSampler::device_step_sync(boomgpu_ctx *ctx, const dou
                                                      double *xtx, double *xty, double scalars[4]) {
   return boomgpu_poisson_step(ctx, beta, seed, iteration, xtx, xty, scalars);
 }
+int PoissonRegressionAuxMixSampler::device_step_active(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration,
+                                                       const int32_t *cols, int k, double *G, double *diag, double *xty, double scalars[4]) {
+  return boomgpu_poisson_step_active(ctx, beta, seed, iteration, cols, k, G, diag, xty, scalars);
+}
 int PoissonRegressionAuxMixSampler::device_loglike_derivs(boomgpu_ctx *ctx, const double *beta, double *loglike, double *g, double *h) {
   return boomgpu_poisson_loglike_derivs(ctx, beta, loglike, g, h);
 }
@@ -899,7 +903,7 @@ PoissonRegressionSpikeSlabSampler::PoissonRegressionSpikeSlabSampler(PoissonRegr
   if ((int)spike_->potential_nvars() != model_->xdim()) report_error("Spike does not match model dimension.");
 }
 void PoissonRegressionSpikeSlabSampler::draw() {   // PoissonRegressionSpikeSlabSampler.cpp:55-59
-  impute_latent_data();
+  if (!impute_latent_data_active(model_->coef().inc())) impute_latent_data();
   if (allow_model_selection_) draw_model_indicators();
   draw_beta();
 }

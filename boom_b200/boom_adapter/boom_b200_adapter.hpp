@@ -279,6 +279,8 @@ class PoissonRegressionAuxMixSampler : public DeviceImputerBase {
   void install_tables(boomgpu_ctx *ctx) override;
   void pack_rows(int64_t row0, int64_t nrows, double *X, void *y, double *aux) const override;
   void observe_row_objects(bool tf) override;
+  int device_step_active(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, const int32_t *cols, int k,
+                         double *G, double *diag, double *xty, double scalars[4]) override;
   int device_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *suf_dev) override;
   int device_step_sync(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *xtx, double *xty,
                        double scalars[4]) override;

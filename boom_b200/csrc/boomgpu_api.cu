@@ -80,6 +80,8 @@ struct boomgpu_ctx {
   bool xty_only = false;                           // this step wants X'z alone (probit: X'WX is constant)
   int syrk_diag = 0;                               // 0 strip form for whole diagonal regions, 1 unit form everywhere
   int syrk_filter = 0;                             // profiling aid: time the off-diagonal / diagonal regions of the SYRK alone
+  int syrk_order = 1;                              // 1 off-diagonal regions first, diagonal last (short CTAs fill the tail); 0 k-slice major
+  int syrk_waves = 30;                             // CTAs per SM the split-K aims for
   int gather = 0;                                  // option: 0 auto (sparse beta -> gather pass), 1 never, 2 whenever beta has a zero
   double *suf_dev = nullptr; int64_t suf_cap = 0;
   double *suf_pin = nullptr; int64_t suf_pin_cap = 0;
@@ -520,14 +522,16 @@ int launch_syrk(boomgpu_ctx *ctx, double *suf) {
   sp.w = ctx->w_buf; sp.s = ctx->s_buf;
   sp.nblk = (ctx->p + 127) / 128;
   sp.nregions = sp.nblk * (sp.nblk + 1) / 2;
-  // ~20 waves of CTAs for dynamic balance (diagonal regions are cheaper), at least 2048 rows per CTA
-  int64_t ksplit = (20 * (int64_t)ctx->sms + sp.nregions - 1) / sp.nregions;
+  // ~30 CTAs per SM for dynamic balance (measured, profiles/bench_r02/run22_syrk_order.jsonl: 20 -> 30 is worth 0.5-1.5 %
+  // with the off-diagonal-first order; more only adds partial tiles), at least 2048 rows per CTA
+  int64_t ksplit = (ctx->syrk_waves * (int64_t)ctx->sms + sp.nregions - 1) / sp.nregions;
   ksplit = std::min<int64_t>(ksplit, std::max<int64_t>(1, ctx->n / 2048));
   ksplit = std::max<int64_t>(ksplit, 1);
   int64_t rows = (ctx->n + ksplit - 1) / ksplit;
   rows = ((rows + kSyrkKB - 1) / kSyrkKB) * kSyrkKB;
   ksplit = std::max<int64_t>(1, (ctx->n + rows - 1) / rows);
   sp.ksplit = (int)ksplit;
+  sp.order = ctx->syrk_order;
   sp.rows_per_slice = rows;
   const int64_t need = ksplit * sp.nregions * kSyrkTileLen;
   if (ensure(ctx, &ctx->partials, &ctx->partials_cap, need)) return BOOMGPU_ERR_CUDA;
@@ -1049,6 +1053,11 @@ int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value) {
   if (!strcmp(name, "single_launch")) { ctx->single_launch = value != 0; return 0; }
   if (!strcmp(name, "syrk_diag")) { ctx->syrk_diag = value != 0; return 0; }
   if (!strcmp(name, "syrk_filter")) { ctx->syrk_filter = (int)value; return 0; }
+  if (!strcmp(name, "syrk_order")) { ctx->syrk_order = value != 0; return 0; }
+  if (!strcmp(name, "syrk_waves")) {
+    if (value < 1 || value > 256) return fail(ctx, BOOMGPU_ERR_ARG, "syrk_waves must be in 1..256");
+    ctx->syrk_waves = (int)value; return 0;
+  }
   if (!strcmp(name, "gather")) {
     if (value < 0 || value > 2) return fail(ctx, BOOMGPU_ERR_ARG, "gather must be 0 (auto), 1 (never) or 2 (whenever beta has a zero)");
     ctx->gather = (int)value;

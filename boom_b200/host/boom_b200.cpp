@@ -1277,31 +1277,33 @@ void PoissonRegressionAuxMixSampler::draw() {
   impute_latent_data();
   draw_beta_given_complete_data();
 }
-void PoissonRegressionAuxMixSampler::impute_latent_data() {
-  if (latent_data_fixed_) return;
+// The reference extends its table per observation inside the draw (NormalMixtureApproximationTable::approximate,
+// NormalMixtureApproximation.cpp:472-532).  Here: once per (data, table, context), ask the device which counts occur,
+// add the entries the grid lacks by the same rule, then state the table (the C side skips an unchanged upload).
+int PoissonRegressionAuxMixSampler::ensure_table(boomgpu_ctx *ctx) {
   PoissonTableStore &t(poisson_table_store());
   if (t.nu.empty())
     report_error("PoissonRegressionAuxMixSampler: no mixture table; call set_mixture_table with the serialized "
                  "NormalMixtureApproximationTable (see boom_b200/data/poisson_mixture_table.json)");
+  std::lock_guard<std::mutex> guard(t.lock);
+  if (counts_checked_ctx_ != ctx || counts_checked_data_version_ != model_->data_version() || counts_checked_table_version_ != t.version) {
+    std::vector<unsigned char> present((size_t)std::max<int64_t>(t.largest, 1), 0);
+    if (int rc = boomgpu_poisson_counts_present(ctx, present.data(), (int64_t)present.size())) return rc;
+    const size_t before = t.table.size();
+    for (int64_t v = std::max<int64_t>(1, t.table.smallest_index()); v < (int64_t)present.size() && v < t.table.largest_index(); ++v)
+      if (present[(size_t)v] && !t.table.contains(v)) t.table.approximate(v);
+    if (t.table.size() != before) { t.flatten(); ++t.version; }
+    counts_checked_ctx_ = ctx; counts_checked_data_version_ = model_->data_version(); counts_checked_table_version_ = t.version;
+  }
+  return boomgpu_set_poisson_table(ctx, (int)t.nu.size(), t.nu.data(), t.offset.data(), t.weights.data(), t.mu.data(),
+                                   t.sigma.data(), t.largest);
+}
+
+void PoissonRegressionAuxMixSampler::impute_latent_data() {
+  if (latent_data_fixed_) return;
+  active_.valid = false;
   const uint64_t seed = device_seed_, it = iteration_++;
   const Vector &beta(model_->Beta());
-  // The reference extends its table per observation inside the draw (NormalMixtureApproximationTable::approximate,
-  // NormalMixtureApproximation.cpp:472-532).  Here: once per (data, table, context), ask the device which counts occur,
-  // add the entries the grid lacks by the same rule, then state the table (the C side skips an unchanged upload).
-  auto ensure_table = [&](boomgpu_ctx *ctx) {
-    std::lock_guard<std::mutex> guard(t.lock);
-    if (counts_checked_ctx_ != ctx || counts_checked_data_version_ != model_->data_version() || counts_checked_table_version_ != t.version) {
-      std::vector<unsigned char> present((size_t)std::max<int64_t>(t.largest, 1), 0);
-      if (int rc = boomgpu_poisson_counts_present(ctx, present.data(), (int64_t)present.size())) return rc;
-      const size_t before = t.table.size();
-      for (int64_t v = std::max<int64_t>(1, t.table.smallest_index()); v < (int64_t)present.size() && v < t.table.largest_index(); ++v)
-        if (present[(size_t)v] && !t.table.contains(v)) t.table.approximate(v);
-      if (t.table.size() != before) { t.flatten(); ++t.version; }
-      counts_checked_ctx_ = ctx; counts_checked_data_version_ = model_->data_version(); counts_checked_table_version_ = t.version;
-    }
-    return boomgpu_set_poisson_table(ctx, (int)t.nu.size(), t.nu.data(), t.offset.data(), t.weights.data(), t.mu.data(),
-                                     t.sigma.data(), t.largest);
-  };
   run_device_step(
       *model_, suf_, packed_,
       [&](boomgpu_ctx *ctx, double *suf_dev) {
@@ -1313,7 +1315,45 @@ void PoissonRegressionAuxMixSampler::impute_latent_data() {
         return boomgpu_poisson_step(ctx, beta.data(), seed, it, xtwx, xtwy, scalars);
       });
 }
+
+bool PoissonRegressionAuxMixSampler::impute_latent_data_active(const std::vector<int> &cols_in) {
+  const int p = model_->xdim();
+  if (latent_data_fixed_ || p <= 64 || model_->allreduce() || cols_in.size() > 128) return false;
+  std::vector<int> cols(cols_in);
+  if (cols.empty()) cols.push_back(0);
+  DeviceData &dev(model_->device_data());
+  dev.check(ensure_table(dev.ctx()));
+  const int k = (int)cols.size();
+  active_.cols = cols;
+  active_.G.resize((size_t)p * k); active_.diag.resize(p); active_.xty.resize(p);
+  std::vector<int32_t> c32(cols.begin(), cols.end());
+  dev.check(boomgpu_poisson_step_active(dev.ctx(), model_->Beta().data(), device_seed_, iteration_++, c32.data(), k,
+                                        active_.G.data(), active_.diag.data(), active_.xty.data(), active_.scalars));
+  active_.valid = true;
+  return true;
+}
+
+std::unique_ptr<StatView> PoissonRegressionAuxMixSampler::statistics_view() {
+  if (!active_.valid) return std::unique_ptr<StatView>(new StatView(suf_));
+  DeviceData *dev = &model_->device_data();
+  ActiveSetState *st = &active_;
+  return std::unique_ptr<StatView>(new StatView(model_->xdim(), active_.cols, active_.G, active_.diag, active_.xty,
+                                               [dev, st](int j, double *out) {
+                                                 dev->check(boomgpu_weighted_column(dev->ctx(), j, out));
+                                                 ++st->columns_fetched;
+                                               }));
+}
+
+void PoissonRegressionAuxMixSampler::materialize_full_statistics() const {
+  DeviceData &dev(model_->device_data());
+  const int p = model_->xdim();
+  dev.check(boomgpu_full_statistics(dev.ctx(), suf_.xtx_storage(p), suf_.xty_storage()));
+  suf_.set_scalars(active_.scalars[0], active_.scalars[1], active_.scalars[2], active_.scalars[3]);
+  active_.valid = false;
+}
+
 void PoissonRegressionAuxMixSampler::draw_beta_given_complete_data() {
+  if (active_.valid) materialize_full_statistics();
   const int p = model_->xdim();
   SpdMatrix ivar(prior_->siginv());
   Vector ivar_mu(suf_.xty());
@@ -1335,9 +1375,22 @@ PoissonRegressionSpikeSlabSampler::PoissonRegressionSpikeSlabSampler(PoissonRegr
   if (spike->potential_nvars() != model->xdim()) report_error("Spike does not match model dimension.");
 }
 void PoissonRegressionSpikeSlabSampler::draw() {
-  impute_latent_data();
-  core_.draw_model_indicators(rng(), model_->coef(), suf_);
-  core_.draw_beta(rng(), model_->coef(), suf_);
+  if (!(active_.enabled && impute_latent_data_active(model_->coef().inc().included_positions()))) impute_latent_data();
+  draw_model_indicators();
+  draw_beta();
+}
+void PoissonRegressionSpikeSlabSampler::draw_model_indicators() {
+  std::unique_ptr<StatView> v(statistics_view());
+  core_.draw_model_indicators(rng(), model_->coef(), *v);
+  if (active_.valid) kept_view_ = std::move(v);   // the columns the sweep fetched: draw_beta reads them next
+}
+void PoissonRegressionSpikeSlabSampler::draw_beta() {
+  if (active_.valid && kept_view_) { core_.draw_beta(rng(), model_->coef(), *kept_view_); kept_view_.reset(); return; }
+  std::unique_ptr<StatView> v(statistics_view());
+  core_.draw_beta(rng(), model_->coef(), *v);
+}
+double PoissonRegressionSpikeSlabSampler::log_model_prob(const Selector &g) const {
+  return core_.log_model_prob(g, complete_data_sufficient_statistics());
 }
 double PoissonRegressionSpikeSlabSampler::logpri() const { return core_.logpri(model_->coef()); }
 std::shared_ptr<PoissonRegressionSpikeSlabSampler> PoissonRegressionSpikeSlabSampler::clone_to_new_host(

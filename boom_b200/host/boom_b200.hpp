@@ -561,10 +561,12 @@ class PoissonRegressionAuxMixSampler : public PosteriorSampler {
   double logpri() const override;
   void impute_latent_data();
   void draw_beta_given_complete_data();  // .cpp:123-128
-  const WeightedRegSuf &complete_data_sufficient_statistics() const { return suf_; }
-  void clear_complete_data_sufficient_statistics() { suf_.clear(); }
+  // the full statistics; after an active-set step they are computed on demand from the latents still in HBM
+  const WeightedRegSuf &complete_data_sufficient_statistics() const { if (active_.valid) materialize_full_statistics(); return suf_; }
+  void clear_complete_data_sufficient_statistics() { active_.valid = false; suf_.clear(); }
   void update_complete_data_sufficient_statistics(double precision_weighted_sum, double total_precision,
                                                   const Vector &x) {  // .cpp:153-158
+    active_.valid = false;
     suf_.add_data(x, precision_weighted_sum / total_precision, total_precision);
   }
   void fix_latent_data(bool fixed = true) { latent_data_fixed_ = fixed; }
@@ -582,11 +584,17 @@ class PoissonRegressionAuxMixSampler : public PosteriorSampler {
 
  protected:
   void on_seed() override;
+  // active-set form of the imputation, as on the logit samplers (BinomialLogitAuxmixSampler::impute_latent_data_active)
+  bool impute_latent_data_active(const std::vector<int> &cols);
+  std::unique_ptr<StatView> statistics_view();
+  void materialize_full_statistics() const;
   PoissonRegressionModel *model_;
   std::shared_ptr<MvnBase> prior_;
-  WeightedRegSuf suf_;
+  mutable WeightedRegSuf suf_;
+  mutable ActiveSetState active_;
 
  private:
+  int ensure_table(boomgpu_ctx *ctx);   // the table on the device holds every count of the data (extends it where the grid lacks one)
   bool latent_data_fixed_ = false;
   uint64_t device_seed_, iteration_ = 0;
   uint64_t counts_checked_data_version_ = 0, counts_checked_table_version_ = 0;
@@ -603,6 +611,13 @@ class PoissonRegressionSpikeSlabSampler : public PoissonRegressionAuxMixSampler 
   double logpri() const override;
   void allow_model_selection(bool tf) { core_.allow_model_selection(tf); }
   void limit_model_selection(int max_flips) { core_.limit_model_selection(max_flips); }
+  void draw_model_indicators();        // SpikeSlabSampler.cpp:40-100 with sigsq = 1
+  void draw_beta();                    // SpikeSlabSampler.cpp:102-140
+  double log_model_prob(const Selector &g) const;
+  // Active-set statistics, as on BinomialLogitSpikeSlabSampler (off by default; the same chain as with the full matrix)
+  void set_active_set_statistics(bool tf) { active_.enabled = tf; }
+  bool active_set_statistics() const { return active_.enabled; }
+  int64_t active_set_columns_fetched() const { return active_.columns_fetched; }
   std::shared_ptr<PoissonRegressionSpikeSlabSampler> clone_to_new_host(PoissonRegressionModel *new_host) const;   // .cpp:44-50
   void find_posterior_mode(double epsilon = 1e-5);   // PoissonRegressionSpikeSlabSampler.cpp:69-106
   bool can_find_posterior_mode() const { return true; }
@@ -610,6 +625,7 @@ class PoissonRegressionSpikeSlabSampler : public PoissonRegressionAuxMixSampler 
 
  private:
   SpikeSlabCore core_;
+  std::unique_ptr<StatView> kept_view_;
   double log_posterior_at_mode_ = -1.0 / 0.0;
 };
 

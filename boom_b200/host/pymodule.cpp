@@ -275,7 +275,17 @@ PYBIND11_MODULE(_host, m) {
       .def("find_posterior_mode", &PoissonRegressionSpikeSlabSampler::find_posterior_mode, py::arg("epsilon") = 1e-5)
       .def_property_readonly("log_posterior_at_mode", &PoissonRegressionSpikeSlabSampler::log_posterior_at_mode)
       .def("allow_model_selection", &PoissonRegressionSpikeSlabSampler::allow_model_selection)
-      .def("limit_model_selection", &PoissonRegressionSpikeSlabSampler::limit_model_selection);
+      .def("limit_model_selection", &PoissonRegressionSpikeSlabSampler::limit_model_selection)
+      .def("draw_model_indicators", &PoissonRegressionSpikeSlabSampler::draw_model_indicators)
+      .def("draw_beta", &PoissonRegressionSpikeSlabSampler::draw_beta)
+      .def("log_model_prob", [](const PoissonRegressionSpikeSlabSampler &s, std::vector<bool> bits) {
+        Selector g((int)bits.size(), false);
+        for (size_t i = 0; i < bits.size(); ++i) if (bits[i]) g.add((int)i);
+        return s.log_model_prob(g);
+      })
+      .def("set_active_set_statistics", &PoissonRegressionSpikeSlabSampler::set_active_set_statistics)
+      .def_property_readonly("active_set_statistics", &PoissonRegressionSpikeSlabSampler::active_set_statistics)
+      .def_property_readonly("active_set_columns_fetched", &PoissonRegressionSpikeSlabSampler::active_set_columns_fetched);
 
   // CPU-side test hook for the mode finder: the derivatives come from a Python callable (tests pass the oracle's), so
   // SpikeSlabCore::find_posterior_mode runs without a device

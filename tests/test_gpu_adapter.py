@@ -135,12 +135,14 @@ def test_probit_sibling_on_boom_models():
     assert np.all(np.array(r["b200"]["inclusion"])[:4] > 0.9)
 
 
-def test_active_set_option_on_the_adapter():
-    """set_active_set_statistics(true) on B200::BinomialLogitSpikeSlabSampler: the same chain as with the full statistics
-    (same seed), columns fetched only when the sweep adds a variable, suf() still the full matrix."""
+@pytest.mark.parametrize("mode", ["active", "pactive"])
+def test_active_set_option_on_the_adapter(mode):
+    """set_active_set_statistics(true) on B200::BinomialLogitSpikeSlabSampler / B200::PoissonRegressionSpikeSlabSampler: the same
+    chain as with the full statistics (same seed), columns fetched only when the sweep adds a variable, suf() still the full
+    matrix."""
     if not os.path.exists(EXE):
         pytest.skip("oracle/_ref/boom_adapter_demo not built")
-    out = subprocess.run([EXE, "active", "20000", "120", "5", "30", "0"], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([EXE, mode, "20000", "120", "5", "30", "0"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["same_model"] is True and r["chain_max_abs_diff"] < 1e-7

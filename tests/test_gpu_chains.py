@@ -298,3 +298,40 @@ def test_active_set_statistics_give_the_same_chain():
     np.testing.assert_allclose(xtx_on_demand, full_last, rtol=1e-9, atol=1e-9)
     assert fetched >= 6        # the six true variables entered one by one, each through a fetched column
     assert np.count_nonzero(chains[1][-1]) >= 6
+
+
+def test_poisson_active_set_statistics_give_the_same_chain():
+    """The same option on PoissonRegressionSpikeSlabSampler (boomgpu_poisson_step_active): identical decisions, coefficients
+    equal up to summation order, the full WeightedRegSuf (with its four scalars) on demand."""
+    import boom_b200
+    from oracle import oracle as O
+    n, p = 20_000, 120
+    X, y, ex, beta_true = O.synth_poisson(n, p, 5, seed=78)
+    boom_b200.load_poisson_mixture_table()
+    chains, sufs = [], []
+    fetched = 0
+    for active in (False, True):
+        model = boom_b200.PoissonRegressionModel(X, y, ex)
+        s = boom_b200.PoissonRegressionSpikeSlabSampler(model, boom_b200.MvnModel(np.zeros(p), np.eye(p)),
+                                                        boom_b200.VariableSelectionPrior(p, 5.0 / p), 1, boom_b200.RNG(22))
+        s.set_active_set_statistics(active)
+        assert s.active_set_statistics == active
+        model.set_method(s)
+        model.drop_all()
+        model.add(0)
+        out = []
+        for it in range(40):
+            model.sample_posterior()
+            out.append(np.array(model.Beta))
+        chains.append(np.array(out))
+        suf = s.complete_data_sufficient_statistics
+        sufs.append((np.array(suf.xtx), np.array(suf.xty), suf.n, suf.yty, suf.sumw, suf.sumlogw))
+        if active:
+            fetched = s.active_set_columns_fetched
+    assert np.array_equal(chains[0] != 0, chains[1] != 0)
+    np.testing.assert_allclose(chains[1], chains[0], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(sufs[1][0], sufs[0][0], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(sufs[1][1], sufs[0][1], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(sufs[1][2:], sufs[0][2:], rtol=1e-10)
+    assert fetched >= 3
+    assert np.count_nonzero(chains[1][-1]) >= 4

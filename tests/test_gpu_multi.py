@@ -262,3 +262,67 @@ def test_log_likelihood_and_mode_are_all_reduced_under_sharding(native):
     s.find_posterior_mode(1e-8)
     np.testing.assert_allclose(res[0][5], np.array(model.Beta), rtol=1e-7, atol=1e-9)
     assert res[0][6] == pytest.approx(s.log_posterior_at_mode, rel=1e-10)
+
+
+def _active_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import boom_b200
+    from boom_b200 import distributed as shard
+    from oracle import oracle as O
+    try:
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world, device_id=dev)
+        n, p = 30_001, 150
+        X, y, nt, _ = O.synth_binomial(n, p, 6, seed=77, max_trials=1)
+        row0, row1 = shard.shard_range(n, world, rank)
+        stream = torch.cuda.Stream(device=dev)
+        chains, fetched = [], 0
+        for active in (False, True):
+            model = boom_b200.BinomialLogitModel(X[row0:row1], y[row0:row1], nt[row0:row1])
+            s = boom_b200.BinomialLogitSpikeSlabSampler(model, boom_b200.MvnModel(np.zeros(p), np.eye(p)),
+                                                        boom_b200.VariableSelectionPrior(p, 6.0 / p), 10, boom_b200.RNG(21))
+            s.set_active_set_statistics(active)
+            model.set_method(s)
+            shard.attach(model, n, stream, dev, rank, world, native=True)
+            model.drop_all()
+            model.add(0)
+            out = []
+            for _ in range(30):
+                model.sample_posterior()
+                out.append(np.array(model.Beta))
+            chains.append(np.array(out))
+            if active:
+                fetched = s.active_set_columns_fetched
+                assert s.suf.sample_size == n
+            del s, model
+        q.put((rank, chains[0], chains[1], fetched))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, "FAIL: %r" % (e,), None, 0))
+
+
+def test_active_set_statistics_under_sharding():
+    """The active-set option with the native communicator: the panel product, the fetched columns and the on-demand full
+    statistics are all-reduced inside the C ABI; both ranks walk the same chain, which is the full-statistics chain."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_active_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted((q.get(timeout=600) for _ in procs), key=lambda t: t[0])
+    for pr in procs:
+        pr.join(timeout=60)
+    assert not isinstance(res[0][1], str) and not isinstance(res[1][1], str), res
+    np.testing.assert_array_equal(res[0][2], res[1][2])                      # the two ranks: identical
+    assert np.array_equal(res[0][1] != 0, res[0][2] != 0)                    # same decisions as the full-statistics chain
+    np.testing.assert_allclose(res[0][2], res[0][1], rtol=1e-7, atol=1e-9)
+    assert res[0][3] >= 6

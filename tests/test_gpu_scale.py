@@ -1,12 +1,12 @@
 """GPU parity at the shapes bench.py runs at (VERDICT r01 "what's weak" 1, 3), through the C ABI.
 
 The small parity cases (tests/test_gpu_parity.py) never reach the launch geometry of the benchmark configs:
-C3 runs the split-K SYRK with ksplit = 296 (2960 CTAs), C4 with 32 column blocks / 528 regions and TMA tiles at
+C3 runs the split-K SYRK with ksplit = 444 (4440 CTAs), C4 with 32 column blocks / 528 regions and TMA tiles at
 column offsets >= 512, C5 streams 25-200 M rows through the single-pass kernel.  Here the same oracle is run
 on disjoint row blocks on all host cores (tests/helpers.py: *_blocked, block results summed in long double) so
 that the comparison stays in seconds:
 
-  * accumulate + logit_step at n = 1.2 M, p = 500  (ksplit = 296, the C3 geometry per CTA);
+  * accumulate + logit_step at n = 1.2 M, p = 500  (ksplit = 444, the C3 geometry per CTA);
   * p in {520, 1000, 4000} (nblk 5 / 8 / 32, ragged last block), incl. the page-locked direct-copy landing;
   * a C5-shaped single pass, n = 50 M, p = 16: sample_size, X'WX, X'Wz and the indicator histogram;
   * the branches the small cases never take: Poisson |eta| >= 600 (PoissonDataImputer.cpp:55-79), exposure 0,
@@ -32,7 +32,7 @@ def _latents(n, seed):
 
 
 def test_c3_geometry_accumulate_and_step():
-    """n = 1.2 M, p = 500: launch_syrk picks ksplit = min(296, n / 2048) = 296, as at C3 (n = 10 M)."""
+    """n = 1.2 M, p = 500: launch_syrk picks ksplit = min(444, n / 2048) = 444, as at C3 (n = 10 M)."""
     n, p = 1_200_000, 500
     X, y, nt, beta = H.synth_binomial_parallel(n, p, 20, seed=301)
     w, s = _latents(n, 5)
@@ -63,7 +63,18 @@ def test_wide_p_accumulate_and_step(n, p):
     assert normwise_err(xtx, rxtx) < 1e-12
     assert vec_err(xty, rxty) < 1e-12
     np.testing.assert_array_equal(xtx, xtx.T)
-    del xtx
+    # the order in which the CTAs are scheduled (off-diagonal regions first / k-slice major) and the split-K depth change who
+    # computes what when, never the sums: same partial per (k-slice, region), same reduction order -> the same bits
+    ctx.set_option("syrk_order", 0)
+    xtx0, xty0 = ctx.accumulate(w, s)
+    np.testing.assert_array_equal(xtx0, xtx)
+    np.testing.assert_array_equal(xty0, xty)
+    ctx.set_option("syrk_order", 1)
+    ctx.set_option("syrk_waves", 7)
+    xtx0, xty0 = ctx.accumulate(w, s)
+    assert normwise_err(xtx0, rxtx) < 1e-12 and vec_err(xty0, rxty) < 1e-12
+    ctx.set_option("syrk_waves", 30)
+    del xtx, xtx0
     rxtx, rxty, rss, _ = H.logit_step_blocked(X, y, nt, beta, 10, mix, 43, 2)
     out = np.full((p, p), np.nan)
     boom_b200.Context.pin_host(out)
