@@ -26,6 +26,11 @@ The JSON line's top level is the HEADLINE workload (default C3, the config BASEL
                 did not travel to the box: the oracle's C port, one thread (kind "port").  The same for --impl reference.
   secondary     the other BASELINE.json configs under the same clock (value, ms_per_step, roofline, clocks each):
                 N = 1: C1 (1000 iterations), C2, C5, C4;  N > 1: C4 and C5 (the multi-GPU configs).
+                plus c3_active_set / c4_active_set: the spike-and-slab configs with the active-set statistics option.
+                HBM-bound kernels also carry roofline.burst (the same kernel after a 2 s pause: the sustained figure runs
+                under the board's power cap, see profiles/README.md).
+  e2e_adapter   (N = 1) the BOOM-typed adapter on BOOM's own model classes beside the standalone classes on the same rows
+                (oracle/_ref/boom_adapter_demo bench, row samples of C3's and C4's shapes): ms per Gibbs iteration each.
   multi_gpu_parity / selftest   (N > 1) before timing: the all-reduced statistics of one step over the N shards against the
                 same step on ONE context holding all rows (rank 0 regenerates them), and the agreement of a short sharded
                 chain with the one-GPU chain -- tests/test_gpu_multi.py's checks, under the driver's own launch.
@@ -573,6 +578,28 @@ class Bench:
         return res
 
 
+def adapter_block():
+    """The BOOM-typed drop-in (boom_b200/boom_adapter: samplers derived from BOOM::PosteriorSampler on BOOM's own model
+    classes, n heap-allocated Data objects) beside the standalone classes on the same rows, at row samples of C3's and C4's
+    shapes: what the BOOM surface costs per Gibbs iteration on top of the device step.  The demo binary links the reference
+    library as the adapter's HOST FRAMEWORK, so it exists only where the reference was compiled."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "boom_adapter_demo")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/boom_adapter_demo not built (needs the reference sources)"}
+    out = {"how": "boom_adapter_demo bench n p nonzero iters burn: BinomialLogitSpikeSlabSampler through BOOM's "
+                  "model->sample_posterior() vs the standalone classes, same rows, wall clock per iteration"}
+    for tag, argv in (("p500", ["400000", "500", "20", "10", "3"]), ("p4000", ["40000", "4000", "40", "4", "2"])):
+        try:
+            r = subprocess.run([exe, "bench"] + argv, capture_output=True, text=True, timeout=600)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            out[tag] = json.loads(line[-1]) if r.returncode == 0 and line else {"unavailable": (r.stderr or "no output")[-200:]}
+            if "adapter_ms_per_iter" in out[tag]:
+                out[tag]["adapter_over_standalone"] = out[tag]["adapter_ms_per_iter"] / out[tag]["standalone_ms_per_iter"]
+        except (OSError, subprocess.TimeoutExpired, ValueError) as e:
+            out[tag] = {"unavailable": repr(e)[-200:]}
+    return out
+
+
 def cpu_baseline_block(kind, sampler, n, p, nonzero):
     r, why = run_reference(kind, sampler, n, p, nonzero, 3, 1)
     if r is None:
@@ -603,6 +630,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-array e2e leg (development aid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-adapter", action="store_true", help="skip the BOOM-adapter leg (e2e_adapter)")
     ap.add_argument("--no-burst", action="store_true", help="skip the burst re-measurement of HBM-bound kernels (2 s pause + 4 iterations)")
     ap.add_argument("--no-secondary", action="store_true", help="headline workload only (development aid, profiling)")
     ap.add_argument("--no-selftest", action="store_true", help="skip the N > 1 parity check before timing")
@@ -664,6 +692,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_block(kind, sampler, n, p, nonzero)
+    adapter = None
+    if rank == 0 and world == 1 and not args.no_secondary and not args.rows and not args.no_adapter:
+        b.torch.cuda.empty_cache()
+        adapter = adapter_block()
     if b.clocks:
         b.clocks.close()
     if rank == 0:
@@ -675,6 +707,8 @@ def main():
             line["e2e"] = head["e2e"]
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if adapter is not None:
+            line["e2e_adapter"] = adapter
         if secondary:
             line["secondary"] = secondary
         if st is not None:
