@@ -392,12 +392,25 @@ template <int MODEL>
 struct TmaLauncher {
   template <int NB>
   static int go(boomgpu_ctx *ctx, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts, const TailParams &tail) {
-    auto kern = fused_tma_kernel<NB, MODEL>;
-    constexpr int NW = tma_warps(NB);
+    // wide tiles, the two draw models: accumulators parked in tensor memory between DMMA phases -> 12 warps instead of 8
+    // (registers are allocated per warpgroup on sm_100: 10 warps get the 168 registers of 12, so there is no 10-warp form)
+    // Measured (profiles/bench_r02/run27_tmem_park.txt, ms per launch, 8 warps -> 12 warps parked): Poisson p = 40 / 48 / 50 / 64
+    // 0.561 -> 0.483, 0.658 -> 0.588, 0.233 -> 0.222, 0.988 -> 1.063; logit p = 40 / 48 / 56 / 64 0.832 -> 0.728, 1.012 -> 0.911,
+    // 1.24 -> 2.06, 1.62 -> 3.74 (at NB >= 7 the logit draw spills inside the k-steps at 168 registers).  So: automatic for
+    // NB = 5, 6 and for the Poisson model at NB = 7; small_variant = 2 never parks, 4 parks wherever the form exists.
+    if constexpr (NB >= 5 && (MODEL == kLogit || MODEL == kPoisson)) {
+      const bool faster = NB <= 6 || (NB == 7 && MODEL == kPoisson);
+      if (ctx->small_variant == 4 || (ctx->small_variant == 0 && faster)) return go_impl<NB, 12, true>(ctx, d, prm, out, nparts, tail);
+    }
+    return go_impl<NB, tma_warps(NB), false>(ctx, d, prm, out, nparts, tail);
+  }
+  template <int NB, int NW, bool PARK>
+  static int go_impl(boomgpu_ctx *ctx, const RowData &d, const DrawParams &prm, const RowOut &out, int *nparts, const TailParams &tail) {
+    auto kern = fused_tma_kernel<NB, MODEL, NW, PARK>;
     BetaParam bp;
     memset(&bp, 0, sizeof(bp));
     memcpy(bp.b, ctx->beta_pin, sizeof(double) * d.p);
-    const size_t smem = tma_smem_bytes(NB);
+    const size_t smem = tma_smem_bytes(NB, NW, PARK);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (int rc = ensure_xmap(ctx, ctx->xmap_small, ctx->X, ctx->ldx, tma_padw(NB), tma_slice_rows(NB))) return rc;
     const int64_t nslices = (d.n + tma_slice_rows(NB) - 1) / tma_slice_rows(NB);
@@ -1064,7 +1077,7 @@ int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value) {
     return 0;
   }
   if (!strcmp(name, "small_variant")) {
-    if (value < 0 || value > 3) return fail(ctx, BOOMGPU_ERR_ARG, "small_variant must be 0, 1, 2 or 3");
+    if (value < 0 || value > 4) return fail(ctx, BOOMGPU_ERR_ARG, "small_variant must be 0 .. 4");
     ctx->small_variant = (int)value;
     return 0;
   }

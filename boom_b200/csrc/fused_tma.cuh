@@ -18,6 +18,7 @@
 //   partials in CTA order -- one thread per output element, 16 loads in flight -- and writes the statistics to the
 //   device buffer and to the host-mapped copy: one launch per Gibbs step, deterministic (no floating point atomics).
 //   Option single_launch = 0 keeps the separate reduce_partials_kernel.
+//   Wide tiles (NB >= 5) also exist in a 12-warp form whose accumulators live in tensor memory between DMMA phases (PARK, below).
 //
 //   Algorithmic traffic: 8 (p + 2) bytes per observation, read once.
 //   Reference equivalent: Imputer.hpp:175-180 over BinomialLogitAuxmixSampler.cpp:61-97 /
@@ -85,10 +86,11 @@ __host__ __device__ constexpr int tma_stages(int nb) { return nb <= 2 ? BOOMGPU_
 __host__ __device__ constexpr int tma_padw(int nb) { return 8 * nb + 2; }
 __host__ __device__ constexpr int tma_slice_rows(int nb) { return 32 * tma_rpl(nb); }
 __host__ __device__ constexpr int tma_slice_doubles(int nb) { return tma_slice_rows(nb) * tma_padw(nb); }
-__host__ __device__ constexpr size_t tma_smem_bytes(int nb) {
-  return sizeof(double) * ((size_t)tma_warps(nb) * tma_stages(nb) * tma_slice_doubles(nb) + 8 * nb + 64) +
-         sizeof(uint64_t) * tma_warps(nb) * tma_stages(nb) + 128;
+__host__ __device__ constexpr size_t tma_smem_bytes(int nb, int nw, bool park = false) {
+  return sizeof(double) * ((size_t)nw * tma_stages(nb) * tma_slice_doubles(nb) + 8 * nb + 64 + (park ? 4 * 32 * nw : 0)) +
+         sizeof(uint64_t) * nw * tma_stages(nb) + 128;
 }
+__host__ __device__ constexpr size_t tma_smem_bytes(int nb) { return tma_smem_bytes(nb, tma_warps(nb)); }
 __host__ __device__ constexpr int64_t tma_partial_len(int nb) { return 64 * nb * nb + 8 * nb + 8; }
 
 // beta travels as a kernel parameter (p <= 64: 512 bytes of the constant bank): no host->device copy per step
@@ -188,11 +190,63 @@ __device__ __forceinline__ void sum_partials_tail(const double *__restrict__ par
   }
 }
 
-template <int NB, int MODEL>
-__global__ void __launch_bounds__(32 * tma_warps(NB), 1)
+// ---- accumulators parked in tensor memory (wide tiles, option small_variant = 4 / 5) -------------------------------------
+// The register-resident triangle of a wide tile (NB = 7: 28 atoms = 112 registers) is dead weight during a warp's draw phase
+// and caps the CTA at 8 warps x 255 registers, while the draw phase is a long dependent chain per lane that only MORE warps
+// hide (ncu, C2: tensor pipe 52 % active, issue slots 25 %).  Blackwell's tensor memory (256 KB per SM, idle here: FP64 has
+// no tcgen05.mma) takes the triangle between the DMMA phases: tcgen05.st after a slice's k-steps, tcgen05.ld before the next
+// slice's -- 32x32b shape, lane = thread, one 32-bit column per register, each warp in its own lane quadrant
+// (32 (warp mod 4)) and column slot, so no two warps ever touch the same cell.  The kernel then fits 10 or 12 warps.
+constexpr int kParkColsPerWarp = 160;   // >= 4 * 36 (NB = 8), a multiple of 16; three warps per lane quadrant: 480 of 512 columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&u)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+               "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]), "r"(u[10]),
+               "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&u)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+                 "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+               : "r"(taddr)
+               : "memory");
+}
+template <int NA>
+__device__ __forceinline__ void tmem_park(uint32_t taddr, const double (&c)[NA][2]) {
+  constexpr int NR = 4 * NA, NCH = (NR + 15) / 16;
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    uint32_t u[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int r = 16 * ch + i;   // register r: atom r / 4, component (r % 4) / 2, low / high word r % 2
+      u[i] = r < NR ? (uint32_t)((r & 1) ? __double2hiint(c[r / 4][(r % 4) / 2]) : __double2loint(c[r / 4][(r % 4) / 2])) : 0u;
+    }
+    tmem_st16(taddr + 16 * ch, u);
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+}
+template <int NA>
+__device__ __forceinline__ void tmem_unpark(uint32_t taddr, double (&c)[NA][2]) {
+  constexpr int NR = 4 * NA, NCH = (NR + 15) / 16;
+  uint32_t u[NCH][16];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) tmem_ld16(taddr + 16 * ch, u[ch]);
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int r = 4 * a + 2 * j;
+      c[a][j] = __hiloint2double((int)u[(r + 1) / 16][(r + 1) % 16], (int)u[r / 16][r % 16]);
+    }
+}
+
+template <int NB, int MODEL, int NWT = tma_warps(NB), bool PARK = false>
+__global__ void __launch_bounds__(32 * NWT, 1)
 fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams prm, RowOut out, const __grid_constant__ BetaParam beta,
                  double *__restrict__ partials, int *err, TailParams tail) {
-  constexpr int NW = tma_warps(NB);
+  constexpr int NW = NWT;
   constexpr int S = tma_stages(NB);
   constexpr int RPL = tma_rpl(NB);
   constexpr int ROWS = 32 * RPL;
@@ -201,11 +255,14 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
   constexpr int P8 = 8 * NB;
   constexpr int NA = NB * (NB + 1) / 2;
   constexpr uint32_t kSliceBytes = SLICE * sizeof(double);
+  static_assert(!PARK || (NW <= 12 && 4 * NA <= kParkColsPerWarp), "tensor-memory parking: at most three warps per lane quadrant");
   extern __shared__ __align__(128) double smem[];
   double *ring = smem;                                  // [NW][S][SLICE]
   double *beta_s = smem + (size_t)NW * S * SLICE;       // P8
   double *red_s = beta_s + P8;                          // 64
-  uint64_t *bars = reinterpret_cast<uint64_t *>(red_s + 64);  // [NW][S]
+  double *sc_s = red_s + 64;                            // parked form only: [4][32 NW] per-thread scalar statistics
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sc_s + (PARK ? 4 * 32 * NW : 0));  // [NW][S]
+  __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int p = d.p;
@@ -213,7 +270,13 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
     for (int i = 0; i < NW * S; ++i) mbar_init(bars + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  if (PARK && wid == 0) {   // the whole tensor memory of the SM (one CTA per SM): 512 columns x 128 lanes x 32 bits
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
   __syncthreads();
+  // this warp's cells: lanes 32 (wid mod 4) .. + 31 (the only ones it may address), columns [slot * 160, + 4 NA)
+  const uint32_t my_tmem = PARK ? tmem_base_s + ((uint32_t)(32 * (wid & 3)) << 16) + (uint32_t)((wid >> 2) * kParkColsPerWarp) : 0u;
 
   // slices of ROWS rows are dealt to (CTA, warp): the k-th slice of this warp is ((blockIdx + k grid) NW + wid)
   const int64_t nslices = (d.n + ROWS - 1) / ROWS;
@@ -240,6 +303,11 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
 #pragma unroll
   for (int b = 0; b < NB; ++b) xty_acc[b] = 0.0;
   double sc_count = 0, sc_ywy = 0, sc_sumw = 0, sc_sumlogw = 0;
+  if (PARK) {
+    tmem_park<NA>(my_tmem, c);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sc_s[k * 32 * NW + tid] = 0.0;
+  }
 
   int slot = 0;
   uint32_t phase = 0;
@@ -326,26 +394,50 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
     __syncwarp();
 
     // ---- the warp's rank-1 updates: DMMA k-steps of 4 rows
-#pragma unroll(NB <= 2 ? 8 : (NB <= 4 ? 4 : 2))
+    if (PARK) {
+      // nothing of the draw phase stays in registers across the k-steps: the scalar statistics go to this thread's cells
+      sc_s[0 * 32 * NW + tid] += sc_count; sc_s[1 * 32 * NW + tid] += sc_ywy;
+      sc_s[2 * 32 * NW + tid] += sc_sumw;  sc_s[3 * 32 * NW + tid] += sc_sumlogw;
+      sc_count = 0; sc_ywy = 0; sc_sumw = 0; sc_sumlogw = 0;
+      tmem_unpark<NA>(my_tmem, c);
+    }
+#pragma unroll(NB <= 2 ? 8 : (NB <= 4 ? 4 : (PARK ? 1 : 2)))
     for (int kk = 0; kk < ROWS / 4; ++kk) {
       const int row = 8 * (kk >> 1) + (kk & 1) + 2 * (lane & 3);   // the k-step's four rows, two apart (bank layout: tma_padw)
       const double2 ws = *reinterpret_cast<const double2 *>(xs + row * PADW + P8);
       const double wk = ws.x, sk = ws.y;
       const double *xr = xs + row * PADW + (lane >> 2);
-      double xa[NB], xw[NB];
+      if (PARK) {   // register diet: the A fragment of one atom row at a time
+        double xa[NB];
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        xa[b] = xr[8 * b];
-        xw[b] = xa[b] * wk;
-        xty_acc[b] = fma(xa[b], sk, xty_acc[b]);
+        for (int b = 0; b < NB; ++b) {
+          xa[b] = xr[8 * b];
+          xty_acc[b] = fma(xa[b], sk, xty_acc[b]);
+        }
+        int a = 0;
+#pragma unroll
+        for (int bi = 0; bi < NB; ++bi) {
+          const double xwi = xa[bi] * wk;
+#pragma unroll
+          for (int bj = bi; bj < NB; ++bj) { dmma884(c[a][0], c[a][1], xwi, xa[bj]); ++a; }
+        }
+      } else {
+        double xa[NB], xw[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          xa[b] = xr[8 * b];
+          xw[b] = xa[b] * wk;
+          xty_acc[b] = fma(xa[b], sk, xty_acc[b]);
+        }
+        int a = 0;
+#pragma unroll
+        for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+          for (int bj = bi; bj < NB; ++bj) { dmma884(c[a][0], c[a][1], xw[bi], xa[bj]); ++a; }
       }
-      int a = 0;
-#pragma unroll
-      for (int bi = 0; bi < NB; ++bi)
-#pragma unroll
-        for (int bj = bi; bj < NB; ++bj) { dmma884(c[a][0], c[a][1], xw[bi], xa[bj]); ++a; }
     }
 
+    if (PARK) tmem_park<NA>(my_tmem, c);
     // ---- re-arm the slot S slices ahead (all lanes are done with it; the generic-proxy writes of (w, s) are
     // ordered before the async-proxy overwrite)
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -361,7 +453,9 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
   }
 
   // ---- CTA reduction in warp order (deterministic), one partial per CTA
+  if (PARK) tmem_unpark<NA>(my_tmem, c);
   __syncthreads();  // every issued copy has been consumed: the ring is free
+  if (PARK && wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base_s) : "memory");
   constexpr int TILE = P8 * P8 + P8;    // [P8 x P8 | X'Wz P8]
   // X'Wz: lanes with the same (lane >> 2) hold the rows = lane & 3 (mod 4) of the same columns
 #pragma unroll
@@ -421,6 +515,10 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
       __syncthreads();
     }
     for (int e = tid; e < TILE; e += 32 * NW) my[e] = smem[e];
+  }
+  if (PARK) {
+    sc_count += sc_s[0 * 32 * NW + tid]; sc_ywy += sc_s[1 * 32 * NW + tid];
+    sc_sumw += sc_s[2 * 32 * NW + tid];  sc_sumlogw += sc_s[3 * 32 * NW + tid];
   }
   double v0 = warp_sum(sc_count), v1 = warp_sum(sc_ywy), v2 = warp_sum(sc_sumw), v3 = warp_sum(sc_sumlogw);
   if (lane == 0) { red_s[wid * 4 + 0] = v0; red_s[wid * 4 + 1] = v1; red_s[wid * 4 + 2] = v2; red_s[wid * 4 + 3] = v3; }

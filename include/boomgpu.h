@@ -73,8 +73,10 @@ int boomgpu_set_stream(boomgpu_ctx *ctx, void *cuda_stream);
 int boomgpu_set_row_offset(boomgpu_ctx *ctx, uint64_t first_global_row);
 /* options: "path" = 0 auto | 1 fused single pass (p <= 64) | 2 two-pass imputer + DMMA SYRK;
  *          "small_variant" = 0 auto (the TMA-fed warp-autonomous kernel when X has an even leading dimension and a 16-byte
- *                            aligned base) | 1 force the cp.async kernel | 2 = 0 | 3 the warp-specialised kernel for
- *                            40 < p <= 64 (accumulate warps + draw warps: measured no faster, kept as an experiment);
+ *                            aligned base; for 32 < p <= 48, and the Poisson model up to p = 56, its 12-warp form that parks
+ *                            the accumulators in tensor memory between DMMA phases) | 1 force the cp.async kernel |
+ *                            2 the TMA kernel, never parked | 3 the warp-specialised kernel for 32 < p <= 64 (accumulate
+ *                            warps + draw warps: measured no faster, kept as an experiment) | 4 parked wherever 32 < p <= 64;
  *          "single_launch" = 1 (default) the small-p step is one kernel whose last CTA sums the per-CTA partials | 0 a
  *                            separate reduction kernel;
  *          "gather" = 0 auto (two-pass path: a beta with fewer than p / 4 non-zeros reads only those columns of X in the

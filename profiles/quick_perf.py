@@ -16,7 +16,8 @@ CFG = {
     "c4": ("logit", 2_000_000, 4000), "c5": ("logit", 25_000_000, 16), "c3s": ("logit", 1_000_000, 500),
     "p128": ("logit", 4_000_000, 128), "p64": ("logit", 8_000_000, 64), "p32": ("logit", 8_000_000, 32),
     "c4s": ("logit", 500_000, 4000), "p1000": ("logit", 2_000_000, 1000), "p260": ("logit", 4_000_000, 260),
-    "c5m": ("logit", 100_000_000, 16), "c5f": ("logit", 200_000_000, 16), "c2x4": ("poisson", 4_000_000, 50),
+    "p40": ("logit", 8_000_000, 40), "p48l": ("logit", 8_000_000, 48), "p56": ("logit", 8_000_000, 56), "p40p": ("poisson", 4_000_000, 40),
+    "p64p": ("poisson", 4_000_000, 64), "c5m": ("logit", 100_000_000, 16), "c5f": ("logit", 200_000_000, 16), "c2x4": ("poisson", 4_000_000, 50),
     "p8": ("logit", 25_000_000, 8), "p24": ("logit", 12_000_000, 24), "p48": ("poisson", 4_000_000, 48),
 }
 
@@ -53,6 +54,9 @@ def main():
         X, y, aux, beta = make(kind, n, p, dev)
         ctx = boom_b200.Context(0)
         ctx.set_option("timing", 1)
+        for kv in os.environ.get("QP_OPTIONS", "").split(","):   # e.g. QP_OPTIONS=small_variant=4,syrk_waves=24
+            if "=" in kv:
+                ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
         if kind == "logit":
             ctx.set_logit_mixture(*boom_b200.default_logit_mixture())
             ctx.adopt_binomial(n, p, X.data_ptr(), p, y.data_ptr(), aux.data_ptr(), keepalive=(X, y, aux))

@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "boom_b200", "libboomgpu.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
-KEY = ("DMMA", "UTMALDG", "UBLKCP", "SYNCS", "USETMAXREG", "DFMA", "DMUL", "DADD", "MUFU", "LDS", "STS", "LDG", "STG", "SHFL", "ATOM", "RED",
+KEY = ("DMMA", "UTMALDG", "UBLKCP", "SYNCS", "USETMAXREG", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "DFMA", "DMUL", "DADD", "MUFU", "LDS", "STS", "LDG", "STG", "SHFL", "ATOM", "RED",
        "MEMBAR", "FENCE", "BAR", "IMAD", "LOP3", "FFMA", "NOP")
 name, counts, order = None, {}, []
 for line in sass.splitlines():

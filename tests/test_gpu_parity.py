@@ -214,10 +214,12 @@ def test_poisson_indicators_exact_at_scale():
 
 
 @pytest.mark.parametrize("n,p,kind", [(5003, 20, "logit"), (40_000, 16, "logit"), (3000, 64, "logit"), (7001, 50, "poisson"),
-                                      (33, 1, "logit"), (100_000, 7, "logit")])
+                                      (33, 1, "logit"), (100_000, 7, "logit"), (60_001, 40, "poisson"), (50_003, 48, "logit")])
 def test_small_p_variants_agree_with_oracle(n, p, kind):
-    """p <= 64: the TMA-fed warp-autonomous kernel (default) and the cp.async kernel (X that TMA cannot describe)."""
-    for variant in (0, 1, 3):
+    """p <= 64: the TMA-fed warp-autonomous kernel (0: automatic choice between its 8-warp form and, for wide tiles, the
+    12-warp form with the accumulators parked in tensor memory; 2: never parked; 4: parked wherever 32 < p <= 64), the cp.async
+    kernel (1: X that TMA cannot describe) and the warp-specialised kernel (3)."""
+    for variant in (0, 1, 2, 3, 4):
         if kind == "logit":
             X, y, nt, beta = O.synth_binomial(n, p, min(3, p - 1), seed=50 + p, max_trials=2)
             ctx, mix = logit_ctx(X, y, nt)
