@@ -344,6 +344,65 @@ PYBIND11_MODULE(_host, m) {
     for (int i = 0; i < p; ++i) { inc_sum[i] /= sweeps; beta_sum[i] /= sweeps; }
     return py::make_tuple(from_vec(inc_sum), from_vec(beta_sum));
   });
+  m.def("spike_slab_sweep_active", [](RNG &rng, const NpD &xtx, const NpD &xty, const std::shared_ptr<MvnBase> &slab,
+                                      const std::shared_ptr<VariableSelectionPrior> &spike, std::vector<bool> bits, int sweeps,
+                                      bool fisher_yates) {
+    // the same driver on the ACTIVE-SET view of the statistics: before every sweep the view holds only the
+    // columns of the included variables, the diagonal and X'Wz, and fetches a further column (here: from the same matrix)
+    // when the sweep adds a variable.  Returns the chain of (inclusion bits, beta) per sweep and the number of fetches.
+    const int p = (int)xty.size();
+    const double *A = xtx.data();
+    Vector xty_v(xty.data(), xty.data() + p), diag(p);
+    for (int i = 0; i < p; ++i) diag[i] = A[(size_t)i * p + i];
+    GlmCoefs coef(p, false);
+    Selector g(p, false);
+    for (int i = 0; i < p; ++i) if (bits[i]) g.add(i);
+    coef.set_inc(g);
+    SpikeSlabCore core(slab, spike, fisher_yates);
+    py::list chain;
+    int fetched = 0;
+    for (int s = 0; s < sweeps; ++s) {
+      std::vector<int> cols = coef.inc().included_positions();
+      if (cols.empty()) cols.push_back(0);
+      const int k = (int)cols.size();
+      Vector G((size_t)p * k);
+      for (int i = 0; i < p; ++i) for (int a = 0; a < k; ++a) G[(size_t)i * k + a] = A[(size_t)i * p + cols[a]];
+      StatView view(p, cols, G, diag, xty_v, [&](int j, double *out) {
+        for (int i = 0; i < p; ++i) out[i] = A[(size_t)i * p + j];
+        ++fetched;
+      });
+      core.draw_model_indicators(rng, coef, view);
+      core.draw_beta(rng, coef, view);
+      std::vector<bool> inc(p);
+      for (int i = 0; i < p; ++i) inc[i] = coef.inc()[i];
+      chain.append(py::make_tuple(inc, from_vec(coef.Beta())));
+    }
+    return py::make_tuple(chain, fetched);
+  });
+  m.def("spike_slab_chain", [](RNG &rng, const NpD &xtx, const NpD &xty, const std::shared_ptr<MvnBase> &slab,
+                               const std::shared_ptr<VariableSelectionPrior> &spike, std::vector<bool> bits, int sweeps, bool fisher_yates) {
+    // spike_slab_sweep returning the chain itself (full statistics): what spike_slab_sweep_active is compared with
+    const int p = (int)xty.size();
+    Vector packed((size_t)p * p + p + 4, 0.0);
+    std::copy(xtx.data(), xtx.data() + (size_t)p * p, packed.begin());
+    std::copy(xty.data(), xty.data() + p, packed.begin() + (size_t)p * p);
+    WeightedRegSuf suf(p);
+    suf.reset(packed.data(), p);
+    GlmCoefs coef(p, false);
+    Selector g(p, false);
+    for (int i = 0; i < p; ++i) if (bits[i]) g.add(i);
+    coef.set_inc(g);
+    SpikeSlabCore core(slab, spike, fisher_yates);
+    py::list chain;
+    for (int s = 0; s < sweeps; ++s) {
+      core.draw_model_indicators(rng, coef, suf);
+      core.draw_beta(rng, coef, suf);
+      std::vector<bool> inc(p);
+      for (int i = 0; i < p; ++i) inc[i] = coef.inc()[i];
+      chain.append(py::make_tuple(inc, from_vec(coef.Beta())));
+    }
+    return chain;
+  });
   m.def("flip_path_log_probs", [](const NpD &xtx, const NpD &xty, const std::shared_ptr<MvnBase> &slab,
                                   const std::shared_ptr<VariableSelectionPrior> &spike, std::vector<bool> bits,
                                   std::vector<int> flips, std::vector<bool> accept) {

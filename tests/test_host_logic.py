@@ -260,3 +260,31 @@ def test_poisson_table_offgrid_entries_follow_the_reference_rule(golden):
     assert np.array_equal(h.poisson_mixture_table(), ser)
     assert again[3] < 1e-6
     boom_b200.load_poisson_mixture_table()    # back to the shipped table for the other tests
+
+
+@pytest.mark.parametrize("fisher_yates", [False, True])
+def test_sweep_on_the_active_set_view_is_the_sweep_on_the_full_matrix(fisher_yates):
+    """StatView: a sweep over the inclusion indicators reads of X'WX only the columns of the included variables
+    and the diagonal; with those columns, the diagonal and X'Wz held, and a further column fetched whenever the sweep ADDS a
+    variable, the chain is bit for bit the one the full matrix gives (same random stream, same arithmetic) -- on the host
+    alone, no device: the fetch callback reads the same matrix."""
+    h = boom_b200.host()
+    p = 40
+    rng = np.random.default_rng(11)
+    X = rng.normal(size=(400, p)); X[:, 0] = 1.0
+    w = 0.2 + rng.random(400)
+    beta = np.zeros(p); beta[[0, 3, 7, 19, 33]] = [0.5, 1.0, -1.0, 0.8, -0.7]
+    z = X @ beta + rng.normal(size=400) / np.sqrt(w)
+    xtx = (X.T * w) @ X
+    xty = (X.T * w) @ z
+    slab = boom_b200.MvnModel(np.zeros(p), np.eye(p), True)
+    spike = boom_b200.VariableSelectionPrior(np.full(p, 0.1))
+    start = [True] + [False] * (p - 1)
+    full = h.spike_slab_chain(boom_b200.RNG(5), xtx, xty, slab, spike, start, 60, fisher_yates)
+    active, fetched = h.spike_slab_sweep_active(boom_b200.RNG(5), xtx, xty, slab, spike, start, 60, fisher_yates)
+    assert len(full) == len(active) == 60
+    for (g0, b0), (g1, b1) in zip(full, active):
+        assert list(g0) == list(g1)
+        np.testing.assert_array_equal(np.asarray(b0), np.asarray(b1))
+    assert fetched >= 4                                   # the four true variables outside the start model came in through fetches
+    assert sum(full[-1][0]) >= 5
