@@ -129,10 +129,17 @@ class Context:
 
     # ---- data
     def upload_binomial(self, X, y, ntrials):
-        X, y, ntrials = _f64(X), _f64(y), _f64(ntrials)
+        """X: (n, p) float64; a row-strided view (X_wide[:, :p]) is passed as it is, with its leading dimension."""
+        X = np.asarray(X)
+        if X.dtype == np.float64 and X.ndim == 2 and X.shape[1] and X.strides[1] == 8 and X.strides[0] % 8 == 0 and X.strides[0] >= 8 * X.shape[1]:
+            ldx = X.strides[0] // 8
+        else:
+            X = _f64(X)
+            ldx = X.shape[1]
+        y, ntrials = _f64(y), _f64(ntrials)
         n, p = X.shape
-        self._check(self._lib.boomgpu_upload_binomial(self._h, C.c_int64(n), C.c_int(p), _dp(X), C.c_int64(p), _dp(y),
-                                                      _dp(ntrials)))
+        self._check(self._lib.boomgpu_upload_binomial(self._h, C.c_int64(n), C.c_int(p), _dp(X),
+                                                      C.c_int64(ldx), _dp(y), _dp(ntrials)))
         self.n, self.p = n, p
 
     def upload_poisson(self, X, y, exposure):

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -861,6 +862,58 @@ int upload_array(boomgpu_ctx *ctx, const T *host, int64_t count, const T **dev_o
   return 0;
 }
 
+// A large X in pageable host memory (C3: 40 GB): a plain cudaMemcpy2D stages it through the driver's own bounce buffers at
+// ~10 GB/s (4.2 s at C3).  Here: three page-locked staging buffers of 64 MB, filled by a few host threads (memcpy of
+// whole rows, already in the device's padded pitch) while the previous ones are in flight on the stream.
+int upload_x_staged(boomgpu_ctx *ctx, double *dX, int64_t ldd, int64_t n, int p, const double *X, int64_t ldx) {
+  constexpr int kBufs = 3;
+  const size_t row_bytes = sizeof(double) * (size_t)p;
+  const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(((size_t)64 << 20) / row_bytes));
+  double *stage[kBufs] = {nullptr, nullptr, nullptr};
+  cudaEvent_t done[kBufs] = {nullptr, nullptr, nullptr};
+  bool in_flight[kBufs] = {false, false, false};
+  int rc = 0;
+  for (int b = 0; b < kBufs && !rc; ++b) {
+    if (cudaMallocHost((void **)&stage[b], row_bytes * (size_t)chunk_rows) != cudaSuccess ||
+        cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming) != cudaSuccess)
+      rc = fail(ctx, BOOMGPU_ERR_CUDA, "staging buffers for the upload: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int nthreads = (int)std::max(1u, std::min(8u, hw ? hw : 1u));
+  int b = 0;
+  for (int64_t r0 = 0; r0 < n && !rc; r0 += chunk_rows, b = (b + 1) % kBufs) {
+    const int64_t rows = std::min(chunk_rows, n - r0);
+    if (in_flight[b] && cudaEventSynchronize(done[b]) != cudaSuccess) { rc = fail(ctx, BOOMGPU_ERR_CUDA, "upload: event wait failed"); break; }
+    double *dst = stage[b];
+    auto copy_rows = [=](int64_t a, int64_t z) {
+      if (ldx == p) { memcpy(dst + (size_t)a * p, X + (size_t)(r0 + a) * ldx, row_bytes * (size_t)(z - a)); return; }
+      for (int64_t i = a; i < z; ++i) memcpy(dst + (size_t)i * p, X + (size_t)(r0 + i) * ldx, row_bytes);
+    };
+    if (nthreads == 1 || rows < 4 * nthreads) {
+      copy_rows(0, rows);
+    } else {
+      std::vector<std::thread> pool;
+      const int64_t per = (rows + nthreads - 1) / nthreads;
+      for (int t = 0; t < nthreads; ++t) {
+        const int64_t a = t * per, z = std::min(rows, a + per);
+        if (a < z) pool.emplace_back(copy_rows, a, z);
+      }
+      for (auto &th : pool) th.join();
+    }
+    if (cudaMemcpy2DAsync(dX + (size_t)r0 * ldd, sizeof(double) * ldd, dst, row_bytes, row_bytes, (size_t)rows, cudaMemcpyHostToDevice,
+                          ctx->stream) != cudaSuccess ||
+        cudaEventRecord(done[b], ctx->stream) != cudaSuccess)
+      rc = fail(ctx, BOOMGPU_ERR_CUDA, "upload: %s", cudaGetErrorString(cudaGetLastError()));
+    in_flight[b] = true;
+  }
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) rc = fail(ctx, BOOMGPU_ERR_CUDA, "upload: %s", cudaGetErrorString(cudaGetLastError()));
+  for (int i = 0; i < kBufs; ++i) {
+    if (done[i]) cudaEventDestroy(done[i]);
+    if (stage[i]) cudaFreeHost(stage[i]);
+  }
+  return rc;
+}
+
 int upload_x(boomgpu_ctx *ctx, int64_t n, int p, const double *X, int64_t ldx) {
   // device layout: row major, leading dimension rounded up to 8 doubles (64 B), pad columns zero
   const int64_t ldd = ((int64_t)p + 7) / 8 * 8;
@@ -869,8 +922,13 @@ int upload_x(boomgpu_ctx *ctx, int64_t n, int p, const double *X, int64_t ldx) {
   ctx->owned.push_back(dX);
   if (n) {
     if (ldd != p) CU(cudaMemsetAsync(dX, 0, sizeof(double) * (size_t)(n * ldd), ctx->stream));
-    CU(cudaMemcpy2DAsync(dX, sizeof(double) * ldd, X, sizeof(double) * ldx, sizeof(double) * p, (size_t)n,
-                         cudaMemcpyHostToDevice, ctx->stream));
+    const size_t bytes = sizeof(double) * (size_t)n * (size_t)p;
+    if (bytes < ((size_t)256 << 20) || is_pinned_host(X)) {
+      CU(cudaMemcpy2DAsync(dX, sizeof(double) * ldd, X, sizeof(double) * ldx, sizeof(double) * p, (size_t)n,
+                           cudaMemcpyHostToDevice, ctx->stream));
+    } else if (int rc = upload_x_staged(ctx, dX, ldd, n, p, X, ldx)) {
+      return rc;
+    }
   }
   ctx->X = dX; ctx->ldx = ldd; ctx->n = n; ctx->p = p;
   return 0;

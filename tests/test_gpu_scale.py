@@ -347,3 +347,24 @@ def test_active_set_poisson_step():
     assert vec_err(xty, rxty) < 1e-10
     np.testing.assert_allclose(sc, rsc, rtol=1e-10)
     ctx.close()
+
+
+def test_large_pageable_upload_with_a_leading_dimension():
+    """Uploads of 256 MB and more from pageable host memory go through page-locked staging buffers filled by several host
+    threads (upload_x_staged); here with a host leading dimension larger than p (a row-strided view), which takes the
+    row-by-row packing branch.  The statistics must be those of the compact matrix."""
+    n, p, ld = 300_000, 120, 128
+    rng = np.random.default_rng(9)
+    wide = rng.normal(size=(n, ld))
+    wide[:, 0] = 1.0
+    X = wide[:, :p]                                        # strides (8 * 128, 8): passed with ldx = 128
+    assert not X.flags.c_contiguous and X.nbytes >= 256 << 20
+    y = (rng.random(n) < 0.4).astype(float)
+    nt = np.ones(n)
+    w, s = _latents(n, 3)
+    ctx, _ = logit_ctx(X, y, nt)
+    xtx, xty = ctx.accumulate(w, s)
+    Xc = np.ascontiguousarray(X)
+    rxtx, rxty = H.accumulate_blocked(Xc, w, s)
+    assert normwise_err(xtx, rxtx) < 1e-12 and vec_err(xty, rxty) < 1e-12
+    ctx.close()
