@@ -145,7 +145,7 @@ struct TailParams {
 };
 
 // The last CTA of a single-launch step: one THREAD per output element, the partials summed in CTA order (deterministic)
-// with 16 independent loads in flight (a warp per element serialises ~20 elements x 5 dependent L2 round trips on every
+// with 32 independent loads in flight (a warp per element serialises ~20 elements x 5 dependent L2 round trips on every
 // warp: 28 us at C1; this form is ~3 us).  Partials are read around L1: other CTAs of the same grid wrote them.
 template <int NB>
 __device__ __forceinline__ void sum_partials_tail(const double *__restrict__ partials, int nparts, int p, const TailParams &tail,
@@ -169,14 +169,20 @@ __device__ __forceinline__ void sum_partials_tail(const double *__restrict__ par
       }
       double s = 0;
       int cta = 0;
-      for (; cta + 16 <= nparts; cta += 16) {
-        double v[16];
+      for (; cta + 32 <= nparts; cta += 32) {
+        double v[32];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = __ldcg(partials + (int64_t)(cta + u) * plen + src);
+        for (int u = 0; u < 32; ++u) v[u] = __ldcg(partials + (int64_t)(cta + u) * plen + src);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) s += v[u];
+        for (int u = 0; u < 32; ++u) s += v[u];
       }
-      for (; cta < nparts; ++cta) s += __ldcg(partials + (int64_t)cta * plen + src);
+      {   // the remainder (< 32 partials), again with every load in flight before the first add; same order of additions
+        double v[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) v[u] = cta + u < nparts ? __ldcg(partials + (int64_t)(cta + u) * plen + src) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 32; ++u) s += v[u];
+      }
       if (e < ntri) {
         tail.suf[a + (int64_t)b * p] = s;
         tail.suf[b + (int64_t)a * p] = s;

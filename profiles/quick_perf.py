@@ -16,6 +16,7 @@ CFG = {
     "c4": ("logit", 2_000_000, 4000), "c5": ("logit", 25_000_000, 16), "c3s": ("logit", 1_000_000, 500),
     "p128": ("logit", 4_000_000, 128), "p64": ("logit", 8_000_000, 64), "p32": ("logit", 8_000_000, 32),
     "c4s": ("logit", 500_000, 4000), "p1000": ("logit", 2_000_000, 1000), "p260": ("logit", 4_000_000, 260),
+    "c1t": ("logit", 9_000, 20), "c1h": ("logit", 50_000, 20), "c1d": ("logit", 200_000, 20), "c1q": ("logit", 400_000, 20),
     "p40": ("logit", 8_000_000, 40), "p48l": ("logit", 8_000_000, 48), "p56": ("logit", 8_000_000, 56), "p40p": ("poisson", 4_000_000, 40),
     "p64p": ("poisson", 4_000_000, 64), "c5m": ("logit", 100_000_000, 16), "c5f": ("logit", 200_000_000, 16), "c2x4": ("poisson", 4_000_000, 50),
     "p8": ("logit", 25_000_000, 8), "p24": ("logit", 12_000_000, 24), "p48": ("poisson", 4_000_000, 48),
