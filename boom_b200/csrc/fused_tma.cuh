@@ -15,7 +15,7 @@
 //   DFMA per 4 rows.  beta arrives as a kernel parameter.
 //   Epilogue: the warps add their fragments into one shared tile (warp-tile parallel, fixed order per element), the CTA
 //   writes one partial, and the LAST CTA to finish (a counter in global memory, __threadfence on both sides) sums the
-//   partials in CTA order -- one thread per output element, 16 loads in flight -- and writes the statistics to the
+//   partials in CTA order -- one thread per output element, 32 loads in flight -- and writes the statistics to the
 //   device buffer and to the host-mapped copy: one launch per Gibbs step, deterministic (no floating point atomics).
 //   Option single_launch = 0 keeps the separate reduce_partials_kernel.
 //   Wide tiles (NB >= 5) also exist in a 12-warp form whose accumulators live in tensor memory between DMMA phases (PARK, below).
