@@ -83,6 +83,7 @@ struct boomgpu_ctx {
   int syrk_filter = 0;                             // profiling aid: time the off-diagonal / diagonal regions of the SYRK alone
   int syrk_order = 1;                              // 1 off-diagonal regions first, diagonal last (short CTAs fill the tail); 0 k-slice major
   int syrk_waves = 30;                             // CTAs per SM the split-K aims for
+  int syrk_cluster = 0;                            // experiment: launch the SYRK with thread-block clusters of this many CTAs
   int gather = 0;                                  // option: 0 auto (sparse beta -> gather pass), 1 never, 2 whenever beta has a zero
   double *suf_dev = nullptr; int64_t suf_cap = 0;
   double *suf_pin = nullptr; int64_t suf_pin_cap = 0;
@@ -557,7 +558,21 @@ int launch_syrk(boomgpu_ctx *ctx, double *suf) {
   CU(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmemBytes));
   {
     LaunchScope ls(ctx, 2);
-    syrk_dmma_kernel<<<(unsigned)(ksplit * sp.nregions), kSyrkThreads, kSyrkSmemBytes, ctx->stream>>>(ctx->xmap_syrk.map, sp, table);
+    const unsigned grid = (unsigned)(ksplit * sp.nregions);
+    if (ctx->syrk_cluster > 1 && grid % (unsigned)ctx->syrk_cluster == 0) {
+      // experiment (option "syrk_cluster"): co-schedule c consecutive CTAs -- with the off-diagonal-first order the regions of
+      // one k-slice that share panels -- as a thread-block cluster, so that they start together and meet in L2
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kSyrkThreads); cfg.dynamicSmemBytes = kSyrkSmemBytes; cfg.stream = ctx->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)ctx->syrk_cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      if (ctx->syrk_cluster > 8) cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      CU(cudaLaunchKernelEx(&cfg, syrk_dmma_kernel, ctx->xmap_syrk.map, sp, table));
+    } else {
+      syrk_dmma_kernel<<<grid, kSyrkThreads, kSyrkSmemBytes, ctx->stream>>>(ctx->xmap_syrk.map, sp, table);
+    }
   }
   CU(cudaGetLastError());
   {
@@ -1125,6 +1140,10 @@ int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value) {
   if (!strcmp(name, "syrk_diag")) { ctx->syrk_diag = value != 0; return 0; }
   if (!strcmp(name, "syrk_filter")) { ctx->syrk_filter = (int)value; return 0; }
   if (!strcmp(name, "syrk_order")) { ctx->syrk_order = value != 0; return 0; }
+  if (!strcmp(name, "syrk_cluster")) {
+    if (value < 0 || value > 16) return fail(ctx, BOOMGPU_ERR_ARG, "syrk_cluster must be in 0..16");
+    ctx->syrk_cluster = (int)value; return 0;
+  }
   if (!strcmp(name, "syrk_waves")) {
     if (value < 1 || value > 256) return fail(ctx, BOOMGPU_ERR_ARG, "syrk_waves must be in 1..256");
     ctx->syrk_waves = (int)value; return 0;

@@ -84,6 +84,7 @@ int boomgpu_set_row_offset(boomgpu_ctx *ctx, uint64_t first_global_row);
  *          "syrk_order" = 1 (default) the split-K SYRK's off-diagonal regions are scheduled first and the cheaper diagonal
  *                         regions last | 0 k-slice major; "syrk_waves" = CTAs per SM the split-K aims for (default 30);
  *          "syrk_diag" = 0 (default) strip form for whole diagonal regions | 1 unit form; "syrk_filter": profiling aid;
+ *          "syrk_cluster" = c > 1: launch the SYRK with thread-block clusters of c CTAs (experiment; measured slower);
  *          "timing" = 1 records CUDA events around every kernel (boomgpu_get_timings) */
 int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value);
 
