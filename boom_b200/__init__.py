@@ -19,7 +19,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _HOST_NAMES = (
     "RNG", "global_rng", "MvnModel", "MvnBase", "VariableSelectionPrior", "BinomialLogitModel", "PoissonRegressionModel",
     "PosteriorSampler", "BinomialLogitAuxmixSampler", "BinomialLogitSpikeSlabSampler", "PoissonRegressionAuxMixSampler",
-    "PoissonRegressionSpikeSlabSampler", "BinomialProbitModel", "BinomialProbitSpikeSlabSampler", "WeightedRegSuf", "set_logit_mixture", "set_poisson_mixture_table",
+    "PoissonRegressionSpikeSlabSampler", "BinomialProbitModel", "BinomialProbitSpikeSlabSampler", "TRegressionModel", "TRegressionSampler",
+    "DoubleModel", "UniformModel", "GammaModelBase", "GammaModel", "ChisqModel", "WeightedRegSuf", "set_logit_mixture", "set_poisson_mixture_table",
 )
 
 __all__ = ["BoomGpuError", "Context", "library_path", "load_library", "host", "load_poisson_mixture_table", "default_logit_mixture",

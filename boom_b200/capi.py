@@ -27,6 +27,8 @@ SYMBOLS = (
     "boomgpu_poisson_counts_present", "boomgpu_select_columns", "boomgpu_binomial_loglike_derivs_selected",
     "boomgpu_poisson_loglike_derivs_selected", "boomgpu_binomial_loglike_derivs_selected_device", "boomgpu_pin_host", "boomgpu_unpin_host", "boomgpu_comm_unique_id", "boomgpu_comm_init", "boomgpu_comm_destroy", "boomgpu_allreduce", "boomgpu_kernel_launches",
     "boomgpu_get_timings",
+    "boomgpu_upload_regression", "boomgpu_adopt_regression", "boomgpu_student_step", "boomgpu_student_step_device",
+    "boomgpu_student_draw", "boomgpu_student_loglike",
 )
 
 
@@ -151,9 +153,10 @@ class Context:
         self.n, self.p = n, p
 
     def upload_chunked(self, X, y, aux, chunk_rows, poisson=False):
-        """boomgpu_upload_begin / _rows / _end over row chunks (what the BOOM adapter does while walking model->dat())."""
+        """boomgpu_upload_begin / _rows / _end over row chunks (what the BOOM adapter does while walking model->dat()).
+        poisson: False / 0 binomial rows, True / 1 Poisson rows, 2 plain regression rows (aux ignored)."""
         X, aux = _f64(X), _f64(aux)
-        y = np.ascontiguousarray(y, dtype=np.int64 if poisson else np.float64)
+        y = np.ascontiguousarray(y, dtype=np.int64 if int(poisson) == 1 else np.float64)
         n, p = X.shape
         self._check(self._lib.boomgpu_upload_begin(self._h, C.c_int(int(poisson)), C.c_int64(n), C.c_int(p)))
         for a in range(0, n, chunk_rows):
@@ -286,6 +289,47 @@ class Context:
         self._check(self._lib.boomgpu_probit_draw(self._h, _dp(beta), C.c_int(clt_threshold), C.c_uint64(seed), C.c_uint64(iteration),
                                                   _dp(out)))
         return out
+
+    # ---- Student-t sibling (TRegressionSampler)
+    def upload_regression(self, X, y):
+        X, y = _f64(X), _f64(y)
+        n, p = X.shape
+        self._check(self._lib.boomgpu_upload_regression(self._h, C.c_int64(n), C.c_int(p), _dp(X), C.c_int64(X.strides[0] // 8), _dp(y)))
+        self.n, self.p = n, p
+
+    def adopt_regression(self, n, p, dX, ldx, dy, keepalive=()):
+        self._check(self._lib.boomgpu_adopt_regression(self._h, C.c_int64(n), C.c_int(p), C.c_void_p(dX), C.c_int64(ldx), C.c_void_p(dy)))
+        self.n, self.p = n, p
+        self._keep = list(keepalive)
+
+    def student_step(self, beta, sigma, nu, seed, iteration):
+        """(xtwx, xtwy, scalars[n, y'Wy, sum w, sum log w]) of TRegressionSampler::impute_latent_data."""
+        p = self.p
+        beta = _f64(beta)
+        xtwx, xtwy, sc = np.empty((p, p)), np.empty(p), np.empty(4)
+        self._check(self._lib.boomgpu_student_step(self._h, _dp(beta), C.c_double(sigma), C.c_double(nu), C.c_uint64(seed),
+                                                   C.c_uint64(iteration), _dp(xtwx), _dp(xtwy), _dp(sc)))
+        return xtwx, xtwy, sc
+
+    def student_step_device(self, beta, sigma, nu, seed, iteration, suf_dev_ptr):
+        beta = _f64(beta)
+        self._check(self._lib.boomgpu_student_step_device(self._h, _dp(beta), C.c_double(sigma), C.c_double(nu), C.c_uint64(seed),
+                                                          C.c_uint64(iteration), C.c_void_p(suf_dev_ptr)))
+
+    def student_draw(self, beta, sigma, nu, seed, iteration):
+        beta = _f64(beta)
+        out = np.empty(self.n)
+        self._check(self._lib.boomgpu_student_draw(self._h, _dp(beta), C.c_double(sigma), C.c_double(nu), C.c_uint64(seed),
+                                                   C.c_uint64(iteration), _dp(out)))
+        return out
+
+    def student_loglike(self, beta, sigma, nu):
+        """beta=None reuses the residuals of the previous call (the slice sampler on nu)."""
+        out = C.c_double()
+        b = None if beta is None else _f64(beta)
+        self._check(self._lib.boomgpu_student_loglike(self._h, None if b is None else _dp(b), C.c_double(sigma), C.c_double(nu),
+                                                      C.byref(out)))
+        return out.value
 
     def suf_len(self):
         return int(self._lib.boomgpu_suf_len(C.c_int(self.p)))

@@ -33,7 +33,7 @@ struct boomgpu_ctx {
   std::string error;
 
   // data
-  int model = -1;  // kLogit / kPoisson
+  int model = -1;  // kLogit / kPoisson / kStudentT (plain regression data: y only)
   int upload_kind = -1;  // between boomgpu_upload_begin and _end: the model the chunks belong to
   int64_t n = 0;
   int p = 0;
@@ -90,6 +90,8 @@ struct boomgpu_ctx {
   double *partials = nullptr; int64_t partials_cap = 0;
   double *scal_partials = nullptr; int64_t scal_cap = 0;
   double *w_buf = nullptr, *s_buf = nullptr; int64_t ws_cap = 0;
+  double *resid_buf = nullptr; int64_t resid_cap = 0;   // Student-t sibling: y - X beta of the last boomgpu_student_loglike(beta != NULL)
+  bool resid_valid = false;
   int *err_dev = nullptr;
   int *err_pin = nullptr;
   unsigned int *tail_counter = nullptr;   // single-launch small-p step: CTAs that have written their partial
@@ -161,6 +163,7 @@ void free_data(boomgpu_ctx *ctx) {
   ctx->Xt = nullptr; ctx->ldxt = 0;
   ctx->n = 0; ctx->p = 0; ctx->model = -1; ctx->upload_kind = -1;
   ctx->latents_valid = false;
+  ctx->resid_valid = false;
 }
 
 // ---- launch bookkeeping -------------------------------------------------------------------
@@ -864,6 +867,7 @@ DrawParams make_prm(boomgpu_ctx *ctx, int clt, uint64_t seed, uint64_t iteration
   philox_round_keys(prm.key);
   prm.clt_threshold = clt;
   prm.log_alpha = 0.0;
+  prm.t_inv_sigma = 0.0; prm.t_nu = 0.0;
   return prm;
 }
 
@@ -1102,7 +1106,7 @@ void boomgpu_destroy(boomgpu_ctx *ctx) {
   cudaFree(ctx->mix_dev);
   cudaFree(ctx->beta_dev); cudaFreeHost(ctx->beta_pin);
   cudaFree(ctx->suf_dev); cudaFreeHost(ctx->suf_pin);
-  cudaFree(ctx->partials); cudaFree(ctx->scal_partials);
+  cudaFree(ctx->partials); cudaFree(ctx->scal_partials); cudaFree(ctx->resid_buf);
   cudaFree(ctx->w_buf); cudaFree(ctx->s_buf);
   cudaFree(ctx->Xsel); cudaFree(ctx->sel_cols_dev);
   cudaFree(ctx->act_dev); cudaFreeHost(ctx->act_pin); cudaFree(ctx->col_buf);
@@ -1210,17 +1214,18 @@ int boomgpu_upload_begin(boomgpu_ctx *ctx, int poisson, int64_t n, int p) {
   ctx->owned.push_back(daux);
   if (ldd != p && n) CU(cudaMemsetAsync(dX, 0, sizeof(double) * (size_t)(n * ldd), ctx->stream));
   ctx->X = dX; ctx->ldx = ldd; ctx->n = n; ctx->p = p;
-  if (poisson) { ctx->yi = (const int64_t *)dy; ctx->exposure = daux; }
+  if (poisson == 1) { ctx->yi = (const int64_t *)dy; ctx->exposure = daux; }
   else { ctx->y = (const double *)dy; ctx->ntrials = daux; }
   ctx->model = -1;                 // not usable until boomgpu_upload_end
-  ctx->upload_kind = poisson ? kPoisson : kLogit;
+  ctx->upload_kind = poisson == 1 ? kPoisson : poisson == 2 ? kStudentT : kLogit;   // 2: plain regression rows (y only)
   return 0;
 }
 
 int boomgpu_upload_rows(boomgpu_ctx *ctx, int64_t row0, int64_t nrows, const double *X, int64_t ldx, const void *y, const double *aux) {
   if (!ctx) return BOOMGPU_ERR_ARG;
   if (ctx->upload_kind < 0 || !ctx->X) return fail(ctx, BOOMGPU_ERR_STATE, "boomgpu_upload_rows without boomgpu_upload_begin");
-  if (row0 < 0 || nrows < 0 || row0 + nrows > ctx->n || ldx < ctx->p || (nrows > 0 && (!X || !y || !aux)))
+  if (row0 < 0 || nrows < 0 || row0 + nrows > ctx->n || ldx < ctx->p ||
+      (nrows > 0 && (!X || !y || (!aux && ctx->upload_kind != kStudentT))))
     return fail(ctx, BOOMGPU_ERR_ARG, "bad row range [%lld, %lld) of %lld", (long long)row0, (long long)(row0 + nrows), (long long)ctx->n);
   if (nrows == 0) return 0;
   DeviceGuard g(ctx->device);
@@ -1230,7 +1235,7 @@ int boomgpu_upload_rows(boomgpu_ctx *ctx, int64_t row0, int64_t nrows, const dou
   void *dy = ctx->upload_kind == kPoisson ? (void *)(const_cast<int64_t *>(ctx->yi) + row0) : (void *)(const_cast<double *>(ctx->y) + row0);
   double *da = const_cast<double *>(ctx->upload_kind == kPoisson ? ctx->exposure : ctx->ntrials) + row0;
   CU(cudaMemcpyAsync(dy, y, 8 * (size_t)nrows, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(da, aux, sizeof(double) * (size_t)nrows, cudaMemcpyHostToDevice, ctx->stream));
+  if (aux) CU(cudaMemcpyAsync(da, aux, sizeof(double) * (size_t)nrows, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));   // the caller re-uses its chunk buffers
   return 0;
 }
@@ -1264,6 +1269,30 @@ int boomgpu_adopt_poisson(boomgpu_ctx *ctx, int64_t n, int p, const double *dX, 
   free_data(ctx);
   ctx->X = dX; ctx->ldx = ldx; ctx->n = n; ctx->p = p; ctx->yi = dy; ctx->exposure = dexposure;
   ctx->model = kPoisson;
+  return 0;
+}
+
+// plain regression rows (y double, no trials / exposure): the Student-t sibling (TRegressionModel, Models/Glm/TRegression.cpp:43-54)
+int boomgpu_upload_regression(boomgpu_ctx *ctx, int64_t n, int p, const double *X, int64_t ldx, const double *y) {
+  if (int rc = check_dims(ctx, n, p, ldx, X)) return rc;
+  if (n > 0 && !y) return fail(ctx, BOOMGPU_ERR_ARG, "null y");
+  DeviceGuard g(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  free_data(ctx);
+  if (int rc = upload_x(ctx, n, p, X, ldx)) return rc;
+  if (int rc = upload_array(ctx, y, n, &ctx->y)) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->model = kStudentT;
+  return 0;
+}
+
+int boomgpu_adopt_regression(boomgpu_ctx *ctx, int64_t n, int p, const double *dX, int64_t ldx, const double *dy) {
+  if (int rc = check_dims(ctx, n, p, ldx, dX)) return rc;
+  DeviceGuard g(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  free_data(ctx);
+  ctx->X = dX; ctx->ldx = ldx; ctx->n = n; ctx->p = p; ctx->y = dy;
+  ctx->model = kStudentT;
   return 0;
 }
 
@@ -1681,6 +1710,125 @@ int boomgpu_probit_draw(boomgpu_ctx *ctx, const double *beta, int clt_threshold,
   if (!rc) rc = finish_and_check(ctx); else cudaStreamSynchronize(ctx->stream);
   cudaFree(ds);
   return rc;
+}
+
+// ---- Student-t sibling (TRegressionSampler) ------------------------------------------------------------
+static int check_student(boomgpu_ctx *ctx, double sigma, double nu) {
+  if (!ctx) return BOOMGPU_ERR_ARG;
+  if (ctx->model != kStudentT || !ctx->X) return fail(ctx, BOOMGPU_ERR_STATE, "no regression data uploaded to this context");
+  if (!(sigma > 0) || !(nu > 0) || !std::isfinite(sigma) || !std::isfinite(nu))
+    return fail(ctx, BOOMGPU_ERR_ARG, "sigma = %g, nu = %g: both must be positive and finite", sigma, nu);
+  return 0;
+}
+
+static DrawParams make_student_prm(boomgpu_ctx *ctx, double sigma, double nu, uint64_t seed, uint64_t iteration) {
+  DrawParams prm = make_prm(ctx, 0, seed, iteration);
+  prm.t_inv_sigma = 1.0 / sigma; prm.t_nu = nu;
+  return prm;
+}
+
+int boomgpu_student_step_device(boomgpu_ctx *ctx, const double *beta, double sigma, double nu, uint64_t seed, uint64_t iteration,
+                                double *suf_dev) {
+  if (int rc = check_student(ctx, sigma, nu)) return rc;
+  if (!beta || !suf_dev) return fail(ctx, BOOMGPU_ERR_ARG, "null beta / suf_dev");
+  DeviceGuard g(ctx->device);
+  RowOut out{nullptr, nullptr, nullptr, nullptr};
+  return run_step<kStudentT>(ctx, beta, make_student_prm(ctx, sigma, nu, seed, iteration), out, nullptr, nullptr, suf_dev);
+}
+
+int boomgpu_student_step(boomgpu_ctx *ctx, const double *beta, double sigma, double nu, uint64_t seed, uint64_t iteration,
+                         double *xtwx, double *xtwy, double scalars[4]) {
+  if (int rc = check_student(ctx, sigma, nu)) return rc;
+  if (!beta || !xtwx || !xtwy) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
+  DeviceGuard g(ctx->device);
+  if (int rc = ensure_suf(ctx)) return rc;
+  const bool sharded = ctx->comm && ctx->comm_ranks > 1;
+  RowOut out{nullptr, nullptr, nullptr, nullptr};
+  if (int rc = run_step<kStudentT>(ctx, beta, make_student_prm(ctx, sigma, nu, seed, iteration), out, nullptr, nullptr, ctx->suf_dev,
+                                   sharded ? nullptr : ctx->suf_pin))
+    return rc;
+  if (int rc = allreduce_on_stream(ctx, ctx->suf_dev, boomgpu_suf_len(ctx->p))) return rc;
+  bool in_place = false;
+  if (int rc = fetch_suf(ctx, xtwx, &in_place)) return rc;
+  const int p = ctx->p;
+  if (!in_place) memcpy(xtwx, ctx->suf_pin, sizeof(double) * (size_t)p * p);
+  memcpy(xtwy, ctx->suf_pin + (size_t)p * p, sizeof(double) * p);
+  if (scalars) memcpy(scalars, ctx->suf_pin + (size_t)p * p + p, sizeof(double) * 4);
+  return 0;
+}
+
+int boomgpu_student_draw(boomgpu_ctx *ctx, const double *beta, double sigma, double nu, uint64_t seed, uint64_t iteration,
+                         double *weight_out) {
+  if (int rc = check_student(ctx, sigma, nu)) return rc;
+  if (!beta || !weight_out) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
+  DeviceGuard g(ctx->device);
+  if (int rc = ensure_suf(ctx)) return rc;
+  double *dw = nullptr;
+  CU(cudaMalloc((void **)&dw, sizeof(double) * (size_t)std::max<int64_t>(ctx->n, 1)));
+  RowOut out{dw, nullptr, nullptr, nullptr};
+  int rc = run_step<kStudentT>(ctx, beta, make_student_prm(ctx, sigma, nu, seed, iteration), out, nullptr, nullptr, ctx->suf_dev);
+  if (!rc && cudaMemcpyAsync(weight_out, dw, sizeof(double) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+    rc = fail(ctx, BOOMGPU_ERR_CUDA, "copy of draws failed");
+  if (!rc) rc = finish_and_check(ctx); else cudaStreamSynchronize(ctx->stream);
+  cudaFree(dw);
+  return rc;
+}
+
+// Observed-data log likelihood sum_i log dstudent(y_i; x_i'beta, sigma, nu).  beta != NULL: one pass over X stores the
+// residuals; beta == NULL: the residuals of the previous call are reused (8 n bytes per evaluation) -- the slice sampler on
+// nu evaluates the likelihood at several nu with beta fixed.  All-reduced when the context is sharded.
+int boomgpu_student_loglike(boomgpu_ctx *ctx, const double *beta, double sigma, double nu, double *loglike) {
+  if (int rc = check_student(ctx, sigma, nu)) return rc;
+  if (!loglike) return fail(ctx, BOOMGPU_ERR_ARG, "null argument");
+  if (!beta && !ctx->resid_valid) return fail(ctx, BOOMGPU_ERR_STATE, "boomgpu_student_loglike(beta = NULL) before a call with beta");
+  DeviceGuard g(ctx->device);
+  const int p = ctx->p;
+  const int64_t n = ctx->n;
+  if (n == 0) { *loglike = 0.0; ctx->resid_valid = true; return 0; }   // sharded callers add their own shards
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sms * 8));
+  if (ctx->resid_cap < n + grid + 8) ctx->resid_valid = false;
+  if (!beta && !ctx->resid_valid) return fail(ctx, BOOMGPU_ERR_STATE, "boomgpu_student_loglike(beta = NULL) before a call with beta");
+  if (int rc = ensure(ctx, &ctx->resid_buf, &ctx->resid_cap, n + grid + 8)) return rc;   // [residuals | per-CTA partials | result, n]
+  double *parts = ctx->resid_buf + n;
+  if (beta) {
+    ctx->resid_valid = false;
+    if (ctx->beta_cap < p + 2) {   // the step's beta staging buffers
+      if (ctx->beta_dev) { CU(cudaFree(ctx->beta_dev)); ctx->beta_dev = nullptr; }
+      if (ctx->beta_pin) { CU(cudaFreeHost(ctx->beta_pin)); ctx->beta_pin = nullptr; }
+      const size_t bytes = sizeof(double) * (size_t)(p + 2) + sizeof(int) * (size_t)(p + 2);
+      CU(cudaMalloc((void **)&ctx->beta_dev, bytes));
+      CU(cudaMallocHost((void **)&ctx->beta_pin, bytes));
+      ctx->beta_cap = p + 2;
+    }
+    memcpy(ctx->beta_pin, beta, sizeof(double) * p);
+    CU(cudaMemcpyAsync(ctx->beta_dev, ctx->beta_pin, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+    RowData d;
+    memset(&d, 0, sizeof(d));
+    d.X = ctx->X; d.ldx = ctx->ldx; d.n = n; d.p = p; d.y = ctx->y;
+    const int rgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sms * 8));
+    LaunchScope ls(ctx, 4);
+    residual_kernel<<<rgrid, 256, sizeof(double) * p, ctx->stream>>>(d, ctx->beta_dev, ctx->resid_buf);
+  }
+  {
+    LaunchScope ls(ctx, 4);
+    student_loglike_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->resid_buf, n, 1.0 / sigma, nu, parts);
+  }
+  {
+    LaunchScope ls(ctx, 3);
+    reduce_sum_kernel<<<1, 32, 0, ctx->stream>>>(parts, grid, parts + grid);
+  }
+  CU(cudaGetLastError());
+  // [row part | n]: both sum over the shards
+  const double nd = (double)n;
+  CU(cudaMemcpyAsync(parts + grid + 1, &nd, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (int rc = allreduce_on_stream(ctx, parts + grid, 2)) return rc;
+  double res[2] = {0, 0};
+  CU(cudaMemcpyAsync(res, parts + grid, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->resid_valid = true;
+  const double kLogPi = 1.1447298858494001741434;
+  *loglike = res[0] + res[1] * (lgamma(0.5 * (nu + 1.0)) - lgamma(0.5 * nu) - 0.5 * (log(nu) + kLogPi) - log(sigma));
+  return 0;
 }
 
 int boomgpu_accumulate(boomgpu_ctx *ctx, const double *weight, const double *weighted_value, double *xtx, double *xty) {

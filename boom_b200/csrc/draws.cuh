@@ -596,6 +596,42 @@ __device__ __noinline__ bool probit_impute(int clt_threshold, double ntrials, do
   return true;
 }
 
+// ---- Student-t sibling (TRegressionSampler) ----------------------------------
+// Gamma(shape, rate) on the Philox stream.  The reference's TDataImputer::impute (Models/Glm/PosteriorSamplers/
+// TDataImputer.cpp:25-29) calls rgamma_mt (distributions/Rmath_dist.cpp:72-74 -> Bmath/rgamma.cpp, Ahrens-Dieter GD / GS):
+// the same law from another stream.  Here Marsaglia & Tsang's (2000) method: attempt k consumes block k of the row -- its
+// first uniform gives the normal deviate by inversion, its second decides acceptance (>= 95 % accept for shape >= 1).
+// A shape below 1 is drawn as Gamma(shape + 1) U^(1/shape) with U from block 0xFFFF.  Slots as in the oracle (bo_rgamma).
+constexpr uint32_t kGammaBoostSlot = 0xFFFFu;
+constexpr int kGammaMaxAttempts = 4096;
+__device__ inline bool rgamma_philox(double shape, double rate, const RngKey &key, uint64_t row, double *out) {
+  *out = 0;
+  if (!(shape > 0) || !(rate > 0) || !isfinite(shape) || !isfinite(rate)) return false;
+  const double a = shape < 1.0 ? shape + 1.0 : shape;
+  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  double g = -1.0, u0, u1;
+  for (int k = 0; k < kGammaMaxAttempts; ++k) {
+    uniform_pair(key, row, (uint32_t)k, u0, u1);
+    const double x = normcdfinv(u0);
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    if (log(u1) < 0.5 * x * x + d - d * v + d * log(v)) { g = d * v; break; }
+  }
+  if (g < 0) return false;
+  if (shape < 1.0) {
+    uniform_pair(key, row, kGammaBoostSlot, u0, u1);
+    g *= exp(log(u0) / shape);
+  }
+  *out = g / rate;
+  return true;
+}
+
+// log density of the Student t observation y = mu + sigma t_nu at standardised residual delta, WITHOUT the terms that
+// depend on (sigma, nu) alone: -(nu + 1)/2 log1p(delta^2 / nu).  The caller adds n (lgamma((nu+1)/2) - lgamma(nu/2) -
+// log(nu pi)/2 - log sigma)  (dstudent, distributions/student_fix.cpp:28-41 over Bmath dt).
+__device__ __forceinline__ double student_log_kernel(double delta, double nu) { return -0.5 * (nu + 1.0) * log1p(delta * delta / nu); }
+
 // ---- Poisson --------------------------------------------------------------------------
 __device__ __forceinline__ int poisson_table_find(const PoissonTable &t, int64_t nu) {
   if (nu < (int64_t)t.dense_n) return nu >= 0 ? __ldg(t.dense + nu) : -1;

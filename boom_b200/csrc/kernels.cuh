@@ -27,7 +27,8 @@ namespace boomgpu {
 // kLogitLL / kPoissonLL: no draw; the row's "latent" is its log-likelihood curvature, so the same kernels return
 // log likelihood, gradient and (minus) Hessian in one pass (BinomialLogitModel.cpp:140-180, PoissonRegressionModel.cpp:56-95)
 // kProbit: the probit sibling (BinomialProbitSpikeSlabSampler): weight n_i, weighted value = sum of the latent normals
-enum Model : int { kLogit = 0, kPoisson = 1, kSupplied = 2, kLogitLL = 3, kPoissonLL = 4, kProbit = 5 };
+// kStudentT: the Student-t sibling (TRegressionSampler): weight w_i ~ Gamma((nu+1)/2, (nu + delta_i^2)/2), weighted value w_i y_i
+enum Model : int { kLogit = 0, kPoisson = 1, kSupplied = 2, kLogitLL = 3, kPoissonLL = 4, kProbit = 5, kStudentT = 6 };
 
 struct RowData {
   const double *X;
@@ -58,6 +59,7 @@ struct DrawParams {
   RngKey key;
   int clt_threshold;
   double log_alpha;         // kLogitLL: eta = x'beta - log_alpha (BinomialLogitModel.cpp:168)
+  double t_inv_sigma, t_nu; // kStudentT: 1 / sigma and the tail thickness of TRegressionModel
 };
 
 // ---- small helpers ------------------------------------------------------------------------
@@ -94,6 +96,7 @@ __device__ __forceinline__ RowObs load_obs(const RowData &d, int64_t i) {
   o.y = 0; o.aux = 0; o.yi = 0;
   if (MODEL == kLogit || MODEL == kLogitLL || MODEL == kProbit) { o.y = __ldg(d.y + i); o.aux = __ldg(d.ntrials + i); }
   else if (MODEL == kPoisson || MODEL == kPoissonLL) { o.yi = __ldg(d.yi + i); o.aux = __ldg(d.exposure + i); }
+  else if (MODEL == kStudentT) { o.y = __ldg(d.y + i); }
   else { o.y = __ldg(d.w_in + i); o.aux = __ldg(d.s_in + i); }
   return o;
 }
@@ -133,6 +136,14 @@ __device__ __forceinline__ RowLatent impute_row(const RowData &d, const DrawPara
     if (!ok) { atomicOr(err, 2); sz = 0; }
     r.w = ok ? obs.aux : 0.0;    // refresh_xtx: xtx += n_i x x' (BinomialProbitSpikeSlabSampler.cpp:72-78)
     r.s = sz;
+  } else if (MODEL == kStudentT) {
+    // TRegressionSampler::impute_latent_data (TRegressionSampler.cpp:128-143): weight | residual, then
+    // WeightedRegSuf::add_data(x, y, weight) and the weight model's GammaSuf (sum, sum of logs: the same two scalars)
+    const double delta = (obs.y - eta) * prm.t_inv_sigma;
+    double w;
+    const bool ok = isfinite(delta) && rgamma_philox(0.5 * (prm.t_nu + 1.0), 0.5 * (prm.t_nu + delta * delta), prm.key, d.row_offset + (uint64_t)i, &w);
+    if (!ok) { atomicOr(err, 2); w = 0; }
+    r.w = w; r.s = w * obs.y; r.yWy = w * obs.y * obs.y; r.sumlogw = ok ? log(w) : 0.0;
   } else if (MODEL == kLogitLL) {
     // w = n p q (so that -X'WX is the Hessian), s = y - n p (X's is the gradient), the log density rides in the yWy slot
     const double e = eta - prm.log_alpha;
@@ -1113,6 +1124,44 @@ __global__ void __launch_bounds__(256) loglike_kernel(RowData d, const double *_
       else acc += dpois_log((double)d.yi[i], d.exposure[i] * exp(e));
     }
   }
+  if (lane == 0) red_s[wid] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0;
+    for (int w = 0; w < 8; ++w) s += red_s[w];
+    partials[blockIdx.x] = s;
+  }
+}
+
+// Student-t sibling: residuals e_i = y_i - x_i'beta (warp per row) ...
+__global__ void __launch_bounds__(256) residual_kernel(RowData d, const double *__restrict__ beta, double *__restrict__ resid) {
+  extern __shared__ __align__(128) double smem[];
+  double *beta_s = smem;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int j = tid; j < d.p; j += 256) beta_s[j] = beta[j];
+  __syncthreads();
+  const int warps_per_grid = gridDim.x * 8;
+  for (int64_t i = (int64_t)blockIdx.x * 8 + wid; i < d.n; i += warps_per_grid) {
+    const double *xr = d.X + i * d.ldx;
+    double e = 0;
+    for (int j = lane; j < d.p; j += 32) e = fma(__ldg(xr + j), beta_s[j], e);
+    e = warp_sum(e);
+    if (lane == 0) resid[i] = d.y[i] - e;
+  }
+}
+
+// ... and the part of the observed-data log likelihood that depends on the rows, from the stored residuals:
+// sum_i -(nu + 1)/2 log1p(e_i^2 / (nu sigma^2)).  The slice sampler on nu (TRegressionSampler::draw_nu_given_observed_data,
+// TRegressionSampler.cpp:173-176 over TRegressionModel::log_likelihood, TRegression.cpp:74-86) evaluates it several times per
+// draw with beta and sigma fixed: 8 n bytes per evaluation instead of a pass over X.  Fixed-order partials.
+__global__ void __launch_bounds__(256) student_loglike_kernel(const double *__restrict__ resid, int64_t n, double inv_sigma, double nu,
+                                                              double *__restrict__ partials) {
+  __shared__ double red_s[8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  double acc = 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + tid; i < n; i += (int64_t)gridDim.x * 256)
+    acc += student_log_kernel(__ldg(resid + i) * inv_sigma, nu);
+  acc = warp_sum(acc);
   if (lane == 0) red_s[wid] = acc;
   __syncthreads();
   if (tid == 0) {

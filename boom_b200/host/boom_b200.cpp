@@ -1456,4 +1456,330 @@ void BinomialProbitSpikeSlabSampler::impute_latent_data() {
   xtx_data_version_ = model_->data_version();
 }
 
+// =============================================================================================
+// The Student-t sibling: TRegressionModel + TRegressionSampler and the small scalar samplers it owns.
+// =============================================================================================
+UniformModel::UniformModel(double lo, double hi) : lo_(lo), hi_(hi) {
+  if (!(hi > lo)) report_error("UniformModel: hi must exceed lo");
+}
+double UniformModel::logp(double x) const {
+  return (x >= lo_ && x <= hi_) ? -std::log(hi_ - lo_) : -std::numeric_limits<double>::infinity();
+}
+
+GammaModel::GammaModel(double a, double b) : a_(a), b_(b) {
+  if (!(a > 0) || !(b > 0)) report_error("GammaModel: shape and rate must be positive");
+}
+double GammaModelBase::logp(double x) const {   // dgamma(x, a, b, log) with b a rate
+  const double a = alpha(), b = beta();
+  if (x < 0) return -std::numeric_limits<double>::infinity();
+  if (x == 0) return a < 1 ? std::numeric_limits<double>::infinity() : a == 1 ? std::log(b) : -std::numeric_limits<double>::infinity();
+  return a * std::log(b) - std::lgamma(a) + (a - 1.0) * std::log(x) - b * x;
+}
+
+double rgamma_mt(RNG &rng, double a, double b) {
+  if (!(a > 0) || !(b > 0)) report_error("rgamma_mt: shape and rate must be positive");
+  std::gamma_distribution<double> d(a, 1.0 / b);
+  return d(rng.generator());
+}
+double rexp_mt(RNG &rng, double lambda) {
+  double u = rng();
+  while (u <= 0) u = rng();
+  return -std::log(u) / lambda;
+}
+// Gamma(a, b) given x > cut.  Below the mode: plain rejection, as the reference (trun_gamma.cpp:76-81).  Beyond it the
+// reference runs an adaptive rejection sampler (a > 1) or slice steps; here an exact exponential-envelope rejection:
+// x = cut + Exp(lambda), lambda = b - (a-1)/cut (a > 1) or b (a <= 1), accepted with probability
+// (x/cut)^(a-1) exp(-(a-1)(x-cut)/cut) (resp. (x/cut)^(a-1)), both <= 1.
+double rtrun_gamma_mt(RNG &rng, double a, double b, double cut) {
+  if (!(cut > 0)) return rgamma_mt(rng, a, b);
+  const double mode = (a - 1.0) / b;
+  if (cut < mode) {
+    double x;
+    do { x = rgamma_mt(rng, a, b); } while (x < cut);
+    return x;
+  }
+  const double slope = a > 1.0 ? (a - 1.0) / cut : 0.0;
+  const double lambda = b - slope;
+  for (int tries = 0; tries < 100000; ++tries) {
+    const double x = cut + rexp_mt(rng, lambda);
+    const double log_accept = (a - 1.0) * std::log(x / cut) - slope * (x - cut);
+    if (std::log(std::max(rng(), 1e-300)) <= log_accept) return x;
+  }
+  report_error("rtrun_gamma_mt: rejection sampler failed");
+}
+
+GenericGaussianVarianceSampler::GenericGaussianVarianceSampler(const std::shared_ptr<GammaModelBase> &prior, double sigma_max)
+    : prior_(prior), sigma_max_(std::numeric_limits<double>::infinity()) { set_sigma_max(sigma_max); }
+void GenericGaussianVarianceSampler::set_sigma_max(double sigma_max) {
+  if (sigma_max < 0) report_error("sigma_max must be non-negative.");
+  sigma_max_ = sigma_max;
+}
+double GenericGaussianVarianceSampler::draw(RNG &rng, double data_df, double data_ss, double scale) const {
+  if (!prior_) report_error("GenericGaussianVarianceSampler is disabled because it was built with a null prior.");
+  const double DF = data_df + 2 * prior_->alpha();
+  const double SS = data_ss + 2 * prior_->beta() * scale * scale;
+  if (sigma_max_ == 0.0) return 0.0;
+  if (std::isinf(sigma_max_)) return 1.0 / rgamma_mt(rng, DF / 2, SS / 2);
+  return 1.0 / rtrun_gamma_mt(rng, DF / 2, SS / 2, 1.0 / (sigma_max_ * sigma_max_));
+}
+double GenericGaussianVarianceSampler::posterior_mode(double data_df, double data_ss) const {
+  if (!prior_) report_error("GenericGaussianVarianceSampler is disabled because it was built with a null prior.");
+  const double alpha = (data_df + 2 * prior_->alpha()) / 2, beta = (data_ss + 2 * prior_->beta()) / 2;
+  const double mode = beta / (alpha + 1), cap = sigma_max_ * sigma_max_;
+  return mode > cap ? cap : mode;
+}
+double GenericGaussianVarianceSampler::log_prior(double sigsq) const {
+  if (!prior_) report_error("GenericGaussianVarianceSampler is disabled because it was built with a null prior.");
+  return prior_->logp(1.0 / sigsq) - 2 * std::log(sigsq);
+}
+
+// ---- ScalarSliceSampler (Samplers/ScalarSliceSampler.cpp) -------------------------------------
+ScalarSliceSampler::ScalarSliceSampler(const Fun &logf, bool unimodal, double dx, RNG *rng)
+    : logf_(logf), rng_(rng), suggested_dx_(dx), unimodal_(unimodal) {}
+void ScalarSliceSampler::set_lower_limit(double lo) {
+  if (std::isfinite(lo)) { lo_ = lower_bound_ = lo; lo_set_ = true; } else lo_set_ = false;
+}
+void ScalarSliceSampler::set_upper_limit(double hi) {
+  if (std::isfinite(hi)) { hi_ = upper_bound_ = hi; hi_set_ = true; } else hi_set_ = false;
+}
+void ScalarSliceSampler::handle_error(const std::string &msg, double x) const {
+  std::ostringstream err;
+  err << msg << " in ScalarSliceSampler\nlo = " << lo_ << "  logp(lo) = " << logplo_ << "\nhi = " << hi_ << "  logp(hi) = " << logphi_
+      << "\nx  = " << x << "  logp(x)  = " << logp_slice_ << "\n";
+  report_error(err.str());
+}
+void ScalarSliceSampler::double_hi(double x) {
+  hi_ = x + 2 * (hi_ - x);
+  if (!std::isfinite(hi_)) handle_error("infinite upper limit", x);
+  logphi_ = f(hi_);
+}
+void ScalarSliceSampler::double_lo(double x) {
+  lo_ = x - 2 * (x - lo_);
+  if (!std::isfinite(lo_)) handle_error("infinite lower limit", x);
+  logplo_ = f(lo_);
+}
+bool ScalarSliceSampler::find_upper_limit(double x) {   // .cpp:185-201
+  hi_ = x + suggested_dx_;
+  logphi_ = f(hi_);
+  int doubling_count = 0;
+  while (logphi_ >= logp_slice_ || (!unimodal_ && runif_mt(*rng_) > .5)) {
+    double_hi(x);
+    if (++doubling_count > 100) return false;
+  }
+  if (x > hi_ || std::isnan(logphi_)) handle_error("problem with the upper limit", x);
+  return true;
+}
+bool ScalarSliceSampler::find_lower_limit(double x) {   // .cpp:203-219
+  lo_ = x - suggested_dx_;
+  logplo_ = f(lo_);
+  int doubling_count = 0;
+  while (logplo_ >= logp_slice_ || (!unimodal_ && runif_mt(*rng_) > .5)) {
+    double_lo(x);
+    if (++doubling_count > 100) return false;
+  }
+  if (x < lo_ || std::isnan(logplo_)) handle_error("problem with the lower limit", x);
+  return true;
+}
+bool ScalarSliceSampler::find_limits_unbounded(double x) {   // .cpp:138-170
+  hi_ = x + suggested_dx_;
+  lo_ = x - suggested_dx_;
+  logphi_ = f(hi_);
+  logplo_ = f(lo_);
+  if (unimodal_) {
+    while (logphi_ >= logp_slice_) double_hi(x);
+    while (logplo_ >= logp_slice_) double_lo(x);
+    return true;
+  }
+  int doubling_count = 0;
+  while (!((logphi_ < logp_slice_) && (logplo_ < logp_slice_))) {
+    if (runif_mt(*rng_, -1, 1) > 0) double_hi(x); else double_lo(x);
+    if (++doubling_count > 100) return false;
+  }
+  return true;
+}
+void ScalarSliceSampler::find_limits(double x) {   // .cpp:108-133
+  logp_slice_ = f(x) - rexp_mt(*rng_, 1.0);
+  if (!std::isfinite(logp_slice_)) handle_error("initial value leads to infinite probability", x);
+  bool found = true;
+  if (lo_set_ && hi_set_) {
+    lo_ = lower_bound_; logplo_ = f(lo_);
+    hi_ = upper_bound_; logphi_ = f(hi_);
+  } else if (lo_set_) {
+    lo_ = lower_bound_; logplo_ = f(lo_);
+    found = find_upper_limit(x);
+  } else if (hi_set_) {
+    found = find_lower_limit(x);
+    hi_ = upper_bound_; logphi_ = f(hi_);
+  } else {
+    found = find_limits_unbounded(x);
+  }
+  if (x < lo_ || x > hi_) handle_error("problem building slice:  x out of bounds", x);
+  if (found) {
+    const bool logood = lo_set_ || (logplo_ <= logp_slice_), higood = hi_set_ || (logphi_ <= logp_slice_);
+    if (!(logood && higood)) handle_error("problem with probabilities", x);
+  }
+}
+void ScalarSliceSampler::contract(double x, double x_cand, double logp) {   // .cpp:92-104
+  if (x_cand > x) { hi_ = x_cand; logphi_ = logp; } else { lo_ = x_cand; logplo_ = logp; }
+  if (estimate_dx_) {
+    suggested_dx_ = hi_ - lo_;
+    if (suggested_dx_ < min_dx_) suggested_dx_ = min_dx_;
+  }
+}
+double ScalarSliceSampler::draw(double x) {   // .cpp:67-88
+  if (!rng_) report_error("ScalarSliceSampler: no random number generator");
+  find_limits(x);
+  for (int tries = 0; tries <= 100; ++tries) {
+    const double x_cand = runif_mt(*rng_, lo_, hi_);
+    const double logp_cand = f(x_cand);
+    if (logp_cand >= logp_slice_) return x_cand;
+    contract(x, x_cand, logp_cand);
+  }
+  handle_error("number of tries exceeded", x);
+}
+
+// ---- TRegressionModel -------------------------------------------------------------------------
+TRegressionModel::TRegressionModel(int64_t n, int p, const double *X, const double *y) : GlmModelBase(p) {
+  x_.assign(X, X + (size_t)n * p);
+  y_.assign(y, y + n);
+}
+void TRegressionModel::add_data(double y, const Vector &x) {
+  if ((int)x.size() != xdim()) report_error("TRegressionModel::add_data: wrong size x");
+  if (adopted_ || borrowed_) report_error("add_data on a model whose data live in adopted / borrowed memory");
+  x_.insert(x_.end(), x.begin(), x.end());
+  y_.push_back(y);
+  touch();
+}
+void TRegressionModel::adopt_device_data(int64_t n, const double *dX, int64_t ldx, const double *dy) {
+  adopted_ = true; adopted_n_ = n; dX_ = dX; dldx_ = ldx; dy_ = dy;
+  touch();
+}
+void TRegressionModel::borrow_host_data(int64_t n, const double *X, int64_t ldx, const double *y, std::shared_ptr<void> keepalive) {
+  borrowed_ = true; adopted_ = false; adopted_n_ = n; dX_ = X; dldx_ = ldx; dy_ = y;
+  keepalive_ = std::move(keepalive);
+  touch();
+}
+void TRegressionModel::upload(DeviceData &dev) {
+  if (borrowed_) { dev.check(boomgpu_upload_regression(dev.ctx(), adopted_n_, xdim(), dX_, dldx_, dy_)); return; }
+  if (adopted_) dev.check(boomgpu_adopt_regression(dev.ctx(), adopted_n_, xdim(), dX_, dldx_, dy_));
+  else dev.check(boomgpu_upload_regression(dev.ctx(), (int64_t)y_.size(), xdim(), x_.data(), xdim(), y_.data()));
+}
+void TRegressionModel::set_sigsq(double s2) {
+  if (!(s2 > 0)) report_error("TRegressionModel::set_sigsq: sigsq must be positive");
+  sigsq_ = s2;
+}
+void TRegressionModel::set_nu(double nu) {
+  if (!(nu > 0)) report_error("TRegressionModel::set_nu: nu must be positive");
+  nu_ = nu;
+}
+double TRegressionModel::log_likelihood(const Vector &beta, double sigsq, double nu) {
+  if ((int)beta.size() != xdim()) report_error("log_likelihood: wrong size beta");
+  if (!(nu > 0) || !(sigsq > 0)) return -std::numeric_limits<double>::infinity();
+  if (allreduce()) report_error("TRegressionModel::log_likelihood: shard through set_communicator (the all-reduce hook is not supported here)");
+  DeviceData &dev(device_data());
+  double ans = 0;
+  dev.check(boomgpu_student_loglike(dev.ctx(), beta.data(), std::sqrt(sigsq), nu, &ans));
+  return ans;
+}
+double TRegressionModel::log_likelihood_same_beta(double sigsq, double nu) {
+  if (!(nu > 0) || !(sigsq > 0)) return -std::numeric_limits<double>::infinity();
+  DeviceData &dev(device_data());
+  double ans = 0;
+  dev.check(boomgpu_student_loglike(dev.ctx(), nullptr, std::sqrt(sigsq), nu, &ans));
+  return ans;
+}
+double TRegressionModel::log_likelihood_derivs(const Vector &, Vector *, SpdMatrix *) {
+  report_error("derivatives of the TRegressionModel log likelihood are not provided (TRegression.cpp:118-121)");
+}
+
+// ---- TRegressionSampler -----------------------------------------------------------------------
+TRegressionSampler::TRegressionSampler(TRegressionModel *model, const std::shared_ptr<MvnBase> &coefficient_prior,
+                                       const std::shared_ptr<GammaModelBase> &siginv_prior,
+                                       const std::shared_ptr<DoubleModel> &nu_prior, RNG &seeding_rng)
+    : PosteriorSampler(seeding_rng), model_(model), coefficient_prior_(coefficient_prior), siginv_prior_(siginv_prior),
+      nu_prior_(nu_prior), suf_(model ? model->xdim() : 0), sigsq_sampler_(siginv_prior),
+      nu_observed_([this](double nu) {
+                     // TRegressionLogPosterior (.cpp:31-49); the residuals of the current beta are computed once per draw
+                     double ans = nu_prior_->logp(nu);
+                     if (!(ans > -std::numeric_limits<double>::infinity())) return ans;
+                     if (!residuals_current_) {
+                       residuals_current_ = true;
+                       return ans + model_->log_likelihood(model_->Beta(), model_->sigsq(), nu);
+                     }
+                     return ans + model_->log_likelihood_same_beta(model_->sigsq(), nu);
+                   }, false, 1.0, &rng()),
+      nu_complete_([this](double nu) {
+                     // TRegressionCompleteDataLogPosterior (.cpp:51-72) over ScaledChisqModel::Loglike (ScaledChisqModel.cpp:52-82)
+                     if (nu <= 0.0) return -std::numeric_limits<double>::infinity();
+                     double ans = nu_prior_->logp(nu);
+                     if (!(ans > -std::numeric_limits<double>::infinity())) return ans;
+                     const double nu2 = nu / 2.0;
+                     return ans + suf_.n() * (nu2 * std::log(nu2) - std::lgamma(nu2)) + (nu2 - 1) * suf_.sumlogw() - nu2 * suf_.sumw();
+                   }, false, 1.0, &rng()) {
+  if (!model) report_error("TRegressionSampler: null model");
+  if (!coefficient_prior || coefficient_prior->dim() != model->xdim()) report_error("Prior does not match model dimension.");
+  if (!siginv_prior || !nu_prior) report_error("TRegressionSampler: null prior");
+  nu_observed_.set_lower_limit(0.0);
+  nu_complete_.set_lower_limit(0.0);
+  device_seed_ = seed_rng(rng());
+}
+void TRegressionSampler::on_seed() { device_seed_ = seed_rng(rng()); iteration_ = 0; }
+
+void TRegressionSampler::draw() {
+  impute_latent_data();
+  draw_beta_full_conditional();
+  draw_sigsq_full_conditional();
+  draw_nu_given_observed_data();
+}
+double TRegressionSampler::logpri() const {
+  return nu_prior_->logp(model_->nu()) + sigsq_sampler_.log_prior(model_->sigsq()) + coefficient_prior_->logp(model_->Beta());
+}
+void TRegressionSampler::impute_latent_data() {
+  if (latent_data_fixed_) return;
+  const uint64_t seed = device_seed_, it = iteration_++;
+  const Vector &beta(model_->Beta());
+  const double sigma = model_->sigma(), nu = model_->nu();
+  run_device_step(
+      *model_, suf_, packed_,
+      [&](boomgpu_ctx *ctx, double *suf_dev) { return boomgpu_student_step_device(ctx, beta.data(), sigma, nu, seed, it, suf_dev); },
+      [&](boomgpu_ctx *ctx, double *xtx, double *xty, double *scalars) {
+        return boomgpu_student_step(ctx, beta.data(), sigma, nu, seed, it, xtx, xty, scalars);
+      });
+}
+void TRegressionSampler::draw_beta_full_conditional() {   // draw_beta_full_conditional_impl, .cpp:74-85
+  const int p = model_->xdim();
+  const double sigsq = model_->sigsq();
+  SpdMatrix precision(coefficient_prior_->siginv());
+  Vector scaled_mean(p, 0.0);
+  for (int i = 0; i < p; ++i) {
+    double s = 0;
+    for (int j = 0; j < p; ++j) {
+      precision.a[(size_t)i * p + j] += suf_.xtx()(i, j) / sigsq;
+      s += coefficient_prior_->siginv()(i, j) * coefficient_prior_->mu()[j];
+    }
+    scaled_mean[i] = s + suf_.xty()[i] / sigsq;
+  }
+  model_->set_Beta(rmvn_suf_mt(rng(), precision, scaled_mean));
+  residuals_current_ = false;
+}
+void TRegressionSampler::draw_sigsq_full_conditional() {   // .cpp:165-171; SSE = y'Wy - 2 b'X'Wy + b'X'WXb (WeightedRegressionModel.cpp:89-95)
+  const int p = model_->xdim();
+  const Vector &b(model_->Beta());
+  double bxy = 0, bxxb = 0;
+  for (int i = 0; i < p; ++i) {
+    if (b[i] == 0.0) continue;
+    bxy += b[i] * suf_.xty()[i];
+    double s = 0;
+    for (int j = 0; j < p; ++j) s += suf_.xtx()(i, j) * b[j];
+    bxxb += b[i] * s;
+  }
+  const double sse = suf_.yty() - 2 * bxy + bxxb;
+  model_->set_sigsq(sigsq_sampler_.draw(rng(), suf_.n(), sse));
+}
+void TRegressionSampler::draw_nu_given_complete_data() { model_->set_nu(nu_complete_.draw(model_->nu())); }
+void TRegressionSampler::draw_nu_given_observed_data() {
+  residuals_current_ = false;   // beta may have been set from outside since the last draw
+  model_->set_nu(nu_observed_.draw(model_->nu()));
+}
+
 }  // namespace BOOM_B200

@@ -23,6 +23,7 @@
 // boom_b200/boom_adapter derives the same samplers from BOOM::PosteriorSampler for a true drop-in.
 #pragma once
 
+#include <cmath>
 #include <cstdint>
 #include <functional>
 #include <memory>
@@ -665,6 +666,175 @@ class BinomialProbitSpikeSlabSampler : public PosteriorSampler {
   WeightedRegSuf suf_;
   int clt_threshold_;
   uint64_t device_seed_, iteration_ = 0, xtx_data_version_ = 0;
+  Vector packed_;
+};
+
+// ---- the Student-t sibling -----------------------------------------------------
+// Models/DoubleModel.hpp: a prior on a scalar is read through logp().
+class DoubleModel {
+ public:
+  virtual ~DoubleModel() {}
+  virtual double logp(double x) const = 0;
+};
+// Models/UniformModel.hpp:71: flat on [lo, hi]
+class UniformModel : public DoubleModel {
+ public:
+  explicit UniformModel(double lo = 0, double hi = 1);
+  double logp(double x) const override;
+  double lo() const { return lo_; }
+  double hi() const { return hi_; }
+
+ private:
+  double lo_, hi_;
+};
+// Models/GammaModel.hpp: GammaModelBase is read through alpha() (shape) and beta() (rate); logp = dgamma(x, a, b, log)
+class GammaModelBase : public DoubleModel {
+ public:
+  virtual double alpha() const = 0;
+  virtual double beta() const = 0;
+  double logp(double x) const override;
+};
+class GammaModel : public GammaModelBase {
+ public:
+  GammaModel(double a, double b);
+  double alpha() const override { return a_; }
+  double beta() const override { return b_; }
+
+ private:
+  double a_, b_;
+};
+// Models/ChisqModel.hpp: the prior "df observations with standard deviation sigma_estimate" on 1 / sigma^2
+class ChisqModel : public GammaModel {
+ public:
+  ChisqModel(double df, double sigma_estimate) : GammaModel(df / 2.0, df * sigma_estimate * sigma_estimate / 2.0) {}
+};
+double rgamma_mt(RNG &rng, double a, double b);                   // shape a, RATE b (distributions/Rmath_dist.cpp:72-74)
+double rtrun_gamma_mt(RNG &rng, double a, double b, double cut);  // Gamma(a, b) given x > cut (distributions/trun_gamma.cpp:73-106)
+double rexp_mt(RNG &rng, double lambda);
+
+// Models/PosteriorSamplers/GenericGaussianVarianceSampler.{hpp,cpp}: sigma^2 | data_df, data_ss under a Gamma prior on
+// 1 / sigma^2, optionally truncated to sigma <= sigma_max.
+class GenericGaussianVarianceSampler {
+ public:
+  explicit GenericGaussianVarianceSampler(const std::shared_ptr<GammaModelBase> &prior, double sigma_max = 1.0 / 0.0);
+  void set_sigma_max(double sigma_max);
+  double sigma_max() const { return sigma_max_; }
+  double draw(RNG &rng, double data_df, double data_ss, double prior_sigma_guess_scale_factor = 1.0) const;   // .cpp:44-63
+  double posterior_mode(double data_df, double data_ss) const;
+  double log_prior(double sigsq) const;                                                                    // .cpp:82-92
+
+ private:
+  std::shared_ptr<GammaModelBase> prior_;
+  double sigma_max_;
+};
+
+// Samplers/ScalarSliceSampler.{hpp,cpp}: Neal's (2003) slice sampler for a scalar log density, with optional finite
+// limits; stepping out by doubling (and, for a possibly multimodal target, the randomised doubling of .cpp:199-236).
+class ScalarSliceSampler {
+ public:
+  typedef std::function<double(double)> Fun;
+  ScalarSliceSampler(const Fun &logf, bool unimodal = false, double suggested_dx = 1.0, RNG *rng = nullptr);
+  void set_rng(RNG *rng) { rng_ = rng; }
+  void set_suggested_dx(double dx) { suggested_dx_ = dx; }
+  void set_min_dx(double dx) { min_dx_ = dx; }
+  void estimate_dx(bool yn) { estimate_dx_ = yn; }
+  void set_limits(double lo, double hi) { set_lower_limit(lo); set_upper_limit(hi); }
+  void set_lower_limit(double lo);
+  void set_upper_limit(double hi);
+  void unset_limits() { lo_set_ = hi_set_ = false; }
+  double draw(double x);
+  double logp(double x) const { return logf_(x); }
+  int64_t function_evaluations() const { return evals_; }
+
+ private:
+  double f(double x) { ++evals_; return logf_(x); }
+  void find_limits(double x);
+  bool find_limits_unbounded(double x);
+  bool find_upper_limit(double x);
+  bool find_lower_limit(double x);
+  void double_hi(double x);
+  void double_lo(double x);
+  void contract(double x, double x_cand, double logp);
+  [[noreturn]] void handle_error(const std::string &msg, double x) const;
+  Fun logf_;
+  RNG *rng_;
+  double suggested_dx_, min_dx_ = -1;
+  double lo_ = 0, hi_ = 0, lower_bound_ = 0, upper_bound_ = 0, logplo_ = 0, logphi_ = 0, logp_slice_ = 0;
+  bool lo_set_ = false, hi_set_ = false, unimodal_, estimate_dx_ = true;
+  int64_t evals_ = 0;
+};
+
+// TRegressionModel (Models/Glm/TRegression.{hpp,cpp}): y_i = x_i'beta + sigma t_nu.  Parameters beta, sigsq, nu as in the
+// reference's ParamPolicy_3 (defaults sigsq = 1, nu = 30: TRegression.cpp:33-35); the rows live in HBM.
+class TRegressionModel : public GlmModelBase {
+ public:
+  explicit TRegressionModel(int xdim) : GlmModelBase(xdim) {}
+  TRegressionModel(int64_t n, int p, const double *X, const double *y);   // TRegression.cpp:41-51: X row major n x p
+  void add_data(double y, const Vector &x);                              // model->add_data(new RegressionData(y, x))
+  void adopt_device_data(int64_t n, const double *dX, int64_t ldx, const double *dy);
+  void borrow_host_data(int64_t n, const double *X, int64_t ldx, const double *y, std::shared_ptr<void> keepalive);
+  int64_t nobs() const { return (adopted_ || borrowed_) ? adopted_n_ : (int64_t)y_.size(); }
+  double sigsq() const { return sigsq_; }
+  double sigma() const { return std::sqrt(sigsq_); }
+  void set_sigsq(double s2);
+  double nu() const { return nu_; }
+  void set_nu(double nu);
+  // TRegression.cpp:74-86 on the device (one pass over X; the residuals stay in HBM) ...
+  double log_likelihood(const Vector &beta, double sigsq, double nu);
+  double log_likelihood() { return log_likelihood(Beta(), sigsq_, nu_); }
+  // ... and at another (sigsq, nu) for the SAME beta as the previous call: 8 n bytes instead of a pass over X
+  double log_likelihood_same_beta(double sigsq, double nu);
+  double log_likelihood_derivs(const Vector &beta, Vector *g, SpdMatrix *h) override;   // not provided (TRegression.cpp:118-121)
+
+ protected:
+  void upload(DeviceData &dev) override;
+
+ private:
+  double sigsq_ = 1.0, nu_ = 30.0;
+  Vector y_;
+  const double *dX_ = nullptr, *dy_ = nullptr;
+  int64_t dldx_ = 0;
+};
+
+// TRegressionSampler (Models/Glm/PosteriorSamplers/TRegressionSampler.{hpp,cpp}): the scale-mixture Gibbs sampler.
+//   impute_latent_data     w_i ~ Gamma((nu+1)/2, (nu + delta_i^2)/2) and WeightedRegSuf::add_data(x_i, y_i, w_i): ONE device step
+//   draw_beta_full_conditional    N((Ominv + X'WX/sigsq)^-1 (Ominv b + X'Wy/sigsq), .)  on the host (.cpp:153-160)
+//   draw_sigsq_full_conditional   GenericGaussianVarianceSampler on n and the weighted SSE (.cpp:165-171)
+//   draw_nu_given_observed_data   slice sampler on nu over the Student log likelihood: the device keeps y - X beta and
+//                                 evaluates each candidate nu from 8 n bytes (.cpp:178-181)
+class TRegressionSampler : public PosteriorSampler {
+ public:
+  TRegressionSampler(TRegressionModel *model, const std::shared_ptr<MvnBase> &coefficient_prior,
+                     const std::shared_ptr<GammaModelBase> &siginv_prior, const std::shared_ptr<DoubleModel> &nu_prior,
+                     RNG &seeding_rng = GlobalRng::rng);
+  void draw() override;                 // .cpp:114-119
+  double logpri() const override;       // .cpp:121-126
+  void impute_latent_data();            // .cpp:128-143
+  void draw_beta_full_conditional();
+  void draw_sigsq_full_conditional();
+  void draw_nu_given_complete_data();   // .cpp:173-176: from the weights' GammaSuf alone (ScaledChisqModel.cpp:52-82)
+  void draw_nu_given_observed_data();
+  void set_sigma_upper_limit(double max_sigma) { sigsq_sampler_.set_sigma_max(max_sigma); }
+  const WeightedRegSuf &complete_data_sufficient_statistics() const { return suf_; }
+  void fix_latent_data(bool fixed = true) { latent_data_fixed_ = fixed; }
+  void clear_complete_data_sufficient_statistics() { suf_.clear(); }
+  void update_complete_data_sufficient_statistics(double y, const Vector &x, double weight) { suf_.add_data(x, y, weight); }
+  uint64_t iteration() const { return iteration_; }
+  int64_t likelihood_evaluations() const { return nu_observed_.function_evaluations(); }
+
+ protected:
+  void on_seed() override;
+
+ private:
+  TRegressionModel *model_;
+  std::shared_ptr<MvnBase> coefficient_prior_;
+  std::shared_ptr<GammaModelBase> siginv_prior_;
+  std::shared_ptr<DoubleModel> nu_prior_;
+  WeightedRegSuf suf_;                  // its sumw / sumlogw / n are the weight model's GammaSuf as well
+  GenericGaussianVarianceSampler sigsq_sampler_;
+  ScalarSliceSampler nu_observed_, nu_complete_;
+  bool latent_data_fixed_ = false, residuals_current_ = false;
+  uint64_t device_seed_, iteration_ = 0;
   Vector packed_;
 };
 

@@ -36,7 +36,7 @@ NpD from_vec(const Vector &v) {
 }
 
 template <class M>
-void bind_model_common(py::class_<M, std::shared_ptr<M>> &c) {
+void bind_model_core(py::class_<M, std::shared_ptr<M>> &c) {
   c.def_property_readonly("xdim", &M::xdim)
       .def_property_readonly("sample_size", [](const M &m) { return m.nobs(); })
       .def_property("Beta", [](const M &m) { return from_vec(m.Beta()); }, [](M &m, const NpD &b) { m.set_Beta(to_vec(b)); })
@@ -78,8 +78,13 @@ void bind_model_common(py::class_<M, std::shared_ptr<M>> &c) {
         py::dict out;
         for (int c = 0; c < 5; ++c) out[names[c]] = py::make_tuple(ms[c], cnt[c]);
         return out;
-      }, py::arg("reset") = false)
-      .def("log_likelihood_derivs", [](M &m, const NpD &b) {
+      }, py::arg("reset") = false);
+}
+
+template <class M>
+void bind_model_common(py::class_<M, std::shared_ptr<M>> &c) {
+  bind_model_core(c);
+  c.def("log_likelihood_derivs", [](M &m, const NpD &b) {
         Vector g; SpdMatrix h;
         double ll = m.log_likelihood_derivs(to_vec(b), &g, &h);
         return py::make_tuple(ll, from_vec(g), from_spd(h));
@@ -243,6 +248,80 @@ PYBIND11_MODULE(_host, m) {
       .def("complete_data_sufficient_statistics", &BinomialProbitSpikeSlabSampler::complete_data_sufficient_statistics)
       .def("allow_model_selection", &BinomialProbitSpikeSlabSampler::allow_model_selection)
       .def("limit_model_selection", &BinomialProbitSpikeSlabSampler::limit_model_selection);
+
+  // ---- the Student-t sibling
+  py::class_<DoubleModel, std::shared_ptr<DoubleModel>>(m, "DoubleModel").def("logp", &DoubleModel::logp);
+  py::class_<UniformModel, DoubleModel, std::shared_ptr<UniformModel>>(m, "UniformModel")
+      .def(py::init<double, double>(), py::arg("lo") = 0.0, py::arg("hi") = 1.0);
+  py::class_<GammaModelBase, DoubleModel, std::shared_ptr<GammaModelBase>>(m, "GammaModelBase")
+      .def_property_readonly("alpha", &GammaModelBase::alpha).def_property_readonly("beta", &GammaModelBase::beta);
+  py::class_<GammaModel, GammaModelBase, std::shared_ptr<GammaModel>>(m, "GammaModel").def(py::init<double, double>(), py::arg("a"), py::arg("b"));
+  py::class_<ChisqModel, GammaModel, std::shared_ptr<ChisqModel>>(m, "ChisqModel")
+      .def(py::init<double, double>(), py::arg("df"), py::arg("sigma_estimate"));
+  m.def("rgamma_mt", [](RNG &rng, double a, double b) { return rgamma_mt(rng, a, b); });
+  m.def("rtrun_gamma_mt", [](RNG &rng, double a, double b, double cut) { return rtrun_gamma_mt(rng, a, b, cut); });
+  // test hook: n successive draws of ScalarSliceSampler on a Python log density
+  m.def("slice_sample", [](py::function logf, double x0, int n, double lo, double hi, bool unimodal, RNG &rng) {
+    ScalarSliceSampler s([&logf](double x) { return logf(x).cast<double>(); }, unimodal, 1.0, &rng);
+    s.set_lower_limit(lo); s.set_upper_limit(hi);
+    Vector out((size_t)n);
+    double x = x0;
+    for (int i = 0; i < n; ++i) { x = s.draw(x); out[i] = x; }
+    return from_vec(out);
+  }, py::arg("logf"), py::arg("x0"), py::arg("n"), py::arg("lo") = -1.0 / 0.0, py::arg("hi") = 1.0 / 0.0, py::arg("unimodal") = false,
+     py::arg("rng") = std::ref(GlobalRng::rng));
+  m.def("draw_sigsq", [](const std::shared_ptr<GammaModelBase> &prior, double sigma_max, double df, double ss, int n, RNG &rng) {
+    GenericGaussianVarianceSampler s(prior, sigma_max);
+    Vector out((size_t)n);
+    for (int i = 0; i < n; ++i) out[i] = s.draw(rng, df, ss);
+    return from_vec(out);
+  });
+
+  py::class_<TRegressionModel, std::shared_ptr<TRegressionModel>> trm(m, "TRegressionModel");
+  trm.def(py::init<int>(), py::arg("xdim"))
+      .def(py::init([](const NpD &X, const NpD &y) {
+        if (X.ndim() != 2 || y.size() != X.shape(0)) report_error("TRegressionModel(X, y): shape mismatch");
+        return std::make_shared<TRegressionModel>((int64_t)X.shape(0), (int)X.shape(1), X.data(), y.data());
+      }))
+      .def("add_data", [](TRegressionModel &mo, double y, const NpD &x) { mo.add_data(y, to_vec(x)); })
+      .def("borrow_host_data", [](TRegressionModel &mo, NpD X, NpD y) {
+        if (X.ndim() != 2 || (int)X.shape(1) != mo.xdim() || y.size() != X.shape(0)) report_error("borrow_host_data(X, y): shape mismatch");
+        auto keep = std::make_shared<std::tuple<NpD, NpD>>(X, y);
+        mo.borrow_host_data((int64_t)X.shape(0), X.data(), (int64_t)X.shape(1), y.data(), std::shared_ptr<void>(keep, keep.get()));
+      })
+      .def("adopt_device_data", [](TRegressionModel &mo, int64_t n, uintptr_t dX, int64_t ldx, uintptr_t dy) {
+        mo.adopt_device_data(n, reinterpret_cast<const double *>(dX), ldx, reinterpret_cast<const double *>(dy));
+      })
+      .def_property("sigsq", &TRegressionModel::sigsq, &TRegressionModel::set_sigsq)
+      .def_property_readonly("sigma", &TRegressionModel::sigma)
+      .def_property("nu", &TRegressionModel::nu, &TRegressionModel::set_nu)
+      .def("set_sigsq", &TRegressionModel::set_sigsq)
+      .def("set_nu", &TRegressionModel::set_nu)
+      .def("log_likelihood", [](TRegressionModel &mo) { return mo.log_likelihood(); })
+      .def("log_likelihood", [](TRegressionModel &mo, const NpD &b, double sigsq, double nu) { return mo.log_likelihood(to_vec(b), sigsq, nu); })
+      .def("log_likelihood_same_beta", &TRegressionModel::log_likelihood_same_beta);
+  bind_model_core(trm);
+
+  py::class_<TRegressionSampler, PosteriorSampler, std::shared_ptr<TRegressionSampler>>(m, "TRegressionSampler")
+      .def(py::init([](TRegressionModel *model, const std::shared_ptr<MvnBase> &coefficient_prior,
+                       const std::shared_ptr<GammaModelBase> &siginv_prior, const std::shared_ptr<DoubleModel> &nu_prior, RNG &rng) {
+             return std::make_shared<TRegressionSampler>(model, coefficient_prior, siginv_prior, nu_prior, rng);
+           }),
+           py::arg("model"), py::arg("coefficient_prior"), py::arg("siginv_prior"), py::arg("nu_prior"),
+           py::arg("seeding_rng") = std::ref(GlobalRng::rng), py::keep_alive<1, 2>())
+      .def("impute_latent_data", [](TRegressionSampler &s) { py::gil_scoped_release rel; s.impute_latent_data(); })
+      .def("draw_beta_full_conditional", &TRegressionSampler::draw_beta_full_conditional)
+      .def("draw_sigsq_full_conditional", &TRegressionSampler::draw_sigsq_full_conditional)
+      .def("draw_nu_given_complete_data", &TRegressionSampler::draw_nu_given_complete_data)
+      .def("draw_nu_given_observed_data", [](TRegressionSampler &s) { py::gil_scoped_release rel; s.draw_nu_given_observed_data(); })
+      .def("set_sigma_upper_limit", &TRegressionSampler::set_sigma_upper_limit)
+      .def("fix_latent_data", &TRegressionSampler::fix_latent_data, py::arg("fixed") = true)
+      .def("clear_complete_data_sufficient_statistics", &TRegressionSampler::clear_complete_data_sufficient_statistics)
+      .def("update_complete_data_sufficient_statistics", [](TRegressionSampler &s, double y, const NpD &x, double w) {
+        s.update_complete_data_sufficient_statistics(y, to_vec(x), w); })
+      .def_property_readonly("complete_data_sufficient_statistics", &TRegressionSampler::complete_data_sufficient_statistics,
+                             py::return_value_policy::reference_internal)
+      .def_property_readonly("likelihood_evaluations", &TRegressionSampler::likelihood_evaluations);
 
   py::class_<PoissonRegressionAuxMixSampler, PosteriorSampler, std::shared_ptr<PoissonRegressionAuxMixSampler>>(
       m, "PoissonRegressionAuxMixSampler")

@@ -97,7 +97,7 @@ int boomgpu_upload_poisson(boomgpu_ctx *ctx, int64_t n, int p, const double *X, 
 /* The same upload a chunk of rows at a time, for callers whose rows are not one contiguous host matrix (BOOM: one heap
  * object per observation, IID_DataPolicy.hpp:57-58): begin allocates, rows copies rows [row0, row0 + nrows) and returns when
  * the caller's chunk buffers may be re-used, end makes the data usable.  y: nrows doubles (binomial) or int64 (poisson);
- * aux: trials / exposure. */
+ * aux: trials / exposure.  poisson = 2: plain regression rows for the Student-t sibling (y doubles, aux ignored / NULL). */
 int boomgpu_upload_begin(boomgpu_ctx *ctx, int poisson, int64_t n, int p);
 int boomgpu_upload_rows(boomgpu_ctx *ctx, int64_t row0, int64_t nrows, const double *X, int64_t ldx, const void *y, const double *aux);
 int boomgpu_upload_end(boomgpu_ctx *ctx);
@@ -139,6 +139,23 @@ int boomgpu_probit_step(boomgpu_ctx *ctx, const double *beta, int clt_threshold,
                         double *xtx, double *xtz, int64_t *sample_size);
 int boomgpu_probit_step_device(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
                                double *suf_dev, int xtz_only);
+
+/* The Student-t sibling -- TRegressionSampler::impute_latent_data (Models/Glm/PosteriorSamplers/TRegressionSampler.cpp:128-143)
+ * over TDataImputer::impute (TDataImputer.cpp:25-29), on plain regression rows (boomgpu_upload_regression / _adopt_regression,
+ * or boomgpu_upload_begin with kind 2): w_i ~ Gamma((nu + 1)/2, rate (nu + ((y_i - x_i'beta)/sigma)^2)/2), then
+ * WeightedRegSuf::add_data(x_i, y_i, w_i) (WeightedRegressionModel.cpp:161-169): xtwx = X'WX, xtwy = X'Wy,
+ * scalars = {n, y'Wy, sum w, sum log w} (the last two are also the GammaSuf of the sampler's weight model). */
+int boomgpu_upload_regression(boomgpu_ctx *ctx, int64_t n, int p, const double *X, int64_t ldx, const double *y);
+int boomgpu_adopt_regression(boomgpu_ctx *ctx, int64_t n, int p, const double *dX, int64_t ldx, const double *dy);
+int boomgpu_student_step(boomgpu_ctx *ctx, const double *beta, double sigma, double nu, uint64_t seed, uint64_t iteration,
+                         double *xtwx, double *xtwy, double scalars[4]);
+int boomgpu_student_step_device(boomgpu_ctx *ctx, const double *beta, double sigma, double nu, uint64_t seed, uint64_t iteration,
+                                double *suf_dev);
+/* TRegressionModel::log_likelihood(beta, sigsq, nu) (Models/Glm/TRegression.cpp:74-86) = sum_i log dstudent(y_i; x_i'beta,
+ * sigma, nu), all-reduced over the shards.  beta != NULL: one pass over X, the residuals stay on the device; beta == NULL:
+ * the residuals of the previous call are reused (8 n bytes per evaluation): what the slice sampler on nu
+ * (TRegressionSampler.cpp:173-176) needs, several evaluations per draw with beta and sigma fixed. */
+int boomgpu_student_loglike(boomgpu_ctx *ctx, const double *beta, double sigma, double nu, double *loglike);
 
 /* ACTIVE-SET form of the step (p > 64).  A sweep over the inclusion indicators reads of X'WX only the columns of the
  * variables in the model and the diagonal (log_model_prob selects sub-blocks, BinomialLogitSpikeSlabSampler.cpp:88-117), so the
@@ -205,6 +222,9 @@ int boomgpu_poisson_draw(boomgpu_ctx *ctx, const double *beta, uint64_t seed, ui
 /* per-row sums of the latent probit normals (host array of length n) */
 int boomgpu_probit_draw(boomgpu_ctx *ctx, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
                         double *sum_z_out);
+/* the latent weights of the Student-t sibling, one per row (host array of length n) */
+int boomgpu_student_draw(boomgpu_ctx *ctx, const double *beta, double sigma, double nu, uint64_t seed, uint64_t iteration,
+                         double *weight_out);
 int boomgpu_binomial_loglike(boomgpu_ctx *ctx, const double *beta, double *loglike);
 int boomgpu_poisson_loglike(boomgpu_ctx *ctx, const double *beta, double *loglike);
 /* log likelihood with gradient (p, may be NULL) and Hessian (p x p, symmetric, may be NULL) in one pass over the rows:

@@ -122,6 +122,17 @@ int bo_probit_step(int64_t n, int p, const double *X, int64_t ldx, const double 
                    int clt_threshold, uint64_t seed, uint64_t iteration, uint64_t row_offset, double *xtx, double *xtz,
                    double *draws);
 
+/* ---- Student-t sibling (TRegressionSampler) ------------------------------------------- */
+int bo_rgamma(double shape, double rate, uint64_t seed, uint64_t iteration, uint64_t row, double *out);
+int bo_student_impute(double residual, double sigma, double nu, uint64_t seed, uint64_t iteration, uint64_t row, double *weight);
+int bo_student_step(int64_t n, int p, const double *X, int64_t ldx, const double *y, const double *beta, double sigma, double nu,
+                    uint64_t seed, uint64_t iteration, uint64_t row_offset, double *xtwx, double *xtwy, double scalars[4],
+                    double *weights);
+double bo_student_loglike(int64_t n, int p, const double *X, int64_t ldx, const double *y, const double *beta, double sigma,
+                          double nu);
+void bo_synth_student_y(int64_t n, int p, const double *X, int64_t ldx, const double *beta, double sigma, double nu,
+                        uint64_t seed, uint64_t row_offset, double *y);
+
 /* BinomialLogitModel::log_likelihood (value only, log_alpha = 0) */
 double bo_dbinom_log(double x, double n, double p);
 double bo_binomial_logit_loglike(int64_t n, int p, const double *X, int64_t ldx, const double *y,

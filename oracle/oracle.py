@@ -263,6 +263,44 @@ def probit_step(X, y, ntrials, beta, clt_threshold, seed, iteration, row_offset=
     return xtx.T.copy(), xtz, draws
 
 
+def rgamma(shape, rate, seed, iteration, row):
+    """Gamma(shape, rate) from the row's Philox blocks (Marsaglia-Tsang): the draw behind TDataImputer::impute."""
+    out = C.c_double(0.0)
+    rc = lib().bo_rgamma(C.c_double(shape), C.c_double(rate), C.c_uint64(seed), C.c_uint64(iteration), C.c_uint64(row), C.byref(out))
+    if rc:
+        raise ValueError("bo_rgamma rc=%d" % rc)
+    return out.value
+
+
+def student_step(X, y, beta, sigma, nu, seed, iteration, row_offset=0):
+    """(xtwx, xtwy, scalars[n, y'Wy, sum w, sum log w], weights) of TRegressionSampler::impute_latent_data on the shared stream."""
+    X, y, beta = _f64(X), _f64(y), _f64(beta)
+    n, p = X.shape
+    xtwx, xtwy, sc, w = np.zeros((p, p)), np.zeros(p), np.zeros(4), np.zeros(n)
+    rc = lib().bo_student_step(C.c_int64(n), C.c_int(p), _dp(X), C.c_int64(p), _dp(y), _dp(beta), C.c_double(sigma), C.c_double(nu),
+                               C.c_uint64(seed), C.c_uint64(iteration), C.c_uint64(row_offset), _dp(xtwx), _dp(xtwy), _dp(sc), _dp(w))
+    if rc:
+        raise ValueError("bo_student_step rc=%d" % rc)
+    return xtwx.T.copy(), xtwy, sc, w
+
+
+def student_loglike(X, y, beta, sigma, nu):
+    X, y, beta = _f64(X), _f64(y), _f64(beta)
+    n, p = X.shape
+    lib().bo_student_loglike.restype = C.c_double
+    return lib().bo_student_loglike(C.c_int64(n), C.c_int(p), _dp(X), C.c_int64(p), _dp(y), _dp(beta), C.c_double(sigma), C.c_double(nu))
+
+
+def synth_student(n, p, nonzero, seed, sigma=1.5, nu=4.0, intercept=0.5, row_offset=0):
+    """X, y = X beta + sigma t_nu, beta: the synthetic Student-t regression every arm shares."""
+    X = synth_x(n, p, seed, 1.0, row_offset)
+    beta = synth_beta(p, nonzero, intercept)
+    y = np.zeros(n)
+    lib().bo_synth_student_y(C.c_int64(n), C.c_int(p), _dp(X), C.c_int64(p), _dp(beta), C.c_double(sigma), C.c_double(nu),
+                             C.c_uint64(seed), C.c_uint64(row_offset), _dp(y))
+    return X, y, beta
+
+
 def binomial_logit_loglike(X, y, ntrials, beta):
     X, y, ntrials, beta = _f64(X), _f64(y), _f64(ntrials), _f64(beta)
     n, p = X.shape

@@ -31,7 +31,12 @@
 #include "Models/Glm/PosteriorSamplers/PoissonDataImputer.hpp"
 #include "Models/Glm/PosteriorSamplers/PoissonRegressionAuxMixSampler.hpp"
 #include "Models/Glm/PosteriorSamplers/poisson_mixture_approximation_table.hpp"
+#include "Models/ChisqModel.hpp"
+#include "Models/Glm/PosteriorSamplers/TDataImputer.hpp"
+#include "Models/Glm/PosteriorSamplers/TRegressionSampler.hpp"
+#include "Models/Glm/TRegression.hpp"
 #include "Models/Glm/VariableSelectionPrior.hpp"
+#include "Models/UniformModel.hpp"
 #include "Models/Glm/WeightedRegressionModel.hpp"
 #include "Models/MvnModel.hpp"
 #include "distributions.hpp"
@@ -531,6 +536,81 @@ void golden_chains(const std::string &dir) {
 }
 
 // ------------------------------------------------------------------------------------
+// The Student-t sibling: the reference's TDataImputer draws, TRegressionModel::log_likelihood and a TRegressionSampler chain.
+void golden_student(const std::string &dir) {
+  Json j;
+  {
+    RNG rng(20261017);
+    TDataImputer imputer;
+    struct C { double residual, sigma, nu; };
+    std::vector<std::string> rows;
+    const int N = 200000;
+    for (C c : {C{0.0, 1.0, 4.0}, C{2.5, 1.5, 4.0}, C{-7.0, 0.8, 2.0}, C{0.3, 2.0, 30.0}, C{1.0, 1.0, 0.6}, C{40.0, 1.0, 1.0}}) {
+      std::vector<double> w; w.reserve(N);
+      double s1 = 0, s2 = 0, sl = 0;
+      for (int i = 0; i < N; ++i) {
+        double v = imputer.impute(rng, c.residual, c.sigma, c.nu);
+        w.push_back(v); s1 += v; s2 += v * v; sl += std::log(v);
+      }
+      std::string r = row_json({{"residual", c.residual}, {"sigma", c.sigma}, {"nu", c.nu}, {"N", (double)N}, {"w_mean", s1 / N},
+                                {"w_var", s2 / N - (s1 / N) * (s1 / N)}, {"logw_mean", sl / N}});
+      r.pop_back();
+      r += ", \"w_quantiles\": " + quantiles_json(w) + "}";
+      rows.push_back(r);
+    }
+    j.raw("draw_stats", list_json(rows));
+  }
+  const double sigma_true = 1.5, nu_true = 4.0;
+  auto make_model = [&](int64_t n, int p, int nonzero, uint64_t seed, std::vector<double> *beta_true) {
+    std::vector<double> X((size_t)n * p), y(n), beta(p);
+    bo_synth_x(n, p, seed, 1.0, 0, X.data(), p);
+    bo_synth_beta(p, nonzero, 0.5, beta.data());
+    bo_synth_student_y(n, p, X.data(), p, beta.data(), sigma_true, nu_true, seed, 0, y.data());
+    NEW(TRegressionModel, model)(p);
+    Vector x(p);
+    for (int64_t i = 0; i < n; ++i) {
+      for (int k = 0; k < p; ++k) x[k] = X[i * p + k];
+      NEW(RegressionData, dp)(y[i], x);
+      model->add_data(dp);
+    }
+    if (beta_true) *beta_true = beta;
+    return model;
+  };
+  {
+    // TRegressionModel::log_likelihood(beta, sigsq, nu) on synth_student(n = 500, p = 7, nonzero = 3, seed = 99)
+    std::vector<double> bt;
+    Ptr<TRegressionModel> model = make_model(500, 7, 3, 99, &bt);
+    Vector beta(bt.size());
+    for (size_t k = 0; k < bt.size(); ++k) beta[k] = bt[k] * 0.9 + 0.05;
+    std::vector<std::string> rows;
+    for (double sigma : {0.7, 1.5, 3.0}) for (double nu : {0.8, 4.0, 30.0, 200.0})
+      rows.push_back(row_json({{"sigma", sigma}, {"nu", nu}, {"loglike", model->log_likelihood(beta, sigma * sigma, nu)}}));
+    j.raw("loglike", "{\"n\": 500, \"p\": 7, \"nonzero\": 3, \"seed\": 99, \"beta_scale\": 0.9, \"beta_shift\": 0.05, \"rows\": " + list_json(rows) + "}");
+  }
+  {
+    const int n = 3000, p = 5, iters = 8000, burn = 1000;
+    std::vector<double> bt;
+    Ptr<TRegressionModel> model = make_model(n, p, 3, 777, &bt);
+    NEW(MvnModel, prior)(Vector(p, 0.0), SpdMatrix(p, 100.0));
+    NEW(ChisqModel, siginv_prior)(1.0, 1.0);
+    NEW(UniformModel, nu_prior)(0.5, 60.0);
+    GlobalRng::rng.seed(8675309);
+    NEW(TRegressionSampler, sampler)(model.get(), prior, siginv_prior, nu_prior);
+    model->set_method(sampler);
+    Moments mo(p), sn(2);
+    for (int it = 0; it < iters; ++it) {
+      model->sample_posterior();
+      if (it >= burn) { mo.add(model->Beta()); Vector v(2); v[0] = model->sigma(); v[1] = model->nu(); sn.add(v); }
+    }
+    j.raw("chain", "{\"n\": 3000, \"p\": 5, \"nonzero\": 3, \"seed\": 777, \"sigma_true\": 1.5, \"nu_true\": 4.0, \"iters\": 8000, \"burn\": 1000, "
+                   "\"beta_prior_variance\": 100.0, \"siginv_prior\": [1.0, 1.0], \"nu_prior\": [0.5, 60.0]}");
+    j.arr("chain_beta_true", bt); j.arr("chain_beta_mean", mo.mean()); j.arr("chain_beta_sd", mo.sd());
+    j.arr("chain_sigma_nu_mean", sn.mean()); j.arr("chain_sigma_nu_sd", sn.sd());
+  }
+  write_file(dir + "/ref_student.json", j.str());
+}
+
+// ------------------------------------------------------------------------------------
 // bench <logit|spike|poisson> n p nonzero threads iters warmup
 int run_bench(int argc, char **argv) {
   if (argc < 9) { fprintf(stderr, "usage: bench model n p nonzero threads iters warmup [zellner]\n"); return 2; }
@@ -623,6 +703,7 @@ int main(int argc, char **argv) {
       if (what == "all" || what == "loglike") golden_loglike(dir);
       if (what == "all" || what == "stats") golden_draw_stats(dir);
       if (what == "all" || what == "chains") golden_chains(dir);
+      if (what == "all" || what == "student") golden_student(dir);
       return 0;
     }
     if (argc >= 2 && std::string(argv[1]) == "bench") return run_bench(argc, argv);
