@@ -4,7 +4,7 @@
 // then attaches EITHER the reference sampler OR the B200 sampler with model->set_method(sampler) and calls
 // model->sample_posterior().  Prints one JSON line with the posterior summaries of both chains on the same
 // data; tests/test_gpu_adapter.py compares them within Monte Carlo error.
-//   usage: boom_adapter_demo <logit|spike|poisson|pspike|mode|pmode|fixed|pfixed|bench|api|composite|chunk|probit|active|pactive> n p nonzero iters burn
+//   usage: boom_adapter_demo <logit|spike|poisson|pspike|mode|pmode|fixed|pfixed|bench|api|composite|chunk|probit|treg|active|pactive> n p nonzero iters burn
 //          (mode / pmode: find_posterior_mode; fixed / pfixed: externally driven statistics, host steps only, no GPU;
 //           bench: ms per iteration of the adapter beside the standalone classes; api: the public surface beyond draw())
 #include <chrono>
@@ -26,8 +26,12 @@
 #include "Models/Glm/PosteriorSamplers/BinomialProbitSpikeSlabSampler.hpp"
 #include "Models/Glm/PosteriorSamplers/PoissonRegressionAuxMixSampler.hpp"
 #include "Models/Glm/PosteriorSamplers/PoissonRegressionSpikeSlabSampler.hpp"
+#include "Models/ChisqModel.hpp"
+#include "Models/Glm/PosteriorSamplers/TRegressionSampler.hpp"
+#include "Models/Glm/TRegression.hpp"
 #include "Models/Glm/VariableSelectionPrior.hpp"
 #include "Models/MvnModel.hpp"
+#include "Models/UniformModel.hpp"
 #include "distributions.hpp"
 
 #include "boom_b200_adapter.hpp"
@@ -264,6 +268,57 @@ int main(int argc, char **argv) {
         out[arm] = run(model, iters, burn);
       }
       printf("{\"kind\": \"probit\", \"n\": %d, \"p\": %d, \"iters\": %d, \"burn\": %d, ", n, p, iters, burn);
+      print_vec("beta_true", beta);
+      print_summary("reference", out[0]); printf(", ");
+      print_summary("b200", out[1]);
+      printf("}\n");
+      return 0;
+    }
+    if (kind == "treg") {
+      // the Student-t sibling: TRegressionSampler on BOOM's TRegressionModel, reference vs B200, y = x'beta + 1.5 t_4.
+      // The summaries carry (beta, sigma, nu); the B200 arm also checks its public pieces against the reference's own.
+      Summary out[2];
+      std::vector<double> yt(n);
+      for (int i = 0; i < n; ++i) yt[i] = xs[i].dot(beta) + 1.5 * rnorm() / std::sqrt(rgamma(2.0, 2.0));
+      NEW(MvnModel, prior)(Vector(p, 0.0), SpdMatrix(p, 100.0));
+      NEW(ChisqModel, siginv_prior)(1.0, 1.0);
+      NEW(UniformModel, nu_prior)(0.5, 60.0);
+      double ll_ref = 0, ll_b200 = 0, suf_diff = -1;
+      for (int arm = 0; arm < 2; ++arm) {
+        NEW(TRegressionModel, model)(p);
+        for (int i = 0; i < n; ++i) model->add_data(new RegressionData(yt[i], xs[i]));
+        RNG seeder(arm == 0 ? 61 : 62);
+        Ptr<PosteriorSampler> sampler;
+        Ptr<B200::TRegressionSampler> b200;
+        if (arm == 0) sampler = new TRegressionSampler(model.get(), prior, siginv_prior, nu_prior, seeder);
+        else { b200 = new B200::TRegressionSampler(model.get(), prior, siginv_prior, nu_prior, seeder); sampler = b200; }
+        model->set_method(sampler);
+        Vector s1(p + 2, 0.0), s2(p + 2, 0.0);
+        auto t0 = std::chrono::steady_clock::now();
+        for (int it = 0; it < iters; ++it) {
+          model->sample_posterior();
+          if (it >= burn) {
+            Vector v = concat(model->Beta(), Vector{model->sigma(), model->nu()});
+            for (int j = 0; j < p + 2; ++j) { s1[j] += v[j]; s2[j] += v[j] * v[j]; }
+          }
+        }
+        out[arm].secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const double m = iters - burn;
+        out[arm].mean = s1 / m; out[arm].sd = Vector(p + 2); out[arm].inc = Vector(p + 2, 1.0);
+        for (int j = 0; j < p + 2; ++j) out[arm].sd[j] = std::sqrt(std::max(0.0, s2[j] / m - out[arm].mean[j] * out[arm].mean[j]));
+        if (arm == 1) {
+          // device log likelihood against the reference model's own; the reference-typed statistics against a host recomputation
+          // is not possible (the weights stay on the device), so check their internal consistency instead
+          ll_ref = model->log_likelihood(model->Beta(), model->sigsq(), model->nu());
+          ll_b200 = b200->log_likelihood(model->Beta(), model->sigsq(), model->nu());
+          const WeightedRegSuf &suf(b200->complete_data_sufficient_statistics());
+          suf_diff = std::fabs(suf.n() - n) + (suf.sumw() > 0 ? 0.0 : 1.0) + (suf.xtx()(0, 0) == suf.sumw() ? 0.0 : std::fabs(suf.xtx()(0, 0) - suf.sumw()) / suf.sumw());
+          b200->draw_nu_given_complete_data();
+          if (!(model->nu() > 0.5 && model->nu() < 60.0)) suf_diff += 10;
+        }
+      }
+      printf("{\"kind\": \"treg\", \"n\": %d, \"p\": %d, \"iters\": %d, \"burn\": %d, \"loglike_reference\": %.15g, \"loglike_b200\": %.15g, "
+             "\"suf_consistency\": %.3g, ", n, p, iters, burn, ll_ref, ll_b200, suf_diff);
       print_vec("beta_true", beta);
       print_summary("reference", out[0]); printf(", ");
       print_summary("b200", out[1]);

@@ -93,7 +93,7 @@ void DeviceImputerBase::ensure_device_rows() {
     const int64_t chunk = std::max<int64_t>(1024, (int64_t)(32u << 20) / (8 * (int64_t)p));
     std::vector<double> X((size_t)std::min(n, chunk) * p), aux((size_t)std::min(n, chunk));
     std::vector<int64_t> y((size_t)std::min(n, chunk));   // 8 bytes per row: doubles (binomial) or int64 (poisson)
-    check(boomgpu_upload_begin(ctx_, rows_are_poisson() ? 1 : 0, n, p));
+    check(boomgpu_upload_begin(ctx_, row_kind(), n, p));
     for (int64_t row0 = 0; row0 < n; row0 += chunk) {
       const int64_t rows = std::min(chunk, n - row0);
       pack_rows(row0, rows, X.data(), y.data(), aux.data());
@@ -783,6 +783,167 @@ WeightedRegSuf BinomialProbitSpikeSlabSampler::complete_data_sufficient_statisti
   suf.set_xtwx(xtx);
   suf.set_xtwy(Vector(hsuf_.xty().begin(), hsuf_.xty().end()));
   return suf;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The Student-t sibling.
+namespace {
+// the functors BOOM's ScalarSliceSampler holds (it copies them: they carry only a pointer)
+struct NuObservedTarget {
+  std::function<double(double)> f;
+  double operator()(double nu) const { return f(nu); }
+};
+}  // namespace
+
+TRegressionSampler::TRegressionSampler(TRegressionModel *model, const Ptr<MvnBase> &coefficient_prior,
+                                       const Ptr<GammaModelBase> &siginv_prior, const Ptr<DoubleModel> &nu_prior, RNG &seeding_rng)
+    : DeviceImputerBase(model->xdim(), seeding_rng), model_(model), coefficient_prior_(coefficient_prior),
+      siginv_prior_(siginv_prior), nu_prior_(nu_prior), weight_model_(new ScaledChisqModel(model->nu())),
+      sigsq_sampler_(siginv_prior),
+      nu_observed_data_sampler_(NuObservedTarget{[this](double nu) { return this->nu_log_posterior(nu); }}, false, 1.0, &rng()),
+      nu_complete_data_sampler_(NuObservedTarget{[this](double nu) {
+                                  // TRegressionCompleteDataLogPosterior (TRegressionSampler.cpp:51-72)
+                                  if (nu <= 0.0) return negative_infinity();
+                                  const double ans = nu_prior_->logp(nu);
+                                  if (ans <= negative_infinity()) return ans;
+                                  return ans + weight_model_->log_likelihood(nu);
+                                }}, false, 1.0, &rng()),
+      suf_(model->xdim()) {
+  if (coefficient_prior_->dim() != model_->xdim()) report_error("Prior does not match model dimension.");
+  nu_observed_data_sampler_.set_lower_limit(0.0);
+  nu_complete_data_sampler_.set_lower_limit(0.0);
+  model_->add_observer([this]() { this->mark_stale(); });
+}
+
+void TRegressionSampler::pack_rows(int64_t row0, int64_t nrows, double *X, void *y, double *) const {
+  const std::vector<Ptr<RegressionData>> &data(model_->dat());
+  const int p = xdim_;
+  double *yd = static_cast<double *>(y);
+  for (int64_t i = 0; i < nrows; ++i) {
+    const RegressionData &d(*data[row0 + i]);
+    const Vector &x(d.x());
+    std::copy(x.begin(), x.end(), X + (size_t)i * p);
+    yd[i] = d.y();
+  }
+}
+void TRegressionSampler::observe_row_objects(bool tf) {
+  for (const Ptr<RegressionData> &d : model_->dat()) {
+    d->remove_observer(observer_key());
+    d->Xptr()->remove_observer(observer_key());
+    if (tf) {
+      d->add_observer(observer_key(), [this]() { this->mark_stale(); });
+      d->Xptr()->add_observer(observer_key(), [this]() { this->mark_stale(); });
+    }
+  }
+}
+int TRegressionSampler::device_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *suf_dev) {
+  return boomgpu_student_step_device(ctx, beta, model_->sigma(), model_->nu(), seed, iteration, suf_dev);
+}
+int TRegressionSampler::device_step_sync(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *xtx,
+                                         double *xty, double scalars[4]) {
+  return boomgpu_student_step(ctx, beta, model_->sigma(), model_->nu(), seed, iteration, xtx, xty, scalars);
+}
+int TRegressionSampler::device_loglike_derivs(boomgpu_ctx *, const double *, double *, double *, double *) {
+  report_error("derivatives of the Student-t log likelihood are not provided (TRegression.cpp:118-121)");
+  return 1;
+}
+int TRegressionSampler::device_loglike_derivs_device(boomgpu_ctx *, const double *, double *) {
+  report_error("derivatives of the Student-t log likelihood are not provided (TRegression.cpp:118-121)");
+  return 1;
+}
+int TRegressionSampler::device_loglike_derivs_selected(boomgpu_ctx *, const double *, double *, double *, double *) {
+  report_error("derivatives of the Student-t log likelihood are not provided (TRegression.cpp:118-121)");
+  return 1;
+}
+int TRegressionSampler::device_loglike_derivs_selected_device(boomgpu_ctx *, const double *, double *) {
+  report_error("derivatives of the Student-t log likelihood are not provided (TRegression.cpp:118-121)");
+  return 1;
+}
+
+void TRegressionSampler::draw() {   // TRegressionSampler.cpp:114-119
+  impute_latent_data();
+  draw_beta_full_conditional();
+  draw_sigsq_full_conditional();
+  draw_nu_given_observed_data();
+}
+double TRegressionSampler::logpri() const {   // .cpp:121-126
+  return nu_prior_->logp(model_->nu()) + sigsq_sampler_.log_prior(model_->sigsq()) + coefficient_prior_->logp(model_->Beta());
+}
+
+const WeightedRegSuf &TRegressionSampler::complete_data_sufficient_statistics() const {
+  if (!suf_synced_) {
+    const int p = xdim_;
+    SpdMatrix xtx(p);
+    std::copy(hsuf_.xtx().a.begin(), hsuf_.xtx().a.end(), xtx.data());
+    suf_.reset(xtx, Vector(hsuf_.xty().begin(), hsuf_.xty().end()), hsuf_.yty(), hsuf_.n(), hsuf_.sumw(), hsuf_.sumlogw());
+    suf_synced_ = true;
+  }
+  return suf_;
+}
+void TRegressionSampler::clear_complete_data_sufficient_statistics() {
+  DeviceImputerBase::clear_complete_data_sufficient_statistics();
+  weight_model_->clear_data();
+}
+void TRegressionSampler::update_complete_data_sufficient_statistics(double y, const Vector &x, double weight) {
+  hsuf_.add_data(BOOM_B200::Vector(x.begin(), x.end()), y, weight);
+  statistics_changed();
+}
+
+// draw_beta_full_conditional_impl (.cpp:74-85): precision = Ominv + X'WX / sigsq, scaled mean = Ominv b + X'Wy / sigsq
+void TRegressionSampler::draw_beta_full_conditional() {
+  const int p = xdim_;
+  const double sigsq = model_->sigsq();
+  SpdMatrix precision(coefficient_prior_->siginv());
+  Vector scaled_mean = coefficient_prior_->siginv() * coefficient_prior_->mu();
+  const std::vector<double> &a(hsuf_.xtx().a);
+  for (int i = 0; i < p; ++i) {
+    for (int j = 0; j < p; ++j) precision(i, j) += a[(size_t)i * p + j] / sigsq;
+    scaled_mean[i] += hsuf_.xty()[i] / sigsq;
+  }
+  model_->set_Beta(rmvn_suf_mt(rng(), precision, scaled_mean));
+  residuals_current_ = false;
+}
+// .cpp:165-171 with WeightedRegSuf::weighted_sum_of_squared_errors (WeightedRegressionModel.cpp:89-95) on the landed statistics
+void TRegressionSampler::draw_sigsq_full_conditional() {
+  const int p = xdim_;
+  const Vector &b(model_->Beta());
+  const std::vector<double> &a(hsuf_.xtx().a);
+  double bxy = 0, bxxb = 0;
+  for (int i = 0; i < p; ++i) {
+    if (b[i] == 0.0) continue;
+    bxy += b[i] * hsuf_.xty()[i];
+    double s = 0;
+    for (int j = 0; j < p; ++j) s += a[(size_t)i * p + j] * b[j];
+    bxxb += b[i] * s;
+  }
+  model_->set_sigsq(sigsq_sampler_.draw(rng(), hsuf_.n(), hsuf_.yty() - 2 * bxy + bxxb));
+}
+void TRegressionSampler::draw_nu_given_complete_data() {   // .cpp:173-176: the weights' GammaSuf = (n, sum w, sum log w)
+  weight_model_->suf()->set(hsuf_.sumw(), hsuf_.sumlogw(), hsuf_.n());
+  model_->set_nu(nu_complete_data_sampler_.draw(model_->nu()));
+}
+void TRegressionSampler::draw_nu_given_observed_data() {   // .cpp:178-181
+  residuals_current_ = false;
+  model_->set_nu(nu_observed_data_sampler_.draw(model_->nu()));
+}
+double TRegressionSampler::nu_log_posterior(double nu) {   // TRegressionLogPosterior (.cpp:31-49)
+  double ans = nu_prior_->logp(nu);
+  if (ans <= negative_infinity()) return ans;
+  if (!(nu > 0)) return negative_infinity();
+  ensure_device_rows();
+  double ll = 0;
+  ++ll_evals_;
+  check(boomgpu_student_loglike(device_ctx(), residuals_current_ ? nullptr : model_->Beta().data(), model_->sigma(), nu, &ll));
+  residuals_current_ = true;
+  return ans + ll;
+}
+double TRegressionSampler::log_likelihood(const Vector &beta, double sigsq, double nu) {
+  if (!(nu > 0) || !(sigsq > 0)) return negative_infinity();
+  ensure_device_rows();
+  double ll = 0;
+  residuals_current_ = false;
+  check(boomgpu_student_loglike(device_ctx(), beta.data(), std::sqrt(sigsq), nu, &ll));
+  return ll;
 }
 
 // ---------------------------------------------------------------------------------------------

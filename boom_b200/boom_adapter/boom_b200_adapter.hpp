@@ -7,6 +7,7 @@
 //   BOOM::BinomialLogitSpikeSlabSampler     -> BOOM::B200::BinomialLogitSpikeSlabSampler
 //   BOOM::BinomialLogitCompositeSpikeSlabSampler -> BOOM::B200::BinomialLogitCompositeSpikeSlabSampler  (what R's logit.spike builds)
 //   BOOM::BinomialProbitSpikeSlabSampler    -> BOOM::B200::BinomialProbitSpikeSlabSampler   (sibling)
+//   BOOM::TRegressionSampler                -> BOOM::B200::TRegressionSampler               (sibling)
 //   BOOM::PoissonRegressionAuxMixSampler    -> BOOM::B200::PoissonRegressionAuxMixSampler
 //   BOOM::PoissonRegressionSpikeSlabSampler -> BOOM::B200::PoissonRegressionSpikeSlabSampler
 //
@@ -41,7 +42,12 @@
 #include "Models/Glm/BinomialProbitModel.hpp"
 #include "Models/Glm/PoissonRegressionModel.hpp"
 #include "Models/Glm/PosteriorSamplers/BinomialLogitAuxmixSampler.hpp"
+#include "Models/Glm/TRegression.hpp"
 #include "Models/Glm/VariableSelectionPrior.hpp"
+#include "Models/GammaModel.hpp"
+#include "Models/PosteriorSamplers/GenericGaussianVarianceSampler.hpp"
+#include "Models/ScaledChisqModel.hpp"
+#include "Samplers/ScalarSliceSampler.hpp"
 #include "Models/Glm/WeightedRegressionModel.hpp"
 #include "Models/MvnBase.hpp"
 #include "Models/PosteriorSamplers/PosteriorSampler.hpp"
@@ -90,6 +96,7 @@ class DeviceImputerBase : public PosteriorSampler {
   typedef std::function<void(int64_t row0, int64_t nrows, const double *X, const void *y, const double *aux)> ChunkSink;
   virtual int64_t row_count() const = 0;
   virtual bool rows_are_poisson() const = 0;
+  virtual int row_kind() const { return rows_are_poisson() ? 1 : 0; }   // boomgpu_upload_begin: 0 binomial, 1 Poisson, 2 plain regression
   virtual void install_tables(boomgpu_ctx *ctx) = 0;                     // mixture tables, before the rows
   virtual void pack_rows(int64_t row0, int64_t nrows, double *X, void *y, double *aux) const = 0;
   virtual void observe_row_objects(bool tf) = 0;
@@ -116,6 +123,7 @@ class DeviceImputerBase : public PosteriorSampler {
   // PoissonRegressionSpikeSlabSampler.cpp:69-106): Newton-Raphson on the included coefficients, derivatives from the device
   bool find_mode(GlmCoefs &coef, const Ptr<MvnBase> &slab, const Ptr<VariableSelectionPrior> &spike, double epsilon, double *value);
   void mark_stale() { stale_ = true; }
+  boomgpu_ctx *device_ctx() { return ctx_; }   // valid after ensure_device_rows()
   void check(int rc) const;
   virtual void statistics_changed() {}   // the reference-typed views are out of date
   // host steps on hsuf_
@@ -334,6 +342,61 @@ class BinomialProbitSpikeSlabSampler : public DeviceImputerBase {
   int clt_threshold_;
   bool allow_model_selection_ = true, want_xtx_ = true;
   int max_flips_ = -1;
+};
+
+// TRegressionSampler (Models/Glm/PosteriorSamplers/TRegressionSampler.hpp:34-137): Student-t regression by the scale-mixture
+// augmentation.  The weights w_i | residual and WeightedRegSuf::add_data(x_i, y_i, w_i) are one device step; beta, sigma^2
+// and nu are drawn on the host with BOOM's own rmvn_suf_mt, GenericGaussianVarianceSampler and ScalarSliceSampler -- the
+// slice sampler's target (prior + observed-data Student log likelihood, TRegressionSampler.cpp:31-49) is evaluated on the
+// device from residuals it keeps in HBM: one pass over X per draw of nu, then 8 n bytes per candidate.
+class TRegressionSampler : public DeviceImputerBase {
+ public:
+  TRegressionSampler(TRegressionModel *model, const Ptr<MvnBase> &coefficient_prior, const Ptr<GammaModelBase> &siginv_prior,
+                     const Ptr<DoubleModel> &nu_prior, RNG &seeding_rng = GlobalRng::rng);
+  void draw() override;
+  double logpri() const override;
+  void draw_beta_full_conditional();
+  void draw_sigsq_full_conditional();
+  void draw_nu_given_complete_data();
+  void draw_nu_given_observed_data();
+  void set_sigma_upper_limit(double max_sigma) { sigsq_sampler_.set_sigma_max(max_sigma); }
+  const WeightedRegSuf &complete_data_sufficient_statistics() const;   // the reference's own type, filled on demand
+  void clear_complete_data_sufficient_statistics();
+  void update_complete_data_sufficient_statistics(double y, const Vector &x, double weight);
+  // TRegressionModel::log_likelihood(beta, sigsq, nu) (TRegression.cpp:74-86) evaluated on the device, all shards' rows
+  double log_likelihood(const Vector &beta, double sigsq, double nu);
+  int64_t likelihood_evaluations() const { return ll_evals_; }
+
+ protected:
+  int64_t row_count() const override { return (int64_t)model_->dat().size(); }
+  bool rows_are_poisson() const override { return false; }
+  int row_kind() const override { return 2; }
+  void install_tables(boomgpu_ctx *) override {}
+  void pack_rows(int64_t row0, int64_t nrows, double *X, void *y, double *aux) const override;
+  void observe_row_objects(bool tf) override;
+  int device_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *suf_dev) override;
+  int device_step_sync(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *xtx, double *xty,
+                       double scalars[4]) override;
+  int device_loglike_derivs(boomgpu_ctx *, const double *, double *, double *, double *) override;
+  int device_loglike_derivs_device(boomgpu_ctx *, const double *, double *) override;
+  int device_loglike_derivs_selected(boomgpu_ctx *, const double *, double *, double *, double *) override;
+  int device_loglike_derivs_selected_device(boomgpu_ctx *, const double *, double *) override;
+  const Vector &current_beta() const override { return model_->Beta(); }
+  void statistics_changed() override { suf_synced_ = false; }
+
+ private:
+  double nu_log_posterior(double nu);
+  TRegressionModel *model_;
+  Ptr<MvnBase> coefficient_prior_;
+  Ptr<GammaModelBase> siginv_prior_;
+  Ptr<DoubleModel> nu_prior_;
+  Ptr<ScaledChisqModel> weight_model_;
+  GenericGaussianVarianceSampler sigsq_sampler_;
+  ScalarSliceSampler nu_observed_data_sampler_, nu_complete_data_sampler_;
+  mutable WeightedRegSuf suf_;
+  mutable bool suf_synced_ = false;
+  bool residuals_current_ = false;
+  int64_t ll_evals_ = 0;
 };
 
 class PoissonRegressionSpikeSlabSampler : public PoissonRegressionAuxMixSampler {

@@ -3,6 +3,7 @@
 #include "../../include/boomgpu.h"
 
 #include <algorithm>
+#include <numeric>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -81,7 +82,9 @@ struct boomgpu_ctx {
   bool xty_only = false;                           // this step wants X'z alone (probit: X'WX is constant)
   int syrk_diag = 0;                               // 0 strip form for whole diagonal regions, 1 unit form everywhere
   int syrk_filter = 0;                             // profiling aid: time the off-diagonal / diagonal regions of the SYRK alone
-  int syrk_order = 1;                              // 1 off-diagonal regions first, diagonal last (short CTAs fill the tail); 0 k-slice major
+  int syrk_order = 1;                              // 1 off-diagonal regions first, diagonal last (short CTAs fill the tail); 0 k-slice major;
+                                                   // 2 k-slice major over uniform work items (diagonal regions in pairs)
+  SyrkItem *syrk_items = nullptr; int syrk_items_nblk = -1, syrk_nitems = 0;   // order 2: the work items of one k-slice
   int syrk_waves = 30;                             // CTAs per SM the split-K aims for
   int syrk_cluster = 0;                            // experiment: launch the SYRK with thread-block clusters of this many CTAs
   int gather = 0;                                  // option: 0 auto (sparse beta -> gather pass), 1 never, 2 whenever beta has a zero
@@ -534,6 +537,34 @@ int ensure_ws(boomgpu_ctx *ctx) {
 }
 
 // pass 2 + reduction into suf (device)
+// Order 2 of the SYRK grid: the work items of one k-slice in launch order.  Off-diagonal regions are listed super-tile by
+// super-tile (12 x 12 regions: about the 148 CTAs that run at one time, which then touch 24 distinct panels instead of the
+// 1 + 148 of a row-by-row order -- what made C4's shape read X 18 times), every diagonal super-tile followed by its
+// diagonal regions in pairs (2q, 2q + 1); an odd last diagonal region stands alone.
+int ensure_syrk_items(boomgpu_ctx *ctx, int nblk) {
+  if (ctx->syrk_items && ctx->syrk_items_nblk == nblk) return 0;
+  std::vector<SyrkItem> items;
+  constexpr int T = 12;
+  const int nsuper = (nblk + T - 1) / T;
+  for (int SI = 0; SI < nsuper; ++SI)
+    for (int SJ = SI; SJ < nsuper; ++SJ) {
+      for (int I = SI * T; I < std::min(nblk, (SI + 1) * T); ++I)
+        for (int J = std::max(I + 1, SJ * T); J < std::min(nblk, (SJ + 1) * T); ++J) items.push_back({(int16_t)I, (int16_t)J, 0, 0});
+      if (SJ == SI) {
+        const int lo = SI * T, hi = std::min(nblk, (SI + 1) * T);
+        int I = lo;
+        for (; I + 1 < hi; I += 2) items.push_back({(int16_t)I, (int16_t)(I + 1), 2, 0});
+        if (I < hi) items.push_back({(int16_t)I, (int16_t)I, 1, 0});
+      }
+    }
+  if (ctx->syrk_items) { CU(cudaFree(ctx->syrk_items)); ctx->syrk_items = nullptr; }
+  CU(cudaMalloc((void **)&ctx->syrk_items, sizeof(SyrkItem) * items.size()));
+  CU(cudaMemcpyAsync(ctx->syrk_items, items.data(), sizeof(SyrkItem) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));   // items is a local
+  ctx->syrk_items_nblk = nblk; ctx->syrk_nitems = (int)items.size();
+  return 0;
+}
+
 int launch_syrk(boomgpu_ctx *ctx, double *suf) {
   SyrkParams sp;
   sp.X = ctx->Xt; sp.ldx = ctx->ldxt; sp.n = ctx->n; sp.p = ctx->p;
@@ -542,14 +573,26 @@ int launch_syrk(boomgpu_ctx *ctx, double *suf) {
   sp.nregions = sp.nblk * (sp.nblk + 1) / 2;
   // ~30 CTAs per SM for dynamic balance (measured, profiles/bench_r02/run22_syrk_order.jsonl: 20 -> 30 is worth 0.5-1.5 %
   // with the off-diagonal-first order; more only adds partial tiles), at least 2048 rows per CTA
-  int64_t ksplit = (ctx->syrk_waves * (int64_t)ctx->sms + sp.nregions - 1) / sp.nregions;
+  sp.order = (ctx->syrk_order == 2 && kSyrkConsumerWarps != 8) ? 1 : ctx->syrk_order;
+  sp.items = nullptr; sp.nitems = 0;
+  int per_slice = sp.nregions;                     // CTAs per k-slice
+  if (sp.order == 2) {
+    if (int rc = ensure_syrk_items(ctx, sp.nblk)) return rc;
+    sp.items = ctx->syrk_items; sp.nitems = ctx->syrk_nitems;
+    per_slice = sp.nitems;
+  }
+  int64_t ksplit = (ctx->syrk_waves * (int64_t)ctx->sms + per_slice - 1) / per_slice;
+  if (sp.order == 2) {
+    // uniform CTAs: a grid that is a whole number of waves has no tail at all
+    const int64_t unit = ctx->sms / std::gcd((int64_t)ctx->sms, (int64_t)per_slice);
+    ksplit = std::max<int64_t>(unit, (ksplit + unit / 2) / unit * unit);
+  }
   ksplit = std::min<int64_t>(ksplit, std::max<int64_t>(1, ctx->n / 2048));
   ksplit = std::max<int64_t>(ksplit, 1);
   int64_t rows = (ctx->n + ksplit - 1) / ksplit;
   rows = ((rows + kSyrkKB - 1) / kSyrkKB) * kSyrkKB;
   ksplit = std::max<int64_t>(1, (ctx->n + rows - 1) / rows);
   sp.ksplit = (int)ksplit;
-  sp.order = ctx->syrk_order;
   sp.rows_per_slice = rows;
   const int64_t need = ksplit * sp.nregions * kSyrkTileLen;
   if (ensure(ctx, &ctx->partials, &ctx->partials_cap, need)) return BOOMGPU_ERR_CUDA;
@@ -561,7 +604,7 @@ int launch_syrk(boomgpu_ctx *ctx, double *suf) {
   CU(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmemBytes));
   {
     LaunchScope ls(ctx, 2);
-    const unsigned grid = (unsigned)(ksplit * sp.nregions);
+    const unsigned grid = (unsigned)(ksplit * per_slice);
     if (ctx->syrk_cluster > 1 && grid % (unsigned)ctx->syrk_cluster == 0) {
       // experiment (option "syrk_cluster"): co-schedule c consecutive CTAs -- with the off-diagonal-first order the regions of
       // one k-slice that share panels -- as a thread-block cluster, so that they start together and meet in L2
@@ -1106,7 +1149,7 @@ void boomgpu_destroy(boomgpu_ctx *ctx) {
   cudaFree(ctx->mix_dev);
   cudaFree(ctx->beta_dev); cudaFreeHost(ctx->beta_pin);
   cudaFree(ctx->suf_dev); cudaFreeHost(ctx->suf_pin);
-  cudaFree(ctx->partials); cudaFree(ctx->scal_partials); cudaFree(ctx->resid_buf);
+  cudaFree(ctx->partials); cudaFree(ctx->scal_partials); cudaFree(ctx->resid_buf); cudaFree(ctx->syrk_items);
   cudaFree(ctx->w_buf); cudaFree(ctx->s_buf);
   cudaFree(ctx->Xsel); cudaFree(ctx->sel_cols_dev);
   cudaFree(ctx->act_dev); cudaFreeHost(ctx->act_pin); cudaFree(ctx->col_buf);
@@ -1143,7 +1186,7 @@ int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value) {
   if (!strcmp(name, "single_launch")) { ctx->single_launch = value != 0; return 0; }
   if (!strcmp(name, "syrk_diag")) { ctx->syrk_diag = value != 0; return 0; }
   if (!strcmp(name, "syrk_filter")) { ctx->syrk_filter = (int)value; return 0; }
-  if (!strcmp(name, "syrk_order")) { ctx->syrk_order = value != 0; return 0; }
+  if (!strcmp(name, "syrk_order")) { ctx->syrk_order = value < 0 || value > 2 ? 1 : (int)value; return 0; }
   if (!strcmp(name, "syrk_cluster")) {
     if (value < 0 || value > 16) return fail(ctx, BOOMGPU_ERR_ARG, "syrk_cluster must be in 0..16");
     ctx->syrk_cluster = (int)value; return 0;

@@ -554,6 +554,7 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
                : "memory");
 }
 
+struct SyrkItem { int16_t I, J, kind; int16_t pad; };   // kind 0: off-diagonal region (I, J); 1: diagonal region (I, I); 2: the pair (I, I), (J, J)
 struct SyrkParams {
   const double *X;
   int64_t ldx;
@@ -568,15 +569,33 @@ struct SyrkParams {
   double *partials;  // [ksplit][nregions][kSyrkTileLen]
   int diag_form;     // option "syrk_diag": 0 strip form for whole diagonal regions (default), 1 unit form everywhere
   int filter;        // profiling aid (option "syrk_filter"): 0 all regions, 1 off-diagonal regions only, 2 diagonal only
-  int order;         // option "syrk_order": 1 off-diagonal regions first, diagonal regions last (default), 0 k-slice major
+  int order;         // option "syrk_order": 1 off-diagonal regions first, diagonal regions last, 0 k-slice major,
+                     // 2 k-slice major over UNIFORM work items (off-diagonal regions + PAIRS of diagonal regions), see SyrkItem
+  const SyrkItem *items;          // order 2: the work items of one k-slice, in launch order (device memory)
+  int nitems;
 };
+
+// Order 2.  A diagonal region costs about half an off-diagonal one, which is why order 1 schedules them last -- but then the
+// diagonal CTAs re-read every panel long after the off-diagonal CTAs of the same rows went through, and even perfect sharing
+// in L2 cannot get below 2 x X of DRAM traffic (measured: 2.6 x).  Here TWO diagonal regions (I, I) and (I + 1, I + 1) are
+// one work item: it loads the same two panels as the off-diagonal region (I, I + 1) and computes 2 x 136 atoms against 256,
+// so all CTAs of a k-slice cost the same, are handed out together (k-slice major) and walk the same rows at the same pace:
+// a panel tile is fetched from DRAM by the first CTA that needs it and found in L2 by the others.
+
 
 // CTA -> (k-slice, column blocks I <= J).  The hardware hands CTAs to the SMs in blockIdx order as they free up, so the END of
 // the grid decides how long the last SMs idle: a diagonal region costs about half an off-diagonal one (136 of 256 atoms), so
 // all off-diagonal work (k-slice major: the regions of one k-slice run together and share their panels in L2) goes first and
 // the cheap diagonal CTAs fill the tail (ncu, C3: SM-idle share of the launch 3.0 % with the k-slice major order).
-__device__ __forceinline__ void syrk_block_to_work(int b, const SyrkParams &prm, int &kslice, int &I, int &J) {
+__device__ __forceinline__ void syrk_block_to_work(int b, const SyrkParams &prm, int &kslice, int &I, int &J, int &kind) {
   const int nblk = prm.nblk;
+  if (prm.order == 2) {
+    kslice = b / prm.nitems;
+    const SyrkItem it = prm.items[b - kslice * prm.nitems];
+    I = it.I; J = it.J; kind = it.kind;
+    return;
+  }
+  kind = -1;
   if (prm.order == 0) {
     kslice = b / prm.nregions;
     int i = 0, rem = b - kslice * prm.nregions;
@@ -778,6 +797,79 @@ __device__ __forceinline__ void syrk_consume_strip(const SyrkWarpCtx &wc) {
   }
 }
 
+// Two diagonal regions in one CTA (work item kind 2): the strip form on panel A for region (I, I) and on panel B for region
+// (J, J), k-step by k-step on the same stage.  68 DMMA per k-step and SM sub-partition against the 64 of an off-diagonal
+// region.  A ragged last region (p = 500: 116 of 128 columns) runs through the same code: TMA delivers zeros beyond p, the
+// 23 atoms they make (1 % of a k-slice's work) are computed and never read by the reduction.
+template <int W>
+__device__ __forceinline__ void syrk_consume_strip2(const SyrkWarpCtx &wc, double *tile2) {
+  constexpr int R1 = W, R2 = 15 - W, N1 = 16 - R1, N2 = 16 - R2;
+  const int lane = wc.lane;
+  double cA1[N1][2], cA2[N2][2], cB1[N1][2], cB2[N2][2], cxA1 = 0.0, cxA2 = 0.0, cxB1 = 0.0, cxB2 = 0.0;
+#pragma unroll
+  for (int n = 0; n < N1; ++n) cA1[n][0] = cA1[n][1] = cB1[n][0] = cB1[n][1] = 0.0;
+#pragma unroll
+  for (int n = 0; n < N2; ++n) cA2[n][0] = cA2[n][1] = cB2[n][0] = cB2[n][1] = 0.0;
+  const int off = lane >> 2;
+  for (int it = 0; it < wc.nstages_total; ++it) {
+    const int s = it % kSyrkStages;
+    const uint32_t phase = (it / kSyrkStages) & 1;
+    mbar_wait(wc.full_bar + s, phase);
+    const double *stage = wc.smem + s * kSyrkStageDoubles;
+    const double *w_s = stage + 2 * kSyrkKB * kSyrkPanelLd;
+    const double *s_s = w_s + kSyrkKB;
+#pragma unroll
+    for (int kk = 0; kk < kSyrkKB / 4; ++kk) {
+      const int row = kk * 4 + (lane & 3);
+      const double wv = w_s[row], sv = s_s[row];
+      {
+        const double *xr = stage + row * kSyrkPanelLd + off;
+        double b[N1];
+#pragma unroll
+        for (int n = 0; n < N1; ++n) b[n] = xr[8 * (R1 + n)];
+        const double a1 = b[0] * wv, a2 = b[R2 - R1] * wv;
+#pragma unroll
+        for (int n = 0; n < N1; ++n) dmma884(cA1[n][0], cA1[n][1], a1, b[n]);
+#pragma unroll
+        for (int n = 0; n < N2; ++n) dmma884(cA2[n][0], cA2[n][1], a2, b[R2 - R1 + n]);
+        cxA1 = fma(b[0], sv, cxA1);
+        cxA2 = fma(b[R2 - R1], sv, cxA2);
+      }
+      {
+        const double *xr = stage + kSyrkKB * kSyrkPanelLd + row * kSyrkPanelLd + off;
+        double b[N1];
+#pragma unroll
+        for (int n = 0; n < N1; ++n) b[n] = xr[8 * (R1 + n)];
+        const double a1 = b[0] * wv, a2 = b[R2 - R1] * wv;
+#pragma unroll
+        for (int n = 0; n < N1; ++n) dmma884(cB1[n][0], cB1[n][1], a1, b[n]);
+#pragma unroll
+        for (int n = 0; n < N2; ++n) dmma884(cB2[n][0], cB2[n][1], a2, b[R2 - R1 + n]);
+        cxB1 = fma(b[0], sv, cxB1);
+        cxB2 = fma(b[R2 - R1], sv, cxB2);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(wc.empty_bar + s);
+  }
+  auto store = [&](double *tile, double (&c1)[N1][2], double (&c2)[N2][2], double cx1, double cx2) {
+#pragma unroll
+    for (int n = 0; n < N1; ++n)
+      *reinterpret_cast<double2 *>(tile + (8 * R1 + off) * 128 + 8 * (R1 + n) + 2 * (lane & 3)) = make_double2(c1[n][0], c1[n][1]);
+#pragma unroll
+    for (int n = 0; n < N2; ++n)
+      *reinterpret_cast<double2 *>(tile + (8 * R2 + off) * 128 + 8 * (R2 + n) + 2 * (lane & 3)) = make_double2(c2[n][0], c2[n][1]);
+    cx1 += __shfl_xor_sync(0xffffffffu, cx1, 1); cx1 += __shfl_xor_sync(0xffffffffu, cx1, 2);
+    cx2 += __shfl_xor_sync(0xffffffffu, cx2, 1); cx2 += __shfl_xor_sync(0xffffffffu, cx2, 2);
+    if ((lane & 3) == 0) {
+      tile[128 * 128 + 8 * R1 + off] = cx1;
+      tile[128 * 128 + 8 * R2 + off] = cx2;
+    }
+  };
+  store(wc.tile, cA1, cA2, cxA1, cxA2);
+  store(tile2, cB1, cB2, cxB1, cxB2);
+}
+
 template <int NM>
 __device__ __forceinline__ void syrk_dispatch_nm(int role, const SyrkWarpCtx &wc) {
   if (kSyrkConsumerWarps == 8) {
@@ -821,9 +913,11 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap xmap, SyrkParams prm, SyrkU
   uint64_t *empty_bar = full_bar + kSyrkStages;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  int kslice, I, J;
-  syrk_block_to_work((int)blockIdx.x, prm, kslice, I, J);
-  const int region = I * prm.nblk - I * (I - 1) / 2 + (J - I);   // row-by-row index over the upper triangle (region_to_blocks)
+  int kslice, I, J, kind;
+  syrk_block_to_work((int)blockIdx.x, prm, kslice, I, J, kind);
+  const bool pair = kind == 2;           // two diagonal regions (I, I) and (J, J) on the two panels of this CTA
+  const int region = pair ? I * prm.nblk - I * (I - 1) / 2
+                          : I * prm.nblk - I * (I - 1) / 2 + (J - I);   // row-by-row index over the upper triangle (region_to_blocks)
   const bool diag = (I == J);
   if (prm.filter && (prm.filter == 1) == diag) return;   // profiling aid: results are incomplete on purpose
   const int64_t row_begin = (int64_t)kslice * prm.rows_per_slice;
@@ -874,6 +968,25 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap xmap, SyrkParams prm, SyrkU
   // carries no predicates (a predicated mma.sync costs a WARPSYNC + branch per instruction).
   const int P8 = (prm.p + 7) & ~7;
   const int remJ = P8 - 128 * J;   // columns (whole 8-column atoms) of column block J inside X
+  if (pair) {
+    SyrkWarpCtx wc;
+    wc.smem = smem; wc.full_bar = full_bar; wc.empty_bar = empty_bar; wc.nstages_total = nstages_total;
+    wc.lane = lane;
+    wc.panelB_off = kSyrkKB * kSyrkPanelLd;
+    wc.tile = prm.partials + ((int64_t)kslice * prm.nregions + region) * kSyrkTileLen;
+    double *tile2 = prm.partials + ((int64_t)kslice * prm.nregions + (J * prm.nblk - J * (J - 1) / 2)) * kSyrkTileLen;
+    switch (wid) {
+      case 0: syrk_consume_strip2<0>(wc, tile2); break;
+      case 1: syrk_consume_strip2<1>(wc, tile2); break;
+      case 2: syrk_consume_strip2<2>(wc, tile2); break;
+      case 3: syrk_consume_strip2<3>(wc, tile2); break;
+      case 4: syrk_consume_strip2<4>(wc, tile2); break;
+      case 5: syrk_consume_strip2<5>(wc, tile2); break;
+      case 6: syrk_consume_strip2<6>(wc, tile2); break;
+      default: syrk_consume_strip2<7>(wc, tile2); break;
+    }
+    return;
+  }
   if (kSyrkConsumerWarps == 8 && diag && remJ >= 128 && prm.diag_form == 0) {   // whole diagonal region: strip form
     SyrkWarpCtx wc;
     wc.smem = smem; wc.full_bar = full_bar; wc.empty_bar = empty_bar; wc.nstages_total = nstages_total;

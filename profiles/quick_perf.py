@@ -19,6 +19,7 @@ CFG = {
     "c1t": ("logit", 9_000, 20), "c1h": ("logit", 50_000, 20), "c1d": ("logit", 200_000, 20), "c1q": ("logit", 400_000, 20),
     "p40": ("logit", 8_000_000, 40), "p48l": ("logit", 8_000_000, 48), "p56": ("logit", 8_000_000, 56), "p40p": ("poisson", 4_000_000, 40),
     "p64p": ("poisson", 4_000_000, 64), "c5m": ("logit", 100_000_000, 16), "c5f": ("logit", 200_000_000, 16), "c2x4": ("poisson", 4_000_000, 50),
+    "t16": ("student", 25_000_000, 16), "t50": ("student", 4_000_000, 50), "t20": ("student", 100_000, 20), "t500": ("student", 1_000_000, 500),
     "p8": ("logit", 25_000_000, 8), "p24": ("logit", 12_000_000, 24), "p48": ("poisson", 4_000_000, 48),
 }
 
@@ -42,6 +43,11 @@ def make(kind, n, p, dev):
     if kind == "logit":
         y = (torch.rand(n, dtype=torch.float64, device=dev, generator=g) < torch.sigmoid(eta)).double()
         aux = torch.ones(n, dtype=torch.float64, device=dev)
+    elif kind == "student":   # y = eta + 1.5 t_4
+        z = torch.empty(n, dtype=torch.float64, device=dev).normal_(generator=g)
+        w = torch.distributions.Chi2(torch.tensor(4.0, dtype=torch.float64, device=dev)).sample((n,)) / 4.0
+        y = eta + 1.5 * z / torch.sqrt(w)
+        aux = None
     else:
         y = torch.poisson(torch.exp(eta), generator=g).long()
         aux = torch.ones(n, dtype=torch.float64, device=dev)
@@ -61,14 +67,22 @@ def main():
         if kind == "logit":
             ctx.set_logit_mixture(*boom_b200.default_logit_mixture())
             ctx.adopt_binomial(n, p, X.data_ptr(), p, y.data_ptr(), aux.data_ptr(), keepalive=(X, y, aux))
+        elif kind == "student":
+            ctx.adopt_regression(n, p, X.data_ptr(), p, y.data_ptr(), keepalive=(X, y))
         else:
             ctx.set_poisson_table(*boom_b200.poisson_mixture_table_arrays())
             ctx.adopt_poisson(n, p, X.data_ptr(), p, y.data_ptr(), aux.data_ptr(), keepalive=(X, y, aux))
         suf = torch.empty(ctx.suf_len(), dtype=torch.float64, device=dev)
         iters = 3 if n * p > 1e9 else 20
+        def step(it):
+            if kind == "logit":
+                ctx.logit_step_device(beta, 10, 1, it, suf.data_ptr())
+            elif kind == "student":
+                ctx.student_step_device(beta, 1.5, 4.0, 1, it, suf.data_ptr())
+            else:
+                ctx.poisson_step_device(beta, 1, it, suf.data_ptr())
         for it in range(2):
-            (ctx.logit_step_device(beta, 10, 1, it, suf.data_ptr()) if kind == "logit"
-             else ctx.poisson_step_device(beta, 1, it, suf.data_ptr()))
+            step(it)
         ctx.synchronize(); ctx.timings(reset=True)
         t0 = time.perf_counter()
         mode = os.environ.get("QP_MODE", "")   # "": queued back to back; "sync": wait after every step; "host": the host-result entry
@@ -76,8 +90,7 @@ def main():
             if mode == "host" and kind == "logit":
                 ctx.logit_step(beta, 10, 1, 10 + it)
                 continue
-            (ctx.logit_step_device(beta, 10, 1, 10 + it, suf.data_ptr()) if kind == "logit"
-             else ctx.poisson_step_device(beta, 1, 10 + it, suf.data_ptr()))
+            step(10 + it)
             if mode == "sync":
                 ctx.synchronize()
                 time.sleep(float(os.environ.get("QP_SLEEP", "0")))

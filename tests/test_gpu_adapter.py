@@ -147,3 +147,20 @@ def test_active_set_option_on_the_adapter(mode):
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["same_model"] is True and r["chain_max_abs_diff"] < 1e-7
     assert r["columns_fetched"] >= 5 and r["suf_xtx_rel_diff"] < 1e-9
+
+
+def test_student_t_sibling_on_boom_models():
+    """TRegressionSampler on BOOM's TRegressionModel, y = x'beta + 1.5 t_4: the reference sampler and the B200
+    sampler (BOOM's own rmvn / GenericGaussianVarianceSampler / ScalarSliceSampler around the device step) give the same
+    posterior of (beta, sigma, nu) within Monte Carlo error; the device log likelihood equals TRegressionModel's own."""
+    iters, burn = 6000, 1000
+    r = _demo("treg", 2500, 5, 3, iters, burn)
+    ref, gpu = r["reference"], r["b200"]
+    m0, m1, s0, s1 = (np.array(ref["mean"]), np.array(gpu["mean"]), np.array(ref["sd"]), np.array(gpu["sd"]))
+    tau = np.r_[np.full(len(m0) - 2, TAU), 40.0, 40.0]      # sigma and nu mix slower than beta
+    se = np.sqrt((s0 ** 2 + s1 ** 2) * tau / (iters - burn))
+    assert np.all(np.abs(m0 - m1) < 4 * se + 1e-3), (m0, m1, se)
+    np.testing.assert_allclose(s1, s0, rtol=0.2)
+    assert abs(m1[-2] - 1.5) < 0.2 and 2.5 < m1[-1] < 7.0      # sigma and nu near the truth
+    assert r["loglike_b200"] == pytest.approx(r["loglike_reference"], rel=1e-12)
+    assert r["suf_consistency"] < 1e-10
