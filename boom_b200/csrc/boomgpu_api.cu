@@ -103,8 +103,9 @@ struct boomgpu_ctx {
   // TMA descriptor of X for the single-pass kernel (re-encoded when the data or the tile shape change)
   struct XMap {
     CUtensorMap map;
-    const double *X = nullptr; int64_t n = -1, ldx = -1; int p = -1, box_cols = -1, box_rows = -1;
+    const double *X = nullptr; int64_t n = -1, ldx = -1; int p = -1, box_cols = -1, box_rows = -1, promo = -1;
   } xmap_small, xmap_syrk, xmap_sel;
+  int tma_promotion = 3;   // option: L2 promotion of the SYRK / panel tensor maps: 0 none, 1 64 B, 2 128 B, 3 256 B
 
   bool host_out_written = false;   // the last step's reduction wrote the statistics straight into suf_pin (zero copy)
 
@@ -370,8 +371,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int ensure_xmap(boomgpu_ctx *ctx, boomgpu_ctx::XMap &m, const double *X, int64_t ldx, int box_cols, int box_rows) {
-  if (m.X == X && m.n == ctx->n && m.ldx == ldx && m.p == ctx->p && m.box_cols == box_cols && m.box_rows == box_rows) return 0;
+int ensure_xmap(boomgpu_ctx *ctx, boomgpu_ctx::XMap &m, const double *X, int64_t ldx, int box_cols, int box_rows, int promo = 3) {
+  if (m.X == X && m.n == ctx->n && m.ldx == ldx && m.p == ctx->p && m.box_cols == box_cols && m.box_rows == box_rows && m.promo == promo) return 0;
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void *fn = nullptr;
@@ -385,11 +386,13 @@ int ensure_xmap(boomgpu_ctx *ctx, boomgpu_ctx::XMap &m, const double *X, int64_t
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
   CUresult r = encode(&m.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(X), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                      : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ctx, BOOMGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for n=%lld p=%d ldx=%lld box=%dx%d", (int)r,
                                      (long long)ctx->n, ctx->p, (long long)ldx, box_cols, box_rows);
-  m.X = X; m.n = ctx->n; m.ldx = ldx; m.p = ctx->p; m.box_cols = box_cols; m.box_rows = box_rows;
+  m.X = X; m.n = ctx->n; m.ldx = ldx; m.p = ctx->p; m.box_cols = box_cols; m.box_rows = box_rows; m.promo = promo;
   return 0;
 }
 
@@ -600,7 +603,7 @@ int launch_syrk(boomgpu_ctx *ctx, double *suf) {
   sp.filter = ctx->syrk_filter;
   sp.diag_form = ctx->syrk_diag;
   static const SyrkUnitTable table = make_unit_table();
-  if (int rc = ensure_xmap(ctx, ctx->xmap_syrk, ctx->Xt, ctx->ldxt, kSyrkPanelLd, kSyrkKB)) return rc;
+  if (int rc = ensure_xmap(ctx, ctx->xmap_syrk, ctx->Xt, ctx->ldxt, kSyrkPanelLd, kSyrkKB, ctx->tma_promotion)) return rc;
   CU(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmemBytes));
   {
     LaunchScope ls(ctx, 2);
@@ -684,12 +687,12 @@ int launch_panel(boomgpu_ctx *ctx, double *out, int *ka8_out) {
   pp.ksplit = (int)ksplit; pp.rows_per_slice = rows;
   if (ensure(ctx, &ctx->partials, &ctx->partials_cap, ksplit * pp.nblk * kPanelTileLen)) return BOOMGPU_ERR_CUDA;
   pp.partials = ctx->partials;
-  if (int rc = ensure_xmap(ctx, ctx->xmap_syrk, ctx->Xt, ctx->ldxt, kSyrkPanelLd, kSyrkKB)) return rc;
+  if (int rc = ensure_xmap(ctx, ctx->xmap_syrk, ctx->Xt, ctx->ldxt, kSyrkPanelLd, kSyrkKB, ctx->tma_promotion)) return rc;
   {   // the gathered matrix as a tensor {k columns, n rows}: the box is wider than k, the excess reads as zero
     boomgpu_ctx::XMap &m = ctx->xmap_sel;
     const int p_save = ctx->p;
     ctx->p = k;
-    const int rc = ensure_xmap(ctx, m, ctx->Xsel, ctx->sel_ld, 8 * nba + 4, kSyrkKB);
+    const int rc = ensure_xmap(ctx, m, ctx->Xsel, ctx->sel_ld, 8 * nba + 4, kSyrkKB, ctx->tma_promotion);
     ctx->p = p_save;
     if (rc) return rc;
   }
@@ -1186,6 +1189,7 @@ int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value) {
   if (!strcmp(name, "single_launch")) { ctx->single_launch = value != 0; return 0; }
   if (!strcmp(name, "syrk_diag")) { ctx->syrk_diag = value != 0; return 0; }
   if (!strcmp(name, "syrk_filter")) { ctx->syrk_filter = (int)value; return 0; }
+  if (!strcmp(name, "tma_promotion")) { ctx->tma_promotion = value < 0 || value > 3 ? 3 : (int)value; return 0; }
   if (!strcmp(name, "syrk_order")) { ctx->syrk_order = value < 0 || value > 2 ? 1 : (int)value; return 0; }
   if (!strcmp(name, "syrk_cluster")) {
     if (value < 0 || value > 16) return fail(ctx, BOOMGPU_ERR_ARG, "syrk_cluster must be in 0..16");
