@@ -383,6 +383,31 @@ fused_tma_kernel(const __grid_constant__ CUtensorMap xmap, RowData d, DrawParams
         done = true;
       }
     }
+    if (MODEL == kStudentT && RPL > 1 && prm.t_nu >= 1.0) {
+      // the Student-t weights of this lane's RPL observations: first attempts interleaved (draws.cuh: rgamma_philox_rows)
+      bool all_valid = true;
+#pragma unroll
+      for (int j = 0; j < RPL; ++j) all_valid = all_valid && valid[j];
+      if (__all_sync(0xffffffffu, all_valid)) {
+        uint64_t rows[RPL];
+        double rate[RPL];
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+          rows[j] = d.row_offset + (uint64_t)i[j];
+          const double delta = (obs[j].y - eta[j]) * prm.t_inv_sigma;
+          rate[j] = 0.5 * (prm.t_nu + delta * delta);
+        }
+        if (!rgamma_philox_rows<RPL>(0.5 * (prm.t_nu + 1.0), rate, prm.key, rows, wv)) atomicOr(err, 2);
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+          sv[j] = wv[j] * obs[j].y;
+          sc_count += 1.0; sc_ywy += sv[j] * obs[j].y; sc_sumw += wv[j]; sc_sumlogw += wv[j] > 1e-300 ? log_nobranch(wv[j]) : 0.0;
+          if (out.w) out.w[i[j]] = wv[j];
+          if (out.s) out.s[i[j]] = sv[j];
+        }
+        done = true;
+      }
+    }
     if (!done) {
 #pragma unroll
       for (int j = 0; j < RPL; ++j) {

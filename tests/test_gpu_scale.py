@@ -42,6 +42,10 @@ def test_c3_geometry_accumulate_and_step():
     assert normwise_err(xtx, rxtx) < 1e-12
     assert vec_err(xty, rxty) < 1e-12
     np.testing.assert_array_equal(xtx, xtx.T)
+    ctx.set_option("syrk_order", 2)        # C3's geometry under the paired-diagonal grid: (0,0)+(1,1) and (2,2)+(3,3 ragged)
+    xtx2, xty2 = ctx.accumulate(w, s)
+    assert normwise_err(xtx2, rxtx) < 1e-12 and vec_err(xty2, rxty) < 1e-12
+    ctx.set_option("syrk_order", 1)
     xtx, xty, ss = ctx.logit_step(beta, 10, seed=41, iteration=7)
     rxtx, rxty, rss, _ = H.logit_step_blocked(X, y, nt, beta, 10, mix, 41, 7)
     assert ss == rss == n
@@ -50,7 +54,7 @@ def test_c3_geometry_accumulate_and_step():
     ctx.close()
 
 
-@pytest.mark.parametrize("n,p", [(20_011, 520), (20_011, 1000), (6_007, 4000), (9_001, 2049)])
+@pytest.mark.parametrize("n,p", [(20_011, 520), (20_011, 1000), (6_007, 4000), (9_001, 2049), (12_345, 130), (15_000, 1600)])
 def test_wide_p_accumulate_and_step(n, p):
     """nblk = 5 / 8 / 32 / 17 column blocks with a ragged last block (p = 2049: ONE column in it); TMA tiles at column
     offsets >= 512; at p >= 1000 the p x p matrix also lands through the page-locked direct-copy path."""
@@ -73,6 +77,15 @@ def test_wide_p_accumulate_and_step(n, p):
     ctx.set_option("syrk_waves", 7)
     xtx0, xty0 = ctx.accumulate(w, s)
     assert normwise_err(xtx0, rxtx) < 1e-12 and vec_err(xty0, rxty) < 1e-12
+    # order 2: diagonal regions in pairs on one CTA (strip form on each of its two panels, a ragged last region through the
+    # zero columns TMA delivers; an odd last diagonal region alone), super-tiled region order
+    for waves in (30, 3):
+        ctx.set_option("syrk_order", 2)
+        ctx.set_option("syrk_waves", waves)
+        xtx0, xty0 = ctx.accumulate(w, s)
+        assert normwise_err(xtx0, rxtx) < 1e-12 and vec_err(xty0, rxty) < 1e-12
+        np.testing.assert_array_equal(xtx0, xtx0.T)
+    ctx.set_option("syrk_order", 1)
     ctx.set_option("syrk_waves", 30)
     del xtx, xtx0
     rxtx, rxty, rss, _ = H.logit_step_blocked(X, y, nt, beta, 10, mix, 43, 2)
