@@ -24,7 +24,8 @@ The JSON line's top level is the HEADLINE workload (default C3, the config BASEL
                 oracle/build_ref.sh) on this box's host cores, on a bounded row sample of the same workload
                 (kind "reference"), with all host threads and -- SURVEY 8 d3 -- with one worker; only if that binary
                 did not travel to the box: the oracle's C port, one thread (kind "port").  The same for --impl reference.
-  secondary     the other BASELINE.json configs under the same clock (value, ms_per_step, roofline, clocks each):
+  secondary     the other BASELINE.json configs under the same clock (value, ms_per_step, roofline, clocks each), the active-set
+                runs and the Student-t sibling (student_t):
                 N = 1: C1 (1000 iterations), C2, C5, C4;  N > 1: C4 and C5 (the multi-GPU configs).
                 plus c3_active_set / c4_active_set: the spike-and-slab configs with the active-set statistics option.
                 HBM-bound kernels also carry roofline.burst (the same kernel after a 2 s pause: the sustained figure runs
@@ -490,6 +491,69 @@ class Bench:
             out["e2e"] = e2e_out
         return out
 
+    # ---- the Student-t sibling: TRegressionSampler on y = x'beta + 1.5 t_4, n = 25 M, p = 16 (C5's per-GPU shape)
+    def run_student(self, steps, warmup, n=25_000_000, p=16):
+        import numpy as np
+
+        import boom_b200
+        from boom_b200 import distributed as shard
+        torch = self.torch
+        world, rank, dev = self.world, self.rank, self.dev
+        row0, row1 = shard.shard_range(n, world, rank)
+        rows = row1 - row0
+        g = torch.Generator(device=dev)
+        g.manual_seed(SEED + 7919 * (rank + 1))
+        X = torch.empty((rows, p), dtype=torch.float64, device=dev).normal_(generator=g)
+        X[:, 0] = 1.0
+        bt = torch.tensor(beta_true("poisson", p, 5), dtype=torch.float64, device=dev)
+        z = torch.empty(rows, dtype=torch.float64, device=dev).normal_(generator=g)
+        w = torch.empty(rows, dtype=torch.float64, device=dev).normal_(generator=g) ** 2
+        for _ in range(3):
+            w += torch.empty(rows, dtype=torch.float64, device=dev).normal_(generator=g) ** 2   # chi-square(4)
+        y = X @ bt + 1.5 * z / torch.sqrt(w / 4.0)
+        del z, w
+        model = boom_b200.TRegressionModel(p)
+        model.adopt_device_data(rows, X.data_ptr(), p, y.data_ptr())
+        smp = boom_b200.TRegressionSampler(model, boom_b200.MvnModel(np.zeros(p), 100.0 * np.eye(p)), boom_b200.ChisqModel(1.0, 1.0),
+                                           boom_b200.UniformModel(0.5, 60.0), boom_b200.RNG(SEED))
+        model.set_method(smp)
+        shard.attach(model, n, self.stream, dev, rank, world, native=True)
+        model.set_device_option("timing", 1)
+        for _ in range(warmup):
+            model.sample_posterior()
+        self.barrier()
+        model.kernel_timings(True)
+        launches0, evals0 = model.kernel_launches(), smp.likelihood_evaluations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(self.stream)
+        for _ in range(steps):
+            model.sample_posterior()
+        e1.record(self.stream)
+        self.barrier()
+        t1 = time.perf_counter()
+        dev_ms = self.max_over_ranks(e0.elapsed_time(e1))
+        tm = model.kernel_timings(False)
+        per = {k: (v[0] / max(v[1], 1), v[1]) for k, v in tm.items()}
+        k_ms = per["fused_small"][0]
+        nbytes = 8.0 * rows * (p + 2)
+        roof = {"kernel": "fused_tma_kernel<kStudentT>", "bound": "hbm", "achieved": nbytes / (k_ms * 1e-3) * 1e-9, "peak": self.peaks["hbm_gbs"],
+                "unit": "GB/s", "peak_source": self.peak_src, "algorithmic_bytes_per_launch": nbytes, "kernel_ms": k_ms,
+                "kernel_ms_per_step": {k: round(v[0] * v[1] / steps, 4) for k, v in per.items() if v[1]}}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        out = {"value": steps / (dev_ms * 1e-3), "unit": "iter/s", "steps": steps, "warmup": warmup, "ms_per_step": dev_ms / steps,
+               "config": {"workload": "TRegressionSampler (Student-t sibling, SURVEY 8 f4) n=%d p=%d, y = x'beta + 1.5 t_4" % (n, p), "n": n, "p": p,
+                          "prior": "beta ~ N(0, 100 I), 1/sigma^2 ~ ChisqModel(1, 1), nu ~ U(0.5, 60)",
+                          "iteration": "weights + WeightedRegSuf on the device (one pass over X), beta and sigma^2 on the host, nu by the slice "
+                                       "sampler over the device log likelihood (one residual pass over X, then 8 n bytes per candidate nu)"},
+               "obs_per_sec": steps / (dev_ms * 1e-3) * n, "gpu_launches": int(model.kernel_launches() - launches0) * world,
+               "likelihood_evaluations_per_iteration": (smp.likelihood_evaluations - evals0) / steps,
+               "clocks": self.clocks.window(t0, t1) if self.clocks else None, "roofline": roof,
+               "posterior_draw_at_end": {"sigma": float(model.sigma), "nu": float(model.nu)}}
+        del model, smp, X, y
+        torch.cuda.empty_cache()
+        return out
+
     # ---- N > 1: the sharded statistics against ONE context holding all rows, and a short chain against the one-GPU chain
     def selftest(self, name):
         import numpy as np
@@ -689,6 +753,8 @@ def main():
         # the optional active-set form of the spike-and-slab configs: same chain, fewer flops
         secondary["c3_active_set"] = b.run("c3", 20, 25, e2e=False, active=True)
         secondary["c4_active_set"] = b.run("c4", 10, 45, e2e=False, active=True)
+        # the Student-t sibling
+        secondary["student_t"] = b.run_student(20, 5)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_block(kind, sampler, n, p, nonzero)

@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _HOST_NAMES = (
     "RNG", "global_rng", "MvnModel", "MvnBase", "VariableSelectionPrior", "BinomialLogitModel", "PoissonRegressionModel",
     "PosteriorSampler", "BinomialLogitAuxmixSampler", "BinomialLogitSpikeSlabSampler", "PoissonRegressionAuxMixSampler",
-    "PoissonRegressionSpikeSlabSampler", "BinomialProbitModel", "BinomialProbitSpikeSlabSampler", "TRegressionModel", "TRegressionSampler",
+    "PoissonRegressionSpikeSlabSampler", "BinomialProbitModel", "BinomialProbitSpikeSlabSampler", "TRegressionModel", "TRegressionSampler", "TRegressionSpikeSlabSampler",
     "DoubleModel", "UniformModel", "GammaModelBase", "GammaModel", "ChisqModel", "WeightedRegSuf", "set_logit_mixture", "set_poisson_mixture_table",
 )
 

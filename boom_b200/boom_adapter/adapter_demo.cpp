@@ -4,7 +4,7 @@
 // then attaches EITHER the reference sampler OR the B200 sampler with model->set_method(sampler) and calls
 // model->sample_posterior().  Prints one JSON line with the posterior summaries of both chains on the same
 // data; tests/test_gpu_adapter.py compares them within Monte Carlo error.
-//   usage: boom_adapter_demo <logit|spike|poisson|pspike|mode|pmode|fixed|pfixed|bench|api|composite|chunk|probit|treg|active|pactive> n p nonzero iters burn
+//   usage: boom_adapter_demo <logit|spike|poisson|pspike|mode|pmode|fixed|pfixed|bench|api|composite|chunk|probit|treg|tspike|active|pactive> n p nonzero iters burn
 //          (mode / pmode: find_posterior_mode; fixed / pfixed: externally driven statistics, host steps only, no GPU;
 //           bench: ms per iteration of the adapter beside the standalone classes; api: the public surface beyond draw())
 #include <chrono>
@@ -28,6 +28,7 @@
 #include "Models/Glm/PosteriorSamplers/PoissonRegressionSpikeSlabSampler.hpp"
 #include "Models/ChisqModel.hpp"
 #include "Models/Glm/PosteriorSamplers/TRegressionSampler.hpp"
+#include "Models/Glm/PosteriorSamplers/TRegressionSpikeSlabSampler.hpp"
 #include "Models/Glm/TRegression.hpp"
 #include "Models/Glm/VariableSelectionPrior.hpp"
 #include "Models/MvnModel.hpp"
@@ -269,6 +270,51 @@ int main(int argc, char **argv) {
       }
       printf("{\"kind\": \"probit\", \"n\": %d, \"p\": %d, \"iters\": %d, \"burn\": %d, ", n, p, iters, burn);
       print_vec("beta_true", beta);
+      print_summary("reference", out[0]); printf(", ");
+      print_summary("b200", out[1]);
+      printf("}\n");
+      return 0;
+    }
+    if (kind == "tspike") {
+      // TRegressionSpikeSlabSampler (lm.spike with Student errors) on BOOM's TRegressionModel: reference vs B200
+      Summary out[2];
+      std::vector<double> yt(n);
+      for (int i = 0; i < n; ++i) yt[i] = xs[i].dot(beta) + 1.5 * rnorm() / std::sqrt(rgamma(2.0, 2.0));
+      NEW(MvnModel, tslab)(Vector(p, 0.0), SpdMatrix(p, 4.0));
+      NEW(ChisqModel, siginv_prior)(1.0, 1.0);
+      NEW(UniformModel, nu_prior)(0.5, 60.0);
+      Vector sn_mean[2], sn_sd[2];
+      for (int arm = 0; arm < 2; ++arm) {
+        NEW(TRegressionModel, model)(p);
+        for (int i = 0; i < n; ++i) model->add_data(new RegressionData(yt[i], xs[i]));
+        model->coef().drop_all(); model->coef().add(0);
+        RNG seeder(arm == 0 ? 71 : 72);
+        Ptr<PosteriorSampler> sampler;
+        if (arm == 0) sampler = new TRegressionSpikeSlabSampler(model.get(), tslab, spike, siginv_prior, nu_prior, seeder);
+        else sampler = new B200::TRegressionSpikeSlabSampler(model.get(), tslab, spike, siginv_prior, nu_prior, seeder);
+        model->set_method(sampler);
+        Vector s1(p, 0.0), s2(p, 0.0), inc(p, 0.0), t1(2, 0.0), t2(2, 0.0);
+        auto t0 = std::chrono::steady_clock::now();
+        for (int it = 0; it < iters; ++it) {
+          model->sample_posterior();
+          if (it >= burn) {
+            const Vector &b(model->Beta());
+            for (int j = 0; j < p; ++j) { s1[j] += b[j]; s2[j] += b[j] * b[j]; inc[j] += model->coef().inc()[j]; }
+            const double v[2] = {model->sigma(), model->nu()};
+            for (int j = 0; j < 2; ++j) { t1[j] += v[j]; t2[j] += v[j] * v[j]; }
+          }
+        }
+        out[arm].secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const double m = iters - burn;
+        out[arm].mean = s1 / m; out[arm].sd = Vector(p); out[arm].inc = inc / m;
+        for (int j = 0; j < p; ++j) out[arm].sd[j] = std::sqrt(std::max(0.0, s2[j] / m - out[arm].mean[j] * out[arm].mean[j]));
+        sn_mean[arm] = t1 / m; sn_sd[arm] = Vector(2);
+        for (int j = 0; j < 2; ++j) sn_sd[arm][j] = std::sqrt(std::max(0.0, t2[j] / m - sn_mean[arm][j] * sn_mean[arm][j]));
+      }
+      printf("{\"kind\": \"tspike\", \"n\": %d, \"p\": %d, \"iters\": %d, \"burn\": %d, ", n, p, iters, burn);
+      print_vec("beta_true", beta);
+      print_vec("reference_sigma_nu_mean", sn_mean[0]); print_vec("reference_sigma_nu_sd", sn_sd[0]);
+      print_vec("b200_sigma_nu_mean", sn_mean[1]); print_vec("b200_sigma_nu_sd", sn_sd[1]);
       print_summary("reference", out[0]); printf(", ");
       print_summary("b200", out[1]);
       printf("}\n");

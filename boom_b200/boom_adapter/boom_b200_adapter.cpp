@@ -946,6 +946,53 @@ double TRegressionSampler::log_likelihood(const Vector &beta, double sigsq, doub
   return ll;
 }
 
+// ---- TRegressionSpikeSlabSampler
+TRegressionSpikeSlabSampler::TRegressionSpikeSlabSampler(TRegressionModel *model, const Ptr<MvnBase> &slab,
+                                                         const Ptr<VariableSelectionPrior> &spike, const Ptr<GammaModelBase> &siginv_prior,
+                                                         const Ptr<DoubleModel> &nu_prior, RNG &seeding_rng)
+    : TRegressionSampler(model, slab, siginv_prior, nu_prior, seeding_rng), spike_(spike), scaled_(model->xdim()) {
+  if ((int)spike_->potential_nvars() != model->xdim()) report_error("Prior does not match model dimension.");
+}
+const BOOM_B200::WeightedRegSuf &TRegressionSpikeSlabSampler::scaled_statistics() {
+  const int p = xdim_;
+  const double inv = 1.0 / model_->sigsq();
+  double *a = scaled_.xtx_storage(p), *b = scaled_.xty_storage();
+  const std::vector<double> &src(hsuf_.xtx().a);
+  for (size_t e = 0; e < (size_t)p * p; ++e) a[e] = src[e] * inv;
+  for (int j = 0; j < p; ++j) b[j] = hsuf_.xty()[j] * inv;
+  scaled_.set_scalars(hsuf_.n(), hsuf_.yty() * inv, hsuf_.sumw(), hsuf_.sumlogw());
+  return scaled_;
+}
+void TRegressionSpikeSlabSampler::draw() {   // TRegressionSpikeSlabSampler.cpp:41-47
+  impute_latent_data();
+  draw_model_indicators();
+  draw_included_coefficients();
+  draw_sigsq_full_conditional();
+  draw_nu_given_observed_data();
+}
+double TRegressionSpikeSlabSampler::logpri() const {   // .cpp:49-52
+  return spike_slab_logpri(model_->coef(), *coefficient_prior_, *spike_) + nu_prior_->logp(model_->nu()) +
+         siginv_prior_->logp(1.0 / model_->sigsq());
+}
+void TRegressionSpikeSlabSampler::draw_model_indicators() {
+  if (!allow_model_selection_) return;
+  BOOM_B200::SpikeSlabCore c(core(coefficient_prior_, spike_, true));
+  c.allow_model_selection(true);
+  c.limit_model_selection(max_flips_);
+  BOOM_B200::GlmCoefs h = host_coefs(model_->coef(), xdim_, true);
+  BOOM_B200::RNG local(rng().generator()());
+  c.draw_model_indicators(local, h, scaled_statistics());
+  write_back(model_->coef(), h, xdim_, false);
+  coefficients_changed();
+}
+void TRegressionSpikeSlabSampler::draw_included_coefficients() {
+  BOOM_B200::GlmCoefs h = host_coefs(model_->coef(), xdim_, false);
+  BOOM_B200::RNG local(rng().generator()());
+  core(coefficient_prior_, spike_, true).draw_beta(local, h, scaled_statistics());
+  write_back(model_->coef(), h, xdim_, true);
+  coefficients_changed();
+}
+
 // ---------------------------------------------------------------------------------------------
 PoissonRegressionAuxMixSampler::PoissonRegressionAuxMixSampler(PoissonRegressionModel *model, const Ptr<MvnBase> &prior, int,
                                                                RNG &seeding_rng)

@@ -8,6 +8,7 @@
 //   BOOM::BinomialLogitCompositeSpikeSlabSampler -> BOOM::B200::BinomialLogitCompositeSpikeSlabSampler  (what R's logit.spike builds)
 //   BOOM::BinomialProbitSpikeSlabSampler    -> BOOM::B200::BinomialProbitSpikeSlabSampler   (sibling)
 //   BOOM::TRegressionSampler                -> BOOM::B200::TRegressionSampler               (sibling)
+//   BOOM::TRegressionSpikeSlabSampler       -> BOOM::B200::TRegressionSpikeSlabSampler      (what lm.spike builds for Student errors)
 //   BOOM::PoissonRegressionAuxMixSampler    -> BOOM::B200::PoissonRegressionAuxMixSampler
 //   BOOM::PoissonRegressionSpikeSlabSampler -> BOOM::B200::PoissonRegressionSpikeSlabSampler
 //
@@ -383,13 +384,14 @@ class TRegressionSampler : public DeviceImputerBase {
   int device_loglike_derivs_selected_device(boomgpu_ctx *, const double *, double *) override;
   const Vector &current_beta() const override { return model_->Beta(); }
   void statistics_changed() override { suf_synced_ = false; }
-
- private:
-  double nu_log_posterior(double nu);
+  void coefficients_changed() { residuals_current_ = false; }
   TRegressionModel *model_;
   Ptr<MvnBase> coefficient_prior_;
   Ptr<GammaModelBase> siginv_prior_;
   Ptr<DoubleModel> nu_prior_;
+
+ private:
+  double nu_log_posterior(double nu);
   Ptr<ScaledChisqModel> weight_model_;
   GenericGaussianVarianceSampler sigsq_sampler_;
   ScalarSliceSampler nu_observed_data_sampler_, nu_complete_data_sampler_;
@@ -397,6 +399,28 @@ class TRegressionSampler : public DeviceImputerBase {
   mutable bool suf_synced_ = false;
   bool residuals_current_ = false;
   int64_t ll_evals_ = 0;
+};
+
+// TRegressionSpikeSlabSampler (Models/Glm/PosteriorSamplers/TRegressionSpikeSlabSampler.hpp:30-72): the Student-t sampler with the
+// coefficient draw replaced by the generic spike-and-slab steps at the model's residual variance.
+class TRegressionSpikeSlabSampler : public TRegressionSampler {
+ public:
+  TRegressionSpikeSlabSampler(TRegressionModel *model, const Ptr<MvnBase> &coefficient_slab_prior,
+                              const Ptr<VariableSelectionPrior> &coefficient_spike_prior, const Ptr<GammaModelBase> &siginv_prior,
+                              const Ptr<DoubleModel> &nu_prior, RNG &seeding_rng = GlobalRng::rng);
+  void draw() override;
+  double logpri() const override;
+  void draw_model_indicators();
+  void draw_included_coefficients();
+  void allow_model_selection(bool allow) { allow_model_selection_ = allow; }
+  void limit_model_selection(int max_flips) { max_flips_ = max_flips; }
+
+ private:
+  const BOOM_B200::WeightedRegSuf &scaled_statistics();   // X'WX / sigsq, X'Wy / sigsq (SpikeSlabSampler.cpp:131-134,188-193)
+  Ptr<VariableSelectionPrior> spike_;
+  BOOM_B200::WeightedRegSuf scaled_;
+  bool allow_model_selection_ = true;
+  int max_flips_ = -1;
 };
 
 class PoissonRegressionSpikeSlabSampler : public PoissonRegressionAuxMixSampler {

@@ -1832,7 +1832,7 @@ int boomgpu_student_loglike(boomgpu_ctx *ctx, const double *beta, double sigma, 
   const int p = ctx->p;
   const int64_t n = ctx->n;
   if (n == 0) { *loglike = 0.0; ctx->resid_valid = true; return 0; }   // sharded callers add their own shards
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sms * 8));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 1023) / 1024, (int64_t)ctx->sms * 8));
   if (ctx->resid_cap < n + grid + 8) ctx->resid_valid = false;
   if (!beta && !ctx->resid_valid) return fail(ctx, BOOMGPU_ERR_STATE, "boomgpu_student_loglike(beta = NULL) before a call with beta");
   if (int rc = ensure(ctx, &ctx->resid_buf, &ctx->resid_cap, n + grid + 8)) return rc;   // [residuals | per-CTA partials | result, n]
@@ -1852,9 +1852,20 @@ int boomgpu_student_loglike(boomgpu_ctx *ctx, const double *beta, double sigma, 
     RowData d;
     memset(&d, 0, sizeof(d));
     d.X = ctx->X; d.ldx = ctx->ldx; d.n = n; d.p = p; d.y = ctx->y;
-    const int rgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sms * 8));
     LaunchScope ls(ctx, 4);
-    residual_kernel<<<rgrid, 256, sizeof(double) * p, ctx->stream>>>(d, ctx->beta_dev, ctx->resid_buf);
+    if (p <= 128) {   // G lanes per row
+      const int rgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sms * 8));
+      const size_t sm = sizeof(double) * p;
+      if (p <= 1) residual_rows_kernel<1><<<rgrid, 256, sm, ctx->stream>>>(d, ctx->beta_dev, ctx->resid_buf);
+      else if (p <= 2) residual_rows_kernel<2><<<rgrid, 256, sm, ctx->stream>>>(d, ctx->beta_dev, ctx->resid_buf);
+      else if (p <= 4) residual_rows_kernel<4><<<rgrid, 256, sm, ctx->stream>>>(d, ctx->beta_dev, ctx->resid_buf);
+      else if (p <= 8) residual_rows_kernel<8><<<rgrid, 256, sm, ctx->stream>>>(d, ctx->beta_dev, ctx->resid_buf);
+      else if (p <= 16) residual_rows_kernel<16><<<rgrid, 256, sm, ctx->stream>>>(d, ctx->beta_dev, ctx->resid_buf);
+      else residual_rows_kernel<32><<<rgrid, 256, sm, ctx->stream>>>(d, ctx->beta_dev, ctx->resid_buf);
+    } else {
+      const int rgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sms * 8));
+      residual_kernel<<<rgrid, 256, sizeof(double) * p, ctx->stream>>>(d, ctx->beta_dev, ctx->resid_buf);
+    }
   }
   {
     LaunchScope ls(ctx, 4);
@@ -1862,7 +1873,7 @@ int boomgpu_student_loglike(boomgpu_ctx *ctx, const double *beta, double sigma, 
   }
   {
     LaunchScope ls(ctx, 3);
-    reduce_sum_kernel<<<1, 32, 0, ctx->stream>>>(parts, grid, parts + grid);
+    reduce_sum_warp_kernel<<<1, 32, 0, ctx->stream>>>(parts, grid, parts + grid);
   }
   CU(cudaGetLastError());
   // [row part | n]: both sum over the shards

@@ -1246,7 +1246,9 @@ __global__ void __launch_bounds__(256) loglike_kernel(RowData d, const double *_
   }
 }
 
-// Student-t sibling: residuals e_i = y_i - x_i'beta (warp per row) ...
+// Student-t sibling: residuals e_i = y_i - x_i'beta.  Two forms: a warp per row (wide rows), and for p <= 128 G lanes per row
+// with several row groups in flight (at p = 16 the warp-per-row form leaves half the lanes idle and serialises one load latency
+// per row: 3 ms per 25 M rows; a lane per row thrashes L1 with its 128-byte stride: 2.9 ms).
 __global__ void __launch_bounds__(256) residual_kernel(RowData d, const double *__restrict__ beta, double *__restrict__ resid) {
   extern __shared__ __align__(128) double smem[];
   double *beta_s = smem;
@@ -1263,25 +1265,82 @@ __global__ void __launch_bounds__(256) residual_kernel(RowData d, const double *
   }
 }
 
+// G lanes per row (G = the power of two >= min(p, 32)): a warp instruction reads 32 / G consecutive rows -- one contiguous
+// stretch of X when ldx == p -- and the group's partial products meet in log2(G) shuffles; U row groups in flight per warp.
+template <int G>
+__global__ void __launch_bounds__(256) residual_rows_kernel(RowData d, const double *__restrict__ beta, double *__restrict__ resid) {
+  extern __shared__ __align__(128) double smem[];
+  double *beta_s = smem;
+  const int tid = threadIdx.x, lane = tid & 31, p = d.p;
+  for (int j = tid; j < p; j += 256) beta_s[j] = beta[j];
+  __syncthreads();
+  constexpr int RPW = 32 / G, U = 8;      // rows per warp instruction, row groups in flight
+  const int sub = lane / G, col0 = lane % G;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (tid >> 5), nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t base = warp * (RPW * U); base < d.n; base += nwarps * (RPW * U)) {
+    double e[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + u * RPW + sub;
+      e[u] = 0.0;
+      if (i < d.n) {
+        const double *xr = d.X + i * d.ldx;
+        for (int j = col0; j < p; j += G) e[u] = fma(__ldg(xr + j), beta_s[j], e[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) e[u] += __shfl_xor_sync(0xffffffffu, e[u], o);
+      const int64_t i = base + u * RPW + sub;
+      if (col0 == 0 && i < d.n) resid[i] = __ldg(d.y + i) - e[u];
+    }
+  }
+}
+
 // ... and the part of the observed-data log likelihood that depends on the rows, from the stored residuals:
-// sum_i -(nu + 1)/2 log1p(e_i^2 / (nu sigma^2)).  The slice sampler on nu (TRegressionSampler::draw_nu_given_observed_data,
+// sum_i -(nu + 1)/2 log(1 + e_i^2 / (nu sigma^2)).  The slice sampler on nu (TRegressionSampler::draw_nu_given_observed_data,
 // TRegressionSampler.cpp:173-176 over TRegressionModel::log_likelihood, TRegression.cpp:74-86) evaluates it several times per
-// draw with beta and sigma fixed: 8 n bytes per evaluation instead of a pass over X.  Fixed-order partials.
+// draw with beta and sigma fixed: 8 n bytes per evaluation instead of a pass over X.  Four independent chains per thread; fixed
+// assignment of rows to threads and fixed-order partials (deterministic).  log(1 + x) by the branch-free logarithm: its
+// absolute error per term is that of log1p, and the terms are summed.
 __global__ void __launch_bounds__(256) student_loglike_kernel(const double *__restrict__ resid, int64_t n, double inv_sigma, double nu,
                                                               double *__restrict__ partials) {
   __shared__ double red_s[8];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  double acc = 0;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + tid; i < n; i += (int64_t)gridDim.x * 256)
-    acc += student_log_kernel(__ldg(resid + i) * inv_sigma, nu);
-  acc = warp_sum(acc);
-  if (lane == 0) red_s[wid] = acc;
+  const double inv_nu = 1.0 / nu;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t i0 = (int64_t)blockIdx.x * 256 + tid; i0 < n; i0 += 4 * stride) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n) {
+        const double delta = __ldg(resid + i) * inv_sigma;
+        const double arg = fma(delta * delta, inv_nu, 1.0);
+        acc[u] += arg < 1e300 ? log_nobranch(arg) : log(arg);   // overflow / NaN residuals take the library's special cases
+      }
+    }
+  }
+  double a = -0.5 * (nu + 1.0) * ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+  a = warp_sum(a);
+  if (lane == 0) red_s[wid] = a;
   __syncthreads();
   if (tid == 0) {
     double s = 0;
     for (int w = 0; w < 8; ++w) s += red_s[w];
     partials[blockIdx.x] = s;
   }
+}
+
+// fixed-order sum of up to a few thousand partials by one warp: lane l sums its contiguous chunk, the lanes combine in a fixed tree
+__global__ void reduce_sum_warp_kernel(const double *__restrict__ partials, int nparts, double *__restrict__ dst) {
+  const int lane = threadIdx.x;
+  const int chunk = (nparts + 31) / 32;
+  double s = 0;
+  for (int c = lane * chunk; c < min(nparts, (lane + 1) * chunk); ++c) s += partials[c];
+  s = warp_sum(s);
+  if (lane == 0) dst[0] = s;
 }
 
 // X's alone (the probit sibling: X'WX does not change from one iteration to the next, only X'z does): thread t owns column

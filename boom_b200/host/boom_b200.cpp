@@ -1762,6 +1762,45 @@ void TRegressionSampler::draw_beta_full_conditional() {   // draw_beta_full_cond
   model_->set_Beta(rmvn_suf_mt(rng(), precision, scaled_mean));
   residuals_current_ = false;
 }
+
+// ---- TRegressionSpikeSlabSampler ---------------------------------------------------------------
+TRegressionSpikeSlabSampler::TRegressionSpikeSlabSampler(TRegressionModel *model, const std::shared_ptr<MvnBase> &slab,
+                                                         const std::shared_ptr<VariableSelectionPrior> &spike,
+                                                         const std::shared_ptr<GammaModelBase> &siginv_prior,
+                                                         const std::shared_ptr<DoubleModel> &nu_prior, RNG &seeding_rng)
+    : TRegressionSampler(model, slab, siginv_prior, nu_prior, seeding_rng), core_(slab, spike, true), scaled_(model ? model->xdim() : 0) {
+  if (!spike || spike->potential_nvars() != model->xdim()) report_error("Prior does not match model dimension.");
+}
+const WeightedRegSuf &TRegressionSpikeSlabSampler::scaled_statistics() {
+  const int p = model_->xdim();
+  const double inv = 1.0 / model_->sigsq();
+  double *a = scaled_.xtx_storage(p), *b = scaled_.xty_storage();
+  const Vector &src(suf_.xtx().a);
+  for (size_t e = 0; e < (size_t)p * p; ++e) a[e] = src[e] * inv;
+  for (int j = 0; j < p; ++j) b[j] = suf_.xty()[j] * inv;
+  scaled_.set_scalars(suf_.n(), suf_.yty() * inv, suf_.sumw(), suf_.sumlogw());
+  return scaled_;
+}
+void TRegressionSpikeSlabSampler::draw() {
+  impute_latent_data();
+  draw_model_indicators();
+  draw_included_coefficients();
+  draw_sigsq_full_conditional();
+  draw_nu_given_observed_data();
+}
+double TRegressionSpikeSlabSampler::logpri() const {
+  return core_.logpri(model_->coef()) + nu_prior_->logp(model_->nu()) + siginv_prior_->logp(1.0 / model_->sigsq());
+}
+void TRegressionSpikeSlabSampler::draw_model_indicators() {
+  core_.draw_model_indicators(rng(), model_->coef(), scaled_statistics());
+  coefficients_changed();
+}
+void TRegressionSpikeSlabSampler::draw_included_coefficients() {
+  core_.draw_beta(rng(), model_->coef(), scaled_statistics());
+  coefficients_changed();
+}
+double TRegressionSpikeSlabSampler::log_model_prob(const Selector &g) { return core_.log_model_prob(g, scaled_statistics()); }
+
 void TRegressionSampler::draw_sigsq_full_conditional() {   // .cpp:165-171; SSE = y'Wy - 2 b'X'Wy + b'X'WXb (WeightedRegressionModel.cpp:89-95)
   const int p = model_->xdim();
   const Vector &b(model_->Beta());

@@ -824,18 +824,42 @@ class TRegressionSampler : public PosteriorSampler {
 
  protected:
   void on_seed() override;
-
- private:
+  void coefficients_changed() { residuals_current_ = false; }
   TRegressionModel *model_;
   std::shared_ptr<MvnBase> coefficient_prior_;
   std::shared_ptr<GammaModelBase> siginv_prior_;
   std::shared_ptr<DoubleModel> nu_prior_;
   WeightedRegSuf suf_;                  // its sumw / sumlogw / n are the weight model's GammaSuf as well
+
+ private:
   GenericGaussianVarianceSampler sigsq_sampler_;
   ScalarSliceSampler nu_observed_, nu_complete_;
   bool latent_data_fixed_ = false, residuals_current_ = false;
   uint64_t device_seed_, iteration_ = 0;
   Vector packed_;
+};
+
+// TRegressionSpikeSlabSampler (Models/Glm/PosteriorSamplers/TRegressionSpikeSlabSampler.{hpp,cpp}; what BoomSpikeSlab's lm.spike
+// builds for Student errors): TRegressionSampler with the coefficient draw replaced by the generic spike-and-slab steps
+// (SpikeSlabSampler.cpp:40-216) at the model's residual variance -- sigsq enters them only as X'WX / sigsq, X'Wy / sigsq.
+class TRegressionSpikeSlabSampler : public TRegressionSampler {
+ public:
+  TRegressionSpikeSlabSampler(TRegressionModel *model, const std::shared_ptr<MvnBase> &coefficient_slab_prior,
+                              const std::shared_ptr<VariableSelectionPrior> &coefficient_spike_prior,
+                              const std::shared_ptr<GammaModelBase> &siginv_prior, const std::shared_ptr<DoubleModel> &nu_prior,
+                              RNG &seeding_rng = GlobalRng::rng);
+  void draw() override;                 // .cpp:41-47
+  double logpri() const override;       // .cpp:49-52
+  void draw_model_indicators();
+  void draw_included_coefficients();
+  void allow_model_selection(bool allow) { core_.allow_model_selection(allow); }
+  void limit_model_selection(int max_flips) { core_.limit_model_selection(max_flips); }
+  double log_model_prob(const Selector &g);
+
+ private:
+  const WeightedRegSuf &scaled_statistics();   // X'WX / sigsq, X'Wy / sigsq at the model's current sigsq
+  SpikeSlabCore core_;
+  WeightedRegSuf scaled_;
 };
 
 // The logit mixture every BinomialLogit sampler uploads; defaults to the 9-component table of

@@ -323,6 +323,23 @@ PYBIND11_MODULE(_host, m) {
                              py::return_value_policy::reference_internal)
       .def_property_readonly("likelihood_evaluations", &TRegressionSampler::likelihood_evaluations);
 
+  py::class_<TRegressionSpikeSlabSampler, TRegressionSampler, std::shared_ptr<TRegressionSpikeSlabSampler>>(m, "TRegressionSpikeSlabSampler")
+      .def(py::init([](TRegressionModel *model, const std::shared_ptr<MvnBase> &slab, const std::shared_ptr<VariableSelectionPrior> &spike,
+                       const std::shared_ptr<GammaModelBase> &siginv_prior, const std::shared_ptr<DoubleModel> &nu_prior, RNG &rng) {
+             return std::make_shared<TRegressionSpikeSlabSampler>(model, slab, spike, siginv_prior, nu_prior, rng);
+           }),
+           py::arg("model"), py::arg("coefficient_slab_prior"), py::arg("coefficient_spike_prior"), py::arg("siginv_prior"),
+           py::arg("nu_prior"), py::arg("seeding_rng") = std::ref(GlobalRng::rng), py::keep_alive<1, 2>())
+      .def("draw_model_indicators", &TRegressionSpikeSlabSampler::draw_model_indicators)
+      .def("draw_included_coefficients", &TRegressionSpikeSlabSampler::draw_included_coefficients)
+      .def("allow_model_selection", &TRegressionSpikeSlabSampler::allow_model_selection)
+      .def("limit_model_selection", &TRegressionSpikeSlabSampler::limit_model_selection)
+      .def("log_model_prob", [](TRegressionSpikeSlabSampler &s, const std::vector<bool> &bits) {
+        Selector g((int)bits.size(), false);
+        for (size_t i = 0; i < bits.size(); ++i) if (bits[i]) g.add((int)i);
+        return s.log_model_prob(g);
+      });
+
   py::class_<PoissonRegressionAuxMixSampler, PosteriorSampler, std::shared_ptr<PoissonRegressionAuxMixSampler>>(
       m, "PoissonRegressionAuxMixSampler")
       .def(py::init([](PoissonRegressionModel *model, const std::shared_ptr<MvnBase> &prior, int nthreads, RNG &rng) {

@@ -34,6 +34,7 @@
 #include "Models/ChisqModel.hpp"
 #include "Models/Glm/PosteriorSamplers/TDataImputer.hpp"
 #include "Models/Glm/PosteriorSamplers/TRegressionSampler.hpp"
+#include "Models/Glm/PosteriorSamplers/TRegressionSpikeSlabSampler.hpp"
 #include "Models/Glm/TRegression.hpp"
 #include "Models/Glm/VariableSelectionPrior.hpp"
 #include "Models/UniformModel.hpp"
@@ -606,6 +607,34 @@ void golden_student(const std::string &dir) {
                    "\"beta_prior_variance\": 100.0, \"siginv_prior\": [1.0, 1.0], \"nu_prior\": [0.5, 60.0]}");
     j.arr("chain_beta_true", bt); j.arr("chain_beta_mean", mo.mean()); j.arr("chain_beta_sd", mo.sd());
     j.arr("chain_sigma_nu_mean", sn.mean()); j.arr("chain_sigma_nu_sd", sn.sd());
+  }
+  {
+    // TRegressionSpikeSlabSampler (what lm.spike builds for Student errors) on synth_student(n = 3000, p = 12, 3 non-zero slopes)
+    const int n = 3000, p = 12, iters = 8000, burn = 1000;
+    std::vector<double> bt;
+    Ptr<TRegressionModel> model = make_model(n, p, 3, 778, &bt);
+    NEW(MvnModel, slab)(Vector(p, 0.0), SpdMatrix(p, 4.0));
+    NEW(VariableSelectionPrior, spike)(p, 0.3);
+    NEW(ChisqModel, siginv_prior)(1.0, 1.0);
+    NEW(UniformModel, nu_prior)(0.5, 60.0);
+    model->coef().drop_all(); model->coef().add(0);
+    NEW(TRegressionSpikeSlabSampler, sampler)(model.get(), slab, spike, siginv_prior, nu_prior);
+    model->set_method(sampler);
+    Moments mo(p), inc(p), sn(2);
+    for (int it = 0; it < iters; ++it) {
+      model->sample_posterior();
+      if (it >= burn) {
+        mo.add(model->Beta());
+        Vector g(p); for (int k = 0; k < p; ++k) g[k] = model->coef().inc()[k] ? 1.0 : 0.0;
+        inc.add(g);
+        Vector v(2); v[0] = model->sigma(); v[1] = model->nu(); sn.add(v);
+      }
+    }
+    j.raw("spike_chain", "{\"n\": 3000, \"p\": 12, \"nonzero\": 3, \"seed\": 778, \"sigma_true\": 1.5, \"nu_true\": 4.0, \"iters\": 8000, \"burn\": 1000, "
+                         "\"slab_variance\": 4.0, \"prior_inclusion\": 0.3, \"siginv_prior\": [1.0, 1.0], \"nu_prior\": [0.5, 60.0]}");
+    j.arr("spike_chain_beta_true", bt); j.arr("spike_chain_beta_mean", mo.mean()); j.arr("spike_chain_beta_sd", mo.sd());
+    j.arr("spike_chain_inclusion", inc.mean());
+    j.arr("spike_chain_sigma_nu_mean", sn.mean()); j.arr("spike_chain_sigma_nu_sd", sn.sd());
   }
   write_file(dir + "/ref_student.json", j.str());
 }

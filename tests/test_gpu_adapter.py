@@ -164,3 +164,16 @@ def test_student_t_sibling_on_boom_models():
     assert abs(m1[-2] - 1.5) < 0.2 and 2.5 < m1[-1] < 7.0      # sigma and nu near the truth
     assert r["loglike_b200"] == pytest.approx(r["loglike_reference"], rel=1e-12)
     assert r["suf_consistency"] < 1e-10
+
+
+def test_student_t_spike_slab_on_boom_models():
+    """TRegressionSpikeSlabSampler (what lm.spike builds for Student errors) on BOOM's TRegressionModel: reference vs B200 --
+    inclusion probabilities, the coefficients of the strongly included variables, sigma and nu."""
+    iters, burn = 8000, 1000
+    r = _demo("tspike", 2500, 10, 3, iters, burn)
+    _agree(r, iters, burn, strong_only=True)
+    assert np.all(np.array(r["b200"]["inclusion"])[:4] > 0.9)
+    m0, m1 = np.array(r["reference_sigma_nu_mean"]), np.array(r["b200_sigma_nu_mean"])
+    s0, s1 = np.array(r["reference_sigma_nu_sd"]), np.array(r["b200_sigma_nu_sd"])
+    se = np.sqrt((s0 ** 2 + s1 ** 2) * 40.0 / (iters - burn))
+    assert np.all(np.abs(m0 - m1) < 4 * se + 1e-3), (m0, m1, se)

@@ -326,3 +326,86 @@ def test_active_set_statistics_under_sharding():
     assert np.array_equal(res[0][1] != 0, res[0][2] != 0)                    # same decisions as the full-statistics chain
     np.testing.assert_allclose(res[0][2], res[0][1], rtol=1e-7, atol=1e-9)
     assert res[0][3] >= 6
+
+
+def _student_worker(rank, world, uid, q):
+    sys.path.insert(0, ROOT)
+    import boom_b200
+    from boom_b200.distributed import shard_range
+    from oracle import oracle as O
+    try:
+        n, p = 30_011, 9
+        X, y, bt = O.synth_student(n, p, 3, 41)
+        row0, row1 = shard_range(n, world, rank)
+        # (1) the C ABI: all-reduced statistics and log likelihood (with beta, then from the stored residuals)
+        ctx = boom_b200.Context(rank)
+        ctx.upload_regression(X[row0:row1], y[row0:row1])
+        ctx.set_row_offset(row0)
+        ctx.comm_init(uid[0], world, rank)
+        xtwx, xtwy, sc = ctx.student_step(bt * 0.9, 1.4, 3.5, 31, 2)
+        ll1 = ctx.student_loglike(bt * 0.9, 1.4, 3.5)
+        ll2 = ctx.student_loglike(None, 1.1, 8.0)
+        ctx.comm_destroy()
+        ctx.close()
+        # (2) the sampler surface: the same chain on both ranks
+        model = boom_b200.TRegressionModel(X[row0:row1], y[row0:row1])
+        s = boom_b200.TRegressionSpikeSlabSampler(model, boom_b200.MvnModel(np.zeros(p), 4.0 * np.eye(p)),
+                                                  boom_b200.VariableSelectionPrior(p, 0.4), boom_b200.ChisqModel(1.0, 1.0),
+                                                  boom_b200.UniformModel(0.5, 60.0), boom_b200.RNG(19))
+        model.set_method(s)
+        model.set_device(rank)
+        model.set_row_offset(row0)
+        model.set_communicator(uid[1], world, rank)
+        chain = []
+        for _ in range(15):
+            model.sample_posterior()
+            chain.append(np.r_[model.Beta, model.sigsq, model.nu])
+        q.put((rank, xtwx, xtwy, sc, ll1, ll2, np.array(chain)))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, "FAIL: %r" % (e,), None, None, None, None, None))
+
+
+def test_student_t_sibling_under_sharding():
+    """The Student-t step and its log likelihood all-reduce natively (statistics and likelihood of ALL rows on every rank, equal
+    to one context holding all rows), and the sharded TRegressionSpikeSlabSampler chain is identical on both ranks and equal to
+    the one-GPU chain up to summation order."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    import boom_b200
+    from oracle import oracle as O
+    uid = [boom_b200.Context.comm_unique_id(), boom_b200.Context.comm_unique_id()]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_student_worker, args=(r, 2, uid, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted((q.get(timeout=600) for _ in procs), key=lambda t: t[0])
+    for pr in procs:
+        pr.join(timeout=60)
+    assert not isinstance(res[0][1], str) and not isinstance(res[1][1], str), res
+    for k in range(1, 7):
+        np.testing.assert_array_equal(res[0][k], res[1][k])
+    n, p = 30_011, 9
+    X, y, bt = O.synth_student(n, p, 3, 41)
+    one = boom_b200.Context(0)
+    one.upload_regression(X, y)
+    xtwx, xtwy, sc = one.student_step(bt * 0.9, 1.4, 3.5, 31, 2)
+    d = np.sqrt(np.diag(xtwx))
+    assert np.max(np.abs(res[0][1] - xtwx) / np.outer(d, d)) < 1e-12
+    np.testing.assert_allclose(res[0][2], xtwy, rtol=1e-11, atol=1e-9)
+    np.testing.assert_allclose(res[0][3], sc, rtol=1e-11)
+    assert res[0][4] == pytest.approx(one.student_loglike(bt * 0.9, 1.4, 3.5), rel=1e-12)
+    assert res[0][5] == pytest.approx(one.student_loglike(None, 1.1, 8.0), rel=1e-12)
+    one.close()
+    model = boom_b200.TRegressionModel(X, y)
+    s = boom_b200.TRegressionSpikeSlabSampler(model, boom_b200.MvnModel(np.zeros(p), 4.0 * np.eye(p)),
+                                              boom_b200.VariableSelectionPrior(p, 0.4), boom_b200.ChisqModel(1.0, 1.0),
+                                              boom_b200.UniformModel(0.5, 60.0), boom_b200.RNG(19))
+    model.set_method(s)
+    chain = []
+    for _ in range(15):
+        model.sample_posterior()
+        chain.append(np.r_[model.Beta, model.sigsq, model.nu])
+    np.testing.assert_allclose(res[0][6], np.array(chain), rtol=1e-6, atol=1e-8)

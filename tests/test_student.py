@@ -163,6 +163,50 @@ def test_host_full_conditionals_on_fixed_statistics():
     assert np.isfinite(lp)
 
 
+def test_spike_slab_steps_see_the_statistics_scaled_by_sigsq():
+    """TRegressionSpikeSlabSampler: SpikeSlabSampler::log_model_prob(gamma, suf, sigsq) (SpikeSlabSampler.cpp:176-199) =
+    log pi(gamma) + 1/2 log|Om_g| - 1/2 mu_g' Om_g mu_g - sum log diag chol(Om_g + X'WX_gg / sigsq)
+    + 1/2 |L^-1 (X'Wy_g / sigsq + Om_g mu_g)|^2, on externally supplied statistics (no device)."""
+    import boom_b200
+    p, n = 6, 400
+    X, y, _ = O.synth_student(n, p, 2, 23)
+    w = O.student_step(X, y, np.zeros(p), 1.0, 4.0, 3, 0)[3]
+    model = boom_b200.TRegressionModel(p)
+    mu0 = np.linspace(-0.2, 0.3, p)
+    slab = boom_b200.MvnModel(mu0, 2.0 * np.eye(p))
+    pi = np.array([0.9, 0.5, 0.3, 0.2, 0.4, 0.1])
+    spike = boom_b200.VariableSelectionPrior(pi)
+    s = boom_b200.TRegressionSpikeSlabSampler(model, slab, spike, boom_b200.GammaModel(2.0, 3.0), boom_b200.UniformModel(0.5, 60.0),
+                                              boom_b200.RNG(4))
+    s.fix_latent_data(True)
+    for i in range(n):
+        s.update_complete_data_sufficient_statistics(y[i], X[i], w[i])
+    xtx, xty = (X * w[:, None]).T @ X, X.T @ (w * y)
+    for sigsq in (0.6, 2.3):
+        model.sigsq = sigsq
+        for g in ([1, 0, 0, 0, 0, 0], [1, 1, 0, 1, 0, 0], [1, 1, 1, 1, 1, 1], [0, 0, 1, 0, 0, 1]):
+            g = np.array(g, dtype=bool)
+            om = np.eye(int(g.sum())) / 2.0
+            prec = om + xtx[np.ix_(g, g)] / sigsq
+            L = np.linalg.cholesky(prec)
+            S = np.linalg.solve(L, xty[g] / sigsq + om @ mu0[g])
+            want = (np.log(pi[g]).sum() + np.log1p(-pi[~g]).sum() + 0.5 * np.linalg.slogdet(om)[1] - 0.5 * mu0[g] @ om @ mu0[g]
+                    - np.log(np.diag(L)).sum() + 0.5 * S @ S)
+            assert s.log_model_prob(list(g)) == pytest.approx(want, rel=1e-12)
+    # the sweep and the coefficient draw run on those statistics and leave excluded coefficients at exactly zero
+    model.drop_all(); model.add(0)
+    incs = []
+    for _ in range(300):
+        s.draw_model_indicators(); s.draw_included_coefficients(); s.draw_sigsq_full_conditional()
+        incs.append(model.inc.copy())
+        assert np.all(model.Beta[~model.inc] == 0.0)
+    assert np.mean(incs, axis=0)[0] > 0.9 and np.isfinite(s.logpri())
+    s.allow_model_selection(False)
+    before = model.inc.copy()
+    s.draw_model_indicators()
+    assert np.array_equal(before, model.inc)
+
+
 # ------------------------------------------------------------------------------------------ GPU
 def _ctx(X, y, path=0):
     import boom_b200
@@ -310,3 +354,38 @@ def test_student_chain_matches_reference(golden):
             m.sample_posterior()
         return np.r_[m.Beta, m.sigsq, m.nu]
     assert np.array_equal(chain(5), chain(5)) and not np.array_equal(chain(5), chain(6))
+
+
+@pytest.mark.gpu
+def test_student_spike_slab_chain_matches_reference(golden):
+    """TRegressionSpikeSlabSampler through the drop-in surface against the reference's chain on the same data and priors:
+    inclusion probabilities, coefficients of the strongly included variables, sigma and nu."""
+    import boom_b200
+    g = golden("ref_student.json"); c = g["spike_chain"]
+    p = c["p"]
+    X, y, _ = O.synth_student(c["n"], p, c["nonzero"], c["seed"], c["sigma_true"], c["nu_true"])
+    model = boom_b200.TRegressionModel(X, y)
+    model.drop_all(); model.add(0)
+    sampler = boom_b200.TRegressionSpikeSlabSampler(model, boom_b200.MvnModel(np.zeros(p), c["slab_variance"] * np.eye(p)),
+                                                    boom_b200.VariableSelectionPrior(p, c["prior_inclusion"]),
+                                                    boom_b200.ChisqModel(*c["siginv_prior"]), boom_b200.UniformModel(*c["nu_prior"]),
+                                                    boom_b200.RNG(78))
+    model.set_method(sampler)
+    iters, burn = 5000, 800
+    betas, incs, sn = [], [], []
+    for it in range(iters):
+        model.sample_posterior()
+        if it >= burn:
+            betas.append(model.Beta.copy()); incs.append(model.inc.copy()); sn.append((model.sigma, model.nu))
+    betas, incs, sn = np.array(betas), np.array(incs, dtype=float), np.array(sn)
+    ref_inc = np.array(g["spike_chain_inclusion"])
+    assert np.max(np.abs(incs.mean(0) - ref_inc)) < 0.05
+    strong = ref_inc > 0.95
+    n_ref = c["iters"] - c["burn"]
+    rm, rs = np.array(g["spike_chain_beta_mean"]), np.array(g["spike_chain_beta_sd"])
+    se = np.sqrt(rs ** 2 * 10.0 / n_ref + betas.std(0) ** 2 * 10.0 / len(betas))
+    assert np.all(np.abs(betas.mean(0) - rm)[strong] < 4 * se[strong] + 1e-4)
+    np.testing.assert_allclose(betas.std(0)[strong], rs[strong], rtol=0.2)
+    rm2, rs2 = np.array(g["spike_chain_sigma_nu_mean"]), np.array(g["spike_chain_sigma_nu_sd"])
+    se2 = np.sqrt(rs2 ** 2 * 40.0 / n_ref + sn.std(0) ** 2 * 40.0 / len(sn))
+    assert np.all(np.abs(sn.mean(0) - rm2) < 4 * se2 + 1e-4)
