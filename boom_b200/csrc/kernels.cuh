@@ -1279,14 +1279,20 @@ __global__ void __launch_bounds__(256) residual_rows_kernel(RowData d, const dou
   const int64_t warp = (int64_t)blockIdx.x * 8 + (tid >> 5), nwarps = (int64_t)gridDim.x * 8;
   for (int64_t base = warp * (RPW * U); base < d.n; base += nwarps * (RPW * U)) {
     double e[U];
+    const double *xr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t i = base + u * RPW + sub;
+      const int64_t i = min(base + u * RPW + sub, d.n - 1);   // rows beyond n re-read the last row; their result is not stored
+      xr[u] = d.X + i * d.ldx;
       e[u] = 0.0;
-      if (i < d.n) {
-        const double *xr = d.X + i * d.ldx;
-        for (int j = col0; j < p; j += G) e[u] = fma(__ldg(xr + j), beta_s[j], e[u]);
-      }
+    }
+    for (int j = col0; j < p; j += G) {   // the U loads of one trip are independent: all in flight together
+      const double b = beta_s[j];
+      double x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) x[u] = __ldg(xr[u] + j);
+#pragma unroll
+      for (int u = 0; u < U; ++u) e[u] = fma(x[u], b, e[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
