@@ -86,6 +86,7 @@ struct boomgpu_ctx {
                                                    // 2 k-slice major over uniform work items (diagonal regions in pairs)
   SyrkItem *syrk_items = nullptr; int syrk_items_nblk = -1, syrk_nitems = 0;   // order 2: the work items of one k-slice
   int syrk_waves = 30;                             // CTAs per SM the split-K aims for
+  int syrk_rdiag = 1;                              // 1: the ragged last diagonal region runs in syrk_rdiag_kernel (strip form over its atom columns)
   int syrk_cluster = 0;                            // experiment: launch the SYRK with thread-block clusters of this many CTAs
   int gather = 0;                                  // option: 0 auto (sparse beta -> gather pass), 1 never, 2 whenever beta has a zero
   double *suf_dev = nullptr; int64_t suf_cap = 0;
@@ -602,10 +603,18 @@ int launch_syrk(boomgpu_ctx *ctx, double *suf) {
   sp.partials = ctx->partials;
   sp.filter = ctx->syrk_filter;
   sp.diag_form = ctx->syrk_diag;
+  // the ragged last diagonal region (p not a multiple of 128) in its own kernel, unless order 2 has paired it with its neighbour
+  const int rem_cols = ((ctx->p + 7) & ~7) - 128 * (sp.nblk - 1);
+  const int ragged_atoms = rem_cols < 128 ? rem_cols / 8 : 0;
+  const bool side = ragged_atoms > 0 && ctx->syrk_rdiag && kSyrkConsumerWarps == 8 && ctx->syrk_filter == 0 && ctx->syrk_diag == 0 &&
+                    !(sp.order == 2 && sp.nblk % 2 == 0);
+  // ... and, when that block is narrow (<= 12 atom columns; wider ones do as well in the balanced unit form), its off-diagonal regions
+  const bool side_off = side && sp.nblk > 1 && ragged_atoms <= 12 && sp.order != 2;
+  sp.skip_ragged_diag = side ? (side_off ? 3 : 1) : 0;
   static const SyrkUnitTable table = make_unit_table();
   if (int rc = ensure_xmap(ctx, ctx->xmap_syrk, ctx->Xt, ctx->ldxt, kSyrkPanelLd, kSyrkKB, ctx->tma_promotion)) return rc;
   CU(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmemBytes));
-  {
+  if (!(side && sp.nregions == 1)) {   // (64 < p < 128: the ragged diagonal region is the only one)
     LaunchScope ls(ctx, 2);
     const unsigned grid = (unsigned)(ksplit * per_slice);
     if (ctx->syrk_cluster > 1 && grid % (unsigned)ctx->syrk_cluster == 0) {
@@ -624,6 +633,23 @@ int launch_syrk(boomgpu_ctx *ctx, double *suf) {
     }
   }
   CU(cudaGetLastError());
+  if (side) {
+    LaunchScope ls(ctx, 2);
+    const unsigned grid = (unsigned)(ksplit * (side_off ? sp.nblk : 1));
+#define BOOMGPU_RDIAG(A_)                                                                                                   \
+  case A_:                                                                                                                  \
+    CU(cudaFuncSetAttribute(syrk_rdiag_kernel<A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmemBytes));      \
+    syrk_rdiag_kernel<A_><<<grid, kSyrkThreads, kSyrkSmemBytes, ctx->stream>>>(ctx->xmap_syrk.map, sp);                      \
+    break;
+    switch (ragged_atoms) {
+      BOOMGPU_RDIAG(1) BOOMGPU_RDIAG(2) BOOMGPU_RDIAG(3) BOOMGPU_RDIAG(4) BOOMGPU_RDIAG(5) BOOMGPU_RDIAG(6) BOOMGPU_RDIAG(7)
+      BOOMGPU_RDIAG(8) BOOMGPU_RDIAG(9) BOOMGPU_RDIAG(10) BOOMGPU_RDIAG(11) BOOMGPU_RDIAG(12) BOOMGPU_RDIAG(13) BOOMGPU_RDIAG(14)
+      BOOMGPU_RDIAG(15)
+      default: return fail(ctx, BOOMGPU_ERR_ARG, "internal: ragged diagonal region with %d atom columns", ragged_atoms);
+    }
+#undef BOOMGPU_RDIAG
+    CU(cudaGetLastError());
+  }
   {
     LaunchScope ls(ctx, 3);
     const int64_t total = (int64_t)sp.nregions * kSyrkTileLen;
@@ -1189,6 +1215,7 @@ int boomgpu_set_option(boomgpu_ctx *ctx, const char *name, int64_t value) {
   if (!strcmp(name, "single_launch")) { ctx->single_launch = value != 0; return 0; }
   if (!strcmp(name, "syrk_diag")) { ctx->syrk_diag = value != 0; return 0; }
   if (!strcmp(name, "syrk_filter")) { ctx->syrk_filter = (int)value; return 0; }
+  if (!strcmp(name, "syrk_rdiag")) { ctx->syrk_rdiag = value != 0; return 0; }
   if (!strcmp(name, "tma_promotion")) { ctx->tma_promotion = value < 0 || value > 3 ? 3 : (int)value; return 0; }
   if (!strcmp(name, "syrk_order")) { ctx->syrk_order = value < 0 || value > 2 ? 1 : (int)value; return 0; }
   if (!strcmp(name, "syrk_cluster")) {

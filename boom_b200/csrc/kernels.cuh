@@ -571,6 +571,8 @@ struct SyrkParams {
   int filter;        // profiling aid (option "syrk_filter"): 0 all regions, 1 off-diagonal regions only, 2 diagonal only
   int order;         // option "syrk_order": 1 off-diagonal regions first, diagonal regions last, 0 k-slice major,
                      // 2 k-slice major over UNIFORM work items (off-diagonal regions + PAIRS of diagonal regions), see SyrkItem
+  int skip_ragged_diag;           // bit 0: the ragged last diagonal region, bit 1: the off-diagonal regions of the ragged last column
+                                  // block are computed by syrk_rdiag_kernel: their CTAs of this grid exit
   const SyrkItem *items;          // order 2: the work items of one k-slice, in launch order (device memory)
   int nitems;
 };
@@ -920,6 +922,9 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap xmap, SyrkParams prm, SyrkU
                           : I * prm.nblk - I * (I - 1) / 2 + (J - I);   // row-by-row index over the upper triangle (region_to_blocks)
   const bool diag = (I == J);
   if (prm.filter && (prm.filter == 1) == diag) return;   // profiling aid: results are incomplete on purpose
+  if (prm.skip_ragged_diag && !pair && J == prm.nblk - 1 && ((prm.p + 7) & ~7) - 128 * J < 128 &&
+      (prm.skip_ragged_diag & (diag ? 1 : 2)))
+    return;   // syrk_rdiag_kernel's regions
   const int64_t row_begin = (int64_t)kslice * prm.rows_per_slice;
   const int64_t row_end = min(prm.n, row_begin + prm.rows_per_slice);
   const int nstages_total = row_end > row_begin ? (int)((row_end - row_begin + kSyrkKB - 1) / kSyrkKB) : 0;
@@ -1030,6 +1035,179 @@ syrk_dmma_kernel(const __grid_constant__ CUtensorMap xmap, SyrkParams prm, SyrkU
   // atoms of the warp's last unit inside X (1..4); earlier units of the warp are whole
   const int nm = t1 ? nmax1 : (t0 ? nmax0 : 4);
   syrk_dispatch_role(t0 * 100 + t1 * 10 + duty, nm, wc);
+}
+
+// =============================================================================================
+// The RAGGED diagonal region (the last column block when p is not a multiple of 128; the only region when 64 < p < 128) in
+// strip form over its A = ceil(cols / 8) < 16 atom columns.  The 128 x 128 machinery above deals units of 32 x 32 to 8 warps x 2
+// slots, so a region with few columns keeps most warps idle while the CTA still walks its rows at the pace of a full region
+// (p = 70 cost what p = 128 costs: 0.19 of the FP64 peak).  Here warp W owns atom rows W and A - 1 - W -- A + 1 atoms for every
+// busy warp, nothing loaded or multiplied beyond column 8 A -- so the region's time follows its size.  Same ring, same producer,
+// same partial-tile layout as syrk_dmma_kernel (one CTA per k-slice); the main grid's CTAs of this region exit at once.
+// =============================================================================================
+template <int W, int A>
+__device__ __forceinline__ void syrk_consume_rstrip(const SyrkWarpCtx &wc) {
+  constexpr int R1 = W, R2 = A - 1 - W;
+  constexpr bool kBusy = R1 <= R2, kTwo = R1 < R2;
+  constexpr int N1 = kBusy ? A - R1 : 1, N2 = kTwo ? A - R2 : 1;
+  const int lane = wc.lane;
+  double c1[N1][2], c2[N2][2], cx1 = 0.0, cx2 = 0.0;
+#pragma unroll
+  for (int n = 0; n < N1; ++n) c1[n][0] = c1[n][1] = 0.0;
+#pragma unroll
+  for (int n = 0; n < N2; ++n) c2[n][0] = c2[n][1] = 0.0;
+  const int off = lane >> 2;
+  for (int it = 0; it < wc.nstages_total; ++it) {
+    const int s = it % kSyrkStages;
+    const uint32_t phase = (it / kSyrkStages) & 1;
+    mbar_wait(wc.full_bar + s, phase);
+    if (kBusy) {
+      const double *stage = wc.smem + s * kSyrkStageDoubles;
+      const double *w_s = stage + 2 * kSyrkKB * kSyrkPanelLd;
+      const double *s_s = w_s + kSyrkKB;
+#pragma unroll
+      for (int kk = 0; kk < kSyrkKB / 4; ++kk) {
+        const int row = kk * 4 + (lane & 3);
+        const double wv = w_s[row], sv = s_s[row];
+        const double *xr = stage + row * kSyrkPanelLd + off;
+        double b[N1];
+#pragma unroll
+        for (int n = 0; n < N1; ++n) b[n] = xr[8 * (R1 + n)];
+        const double a1 = b[0] * wv;
+#pragma unroll
+        for (int n = 0; n < N1; ++n) dmma884(c1[n][0], c1[n][1], a1, b[n]);
+        cx1 = fma(b[0], sv, cx1);
+        if (kTwo) {
+          const double a2 = b[R2 - R1] * wv;
+#pragma unroll
+          for (int n = 0; n < N2; ++n) dmma884(c2[n][0], c2[n][1], a2, b[R2 - R1 + n]);
+          cx2 = fma(b[R2 - R1], sv, cx2);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(wc.empty_bar + s);
+  }
+  if (!kBusy) return;
+  double *tile = wc.tile;
+#pragma unroll
+  for (int n = 0; n < N1; ++n)
+    *reinterpret_cast<double2 *>(tile + (8 * R1 + off) * 128 + 8 * (R1 + n) + 2 * (lane & 3)) = make_double2(c1[n][0], c1[n][1]);
+  cx1 += __shfl_xor_sync(0xffffffffu, cx1, 1); cx1 += __shfl_xor_sync(0xffffffffu, cx1, 2);
+  if ((lane & 3) == 0) tile[128 * 128 + 8 * R1 + off] = cx1;
+  if (kTwo) {
+#pragma unroll
+    for (int n = 0; n < N2; ++n)
+      *reinterpret_cast<double2 *>(tile + (8 * R2 + off) * 128 + 8 * (R2 + n) + 2 * (lane & 3)) = make_double2(c2[n][0], c2[n][1]);
+    cx2 += __shfl_xor_sync(0xffffffffu, cx2, 1); cx2 += __shfl_xor_sync(0xffffffffu, cx2, 2);
+    if ((lane & 3) == 0) tile[128 * 128 + 8 * R2 + off] = cx2;
+  }
+}
+
+// An off-diagonal region (I, last) whose column block has only AB < 16 atom columns: warp W owns atom rows 2 W and 2 W + 1 of the
+// region and all AB columns -- 2 AB atoms for every warp whatever AB is (the unit form leaves warps idle and runs at the pace of a
+// full region: 32 atoms on the busiest warp).
+template <int AB>
+__device__ __forceinline__ void syrk_consume_cstrip(const SyrkWarpCtx &wc, int W) {
+  const int lane = wc.lane;
+  double c0[AB][2], c1[AB][2];
+#pragma unroll
+  for (int n = 0; n < AB; ++n) c0[n][0] = c0[n][1] = c1[n][0] = c1[n][1] = 0.0;
+  const int off = lane >> 2;
+  for (int it = 0; it < wc.nstages_total; ++it) {
+    const int s = it % kSyrkStages;
+    const uint32_t phase = (it / kSyrkStages) & 1;
+    mbar_wait(wc.full_bar + s, phase);
+    const double *stage = wc.smem + s * kSyrkStageDoubles;
+    const double *w_s = stage + 2 * kSyrkKB * kSyrkPanelLd;
+#pragma unroll
+    for (int kk = 0; kk < kSyrkKB / 4; ++kk) {
+      const int row = kk * 4 + (lane & 3);
+      const double wv = w_s[row];
+      const double *xa = stage + row * kSyrkPanelLd + off + 16 * W;
+      const double *xb = stage + kSyrkKB * kSyrkPanelLd + row * kSyrkPanelLd + off;
+      const double a0 = xa[0] * wv, a1 = xa[8] * wv;
+#pragma unroll
+      for (int n = 0; n < AB; ++n) {
+        const double b = xb[8 * n];
+        dmma884(c0[n][0], c0[n][1], a0, b);
+        dmma884(c1[n][0], c1[n][1], a1, b);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(wc.empty_bar + s);
+  }
+  double *tile = wc.tile;
+#pragma unroll
+  for (int n = 0; n < AB; ++n) {
+    *reinterpret_cast<double2 *>(tile + (16 * W + off) * 128 + 8 * n + 2 * (lane & 3)) = make_double2(c0[n][0], c0[n][1]);
+    *reinterpret_cast<double2 *>(tile + (16 * W + 8 + off) * 128 + 8 * n + 2 * (lane & 3)) = make_double2(c1[n][0], c1[n][1]);
+  }
+}
+
+// grid: k-slice major over the column blocks I = 0 .. nblk - 1 of the ragged last block column: I = nblk - 1 is the diagonal
+// region (strip form), I < nblk - 1 the off-diagonal regions (column-strip form; only when prm.skip_ragged_diag has bit 1)
+template <int A>
+__global__ void __launch_bounds__(kSyrkThreads, 1)
+syrk_rdiag_kernel(const __grid_constant__ CUtensorMap xmap, SyrkParams prm) {
+  extern __shared__ __align__(128) double smem[];
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kSyrkStages * kSyrkStageDoubles);
+  uint64_t *empty_bar = full_bar + kSyrkStages;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool with_offdiag = (prm.skip_ragged_diag & 2) != 0;
+  const int per = with_offdiag ? prm.nblk : 1;
+  const int kslice = (int)blockIdx.x / per, J = prm.nblk - 1;
+  const int I = with_offdiag ? (int)blockIdx.x - kslice * per : J;
+  const bool diag = I == J;
+  if (diag && !(prm.skip_ragged_diag & 1)) return;
+  const int region = I * prm.nblk - I * (I - 1) / 2 + (J - I);
+  const int64_t row_begin = (int64_t)kslice * prm.rows_per_slice;
+  const int64_t row_end = min(prm.n, row_begin + prm.rows_per_slice);
+  const int nstages_total = row_end > row_begin ? (int)((row_end - row_begin + kSyrkKB - 1) / kSyrkKB) : 0;
+  if (tid == 0) {
+    for (int s = 0; s < kSyrkStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, kSyrkConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  constexpr uint32_t kPanelBytes = kSyrkKB * kSyrkPanelLd * sizeof(double);
+  const uint32_t kStageBytes = (diag ? 1u : 2u) * kPanelBytes + 2 * kSyrkKB * 8;
+  if (wid >= kSyrkConsumerWarps) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    if (wid == kSyrkConsumerWarps) {
+      for (int it = 0; it < nstages_total; ++it) {
+        const int s = it % kSyrkStages;
+        const uint32_t phase = (it / kSyrkStages) & 1;
+        mbar_wait(empty_bar + s, phase ^ 1);
+        double *stage = smem + s * kSyrkStageDoubles;
+        const int64_t r0 = row_begin + (int64_t)it * kSyrkKB;
+        if (lane == 0) {
+          mbar_expect_tx(full_bar + s, kStageBytes);
+          tma_load_2d(stage, &xmap, 128 * I, (int)r0, full_bar + s);
+          if (!diag) tma_load_2d(stage + kSyrkKB * kSyrkPanelLd, &xmap, 128 * J, (int)r0, full_bar + s);
+          tma_bulk_g2s(stage + 2 * kSyrkKB * kSyrkPanelLd, prm.w + r0, kSyrkKB * 8, full_bar + s);
+          tma_bulk_g2s(stage + 2 * kSyrkKB * kSyrkPanelLd + kSyrkKB, prm.s + r0, kSyrkKB * 8, full_bar + s);
+        }
+      }
+    }
+    return;
+  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+  SyrkWarpCtx wc;
+  wc.smem = smem; wc.full_bar = full_bar; wc.empty_bar = empty_bar; wc.nstages_total = nstages_total;
+  wc.lane = lane;
+  wc.panelB_off = 0;
+  wc.tile = prm.partials + ((int64_t)kslice * prm.nregions + region) * kSyrkTileLen;
+  if (!diag) { syrk_consume_cstrip<A>(wc, wid); return; }
+  switch (wid) {
+    case 0: syrk_consume_rstrip<0, A>(wc); break;
+    case 1: syrk_consume_rstrip<1, A>(wc); break;
+    case 2: syrk_consume_rstrip<2, A>(wc); break;
+    case 3: syrk_consume_rstrip<3, A>(wc); break;
+    case 4: syrk_consume_rstrip<4, A>(wc); break;
+    case 5: syrk_consume_rstrip<5, A>(wc); break;
+    case 6: syrk_consume_rstrip<6, A>(wc); break;
+    default: syrk_consume_rstrip<7, A>(wc); break;
+  }
 }
 
 // =============================================================================================

@@ -20,6 +20,7 @@ CFG = {
     "p40": ("logit", 8_000_000, 40), "p48l": ("logit", 8_000_000, 48), "p56": ("logit", 8_000_000, 56), "p40p": ("poisson", 4_000_000, 40),
     "p64p": ("poisson", 4_000_000, 64), "c5m": ("logit", 100_000_000, 16), "c5f": ("logit", 200_000_000, 16), "c2x4": ("poisson", 4_000_000, 50),
     "t16": ("student", 25_000_000, 16), "t50": ("student", 4_000_000, 50), "t20": ("student", 100_000, 20), "t500": ("student", 1_000_000, 500),
+    "p70": ("logit", 8_000_000, 70), "p100": ("logit", 8_000_000, 100), "p200": ("logit", 4_000_000, 200), "p384": ("logit", 2_000_000, 384),
     "p8": ("logit", 25_000_000, 8), "p24": ("logit", 12_000_000, 24), "p48": ("poisson", 4_000_000, 48),
 }
 

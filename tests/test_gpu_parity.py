@@ -36,6 +36,25 @@ def test_accumulate_matches_oracle(n, p, path):
     ctx.close()
 
 
+@pytest.mark.parametrize("n,p", [(3000, 65), (3000, 72), (2500, 97), (2500, 120), (2000, 127), (2000, 192), (2000, 248), (1000, 385),
+                                 (1500, 456)])
+def test_ragged_diagonal_region_kernel(n, p):
+    """The ragged last diagonal region (p not a multiple of 128; the whole matrix for 64 < p < 128) runs in syrk_rdiag_kernel,
+    strip form over A = ceil((p mod 128) / 8) atom columns (A = 9, 9, 13, 15, 16 -> whole, 8, 15, 1, 9 here); the 128 x 128
+    unit form of the main kernel stays available (option syrk_rdiag = 0).  Both against the oracle."""
+    X = O.synth_x(n, p, seed=500 + p)
+    w, s = _latents(n, p)
+    ctx, _ = logit_ctx(X, np.zeros(n), np.ones(n))
+    ref_xtx, ref_xty = O.accumulate(X, w, s)
+    for rdiag in (1, 0):
+        ctx.set_option("syrk_rdiag", rdiag)
+        xtx, xty = ctx.accumulate(w, s)
+        assert normwise_err(xtx, ref_xtx) < TOL, rdiag
+        assert vec_err(xty, ref_xty) < TOL, rdiag
+        np.testing.assert_array_equal(xtx, xtx.T)
+    ctx.close()
+
+
 def test_accumulate_golden_fixture(golden):
     g = golden("suf.json")
     n, p = int(g["n"]), int(g["p"])
