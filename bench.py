@@ -401,9 +401,11 @@ class Bench:
                     "unit": "GB/s", "peak_source": self.peak_src, "algorithmic_bytes_per_launch": nbytes,
                     "columns_fetched_in_timed_region": int(smp.active_set_columns_fetched)}
         elif p > 64:
-            k_ms = per["syrk_dmma"][0]
+            # the SYRK of one step: the main grid + (p not a multiple of 128) the launch for the ragged last block column
+            k_ms = per["syrk_dmma"][0] * per["syrk_dmma"][1] / steps
             flops = float(my_rows) * p * (p + 1) + 2.0 * my_rows * p   # weighted SYRK (upper triangle) + X'Wz, FMA = 2
-            roof = {"kernel": "syrk_dmma_kernel", "bound": "tensor", "achieved": flops / (k_ms * 1e-3) * 1e-12,
+            roof = {"kernel": "syrk_dmma_kernel", "launches_per_step": per["syrk_dmma"][1] / steps,
+                    "bound": "tensor", "achieved": flops / (k_ms * 1e-3) * 1e-12,
                     "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "peak_source": "FP64 DMMA issue-rate microbenchmark on this pool "
                     "(profiles/r01_microbench_fp64.jsonl; cuBLAS DGEMM 8192^3 = 35.4); MEASURED_PEAKS.json has no FP64 entry",
                     "algorithmic_flops_per_launch": flops}

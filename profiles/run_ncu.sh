@@ -7,7 +7,7 @@ set -uo pipefail
 TAG=${1:-r01}
 mkdir -p gpurun_out
 # only this library's kernels are profiled (torch's data-generation kernels run unprofiled, at full speed)
-OURS="fused_small|fused_tma|fused_ws|impute_rows|syrk_dmma|panel_dmma|reduce_|loglike|xts_|select_columns|weight_column|counts_present"
+OURS="fused_small|fused_tma|fused_ws|impute_rows|syrk_dmma|syrk_rdiag|panel_dmma|reduce_|loglike|residual|xts_|select_columns|weight_column|counts_present"
 BENCH="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-secondary"
 BENCH5="python bench.py --workload c5 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-secondary"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$OURS" --csv --log-file gpurun_out/${TAG}_launches_c3.csv $BENCH \
