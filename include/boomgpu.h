@@ -82,7 +82,11 @@ int boomgpu_set_row_offset(boomgpu_ctx *ctx, uint64_t first_global_row);
  *          "gather" = 0 auto (two-pass path: a beta with fewer than p / 4 non-zeros reads only those columns of X in the
  *                     imputer pass) | 1 never | 2 whenever beta has a zero;
  *          "syrk_order" = 1 (default) the split-K SYRK's off-diagonal regions are scheduled first and the cheaper diagonal
- *                         regions last | 0 k-slice major; "syrk_waves" = CTAs per SM the split-K aims for (default 30);
+ *                         regions last | 0 k-slice major | 2 k-slice major over uniform work items (diagonal regions in pairs on
+ *                         one CTA: less DRAM traffic with short CTAs, 1 % slower); "syrk_waves" = CTAs per SM the split-K aims
+ *                         for (default 30); "syrk_rdiag" = 1 (default) the ragged last column block (p not a multiple of 128)
+ *                         runs in its own strip-form kernel | 0 in the main kernel's 128 x 128 unit form;
+ *          "tma_promotion" = 3 (default; 0 none, 1 64 B, 2 128 B, 3 256 B): L2 promotion of the SYRK's tensor map;
  *          "syrk_diag" = 0 (default) strip form for whole diagonal regions | 1 unit form; "syrk_filter": profiling aid;
  *          "syrk_cluster" = c > 1: launch the SYRK with thread-block clusters of c CTAs (experiment; measured slower);
  *          "timing" = 1 records CUDA events around every kernel (boomgpu_get_timings) */
