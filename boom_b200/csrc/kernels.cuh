@@ -9,6 +9,10 @@
 //   syrk_dmma_kernel     p  > 64 : pass 2, split-K weighted SYRK  X' diag(w) X  (upper triangle) and
 //                        X's on FP64 DMMA (mma.sync m8n8k4), X tiles staged by TMA tensor tiles
 //                        (cp.async.bulk.tensor.2d + mbarrier) through a 6-stage ring.  FP64-pipe-bound.
+//   syrk_rdiag_kernel    p  > 64 and p not a multiple of 128: the regions of the ragged last column block, in strip forms
+//                        whose work follows the block's width (same ring, same partial tiles).
+//   panel_dmma_kernel    active-set statistics: X' diag(w) X_A for the included columns, one pass over X.
+//   residual_*_kernel, student_loglike_kernel   the Student-t sibling's observed-data log likelihood (nu draw).
 //   reduce_* kernels     deterministic (fixed order) reduction of the per-CTA partials.
 //
 // The reference equivalent of all of this is the per-observation loop
