@@ -585,7 +585,10 @@ int launch_syrk(boomgpu_ctx *ctx, double *suf) {
     sp.items = ctx->syrk_items; sp.nitems = ctx->syrk_nitems;
     per_slice = sp.nitems;
   }
-  int64_t ksplit = (ctx->syrk_waves * (int64_t)ctx->sms + per_slice - 1) / per_slice;
+  // one region (64 < p <= 128): uniform CTAs need no fine split for balance, and every k-slice costs a partial tile to write and
+  // to sum -- 4 CTAs per SM instead of 30 (run 55: p = 70 / 100 / 128 3.26 / 4.68 / 2.79 -> 2.67 / 4.04 / 2.43 ms)
+  const int waves = sp.nregions == 1 ? std::min(ctx->syrk_waves, 4) : ctx->syrk_waves;
+  int64_t ksplit = (waves * (int64_t)ctx->sms + per_slice - 1) / per_slice;
   if (sp.order == 2) {
     // uniform CTAs: a grid that is a whole number of waves has no tail at all
     const int64_t unit = ctx->sms / std::gcd((int64_t)ctx->sms, (int64_t)per_slice);
