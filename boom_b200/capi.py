@@ -28,7 +28,7 @@ SYMBOLS = (
     "boomgpu_poisson_loglike_derivs_selected", "boomgpu_binomial_loglike_derivs_selected_device", "boomgpu_pin_host", "boomgpu_unpin_host", "boomgpu_comm_unique_id", "boomgpu_comm_init", "boomgpu_comm_destroy", "boomgpu_allreduce", "boomgpu_kernel_launches",
     "boomgpu_get_timings",
     "boomgpu_upload_regression", "boomgpu_adopt_regression", "boomgpu_student_step", "boomgpu_student_step_device",
-    "boomgpu_student_draw", "boomgpu_student_loglike",
+    "boomgpu_student_draw", "boomgpu_student_loglike", "boomgpu_student_step_active",
 )
 
 
@@ -310,6 +310,18 @@ class Context:
         self._check(self._lib.boomgpu_student_step(self._h, _dp(beta), C.c_double(sigma), C.c_double(nu), C.c_uint64(seed),
                                                    C.c_uint64(iteration), _dp(xtwx), _dp(xtwy), _dp(sc)))
         return xtwx, xtwy, sc
+
+    def student_step_active(self, beta, sigma, nu, seed, iteration, active):
+        """(G p x k, diag, xtwy, scalars) for the column set `active` (p > 64), as logit_step_active."""
+        p = self.p
+        beta = _f64(beta)
+        act = np.ascontiguousarray(active, dtype=np.int32)
+        k = len(act)
+        G, diag, xty, sc = np.empty((p, k)), np.empty(p), np.empty(p), np.empty(4)
+        self._check(self._lib.boomgpu_student_step_active(self._h, _dp(beta), C.c_double(sigma), C.c_double(nu), C.c_uint64(seed),
+                                                          C.c_uint64(iteration), act.ctypes.data_as(c_i32_p), C.c_int(k), _dp(G), _dp(diag),
+                                                          _dp(xty), _dp(sc)))
+        return G, diag, xty, sc
 
     def student_step_device(self, beta, sigma, nu, seed, iteration, suf_dev_ptr):
         beta = _f64(beta)

@@ -1076,7 +1076,8 @@ int loglike_derivs_device_impl(boomgpu_ctx *ctx, int model, const double *beta, 
 // Runs f with the context looking at X_gamma (n x k) instead of X, then restores it.
 template <int MODEL>
 int step_active_impl(boomgpu_ctx *ctx, int model, const double *beta, int clt_threshold, uint64_t seed, uint64_t iteration,
-                            const int32_t *active, int k, double *G, double *diag, double *xty, double scalars[4]) {
+                            const int32_t *active, int k, double *G, double *diag, double *xty, double scalars[4],
+                            double t_sigma = 0.0, double t_nu = 0.0) {
   if (int rc = check_ready(ctx, model)) return rc;
   if (!beta || !active || k < 1 || !G || !diag || !xty) return fail(ctx, BOOMGPU_ERR_ARG, "null / empty argument");
   if (ctx->p <= 64) return fail(ctx, BOOMGPU_ERR_ARG, "the active-set step is for p > 64 (p = %d runs the single-pass kernel)", ctx->p);
@@ -1095,7 +1096,9 @@ int step_active_impl(boomgpu_ctx *ctx, int model, const double *beta, int clt_th
   RowOut out{nullptr, nullptr, nullptr, nullptr};
   const int path_save = ctx->path;
   ctx->path = 2; ctx->stats_mode = 1;
-  int rc = run_step<MODEL>(ctx, beta, make_prm(ctx, clt_threshold, seed, iteration), out, nullptr, nullptr, ctx->suf_dev);
+  DrawParams prm = make_prm(ctx, clt_threshold, seed, iteration);
+  if (MODEL == kStudentT) { prm.t_inv_sigma = 1.0 / t_sigma; prm.t_nu = t_nu; }
+  int rc = run_step<MODEL>(ctx, beta, prm, out, nullptr, nullptr, ctx->suf_dev);
   ctx->path = path_save; ctx->stats_mode = 0;
   if (rc) return rc;
   int ka8 = 0;
@@ -1832,6 +1835,14 @@ int boomgpu_student_step(boomgpu_ctx *ctx, const double *beta, double sigma, dou
   memcpy(xtwy, ctx->suf_pin + (size_t)p * p, sizeof(double) * p);
   if (scalars) memcpy(scalars, ctx->suf_pin + (size_t)p * p + p, sizeof(double) * 4);
   return 0;
+}
+
+// active-set form of the Student-t step (as boomgpu_logit_step_active): G = X'WX[:, active], the diagonal and X'Wy for the weights
+// drawn at (beta, sigma, nu); the weights stay on the device for boomgpu_weighted_column / boomgpu_full_statistics
+int boomgpu_student_step_active(boomgpu_ctx *ctx, const double *beta, double sigma, double nu, uint64_t seed, uint64_t iteration,
+                                const int32_t *active, int k, double *G, double *diag, double *xty, double scalars[4]) {
+  if (int rc = check_student(ctx, sigma, nu)) return rc;
+  return step_active_impl<kStudentT>(ctx, kStudentT, beta, 0, seed, iteration, active, k, G, diag, xty, scalars, sigma, nu);
 }
 
 int boomgpu_student_draw(boomgpu_ctx *ctx, const double *beta, double sigma, double nu, uint64_t seed, uint64_t iteration,

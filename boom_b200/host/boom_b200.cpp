@@ -1781,8 +1781,79 @@ const WeightedRegSuf &TRegressionSpikeSlabSampler::scaled_statistics() {
   scaled_.set_scalars(suf_.n(), suf_.yty() * inv, suf_.sumw(), suf_.sumlogw());
   return scaled_;
 }
+bool TRegressionSpikeSlabSampler::impute_latent_data_active(const std::vector<int> &cols_in) {
+  const int p = model_->xdim();
+  if (latent_data_is_fixed() || p <= 64 || model_->allreduce() || cols_in.size() > 128) return false;
+  std::vector<int> cols(cols_in);
+  if (cols.empty()) cols.push_back(0);
+  DeviceData &dev(model_->device_data());
+  const int k = (int)cols.size();
+  active_.cols = cols;
+  active_.G.resize((size_t)p * k); active_.diag.resize(p); active_.xty.resize(p);
+  std::vector<int32_t> c32(cols.begin(), cols.end());
+  uint64_t seed, it;
+  next_device_key(&seed, &it);
+  dev.check(boomgpu_student_step_active(dev.ctx(), model_->Beta().data(), model_->sigma(), model_->nu(), seed, it, c32.data(), k,
+                                        active_.G.data(), active_.diag.data(), active_.xty.data(), active_.scalars));
+  // the scalar statistics (n, y'Wy, sum w, sum log w) are complete in this form too: sigsq and nu | weights read them from suf_
+  suf_.set_scalars(active_.scalars[0], active_.scalars[1], active_.scalars[2], active_.scalars[3]);
+  active_.valid = true;
+  view_.reset();
+  return true;
+}
+// The spike-and-slab steps read the statistics divided by sigsq: the view holds scaled copies of the active arrays and scales
+// every column it fetches.  Rebuilt when sigsq has changed since it was made (it has not between the sweep and the beta draw).
+StatView &TRegressionSpikeSlabSampler::scaled_view() {
+  const double sigsq = model_->sigsq();
+  if (view_ && view_sigsq_ == sigsq) return *view_;
+  const int p = model_->xdim();
+  const double inv = 1.0 / sigsq;
+  Vector G(active_.G), diag(active_.diag);
+  for (double &v : G) v *= inv;
+  for (double &v : diag) v *= inv;
+  view_xty_ = active_.xty;
+  for (double &v : view_xty_) v *= inv;
+  DeviceData *dev = &model_->device_data();
+  ActiveSetState *st = &active_;
+  view_.reset(new StatView(p, active_.cols, G, diag, view_xty_, [dev, st, inv, p](int j, double *out) {
+    dev->check(boomgpu_weighted_column(dev->ctx(), j, out));
+    for (int i = 0; i < p; ++i) out[i] *= inv;
+    ++st->columns_fetched;
+  }));
+  view_sigsq_ = sigsq;
+  return *view_;
+}
+void TRegressionSpikeSlabSampler::materialize_full_statistics() const {
+  if (!active_.valid) return;
+  DeviceData &dev(model_->device_data());
+  const int p = model_->xdim();
+  WeightedRegSuf &suf(const_cast<WeightedRegSuf &>(suf_));
+  dev.check(boomgpu_full_statistics(dev.ctx(), suf.xtx_storage(p), suf.xty_storage()));
+  suf.set_scalars(active_.scalars[0], active_.scalars[1], active_.scalars[2], active_.scalars[3]);
+  active_.valid = false;
+}
+double TRegressionSpikeSlabSampler::weighted_sum_of_squared_errors() {
+  if (!active_.valid) return TRegressionSampler::weighted_sum_of_squared_errors();
+  // every included variable's column is in the view (the model's columns at the start of the iteration + the fetched adds)
+  StatView &v(scaled_view());
+  const double sigsq = view_sigsq_;
+  const Vector &b(model_->Beta());
+  const std::vector<int> inc(model_->coef().inc().included_positions());
+  double bxy = 0, bxxb = 0;
+  for (int i : inc) {
+    bxy += b[i] * active_.xty[i];
+    double s = 0;
+    for (int j : inc) s += v.at(i, j) * b[j];
+    bxxb += b[i] * s;
+  }
+  return active_.scalars[1] - 2 * bxy + bxxb * sigsq;
+}
 void TRegressionSpikeSlabSampler::draw() {
-  impute_latent_data();
+  if (!(active_.enabled && impute_latent_data_active(model_->coef().inc().included_positions()))) {
+    active_.valid = false;
+    view_.reset();
+    impute_latent_data();
+  }
   draw_model_indicators();
   draw_included_coefficients();
   draw_sigsq_full_conditional();
@@ -1792,16 +1863,24 @@ double TRegressionSpikeSlabSampler::logpri() const {
   return core_.logpri(model_->coef()) + nu_prior_->logp(model_->nu()) + siginv_prior_->logp(1.0 / model_->sigsq());
 }
 void TRegressionSpikeSlabSampler::draw_model_indicators() {
-  core_.draw_model_indicators(rng(), model_->coef(), scaled_statistics());
+  if (active_.valid) core_.draw_model_indicators(rng(), model_->coef(), scaled_view());
+  else core_.draw_model_indicators(rng(), model_->coef(), scaled_statistics());
   coefficients_changed();
 }
 void TRegressionSpikeSlabSampler::draw_included_coefficients() {
-  core_.draw_beta(rng(), model_->coef(), scaled_statistics());
+  if (active_.valid) core_.draw_beta(rng(), model_->coef(), scaled_view());
+  else core_.draw_beta(rng(), model_->coef(), scaled_statistics());
   coefficients_changed();
 }
-double TRegressionSpikeSlabSampler::log_model_prob(const Selector &g) { return core_.log_model_prob(g, scaled_statistics()); }
+double TRegressionSpikeSlabSampler::log_model_prob(const Selector &g) {
+  materialize_full_statistics();
+  return core_.log_model_prob(g, scaled_statistics());
+}
 
-void TRegressionSampler::draw_sigsq_full_conditional() {   // .cpp:165-171; SSE = y'Wy - 2 b'X'Wy + b'X'WXb (WeightedRegressionModel.cpp:89-95)
+void TRegressionSampler::draw_sigsq_full_conditional() {   // .cpp:165-171
+  model_->set_sigsq(sigsq_sampler_.draw(rng(), suf_.n(), weighted_sum_of_squared_errors()));
+}
+double TRegressionSampler::weighted_sum_of_squared_errors() {   // SSE = y'Wy - 2 b'X'Wy + b'X'WXb (WeightedRegressionModel.cpp:89-95)
   const int p = model_->xdim();
   const Vector &b(model_->Beta());
   double bxy = 0, bxxb = 0;
@@ -1812,8 +1891,7 @@ void TRegressionSampler::draw_sigsq_full_conditional() {   // .cpp:165-171; SSE 
     for (int j = 0; j < p; ++j) s += suf_.xtx()(i, j) * b[j];
     bxxb += b[i] * s;
   }
-  const double sse = suf_.yty() - 2 * bxy + bxxb;
-  model_->set_sigsq(sigsq_sampler_.draw(rng(), suf_.n(), sse));
+  return suf_.yty() - 2 * bxy + bxxb;
 }
 void TRegressionSampler::draw_nu_given_complete_data() { model_->set_nu(nu_complete_.draw(model_->nu())); }
 void TRegressionSampler::draw_nu_given_observed_data() {

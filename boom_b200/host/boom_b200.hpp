@@ -815,7 +815,7 @@ class TRegressionSampler : public PosteriorSampler {
   void draw_nu_given_complete_data();   // .cpp:173-176: from the weights' GammaSuf alone (ScaledChisqModel.cpp:52-82)
   void draw_nu_given_observed_data();
   void set_sigma_upper_limit(double max_sigma) { sigsq_sampler_.set_sigma_max(max_sigma); }
-  const WeightedRegSuf &complete_data_sufficient_statistics() const { return suf_; }
+  const WeightedRegSuf &complete_data_sufficient_statistics() const { materialize_full_statistics(); return suf_; }
   void fix_latent_data(bool fixed = true) { latent_data_fixed_ = fixed; }
   void clear_complete_data_sufficient_statistics() { suf_.clear(); }
   void update_complete_data_sufficient_statistics(double y, const Vector &x, double weight) { suf_.add_data(x, y, weight); }
@@ -825,6 +825,12 @@ class TRegressionSampler : public PosteriorSampler {
  protected:
   void on_seed() override;
   void coefficients_changed() { residuals_current_ = false; }
+  // sum_i w_i (y_i - x_i'beta)^2 from the statistics (WeightedRegressionModel.cpp:89-95); the spike-and-slab sampler answers
+  // from its active-set view when the last imputation ran in that form
+  virtual double weighted_sum_of_squared_errors();
+  virtual void materialize_full_statistics() const {}
+  bool latent_data_is_fixed() const { return latent_data_fixed_; }
+  void next_device_key(uint64_t *seed, uint64_t *iteration) { *seed = device_seed_; *iteration = iteration_++; }
   TRegressionModel *model_;
   std::shared_ptr<MvnBase> coefficient_prior_;
   std::shared_ptr<GammaModelBase> siginv_prior_;
@@ -855,11 +861,27 @@ class TRegressionSpikeSlabSampler : public TRegressionSampler {
   void allow_model_selection(bool allow) { core_.allow_model_selection(allow); }
   void limit_model_selection(int max_flips) { core_.limit_model_selection(max_flips); }
   double log_model_prob(const Selector &g);
+  // Active-set statistics, as on BinomialLogitSpikeSlabSampler (off by default; p > 64, no all-reduce hook): per iteration the
+  // device computes X'WX for the included columns + diagonal + X'Wy, the sweep fetches a column when it adds a variable; the
+  // same chain as with the full matrix.  complete_data_sufficient_statistics() still answers with the full matrix (on demand).
+  void set_active_set_statistics(bool tf) { active_.enabled = tf; }
+  bool active_set_statistics() const { return active_.enabled; }
+  int64_t active_set_columns_fetched() const { return active_.columns_fetched; }
+
+ protected:
+  double weighted_sum_of_squared_errors() override;
+  void materialize_full_statistics() const override;
 
  private:
   const WeightedRegSuf &scaled_statistics();   // X'WX / sigsq, X'Wy / sigsq at the model's current sigsq
+  bool impute_latent_data_active(const std::vector<int> &cols);
+  StatView &scaled_view();                      // the active-set arrays divided by the model's current sigsq
   SpikeSlabCore core_;
   WeightedRegSuf scaled_;
+  mutable ActiveSetState active_;
+  std::unique_ptr<StatView> view_;
+  Vector view_xty_;
+  double view_sigsq_ = 0.0;
 };
 
 // The logit mixture every BinomialLogit sampler uploads; defaults to the 9-component table of

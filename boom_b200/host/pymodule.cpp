@@ -332,6 +332,9 @@ PYBIND11_MODULE(_host, m) {
            py::arg("nu_prior"), py::arg("seeding_rng") = std::ref(GlobalRng::rng), py::keep_alive<1, 2>())
       .def("draw_model_indicators", &TRegressionSpikeSlabSampler::draw_model_indicators)
       .def("draw_included_coefficients", &TRegressionSpikeSlabSampler::draw_included_coefficients)
+      .def("set_active_set_statistics", &TRegressionSpikeSlabSampler::set_active_set_statistics)
+      .def_property_readonly("active_set_statistics", &TRegressionSpikeSlabSampler::active_set_statistics)
+      .def_property_readonly("active_set_columns_fetched", &TRegressionSpikeSlabSampler::active_set_columns_fetched)
       .def("allow_model_selection", &TRegressionSpikeSlabSampler::allow_model_selection)
       .def("limit_model_selection", &TRegressionSpikeSlabSampler::limit_model_selection)
       .def("log_model_prob", [](TRegressionSpikeSlabSampler &s, const std::vector<bool> &bits) {

@@ -155,6 +155,9 @@ int boomgpu_student_step(boomgpu_ctx *ctx, const double *beta, double sigma, dou
                          double *xtwx, double *xtwy, double scalars[4]);
 int boomgpu_student_step_device(boomgpu_ctx *ctx, const double *beta, double sigma, double nu, uint64_t seed, uint64_t iteration,
                                 double *suf_dev);
+/* active-set form, as boomgpu_logit_step_active below (p > 64): G = (X'WX)[:, active], diag, X'Wy; scalars as above */
+int boomgpu_student_step_active(boomgpu_ctx *ctx, const double *beta, double sigma, double nu, uint64_t seed, uint64_t iteration,
+                                const int32_t *active, int k, double *G, double *diag, double *xty, double scalars[4]);
 /* TRegressionModel::log_likelihood(beta, sigsq, nu) (Models/Glm/TRegression.cpp:74-86) = sum_i log dstudent(y_i; x_i'beta,
  * sigma, nu), all-reduced over the shards.  beta != NULL: one pass over X, the residuals stay on the device; beta == NULL:
  * the residuals of the previous call are reused (8 n bytes per evaluation): what the slice sampler on nu

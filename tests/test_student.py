@@ -389,3 +389,55 @@ def test_student_spike_slab_chain_matches_reference(golden):
     rm2, rs2 = np.array(g["spike_chain_sigma_nu_mean"]), np.array(g["spike_chain_sigma_nu_sd"])
     se2 = np.sqrt(rs2 ** 2 * 40.0 / n_ref + sn.std(0) ** 2 * 40.0 / len(sn))
     assert np.all(np.abs(sn.mean(0) - rm2) < 4 * se2 + 1e-4)
+
+
+@pytest.mark.gpu
+def test_student_active_set_matches_the_full_statistics():
+    """boomgpu_student_step_active: the columns of the active set, the diagonal and X'Wy of the SAME weights as the full step
+    (same seed / iteration), a further column on demand, the full matrix from the weights kept in HBM."""
+    n, p = 6000, 150
+    X, y, bt = O.synth_student(n, p, 5, 61)
+    ctx = _ctx(X, y)
+    xtwx, xtwy, sc = ctx.student_step(bt, 1.3, 4.5, 11, 3)
+    act = [0, 1, 2, 3, 4, 5, 77, 149]
+    G, diag, xty, sc2 = ctx.student_step_active(bt, 1.3, 4.5, 11, 3, act)
+    d = np.sqrt(np.diag(xtwx))
+    assert np.max(np.abs(G - xtwx[:, act]) / np.outer(d, d[act])) < 1e-12
+    np.testing.assert_allclose(diag, np.diag(xtwx), rtol=1e-12)
+    assert vec_err(xty, xtwy) < 1e-11
+    np.testing.assert_allclose(sc2, sc, rtol=1e-11)
+    col = ctx.weighted_column(33)
+    assert np.max(np.abs(col - xtwx[:, 33]) / (d * d[33])) < 1e-12
+    fxx, fxy = ctx.full_statistics()
+    assert normwise_err(fxx, xtwx) < 1e-12 and vec_err(fxy, xtwy) < 1e-11
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_student_active_set_chain_is_the_full_statistics_chain():
+    """TRegressionSpikeSlabSampler.set_active_set_statistics(True): the sweep, the coefficient draw and the sigma^2 draw read the
+    same numbers (up to the summation order of the two device kernels), so the chain is the chain of the full-matrix sampler."""
+    import boom_b200
+    n, p = 8000, 140
+    X, y, _ = O.synth_student(n, p, 6, 62)
+
+    def chain(active, iters=25):
+        model = boom_b200.TRegressionModel(X, y)
+        model.drop_all(); model.add(0)
+        s = boom_b200.TRegressionSpikeSlabSampler(model, boom_b200.MvnModel(np.zeros(p), 4.0 * np.eye(p)),
+                                                  boom_b200.VariableSelectionPrior(p, 0.05), boom_b200.ChisqModel(1.0, 1.0),
+                                                  boom_b200.UniformModel(0.5, 60.0), boom_b200.RNG(9))
+        s.set_active_set_statistics(active)
+        model.set_method(s)
+        out = []
+        for _ in range(iters):
+            model.sample_posterior()
+            out.append(np.r_[model.Beta, model.sigsq, model.nu])
+        return np.array(out), s, model
+    full, _, _ = chain(False)
+    act, s, model = chain(True)
+    assert np.array_equal(full[:, :p] != 0, act[:, :p] != 0)            # the same models, iteration by iteration
+    np.testing.assert_allclose(act, full, rtol=1e-7, atol=1e-9)
+    assert s.active_set_columns_fetched >= 5                             # the true variables entered through fetched columns
+    suf = s.complete_data_sufficient_statistics                          # the full matrix on demand, from the weights in HBM
+    assert suf.n == n and np.all(np.isfinite(suf.xtx)) and suf.xtx[0, 0] == pytest.approx(suf.sumw, rel=1e-12)
