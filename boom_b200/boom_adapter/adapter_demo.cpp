@@ -4,7 +4,7 @@
 // then attaches EITHER the reference sampler OR the B200 sampler with model->set_method(sampler) and calls
 // model->sample_posterior().  Prints one JSON line with the posterior summaries of both chains on the same
 // data; tests/test_gpu_adapter.py compares them within Monte Carlo error.
-//   usage: boom_adapter_demo <logit|spike|poisson|pspike|mode|pmode|fixed|pfixed|bench|api|composite|chunk|probit|treg|tspike|active|pactive> n p nonzero iters burn
+//   usage: boom_adapter_demo <logit|spike|poisson|pspike|mode|pmode|fixed|pfixed|bench|api|composite|chunk|probit|treg|tspike|tactive|active|pactive> n p nonzero iters burn
 //          (mode / pmode: find_posterior_mode; fixed / pfixed: externally driven statistics, host steps only, no GPU;
 //           bench: ms per iteration of the adapter beside the standalone classes; api: the public surface beyond draw())
 #include <chrono>
@@ -273,6 +273,45 @@ int main(int argc, char **argv) {
       print_summary("reference", out[0]); printf(", ");
       print_summary("b200", out[1]);
       printf("}\n");
+      return 0;
+    }
+    if (kind == "tactive") {
+      // the active-set option on B200::TRegressionSpikeSlabSampler: same seed, full statistics vs active-set statistics
+      std::vector<Vector> chain[2];
+      long long fetched = 0;
+      double xtx_diff = 0;
+      SpdMatrix full_last;
+      std::vector<double> yt(n);
+      for (int i = 0; i < n; ++i) yt[i] = xs[i].dot(beta) + 1.5 * rnorm() / std::sqrt(rgamma(2.0, 2.0));
+      NEW(MvnModel, tslab)(Vector(p, 0.0), SpdMatrix(p, 4.0));
+      NEW(ChisqModel, siginv_prior)(1.0, 1.0);
+      NEW(UniformModel, nu_prior)(0.5, 60.0);
+      for (int arm = 0; arm < 2; ++arm) {
+        RNG seeder(81);
+        NEW(TRegressionModel, model)(p);
+        for (int i = 0; i < n; ++i) model->add_data(new RegressionData(yt[i], xs[i]));
+        model->coef().drop_all(); model->coef().add(0);
+        Ptr<B200::TRegressionSpikeSlabSampler> s(new B200::TRegressionSpikeSlabSampler(model.get(), tslab, spike, siginv_prior, nu_prior, seeder));
+        s->set_active_set_statistics(arm == 1);
+        model->set_method(s);
+        for (int it = 0; it < iters; ++it) {
+          model->sample_posterior();
+          chain[arm].push_back(concat(model->Beta(), Vector{model->sigsq(), model->nu()}));
+        }
+        if (arm == 0) full_last = s->complete_data_sufficient_statistics().xtx();
+        else {
+          fetched = s->active_set_columns_fetched();
+          xtx_diff = (s->complete_data_sufficient_statistics().xtx() - full_last).max_abs() / full_last.max_abs();
+        }
+      }
+      double dmax = 0; bool same_model = true;
+      for (int it = 0; it < iters; ++it)
+        for (int j = 0; j < p + 2; ++j) {
+          dmax = std::max(dmax, std::fabs(chain[0][it][j] - chain[1][it][j]));
+          if (j < p) same_model = same_model && ((chain[0][it][j] != 0) == (chain[1][it][j] != 0));
+        }
+      printf("{\"kind\": \"tactive\", \"n\": %d, \"p\": %d, \"iters\": %d, \"chain_max_abs_diff\": %.3g, \"same_model\": %s, "
+             "\"columns_fetched\": %lld, \"suf_xtx_rel_diff\": %.3g}\n", n, p, iters, dmax, same_model ? "true" : "false", fetched, xtx_diff);
       return 0;
     }
     if (kind == "tspike") {

@@ -843,6 +843,10 @@ int TRegressionSampler::device_step_sync(boomgpu_ctx *ctx, const double *beta, u
                                          double *xty, double scalars[4]) {
   return boomgpu_student_step(ctx, beta, model_->sigma(), model_->nu(), seed, iteration, xtx, xty, scalars);
 }
+int TRegressionSampler::device_step_active(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, const int32_t *cols,
+                                           int k, double *G, double *diag, double *xty, double scalars[4]) {
+  return boomgpu_student_step_active(ctx, beta, model_->sigma(), model_->nu(), seed, iteration, cols, k, G, diag, xty, scalars);
+}
 int TRegressionSampler::device_loglike_derivs(boomgpu_ctx *, const double *, double *, double *, double *) {
   report_error("derivatives of the Student-t log likelihood are not provided (TRegression.cpp:118-121)");
   return 1;
@@ -871,6 +875,7 @@ double TRegressionSampler::logpri() const {   // .cpp:121-126
 }
 
 const WeightedRegSuf &TRegressionSampler::complete_data_sufficient_statistics() const {
+  materialize_full_statistics();
   if (!suf_synced_) {
     const int p = xdim_;
     SpdMatrix xtx(p);
@@ -905,6 +910,9 @@ void TRegressionSampler::draw_beta_full_conditional() {
 }
 // .cpp:165-171 with WeightedRegSuf::weighted_sum_of_squared_errors (WeightedRegressionModel.cpp:89-95) on the landed statistics
 void TRegressionSampler::draw_sigsq_full_conditional() {
+  model_->set_sigsq(sigsq_sampler_.draw(rng(), hsuf_.n(), weighted_sum_of_squared_errors()));
+}
+double TRegressionSampler::weighted_sum_of_squared_errors() {
   const int p = xdim_;
   const Vector &b(model_->Beta());
   const std::vector<double> &a(hsuf_.xtx().a);
@@ -916,7 +924,7 @@ void TRegressionSampler::draw_sigsq_full_conditional() {
     for (int j = 0; j < p; ++j) s += a[(size_t)i * p + j] * b[j];
     bxxb += b[i] * s;
   }
-  model_->set_sigsq(sigsq_sampler_.draw(rng(), hsuf_.n(), hsuf_.yty() - 2 * bxy + bxxb));
+  return hsuf_.yty() - 2 * bxy + bxxb;
 }
 void TRegressionSampler::draw_nu_given_complete_data() {   // .cpp:173-176: the weights' GammaSuf = (n, sum w, sum log w)
   weight_model_->suf()->set(hsuf_.sumw(), hsuf_.sumlogw(), hsuf_.n());
@@ -963,8 +971,51 @@ const BOOM_B200::WeightedRegSuf &TRegressionSpikeSlabSampler::scaled_statistics(
   scaled_.set_scalars(hsuf_.n(), hsuf_.yty() * inv, hsuf_.sumw(), hsuf_.sumlogw());
   return scaled_;
 }
+// the active-set arrays of this iteration divided by the model's current sigsq, every fetched column scaled alike
+BOOM_B200::StatView &TRegressionSpikeSlabSampler::scaled_view() {
+  const double sigsq = model_->sigsq();
+  if (tview_ && tview_sigsq_ == sigsq && tview_iteration_ == device_iteration()) return *tview_;
+  const int p = xdim_;
+  const double inv = 1.0 / sigsq;
+  BOOM_B200::Vector G(active_.G), diag(active_.diag);
+  for (double &v : G) v *= inv;
+  for (double &v : diag) v *= inv;
+  tview_xty_ = active_.xty;
+  for (double &v : tview_xty_) v *= inv;
+  boomgpu_ctx *ctx = device_ctx();
+  BOOM_B200::ActiveSetState *st = &active_;
+  tview_.reset(new BOOM_B200::StatView(p, active_.cols, G, diag, tview_xty_, [this, ctx, st, inv, p](int j, double *out) {
+    check(boomgpu_weighted_column(ctx, j, out));
+    for (int i = 0; i < p; ++i) out[i] *= inv;
+    ++st->columns_fetched;
+  }));
+  tview_sigsq_ = sigsq;
+  tview_iteration_ = device_iteration();
+  return *tview_;
+}
+double TRegressionSpikeSlabSampler::weighted_sum_of_squared_errors() {
+  if (!active_.valid) return TRegressionSampler::weighted_sum_of_squared_errors();
+  BOOM_B200::StatView &v(scaled_view());
+  const double sigsq = tview_sigsq_;
+  const Vector &b(model_->Beta());
+  const Selector &inc(model_->coef().inc());
+  double bxy = 0, bxxb = 0;
+  for (int a = 0; a < (int)inc.nvars(); ++a) {
+    const int i = inc.indx(a);
+    bxy += b[i] * active_.xty[i];
+    double s = 0;
+    for (int c = 0; c < (int)inc.nvars(); ++c) { const int j = inc.indx(c); s += v.at(i, j) * b[j]; }
+    bxxb += b[i] * s;
+  }
+  return active_.scalars[1] - 2 * bxy + bxxb * sigsq;
+}
 void TRegressionSpikeSlabSampler::draw() {   // TRegressionSpikeSlabSampler.cpp:41-47
-  impute_latent_data();
+  if (impute_latent_data_active(model_->coef().inc())) {
+    // n, y'Wy, sum w, sum log w are complete in this form too: the sigsq draw and nu | weights read them from hsuf_
+    hsuf_.set_scalars(active_.scalars[0], active_.scalars[1], active_.scalars[2], active_.scalars[3]);
+  } else {
+    impute_latent_data();
+  }
   draw_model_indicators();
   draw_included_coefficients();
   draw_sigsq_full_conditional();
@@ -981,14 +1032,16 @@ void TRegressionSpikeSlabSampler::draw_model_indicators() {
   c.limit_model_selection(max_flips_);
   BOOM_B200::GlmCoefs h = host_coefs(model_->coef(), xdim_, true);
   BOOM_B200::RNG local(rng().generator()());
-  c.draw_model_indicators(local, h, scaled_statistics());
+  if (active_.valid) c.draw_model_indicators(local, h, scaled_view());
+  else c.draw_model_indicators(local, h, scaled_statistics());
   write_back(model_->coef(), h, xdim_, false);
   coefficients_changed();
 }
 void TRegressionSpikeSlabSampler::draw_included_coefficients() {
   BOOM_B200::GlmCoefs h = host_coefs(model_->coef(), xdim_, false);
   BOOM_B200::RNG local(rng().generator()());
-  core(coefficient_prior_, spike_, true).draw_beta(local, h, scaled_statistics());
+  if (active_.valid) core(coefficient_prior_, spike_, true).draw_beta(local, h, scaled_view());
+  else core(coefficient_prior_, spike_, true).draw_beta(local, h, scaled_statistics());
   write_back(model_->coef(), h, xdim_, true);
   coefficients_changed();
 }

@@ -125,6 +125,7 @@ class DeviceImputerBase : public PosteriorSampler {
   bool find_mode(GlmCoefs &coef, const Ptr<MvnBase> &slab, const Ptr<VariableSelectionPrior> &spike, double epsilon, double *value);
   void mark_stale() { stale_ = true; }
   boomgpu_ctx *device_ctx() { return ctx_; }   // valid after ensure_device_rows()
+  uint64_t device_iteration() const { return iteration_; }
   void check(int rc) const;
   virtual void statistics_changed() {}   // the reference-typed views are out of date
   // host steps on hsuf_
@@ -378,6 +379,8 @@ class TRegressionSampler : public DeviceImputerBase {
   int device_step(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *suf_dev) override;
   int device_step_sync(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, double *xtx, double *xty,
                        double scalars[4]) override;
+  int device_step_active(boomgpu_ctx *ctx, const double *beta, uint64_t seed, uint64_t iteration, const int32_t *cols, int k,
+                         double *G, double *diag, double *xty, double scalars[4]) override;
   int device_loglike_derivs(boomgpu_ctx *, const double *, double *, double *, double *) override;
   int device_loglike_derivs_device(boomgpu_ctx *, const double *, double *) override;
   int device_loglike_derivs_selected(boomgpu_ctx *, const double *, double *, double *, double *) override;
@@ -385,6 +388,7 @@ class TRegressionSampler : public DeviceImputerBase {
   const Vector &current_beta() const override { return model_->Beta(); }
   void statistics_changed() override { suf_synced_ = false; }
   void coefficients_changed() { residuals_current_ = false; }
+  virtual double weighted_sum_of_squared_errors();   // from hsuf_; the spike-and-slab sampler answers from its active-set view
   TRegressionModel *model_;
   Ptr<MvnBase> coefficient_prior_;
   Ptr<GammaModelBase> siginv_prior_;
@@ -414,11 +418,20 @@ class TRegressionSpikeSlabSampler : public TRegressionSampler {
   void draw_included_coefficients();
   void allow_model_selection(bool allow) { allow_model_selection_ = allow; }
   void limit_model_selection(int max_flips) { max_flips_ = max_flips; }
+  // set_active_set_statistics(true) (DeviceImputerBase) applies here too: the view then carries the statistics divided by sigsq
+
+ protected:
+  double weighted_sum_of_squared_errors() override;
 
  private:
   const BOOM_B200::WeightedRegSuf &scaled_statistics();   // X'WX / sigsq, X'Wy / sigsq (SpikeSlabSampler.cpp:131-134,188-193)
+  BOOM_B200::StatView &scaled_view();
   Ptr<VariableSelectionPrior> spike_;
   BOOM_B200::WeightedRegSuf scaled_;
+  std::unique_ptr<BOOM_B200::StatView> tview_;
+  BOOM_B200::Vector tview_xty_;
+  double tview_sigsq_ = 0.0;
+  uint64_t tview_iteration_ = ~0ull;
   bool allow_model_selection_ = true;
   int max_flips_ = -1;
 };

@@ -177,3 +177,16 @@ def test_student_t_spike_slab_on_boom_models():
     s0, s1 = np.array(r["reference_sigma_nu_sd"]), np.array(r["b200_sigma_nu_sd"])
     se = np.sqrt((s0 ** 2 + s1 ** 2) * 40.0 / (iters - burn))
     assert np.all(np.abs(m0 - m1) < 4 * se + 1e-3), (m0, m1, se)
+
+
+def test_active_set_option_on_the_student_t_adapter():
+    """set_active_set_statistics(true) on B200::TRegressionSpikeSlabSampler: the same chain of (beta, sigsq, nu) as with the full
+    statistics (same seed), columns fetched when the sweep adds a variable, complete_data_sufficient_statistics() still the full
+    matrix."""
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/boom_adapter_demo not built")
+    out = subprocess.run([EXE, "tactive", "12000", "120", "5", "25", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["same_model"] is True and r["chain_max_abs_diff"] < 1e-6
+    assert r["columns_fetched"] >= 5 and r["suf_xtx_rel_diff"] < 1e-9
