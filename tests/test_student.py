@@ -207,6 +207,37 @@ def test_spike_slab_steps_see_the_statistics_scaled_by_sigsq():
     assert np.array_equal(before, model.inc)
 
 
+def test_error_behaviour_of_the_student_t_host_classes():
+    """report_error -> RuntimeError, as in the reference: dimension mismatches at construction, invalid parameters, a slice sampler
+    started where the target is -inf (ScalarSliceSampler.cpp:check_finite)."""
+    import boom_b200
+    H = boom_b200.host()
+    p = 3
+    model = boom_b200.TRegressionModel(p)
+    good = (boom_b200.MvnModel(np.zeros(p), np.eye(p)), boom_b200.GammaModel(1.0, 1.0), boom_b200.UniformModel(0.5, 60.0))
+    with pytest.raises(RuntimeError):
+        boom_b200.TRegressionSampler(model, boom_b200.MvnModel(np.zeros(p + 1), np.eye(p + 1)), good[1], good[2], boom_b200.RNG(1))
+    with pytest.raises(RuntimeError):
+        boom_b200.TRegressionSpikeSlabSampler(model, good[0], boom_b200.VariableSelectionPrior(p + 2, 0.5), good[1], good[2], boom_b200.RNG(1))
+    for bad in (lambda: model.set_sigsq(0.0), lambda: model.set_nu(-1.0), lambda: model.add_data(1.0, np.zeros(p + 1)),
+                lambda: boom_b200.GammaModel(0.0, 1.0), lambda: boom_b200.UniformModel(2.0, 1.0)):
+        with pytest.raises(RuntimeError):
+            bad()
+    with pytest.raises(RuntimeError):                                  # the target is -inf at the starting point
+        H.slice_sample(lambda x: -np.inf if x < 1.0 else -x, 0.5, 3, lo=0.0, rng=boom_b200.RNG(2))
+    s = boom_b200.TRegressionSampler(model, *good, boom_b200.RNG(1))
+    with pytest.raises(RuntimeError):
+        s.set_sigma_upper_limit(-1.0)
+    u = boom_b200.UniformModel(0.5, 60.0)
+    assert u.logp(0.4) == -np.inf and u.logp(1.0) == pytest.approx(-np.log(59.5))
+    g = boom_b200.GammaModel(2.0, 3.0)
+    assert g.logp(-1.0) == -np.inf and g.logp(0.7) == pytest.approx(stats.gamma.logpdf(0.7, 2.0, scale=1 / 3.0))
+    # defaults of the model's parameters (TRegression.cpp:33-35) and their setters
+    assert model.sigsq == 1.0 and model.nu == 30.0
+    model.sigsq = 2.25; model.nu = 7.0
+    assert model.sigma == 1.5 and model.nu == 7.0
+
+
 # ------------------------------------------------------------------------------------------ GPU
 def _ctx(X, y, path=0):
     import boom_b200
