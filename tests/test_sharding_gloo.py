@@ -93,3 +93,49 @@ def test_two_rank_statistics_and_identical_chains():
     for pr in procs:
         pr.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def _student_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    from boom_b200.distributed import shard_range
+    from oracle import oracle as O
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        n, p = 2503, 6
+        X, y, bt = O.synth_student(n, p, 3, seed=12)
+        row0, row1 = shard_range(n, world, rank)
+        beta, sigma, nu = bt * 0.9, 1.4, 3.5
+        # the Student-t step's statistics [X'WX | X'Wy | n, y'Wy, sum w, sum log w] and the two pieces of the log likelihood
+        # (row part, n) are additive over the shards; the weights depend on the GLOBAL row only
+        xtwx, xtwy, sc, w = O.student_step(X[row0:row1], y[row0:row1], beta, sigma, nu, 31, 2, row_offset=row0)
+        full = O.student_step(X, y, beta, sigma, nu, 31, 2)
+        assert np.array_equal(w, full[3][row0:row1])
+        packed = torch.from_numpy(np.concatenate([xtwx.ravel(), xtwy, sc]))
+        dist.all_reduce(packed)
+        packed = packed.numpy()
+        d = np.sqrt(np.diag(full[0]))
+        assert np.max(np.abs(packed[:p * p].reshape(p, p) - full[0]) / np.outer(d, d)) < 1e-13
+        assert np.allclose(packed[p * p:p * p + p], full[1], rtol=1e-12, atol=1e-12)
+        assert np.allclose(packed[p * p + p:], full[2], rtol=1e-12)
+        ll = torch.tensor([O.student_loglike(X[row0:row1], y[row0:row1], beta, sigma, nu)], dtype=torch.float64)
+        dist.all_reduce(ll)
+        assert abs(ll.item() - O.student_loglike(X, y, beta, sigma, nu)) < 1e-9 * n
+        out.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        out.put((rank, "FAIL: %r" % (e,)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_student_t_statistics_and_likelihood():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_student_worker, args=(r, 2, port, out)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [out.get(timeout=240) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
